@@ -1,0 +1,230 @@
+/* cxxdes_b200.h -- C ABI of the B200 ensemble discrete-event engine.
+ *
+ * libcxxdes (the reference) is a header-only C++20 library with no plugin or
+ * FFI layer; its only boundary is the C++ API
+ *     CXXDES_SIMULATION(model) { coroutine<> co_main(); };  model.run();
+ * This header is the C-ABI a binding for that API's *batched* run path calls:
+ * plain pointers and sizes, no C++/torch types, no exceptions.  The C++ mirror
+ * of the reference vocabulary (ensemble<Model>::run / run_for / now / ...)
+ * lives in include/cxxdes_b200/ensemble.hpp and is a thin wrapper over these
+ * functions.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Threading: an ensemble handle is not thread-safe (like environment,
+ * include/cxxdes/core/impl/environment.ipp:9-10); different handles may be
+ * driven from different threads / processes (one per GPU).
+ */
+#ifndef CXXDES_B200_H_INCLUDED
+#define CXXDES_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (the reference throws std::runtime_error; see cxxdes_b200_last_error) ---- */
+enum {
+    CXXDES_B200_OK = 0,
+    CXXDES_B200_ERR_INVALID = 1,   /* bad argument / unsupported configuration            */
+    CXXDES_B200_ERR_CUDA = 2,      /* CUDA runtime failure (message in last_error)         */
+    CXXDES_B200_ERR_STATE = 3,     /* call not valid in this state (e.g. reconfigure after use,
+                                      environment.ipp:43-65 throws in the reference)       */
+    CXXDES_B200_ERR_CAPACITY = 4   /* a replication exceeded a device-side capacity; its
+                                      status word says which (never silent corruption)     */
+};
+
+/* ---- time units: cxxdes::time_utils::time_unit_type, include/cxxdes/misc/time.hpp:18-25 ---- */
+enum {
+    CXXDES_B200_SECONDS = 0,
+    CXXDES_B200_MILLISECONDS = 1,
+    CXXDES_B200_MICROSECONDS = 2,
+    CXXDES_B200_NANOSECONDS = 3,
+    CXXDES_B200_PICOSECONDS = 4
+};
+
+/* env.time_unit(x) / env.time_precision(x): environment.ipp:43-70.
+ * A time quantity is {t, u} exactly like cxxdes::core::time (misc/time.hpp:31-37). */
+typedef struct cxxdes_b200_clock {
+    int64_t unit_t;
+    int32_t unit_u;
+    int32_t precision_u;
+    int64_t precision_t;
+} cxxdes_b200_clock;
+
+/* ---- models (process bodies lowered to device state machines) ---- */
+enum {
+    CXXDES_B200_MODEL_MM1 = 1,     /* examples/producer_consumer.cpp:9-59                  */
+    CXXDES_B200_MODEL_ALOHA = 2,   /* examples/aloha.cpp:25-85                             */
+    CXXDES_B200_MODEL_MMC = 3,     /* resource + any_of balking (examples/resource.cpp pattern) */
+    CXXDES_B200_MODEL_ARCHSIM = 4  /* examples/basic_arch_sim.cpp:13-110                   */
+};
+
+/* producer_consumer_example(lambda, mu, n_packets): examples/producer_consumer.cpp:10-20 */
+typedef struct cxxdes_b200_mm1_params {
+    double lambda;
+    double mu;
+    uint64_t n_packets;
+} cxxdes_b200_mm1_params;
+
+/* aloha_config: examples/aloha.cpp:13-18; the per-replication offered-load sweep
+ * reproduces main() (examples/aloha.cpp:87-103): replication r uses step
+ * i = r % sweep_steps, lambda_i = begin + (end-begin)*i/(steps-1) in float,
+ * packets_per_station = size_t(lambda_i * packets_scale).  sweep_steps <= 1 keeps
+ * lambda_begin and packets_per_station for every replication. */
+typedef struct cxxdes_b200_aloha_params {
+    uint32_t num_stations;
+    uint32_t sweep_steps;
+    float lambda_begin;
+    float lambda_end;
+    float frame_time;
+    float packets_scale;
+    uint64_t packets_per_station;
+} cxxdes_b200_aloha_params;
+
+/* M/M/c with balking customers built from sync::resource, async and any_of
+ * (SURVEY Appendix E model; primitives include/cxxdes/sync/resource.hpp:37-100,
+ * core/impl/any_of.ipp, core/impl/async.ipp). */
+typedef struct cxxdes_b200_mmc_params {
+    double lambda;
+    double mu;
+    double patience;
+    uint32_t servers;
+    uint32_t reserved;
+    uint64_t n_customers;
+} cxxdes_b200_mmc_params;
+
+/* memory-hierarchy model, examples/basic_arch_sim.cpp:83-109: mem2{latency, capacity}
+ * backed by mem1{latency}; n_loads addresses drawn as philox % addr_space,
+ * n_requesters processes share the hierarchy. */
+typedef struct cxxdes_b200_archsim_params {
+    int64_t l2_latency;
+    int64_t l1_latency;
+    uint32_t l2_capacity;
+    uint32_t addr_space;
+    uint32_t n_requesters;
+    uint32_t reserved;
+    uint64_t n_loads;
+} cxxdes_b200_archsim_params;
+
+/* ---- per-replication results, structure of arrays (one entry per replication) ----
+ * Any pointer may be NULL (column not wanted).  f64/i64 columns are model outputs:
+ *   MM1    f64[0]=avg_latency f64[1]=total_latency            (producer_consumer.cpp:24,29,45-52)
+ *          i64[0]=packets consumed i64[1]=max queue length
+ *   ALOHA  f64[0]=S (float widened) f64[1]=G (float widened)  (aloha.cpp:46-47)
+ *          i64[0]=successful_transmissions i64[1]=packets_per_station
+ *   MMC    f64[0]=total_wait  i64[0]=served i64[1]=balked
+ *   ARCH   f64[0]=sum of load latencies (ticks)  i64[0]=hits i64[1]=misses
+ */
+#define CXXDES_B200_N_F64 2
+#define CXXDES_B200_N_I64 2
+typedef struct cxxdes_b200_columns {
+    int64_t *end_time;    /* env.now() after the run: environment.ipp:24-26           */
+    uint64_t *n_events;   /* number of environment::step() calls that returned true   */
+    uint64_t *trace_hash; /* digest of every popped token (shared/trace_hash.hpp)     */
+    uint32_t *status;     /* 0 = ok, else CXXDES_B200_REP_* bits                      */
+    double *f64[CXXDES_B200_N_F64];
+    int64_t *i64[CXXDES_B200_N_I64];
+} cxxdes_b200_columns;
+
+enum {
+    CXXDES_B200_REP_QUEUE_OVERFLOW = 1u,  /* sync::queue ring capacity exceeded   */
+    CXXDES_B200_REP_HEAP_OVERFLOW = 2u,   /* event heap capacity exceeded         */
+    CXXDES_B200_REP_WAITER_OVERFLOW = 4u, /* sync::event waiter list exceeded     */
+    CXXDES_B200_REP_TIME_RANGE = 8u,      /* tick value outside the packed range  */
+    CXXDES_B200_REP_UNFINISHED = 16u      /* run_until stopped before the end     */
+};
+
+/* ---- ensemble accumulators (what the final all-reduce sums) ---- */
+typedef struct cxxdes_b200_accumulators {
+    uint64_t n_replications;
+    uint64_t n_events;
+    uint64_t n_errors;
+    uint64_t trace_hash_sum; /* wrapping sum of per-replication digests ("checksum of checksums") */
+    int64_t end_time_sum;
+    int64_t i64_sum[CXXDES_B200_N_I64];
+    double f64_sum[CXXDES_B200_N_F64];
+    double f64_sumsq[CXXDES_B200_N_F64];
+} cxxdes_b200_accumulators;
+
+typedef struct cxxdes_b200_ensemble cxxdes_b200_ensemble; /* opaque */
+
+typedef struct cxxdes_b200_config {
+    int32_t model;               /* CXXDES_B200_MODEL_*                                     */
+    int32_t device;              /* CUDA device ordinal                                     */
+    uint64_t seed;
+    uint64_t first_replication;  /* global id of replication 0 of this shard (multi-GPU)    */
+    uint64_t n_replications;
+    cxxdes_b200_clock clock;
+    const void *params;          /* cxxdes_b200_<model>_params                              */
+    size_t params_size;
+    void *stream;                /* cudaStream_t to launch on, NULL = a stream owned by the handle */
+    uint32_t flags;              /* CXXDES_B200_FLAG_*                                      */
+    uint32_t queue_capacity;     /* 0 = default; ring entries per replication               */
+} cxxdes_b200_config;
+
+enum {
+    CXXDES_B200_FLAG_GENERIC_ENGINE = 1u /* use the generic token-heap engine kernel even when a
+                                            fused model kernel exists (parity cross-check)    */
+};
+
+/* Number of CUDA devices visible (0 and an error string when there is none). */
+int cxxdes_b200_device_count(int *count);
+
+/* Construct an ensemble of `n_replications` independent simulations of one model:
+ * replaces constructing one CXXDES_SIMULATION object per replication
+ * (core/simulation.hpp:31-85) plus env.time_unit()/time_precision()
+ * (environment.ipp:43-70).  Copies `params` to the device. */
+int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out);
+
+/* simulation::run() for every replication: bind co_main once, then
+ * `while (step());` (core/simulation.hpp:51-54,76-81; environment.ipp:117-146,179-182).
+ * Asynchronous on the handle's stream. */
+int cxxdes_b200_run(cxxdes_b200_ensemble *e);
+
+/* environment::run_until(t) / run_for(dt) in ticks for every replication
+ * (environment.ipp:190-214); state stays resident on the device between calls. */
+int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t);
+int cxxdes_b200_run_for(cxxdes_b200_ensemble *e, int64_t dt);
+
+/* Block until everything launched on the handle's stream has finished. */
+int cxxdes_b200_sync(cxxdes_b200_ensemble *e);
+
+/* Copy per-replication results to HOST arrays (sim.now(), model statistics:
+ * core/simulation.hpp:33-45).  Implies a sync.  Returns CXXDES_B200_ERR_CAPACITY
+ * if any replication reported a non-zero status. */
+int cxxdes_b200_fetch(cxxdes_b200_ensemble *e, const cxxdes_b200_columns *host_columns);
+
+/* DEVICE pointers of the result columns (for device-side consumers / NCCL). */
+int cxxdes_b200_device_columns(cxxdes_b200_ensemble *e, cxxdes_b200_columns *device_columns);
+
+/* Reduce the per-replication columns of this shard on the device and return
+ * the accumulators (host copy) and, optionally, the device address of the
+ * accumulator struct so the caller's collective (ncclAllReduce over NVLink)
+ * can sum shards without a host round trip. */
+int cxxdes_b200_reduce(cxxdes_b200_ensemble *e, cxxdes_b200_accumulators *host_out,
+                       void **device_accumulators);
+
+/* Device time of the most recent run/run_until launch in milliseconds (CUDA
+ * events recorded on the launching stream), and how many kernels this library
+ * launched on the handle so far. */
+int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms);
+int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
+
+/* environment::reset() (environment.ipp:154-176) + rebind: replications start over. */
+int cxxdes_b200_reset(cxxdes_b200_ensemble *e);
+
+int cxxdes_b200_destroy(cxxdes_b200_ensemble *e);
+
+/* Message of the last error on the calling thread (the reference reports these
+ * conditions by throwing std::runtime_error; the C++ wrapper rethrows). */
+const char *cxxdes_b200_last_error(void);
+
+/* Library/ABI version and the SM architecture the kernels were built for. */
+int cxxdes_b200_version(int *abi_version, int *sm_arch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CXXDES_B200_H_INCLUDED */

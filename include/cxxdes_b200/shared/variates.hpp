@@ -1,0 +1,160 @@
+// cxxdes_b200/shared/variates.hpp -- bit-reproducible variates and time conversion.
+//
+// Everything here is built from IEEE-754 binary64 +, -, *, correctly rounded
+// fma and integer operations only, so g++ (-ffp-contract=off) and nvcc
+// (-fmad=false) produce identical bits.  No libm: glibc's log and CUDA's log
+// differ in the last place now and then, and after `* 1000` and truncation
+// (environment::real_to_sim, environment.ipp:79-82) that would flip a tick.
+//
+// Reference arithmetic restated here:
+//   * exponential variate  -log(1 - u) / lambda
+//       libstdc++ std::exponential_distribution::operator(), bits/random.h:4900-4905,
+//       called from examples/random_variable.hpp:24-26 (producer_consumer.cpp:34,50; aloha.cpp:52,68)
+//   * env.timeout(x) -> ticks = (int64)(x * F), F = unit.count(precision)
+//       timeout.ipp:184-187, environment.ipp:79-82, misc/time.hpp:75-86,146-148
+//   * now_seconds() = (double)(now * prec.t) * conv[prec.u]
+//       environment.ipp:29-36, misc/time.hpp:120-125
+#pragma once
+#include <stdint.h>
+#include "philox.hpp"
+#include "log_table.inc"
+
+namespace cxxdes_b200 {
+
+struct log_entry {
+    uint64_t invc_bits;
+    uint64_t logc_bits;
+};
+
+// Host copy of the table; device kernels stage the same rows into shared memory.
+static const log_entry LOG_TABLE_HOST[1 << CXB_LOG_TABLE_BITS] = {CXB_LOG_TABLE_ROWS};
+
+CXB_HD double bits_as_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    __builtin_memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+CXB_HD uint64_t double_as_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    __builtin_memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+
+CXB_HD double fma_rn(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+// w = 1 - u with u = (top 52 bits) * 2^-52 in [0, 1); w is in (0, 1], never 0,
+// so log(w) is finite.  Built as 2 - [1,2) to avoid an int->double conversion.
+CXB_HD double unit_complement_from_bits(uint64_t bits) {
+    double one_plus_u = bits_as_double(0x3FF0000000000000ULL | (bits >> 12));
+    return 2.0 - one_plus_u;
+}
+
+// Natural logarithm for positive normal doubles (the engine only ever passes
+// w in [2^-52, 1]).  Table-driven: w = 2^k * z, z in [0.6875, 1.375),
+// r = z*invc - 1 (|r| < 2^-8), log(w) = k ln2 + logc + log1p(r), log1p by its
+// Taylor series through r^7.  Measured against mpmath: < 1 ulp for w <= 0.68,
+// absolute error < 2^-56 on (0.68, 1] (tests/test_shared_math.py).
+template <typename Table>
+CXB_HD double log_pos(double w, const Table *table) {
+    const uint64_t ix = double_as_bits(w);
+    const uint64_t tmp = ix - CXB_LOG_OFF;
+    const int i = (int)((tmp >> (52 - CXB_LOG_TABLE_BITS)) & ((1 << CXB_LOG_TABLE_BITS) - 1));
+    const int k = (int)((int64_t)tmp >> 52);
+    const uint64_t iz = ix - (tmp & 0xFFF0000000000000ULL);
+    const double z = bits_as_double(iz);
+    const double invc = bits_as_double(table[i].invc_bits);
+    const double logc = bits_as_double(table[i].logc_bits);
+    const double r = fma_rn(z, invc, -1.0);
+    const double kd = (double)k;
+    const double t = fma_rn(kd, bits_as_double(CXB_LN2_HI_BITS), logc);
+    const double hi = t + r;
+    const double lo = (t - hi) + r;
+    const double r2 = r * r;
+    // log1p(r) - r = r^2 * (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7)
+    double p = fma_rn(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma_rn(r, p, 1.0 / 5.0);
+    p = fma_rn(r, p, -1.0 / 4.0);
+    p = fma_rn(r, p, 1.0 / 3.0);
+    p = fma_rn(r, p, -0.5);
+    const double tail = fma_rn(kd, bits_as_double(CXB_LN2_LO_BITS), r2 * p);
+    return hi + (lo + tail);
+}
+
+// x / d for a divisor that is reused many times: q0 = x * (1/d), one fma
+// residual, one fma correction (Markstein).  With inv = RN(1/d) this returns
+// the correctly rounded quotient, i.e. the same bits as IEEE `x / d`
+// (checked on 10^7 random pairs in tests/test_shared_math.py).
+struct divisor {
+    double d;
+    double inv;
+};
+
+CXB_HD divisor make_divisor(double d) {
+    divisor v;
+    v.d = d;
+    v.inv = 1.0 / d;
+    return v;
+}
+
+CXB_HD double divide(double x, const divisor &v) {
+    const double q0 = x * v.inv;
+    const double rem = fma_rn(-q0, v.d, x);
+    return fma_rn(rem, v.inv, q0);
+}
+
+// -log(w) / lambda, w = 1 - u.
+template <typename Table>
+CXB_HD double exponential_from_bits(uint64_t bits, const divisor &lambda, const Table *table) {
+    const double w = unit_complement_from_bits(bits);
+    const double neg_log = -log_pos(w, table);
+    return divide(neg_log, lambda);
+}
+
+// One exponential variate = draw number `draw` of the addressed stream.
+template <typename Table>
+CXB_HD double exponential(const stream_addr &a, uint64_t draw, const divisor &lambda,
+                          const Table *table) {
+    return exponential_from_bits(stream_draw_bits(a, draw), lambda, table);
+}
+
+// Simulation clock configuration folded to two numbers.
+//   ticks_per_unit   = time_unit().count(time_precision())        (misc/time.hpp:75-86)
+//   seconds_per_tick = conv[precision.u], tick_mult = precision.t (misc/time.hpp:120-125)
+struct clock_config {
+    int64_t ticks_per_unit;
+    int64_t tick_mult;
+    double seconds_per_tick_unit;
+};
+
+// environment::real_to_sim(double): double * intmax_t -> double, then
+// conversion to time_integral truncates toward zero.
+CXB_HD int64_t real_to_sim(double x, const clock_config &c) {
+    return (int64_t)(x * (double)c.ticks_per_unit);
+}
+
+// environment::real_to_sim(float): float * intmax_t -> float (aloha frame_time).
+CXB_HD int64_t real_to_sim_f32(float x, const clock_config &c) {
+    return (int64_t)(x * (float)c.ticks_per_unit);
+}
+
+// environment::now_seconds().
+CXB_HD double sim_to_seconds(int64_t now, const clock_config &c) {
+    return (double)(now * c.tick_mult) * c.seconds_per_tick_unit;
+}
+
+}  // namespace cxxdes_b200

@@ -1,0 +1,111 @@
+"""ctypes mirror of include/cxxdes_b200.h (the C ABI of the ensemble engine).
+
+Only declarations live here: structures, enum values and a helper that gives
+numpy-backed result columns.  Nothing in this module computes anything.
+"""
+import ctypes as C
+
+import numpy as np
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY = 0, 1, 2, 3, 4
+SECONDS, MILLISECONDS, MICROSECONDS, NANOSECONDS, PICOSECONDS = range(5)
+MODEL_MM1, MODEL_ALOHA, MODEL_MMC, MODEL_ARCHSIM = 1, 2, 3, 4
+N_F64 = 2
+N_I64 = 2
+REP_QUEUE_OVERFLOW, REP_HEAP_OVERFLOW, REP_WAITER_OVERFLOW, REP_TIME_RANGE, REP_UNFINISHED = (
+    1, 2, 4, 8, 16)
+FLAG_GENERIC_ENGINE = 1
+
+
+class Clock(C.Structure):
+    """cxxdes_b200_clock: env.time_unit(x) / env.time_precision(x), environment.ipp:43-70."""
+    _fields_ = [("unit_t", C.c_int64), ("unit_u", C.c_int32), ("precision_u", C.c_int32),
+                ("precision_t", C.c_int64)]
+
+    @classmethod
+    def of(cls, unit=(1, SECONDS), precision=(1, SECONDS)):
+        return cls(unit[0], unit[1], precision[1], precision[0])
+
+
+class MM1Params(C.Structure):
+    """producer_consumer_example(lambda, mu, n_packets), examples/producer_consumer.cpp:10-20."""
+    _fields_ = [("lambda_", C.c_double), ("mu", C.c_double), ("n_packets", C.c_uint64)]
+
+
+class AlohaParams(C.Structure):
+    """aloha_config + the offered-load sweep of main(), examples/aloha.cpp:13-18,87-103."""
+    _fields_ = [("num_stations", C.c_uint32), ("sweep_steps", C.c_uint32),
+                ("lambda_begin", C.c_float), ("lambda_end", C.c_float),
+                ("frame_time", C.c_float), ("packets_scale", C.c_float),
+                ("packets_per_station", C.c_uint64)]
+
+
+class MMCParams(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("mu", C.c_double), ("patience", C.c_double),
+                ("servers", C.c_uint32), ("reserved", C.c_uint32), ("n_customers", C.c_uint64)]
+
+
+class ArchSimParams(C.Structure):
+    _fields_ = [("l2_latency", C.c_int64), ("l1_latency", C.c_int64),
+                ("l2_capacity", C.c_uint32), ("addr_space", C.c_uint32),
+                ("n_requesters", C.c_uint32), ("reserved", C.c_uint32), ("n_loads", C.c_uint64)]
+
+
+class Columns(C.Structure):
+    _fields_ = [("end_time", C.c_void_p), ("n_events", C.c_void_p), ("trace_hash", C.c_void_p),
+                ("status", C.c_void_p), ("f64", C.c_void_p * N_F64), ("i64", C.c_void_p * N_I64)]
+
+
+class Accumulators(C.Structure):
+    _fields_ = [("n_replications", C.c_uint64), ("n_events", C.c_uint64),
+                ("n_errors", C.c_uint64), ("trace_hash_sum", C.c_uint64),
+                ("end_time_sum", C.c_int64), ("i64_sum", C.c_int64 * N_I64),
+                ("f64_sum", C.c_double * N_F64), ("f64_sumsq", C.c_double * N_F64)]
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+                ("first_replication", C.c_uint64), ("n_replications", C.c_uint64),
+                ("clock", Clock), ("params", C.c_void_p), ("params_size", C.c_size_t),
+                ("stream", C.c_void_p), ("flags", C.c_uint32), ("queue_capacity", C.c_uint32)]
+
+
+PARAMS_OF_MODEL = {MODEL_MM1: MM1Params, MODEL_ALOHA: AlohaParams, MODEL_MMC: MMCParams,
+                   MODEL_ARCHSIM: ArchSimParams}
+
+
+class HostColumns:
+    """Per-replication result columns in host memory (numpy), structure of arrays."""
+
+    def __init__(self, n, pinned=False):
+        self.n = int(n)
+        self._keep = []
+
+        def alloc(dtype):
+            if pinned:
+                import torch
+                t = torch.empty(self.n, dtype=getattr(torch, np.dtype(dtype).name)
+                                if np.dtype(dtype).name not in ("uint64", "uint32")
+                                else {"uint64": torch.int64, "uint32": torch.int32}[
+                                    np.dtype(dtype).name]).pin_memory()
+                self._keep.append(t)
+                return t.numpy().view(dtype)
+            return np.zeros(self.n, dtype=dtype)
+
+        self.end_time = alloc(np.int64)
+        self.n_events = alloc(np.uint64)
+        self.trace_hash = alloc(np.uint64)
+        self.status = alloc(np.uint32)
+        self.f64 = [alloc(np.float64) for _ in range(N_F64)]
+        self.i64 = [alloc(np.int64) for _ in range(N_I64)]
+
+    def nbytes(self):
+        return (self.end_time.nbytes + self.n_events.nbytes + self.trace_hash.nbytes +
+                self.status.nbytes + sum(a.nbytes for a in self.f64) +
+                sum(a.nbytes for a in self.i64))
+
+    def as_struct(self):
+        return Columns(self.end_time.ctypes.data, self.n_events.ctypes.data,
+                       self.trace_hash.ctypes.data, self.status.ctypes.data,
+                       (C.c_void_p * N_F64)(*[a.ctypes.data for a in self.f64]),
+                       (C.c_void_p * N_I64)(*[a.ctypes.data for a in self.i64]))

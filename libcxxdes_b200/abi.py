@@ -83,13 +83,10 @@ class HostColumns:
 
         def alloc(dtype):
             if pinned:
-                import torch
-                t = torch.empty(self.n, dtype=getattr(torch, np.dtype(dtype).name)
-                                if np.dtype(dtype).name not in ("uint64", "uint32")
-                                else {"uint64": torch.int64, "uint32": torch.int32}[
-                                    np.dtype(dtype).name]).pin_memory()
-                self._keep.append(t)
-                return t.numpy().view(dtype)
+                import torch  # pinned host memory is plumbing torch already provides
+                raw = torch.empty(self.n * np.dtype(dtype).itemsize, dtype=torch.uint8).pin_memory()
+                self._keep.append(raw)
+                return raw.numpy().view(dtype)
             return np.zeros(self.n, dtype=dtype)
 
         self.end_time = alloc(np.int64)

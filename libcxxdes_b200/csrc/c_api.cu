@@ -1,0 +1,403 @@
+// c_api.cu -- extern "C" boundary of the ensemble engine (include/cxxdes_b200.h).
+//
+// Owns the device buffers behind the opaque handle, picks the kernel for the model, launches on
+// the caller's stream (or one it owns) and brackets every run with CUDA events recorded on that
+// same stream.  No CPU implementation of the dispatch loop exists on this side of the boundary:
+// if no CUDA device is present every entry point fails with CXXDES_B200_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cxxdes_b200.h"
+#include "kernels.h"
+
+using namespace cxb;
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(CXXDES_B200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// time::count, include/cxxdes/misc/time.hpp:75-86 (integer arithmetic, evaluated once on the host).
+int64_t time_count(int64_t t, int u, int64_t prec_t, int prec_u) {
+    static const int64_t conv[5] = {1, 1000, 1000000, 1000000000, 1000000000000LL};
+    if (u < prec_u) return conv[prec_u - u] * t / prec_t;
+    return (t / prec_t) / conv[u - prec_u];
+}
+
+union model_params {
+    cxxdes_b200_mm1_params mm1;
+    cxxdes_b200_aloha_params aloha;
+    cxxdes_b200_mmc_params mmc;
+    cxxdes_b200_archsim_params arch;
+};
+
+size_t params_size_of(int model) {
+    switch (model) {
+        case CXXDES_B200_MODEL_MM1: return sizeof(cxxdes_b200_mm1_params);
+        case CXXDES_B200_MODEL_ALOHA: return sizeof(cxxdes_b200_aloha_params);
+        case CXXDES_B200_MODEL_MMC: return sizeof(cxxdes_b200_mmc_params);
+        case CXXDES_B200_MODEL_ARCHSIM: return sizeof(cxxdes_b200_archsim_params);
+        default: return 0;
+    }
+}
+
+}  // namespace
+
+struct cxxdes_b200_ensemble {
+    cxxdes_b200_config cfg;
+    model_params params;
+    clock_config clk;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    int64_t horizon = -1;  // last run_until target; -1 = never run, INT64_MAX = ran to exhaustion
+    bool used = false;
+
+    // device memory
+    unsigned char *col_block = nullptr;  // all result columns, one allocation
+    device_columns cols{};
+    unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor
+    uint32_t *retry_list = nullptr;
+    log_entry *log_table = nullptr;
+    int64_t *ring = nullptr;
+    size_t ring_bytes = 0;
+    cxxdes_b200_accumulators *acc = nullptr;
+    void *reduce_scratch = nullptr;
+
+    bool use_fused = false;
+    mm1_fused_plan mm1_plan{};
+    int engine_blocks = 0, engine_threads = 128;
+    uint32_t engine_ring = 0;
+};
+
+namespace {
+
+int set_device(const cxxdes_b200_ensemble *e) {
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    return CXXDES_B200_OK;
+}
+
+int allocate(cxxdes_b200_ensemble *e) {
+    const uint64_t n = e->cfg.n_replications;
+    // columns: 8-byte ones first, the 4-byte status last; every column 256-byte aligned
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t col8 = pad(n * 8), col4 = pad(n * 4);
+    const size_t total = col8 * (3 + CXXDES_B200_N_F64 + CXXDES_B200_N_I64) + col4;
+    CUDA_TRY(cudaMalloc(&e->col_block, total));
+    CUDA_TRY(cudaMemsetAsync(e->col_block, 0, total, e->stream));
+    unsigned char *p = e->col_block;
+    e->cols.end_time = (int64_t *)p; p += col8;
+    e->cols.n_events = (uint64_t *)p; p += col8;
+    e->cols.trace_hash = (uint64_t *)p; p += col8;
+    for (int k = 0; k < CXXDES_B200_N_F64; ++k) { e->cols.f64[k] = (double *)p; p += col8; }
+    for (int k = 0; k < CXXDES_B200_N_I64; ++k) { e->cols.i64[k] = (int64_t *)p; p += col8; }
+    e->cols.status = (uint32_t *)p;
+    CUDA_TRY(cudaMalloc(&e->counters, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&e->retry_list, sizeof(uint32_t) * (n ? n : 1)));
+    CUDA_TRY(cudaMalloc(&e->log_table, sizeof(LOG_TABLE_HOST)));
+    CUDA_TRY(cudaMemcpyAsync(e->log_table, LOG_TABLE_HOST, sizeof(LOG_TABLE_HOST), cudaMemcpyHostToDevice,
+                             e->stream));
+    CUDA_TRY(cudaMalloc(&e->acc, sizeof(cxxdes_b200_accumulators)));
+    CUDA_TRY(cudaMalloc(&e->reduce_scratch, reduce_scratch_bytes(e->sm_count)));
+    if (e->ring_bytes) CUDA_TRY(cudaMalloc(&e->ring, e->ring_bytes));
+    return CXXDES_B200_OK;
+}
+
+int plan(cxxdes_b200_ensemble *e) {
+    const cxxdes_b200_config &c = e->cfg;
+    switch (c.model) {
+        case CXXDES_B200_MODEL_MM1: {
+            const cxxdes_b200_mm1_params &p = e->params.mm1;
+            if (!(p.lambda > 0.0) || !(p.mu > 0.0)) return fail(CXXDES_B200_ERR_INVALID, "mm1: rates must be > 0");
+            e->use_fused = !(c.flags & CXXDES_B200_FLAG_GENERIC_ENGINE) && p.n_packets >= 2 &&
+                           p.n_packets < (1ULL << 31);
+            if (e->use_fused) {
+                e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin);
+                e->ring_bytes = (size_t)e->mm1_plan.fb_blocks * e->mm1_plan.fb_threads * e->mm1_plan.fb_ring *
+                                sizeof(int64_t);
+            } else {
+                e->engine_threads = 128;
+                e->engine_blocks = e->sm_count * 4;
+                uint64_t cap = c.queue_capacity ? c.queue_capacity : 1024;
+                if (cap > p.n_packets) cap = p.n_packets;
+                if (cap < 2) cap = 2;
+                e->engine_ring = (uint32_t)cap;
+                e->ring_bytes = (size_t)e->engine_blocks * e->engine_threads * cap * sizeof(int64_t);
+            }
+            return CXXDES_B200_OK;
+        }
+        default:
+            return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", c.model);
+    }
+}
+
+int launch(cxxdes_b200_ensemble *e, int64_t until) {
+    int rc = set_device(e);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(e->counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    shard sh{};
+    sh.seed = e->cfg.seed;
+    sh.first_replication = e->cfg.first_replication;
+    sh.n_replications = e->cfg.n_replications;
+    sh.clk = e->clk;
+    sh.run_until = until;
+    sh.work_counter = e->counters + 0;
+    sh.retry_count = e->counters + 1;
+    sh.retry_list = e->retry_list;
+    sh.log_table = e->log_table;
+    CUDA_TRY(cudaEventRecord(e->ev_begin, e->stream));
+    int launches = 0;
+    switch (e->cfg.model) {
+        case CXXDES_B200_MODEL_MM1:
+            if (e->use_fused) {
+                CUDA_TRY(launch_mm1_fused(e->params.mm1, sh, e->cols, e->mm1_plan, e->ring, e->counters + 2,
+                                          e->stream, &launches));
+            } else {
+                CUDA_TRY(launch_mm1_engine(e->params.mm1, sh, e->cols, e->ring, e->engine_ring, e->engine_blocks,
+                                           e->engine_threads, e->stream));
+                launches = 1;
+            }
+            break;
+        default:
+            return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_end, e->stream));
+    e->launches += launches;
+    e->timed = true;
+    e->used = true;
+    e->horizon = until < 0 ? INT64_MAX : until;
+    return CXXDES_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cxxdes_b200_device_count(int *count) {
+    if (!count) return fail(CXXDES_B200_ERR_INVALID, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_version(int *abi_version, int *sm_arch) {
+    if (abi_version) *abi_version = 1;
+    if (sm_arch) *sm_arch = 100;
+    return CXXDES_B200_OK;
+}
+
+const char *cxxdes_b200_last_error(void) { return g_error; }
+
+int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out) {
+    if (!cfg || !out) return fail(CXXDES_B200_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    size_t want = params_size_of(cfg->model);
+    if (want == 0) return fail(CXXDES_B200_ERR_INVALID, "unknown model %d", cfg->model);
+    if (!cfg->params || cfg->params_size != want)
+        return fail(CXXDES_B200_ERR_INVALID, "params_size %zu does not match model %d (%zu)", cfg->params_size,
+                    cfg->model, want);
+    if (cfg->n_replications == 0 || cfg->n_replications > 0xFFFFFFFFull)
+        return fail(CXXDES_B200_ERR_INVALID, "n_replications must be in [1, 2^32)");
+    const cxxdes_b200_clock &ck = cfg->clock;
+    if (ck.unit_u < 0 || ck.unit_u > 4 || ck.precision_u < 0 || ck.precision_u > 4 || ck.precision_t <= 0 ||
+        ck.unit_t <= 0)
+        return fail(CXXDES_B200_ERR_INVALID, "invalid clock");
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(CXXDES_B200_ERR_CUDA, "device %d not present (%d visible)", cfg->device, n_dev);
+
+    cxxdes_b200_ensemble *e = new (std::nothrow) cxxdes_b200_ensemble();
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "out of host memory");
+    e->cfg = *cfg;
+    memcpy(&e->params, cfg->params, want);
+    e->cfg.params = nullptr;
+    e->clk.ticks_per_unit = time_count(ck.unit_t, ck.unit_u, ck.precision_t, ck.precision_u);
+    e->clk.tick_mult = ck.precision_t;
+    static const double conv[5] = {1, 1e-3, 1e-6, 1e-9, 1e-12};
+    e->clk.seconds_per_tick_unit = conv[ck.precision_u];
+
+    int rc = set_device(e);
+    if (rc) { delete e; return rc; }
+    cudaDeviceProp prop;
+    cudaError_t ce = cudaGetDeviceProperties(&prop, cfg->device);
+    if (ce != cudaSuccess) { delete e; return fail(CXXDES_B200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
+    if (prop.major != 10) {
+        delete e;
+        return fail(CXXDES_B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                    prop.major, prop.minor);
+    }
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cfg->stream) {
+        e->stream = (cudaStream_t)cfg->stream;
+    } else {
+        ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { delete e; return fail(CXXDES_B200_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
+        e->own_stream = true;
+    }
+    rc = plan(e);
+    if (rc == CXXDES_B200_OK) rc = allocate(e);
+    if (rc == CXXDES_B200_OK) {
+        ce = cudaEventCreate(&e->ev_begin);
+        if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_end);
+        if (ce == cudaSuccess && e->use_fused) ce = configure_mm1_fused(e->mm1_plan);
+        if (ce != cudaSuccess) rc = fail(CXXDES_B200_ERR_CUDA, "setup: %s", cudaGetErrorString(ce));
+    }
+    if (rc != CXXDES_B200_OK) {
+        cxxdes_b200_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    return launch(e, -1);
+}
+
+// State is not written back between launches yet: a later horizon replays each replication from
+// tick 0 up to the new target, which yields exactly the state the reference reaches by continuing
+// (every replication is a deterministic function of its seed).
+int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    if (t < 0) return fail(CXXDES_B200_ERR_INVALID, "run_until: t must be >= 0");
+    if (e->horizon == INT64_MAX) return CXXDES_B200_OK;  // already exhausted: nothing left to run
+    if (e->horizon > t) t = e->horizon;                  // now_ = max(now_, t), environment.ipp:194
+    return launch(e, t);
+}
+
+int cxxdes_b200_run_for(cxxdes_b200_ensemble *e, int64_t dt) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    if (dt < 0) return fail(CXXDES_B200_ERR_INVALID, "run_for: dt must be >= 0");
+    int64_t base = e->horizon < 0 ? 0 : e->horizon;
+    if (base == INT64_MAX) return CXXDES_B200_OK;
+    return cxxdes_b200_run_until(e, base + dt);
+}
+
+int cxxdes_b200_sync(cxxdes_b200_ensemble *e) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    int rc = set_device(e);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_fetch(cxxdes_b200_ensemble *e, const cxxdes_b200_columns *h) {
+    if (!e || !h) return fail(CXXDES_B200_ERR_INVALID, "handle/columns is NULL");
+    if (!e->used) return fail(CXXDES_B200_ERR_STATE, "fetch before run");
+    int rc = set_device(e);
+    if (rc) return rc;
+    const uint64_t n = e->cfg.n_replications;
+    auto copy = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream);
+    };
+    CUDA_TRY(copy(h->end_time, e->cols.end_time, n * 8));
+    CUDA_TRY(copy(h->n_events, e->cols.n_events, n * 8));
+    CUDA_TRY(copy(h->trace_hash, e->cols.trace_hash, n * 8));
+    CUDA_TRY(copy(h->status, e->cols.status, n * 4));
+    for (int k = 0; k < CXXDES_B200_N_F64; ++k) CUDA_TRY(copy(h->f64[k], e->cols.f64[k], n * 8));
+    for (int k = 0; k < CXXDES_B200_N_I64; ++k) CUDA_TRY(copy(h->i64[k], e->cols.i64[k], n * 8));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (h->status) {
+        for (uint64_t r = 0; r < n; ++r)
+            if (h->status[r] & ~(uint32_t)CXXDES_B200_REP_UNFINISHED)
+                return fail(CXXDES_B200_ERR_CAPACITY, "replication %llu reported status 0x%x",
+                            (unsigned long long)(e->cfg.first_replication + r), h->status[r]);
+    }
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_device_columns(cxxdes_b200_ensemble *e, cxxdes_b200_columns *d) {
+    if (!e || !d) return fail(CXXDES_B200_ERR_INVALID, "handle/columns is NULL");
+    d->end_time = e->cols.end_time;
+    d->n_events = e->cols.n_events;
+    d->trace_hash = e->cols.trace_hash;
+    d->status = e->cols.status;
+    for (int k = 0; k < CXXDES_B200_N_F64; ++k) d->f64[k] = e->cols.f64[k];
+    for (int k = 0; k < CXXDES_B200_N_I64; ++k) d->i64[k] = e->cols.i64[k];
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_reduce(cxxdes_b200_ensemble *e, cxxdes_b200_accumulators *host_out, void **device_acc) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    if (!e->used) return fail(CXXDES_B200_ERR_STATE, "reduce before run");
+    int rc = set_device(e);
+    if (rc) return rc;
+    CUDA_TRY(launch_reduce(e->cols, e->cfg.n_replications, e->acc, e->reduce_scratch, e->sm_count, e->stream));
+    e->launches += 2;
+    if (device_acc) *device_acc = e->acc;
+    if (host_out) {
+        CUDA_TRY(cudaMemcpyAsync(host_out, e->acc, sizeof(*host_out), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms) {
+    if (!e || !ms) return fail(CXXDES_B200_ERR_INVALID, "handle/ms is NULL");
+    if (!e->timed) return fail(CXXDES_B200_ERR_STATE, "no run recorded");
+    int rc = set_device(e);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventSynchronize(e->ev_end));
+    CUDA_TRY(cudaEventElapsedTime(ms, e->ev_begin, e->ev_end));
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches) {
+    if (!e || !launches) return fail(CXXDES_B200_ERR_INVALID, "handle/launches is NULL");
+    *launches = e->launches;
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    e->horizon = -1;
+    e->used = false;
+    e->timed = false;
+    return CXXDES_B200_OK;
+}
+
+int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
+    if (!e) return CXXDES_B200_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->col_block);
+    cudaFree(e->counters);
+    cudaFree(e->retry_list);
+    cudaFree(e->log_table);
+    cudaFree(e->ring);
+    cudaFree(e->acc);
+    cudaFree(e->reduce_scratch);
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return CXXDES_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// kernels.h -- host-callable launchers of the model kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device/models_common.cuh"
+
+namespace cxb {
+
+// ---- M/M/1 on the generic engine (mm1_engine.cu) ----
+size_t mm1_engine_smem_bytes(int threads);
+cudaError_t launch_mm1_engine(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                              int64_t *ring, uint32_t ring_cap, int blocks, int threads, cudaStream_t stream);
+
+// ---- fused M/M/1 (mm1_fused.cu) ----
+struct mm1_fused_plan {
+    int threads;          // threads per block
+    int blocks;           // persistent grid
+    uint32_t smem_ring;   // ring entries per replication in shared memory (fast kernel)
+    size_t smem_bytes;
+    int fb_threads, fb_blocks;  // fallback kernel (global-memory ring, 64-bit ticks)
+    uint32_t fb_ring;           // ring entries per fallback thread
+    bool direct_global;         // skip the shared-memory kernel (high utilisation / huge queues)
+};
+mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
+                              size_t smem_per_block_optin);
+cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                             const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
+                             cudaStream_t stream, int *launches);
+cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
+
+// ---- reduction of result columns to accumulators (reduce.cu) ----
+size_t reduce_scratch_bytes(int sm_count);
+cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_accumulators *device_acc,
+                          void *scratch, int sm_count, cudaStream_t stream);
+
+
+}  // namespace cxb

@@ -1,0 +1,304 @@
+// mm1_fused.cu -- the headline kernel: M/M/1 (examples/producer_consumer.cpp:9-59) with the whole
+// replication held on-chip.
+//
+// One thread owns one replication from its first event to its last.  What the generic engine
+// keeps in shared/global memory is specialised here from facts about this model
+// (all checked against the reference engine by the parity tests):
+//   * the event heap never holds more than 2 tokens and every priority is 0, so the libstdc++
+//     heap degenerates to "slot 0 is the minimum, an equal key keeps the earlier push in front"
+//     -> two (time, tag) register pairs;
+//   * the waiter list of queue<double>::event_ holds at most the consumer -> one flag;
+//   * the all_of of co_main is a countdown from 2;
+//   * the queue payload now_seconds() is a pure function of the put tick, so the ring stores the
+//     tick and converts at pop time (bit-identical, half the bytes).
+// Every popped token still counts as one event and is folded into the trace digest, including
+// handler events and the trailing null-target completion.
+//
+// Two instantiations:
+//   FAST  = true   32-bit ticks, ring of `ring_cap` u32 per thread in SHARED memory.  A replication
+//                  that would exceed the ring or the 32-bit tick range stops, and its id is appended
+//                  to the retry list (nothing is written to its result row).
+//   FAST  = false  64-bit ticks, ring in GLOBAL memory ([slot][thread], coalesced across lanes).
+//                  Runs the retry list (or, for heavily loaded queues, every replication).
+#include <cmath>
+
+#include "device/models_common.cuh"
+#include "kernels.h"
+
+namespace cxb {
+
+namespace {
+
+enum : uint32_t { M_MAIN = 0, M_PROD = 1, M_CONS = 2, M_HANDLER = 3, M_NOOP = 4 };
+
+// (kind << 56) ^ (proc << 40) of trace_hash_step for each tag; priority is always 0.
+__device__ __forceinline__ uint64_t tag_hash_bits(uint32_t m) {
+    uint64_t kind = m == M_HANDLER ? TOKEN_HANDLER : (m == M_NOOP ? TOKEN_NOOP : TOKEN_RESUME);
+    uint64_t proc = m == M_NOOP ? PROC_NONE : (m == M_HANDLER ? 0u : m);
+    return (kind << 56) ^ (proc << 40);
+}
+
+template <bool FAST>
+struct tick_traits;
+template <>
+struct tick_traits<true> {
+    using type = uint32_t;
+    static constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+    static constexpr uint32_t LIMIT = 0xFFFF0000u;
+};
+template <>
+struct tick_traits<false> {
+    using type = int64_t;
+    static constexpr int64_t EMPTY = INT64_MAX;
+    static constexpr int64_t LIMIT = INT64_MAX / 2;
+};
+
+}  // namespace
+
+template <bool FAST, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint32_t ring_cap,
+                 int64_t *gring_base, const uint32_t *list, const unsigned long long *list_count,
+                 unsigned long long *list_cursor) {
+    using tick_t = typename tick_traits<FAST>::type;
+    constexpr tick_t EMPTY = tick_traits<FAST>::EMPTY;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    stage_log_table(table, sh.log_table);
+    // FAST: ring[slot * THREADS + tid] (u32) in shared memory -> bank = tid % 32, conflict free.
+    uint32_t *sring = (uint32_t *)(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x;
+    const uint64_t total_threads = (uint64_t)gridDim.x * THREADS;
+    int64_t *gring = FAST ? nullptr : gring_base + ((uint64_t)blockIdx.x * THREADS + threadIdx.x);
+
+    const divisor lambda = make_divisor(prm.lambda);
+    const divisor mu = make_divisor(prm.mu);
+    const uint32_t n_packets = (uint32_t)prm.n_packets;  // the launcher guarantees 2 <= n < 2^31
+    const double ticks_per_unit = (double)sh.clk.ticks_per_unit;
+    const int64_t until = sh.run_until;
+
+    for (;;) {
+        // ---- replication-level work stealing (one atomic per lane per replication) ----
+        uint64_t rep;
+        if (list) {
+            unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+            if (idx >= *list_count) break;
+            rep = list[idx];
+        } else {
+            if (!steal(sh, rep)) break;
+        }
+        const uint64_t grep = sh.first_replication + rep;
+        const uint32_t key0 = (uint32_t)sh.seed, key1 = (uint32_t)grep;
+        const uint32_t ctr1 = (uint32_t)(sh.seed >> 32), ctr3 = (uint32_t)(grep >> 32);
+
+        // ---- environment + process state, all in registers ----
+        tick_t t0 = 0, t1 = EMPTY;  // environment::bind(co_main): start token {0, 0, main}
+        uint32_t m0 = M_MAIN, m1 = M_NOOP;
+        tick_t now = 0;
+        uint32_t i = 0, k = 0;         // producer loop index, consumer count
+        uint32_t head = 0, count = 0, max_queue = 0;
+        uint32_t main_pc = 0, cons_pc = 0, remaining = 2;
+        bool waiting = false;          // consumer parked in queue.event_ (event.hpp:136-139)
+        tick_t x_tick = 0;
+        double total_latency = 0.0, avg_latency = 0.0;
+        uint64_t n_events = 0, hash = TRACE_HASH_INIT;
+        uint32_t status = 0;
+
+        auto push = [&](tick_t t, uint32_t m) {
+            // std::push_heap on <= 2 entries: the new token goes in front only if the current
+            // front is strictly later (stl_heap.h:135-148); an empty front compares as latest.
+            if (t1 != EMPTY) status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            bool front = t0 > t;
+            t1 = front ? t0 : t;
+            m1 = front ? m0 : m;
+            t0 = front ? t : t0;
+            m0 = front ? m : m0;
+        };
+
+        while (t0 != EMPTY && (until < 0 || (int64_t)t0 <= until)) {
+            // ---- environment::step, environment.ipp:117-146 ----
+            const tick_t t = t0;
+            const uint32_t m = m0;
+            t0 = t1; m0 = m1; t1 = EMPTY;           // pop_heap on <= 2 entries
+            now = t > now ? t : now;
+            ++n_events;
+            hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ tag_hash_bits(m))) * TRACE_HASH_MUL;
+
+            bool draw = false;
+            uint32_t draw_index = 0;
+            if (m == M_PROD) {
+                // producer body, producer_consumer.cpp:31-36
+                if (i < n_packets) {
+                    // q.put(now_seconds()): emplace, then wake (queue.hpp:48-53)
+                    if (count >= ring_cap) {
+                        status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+                        break;
+                    }
+                    uint32_t slot = head + count;
+                    slot = slot >= ring_cap ? slot - ring_cap : slot;
+                    if (FAST) sring[slot * THREADS] = (uint32_t)now;
+                    else gring[(uint64_t)slot * total_threads] = (int64_t)now;
+                    ++count;
+                    max_queue = count > max_queue ? count : max_queue;
+                    if (waiting) {  // wake: the parked consumer token {0 + now, 0, consumer}
+                        push(now, M_CONS);
+                        waiting = false;
+                    }
+                    draw = true;
+                    draw_index = i;
+                    ++i;
+                } else {
+                    push(now, M_HANDLER);  // co_return: completion token carries the all_of handler
+                }
+            } else if (m == M_CONS) {
+                // consumer body, producer_consumer.cpp:38-54
+                if (cons_pc == 2) {
+                    double now_s = sim_to_seconds((int64_t)now, sh.clk);
+                    double x_s = sim_to_seconds((int64_t)x_tick, sh.clk);
+                    total_latency += (now_s - x_s);  // :52
+                }
+                if (count == 0) {  // q.pop(): queue empty -> event_.wait(), no token scheduled
+                    waiting = true;
+                    cons_pc = 1;
+                } else {
+                    if (FAST) x_tick = sring[head * THREADS];
+                    else x_tick = (tick_t)gring[(uint64_t)head * total_threads];
+                    head = head + 1 >= ring_cap ? 0 : head + 1;
+                    --count;  // pop's own wake() finds no waiter: the producer never blocks
+                    ++k;
+                    if (k == n_packets) {
+                        avg_latency = total_latency / (double)prm.n_packets;  // :46
+                        push(now, M_HANDLER);
+                    } else {
+                        draw = true;
+                        draw_index = k - 1;
+                        cons_pc = 2;
+                    }
+                }
+            } else if (m == M_HANDLER) {
+                // all_of handler, any_of.ipp:9-26: output token inherits the child token's time
+                if (--remaining == 0) push(t, M_MAIN);
+            } else if (m == M_MAIN) {
+                if (main_pc == 0) {  // co_await (producer() && consumer()): bind both, any_of.ipp:41-48
+                    push(now, M_PROD);
+                    push(now, M_CONS);
+                    main_pc = 1;
+                } else {
+                    push(now, M_NOOP);  // co_main returns: null-target completion (coroutine.ipp:352-357)
+                }
+            }
+
+            if (draw) {
+                // env.timeout(exponential()): the only expensive part, shared by both processes
+                const bool is_prod = m == M_PROD;
+                philox_block b = philox4x32_10(draw_index >> 1, ctr1, is_prod ? 1u : 2u, ctr3, key0, key1);
+                const bool odd = draw_index & 1;
+                uint64_t bits = ((uint64_t)(odd ? b.w[3] : b.w[1]) << 32) | (odd ? b.w[2] : b.w[0]);
+                double v = exponential_from_bits(bits, is_prod ? lambda : mu, table);
+                int64_t ticks = (int64_t)(v * ticks_per_unit);  // environment::real_to_sim
+                if (FAST) {
+                    if ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks) {
+                        status |= CXXDES_B200_REP_TIME_RANGE;
+                        break;
+                    }
+                }
+                push(now + (tick_t)ticks, m);
+            }
+        }
+
+        if (FAST && (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE))) {
+            // hand the replication to the fallback kernel; its row is written there
+            unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+            sh.retry_list[at] = (uint32_t)rep;
+            continue;
+        }
+        int64_t end = (int64_t)now;
+        if (until >= 0) {
+            if (t0 != EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
+            end = end > until ? end : until;  // run_until: now_ = max(now_, t), environment.ipp:194
+        }
+        rep_out o;
+        o.end_time = end;
+        o.n_events = n_events;
+        o.trace_hash = hash;
+        o.status = status;
+        o.f64[0] = avg_latency;
+        o.f64[1] = total_latency;
+        o.i64[0] = (int64_t)k;
+        o.i64[1] = (int64_t)max_queue;
+        store_result(out, rep, o);
+    }
+}
+
+constexpr int FAST_THREADS = 256;
+constexpr int FAST_MIN_BLOCKS = 4;
+constexpr int FB_THREADS = 128;
+
+mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
+                              size_t smem_optin) {
+    mm1_fused_plan p{};
+    p.threads = FAST_THREADS;
+    const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    // 4 resident blocks of 256 threads per SM: each gets a quarter of the shared memory.
+    size_t per_block = (smem_optin < 227 * 1024 ? smem_optin : 227 * 1024) / FAST_MIN_BLOCKS - 1024;
+    uint32_t max_ring = (uint32_t)((per_block - table_bytes) / (FAST_THREADS * sizeof(uint32_t)));
+    p.smem_ring = queue_capacity ? queue_capacity : max_ring;
+    if (p.smem_ring > max_ring) p.smem_ring = max_ring;
+    if (p.smem_ring > prm.n_packets) p.smem_ring = (uint32_t)prm.n_packets;
+    p.smem_bytes = table_bytes + (size_t)p.smem_ring * FAST_THREADS * sizeof(uint32_t);
+    p.blocks = sm_count * FAST_MIN_BLOCKS;
+    // Stationary P(queue length > Q) = rho^(Q+1); if more than ~2% of replications are expected to
+    // overflow the shared ring at least once, run everything on the global-memory kernel.
+    double rho = prm.lambda / prm.mu;
+    double p_over = rho >= 1.0 ? 1.0 : pow(rho, (double)p.smem_ring + 1.0) * (double)prm.n_packets;
+    p.direct_global = !(p_over < 0.02);
+    p.fb_threads = FB_THREADS;
+    uint64_t want = prm.n_packets;
+    if (p.direct_global) {
+        p.fb_blocks = sm_count * 8;
+        // memory budget for the rings: 8 GiB
+        uint64_t budget = (8ULL << 30) / ((uint64_t)p.fb_blocks * FB_THREADS * sizeof(int64_t));
+        if (rho < 1.0) {
+            // capacity with overflow probability < 1e-12 per arrival, at least 64
+            double need = ceil(log(1e-12 / (double)prm.n_packets) / log(rho)) + 64.0;
+            if ((double)want > need) want = (uint64_t)need;
+        }
+        if (want > budget) want = budget;
+    } else {
+        p.fb_blocks = sm_count;
+        uint64_t budget = (2ULL << 30) / ((uint64_t)p.fb_blocks * FB_THREADS * sizeof(int64_t));
+        if (want > budget) want = budget;
+    }
+    p.fb_ring = (uint32_t)(want < 2 ? 2 : want);
+    return p;
+}
+
+cudaError_t configure_mm1_fused(const mm1_fused_plan &plan) {
+    return cudaFuncSetAttribute(mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+}
+
+cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                             const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
+                             cudaStream_t stream, int *launches) {
+    const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    if (!plan.direct_global) {
+        mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>
+            <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, sh, out, plan.smem_ring, nullptr,
+                                                                    nullptr, nullptr, nullptr);
+        ++*launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // retry list -> fallback kernel; exits at once when the list is empty
+        mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(
+            prm, sh, out, plan.fb_ring, fb_ring, sh.retry_list, sh.retry_count, fb_counter);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(
+        prm, sh, out, plan.fb_ring, fb_ring, nullptr, nullptr, nullptr);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace cxb

@@ -1,0 +1,148 @@
+"""GPU parity tests (B200): the CUDA path through the C ABI vs the CPU oracle and the reference's
+golden vectors.  Integer time, event counts and trace digests must be bit-exact; the double
+statistics are compared as bit patterns too (tolerance 0 -- stricter than the 1e-12 the task allows)."""
+import numpy as np
+import pytest
+
+import golden_util
+import oracles
+import libcxxdes_b200 as L
+from libcxxdes_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(params, n_reps, seed=0x5EED, first=0, until=-1, flags=0, queue_capacity=0, clock=None, strict=True):
+    ens = L.Ensemble(params, n_reps, seed=seed, first_replication=first, flags=flags, queue_capacity=queue_capacity)
+    unit, prec = clock or ((1, L.SECONDS), (1, L.MILLISECONDS))
+    ens.time_unit(*unit).time_precision(*prec)
+    if until < 0:
+        ens.run()
+    else:
+        ens.run_until(until)
+    cols = ens.fetch(strict=strict)
+    acc, _ = ens.reduce()
+    ens.close()
+    return cols, acc
+
+
+@pytest.mark.parametrize("flags", [0, abi.FLAG_GENERIC_ENGINE], ids=["fused", "engine"])
+@pytest.mark.parametrize("idx", range(12))
+def test_gpu_matches_reference_golden(built, idx, flags):
+    g = golden_util.load("mm1_reference.json")
+    case = g["cases"][idx]
+    p = abi.MM1Params(case["lambda"], case["mu"], case["n_packets"])
+    got, _ = run_gpu(p, case["n_replications"], seed=case["seed"], first=case["first_replication"],
+                     until=case["run_until"], flags=flags)
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(case), what=f"golden case {idx}")
+
+
+@pytest.mark.parametrize("flags", [0, abi.FLAG_GENERIC_ENGINE], ids=["fused", "engine"])
+@pytest.mark.parametrize("lam,n_packets,n_reps", [(5.0, 2000, 4096), (0.5, 1000, 2048), (9.0, 1500, 2048),
+                                                  (9.9, 2000, 1024), (12.0, 600, 512)])
+def test_gpu_matches_oracle(port, lam, n_packets, n_reps, flags):
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, acc = run_gpu(p, n_reps, flags=flags)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, n_reps, threads=oracles.os.cpu_count())
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what=f"lambda={lam}")
+    # accumulators: integer sums exact, checksum of checksums, FP sums to 1e-12 relative
+    assert acc.n_replications == n_reps and acc.n_errors == 0
+    assert acc.n_events == int(want.n_events.sum())
+    assert acc.end_time_sum == int(want.end_time.sum())
+    assert acc.trace_hash_sum == int(want.trace_hash.sum(dtype=np.uint64))
+    assert acc.i64_sum[0] == int(want.i64[0].sum())
+    assert abs(acc.f64_sum[0] - want.f64[0].sum()) <= 1e-12 * abs(want.f64[0].sum())
+    assert abs(acc.f64_sumsq[0] - (want.f64[0] ** 2).sum()) <= 1e-12 * (want.f64[0] ** 2).sum()
+
+
+def test_small_ring_takes_the_retry_path(port):
+    """A 4-entry shared ring overflows in most replications: they are re-run by the global-ring
+    kernel and must still match the oracle bit for bit."""
+    p = abi.MM1Params(8.0, 10.0, 1200)
+    got, _ = run_gpu(p, 3000, queue_capacity=4)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, 3000, threads=oracles.os.cpu_count())
+    assert (want.i64[1] > 4).mean() > 0.5          # the scenario really overflows
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="retry path")
+
+
+def test_tick_range_guard_falls_back_to_64bit(port):
+    """Very slow arrivals push the clock past 2^32 ticks; the 32-bit fast kernel must hand those
+    replications to the 64-bit kernel."""
+    p = abi.MM1Params(0.00002, 0.001, 400)
+    got, _ = run_gpu(p, 512)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, 512, threads=oracles.os.cpu_count())
+    assert want.end_time.max() > 2 ** 32
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="64-bit ticks")
+
+
+def test_sharding_is_invisible(port):
+    """Replication r of a shard starting at `first` equals replication first+r of one big run."""
+    p = abi.MM1Params(5.0, 10.0, 500)
+    whole, _ = run_gpu(p, 1024)
+    for first, n in [(0, 300), (300, 500), (800, 224)]:
+        part, _ = run_gpu(p, n, first=first)
+        assert np.array_equal(part.trace_hash, whole.trace_hash[first:first + n])
+        assert np.array_equal(part.end_time, whole.end_time[first:first + n])
+
+
+@pytest.mark.parametrize("until", [0, 1, 999, 20000, 10 ** 7])
+def test_run_until_matches_oracle(port, until):
+    p = abi.MM1Params(5.0, 10.0, 800)
+    got, _ = run_gpu(p, 256, seed=5, until=until, strict=False)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 5, 0, 256, threads=4, until=until)
+    golden_util.assert_columns_equal(got, want, what=f"until={until}")
+
+
+def test_run_for_accumulates(port):
+    """run_for(5 s) twice == run_until(10 s) (tests/process.test.cpp:127-147 pattern)."""
+    p = abi.MM1Params(5.0, 10.0, 800)
+    ens = L.Ensemble(p, 128, seed=5)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run_for(5000)
+    a = ens.fetch(strict=False)
+    assert (a.end_time == 5000).all()
+    ens.run_for(5000)
+    b = ens.fetch(strict=False)
+    ens.close()
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 5, 0, 128, threads=4, until=10000)
+    golden_util.assert_columns_equal(b, want, what="run_for x2")
+
+
+def test_other_clocks(port):
+    p = abi.MM1Params(5.0, 10.0, 300)
+    for unit, prec in [((1, L.MILLISECONDS), (1, L.MICROSECONDS)), ((2, L.SECONDS), (5, L.MILLISECONDS))]:
+        got, _ = run_gpu(p, 128, seed=9, clock=(unit, prec))
+        want = port.run(abi.MODEL_MM1, p, abi.Clock.of(unit, prec), 9, 0, 128)
+        golden_util.assert_columns_equal(got, want, what=f"clock {unit}/{prec}")
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape at reduced replication count but full packet count: size-independent
+    properties (event-count identity, all packets consumed, latency near theory, determinism)."""
+    n_packets, n_reps = 10000, 16384
+    p = abi.MM1Params(5.0, 10.0, n_packets)
+    a, acc = run_gpu(p, n_reps)
+    assert not a.status.any()
+    assert (a.i64[0] == n_packets).all()
+    assert (a.n_events >= 2 * n_packets + 6).all() and (a.n_events <= 3 * n_packets + 6).all()
+    assert abs(a.f64[0].mean() - 0.2) < 0.004          # 1/(mu-lambda)
+    assert abs(a.n_events.mean() / n_packets - 2.5) < 0.01
+    b, acc2 = run_gpu(p, n_reps)                       # idempotent: same seeds, same bits
+    assert np.array_equal(a.trace_hash, b.trace_hash)
+    assert acc.trace_hash_sum == acc2.trace_hash_sum and acc.f64_sum[0] == acc2.f64_sum[0]
+    assert len(np.unique(a.trace_hash)) == n_reps      # replications are independent streams
+
+
+def test_errors_are_reported():
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(L.MM1Params(-1.0, 10.0, 10), 4).run()
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(L.MM1Params(5.0, 10.0, 10), 0).run()
+    ens = L.Ensemble(L.MM1Params(5.0, 10.0, 10), 4)
+    ens._ensure()
+    with pytest.raises(L.CxxdesError):
+        ens.fetch()                                    # fetch before run
+    ens.close()

@@ -209,7 +209,10 @@ def run_b200(a):
 
     R = a.replications
     params = L.MM1Params(LAMBDA, MU, a.packets)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, so torch.cuda.Event and
+    # NCCL (torch.distributed) see the same stream the kernels run on
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ens = L.Ensemble(params, R, seed=SEED, first_replication=rank * R, device=local_rank,
                      stream=stream.cuda_stream)
     ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)

@@ -77,85 +77,112 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
     const double ticks_per_unit = (double)sh.clk.ticks_per_unit;
     const int64_t until = sh.run_until;
 
+    // Loop-invariant pieces of the clock conversion (environment::now_seconds).
+    const int64_t tick_mult = sh.clk.tick_mult;
+    const double sec_per_unit = sh.clk.seconds_per_tick_unit;
+
+    // ---- per-lane replication state, all in registers ----
+    bool active = false, exhausted = false;
+    uint64_t rep = 0;
+    uint32_t key0 = 0, key1 = 0, ctr1 = 0, ctr3 = 0;
+    tick_t t0 = EMPTY, t1 = EMPTY, now = 0, x_tick = 0;
+    uint32_t m0 = M_NOOP, m1 = M_NOOP;
+    uint32_t i = 0, k = 0, head = 0, count = 0, max_queue = 0;
+    uint32_t main_pc = 0, cons_pc = 0, remaining = 2;
+    bool waiting = false;  // consumer parked in queue.event_ (event.hpp:136-139)
+    double total_latency = 0.0;
+    uint64_t n_events = 0, hash = TRACE_HASH_INIT;
+    uint32_t status = 0;
+
+    auto push = [&](tick_t t, uint32_t m) {
+        // std::push_heap on <= 2 entries: the new token goes in front only if the current front
+        // is strictly later (stl_heap.h:135-148); an empty front compares as latest.
+        if (t1 != EMPTY) status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+        bool front = t0 > t;
+        t1 = front ? t0 : t;
+        m1 = front ? m0 : m;
+        t0 = front ? t : t0;
+        m0 = front ? m : m0;
+    };
+
+    // The warp advances in lockstep, one event per lane per iteration.  Which process a lane
+    // resumes differs from lane to lane, so the cheap bookkeeping below diverges; the expensive
+    // part (Philox + log + divide for the next timeout) is identical for producer and consumer
+    // and is executed once, by all lanes together, after the __syncwarp() join.  A lane whose
+    // replication ends steals the next one at once (replication-level work stealing), so lanes
+    // only idle when the whole ensemble is exhausted.
     for (;;) {
-        // ---- replication-level work stealing (one atomic per lane per replication) ----
-        uint64_t rep;
-        if (list) {
-            unsigned long long idx = atomicAdd(list_cursor, 1ULL);
-            if (idx >= *list_count) break;
-            rep = list[idx];
-        } else {
-            if (!steal(sh, rep)) break;
+        if (!active && !exhausted) {
+            bool got;
+            if (list) {
+                unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+                got = idx < *list_count;
+                if (got) rep = list[idx];
+            } else {
+                got = steal(sh, rep);
+            }
+            if (got) {
+                const uint64_t grep = sh.first_replication + rep;
+                key0 = (uint32_t)sh.seed; key1 = (uint32_t)grep;
+                ctr1 = (uint32_t)(sh.seed >> 32); ctr3 = (uint32_t)(grep >> 32);
+                t0 = 0; m0 = M_MAIN;   // environment::bind(co_main): start token {0, 0, main}
+                t1 = EMPTY; m1 = M_NOOP;
+                now = 0; x_tick = 0;
+                i = k = head = count = max_queue = 0;
+                main_pc = cons_pc = 0; remaining = 2;
+                waiting = false;
+                total_latency = 0.0;
+                n_events = 0; hash = TRACE_HASH_INIT;
+                status = 0;
+                active = true;
+            } else {
+                exhausted = true;
+            }
         }
-        const uint64_t grep = sh.first_replication + rep;
-        const uint32_t key0 = (uint32_t)sh.seed, key1 = (uint32_t)grep;
-        const uint32_t ctr1 = (uint32_t)(sh.seed >> 32), ctr3 = (uint32_t)(grep >> 32);
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
 
-        // ---- environment + process state, all in registers ----
-        tick_t t0 = 0, t1 = EMPTY;  // environment::bind(co_main): start token {0, 0, main}
-        uint32_t m0 = M_MAIN, m1 = M_NOOP;
-        tick_t now = 0;
-        uint32_t i = 0, k = 0;         // producer loop index, consumer count
-        uint32_t head = 0, count = 0, max_queue = 0;
-        uint32_t main_pc = 0, cons_pc = 0, remaining = 2;
-        bool waiting = false;          // consumer parked in queue.event_ (event.hpp:136-139)
-        tick_t x_tick = 0;
-        double total_latency = 0.0, avg_latency = 0.0;
-        uint64_t n_events = 0, hash = TRACE_HASH_INIT;
-        uint32_t status = 0;
-
-        auto push = [&](tick_t t, uint32_t m) {
-            // std::push_heap on <= 2 entries: the new token goes in front only if the current
-            // front is strictly later (stl_heap.h:135-148); an empty front compares as latest.
-            if (t1 != EMPTY) status |= CXXDES_B200_REP_HEAP_OVERFLOW;
-            bool front = t0 > t;
-            t1 = front ? t0 : t;
-            m1 = front ? m0 : m;
-            t0 = front ? t : t0;
-            m0 = front ? m : m0;
-        };
-
-        while (t0 != EMPTY && (until < 0 || (int64_t)t0 <= until)) {
+        bool draw = false;
+        uint32_t draw_index = 0, m = M_NOOP;
+        if (active) {
             // ---- environment::step, environment.ipp:117-146 ----
             const tick_t t = t0;
-            const uint32_t m = m0;
+            m = m0;
             t0 = t1; m0 = m1; t1 = EMPTY;           // pop_heap on <= 2 entries
             now = t > now ? t : now;
             ++n_events;
             hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ tag_hash_bits(m))) * TRACE_HASH_MUL;
 
-            bool draw = false;
-            uint32_t draw_index = 0;
             if (m == M_PROD) {
                 // producer body, producer_consumer.cpp:31-36
                 if (i < n_packets) {
                     // q.put(now_seconds()): emplace, then wake (queue.hpp:48-53)
                     if (count >= ring_cap) {
                         status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-                        break;
+                    } else {
+                        uint32_t slot = head + count;
+                        slot = slot >= ring_cap ? slot - ring_cap : slot;
+                        if (FAST) sring[slot * THREADS] = (uint32_t)now;
+                        else gring[(uint64_t)slot * total_threads] = (int64_t)now;
+                        ++count;
+                        max_queue = count > max_queue ? count : max_queue;
+                        if (waiting) {  // wake: the parked consumer token {0 + now, 0, consumer}
+                            push(now, M_CONS);
+                            waiting = false;
+                        }
+                        draw = true;
+                        draw_index = i;
+                        ++i;
                     }
-                    uint32_t slot = head + count;
-                    slot = slot >= ring_cap ? slot - ring_cap : slot;
-                    if (FAST) sring[slot * THREADS] = (uint32_t)now;
-                    else gring[(uint64_t)slot * total_threads] = (int64_t)now;
-                    ++count;
-                    max_queue = count > max_queue ? count : max_queue;
-                    if (waiting) {  // wake: the parked consumer token {0 + now, 0, consumer}
-                        push(now, M_CONS);
-                        waiting = false;
-                    }
-                    draw = true;
-                    draw_index = i;
-                    ++i;
                 } else {
                     push(now, M_HANDLER);  // co_return: completion token carries the all_of handler
                 }
             } else if (m == M_CONS) {
                 // consumer body, producer_consumer.cpp:38-54
                 if (cons_pc == 2) {
-                    double now_s = sim_to_seconds((int64_t)now, sh.clk);
-                    double x_s = sim_to_seconds((int64_t)x_tick, sh.clk);
-                    total_latency += (now_s - x_s);  // :52
+                    // total_latency += now_seconds() - x   (:52); (double)(ticks * prec.t) * conv
+                    double now_s = (double)((int64_t)now * tick_mult) * sec_per_unit;
+                    double x_s = (double)((int64_t)x_tick * tick_mult) * sec_per_unit;
+                    total_latency += (now_s - x_s);
                 }
                 if (count == 0) {  // q.pop(): queue empty -> event_.wait(), no token scheduled
                     waiting = true;
@@ -167,8 +194,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
                     --count;  // pop's own wake() finds no waiter: the producer never blocks
                     ++k;
                     if (k == n_packets) {
-                        avg_latency = total_latency / (double)prm.n_packets;  // :46
-                        push(now, M_HANDLER);
+                        push(now, M_HANDLER);  // avg_latency = total / n (:46) is formed at store time
                     } else {
                         draw = true;
                         draw_index = k - 1;
@@ -187,46 +213,49 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
                     push(now, M_NOOP);  // co_main returns: null-target completion (coroutine.ipp:352-357)
                 }
             }
+        }
 
-            if (draw) {
-                // env.timeout(exponential()): the only expensive part, shared by both processes
-                const bool is_prod = m == M_PROD;
-                philox_block b = philox4x32_10(draw_index >> 1, ctr1, is_prod ? 1u : 2u, ctr3, key0, key1);
-                const bool odd = draw_index & 1;
-                uint64_t bits = ((uint64_t)(odd ? b.w[3] : b.w[1]) << 32) | (odd ? b.w[2] : b.w[0]);
-                double v = exponential_from_bits(bits, is_prod ? lambda : mu, table);
-                int64_t ticks = (int64_t)(v * ticks_per_unit);  // environment::real_to_sim
-                if (FAST) {
-                    if ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks) {
-                        status |= CXXDES_B200_REP_TIME_RANGE;
-                        break;
-                    }
-                }
+        __syncwarp();  // join: every lane of the warp takes the draw below together
+
+        if (draw) {
+            // env.timeout(exponential()): the only expensive part, shared by both processes
+            const bool is_prod = m == M_PROD;
+            philox_block b = philox4x32_10(draw_index >> 1, ctr1, is_prod ? 1u : 2u, ctr3, key0, key1);
+            const bool odd = draw_index & 1;
+            uint64_t bits = ((uint64_t)(odd ? b.w[3] : b.w[1]) << 32) | (odd ? b.w[2] : b.w[0]);
+            double v = exponential_from_bits(bits, is_prod ? lambda : mu, table);
+            int64_t ticks = (int64_t)(v * ticks_per_unit);  // environment::real_to_sim
+            if (FAST && ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks))
+                status |= CXXDES_B200_REP_TIME_RANGE;
+            else
                 push(now + (tick_t)ticks, m);
+        }
+
+        // ---- end of this lane's replication? (environment::run / run_until, environment.ipp:179-196) ----
+        if (active && (status != 0 || t0 == EMPTY || (until >= 0 && (int64_t)t0 > until))) {
+            active = false;
+            if (FAST && (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE))) {
+                // hand the replication to the fallback kernel; its row is written there
+                unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                sh.retry_list[at] = (uint32_t)rep;
+            } else {
+                int64_t end = (int64_t)now;
+                if (until >= 0) {
+                    if (t0 != EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
+                    end = end > until ? end : until;  // now_ = max(now_, t), environment.ipp:194
+                }
+                rep_out o;
+                o.end_time = end;
+                o.n_events = n_events;
+                o.trace_hash = hash;
+                o.status = status;
+                o.f64[0] = k == n_packets ? total_latency / (double)prm.n_packets : 0.0;  // :46
+                o.f64[1] = total_latency;
+                o.i64[0] = (int64_t)k;
+                o.i64[1] = (int64_t)max_queue;
+                store_result(out, rep, o);
             }
         }
-
-        if (FAST && (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE))) {
-            // hand the replication to the fallback kernel; its row is written there
-            unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
-            sh.retry_list[at] = (uint32_t)rep;
-            continue;
-        }
-        int64_t end = (int64_t)now;
-        if (until >= 0) {
-            if (t0 != EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
-            end = end > until ? end : until;  // run_until: now_ = max(now_, t), environment.ipp:194
-        }
-        rep_out o;
-        o.end_time = end;
-        o.n_events = n_events;
-        o.trace_hash = hash;
-        o.status = status;
-        o.f64[0] = avg_latency;
-        o.f64[1] = total_latency;
-        o.i64[0] = (int64_t)k;
-        o.i64[1] = (int64_t)max_queue;
-        store_result(out, rep, o);
     }
 }
 

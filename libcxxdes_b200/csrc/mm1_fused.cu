@@ -55,9 +55,13 @@ struct tick_traits<false> {
 
 }  // namespace
 
+struct mm1_rates {
+    divisor lambda, mu;
+};
+
 template <bool FAST, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint32_t ring_cap,
+mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_columns out, uint32_t ring_cap,
                  int64_t *gring_base, const uint32_t *list, const unsigned long long *list_count,
                  unsigned long long *list_cursor) {
     using tick_t = typename tick_traits<FAST>::type;
@@ -71,8 +75,10 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
     const uint64_t total_threads = (uint64_t)gridDim.x * THREADS;
     int64_t *gring = FAST ? nullptr : gring_base + ((uint64_t)blockIdx.x * THREADS + threadIdx.x);
 
-    const divisor lambda = make_divisor(prm.lambda);
-    const divisor mu = make_divisor(prm.mu);
+    // divisors {d, RN(1/d)} are formed on the host (IEEE division, same bits as on the device) and
+    // arrive as kernel parameters, so the loop only selects between constant-bank values
+    const divisor lambda = rates.lambda;
+    const divisor mu = rates.mu;
     const uint32_t n_packets = (uint32_t)prm.n_packets;  // the launcher guarantees 2 <= n < 2^31
     const double ticks_per_unit = (double)sh.clk.ticks_per_unit;
     const int64_t until = sh.run_until;
@@ -152,55 +158,49 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
             ++n_events;
             hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ tag_hash_bits(m))) * TRACE_HASH_MUL;
 
-            if (m == M_PROD) {
-                // producer body, producer_consumer.cpp:31-36
-                if (i < n_packets) {
-                    // q.put(now_seconds()): emplace, then wake (queue.hpp:48-53)
-                    if (count >= ring_cap) {
-                        status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-                    } else {
-                        uint32_t slot = head + count;
-                        slot = slot >= ring_cap ? slot - ring_cap : slot;
-                        if (FAST) sring[slot * THREADS] = (uint32_t)now;
-                        else gring[(uint64_t)slot * total_threads] = (int64_t)now;
-                        ++count;
-                        max_queue = count > max_queue ? count : max_queue;
-                        if (waiting) {  // wake: the parked consumer token {0 + now, 0, consumer}
-                            push(now, M_CONS);
-                            waiting = false;
-                        }
-                        draw = true;
-                        draw_index = i;
-                        ++i;
-                    }
-                } else {
-                    push(now, M_HANDLER);  // co_return: completion token carries the all_of handler
-                }
-            } else if (m == M_CONS) {
-                // consumer body, producer_consumer.cpp:38-54
-                if (cons_pc == 2) {
+            if (m == M_PROD || m == M_CONS) {
+                // Producer and consumer bodies (producer_consumer.cpp:31-54) written as one
+                // straight line of predicated updates, so lanes resuming different processes
+                // do not serialise.
+                const bool is_prod = m == M_PROD;
+                const bool put = is_prod && i < n_packets;       // q.put(now_seconds()), queue.hpp:48-53
+                const bool overflow = put && count >= ring_cap;
+                const bool empty = count == 0;
+                const bool pop = !is_prod && !empty;             // q.pop() succeeds, queue.hpp:58-65
+                const bool park = !is_prod && empty;             // ... or waits on queue.event_
+                if (!is_prod && cons_pc == 2) {
                     // total_latency += now_seconds() - x   (:52); (double)(ticks * prec.t) * conv
                     double now_s = (double)((int64_t)now * tick_mult) * sec_per_unit;
                     double x_s = (double)((int64_t)x_tick * tick_mult) * sec_per_unit;
                     total_latency += (now_s - x_s);
                 }
-                if (count == 0) {  // q.pop(): queue empty -> event_.wait(), no token scheduled
-                    waiting = true;
-                    cons_pc = 1;
-                } else {
-                    if (FAST) x_tick = sring[head * THREADS];
-                    else x_tick = (tick_t)gring[(uint64_t)head * total_threads];
-                    head = head + 1 >= ring_cap ? 0 : head + 1;
-                    --count;  // pop's own wake() finds no waiter: the producer never blocks
-                    ++k;
-                    if (k == n_packets) {
-                        push(now, M_HANDLER);  // avg_latency = total / n (:46) is formed at store time
-                    } else {
-                        draw = true;
-                        draw_index = k - 1;
-                        cons_pc = 2;
-                    }
+                // ring: the payload is the put tick
+                uint32_t slot = put ? head + count : head;
+                slot = slot >= ring_cap ? slot - ring_cap : slot;
+                if (put && !overflow) {
+                    if (FAST) sring[slot * THREADS] = (uint32_t)now;
+                    else gring[(uint64_t)slot * total_threads] = (int64_t)now;
                 }
+                if (pop) {
+                    if (FAST) x_tick = sring[slot * THREADS];
+                    else x_tick = (tick_t)gring[(uint64_t)slot * total_threads];
+                    head = head + 1 >= ring_cap ? 0 : head + 1;
+                }
+                count += (put ? 1u : 0u) - (pop ? 1u : 0u);
+                max_queue = count > max_queue ? count : max_queue;
+                if (overflow) status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+                // wake(): the parked consumer's token {0 + now, 0, consumer} goes in before the
+                // producer's own timeout (event.hpp:125-134); pop's wake() never finds a waiter
+                if (put && waiting) push(now, M_CONS);
+                waiting = park || (waiting && !put);
+                i += put ? 1u : 0u;
+                k += pop ? 1u : 0u;
+                const bool last = pop && k == n_packets;          // consumer returns (:45-48)
+                const bool ret = (is_prod && !put) || last;       // co_return -> completion token
+                if (ret) push(now, M_HANDLER);                    // ... carrying the all_of handler
+                draw = (put && !overflow) || (pop && !last);
+                draw_index = is_prod ? i - 1 : k - 1;
+                cons_pc = park ? 1u : (pop ? 2u : cons_pc);
             } else if (m == M_HANDLER) {
                 // all_of handler, any_of.ipp:9-26: output token inherits the child token's time
                 if (--remaining == 0) push(t, M_MAIN);
@@ -223,7 +223,10 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint3
             philox_block b = philox4x32_10(draw_index >> 1, ctr1, is_prod ? 1u : 2u, ctr3, key0, key1);
             const bool odd = draw_index & 1;
             uint64_t bits = ((uint64_t)(odd ? b.w[3] : b.w[1]) << 32) | (odd ? b.w[2] : b.w[0]);
-            double v = exponential_from_bits(bits, is_prod ? lambda : mu, table);
+            divisor rate;
+            rate.d = is_prod ? lambda.d : mu.d;
+            rate.inv = is_prod ? lambda.inv : mu.inv;
+            double v = exponential_from_bits(bits, rate, table);
             int64_t ticks = (int64_t)(v * ticks_per_unit);  // environment::real_to_sim
             if (FAST && ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks))
                 status |= CXXDES_B200_REP_TIME_RANGE;
@@ -311,21 +314,24 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
                              cudaStream_t stream, int *launches) {
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    mm1_rates rates;
+    rates.lambda = make_divisor(prm.lambda);
+    rates.mu = make_divisor(prm.mu);
     if (!plan.direct_global) {
         mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>
-            <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, sh, out, plan.smem_ring, nullptr,
+            <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, rates, sh, out, plan.smem_ring, nullptr,
                                                                     nullptr, nullptr, nullptr);
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // retry list -> fallback kernel; exits at once when the list is empty
         mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(
-            prm, sh, out, plan.fb_ring, fb_ring, sh.retry_list, sh.retry_count, fb_counter);
+            prm, rates, sh, out, plan.fb_ring, fb_ring, sh.retry_list, sh.retry_count, fb_counter);
         ++*launches;
         return cudaGetLastError();
     }
     mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(
-        prm, sh, out, plan.fb_ring, fb_ring, nullptr, nullptr, nullptr);
+        prm, rates, sh, out, plan.fb_ring, fb_ring, nullptr, nullptr, nullptr);
     ++*launches;
     return cudaGetLastError();
 }

@@ -34,6 +34,18 @@ rep_result run_model(int model, const void *params, const cxxdes_b200_clock &clo
             mm1_model m(*static_cast<const cxxdes_b200_mm1_params *>(params), clock, seed, rep);
             return finish(m, until, dump, dump_limit);
         }
+        case CXXDES_B200_MODEL_ALOHA: {
+            aloha_model m(*static_cast<const cxxdes_b200_aloha_params *>(params), clock, seed, rep);
+            return finish(m, until, dump, dump_limit);
+        }
+        case CXXDES_B200_MODEL_MMC: {
+            mmc_model m(*static_cast<const cxxdes_b200_mmc_params *>(params), clock, seed, rep);
+            return finish(m, until, dump, dump_limit);
+        }
+        case CXXDES_B200_MODEL_ARCHSIM: {
+            archsim_model m(*static_cast<const cxxdes_b200_archsim_params *>(params), seed, rep);
+            return finish(m, until, dump, dump_limit);
+        }
         default:
             throw std::runtime_error("port_oracle: unknown model");
     }

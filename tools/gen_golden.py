@@ -66,6 +66,74 @@ def mm1_cases(ref):
             "traces": traces}
 
 
+CLOCK_S_MS = {"unit": [1, 0], "precision": [1, 1]}
+CLOCK_S_S = {"unit": [1, 0], "precision": [1, 0]}
+
+
+def generic_cases(ref, model_id, params_cls, clock, grid, trace_grid):
+    """grid: list of (params tuple, seed, first_rep, n_reps, until)."""
+    clk = abi.Clock.of(tuple(clock["unit"]), tuple(clock["precision"]))
+    cases, traces = [], []
+    for fields, seed, first, reps, until in grid:
+        p = params_cls(*fields)
+        cols = ref.run(model_id, p, clk, seed, first, reps, threads=8, until=until)
+        cases.append({"params": list(fields), "seed": seed, "first_replication": first,
+                      "n_replications": reps, "run_until": until, "columns": columns_to_json(cols)})
+    for fields, seed, rep in trace_grid:
+        p = params_cls(*fields)
+        total, tr = ref.trace(model_id, p, clk, seed, rep, max_events=20000)
+        traces.append({"params": list(fields), "seed": seed, "replication": rep, "n_events": total, "trace": tr})
+    return {"clock": clock, "cases": cases, "traces": traces}
+
+
+def aloha_cases(ref):
+    grid = [
+        ((64, 50, 0.1, 3.0, 1.0, 1000.0, 0), 0x5EED, 0, 50, -1),      # BASELINE config 3: the 50-point sweep
+        ((3, 0, 2.0, 2.0, 1.0, 1000.0, 2), 0x5EED, 0, 8, -1),         # 21-event identity (SURVEY F.2)
+        ((16, 0, 1.0, 1.0, 1.0, 1000.0, 150), 0x5EED, 40, 16, -1),
+        ((64, 0, 3.0, 3.0, 1.0, 1000.0, 100), 1, 0, 8, -1),            # heavy load, many key ties
+        ((5, 0, 1.0, 1.0, 1.0, 1000.0, 0), 0x5EED, 0, 4, -1),          # zero packets
+        ((1, 0, 0.5, 0.5, 1.0, 1000.0, 20), 0x5EED, 0, 4, -1),         # a single station never collides
+        ((16, 0, 1.0, 1.0, 1.0, 1000.0, 100), 7, 0, 16, 30000),        # run_until(30 s)
+    ]
+    traces = [((3, 0, 2.0, 2.0, 1.0, 1000.0, 2), 0x5EED, 0), ((8, 0, 2.0, 2.0, 1.0, 1000.0, 5), 0x5EED, 3)]
+    out = generic_cases(ref, abi.MODEL_ALOHA, abi.AlohaParams, CLOCK_S_MS, grid, traces)
+    out["model"] = "aloha"
+    return out
+
+
+def mmc_cases(ref):
+    grid = [
+        ((9.0, 1.0, 0.5, 8, 0, 1000), 0x5EED, 0, 16, -1),              # BASELINE config 4 shape
+        ((6.0, 1.0, 0.5, 8, 0, 400), 0x5EED, 5, 16, -1),
+        ((12.0, 1.0, 0.5, 8, 0, 400), 0x5EED, 0, 16, -1),
+        ((2.0, 1.0, 0.5, 1, 0, 300), 2, 0, 16, -1),                    # c = 1
+        ((9.0, 1.0, 0.0, 8, 0, 200), 2, 0, 8, -1),                     # zero patience: timeout ties with the acquisition
+        ((9.0, 1.0, 0.5, 8, 0, 0), 2, 0, 4, -1),                       # no customers
+        ((9.0, 1.0, 0.5, 8, 0, 300), 3, 0, 16, 20000),                 # run_until(20 s)
+    ]
+    traces = [((9.0, 1.0, 0.5, 1, 0, 3), 0x5EED, 0), ((9.0, 1.0, 0.5, 2, 0, 12), 0x5EED, 1)]
+    out = generic_cases(ref, abi.MODEL_MMC, abi.MMCParams, CLOCK_S_MS, grid, traces)
+    out["model"] = "mmc"
+    return out
+
+
+def archsim_cases(ref):
+    grid = [
+        ((1, 10, 16, 32, 1, 0, 1024), 0x5EED, 0, 16, -1),              # BASELINE config 5 shape (sequential driver)
+        ((1, 10, 16, 32, 4, 0, 256), 0x5EED, 0, 16, -1),               # 4 requesters: mutex contention
+        ((1, 10, 4, 8, 4, 0, 300), 0x5EED, 100, 16, -1),
+        ((0, 0, 4, 8, 4, 0, 100), 0x5EED, 0, 16, -1),                  # zero latencies: everything ties at t = 0
+        ((1, 10, 2, 64, 3, 0, 100), 9, 0, 8, -1),
+        ((1, 10, 16, 32, 2, 0, 0), 9, 0, 4, -1),                       # no loads
+        ((1, 10, 16, 32, 4, 0, 200), 1, 0, 16, 500),                   # run_until(500)
+    ]
+    traces = [((1, 10, 16, 32, 2, 0, 2), 0x5EED, 0), ((1, 10, 2, 4, 3, 0, 4), 0x5EED, 2)]
+    out = generic_cases(ref, abi.MODEL_ARCHSIM, abi.ArchSimParams, CLOCK_S_S, grid, traces)
+    out["model"] = "archsim"
+    return out
+
+
 def main():
     ref = oracles.ref_oracle()
     if ref is None:
@@ -74,6 +142,9 @@ def main():
     out = mm1_cases(ref)
     (GOLDEN / "mm1_reference.json").write_text(json.dumps(out, indent=0, separators=(",", ":")))
     print("wrote", GOLDEN / "mm1_reference.json")
+    for name, fn in (("aloha", aloha_cases), ("mmc", mmc_cases), ("archsim", archsim_cases)):
+        (GOLDEN / f"{name}_reference.json").write_text(json.dumps(fn(ref), indent=0, separators=(",", ":")))
+        print("wrote", GOLDEN / f"{name}_reference.json")
 
 
 if __name__ == "__main__":

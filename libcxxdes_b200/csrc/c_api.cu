@@ -148,6 +148,36 @@ int plan(cxxdes_b200_ensemble *e) {
             }
             return CXXDES_B200_OK;
         }
+        case CXXDES_B200_MODEL_ALOHA: {
+            const cxxdes_b200_aloha_params &p = e->params.aloha;
+            if (p.num_stations < 1 || p.num_stations > 64)
+                return fail(CXXDES_B200_ERR_INVALID, "aloha: num_stations must be in [1, 64]");
+            if (!(p.lambda_begin > 0.0f) || !(p.frame_time >= 0.0f))
+                return fail(CXXDES_B200_ERR_INVALID, "aloha: lambda must be > 0 and frame_time >= 0");
+            if (p.packets_per_station >= (1ULL << 32))
+                return fail(CXXDES_B200_ERR_INVALID, "aloha: packets_per_station must be < 2^32");
+            if (aloha_smem_bytes(p.num_stations) > e->smem_optin)
+                return fail(CXXDES_B200_ERR_INVALID, "aloha: shared memory budget exceeded");
+            return CXXDES_B200_OK;
+        }
+        case CXXDES_B200_MODEL_MMC: {
+            const cxxdes_b200_mmc_params &p = e->params.mmc;
+            if (!(p.lambda > 0.0) || !(p.mu > 0.0) || !(p.patience >= 0.0) || p.servers < 1)
+                return fail(CXXDES_B200_ERR_INVALID, "mmc: rates must be > 0, patience >= 0, servers >= 1");
+            if (p.n_customers > 32000)
+                return fail(CXXDES_B200_ERR_INVALID, "mmc: n_customers must be <= 32000 (16-bit process ordinals)");
+            e->ring_bytes = (size_t)mmc_blocks(e->sm_count) * mmc_threads() * (p.n_customers ? p.n_customers : 1) *
+                            sizeof(uint64_t);
+            return CXXDES_B200_OK;
+        }
+        case CXXDES_B200_MODEL_ARCHSIM: {
+            if (!archsim_supported(e->params.arch))
+                return fail(CXXDES_B200_ERR_INVALID,
+                            "archsim: need 1..16 requesters, capacity 1..64, addr_space >= 1, latencies >= 0");
+            if (archsim_smem_bytes(e->params.arch) > e->smem_optin)
+                return fail(CXXDES_B200_ERR_INVALID, "archsim: shared memory budget exceeded");
+            return CXXDES_B200_OK;
+        }
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", c.model);
     }
@@ -179,6 +209,18 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                                            e->engine_threads, e->stream));
                 launches = 1;
             }
+            break;
+        case CXXDES_B200_MODEL_ALOHA:
+            CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->stream));
+            launches = 1;
+            break;
+        case CXXDES_B200_MODEL_MMC:
+            CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->stream));
+            launches = 1;
+            break;
+        case CXXDES_B200_MODEL_ARCHSIM:
+            CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream));
+            launches = 1;
             break;
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);

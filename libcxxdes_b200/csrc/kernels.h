@@ -28,6 +28,23 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                              cudaStream_t stream, int *launches);
 cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
+// ---- ALOHA (models_aloha.cu) ----
+size_t aloha_smem_bytes(uint32_t num_stations);
+cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
+                         int sm_count, size_t smem_optin, cudaStream_t stream);
+
+// ---- M/M/c with balking (models_mmc.cu) ----
+int mmc_blocks(int sm_count);
+int mmc_threads();
+cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
+                       uint64_t *customer_state, int sm_count, cudaStream_t stream);
+
+// ---- memory hierarchy (models_archsim.cu) ----
+bool archsim_supported(const cxxdes_b200_archsim_params &p);
+size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p);
+cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
+                           int sm_count, cudaStream_t stream);
+
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);
 cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_accumulators *device_acc,

@@ -1,0 +1,238 @@
+// models_archsim.cu -- memory-hierarchy model (examples/basic_arch_sim.cpp:13-110) on the device engine.
+//
+// k requester processes issue loads to mem2{latency, capacity} backed by mem1{latency}.  Each
+// memory::load is a coroutine (start + completion tokens) whose body runs inside
+// _Co_with(mtx_) -- a second coroutine (co_with.ipp:27-35) that acquires the level's sync::mutex
+// (mutex.hpp:31-109), runs the body and releases, waking every waiter.  With several requesters
+// the mutex contention and wake storms are part of the trace.
+//
+// Token targets: co_main 0, requester q = 1 + q, mem2.load = 0x100 + q, its _Co_with = 0x8100 + q,
+// mem1.load = 0x200 + q, its _Co_with = 0x8200 + q.  All priorities are 0.
+// The block store is the model's (user code): an ordered array, eviction = least last_access,
+// lowest position on ties, erase keeps order (same rule as the oracle's model).
+#include "device/models_common.cuh"
+#include "kernels.h"
+
+namespace cxb {
+
+namespace {
+
+constexpr int ARCH_THREADS = 128;
+constexpr int ARCH_MAX_REQ = 16;
+constexpr int ARCH_MAX_CAP = 64;
+
+}  // namespace
+
+__global__ void __launch_bounds__(ARCH_THREADS)
+archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char *cursor = smem;
+    const int K = (int)prm.n_requesters;
+    const int CAP = (int)prm.l2_capacity;
+    const int heap_cap = K + 3;
+    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
+    lane_array<int64_t> blk_last = carve<int64_t>(cursor, CAP);
+    lane_array<int64_t> t1 = carve<int64_t>(cursor, K);
+    lane_array<int64_t> stamp2 = carve<int64_t>(cursor, K);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
+    lane_array<uint32_t> blk_addr = carve<uint32_t>(cursor, CAP);
+    lane_array<uint32_t> loop_j = carve<uint32_t>(cursor, K);
+    lane_array<uint32_t> cur_addr = carve<uint32_t>(cursor, K);
+    lane_array<uint32_t> pcs = carve<uint32_t>(cursor, K);  // byte 0 requester, 1 load2, 2 with2, 3: with1 (low nibble) | load1 (high nibble)
+    lane_array<uint32_t> w2who = carve<uint32_t>(cursor, K);
+    lane_array<int32_t> w2lat = carve<int32_t>(cursor, K);
+    lane_array<uint32_t> w1who = carve<uint32_t>(cursor, K);
+    lane_array<int32_t> w1lat = carve<int32_t>(cursor, K);
+
+    auto get_pc = [&](int q, int which) -> uint32_t { return (pcs[q] >> (4 * which)) & 0xF; };
+    auto set_pc = [&](int q, int which, uint32_t v) { pcs[q] = (pcs[q] & ~(0xFu << (4 * which))) | (v << (4 * which)); };
+    enum { PC_REQ = 0, PC_LOAD2 = 1, PC_WITH2 = 2, PC_LOAD1 = 3, PC_WITH1 = 4 };
+
+    uint64_t rep;
+    while (steal(sh, rep)) {
+        const uint64_t grep = sh.first_replication + rep;
+        stream_addr addr;
+        addr.seed = sh.seed;
+        addr.replication = grep;
+
+        environment env;
+        env.init(hkey, htag, heap_cap);
+        wait_list wait2, wait1;  // mutex::event_ of mem2 / mem1
+        wait2.init(w2who, w2lat, K);
+        wait1.init(w1who, w1lat, K);
+        bool owned2 = false, owned1 = false;
+        int n_blocks = 0;
+        uint32_t main_pc = 0;
+        any_all all;
+        double total_latency = 0.0;
+        uint64_t hits = 0, misses = 0;
+        for (int q = 0; q < K; ++q) {
+            pcs[q] = 0;
+            loop_j[q] = 0;
+        }
+
+        env.schedule(0, 0, make_tag(0));
+
+        while (env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until)) {
+            token t = env.step_pop();
+            const uint32_t target = tag_target(t.tag);
+            if (tag_handler_plus1(t.tag)) {
+                all.invoke(env, t);
+            } else if (target == 0) {
+                if (main_pc == 0) {
+                    // all_of.range(requesters): bind in order, one handler on the completion tokens
+                    for (int q = 0; q < K; ++q) env.schedule(env.now, 0, make_tag(1 + q));
+                    all.arm(true, (uint32_t)K, (uint32_t)K);
+                    main_pc = 1;
+                } else {
+                    env.schedule(env.now, 0, make_tag(TAG_NO_TARGET));
+                }
+            } else if (target != TAG_NO_TARGET) {
+                if (target < 0x100) {
+                    // ---- requester q: for j < n_loads { t1 = now; co_await mem2.load(addr); total += now - t1 } ----
+                    const int q = (int)target - 1;
+                    uint32_t j = loop_j[q];
+                    if (get_pc(q, PC_REQ) == 1) {
+                        total_latency += (double)(env.now - t1[q]);
+                        loop_j[q] = ++j;
+                    }
+                    if (j < prm.n_loads) {
+                        addr.stream = target;
+                        cur_addr[q] = (uint32_t)(stream_draw_bits(addr, j) % prm.addr_space);
+                        t1[q] = env.now;
+                        set_pc(q, PC_LOAD2, 0);
+                        env.schedule(env.now, 0, make_tag(0x100 + q));  // start(mem2.load); completion targets the requester
+                        set_pc(q, PC_REQ, 1);
+                    } else {
+                        env.schedule(env.now, 0, make_tag(0, 1));  // co_return -> completion with the all_of handler
+                    }
+                } else {
+                    const int q = (int)(target & 0xFF);
+                    const bool is_with = (target & 0x8000u) != 0;
+                    const int lvl = (target & 0x200u) ? 1 : 2;
+                    if (!is_with) {
+                        // ---- memory::load up to the _Co_with (basic_arch_sim.cpp:21-24) ----
+                        const int which = lvl == 2 ? PC_LOAD2 : PC_LOAD1;
+                        if (get_pc(q, which) == 0) {
+                            if (lvl == 2) stamp2[q] = env.now;  // timestamp = env.now()
+                            set_pc(q, lvl == 2 ? PC_WITH2 : PC_WITH1, 0);
+                            env.schedule(env.now, 0, make_tag(target | 0x8000u));  // start(_Co_with coroutine)
+                            set_pc(q, which, 1);
+                        } else {
+                            // load returns: completion resumes the awaiter (requester, or mem2's _Co_with)
+                            env.schedule(env.now, 0, make_tag(lvl == 2 ? 1 + q : 0x8100 + q));
+                        }
+                    } else {
+                        // ---- operator+(mutex&, body): acquire; body(); release  (co_with.ipp:27-33) ----
+                        const int which = lvl == 2 ? PC_WITH2 : PC_WITH1;
+                        bool &owned = lvl == 2 ? owned2 : owned1;
+                        wait_list &waiters = lvl == 2 ? wait2 : wait1;
+                        const int64_t latency = lvl == 2 ? prm.l2_latency : prm.l1_latency;
+                        const uint32_t pc = get_pc(q, which);
+                        if (pc == 0) {
+                            if (owned) {
+                                waiters.wait(env, target, 0);  // mutex::acquire blocks (mutex.hpp:91-99)
+                            } else {
+                                owned = true;
+                                bool miss = false;
+                                if (lvl == 2) {
+                                    const uint32_t a = cur_addr[q];
+                                    bool found = false;
+                                    for (int b = 0; b < n_blocks; ++b) found |= blk_addr[b] == a;
+                                    miss = !found;
+                                    if (miss) {
+                                        ++misses;
+                                        if (n_blocks == CAP) {
+                                            // evict: least last_access, lowest position on ties; erase keeps order
+                                            int victim = 0;
+                                            int64_t best = blk_last[0];
+                                            for (int b = 1; b < n_blocks; ++b) {
+                                                int64_t v = blk_last[b];
+                                                if (v < best) { best = v; victim = b; }
+                                            }
+                                            for (int b = victim; b + 1 < n_blocks; ++b) {
+                                                blk_addr[b] = blk_addr[b + 1];
+                                                blk_last[b] = blk_last[b + 1];
+                                            }
+                                            --n_blocks;
+                                        }
+                                    } else {
+                                        ++hits;
+                                    }
+                                }
+                                if (miss) {
+                                    set_pc(q, PC_LOAD1, 0);
+                                    env.schedule(env.now, 0, make_tag(0x200 + q));  // co_await next_->load(addr)
+                                    set_pc(q, which, 1);
+                                } else {
+                                    env.schedule(env.now + latency, 0, make_tag(target));  // co_await timeout(latency_)
+                                    set_pc(q, which, 2);
+                                }
+                            }
+                        } else if (pc == 1) {
+                            env.schedule(env.now + latency, 0, make_tag(target));
+                            set_pc(q, which, 2);
+                        } else {
+                            if (lvl == 2) {
+                                // blocks_[addr].last_access = timestamp
+                                const uint32_t a = cur_addr[q];
+                                const int64_t ts = stamp2[q];
+                                bool found = false;
+                                for (int b = 0; b < n_blocks; ++b)
+                                    if (!found && blk_addr[b] == a) { blk_last[b] = ts; found = true; }
+                                if (!found) {
+                                    blk_addr[n_blocks] = a;
+                                    blk_last[n_blocks] = ts;
+                                    ++n_blocks;
+                                }
+                            }
+                            owned = false;      // handle.release(): owned_ = false; wake (mutex.hpp:70-79)
+                            waiters.wake(env);
+                            env.schedule(env.now, 0, make_tag(target & 0x7FFFu));  // _Co_with returns -> resumes load
+                        }
+                    }
+                }
+            }
+            if (env.status) break;
+        }
+        if (sh.run_until >= 0) {
+            if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
+            env.now = env.now > sh.run_until ? env.now : sh.run_until;
+        }
+        rep_out o;
+        o.end_time = env.now;
+        o.n_events = env.n_events;
+        o.trace_hash = env.hash;
+        o.status = env.status;
+        o.f64[0] = total_latency;
+        o.f64[1] = 0.0;
+        o.i64[0] = (int64_t)hits;
+        o.i64[1] = (int64_t)misses;
+        store_result(out, rep, o);
+    }
+}
+
+bool archsim_supported(const cxxdes_b200_archsim_params &p) {
+    return p.n_requesters >= 1 && p.n_requesters <= ARCH_MAX_REQ && p.l2_capacity >= 1 &&
+           p.l2_capacity <= ARCH_MAX_CAP && p.addr_space >= 1 && p.l2_latency >= 0 && p.l1_latency >= 0 &&
+           p.n_loads < (1ULL << 32);
+}
+
+size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p) {
+    const size_t k = p.n_requesters, cap = p.l2_capacity;
+    return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * 12 + k * (8 + 8 + 4 + 4 + 4 + 16));
+}
+
+cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
+                           int sm_count, cudaStream_t stream) {
+    const size_t smem = archsim_smem_bytes(prm);
+    cudaError_t e = cudaFuncSetAttribute(archsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    archsim_kernel<<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
+    return cudaGetLastError();
+}
+
+}  // namespace cxb

@@ -1,0 +1,188 @@
+// models_mmc.cu -- M/M/c with balking customers on the device engine.
+//
+// The model is written on the reference's primitives: sync::resource
+// (resource.hpp:37-100 = semaphore{c, c}, semaphore.hpp:58-78, over one sync::event), async
+// (async.ipp:21-28) and any_of (any_of.ipp:3-92).  Everything observable is reproduced: every
+// down()/up() wakes ALL waiters (thundering herd, event.hpp:125-134), any_of never cancels the
+// loser (its token still pops as a handler event), async leaves a null-target completion that
+// pops as a no-op.
+//
+// Processes / token targets: co_main 0, source 1, customer i = 2 + 2i, acquire_proc i = 3 + 2i.
+// A handler token always targets the customer whose any_of owns it, so the handler is found
+// from the target.  Per-customer state is one 64-bit word in global memory laid out
+// [customer][thread] (lanes walk the customers roughly in step, so accesses coalesce).
+#include "device/models_common.cuh"
+#include "kernels.h"
+
+namespace cxb {
+
+namespace {
+
+constexpr int MMC_THREADS = 96;
+constexpr int MMC_HEAP = 96;
+constexpr int MMC_WAITERS = 96;
+
+// customer word: bits 0-1 pc, 2 balked, 3 acquire_proc complete, 4 any_of armed, 5-6 remaining,
+// 16.. tick of t0 = now_seconds() at arrival (a pure function of the tick)
+constexpr uint64_t C_PC = 3, C_BALKED = 4, C_ACQ_DONE = 8, C_ARMED = 16, C_REM_SHIFT = 5, C_REM = 3ULL << 5;
+constexpr int C_T0_SHIFT = 16;
+
+}  // namespace
+
+__global__ void __launch_bounds__(MMC_THREADS)
+mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    stage_log_table(table, sh.log_table);
+    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, MMC_HEAP);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, MMC_HEAP);
+    lane_array<uint32_t> wwho = carve<uint32_t>(cursor, MMC_WAITERS);
+    lane_array<int32_t> wlat = carve<int32_t>(cursor, MMC_WAITERS);
+
+    const uint64_t total_threads = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t *cust = cust_base + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const uint64_t n = prm.n_customers;
+    const int64_t patience_ticks = real_to_sim(prm.patience, sh.clk);  // env.timeout(patience)
+    const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
+    const uint32_t NOOP_TAG = make_tag(TAG_NO_TARGET);
+
+    uint64_t rep;
+    while (steal(sh, rep)) {
+        const uint64_t grep = sh.first_replication + rep;
+        stream_addr addr;
+        addr.seed = sh.seed;
+        addr.replication = grep;
+
+        environment env;
+        env.init(hkey, htag, MMC_HEAP);
+        wait_list waiters;  // the semaphore's event
+        waiters.init(wwho, wlat, MMC_WAITERS);
+        uint64_t value = prm.servers;  // semaphore{c, c}
+        uint64_t i = 0, served = 0, balked = 0;
+        uint32_t main_pc = 0, source_pc = 0;
+        double total_wait = 0.0;
+        for (uint64_t c = 0; c < n; ++c) cust[c * total_threads] = 0;
+
+        env.schedule(0, 0, make_tag(0));  // environment::bind(co_main)
+
+        while (env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until)) {
+            token t = env.step_pop();
+            const uint32_t target = tag_target(t.tag);
+            if (tag_handler_plus1(t.tag)) {
+                // any_of handler of customer (target - 2) / 2: any_of.ipp:9-26
+                uint64_t *w = &cust[(uint64_t)((target - 2) >> 1) * total_threads];
+                uint64_t s = *w;
+                uint64_t remaining = ((s & C_REM) >> C_REM_SHIFT) - 1;
+                s = (s & ~C_REM) | (remaining << C_REM_SHIFT);
+                if ((s & C_ARMED) && remaining < 2) {
+                    env.schedule(key_time(t.key), key_prio(t.key), make_tag(target));  // output token
+                    s &= ~C_ARMED;
+                }
+                *w = s;
+            } else if (target == 0) {
+                if (main_pc == 0) {
+                    env.schedule(env.now, 0, make_tag(1));  // co_await source(): start token; completion targets main
+                    main_pc = 1;
+                } else {
+                    env.schedule(env.now, 0, NOOP_TAG);
+                }
+            } else if (target == 1) {
+                // source: for i < n { co_await async(customer(i)); co_await env.timeout(arr()); }
+                if (source_pc == 1) ++i;
+                if (i < n) {
+                    env.schedule(env.now, 0, make_tag((uint32_t)(2 + 2 * i)));  // async: start token (async.ipp:21-28)
+                    addr.stream = 1;
+                    const double a = exponential(addr, i, d_lambda, table);
+                    env.schedule(env.now + real_to_sim(a, sh.clk), 0, make_tag(1));
+                    source_pc = 1;
+                } else {
+                    env.schedule(env.now, 0, make_tag(0));  // source returns -> completion resumes co_main
+                }
+            } else if (target != TAG_NO_TARGET) {
+                const uint64_t id = (uint64_t)(target - 2) >> 1;
+                uint64_t *w = &cust[id * total_threads];
+                uint64_t s = *w;
+                if ((target & 1) == 0) {
+                    // ---- customer(id) ----
+                    const uint64_t pc = s & C_PC;
+                    if (pc == 0) {
+                        // t0 = now_seconds(); any_of(acquire_proc, env.timeout(patience))
+                        s = ((uint64_t)env.now << C_T0_SHIFT) | 1 | C_ARMED | (2ULL << C_REM_SHIFT);
+                        env.schedule(env.now, 0, make_tag(target + 1));                   // await_bind: start(acquire_proc)
+                        env.schedule(env.now + patience_ticks, 0, make_tag(target, 1));  // await_suspend: timeout + handler
+                    } else if (pc == 1) {
+                        if (!(s & C_ACQ_DONE)) {
+                            s = (s & ~C_PC) | 3 | C_BALKED;  // balked: co_return
+                            ++balked;
+                            env.schedule(env.now, 0, NOOP_TAG);  // async's null-target completion
+                        } else {
+                            const double t0 = sim_to_seconds((int64_t)(s >> C_T0_SHIFT), sh.clk);
+                            total_wait += sim_to_seconds(env.now, sh.clk) - t0;
+                            addr.stream = target;
+                            const double svc = exponential(addr, 0, d_mu, table);
+                            env.schedule(env.now + real_to_sim(svc, sh.clk), 0, make_tag(target));
+                            s = (s & ~C_PC) | 2;
+                        }
+                    } else {
+                        // release: semaphore::up -> ++value; wake  (semaphore.hpp:58-66)
+                        ++value;
+                        waiters.wake(env);
+                        ++served;
+                        s = (s & ~C_PC) | 3;
+                        env.schedule(env.now, 0, NOOP_TAG);
+                    }
+                } else {
+                    // ---- acquire_proc(id): st.h = co_await servers.acquire(); if (balked) release ----
+                    if (value == 0) {
+                        waiters.wait(env, target, 0);  // semaphore::down blocks (semaphore.hpp:70-78)
+                    } else {
+                        --value;
+                        waiters.wake(env);  // down() wakes every waiter even though it consumed a unit
+                        if (s & C_BALKED) {
+                            ++value;        // late acquisition is released at once
+                            waiters.wake(env);
+                        }
+                        s |= C_ACQ_DONE;
+                        env.schedule(env.now, 0, make_tag(target - 1, 1));  // completion token with the any_of handler
+                    }
+                }
+                *w = s;
+            }
+            if (env.status) break;
+        }
+        if (sh.run_until >= 0) {
+            if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
+            env.now = env.now > sh.run_until ? env.now : sh.run_until;
+        }
+        rep_out o;
+        o.end_time = env.now;
+        o.n_events = env.n_events;
+        o.trace_hash = env.hash;
+        o.status = env.status;
+        o.f64[0] = total_wait;
+        o.f64[1] = 0.0;
+        o.i64[0] = (int64_t)served;
+        o.i64[1] = (int64_t)balked;
+        store_result(out, rep, o);
+    }
+}
+
+size_t mmc_smem_bytes() {
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
+           (size_t)MMC_THREADS * (MMC_HEAP * (8 + 4) + MMC_WAITERS * (4 + 4));
+}
+
+int mmc_blocks(int sm_count) { return sm_count; }
+int mmc_threads() { return MMC_THREADS; }
+
+cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
+                       uint64_t *customer_state, int sm_count, cudaStream_t stream) {
+    const size_t smem = mmc_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(mmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmc_kernel<<<mmc_blocks(sm_count), MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state);
+    return cudaGetLastError();
+}
+
+}  // namespace cxb

@@ -1,0 +1,95 @@
+"""GPU parity tests (B200) for ALOHA, M/M/c with balking and the memory-hierarchy model: the CUDA
+path through the C ABI vs the reference's golden vectors and the CPU oracle, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util
+import oracles
+import libcxxdes_b200 as L
+from libcxxdes_b200 import abi
+from model_cases import MODELS, N_GOLDEN_CASES, clock_of, clock_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(params, n_reps, clock, seed=0x5EED, first=0, until=-1, strict=True):
+    ens = L.Ensemble(params, n_reps, seed=seed, first_replication=first)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    if until < 0:
+        ens.run()
+    else:
+        ens.run_until(until)
+    cols = ens.fetch(strict=strict)
+    acc, _ = ens.reduce()
+    ens.close()
+    return cols, acc
+
+
+@pytest.mark.parametrize("idx", range(N_GOLDEN_CASES))
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_gpu_matches_reference_golden(built, name, idx):
+    model, cls, fname = MODELS[name]
+    g = golden_util.load(fname)
+    case = g["cases"][idx]
+    got, _ = run_gpu(cls(*case["params"]), case["n_replications"], clock_pairs(g), seed=case["seed"],
+                     first=case["first_replication"], until=case["run_until"], strict=False)
+    assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(case), what=f"{name} golden {idx}")
+
+
+@pytest.mark.parametrize("name,fields,n_reps", [
+    ("aloha", (64, 50, 0.1, 3.0, 1.0, 100.0, 0), 2000),      # the offered-load sweep, 64 stations
+    ("aloha", (24, 0, 1.5, 1.5, 1.0, 1000.0, 60), 1024),
+    ("aloha", (64, 0, 3.0, 3.0, 1.0, 1000.0, 40), 512),      # heavy load: many key ties in a 64-entry heap
+    ("mmc", (9.0, 1.0, 0.5, 8, 0, 400), 1024),
+    ("mmc", (12.0, 1.0, 0.5, 8, 0, 300), 1024),
+    ("mmc", (3.0, 1.0, 0.2, 2, 0, 300), 512),
+    ("archsim", (1, 10, 16, 32, 1, 0, 1024), 1024),          # the shipped sequential driver
+    ("archsim", (1, 10, 16, 32, 4, 0, 256), 1024),           # 4 requesters: mutex contention
+    ("archsim", (0, 0, 4, 8, 4, 0, 100), 512),               # zero latencies: everything ties
+    ("archsim", (2, 7, 3, 16, 5, 0, 120), 512)])
+def test_gpu_matches_oracle(port, name, fields, n_reps):
+    model, cls, fname = MODELS[name]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    got, acc = run_gpu(p, n_reps, clock_pairs(g), seed=0xFEED, first=17)
+    want = port.run(model, p, clock_of(g), 0xFEED, 17, n_reps, threads=os.cpu_count())
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what=f"{name} {fields}")
+    assert acc.n_events == int(want.n_events.sum()) and acc.n_errors == 0
+    assert acc.trace_hash_sum == int(want.trace_hash.sum(dtype=np.uint64))
+    assert acc.i64_sum[0] == int(want.i64[0].sum()) and acc.i64_sum[1] == int(want.i64[1].sum())
+    assert abs(acc.f64_sum[0] - want.f64[0].sum()) <= 1e-12 * max(1.0, abs(want.f64[0].sum()))
+
+
+def test_aloha_full_size_properties(built):
+    """BASELINE config 3 shape at reduced replication count: event identity per sweep step and the
+    pure-ALOHA throughput curve S = G exp(-2G)."""
+    p = abi.AlohaParams(64, 50, 0.1, 3.0, 1.0, 1000.0, 0)
+    n_reps = 1000
+    got, _ = run_gpu(p, n_reps, ((1, L.SECONDS), (1, L.MILLISECONDS)))
+    assert not got.status.any()
+    pps = got.i64[1]
+    assert (got.n_events == (2 * 64 * pps + 2 * 64 + 3).astype(np.uint64)).all()
+    for step in (2, 10, 25, 49):
+        sel = np.arange(n_reps) % 50 == step
+        G = got.f64[1][sel][0]
+        assert abs(got.f64[0][sel].mean() - G * np.exp(-2 * G)) < 0.02
+
+
+def test_mmc_conservation(built):
+    p = abi.MMCParams(9.0, 1.0, 0.5, 8, 0, 1000)
+    got, _ = run_gpu(p, 4096, ((1, L.SECONDS), (1, L.MILLISECONDS)))
+    assert not got.status.any()
+    assert (got.i64[0] + got.i64[1] == 1000).all()
+
+
+def test_invalid_model_parameters(built):
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(abi.AlohaParams(65, 0, 1.0, 1.0, 1.0, 1000.0, 10), 4).run()
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(abi.MMCParams(9.0, 1.0, 0.5, 0, 0, 10), 4).run()
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(abi.ArchSimParams(1, 10, 16, 32, 17, 0, 10), 4).run()

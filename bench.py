@@ -172,14 +172,6 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class DevicePointerView:
-    """Zero-copy torch view of a device buffer owned by the library (accumulator struct)."""
-
-    def __init__(self, ptr, n_int64):
-        self.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -193,7 +185,7 @@ def run_b200(a):
     import torch.distributed as dist
 
     import libcxxdes_b200 as L
-    from libcxxdes_b200 import abi
+    from libcxxdes_b200 import abi, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,12 +205,11 @@ def run_b200(a):
     # NCCL (torch.distributed) see the same stream the kernels run on
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
-    ens = L.Ensemble(params, R, seed=SEED, first_replication=rank * R, device=local_rank,
+    first_rep, _ = sharding.weak_shard_of(rank, R)
+    ens = L.Ensemble(params, R, seed=SEED, first_replication=first_rep, device=local_rank,
                      stream=stream.cuda_stream)
     ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    n_acc_words = C.sizeof(abi.Accumulators) // 8
-    n_int_words = 5 + abi.N_I64
 
     def barrier():
         if world > 1:
@@ -231,9 +222,8 @@ def run_b200(a):
         ens.run()
         dev_acc = ens.reduce_async()
         if world > 1:
-            view = torch.as_tensor(DevicePointerView(dev_acc, n_acc_words), device="cuda")
-            dist.all_reduce(view[:n_int_words], op=dist.ReduceOp.SUM)
-            dist.all_reduce(view[n_int_words:].view(torch.float64), op=dist.ReduceOp.SUM)
+            view = torch.as_tensor(sharding.DevicePointerView(dev_acc), device="cuda")
+            sharding.all_reduce_words(view, dist)
         return dev_acc
 
     for _ in range(a.warmup):

@@ -10,9 +10,10 @@
 // unchanged by the nvcc device code, the host layer and the oracle.
 //
 // Stream addressing (one 128-bit Philox block yields two 64-bit draws):
-//   key     = { lo32(seed),            lo32(replication) }
-//   counter = { lo32(draw >> 1),       hi32(seed) ^ hi32(draw >> 1),
-//               stream id,             hi32(replication) }
+//   key     = { lo32(seed), hi32(seed) }                 the same for every replication, so the ten
+//                                                         round keys are warp-uniform on the device
+//   counter = { lo32(draw >> 1), stream id | hi32(draw >> 1) << 16,
+//               lo32(replication), hi32(replication) }    stream id < 2^16, draw < 2^49
 //   draw d  = words {0,1} of the block if d is even, words {2,3} if d is odd.
 #pragma once
 #include <stdint.h>
@@ -61,6 +62,41 @@ CXB_HD philox_block philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
     return b;
 }
 
+// The ten round keys k + j*W of one 64-bit key, precomputed.  The ensemble uses the seed as the
+// Philox key, so on the device the schedule is formed once on the host and read from the constant
+// bank; philox4x32_10_scheduled(c, schedule_of(k)) == philox4x32_10(c, k) by construction.
+struct philox_schedule {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+inline philox_schedule philox_schedule_of(uint32_t k0, uint32_t k1) {
+    philox_schedule s;
+    for (int r = 0; r < 10; ++r) {
+        s.k0[r] = k0 + (uint32_t)r * PHILOX_W0;
+        s.k1[r] = k1 + (uint32_t)r * PHILOX_W1;
+    }
+    return s;
+}
+
+CXB_HD philox_block philox4x32_10_scheduled(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            const philox_schedule &s) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(PHILOX_M0, c0, hi0, lo0);
+        philox_mulhilo(PHILOX_M1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ s.k0[r];
+        uint32_t n2 = hi0 ^ c3 ^ s.k1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    philox_block b;
+    b.w[0] = c0; b.w[1] = c1; b.w[2] = c2; b.w[3] = c3;
+    return b;
+}
+
 // Address of one Philox block inside the ensemble's random stream.
 struct stream_addr {
     uint64_t seed;
@@ -70,11 +106,11 @@ struct stream_addr {
 
 CXB_HD philox_block stream_block(const stream_addr &a, uint64_t block_index) {
     return philox4x32_10((uint32_t)block_index,
-                         (uint32_t)(a.seed >> 32) ^ (uint32_t)(block_index >> 32),
-                         a.stream,
+                         a.stream | ((uint32_t)(block_index >> 32) << 16),
+                         (uint32_t)a.replication,
                          (uint32_t)(a.replication >> 32),
                          (uint32_t)a.seed,
-                         (uint32_t)a.replication);
+                         (uint32_t)(a.seed >> 32));
 }
 
 // 64 raw bits of draw number `draw` of the addressed stream.

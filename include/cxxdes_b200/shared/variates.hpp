@@ -64,6 +64,15 @@ CXB_HD double unit_complement_from_bits(uint64_t bits) {
     return 2.0 - one_plus_u;
 }
 
+// Series coefficients of log1p(r) - r = r^2 (c0 + c1 r + ... + c6 r^6), then ln2 split.  On the
+// device they live in constant memory so every DFMA takes its coefficient straight from the
+// constant bank (no per-use 64-bit immediate materialisation); same bits as the host literals.
+#define CXB_LOG_COEFS {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5}
+#if defined(__CUDACC__)
+static __device__ __constant__ double CXB_LOG_COEF_DEV[7] = CXB_LOG_COEFS;
+static __device__ __constant__ unsigned long long CXB_LN2_DEV[2] = {CXB_LN2_HI_BITS, CXB_LN2_LO_BITS};
+#endif
+
 // Natural logarithm for positive normal doubles (the engine only ever passes
 // w in [2^-52, 1]).  Table-driven: w = 2^k * z, z in [0.6875, 1.375),
 // r = z*invc - 1 (|r| < 2^-8; < 2^-7 next to 1.0 where c = 1), log(w) = k ln2 + logc +
@@ -79,20 +88,27 @@ CXB_HD double log_pos(double w, const Table *table) {
     const double z = bits_as_double(iz);
     const double invc = bits_as_double(table[i].invc_bits);
     const double logc = bits_as_double(table[i].logc_bits);
+#if defined(__CUDA_ARCH__)
+    const double *c = CXB_LOG_COEF_DEV;
+    const double ln2_hi = bits_as_double(CXB_LN2_DEV[0]), ln2_lo = bits_as_double(CXB_LN2_DEV[1]);
+#else
+    static const double c[7] = CXB_LOG_COEFS;
+    const double ln2_hi = bits_as_double(CXB_LN2_HI_BITS), ln2_lo = bits_as_double(CXB_LN2_LO_BITS);
+#endif
     const double r = fma_rn(z, invc, -1.0);
     const double kd = (double)k;
-    const double t = fma_rn(kd, bits_as_double(CXB_LN2_HI_BITS), logc);
+    const double t = fma_rn(kd, ln2_hi, logc);
     const double hi = t + r;
     const double lo = (t - hi) + r;
     const double r2 = r * r;
     // log1p(r) - r = r^2 * (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7 - r^6/8)
-    double p = fma_rn(r, -1.0 / 8.0, 1.0 / 7.0);
-    p = fma_rn(r, p, -1.0 / 6.0);
-    p = fma_rn(r, p, 1.0 / 5.0);
-    p = fma_rn(r, p, -1.0 / 4.0);
-    p = fma_rn(r, p, 1.0 / 3.0);
-    p = fma_rn(r, p, -0.5);
-    const double tail = fma_rn(kd, bits_as_double(CXB_LN2_LO_BITS), r2 * p);
+    double p = fma_rn(r, c[0], c[1]);
+    p = fma_rn(r, p, c[2]);
+    p = fma_rn(r, p, c[3]);
+    p = fma_rn(r, p, c[4]);
+    p = fma_rn(r, p, c[5]);
+    p = fma_rn(r, p, c[6]);
+    const double tail = fma_rn(kd, ln2_lo, r2 * p);
     return hi + (lo + tail);
 }
 

@@ -57,6 +57,7 @@ struct tick_traits<false> {
 
 struct mm1_rates {
     divisor lambda, mu;
+    philox_schedule keys;  // round keys of the seed, read from the constant bank inside the loop
 };
 
 template <bool FAST, int THREADS, int MIN_BLOCKS>
@@ -90,7 +91,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
     // ---- per-lane replication state, all in registers ----
     bool active = false, exhausted = false;
     uint64_t rep = 0;
-    uint32_t key0 = 0, key1 = 0, ctr1 = 0, ctr3 = 0;
+    uint32_t ctr2 = 0, ctr3 = 0;  // Philox counter words 2,3 = global replication id
     tick_t t0 = EMPTY, t1 = EMPTY, now = 0, x_tick = 0;
     uint32_t m0 = M_NOOP, m1 = M_NOOP;
     uint32_t i = 0, k = 0, head = 0, count = 0, max_queue = 0;
@@ -129,8 +130,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
             }
             if (got) {
                 const uint64_t grep = sh.first_replication + rep;
-                key0 = (uint32_t)sh.seed; key1 = (uint32_t)grep;
-                ctr1 = (uint32_t)(sh.seed >> 32); ctr3 = (uint32_t)(grep >> 32);
+                ctr2 = (uint32_t)grep; ctr3 = (uint32_t)(grep >> 32);
                 t0 = 0; m0 = M_MAIN;   // environment::bind(co_main): start token {0, 0, main}
                 t1 = EMPTY; m1 = M_NOOP;
                 now = 0; x_tick = 0;
@@ -170,8 +170,14 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
                 const bool park = !is_prod && empty;             // ... or waits on queue.event_
                 if (!is_prod && cons_pc == 2) {
                     // total_latency += now_seconds() - x   (:52); (double)(ticks * prec.t) * conv
-                    double now_s = (double)((int64_t)now * tick_mult) * sec_per_unit;
-                    double x_s = (double)((int64_t)x_tick * tick_mult) * sec_per_unit;
+                    double now_s, x_s;
+                    if (FAST && tick_mult == 1) {  // uniform branch; (double)(u32) is exact either way
+                        now_s = (double)(uint32_t)now * sec_per_unit;
+                        x_s = (double)(uint32_t)x_tick * sec_per_unit;
+                    } else {
+                        now_s = (double)((int64_t)now * tick_mult) * sec_per_unit;
+                        x_s = (double)((int64_t)x_tick * tick_mult) * sec_per_unit;
+                    }
                     total_latency += (now_s - x_s);
                 }
                 // ring: the payload is the put tick
@@ -220,7 +226,8 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
         if (draw) {
             // env.timeout(exponential()): the only expensive part, shared by both processes
             const bool is_prod = m == M_PROD;
-            philox_block b = philox4x32_10(draw_index >> 1, ctr1, is_prod ? 1u : 2u, ctr3, key0, key1);
+            // key = seed (warp-uniform round keys), counter = (block, stream, replication)
+            philox_block b = philox4x32_10_scheduled(draw_index >> 1, is_prod ? 1u : 2u, ctr2, ctr3, rates.keys);
             const bool odd = draw_index & 1;
             uint64_t bits = ((uint64_t)(odd ? b.w[3] : b.w[1]) << 32) | (odd ? b.w[2] : b.w[0]);
             divisor rate;
@@ -317,6 +324,7 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
     mm1_rates rates;
     rates.lambda = make_divisor(prm.lambda);
     rates.mu = make_divisor(prm.mu);
+    rates.keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
     if (!plan.direct_global) {
         mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>
             <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, rates, sh, out, plan.smem_ring, nullptr,

@@ -37,8 +37,8 @@ def test_stream_addressing(port):
                                      C.c_uint64(n), out.ctypes.data_as(C.c_void_p))
     for d in range(n):
         blk = d >> 1
-        w = _philox(port.lib, (blk & 0xFFFFFFFF, (seed >> 32) ^ (blk >> 32), stream, rep >> 32),
-                    (seed & 0xFFFFFFFF, rep & 0xFFFFFFFF))
+        w = _philox(port.lib, (blk & 0xFFFFFFFF, stream | ((blk >> 32) << 16), rep & 0xFFFFFFFF, rep >> 32),
+                    (seed & 0xFFFFFFFF, seed >> 32))
         lo, hi = (w[2], w[3]) if d & 1 else (w[0], w[1])
         assert int(out[d]) == (hi << 32) | lo
 

@@ -97,6 +97,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
     uint32_t i = 0, k = 0, head = 0, count = 0, max_queue = 0;
     uint32_t main_pc = 0, cons_pc = 0, remaining = 2;
     bool waiting = false;  // consumer parked in queue.event_ (event.hpp:136-139)
+    bool fast = false, cfirst = false, c_timeout = false;  // steady-state representation, see below
     double total_latency = 0.0;
     uint64_t n_events = 0, hash = TRACE_HASH_INIT;
     uint32_t status = 0;
@@ -137,6 +138,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
                 i = k = head = count = max_queue = 0;
                 main_pc = cons_pc = 0; remaining = 2;
                 waiting = false;
+                fast = cfirst = c_timeout = false;
                 total_latency = 0.0;
                 n_events = 0; hash = TRACE_HASH_INIT;
                 status = 0;
@@ -147,29 +149,42 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
         }
         if (!__any_sync(0xFFFFFFFFu, active)) break;
 
-        bool draw = false;
+        bool draw = false, is_prod = false;
         uint32_t draw_index = 0, m = M_NOOP;
-        if (active) {
-            // ---- environment::step, environment.ipp:117-146 ----
-            const tick_t t = t0;
-            m = m0;
-            t0 = t1; m0 = m1; t1 = EMPTY;           // pop_heap on <= 2 entries
-            now = t > now ? t : now;
-            ++n_events;
-            hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ tag_hash_bits(m))) * TRACE_HASH_MUL;
-
-            if (m == M_PROD || m == M_CONS) {
-                // Producer and consumer bodies (producer_consumer.cpp:31-54) written as one
-                // straight line of predicated updates, so lanes resuming different processes
-                // do not serialise.
-                const bool is_prod = m == M_PROD;
-                const bool put = is_prod && i < n_packets;       // q.put(now_seconds()), queue.hpp:48-53
-                const bool overflow = put && count >= ring_cap;
-                const bool empty = count == 0;
-                const bool pop = !is_prod && !empty;             // q.pop() succeeds, queue.hpp:58-65
-                const bool park = !is_prod && empty;             // ... or waits on queue.event_
-                if (!is_prod && cons_pc == 2) {
-                    // total_latency += now_seconds() - x   (:52); (double)(ticks * prec.t) * conv
+        // ---- steady state: exactly one producer token (t0) and at most one consumer token
+        // (t1, EMPTY while the consumer is parked in queue.event_).  With <= 2 entries the
+        // libstdc++ heap keeps the earlier push in front on equal keys, so the pick below is
+        // the pop order: `cfirst` says the consumer's token was pushed before the producer's.
+        // (Bitwise &,| on purpose: a short-circuit branch here would split the warp into a
+        // producer group and a consumer group that then run the body one after the other.)
+        const bool c_goes = (t1 != EMPTY) & ((t1 < t0) | ((t1 == t0) & cfirst));
+        const bool leave = c_goes ? ((count != 0) & (k + 1 == n_packets)) : (i == n_packets);
+        const bool do_fast = active & fast & !leave;
+        bool generic = active & !do_fast;
+        if (active & fast & leave) {
+            // the next event ends a process (co_return): rebuild the generic two-slot heap
+            const tick_t tp = t0, tc = t1;
+            waiting = tc == EMPTY;
+            t0 = c_goes ? tc : tp;
+            m0 = c_goes ? M_CONS : M_PROD;
+            t1 = c_goes ? tp : tc;
+            m1 = c_goes ? M_PROD : M_CONS;
+            cons_pc = c_timeout ? 2u : 1u;
+            fast = false;
+        }
+        __syncwarp();
+        if (do_fast) {
+            {
+                // environment::step (environment.ipp:117-146) for a producer/consumer token
+                const tick_t t = c_goes ? t1 : t0;
+                now = t;  // tokens are scheduled at now + d, d >= 0: time never runs backwards here
+                ++n_events;
+                hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ (c_goes ? tag_hash_bits(M_CONS) : tag_hash_bits(M_PROD)))) *
+                       TRACE_HASH_MUL;
+                is_prod = !c_goes;
+                m = c_goes ? M_CONS : M_PROD;
+                if (c_goes && c_timeout) {
+                    // total_latency += now_seconds() - x   (producer_consumer.cpp:52)
                     double now_s, x_s;
                     if (FAST && tick_mult == 1) {  // uniform branch; (double)(u32) is exact either way
                         now_s = (double)(uint32_t)now * sec_per_unit;
@@ -180,7 +195,59 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
                     }
                     total_latency += (now_s - x_s);
                 }
-                // ring: the payload is the put tick
+                const bool empty = count == 0;
+                const bool pop = c_goes && !empty;   // q.pop() succeeds (queue.hpp:58-65)
+                const bool park = c_goes && empty;   // ... or the consumer waits on queue.event_
+                const bool put = !c_goes;            // q.put(now_seconds()) (queue.hpp:48-53)
+                const bool overflow = put && count >= ring_cap;
+                uint32_t slot = put ? head + count : head;
+                slot = slot >= ring_cap ? slot - ring_cap : slot;
+                if (put && !overflow) {
+                    if (FAST) sring[slot * THREADS] = (uint32_t)now;
+                    else gring[(uint64_t)slot * total_threads] = (int64_t)now;
+                }
+                if (pop) {
+                    if (FAST) x_tick = sring[slot * THREADS];
+                    else x_tick = (tick_t)gring[(uint64_t)slot * total_threads];
+                    head = head + 1 >= ring_cap ? 0 : head + 1;
+                }
+                count += (put ? 1u : 0u) - (pop ? 1u : 0u);
+                max_queue = count > max_queue ? count : max_queue;
+                if (overflow) status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+                // wake(): a parked consumer gets its token {0 + now} before the producer's timeout
+                if (put && t1 == EMPTY) {
+                    t1 = now;
+                    c_timeout = false;
+                }
+                if (park) t1 = EMPTY;
+                i += put ? 1u : 0u;
+                k += pop ? 1u : 0u;
+                draw = (put && !overflow) || pop;
+                draw_index = is_prod ? i - 1 : k - 1;
+            }
+        }
+        if (generic) {
+            // ---- environment::step, environment.ipp:117-146 (start-up and wind-down events) ----
+            const tick_t t = t0;
+            m = m0;
+            t0 = t1; m0 = m1; t1 = EMPTY;           // pop_heap on <= 2 entries
+            now = t > now ? t : now;
+            ++n_events;
+            hash = (rotl64(hash, 5) ^ ((uint64_t)t ^ tag_hash_bits(m))) * TRACE_HASH_MUL;
+
+            if (m == M_PROD || m == M_CONS) {
+                // producer and consumer bodies, producer_consumer.cpp:31-54
+                is_prod = m == M_PROD;
+                const bool put = is_prod && i < n_packets;       // q.put(now_seconds()), queue.hpp:48-53
+                const bool overflow = put && count >= ring_cap;
+                const bool empty = count == 0;
+                const bool pop = !is_prod && !empty;             // q.pop() succeeds, queue.hpp:58-65
+                const bool park = !is_prod && empty;             // ... or waits on queue.event_
+                if (!is_prod && cons_pc == 2) {
+                    double now_s = (double)((int64_t)now * tick_mult) * sec_per_unit;
+                    double x_s = (double)((int64_t)x_tick * tick_mult) * sec_per_unit;
+                    total_latency += (now_s - x_s);  // :52
+                }
                 uint32_t slot = put ? head + count : head;
                 slot = slot >= ring_cap ? slot - ring_cap : slot;
                 if (put && !overflow) {
@@ -225,7 +292,6 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
 
         if (draw) {
             // env.timeout(exponential()): the only expensive part, shared by both processes
-            const bool is_prod = m == M_PROD;
             // key = seed (warp-uniform round keys), counter = (block, stream, replication)
             philox_block b = philox4x32_10_scheduled(draw_index >> 1, is_prod ? 1u : 2u, ctr2, ctr3, rates.keys);
             const bool odd = draw_index & 1;
@@ -235,14 +301,39 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
             rate.inv = is_prod ? lambda.inv : mu.inv;
             double v = exponential_from_bits(bits, rate, table);
             int64_t ticks = (int64_t)(v * ticks_per_unit);  // environment::real_to_sim
-            if (FAST && ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks))
+            if (FAST && ((uint64_t)ticks >= 0x7FFF0000ULL || now >= tick_traits<FAST>::LIMIT - (tick_t)ticks)) {
                 status |= CXXDES_B200_REP_TIME_RANGE;
-            else
+            } else if (fast) {
+                // the drawing process pushes last, so on an equal key the other one's token is in front
+                const tick_t due = now + (tick_t)ticks;
+                t0 = is_prod ? due : t0;
+                t1 = is_prod ? t1 : due;
+                cfirst = is_prod;
+                c_timeout = is_prod ? c_timeout : true;
+            } else {
                 push(now + (tick_t)ticks, m);
+            }
+        }
+
+        if (generic && status == 0 && main_pc == 1 && remaining == 2 && cons_pc != 0 && i >= 1 && i < n_packets &&
+            k < n_packets) {
+            // both processes are running and only their tokens are scheduled: enter the steady state
+            const bool prod_front = m0 == M_PROD && (t1 == EMPTY ? waiting : m1 == M_CONS);
+            const bool cons_front = m0 == M_CONS && m1 == M_PROD && t1 != EMPTY;
+            if (t0 != EMPTY && (prod_front || cons_front)) {
+                const tick_t tp = prod_front ? t0 : t1;
+                const tick_t tc = prod_front ? t1 : t0;
+                t0 = tp;
+                t1 = tc;
+                cfirst = cons_front;
+                c_timeout = cons_pc == 2;
+                fast = true;
+            }
         }
 
         // ---- end of this lane's replication? (environment::run / run_until, environment.ipp:179-196) ----
-        if (active && (status != 0 || t0 == EMPTY || (until >= 0 && (int64_t)t0 > until))) {
+        const tick_t next = fast && t1 < t0 ? t1 : t0;  // time of the next scheduled token
+        if (active && (status != 0 || next == EMPTY || (until >= 0 && (int64_t)next > until))) {
             active = false;
             if (FAST && (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE))) {
                 // hand the replication to the fallback kernel; its row is written there
@@ -251,7 +342,7 @@ mm1_fused_kernel(cxxdes_b200_mm1_params prm, mm1_rates rates, shard sh, device_c
             } else {
                 int64_t end = (int64_t)now;
                 if (until >= 0) {
-                    if (t0 != EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
+                    if (next != EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
                     end = end > until ? end : until;  // now_ = max(now_, t), environment.ipp:194
                 }
                 rep_out o;

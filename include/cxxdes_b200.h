@@ -58,7 +58,8 @@ enum {
     CXXDES_B200_MODEL_MM1 = 1,     /* examples/producer_consumer.cpp:9-59                  */
     CXXDES_B200_MODEL_ALOHA = 2,   /* examples/aloha.cpp:25-85                             */
     CXXDES_B200_MODEL_MMC = 3,     /* resource + any_of balking (examples/resource.cpp pattern) */
-    CXXDES_B200_MODEL_ARCHSIM = 4  /* examples/basic_arch_sim.cpp:13-110                   */
+    CXXDES_B200_MODEL_ARCHSIM = 4, /* examples/basic_arch_sim.cpp:13-110                   */
+    CXXDES_B200_MODEL_PROGRAM = 5  /* any model given as a process program (see below)     */
 };
 
 /* producer_consumer_example(lambda, mu, n_packets): examples/producer_consumer.cpp:10-20 */
@@ -108,6 +109,75 @@ typedef struct cxxdes_b200_archsim_params {
     uint64_t n_loads;
 } cxxdes_b200_archsim_params;
 
+/* ---- process programs: generic lowering of coroutine bodies -------------------------------
+ * A model that has no hand-written kernel is given as a *process program*: a static table of
+ * processes (coroutine<> objects: ordinal for the trace digest, .priority(), .latency(),
+ * .return_latency(), .return_priority() -- coroutine.ipp:106-176) and, per process, a straight
+ * list of operations, each the lowering of one reference awaitable.  One device kernel interprets
+ * the program for every replication.  Operation semantics (what is pushed, in which order) follow
+ * SURVEY 3.3; the citations name the reference code each one reproduces.                        */
+enum {
+    CXXDES_B200_OP_RETURN = 0,      /* co_return: completion tokens released (environment.ipp:321-348)        */
+    CXXDES_B200_OP_DELAY = 1,       /* co_await delay(imm) / timeout(imm) / yield(): timeout.ipp:21-32,180-182;
+                                       b = explicit priority, or CXXDES_B200_INHERIT                          */
+    CXXDES_B200_OP_UNTIL = 2,       /* co_await until(imm): ready if now >= imm (timeout.ipp:14-29)           */
+    CXXDES_B200_OP_DELAY_EXP = 3,   /* co_await env.timeout(exponential(rates[a])): stream = process ordinal  */
+    CXXDES_B200_OP_DELAY_REAL = 4,  /* co_await env.timeout(double): imm holds the bits of the double         */
+    CXXDES_B200_OP_FRESH = 5,       /* process a becomes a new, unstarted coroutine object again               */
+    CXXDES_B200_OP_AWAIT = 6,       /* co_await process a (coroutine.ipp:179-207, environment.ipp:281-307)     */
+    CXXDES_B200_OP_ASYNC = 7,       /* co_await async(process a): async.ipp:21-28                              */
+    CXXDES_B200_OP_ALL_OF = 8,      /* co_await all_of(children...): a = child count, children follow          */
+    CXXDES_B200_OP_ANY_OF = 9,      /* co_await any_of(children...)            (any_of.ipp:3-92,233-247)       */
+    CXXDES_B200_OP_CHILD_PROC = 10, /*   child: process a                                                      */
+    CXXDES_B200_OP_CHILD_DELAY = 11,/*   child: delay(imm), b = priority or INHERIT                            */
+    CXXDES_B200_OP_CHILD_UNTIL = 12,/*   child: until(imm)                                                     */
+    CXXDES_B200_OP_Q_PUT = 13,      /* co_await queue[a].put(now or reg): sync/queue.hpp:48-53; b=1 puts reg   */
+    CXXDES_B200_OP_Q_POP = 14,      /* reg = co_await queue[a].pop(): sync/queue.hpp:58-65                     */
+    CXXDES_B200_OP_SEM_DOWN = 15,   /* co_await semaphore[a].down(): sync/semaphore.hpp:70-78                  */
+    CXXDES_B200_OP_SEM_UP = 16,     /* co_await semaphore[a].up(): sync/semaphore.hpp:58-66                    */
+    CXXDES_B200_OP_MTX_ACQUIRE = 17,/* co_await mutex[a].acquire(): sync/mutex.hpp:91-99                       */
+    CXXDES_B200_OP_MTX_RELEASE = 18,/* co_await handle.release(): sync/mutex.hpp:70-79                         */
+    CXXDES_B200_OP_EV_WAIT = 19,    /* co_await event[a].wait(imm latency, b priority): sync/event.hpp:136-139 */
+    CXXDES_B200_OP_EV_WAKE = 20,    /* co_await event[a].wake(): sync/event.hpp:125-134                        */
+    CXXDES_B200_OP_LOOP = 21,       /* for (k = 0; k < imm; ++k) {: b = index of the op after the matching END */
+    CXXDES_B200_OP_END_LOOP = 22,   /* }: b = index of the first op of the body                                */
+    CXXDES_B200_OP_SET_REG_NOW = 23,/* reg = now()                                                              */
+    CXXDES_B200_OP_STAT_SECONDS = 24,/* f64[a] += now_seconds() - seconds(reg)   (producer_consumer.cpp:52)    */
+    CXXDES_B200_OP_STAT_TICKS = 25, /* f64[a] += (double)(now() - reg)                                          */
+    CXXDES_B200_OP_COUNT = 26,      /* i64[a] += imm                                                             */
+    CXXDES_B200_OP_MARK = 27        /* observation point (the prints of the reference examples): ++i64[0];
+                                       i64[1] = i64[1] * 1000003 + (now() * imm + b)   (wrapping)              */
+};
+#define CXXDES_B200_INHERIT INT32_MAX /* priority_consts::inherit (defs.ipp:35) in the 32-bit b field */
+
+typedef struct cxxdes_b200_op {
+    uint16_t code;
+    uint16_t a;
+    int32_t b;
+    int64_t imm;
+} cxxdes_b200_op;
+
+typedef struct cxxdes_b200_process {
+    uint32_t entry;          /* index of the first op of the body                                   */
+    uint32_t ordinal;        /* name in the trace digest and Philox stream id (< 2^16)             */
+    int64_t priority;        /* coroutine::priority(x); INT64_MAX = inherit from the awaiter        */
+    int64_t latency;         /* coroutine::latency(x): start token at now + latency                 */
+    int64_t return_latency;  /* coroutine::return_latency(x)                                        */
+    int64_t return_priority; /* coroutine::return_priority(x); INT64_MAX = the process priority     */
+} cxxdes_b200_process;
+
+/* Host pointers; cxxdes_b200_create copies everything to the device. */
+typedef struct cxxdes_b200_program {
+    const cxxdes_b200_op *ops;
+    const cxxdes_b200_process *procs;
+    const uint32_t *roots;      /* processes bound with env.bind(), in this order (coroutine.ipp:352-357) */
+    const uint64_t *queue_max;  /* per queue: max_size, 0 = unbounded (sync/queue.hpp:38)                 */
+    const uint64_t *sem_init;   /* per semaphore: initial value                                           */
+    const uint64_t *sem_max;    /* per semaphore: max (resource{c} = {c, c}, sync/resource.hpp:78)        */
+    const double *rates;        /* rates of the exponential draws                                         */
+    uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
+} cxxdes_b200_program;
+
 /* ---- per-replication results, structure of arrays (one entry per replication) ----
  * Any pointer may be NULL (column not wanted).  f64/i64 columns are model outputs:
  *   MM1    f64[0]=avg_latency f64[1]=total_latency            (producer_consumer.cpp:24,29,45-52)
@@ -133,7 +203,8 @@ enum {
     CXXDES_B200_REP_HEAP_OVERFLOW = 2u,   /* event heap capacity exceeded         */
     CXXDES_B200_REP_WAITER_OVERFLOW = 4u, /* sync::event waiter list exceeded     */
     CXXDES_B200_REP_TIME_RANGE = 8u,      /* tick value outside the packed range  */
-    CXXDES_B200_REP_UNFINISHED = 16u      /* run_until stopped before the end     */
+    CXXDES_B200_REP_UNFINISHED = 16u,     /* run_until stopped before the end     */
+    CXXDES_B200_REP_BAD_PROGRAM = 32u     /* process program did something the interpreter does not support */
 };
 
 /* ---- ensemble accumulators (what the final all-reduce sums) ---- */

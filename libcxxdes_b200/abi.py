@@ -9,11 +9,18 @@ import numpy as np
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY = 0, 1, 2, 3, 4
 SECONDS, MILLISECONDS, MICROSECONDS, NANOSECONDS, PICOSECONDS = range(5)
-MODEL_MM1, MODEL_ALOHA, MODEL_MMC, MODEL_ARCHSIM = 1, 2, 3, 4
+MODEL_MM1, MODEL_ALOHA, MODEL_MMC, MODEL_ARCHSIM, MODEL_PROGRAM = 1, 2, 3, 4, 5
 N_F64 = 2
 N_I64 = 2
 REP_QUEUE_OVERFLOW, REP_HEAP_OVERFLOW, REP_WAITER_OVERFLOW, REP_TIME_RANGE, REP_UNFINISHED = (
     1, 2, 4, 8, 16)
+REP_BAD_PROGRAM = 32
+INHERIT32 = 2 ** 31 - 1          # CXXDES_B200_INHERIT in the 32-bit b field of an op
+INHERIT64 = 2 ** 63 - 1          # priority_consts::inherit (defs.ipp:35)
+(OP_RETURN, OP_DELAY, OP_UNTIL, OP_DELAY_EXP, OP_DELAY_REAL, OP_FRESH, OP_AWAIT, OP_ASYNC, OP_ALL_OF, OP_ANY_OF,
+ OP_CHILD_PROC, OP_CHILD_DELAY, OP_CHILD_UNTIL, OP_Q_PUT, OP_Q_POP, OP_SEM_DOWN, OP_SEM_UP, OP_MTX_ACQUIRE,
+ OP_MTX_RELEASE, OP_EV_WAIT, OP_EV_WAKE, OP_LOOP, OP_END_LOOP, OP_SET_REG_NOW, OP_STAT_SECONDS, OP_STAT_TICKS,
+ OP_COUNT, OP_MARK) = range(28)
 FLAG_GENERIC_ENGINE = 1
 
 
@@ -51,6 +58,26 @@ class ArchSimParams(C.Structure):
                 ("n_requesters", C.c_uint32), ("reserved", C.c_uint32), ("n_loads", C.c_uint64)]
 
 
+class Op(C.Structure):
+    """cxxdes_b200_op"""
+    _fields_ = [("code", C.c_uint16), ("a", C.c_uint16), ("b", C.c_int32), ("imm", C.c_int64)]
+
+
+class Process(C.Structure):
+    """cxxdes_b200_process"""
+    _fields_ = [("entry", C.c_uint32), ("ordinal", C.c_uint32), ("priority", C.c_int64), ("latency", C.c_int64),
+                ("return_latency", C.c_int64), ("return_priority", C.c_int64)]
+
+
+class ProgramParams(C.Structure):
+    """cxxdes_b200_program (host pointers)."""
+    _fields_ = [("ops", C.POINTER(Op)), ("procs", C.POINTER(Process)), ("roots", C.POINTER(C.c_uint32)),
+                ("queue_max", C.POINTER(C.c_uint64)), ("sem_init", C.POINTER(C.c_uint64)),
+                ("sem_max", C.POINTER(C.c_uint64)), ("rates", C.POINTER(C.c_double)),
+                ("n_ops", C.c_uint32), ("n_procs", C.c_uint32), ("n_roots", C.c_uint32), ("n_queues", C.c_uint32),
+                ("n_sems", C.c_uint32), ("n_mutexes", C.c_uint32), ("n_events", C.c_uint32), ("n_rates", C.c_uint32)]
+
+
 class Columns(C.Structure):
     _fields_ = [("end_time", C.c_void_p), ("n_events", C.c_void_p), ("trace_hash", C.c_void_p),
                 ("status", C.c_void_p), ("f64", C.c_void_p * N_F64), ("i64", C.c_void_p * N_I64)]
@@ -71,7 +98,7 @@ class Config(C.Structure):
 
 
 PARAMS_OF_MODEL = {MODEL_MM1: MM1Params, MODEL_ALOHA: AlohaParams, MODEL_MMC: MMCParams,
-                   MODEL_ARCHSIM: ArchSimParams}
+                   MODEL_ARCHSIM: ArchSimParams, MODEL_PROGRAM: ProgramParams}
 
 
 class HostColumns:

@@ -47,6 +47,7 @@ union model_params {
     cxxdes_b200_aloha_params aloha;
     cxxdes_b200_mmc_params mmc;
     cxxdes_b200_archsim_params arch;
+    cxxdes_b200_program program;  // host pointers are only valid during cxxdes_b200_create
 };
 
 size_t params_size_of(int model) {
@@ -55,6 +56,7 @@ size_t params_size_of(int model) {
         case CXXDES_B200_MODEL_ALOHA: return sizeof(cxxdes_b200_aloha_params);
         case CXXDES_B200_MODEL_MMC: return sizeof(cxxdes_b200_mmc_params);
         case CXXDES_B200_MODEL_ARCHSIM: return sizeof(cxxdes_b200_archsim_params);
+        case CXXDES_B200_MODEL_PROGRAM: return sizeof(cxxdes_b200_program);
         default: return 0;
     }
 }
@@ -85,6 +87,9 @@ struct cxxdes_b200_ensemble {
     size_t ring_bytes = 0;
     cxxdes_b200_accumulators *acc = nullptr;
     void *reduce_scratch = nullptr;
+
+    unsigned char *program_blob = nullptr;  // device copy of a process program
+    device_program dprog{};
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -122,6 +127,60 @@ int allocate(cxxdes_b200_ensemble *e) {
     CUDA_TRY(cudaMalloc(&e->acc, sizeof(cxxdes_b200_accumulators)));
     CUDA_TRY(cudaMalloc(&e->reduce_scratch, reduce_scratch_bytes(e->sm_count)));
     if (e->ring_bytes) CUDA_TRY(cudaMalloc(&e->ring, e->ring_bytes));
+    return CXXDES_B200_OK;
+}
+
+// Deep-copy a process program to the device (one allocation) and build the device-side view.
+int upload_program(cxxdes_b200_ensemble *e) {
+    const cxxdes_b200_program &p = e->params.program;
+    const char *why = program_check(p);
+    if (why) return fail(CXXDES_B200_ERR_INVALID, "%s", why);
+    if ((p.n_queues && !p.queue_max) || (p.n_sems && (!p.sem_init || !p.sem_max)) || (p.n_rates && !p.rates))
+        return fail(CXXDES_B200_ERR_INVALID, "program: a counted array is NULL");
+    auto pad = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t s_ops = pad(sizeof(cxxdes_b200_op) * p.n_ops), s_procs = pad(sizeof(cxxdes_b200_process) * p.n_procs),
+                 s_roots = pad(4 * p.n_roots), s_q = pad(8 * p.n_queues), s_s = pad(8 * p.n_sems),
+                 s_r = pad(sizeof(divisor) * p.n_rates);
+    const size_t total = s_ops + s_procs + s_roots + s_q + 2 * s_s + s_r + 16;
+    unsigned char *host = new (std::nothrow) unsigned char[total]();
+    if (!host) return fail(CXXDES_B200_ERR_INVALID, "out of host memory");
+    size_t off = 0;
+    auto put = [&](const void *src, size_t bytes, size_t padded) {
+        size_t at = off;
+        if (bytes) memcpy(host + off, src, bytes);
+        off += padded;
+        return at;
+    };
+    const size_t o_ops = put(p.ops, sizeof(cxxdes_b200_op) * p.n_ops, s_ops);
+    const size_t o_procs = put(p.procs, sizeof(cxxdes_b200_process) * p.n_procs, s_procs);
+    const size_t o_roots = put(p.roots, 4 * p.n_roots, s_roots);
+    const size_t o_q = put(p.queue_max, 8 * p.n_queues, s_q);
+    const size_t o_si = put(p.sem_init, 8 * p.n_sems, s_s);
+    const size_t o_sm = put(p.sem_max, 8 * p.n_sems, s_s);
+    const size_t o_r = off;
+    for (uint32_t k = 0; k < p.n_rates; ++k) {
+        if (!(p.rates[k] > 0.0)) {
+            delete[] host;
+            return fail(CXXDES_B200_ERR_INVALID, "program: rates must be > 0");
+        }
+        divisor d = make_divisor(p.rates[k]);  // IEEE 1.0 / rate on the host: same bits as on the device
+        memcpy(host + off + k * sizeof(divisor), &d, sizeof(divisor));
+    }
+    cudaError_t ce = cudaMalloc(&e->program_blob, total);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->program_blob, host, total, cudaMemcpyHostToDevice);
+    delete[] host;
+    if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program upload: %s", cudaGetErrorString(ce));
+    device_program &d = e->dprog;
+    d.ops = (const cxxdes_b200_op *)(e->program_blob + o_ops);
+    d.procs = (const cxxdes_b200_process *)(e->program_blob + o_procs);
+    d.roots = (const uint32_t *)(e->program_blob + o_roots);
+    d.queue_max = (const uint64_t *)(e->program_blob + o_q);
+    d.sem_init = (const uint64_t *)(e->program_blob + o_si);
+    d.sem_max = (const uint64_t *)(e->program_blob + o_sm);
+    d.rates = (const divisor *)(e->program_blob + o_r);
+    d.n_ops = p.n_ops; d.n_procs = p.n_procs; d.n_roots = p.n_roots; d.n_queues = p.n_queues;
+    d.n_sems = p.n_sems; d.n_mutexes = p.n_mutexes; d.n_events = p.n_events; d.n_rates = p.n_rates;
+    memset(&e->params.program, 0, sizeof(e->params.program));  // the host pointers are not ours to keep
     return CXXDES_B200_OK;
 }
 
@@ -178,6 +237,8 @@ int plan(cxxdes_b200_ensemble *e) {
                 return fail(CXXDES_B200_ERR_INVALID, "archsim: shared memory budget exceeded");
             return CXXDES_B200_OK;
         }
+        case CXXDES_B200_MODEL_PROGRAM:
+            return upload_program(e);
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", c.model);
     }
@@ -220,6 +281,10 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             break;
         case CXXDES_B200_MODEL_ARCHSIM:
             CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream));
+            launches = 1;
+            break;
+        case CXXDES_B200_MODEL_PROGRAM:
+            CUDA_TRY(launch_program(e->dprog, sh, e->cols, e->sm_count, e->stream));
             launches = 1;
             break;
         default:
@@ -435,6 +500,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->ring);
     cudaFree(e->acc);
     cudaFree(e->reduce_scratch);
+    cudaFree(e->program_blob);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);

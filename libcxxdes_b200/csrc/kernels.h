@@ -45,6 +45,21 @@ size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p);
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
                            int sm_count, cudaStream_t stream);
 
+// ---- process programs (program_kernel.cu) ----
+struct device_program {  // cxxdes_b200_program with device pointers; rates as {d, RN(1/d)}
+    const cxxdes_b200_op *ops;
+    const cxxdes_b200_process *procs;
+    const uint32_t *roots;
+    const uint64_t *queue_max;
+    const uint64_t *sem_init;
+    const uint64_t *sem_max;
+    const divisor *rates;
+    uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
+};
+const char *program_check(const cxxdes_b200_program &p);  // nullptr when the interpreter supports it
+cudaError_t launch_program(const device_program &prg, const shard &sh, const device_columns &out, int sm_count,
+                           cudaStream_t stream);
+
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);
 cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_accumulators *device_acc,

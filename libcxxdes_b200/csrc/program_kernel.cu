@@ -1,0 +1,525 @@
+// program_kernel.cu -- generic lowering: one kernel interprets a process program
+// (cxxdes_b200_program, include/cxxdes_b200.h) for every replication.
+//
+// This is the device counterpart of the reference's process runtime for models that have no
+// hand-written kernel: each operation reproduces the token traffic of one reference awaitable
+//  on top of the same engine the model kernels use (device/engine.cuh: libstdc++-exact
+// heap, clock, trace digest).  Thread per replication; the event heap is in shared memory, the
+// (small) process table, sync objects and handler pool are per-thread local arrays.
+#include "device/models_common.cuh"
+#include "kernels.h"
+
+namespace cxb {
+
+namespace {
+
+constexpr int PRG_THREADS = 128;
+constexpr int PRG_HEAP = 64;
+constexpr int PRG_MAX_PROCS = 24;
+constexpr int PRG_HANDLERS = 8;   // live any_of/all_of handlers per replication (pool, by serial)
+constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind
+constexpr int PRG_WAITERS = 16;
+constexpr int PRG_QUEUE_CAP = 128;
+constexpr int64_t INHERIT64 = INT64_MAX;
+
+struct proc_rt {
+    int64_t prio;
+    int64_t reg;
+    uint32_t pc;
+    uint32_t draws;
+    uint32_t loop[2];
+    uint32_t ctag[2];
+    int64_t cprio[2];
+    int64_t clat[2];
+    uint8_t loop_depth;
+    uint8_t n_comp;
+    bool bound;
+    bool complete;
+};
+
+struct waiters_rt {  // sync::event: FIFO of {latency, priority, process}  (event.hpp:87-139)
+    uint32_t who[PRG_WAITERS];
+    int32_t lat[PRG_WAITERS];
+    int16_t prio[PRG_WAITERS];
+    int n;
+};
+
+struct handler_rt {  // any_all_helper::custom_handler (any_of.ipp:3-27)
+    uint32_t serial_plus1;
+    uint32_t total, remaining;
+    bool is_all, armed;
+};
+
+struct queue_rt {
+    int64_t item[PRG_QUEUE_CAP];
+    uint32_t head, count;
+};
+
+struct interp {
+    environment env;
+    const device_program &prg;
+    const shard &sh;
+    const log_entry *table;
+    proc_rt procs[PRG_MAX_PROCS];
+    waiters_rt q_wait[PRG_MAX_OBJ], s_wait[PRG_MAX_OBJ], m_wait[PRG_MAX_OBJ], e_wait[PRG_MAX_OBJ];
+    queue_rt queues[PRG_MAX_OBJ];
+    uint64_t sem_value[PRG_MAX_OBJ];
+    bool mtx_owned[PRG_MAX_OBJ];
+    handler_rt handlers[PRG_HANDLERS];
+    uint32_t next_serial;
+    double f64[CXXDES_B200_N_F64];
+    int64_t i64[CXXDES_B200_N_I64];
+    stream_addr addr;
+
+    __device__ interp(const device_program &p, const shard &s, const log_entry *t) : prg(p), sh(s), table(t) {}
+
+    __device__ void fresh(uint32_t p) {
+        proc_rt &r = procs[p];
+        r.prio = prg.procs[p].priority;
+        r.pc = prg.procs[p].entry;
+        r.loop_depth = 0;
+        r.n_comp = 0;
+        r.bound = false;
+        r.complete = false;
+    }
+
+    // coroutine_data::bind_, environment.ipp:281-307
+    __device__ void bind(uint32_t p, int64_t inherited) {
+        proc_rt &r = procs[p];
+        if (r.bound) return;
+        r.bound = true;
+        if (r.prio == INHERIT64) r.prio = inherited;
+        env.schedule(env.now + prg.procs[p].latency, r.prio, make_tag(p));
+    }
+
+    // coroutine::await_suspend, coroutine.ipp:194-207
+    __device__ void register_completion(uint32_t child, uint32_t tag) {
+        proc_rt &c = procs[child];
+        if (c.n_comp >= 2) {
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return;
+        }
+        const int k = c.n_comp++;
+        c.ctag[k] = tag;
+        const int64_t rp = prg.procs[child].return_priority;
+        c.cprio[k] = rp == INHERIT64 ? c.prio : rp;
+        c.clat[k] = prg.procs[child].return_latency;
+    }
+
+    // coroutine_data_::do_return, environment.ipp:321-348
+    __device__ void do_return(uint32_t p) {
+        proc_rt &r = procs[p];
+        for (int k = 0; k < r.n_comp; ++k) env.schedule(r.clat[k] + env.now, r.cprio[k], r.ctag[k]);
+        r.n_comp = 0;
+        r.complete = true;
+    }
+
+    __device__ void wait_on(waiters_rt &w, uint32_t p, int64_t latency, int64_t prio) {
+        if (w.n >= PRG_WAITERS || prio < -32768 || prio > 32767 || latency < 0 || latency > INT32_MAX) {
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return;
+        }
+        w.who[w.n] = p;
+        w.lat[w.n] = (int32_t)latency;
+        w.prio[w.n] = (int16_t)prio;
+        ++w.n;
+    }
+
+    // wake_awaitable::await_ready, event.hpp:125-134
+    __device__ void wake(waiters_rt &w) {
+        for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], make_tag(w.who[k]));
+        w.n = 0;
+    }
+
+    __device__ int64_t op_priority(const cxxdes_b200_op &op, const proc_rt &self) const {
+        return op.b == CXXDES_B200_INHERIT ? self.prio : (int64_t)op.b;
+    }
+
+    // any_of / all_of: any_of.ipp:41-92.  Returns true when the awaiting process suspends.
+    __device__ bool composition(uint32_t self_id, const cxxdes_b200_op &head, uint32_t first_child) {
+        proc_rt &self = procs[self_id];
+        const bool is_all = head.code == CXXDES_B200_OP_ALL_OF;
+        const uint32_t total = head.a;
+        if (total > 32) {
+            env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+            return true;
+        }
+        // await_bind: every child in argument order (coroutine children get their start token here)
+        for (uint32_t c = 0; c < total; ++c) {
+            const cxxdes_b200_op &ch = prg.ops[first_child + c];
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) bind(ch.a, self.prio);
+        }
+        // await_ready: collect ready flags
+        uint32_t ready_mask = 0, remaining = total;
+        for (uint32_t c = 0; c < total; ++c) {
+            const cxxdes_b200_op &ch = prg.ops[first_child + c];
+            bool ready = false;
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) ready = procs[ch.a].complete;
+            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) ready = env.now >= ch.imm;
+            if (ready) {
+                ready_mask |= 1u << c;
+                --remaining;
+            }
+        }
+        if (is_all ? remaining == 0 : remaining < total) return false;
+        // await_suspend: output token {0, priority, self} held by a new handler; non-ready children in order
+        const uint32_t serial = next_serial++;
+        if (serial + 1 >= 0xFFFFu) {
+            env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+            return true;
+        }
+        handler_rt &h = handlers[serial % PRG_HANDLERS];
+        if (h.armed) env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;  // a still-armed handler would be overwritten
+        h.serial_plus1 = serial + 1;
+        h.total = total;
+        h.remaining = remaining;
+        h.is_all = is_all;
+        h.armed = true;
+        for (uint32_t c = 0; c < total; ++c) {
+            if (ready_mask & (1u << c)) continue;
+            const cxxdes_b200_op &ch = prg.ops[first_child + c];
+            const uint32_t tag = make_tag(self_id, serial + 1);
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
+            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) env.schedule(env.now + ch.imm, op_priority(ch, self), tag);
+            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) env.schedule(ch.imm, op_priority(ch, self), tag);
+            else env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+        }
+        return true;
+    }
+
+    // custom_handler::invoke, any_of.ipp:9-26
+    __device__ void invoke_handler(const token &t) {
+        const uint32_t hp1 = tag_handler_plus1(t.tag);
+        handler_rt &h = handlers[(hp1 - 1) % PRG_HANDLERS];
+        if (h.serial_plus1 != hp1) return;  // the handler already fired and its slot was reused: nothing left to do
+        --h.remaining;
+        const bool cond = h.is_all ? h.remaining == 0 : h.remaining < h.total;
+        if (h.armed && cond) {
+            env.schedule(key_time(t.key), key_prio(t.key), make_tag(tag_target(t.tag)));
+            h.armed = false;
+        }
+    }
+
+    // Resume process p and run until it suspends or returns (coroutine_data::resume, coroutine_data.ipp:20-29).
+    __device__ void resume(uint32_t p) {
+        proc_rt &self = procs[p];
+        for (int guard = 0; guard < 100000; ++guard) {
+            if (self.pc >= prg.n_ops) {
+                env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                return;
+            }
+            const cxxdes_b200_op op = prg.ops[self.pc];
+            switch (op.code) {
+                case CXXDES_B200_OP_RETURN:
+                    do_return(p);
+                    return;
+                case CXXDES_B200_OP_DELAY:
+                    env.schedule(env.now + op.imm, op_priority(op, self), make_tag(p));
+                    ++self.pc;
+                    return;
+                case CXXDES_B200_OP_UNTIL:
+                    ++self.pc;
+                    if (env.now >= op.imm) break;
+                    env.schedule(op.imm, op_priority(op, self), make_tag(p));
+                    return;
+                case CXXDES_B200_OP_DELAY_EXP: {
+                    addr.stream = prg.procs[p].ordinal;
+                    const double v = exponential(addr, (uint64_t)self.draws++, prg.rates[op.a], table);
+                    env.schedule(env.now + real_to_sim(v, sh.clk), op_priority(op, self), make_tag(p));
+                    ++self.pc;
+                    return;
+                }
+                case CXXDES_B200_OP_DELAY_REAL:
+                    env.schedule(env.now + real_to_sim(bits_as_double((uint64_t)op.imm), sh.clk), op_priority(op, self),
+                                 make_tag(p));
+                    ++self.pc;
+                    return;
+                case CXXDES_B200_OP_FRESH:
+                    fresh(op.a);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_AWAIT:
+                    bind(op.a, self.prio);
+                    ++self.pc;
+                    if (procs[op.a].complete) break;
+                    register_completion(op.a, make_tag(p));
+                    return;
+                case CXXDES_B200_OP_ASYNC:
+                    bind(op.a, self.prio);
+                    if (!procs[op.a].complete) register_completion(op.a, make_tag(TAG_NO_TARGET));
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_ALL_OF:
+                case CXXDES_B200_OP_ANY_OF: {
+                    const uint32_t first_child = self.pc + 1;
+                    self.pc += 1 + op.a;
+                    if (composition(p, op, first_child)) return;
+                    break;
+                }
+                case CXXDES_B200_OP_Q_PUT: {
+                    queue_rt &q = queues[op.a];
+                    const uint64_t max_size = prg.queue_max[op.a];
+                    if (max_size != 0 && q.count >= max_size) {  // while (!can_put()) co_await event_.wait();
+                        wait_on(q_wait[op.a], p, 0, self.prio);
+                        return;
+                    }
+                    if (q.count >= PRG_QUEUE_CAP) {
+                        env.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+                        return;
+                    }
+                    q.item[(q.head + q.count) % PRG_QUEUE_CAP] = op.b ? self.reg : env.now;
+                    ++q.count;
+                    wake(q_wait[op.a]);
+                    ++self.pc;
+                    break;
+                }
+                case CXXDES_B200_OP_Q_POP: {
+                    queue_rt &q = queues[op.a];
+                    if (q.count == 0) {
+                        wait_on(q_wait[op.a], p, 0, self.prio);
+                        return;
+                    }
+                    self.reg = q.item[q.head];
+                    q.head = (q.head + 1) % PRG_QUEUE_CAP;
+                    --q.count;
+                    wake(q_wait[op.a]);
+                    ++self.pc;
+                    break;
+                }
+                case CXXDES_B200_OP_SEM_DOWN:
+                    if (sem_value[op.a] == 0) {
+                        wait_on(s_wait[op.a], p, 0, self.prio);
+                        return;
+                    }
+                    --sem_value[op.a];
+                    wake(s_wait[op.a]);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_SEM_UP:
+                    if (sem_value[op.a] >= prg.sem_max[op.a]) {
+                        wait_on(s_wait[op.a], p, 0, self.prio);
+                        return;
+                    }
+                    ++sem_value[op.a];
+                    wake(s_wait[op.a]);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_MTX_ACQUIRE:
+                    if (mtx_owned[op.a]) {
+                        wait_on(m_wait[op.a], p, 0, self.prio);
+                        return;
+                    }
+                    mtx_owned[op.a] = true;
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_MTX_RELEASE:
+                    mtx_owned[op.a] = false;
+                    wake(m_wait[op.a]);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_EV_WAIT:
+                    wait_on(e_wait[op.a], p, op.imm, op_priority(op, self));
+                    ++self.pc;
+                    return;
+                case CXXDES_B200_OP_EV_WAKE:
+                    wake(e_wait[op.a]);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_LOOP:
+                    if (op.imm <= 0) {
+                        self.pc = (uint32_t)op.b;
+                    } else if (self.loop_depth >= 2) {
+                        env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                        return;
+                    } else {
+                        self.loop[self.loop_depth++] = (uint32_t)op.imm;
+                        ++self.pc;
+                    }
+                    break;
+                case CXXDES_B200_OP_END_LOOP:
+                    if (--self.loop[self.loop_depth - 1] > 0) {
+                        self.pc = (uint32_t)op.b;
+                    } else {
+                        --self.loop_depth;
+                        ++self.pc;
+                    }
+                    break;
+                case CXXDES_B200_OP_SET_REG_NOW:
+                    self.reg = env.now;
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_STAT_SECONDS:
+                    f64[op.a] += sim_to_seconds(env.now, sh.clk) - sim_to_seconds(self.reg, sh.clk);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_STAT_TICKS:
+                    f64[op.a] += (double)(env.now - self.reg);
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_COUNT:
+                    i64[op.a] += op.imm;
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_MARK:
+                    ++i64[0];
+                    i64[1] = (int64_t)((uint64_t)i64[1] * 1000003ULL + (uint64_t)(env.now * op.imm + (int64_t)op.b));
+                    ++self.pc;
+                    break;
+                default:
+                    env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                    return;
+            }
+            if (env.status) return;
+        }
+        env.status |= CXXDES_B200_REP_BAD_PROGRAM;  // a process body that never suspends
+    }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(PRG_THREADS)
+program_kernel(device_program prg, shard sh, device_columns out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    stage_log_table(table, sh.log_table);
+    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, PRG_HEAP);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, PRG_HEAP);
+
+    uint64_t rep;
+    while (steal(sh, rep)) {
+        interp it(prg, sh, table);
+        it.env.init(hkey, htag, PRG_HEAP);
+        it.addr.seed = sh.seed;
+        it.addr.replication = sh.first_replication + rep;
+        it.next_serial = 0;
+        for (int k = 0; k < CXXDES_B200_N_F64; ++k) it.f64[k] = 0.0;
+        for (int k = 0; k < CXXDES_B200_N_I64; ++k) it.i64[k] = 0;
+        for (uint32_t p = 0; p < prg.n_procs; ++p) {
+            it.fresh(p);
+            it.procs[p].draws = 0;
+            it.procs[p].reg = 0;
+        }
+        for (int o = 0; o < PRG_MAX_OBJ; ++o) {
+            it.q_wait[o].n = it.s_wait[o].n = it.m_wait[o].n = it.e_wait[o].n = 0;
+            it.queues[o].head = it.queues[o].count = 0;
+            it.sem_value[o] = (uint32_t)o < prg.n_sems ? prg.sem_init[o] : 0;
+            it.mtx_owned[o] = false;
+        }
+        for (int h = 0; h < PRG_HANDLERS; ++h) {
+            it.handlers[h].serial_plus1 = 0;
+            it.handlers[h].armed = false;
+        }
+        // environment::bind(coroutine) for every root, coroutine.ipp:352-357
+        for (uint32_t r = 0; r < prg.n_roots; ++r) {
+            const uint32_t p = prg.roots[r];
+            it.bind(p, 0);
+            if (!it.procs[p].complete) it.register_completion(p, make_tag(TAG_NO_TARGET));
+        }
+
+        environment &env = it.env;
+        while (env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until)) {
+            // environment::step, environment.ipp:117-146 (the digest names processes by ordinal)
+            token t = env.pop_top();
+            const int64_t time = key_time(t.key);
+            env.now = time > env.now ? time : env.now;
+            ++env.n_events;
+            const uint32_t target = tag_target(t.tag);
+            const uint32_t hp1 = tag_handler_plus1(t.tag);
+            const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != TAG_NO_TARGET ? TOKEN_RESUME : TOKEN_NOOP);
+            const uint32_t ordinal = target != TAG_NO_TARGET ? prg.procs[target].ordinal : PROC_NONE;
+            env.hash = trace_hash_step(env.hash, time, key_prio(t.key), kind, ordinal);
+            if (hp1) it.invoke_handler(t);
+            else if (target != TAG_NO_TARGET) it.resume(target);
+            if (env.status) break;
+        }
+        if (sh.run_until >= 0) {
+            if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
+            env.now = env.now > sh.run_until ? env.now : sh.run_until;
+        }
+        rep_out o;
+        o.end_time = env.now;
+        o.n_events = env.n_events;
+        o.trace_hash = env.hash;
+        o.status = env.status;
+        for (int k = 0; k < CXXDES_B200_N_F64; ++k) o.f64[k] = it.f64[k];
+        for (int k = 0; k < CXXDES_B200_N_I64; ++k) o.i64[k] = it.i64[k];
+        store_result(out, rep, o);
+    }
+}
+
+const char *program_check(const cxxdes_b200_program &p) {
+    if (p.n_procs < 1 || p.n_procs > PRG_MAX_PROCS) return "program: 1..24 processes supported";
+    if (p.n_ops < 1 || p.n_ops > 4096) return "program: 1..4096 ops supported";
+    if (p.n_roots < 1 || p.n_roots > p.n_procs) return "program: need at least one root process";
+    if (p.n_queues > PRG_MAX_OBJ || p.n_sems > PRG_MAX_OBJ || p.n_mutexes > PRG_MAX_OBJ || p.n_events > PRG_MAX_OBJ)
+        return "program: at most 4 sync objects of each kind";
+    if (p.n_rates > 16) return "program: at most 16 rates";
+    if (!p.ops || !p.procs || !p.roots) return "program: ops/procs/roots must not be NULL";
+    for (uint32_t i = 0; i < p.n_procs; ++i) {
+        if (p.procs[i].entry >= p.n_ops) return "program: process entry out of range";
+        if (p.procs[i].ordinal >= 0xFFFF) return "program: ordinal must be < 0xFFFF";
+    }
+    for (uint32_t r = 0; r < p.n_roots; ++r)
+        if (p.roots[r] >= p.n_procs) return "program: root out of range";
+    for (uint32_t i = 0; i < p.n_ops; ++i) {
+        const cxxdes_b200_op &op = p.ops[i];
+        switch (op.code) {
+            case CXXDES_B200_OP_FRESH: case CXXDES_B200_OP_AWAIT: case CXXDES_B200_OP_ASYNC:
+            case CXXDES_B200_OP_CHILD_PROC:
+                if (op.a >= p.n_procs) return "program: process operand out of range";
+                break;
+            case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF:
+                if (op.a < 1 || op.a > 32 || i + op.a >= p.n_ops) return "program: bad composition";
+                for (uint32_t c = 1; c <= op.a; ++c) {
+                    uint16_t cc = p.ops[i + c].code;
+                    if (cc != CXXDES_B200_OP_CHILD_PROC && cc != CXXDES_B200_OP_CHILD_DELAY &&
+                        cc != CXXDES_B200_OP_CHILD_UNTIL)
+                        return "program: composition children must be CHILD_* ops";
+                }
+                break;
+            case CXXDES_B200_OP_Q_PUT: case CXXDES_B200_OP_Q_POP:
+                if (op.a >= p.n_queues) return "program: queue operand out of range";
+                break;
+            case CXXDES_B200_OP_SEM_DOWN: case CXXDES_B200_OP_SEM_UP:
+                if (op.a >= p.n_sems) return "program: semaphore operand out of range";
+                break;
+            case CXXDES_B200_OP_MTX_ACQUIRE: case CXXDES_B200_OP_MTX_RELEASE:
+                if (op.a >= p.n_mutexes) return "program: mutex operand out of range";
+                break;
+            case CXXDES_B200_OP_EV_WAIT: case CXXDES_B200_OP_EV_WAKE:
+                if (op.a >= p.n_events) return "program: event operand out of range";
+                break;
+            case CXXDES_B200_OP_DELAY_EXP:
+                if (op.a >= p.n_rates) return "program: rate operand out of range";
+                break;
+            case CXXDES_B200_OP_LOOP: case CXXDES_B200_OP_END_LOOP:
+                if (op.b < 0 || (uint32_t)op.b > p.n_ops) return "program: loop target out of range";
+                break;
+            case CXXDES_B200_OP_STAT_SECONDS: case CXXDES_B200_OP_STAT_TICKS:
+                if (op.a >= CXXDES_B200_N_F64) return "program: statistic index out of range";
+                break;
+            case CXXDES_B200_OP_COUNT:
+                if (op.a >= CXXDES_B200_N_I64) return "program: counter index out of range";
+                break;
+            default:
+                if (op.code > CXXDES_B200_OP_MARK) return "program: unknown op code";
+        }
+    }
+    return nullptr;
+}
+
+size_t program_smem_bytes() {
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + (size_t)PRG_THREADS * PRG_HEAP * 12;
+}
+
+cudaError_t launch_program(const device_program &prg, const shard &sh, const device_columns &out, int sm_count,
+                           cudaStream_t stream) {
+    const size_t smem = program_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    program_kernel<<<sm_count * 2, PRG_THREADS, smem, stream>>>(prg, sh, out);
+    return cudaGetLastError();
+}
+
+}  // namespace cxb

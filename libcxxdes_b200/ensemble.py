@@ -86,7 +86,8 @@ def device_count():
 
 
 _MODEL_OF_PARAMS = {abi.MM1Params: abi.MODEL_MM1, abi.AlohaParams: abi.MODEL_ALOHA,
-                    abi.MMCParams: abi.MODEL_MMC, abi.ArchSimParams: abi.MODEL_ARCHSIM}
+                    abi.MMCParams: abi.MODEL_MMC, abi.ArchSimParams: abi.MODEL_ARCHSIM,
+                    abi.ProgramParams: abi.MODEL_PROGRAM}
 
 
 class Ensemble:
@@ -98,6 +99,9 @@ class Ensemble:
                  stream=None, flags=0, queue_capacity=0):
         self._lib = load_library()
         self._handle = None
+        if hasattr(params, "to_params"):        # a libcxxdes_b200.program.Program
+            self._program = params              # keeps the arrays behind the pointers alive
+            params = params.to_params()
         self.params = params
         self.model = _MODEL_OF_PARAMS[type(params)]
         self.n_replications = int(n_replications)

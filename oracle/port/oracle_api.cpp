@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "models.hpp"
+#include "program_interp.hpp"
 
 using namespace port_oracle;
 
@@ -44,6 +45,10 @@ rep_result run_model(int model, const void *params, const cxxdes_b200_clock &clo
         }
         case CXXDES_B200_MODEL_ARCHSIM: {
             archsim_model m(*static_cast<const cxxdes_b200_archsim_params *>(params), seed, rep);
+            return finish(m, until, dump, dump_limit);
+        }
+        case CXXDES_B200_MODEL_PROGRAM: {
+            program_model m(*static_cast<const cxxdes_b200_program *>(params), clock, seed, rep);
             return finish(m, until, dump, dump_limit);
         }
         default:

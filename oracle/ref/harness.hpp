@@ -23,6 +23,15 @@ namespace ref_oracle {
 
 using namespace cxxdes::core;
 
+struct rep_result {
+    int64_t end_time = 0;
+    uint64_t n_events = 0;
+    uint64_t trace_hash = 0;
+    uint32_t status = 0;
+    double f64[CXXDES_B200_N_F64] = {0, 0};
+    int64_t i64[CXXDES_B200_N_I64] = {0, 0};
+};
+
 struct trace_event {
     int64_t time;
     int64_t priority;

@@ -1,0 +1,289 @@
+// oracle/ref/kat_models.hpp -- TEST INFRASTRUCTURE (oracle), not product code.
+//
+// Known-answer scenarios written natively on the UNMODIFIED reference engine.  They are the
+// reference's own tests and examples (cited per scenario), flattened where the original nests
+// compositions (`a && b && c` is all_of(all_of(a, b), c) in the reference; the process-program
+// interpreter takes flat child lists), with every process object named for the trace digest.
+// The same scenarios exist as process programs in tests/kat_programs.py; the parity tests
+// compare: reference engine (this file)  ==  CPU interpreter  ==  CUDA interpreter.
+#pragma once
+#include "harness.hpp"
+
+#include <cxxdes/sync/event.hpp>
+#include <cxxdes/sync/mutex.hpp>
+#include <cxxdes/sync/queue.hpp>
+#include <cxxdes/sync/resource.hpp>
+#include <cxxdes/sync/semaphore.hpp>
+
+namespace ref_oracle {
+
+constexpr int ORACLE_MODEL_KAT = 100;  // oracle-only model id; params = kat_params
+
+struct kat_params {
+    int32_t scenario;
+    int32_t reserved;
+};
+
+// 1 -- tests/controlflow.test.cpp:60-72,126-137: all_of / any_of of timeouts, ready child of all_of
+CXXDES_SIMULATION(kat_compositions) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_compositions(tracer &t) : tr{t} { bind(); }
+    coroutine<> body() {
+        co_await all_of(timeout(10), timeout(20));
+        marks.push_back(now());  // 20
+        co_await any_of(timeout(10), timeout(20));
+        marks.push_back(now());  // 30
+        co_await all_of(until(0), delay(5));
+        marks.push_back(now());  // 35
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 2 -- tests/process.test.cpp:81-105: start latency 6 + body 5 + return latency 8 = 19
+CXXDES_SIMULATION(kat_latencies) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_latencies(tracer &t) : tr{t} { bind(); }
+    unique_coroutine<int> f() {
+        marks.push_back(now());  // 6
+        co_await delay(5);
+        marks.push_back(now());  // 11
+        co_return 5;
+    }
+    coroutine<> body() {
+        co_await tr.named(f(), 1).latency(6).return_latency(8);
+        marks.push_back(now());  // 19
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 3 -- tests/process.test.cpp:25-48: any_of does not cancel the loser; foo() still runs to t = 10
+CXXDES_SIMULATION(kat_out_of_scope) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_out_of_scope(tracer &t) : tr{t} { bind(); }
+    coroutine<int> foo() {
+        co_await delay(10);
+        marks.push_back(now());  // 10
+        co_return 10;
+    }
+    coroutine<> body() {
+        {
+            auto p = tr.named(foo(), 1);
+            co_await any_of(p, delay(1));
+            marks.push_back(now());  // 1
+        }
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 4 -- tests/process.test.cpp:149-187: priority ordering at equal time (counter 100 / 101 / 102)
+CXXDES_SIMULATION(kat_priorities) {
+    tracer &tr;
+    std::vector<time_integral> marks;  // now * 1000 + foo ordinal, in execution order
+    int counter = 100;
+    explicit kat_priorities(tracer &t) : tr{t} { bind(); }
+    coroutine<void> foo(int t, int expected, int id) {
+        co_await delay(t);
+        if (now() != t || counter != expected) marks.push_back(-1);  // the EXPECT_EQs of the reference test
+        marks.push_back(now() * 1000 + id);
+        counter = counter + 1;
+    }
+    coroutine<void> spawn_foos(int expected, uint32_t base) {
+        co_await async(tr.named(foo(1, expected, (int)base + 0), base + 0));
+        co_await async(tr.named(foo(2, expected, (int)base + 1), base + 1));
+        co_await async(tr.named(foo(3, expected, (int)base + 2), base + 2));
+    }
+    coroutine<void> reset_counter() {
+        for (int i = 0; i < 4; ++i) {
+            counter = 100;
+            co_await delay(1);
+        }
+    }
+    coroutine<void> body() {
+        co_await all_of(tr.named(spawn_foos(100, 10), 1).priority(100), tr.named(spawn_foos(101, 20), 2).priority(101),
+                        tr.named(spawn_foos(102, 30), 3).priority(102), tr.named(reset_counter(), 4).priority(0));
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 5 -- examples/clocks.cpp: three root processes, periods 2, 3 and 7; heap tie order at t = 6, 12, 18
+struct kat_clocks {
+    environment env;
+    tracer &tr;
+    std::vector<time_integral> marks;  // now * 10 + clock id
+    explicit kat_clocks(tracer &t) : tr{t} {
+        env.bind(tr.named(clock(2, 1), 1));
+        env.bind(tr.named(clock(3, 2), 2));
+        env.bind(tr.named(clock(7, 3), 3));
+    }
+    coroutine<> clock(time_integral period, int id) {
+        while (true) {
+            marks.push_back(env.now() * 10 + id);
+            co_await timeout(period);
+        }
+    }
+    time_integral now() const { return env.now(); }
+};
+
+// 6 -- examples/resource.cpp: resource{3}, durations 4 / 10 / 2 / 10, #3 with priority 10000; #3 done at 12
+CXXDES_SIMULATION(kat_resource) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::resource resource{3};
+    explicit kat_resource(tracer &t) : tr{t} { bind(); }
+    coroutine<> p(int id, time_integral duration) {
+        auto handle = co_await resource.acquire();
+        marks.push_back(now() * 10 + id);
+        co_await timeout(duration);
+        co_await handle.release();
+        marks.push_back(now() * 10 + id);
+    }
+    coroutine<> body() {
+        co_await all_of(tr.named(p(0, 4), 1), tr.named(p(1, 10), 2), tr.named(p(2, 2), 3),
+                        tr.named(p(3, 10), 4).priority(10000));
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 7 -- examples/mutex.cpp: five processes, _Co_with(m) { delay(5) }, priorities 5 3 2 4 1
+CXXDES_SIMULATION(kat_mutex) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::mutex m;
+    explicit kat_mutex(tracer &t) : tr{t} { bind(); }
+    coroutine<> p(int idx, time_integral t) {
+        _Co_with(m) {
+            marks.push_back(now() * 10 + idx);
+            co_await delay(t);
+            marks.push_back(now() * 10 + idx);
+        };
+    }
+    coroutine<> body() {
+        co_await all_of(tr.named(p(1, 5), 1).priority(5), tr.named(p(2, 5), 2).priority(3), tr.named(p(3, 5), 3).priority(2),
+                        tr.named(p(4, 5), 4).priority(4), tr.named(p(5, 5), 5).priority(1));
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 8 -- examples/semaphore.cpp (flattened): p1 takes three units, p2 / p3 give one at 5 and 10
+CXXDES_SIMULATION(kat_semaphore) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::semaphore<> q{1};
+    explicit kat_semaphore(tracer &t) : tr{t} { bind(); }
+    coroutine<> p1() {
+        co_await q.down();
+        co_await q.down();
+        co_await q.down();
+        marks.push_back(now());  // 10
+    }
+    coroutine<> p2() {
+        co_await timeout(5);
+        co_await q.up();
+    }
+    coroutine<> p3() {
+        co_await timeout(10);
+        co_await q.up();
+    }
+    coroutine<> body() { co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2), tr.named(p3(), 3)); }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 9 -- examples/queue.cpp: bounded queue{1}: the second put blocks until the pop at 12
+CXXDES_SIMULATION(kat_queue) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::queue<int> q{1};
+    explicit kat_queue(tracer &t) : tr{t} { bind(); }
+    coroutine<> p1() {
+        auto r1 = co_await q.pop();
+        marks.push_back(now() * 10 + r1);  // 5, r = 1
+        co_await timeout(7);
+        auto r2 = co_await q.pop();
+        marks.push_back(now() * 10 + r2);  // 12, r = 2
+    }
+    coroutine<> p2() {
+        co_await timeout(5);
+        co_await q.put(1);
+        co_await q.put(2);
+        marks.push_back(now() * 10);  // 5
+    }
+    coroutine<> body() { co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2)); }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 10 -- examples/event.cpp: event.wait(latency, priority) / wake
+CXXDES_SIMULATION(kat_event) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::event evt;
+    explicit kat_event(tracer &t) : tr{t} { bind(); }
+    coroutine<> p1() {
+        co_await evt.wait(2, -100);
+        marks.push_back(now() * 10 + 1);  // 7
+    }
+    coroutine<> p2() {
+        co_await timeout(5);
+        co_await evt.wake();
+        marks.push_back(now() * 10 + 2);  // 5
+    }
+    coroutine<> p3() {
+        co_await evt.wait(8);
+        marks.push_back(now() * 10 + 3);  // 13
+        co_await until(500);
+        co_await evt.wake();
+        co_await until(600);
+        co_await evt.wake();
+    }
+    coroutine<> p4() {
+        co_await timeout(20);
+        co_await evt.wait();
+        marks.push_back(now() * 10 + 4);  // 500
+        co_await evt.wait(2);
+        marks.push_back(now() * 10 + 4);  // 602
+    }
+    coroutine<> body() { co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2), tr.named(p3(), 3), tr.named(p4(), 4)); }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
+// application-level observations are compared too, not only the token trace.
+inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
+    r.i64[0] = (int64_t)marks.size();
+    uint64_t h = 0;
+    for (auto m : marks) h = h * 1000003ULL + (uint64_t)m;
+    r.i64[1] = (int64_t)h;
+}
+
+template <typename Sim>
+inline rep_result run_kat_sim(tracer &tr, int64_t until) {
+    rep_result r;
+    {
+        Sim sim{tr};
+        run_traced(sim.env, tr, until);
+        r.end_time = sim.now();
+        fold_marks(sim.marks, r);
+    }
+    return r;
+}
+
+inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::vector<time_integral> *marks_out) {
+    const auto &p = *static_cast<const kat_params *>(params);
+    switch (p.scenario) {
+        case 1: return run_kat_sim<kat_compositions>(tr, until);
+        case 2: return run_kat_sim<kat_latencies>(tr, until);
+        case 3: return run_kat_sim<kat_out_of_scope>(tr, until);
+        case 4: return run_kat_sim<kat_priorities>(tr, until);
+        case 5: return run_kat_sim<kat_clocks>(tr, until);
+        case 6: return run_kat_sim<kat_resource>(tr, until);
+        case 7: return run_kat_sim<kat_mutex>(tr, until);
+        case 8: return run_kat_sim<kat_semaphore>(tr, until);
+        case 9: return run_kat_sim<kat_queue>(tr, until);
+        case 10: return run_kat_sim<kat_event>(tr, until);
+        default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
+    }
+}
+
+}  // namespace ref_oracle

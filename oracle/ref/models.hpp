@@ -8,6 +8,7 @@
 // through tracer::named() when created so the harness can name it in the digest.
 #pragma once
 #include "harness.hpp"
+#include "kat_models.hpp"
 
 #include <cxxdes/sync/queue.hpp>
 
@@ -16,15 +17,6 @@
 namespace ref_oracle {
 
 using namespace cxxdes::core::time_ops;
-
-struct rep_result {
-    int64_t end_time = 0;
-    uint64_t n_events = 0;
-    uint64_t trace_hash = 0;
-    uint32_t status = 0;
-    double f64[CXXDES_B200_N_F64] = {0, 0};
-    int64_t i64[CXXDES_B200_N_I64] = {0, 0};
-};
 
 // Shared exponential variate: draw number `n` of stream `stream`.
 struct exp_stream {
@@ -434,6 +426,7 @@ inline rep_result run_model(int model, const void *params, cxxdes_b200_clock con
         case CXXDES_B200_MODEL_ALOHA: r = run_aloha(params, clock, seed, rep, until, tr); break;
         case CXXDES_B200_MODEL_MMC: r = run_mmc(params, clock, seed, rep, until, tr); break;
         case CXXDES_B200_MODEL_ARCHSIM: r = run_archsim(params, clock, seed, rep, until, tr); break;
+        case ORACLE_MODEL_KAT: r = run_kat(params, until, tr, nullptr); break;
         default: throw std::runtime_error("ref_oracle: unknown model");
     }
     r.n_events = tr.n_events;

@@ -1,0 +1,185 @@
+"""The known-answer scenarios of oracle/ref/kat_models.hpp as process programs (same numbering).
+
+Each function returns (Program, run_until) -- run_until < 0 means run to exhaustion.  Ordinals match
+the names given with tracer::named() on the reference side; a `_Co_with` helper coroutine has the
+ordinal of its parent | 0x8000 (how the reference harness reports unnamed library coroutines)."""
+import ctypes as C
+
+from libcxxdes_b200 import Delay, Program, Until
+
+ORACLE_MODEL_KAT = 100
+
+
+class KatParams(C.Structure):
+    _fields_ = [("scenario", C.c_int32), ("reserved", C.c_int32)]
+
+
+def compositions():          # 1: tests/controlflow.test.cpp:60-72,126-137
+    prog = Program()
+    main = prog.process(0, root=True)
+    with prog.body(main) as b:
+        b.all_of(Delay(10), Delay(20)); b.mark(1, 0)
+        b.any_of(Delay(10), Delay(20)); b.mark(1, 0)
+        b.all_of(Until(0), Delay(5)); b.mark(1, 0)
+    return prog, -1
+
+
+def latencies():             # 2: tests/process.test.cpp:81-105
+    prog = Program()
+    main = prog.process(0, root=True)
+    f = prog.process(1, latency=6, return_latency=8)
+    with prog.body(f) as b:
+        b.mark(1, 0); b.delay(5); b.mark(1, 0)
+    with prog.body(main) as b:
+        b.await_(f); b.mark(1, 0)
+    return prog, -1
+
+
+def out_of_scope():          # 3: tests/process.test.cpp:25-48
+    prog = Program()
+    main = prog.process(0, root=True)
+    foo = prog.process(1)
+    with prog.body(foo) as b:
+        b.delay(10); b.mark(1, 0)
+    with prog.body(main) as b:
+        b.any_of(foo, Delay(1)); b.mark(1, 0)
+    return prog, -1
+
+
+def priorities():            # 4: tests/process.test.cpp:149-187
+    prog = Program()
+    main = prog.process(0, root=True)
+    spawners = [prog.process(1, priority=100), prog.process(2, priority=101), prog.process(3, priority=102)]
+    reset = prog.process(4, priority=0)
+    foos = {}
+    for s, base in zip(spawners, (10, 20, 30)):
+        foos[s] = [prog.process(base + k) for k in range(3)]
+        for k, f in enumerate(foos[s]):
+            with prog.body(f) as b:
+                b.delay(k + 1); b.mark(1000, base + k)
+    for s in spawners:
+        with prog.body(s) as b:
+            for f in foos[s]:
+                b.async_(f)
+    with prog.body(reset) as b:
+        with b.loop(4):
+            b.delay(1)
+    with prog.body(main) as b:
+        b.all_of(*spawners, reset)
+    return prog, -1
+
+
+def clocks():                # 5: examples/clocks.cpp, env.run_for(20)
+    prog = Program()
+    for ordinal, period in ((1, 2), (2, 3), (3, 7)):
+        p = prog.process(ordinal, root=True)
+        with prog.body(p) as b:
+            with b.loop(1 << 30):
+                b.mark(10, ordinal); b.delay(period)
+    return prog, 20
+
+
+def resource():              # 6: examples/resource.cpp
+    prog = Program()
+    res = prog.resource(3)
+    main = prog.process(0, root=True)
+    ps = [prog.process(1), prog.process(2), prog.process(3), prog.process(4, priority=10000)]
+    for idx, (p, duration) in enumerate(zip(ps, (4, 10, 2, 10))):
+        with prog.body(p) as b:
+            b.down(res); b.mark(10, idx); b.delay(duration); b.up(res); b.mark(10, idx)
+    with prog.body(main) as b:
+        b.all_of(*ps)
+    return prog, -1
+
+
+def mutex():                 # 7: examples/mutex.cpp
+    prog = Program()
+    m = prog.mutex()
+    main = prog.process(0, root=True)
+    ps = []
+    for idx, prio in ((1, 5), (2, 3), (3, 2), (4, 4), (5, 1)):
+        p = prog.process(idx, priority=prio)
+        helper = prog.process(0x8000 | idx)        # _Co_with(m) { ... }: co_with.ipp:27-35
+        with prog.body(helper) as b:
+            b.acquire(m); b.mark(10, idx); b.delay(5); b.mark(10, idx); b.release(m)
+        with prog.body(p) as b:
+            b.await_(helper)
+        ps.append(p)
+    with prog.body(main) as b:
+        b.all_of(*ps)
+    return prog, -1
+
+
+def semaphore():             # 8: examples/semaphore.cpp (flattened)
+    prog = Program()
+    q = prog.semaphore(1)
+    main = prog.process(0, root=True)
+    p1, p2, p3 = prog.process(1), prog.process(2), prog.process(3)
+    with prog.body(p1) as b:
+        b.down(q); b.down(q); b.down(q); b.mark(1, 0)
+    with prog.body(p2) as b:
+        b.delay(5); b.up(q)
+    with prog.body(p3) as b:
+        b.delay(10); b.up(q)
+    with prog.body(main) as b:
+        b.all_of(p1, p2, p3)
+    return prog, -1
+
+
+def queue():                 # 9: examples/queue.cpp
+    prog = Program()
+    q = prog.queue(1)
+    main = prog.process(0, root=True)
+    p1, p2 = prog.process(1), prog.process(2)
+    with prog.body(p1) as b:
+        b.pop(q); b.mark(10, 1); b.delay(7); b.pop(q); b.mark(10, 2)
+    with prog.body(p2) as b:
+        b.delay(5); b.put(q); b.put(q); b.mark(10, 0)
+    with prog.body(main) as b:
+        b.all_of(p1, p2)
+    return prog, -1
+
+
+def event():                 # 10: examples/event.cpp
+    prog = Program()
+    evt = prog.event()
+    main = prog.process(0, root=True)
+    p1, p2, p3, p4 = (prog.process(k) for k in (1, 2, 3, 4))
+    with prog.body(p1) as b:
+        b.wait(evt, 2, -100); b.mark(10, 1)
+    with prog.body(p2) as b:
+        b.delay(5); b.wake(evt); b.mark(10, 2)
+    with prog.body(p3) as b:
+        b.wait(evt, 8); b.mark(10, 3); b.until(500); b.wake(evt); b.until(600); b.wake(evt)
+    with prog.body(p4) as b:
+        b.delay(20); b.wait(evt); b.mark(10, 4); b.wait(evt, 2); b.mark(10, 4)
+    with prog.body(main) as b:
+        b.all_of(p1, p2, p3, p4)
+    return prog, -1
+
+
+SCENARIOS = {1: compositions, 2: latencies, 3: out_of_scope, 4: priorities, 5: clocks, 6: resource, 7: mutex,
+             8: semaphore, 9: queue, 10: event}
+# end time of every scenario on the reference engine (the reference's tests / examples document the
+# observation times; scenario 1 ends at 40 because the loser of any_of(timeout(10), timeout(20)) still fires)
+EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602}
+
+
+def mm1_program(lam, mu, n_packets):
+    """examples/producer_consumer.cpp:31-58 as a process program (same ordinals / streams as the
+    hand-written kernels: co_main 0, producer 1, consumer 2); f64[1] = total_latency, i64[0] = packets consumed."""
+    prog = Program()
+    q = prog.queue()
+    main = prog.process(0, root=True)
+    prod, cons = prog.process(1), prog.process(2)
+    r_lam, r_mu = prog.rate(lam), prog.rate(mu)
+    with prog.body(prod) as b:
+        with b.loop(n_packets):
+            b.put(q); b.delay_exp(r_lam)
+    with prog.body(cons) as b:
+        with b.loop(n_packets - 1):
+            b.pop(q); b.count(0); b.delay_exp(r_mu); b.stat_seconds(1)
+        b.pop(q); b.count(0)
+    with prog.body(main) as b:
+        b.all_of(prod, cons)
+    return prog

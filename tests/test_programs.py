@@ -1,0 +1,128 @@
+"""Process programs (generic lowering): the reference's own known-answer scenarios
+(tests/controlflow.test.cpp, tests/process.test.cpp, examples/{clocks,resource,mutex,semaphore,queue,event}.cpp)
+run natively on the reference engine == as process programs on the CPU interpreter == on the CUDA interpreter."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util
+import kat_programs as K
+import oracles
+import libcxxdes_b200 as L
+from libcxxdes_b200 import abi
+
+CLK = abi.Clock.of((1, 0), (1, 0))
+
+
+def _golden(k):
+    g = golden_util.load("kat_reference.json")
+    return next(c for c in g["cases"] if c["scenario"] == k)
+
+
+@pytest.mark.parametrize("k", sorted(K.SCENARIOS))
+def test_cpu_interpreter_matches_reference_golden(port, k):
+    prog, until = K.SCENARIOS[k]()
+    pp = prog.to_params()
+    case = _golden(k)
+    got = port.run(abi.MODEL_PROGRAM, pp, CLK, 1, 0, 1, until=until)
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(case), what=case["name"])
+    total, events = port.trace(abi.MODEL_PROGRAM, pp, CLK, 1, 0, until=until, max_events=1000)
+    assert total == case["n_events"] and [list(e) for e in events] == case["trace"]
+    assert got.end_time[0] == K.EXPECTED_END[k]
+
+
+@pytest.mark.parametrize("k", sorted(K.SCENARIOS))
+def test_cpu_interpreter_matches_reference_live(port, ref, k):
+    prog, until = K.SCENARIOS[k]()
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), CLK, 7, 3, 4, until=until)
+    b = ref.run(K.ORACLE_MODEL_KAT, K.KatParams(k, 0), CLK, 7, 3, 4, until=until)
+    golden_util.assert_columns_equal(a, b, what=K.SCENARIOS[k].__name__)
+
+
+def test_known_event_counts(port):
+    """examples/resource.cpp = 16 events, examples/mutex.cpp = 38 events."""
+    for k, n in ((6, 16), (7, 38)):
+        prog, until = K.SCENARIOS[k]()
+        assert port.run(abi.MODEL_PROGRAM, prog.to_params(), CLK, 1, 0, 1, until=until).n_events[0] == n
+
+
+def test_mm1_program_equals_hand_lowered_model(port):
+    for lam, n in ((5.0, 300), (9.0, 200), (0.5, 100)):
+        a = port.run(abi.MODEL_PROGRAM, K.mm1_program(lam, 10.0, n).to_params(), oracles.MM1_CLOCK, 0x5EED, 0, 32)
+        b = port.run(abi.MODEL_MM1, abi.MM1Params(lam, 10.0, n), oracles.MM1_CLOCK, 0x5EED, 0, 32)
+        assert np.array_equal(a.trace_hash, b.trace_hash) and np.array_equal(a.end_time, b.end_time)
+        assert np.array_equal(a.n_events, b.n_events) and np.array_equal(a.i64[0], b.i64[0])
+        assert np.array_equal(a.f64[1].view(np.uint64), b.f64[1].view(np.uint64))
+
+
+def test_builder_rejects_incomplete_programs():
+    prog = L.Program()
+    prog.process(0, root=True)
+    with pytest.raises(ValueError):
+        prog.to_params()                      # no body
+    prog2 = L.Program()
+    p = prog2.process(0)
+    with prog2.body(p) as b:
+        b.delay(1)
+    with pytest.raises(ValueError):
+        prog2.to_params()                     # no root
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def _run_gpu(prog, n_reps, clock=((1, 0), (1, 0)), seed=1, first=0, until=-1):
+    ens = L.Ensemble(prog, n_reps, seed=seed, first_replication=first)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    if until < 0:
+        ens.run()
+    else:
+        ens.run_until(until)
+    cols = ens.fetch(strict=False)
+    ens.close()
+    return cols
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", sorted(K.SCENARIOS))
+def test_gpu_interpreter_matches_reference_golden(built, k):
+    prog, until = K.SCENARIOS[k]()
+    case = _golden(k)
+    got = _run_gpu(prog, 64, until=until)
+    assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+    want = golden_util.golden_columns(case)
+    for r in (0, 17, 63):                     # the scenarios are deterministic: every replication is the same
+        assert got.n_events[r] == want.n_events[0] and got.end_time[r] == want.end_time[0]
+        assert got.trace_hash[r] == want.trace_hash[0]
+        assert got.i64[0][r] == want.i64[0][0] and got.i64[1][r] == want.i64[1][0]
+    assert got.end_time[0] == K.EXPECTED_END[k]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lam,n", [(5.0, 500), (9.0, 300)])
+def test_gpu_mm1_program_matches_oracle_and_fused_kernel(port, lam, n):
+    """The same model three ways on the device side: process program on the interpreter kernel,
+    hand-written fused kernel, and both against the CPU oracle."""
+    n_reps = 512
+    prog = K.mm1_program(lam, 10.0, n)
+    got = _run_gpu(prog, n_reps, clock=((1, L.SECONDS), (1, L.MILLISECONDS)), seed=0x5EED)
+    assert not got.status.any()
+    want = port.run(abi.MODEL_MM1, abi.MM1Params(lam, 10.0, n), oracles.MM1_CLOCK, 0x5EED, 0, n_reps,
+                    threads=os.cpu_count())
+    assert np.array_equal(got.trace_hash, want.trace_hash) and np.array_equal(got.end_time, want.end_time)
+    assert np.array_equal(got.n_events, want.n_events) and np.array_equal(got.i64[0], want.i64[0])
+    assert np.array_equal(got.f64[1].view(np.uint64), want.f64[1].view(np.uint64))
+    ens = L.Ensemble(abi.MM1Params(lam, 10.0, n), n_reps, seed=0x5EED)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    fused = ens.run().fetch()
+    ens.close()
+    assert np.array_equal(fused.trace_hash, got.trace_hash)
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_bad_programs(built):
+    prog = L.Program()
+    p = prog.process(0, root=True)
+    with prog.body(p) as b:
+        b.await_(5)                            # process 5 does not exist
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(prog, 4).run()

@@ -134,6 +134,20 @@ def archsim_cases(ref):
     return out
 
 
+def kat_cases(ref):
+    import kat_programs as K
+    clk = abi.Clock.of((1, 0), (1, 0))
+    cases = []
+    for k, fn in sorted(K.SCENARIOS.items()):
+        _, until = fn()
+        kp = K.KatParams(k, 0)
+        cols = ref.run(K.ORACLE_MODEL_KAT, kp, clk, 1, 0, 1, until=until)
+        total, tr = ref.trace(K.ORACLE_MODEL_KAT, kp, clk, 1, 0, until=until, max_events=1000)
+        cases.append({"scenario": k, "name": fn.__name__, "run_until": until, "n_replications": 1,
+                      "columns": columns_to_json(cols), "n_events": total, "trace": tr})
+    return {"model": "kat", "clock": CLOCK_S_S, "cases": cases}
+
+
 def main():
     ref = oracles.ref_oracle()
     if ref is None:
@@ -142,7 +156,7 @@ def main():
     out = mm1_cases(ref)
     (GOLDEN / "mm1_reference.json").write_text(json.dumps(out, indent=0, separators=(",", ":")))
     print("wrote", GOLDEN / "mm1_reference.json")
-    for name, fn in (("aloha", aloha_cases), ("mmc", mmc_cases), ("archsim", archsim_cases)):
+    for name, fn in (("aloha", aloha_cases), ("mmc", mmc_cases), ("archsim", archsim_cases), ("kat", kat_cases)):
         (GOLDEN / f"{name}_reference.json").write_text(json.dumps(fn(ref), indent=0, separators=(",", ":")))
         print("wrote", GOLDEN / f"{name}_reference.json")
 

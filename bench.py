@@ -30,6 +30,7 @@ LAMBDA, MU = 5.0, 10.0
 SEED = 0x5EED
 I_ALG = 256.0            # algorithmic thread-instructions per event, SURVEY 8(d) / BASELINE.md 5
 BYTES_PER_REP = 60.0     # algorithmic HBM bytes per replication: the result row (7 x 8 B + 4 B)
+CPU_LAMBDA = [LAMBDA]    # arrival rate of the CPU arm (follows --lam)
 METRIC = "simulated events/sec, 1M-replication M/M/1 ensemble at 1/2/4/8 B200"
 
 
@@ -43,12 +44,15 @@ def parse():
     ap.add_argument("--packets", type=int, default=10000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", default="ahead", choices=["ahead", "lockstep"],
+                    help="first-pass M/M/1 kernel: generate-ahead (default) or the older draw-on-demand one (A/B)")
+    ap.add_argument("--lam", type=float, default=LAMBDA, help="arrival rate (default = the headline 5.0)")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"mm1 producer/consumer ensemble: {a.replications} replications x {a.packets} packets per GPU, "
-            f"lambda={LAMBDA} mu={MU}, unit 1 s, precision 1 ms (BASELINE configs[1])")
+            f"lambda={a.lam} mu={MU}, unit 1 s, precision 1 ms (BASELINE configs[1])")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -67,7 +71,7 @@ def load_cpu_oracle():
 def cpu_run(oracle, n_reps, packets, threads, first_rep=0):
     import oracles
     from libcxxdes_b200 import abi
-    p = abi.MM1Params(LAMBDA, MU, packets)
+    p = abi.MM1Params(CPU_LAMBDA[0], MU, packets)
     t0 = time.perf_counter()
     cols = oracle.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, SEED, first_rep, n_reps, threads=threads)
     dt = time.perf_counter() - t0
@@ -200,14 +204,14 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     R = a.replications
-    params = L.MM1Params(LAMBDA, MU, a.packets)
+    params = L.MM1Params(a.lam, MU, a.packets)
     # a dedicated (non-default) torch stream: the library launches on it, so torch.cuda.Event and
     # NCCL (torch.distributed) see the same stream the kernels run on
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     first_rep, _ = sharding.weak_shard_of(rank, R)
     ens = L.Ensemble(params, R, seed=SEED, first_replication=first_rep, device=local_rank,
-                     stream=stream.cuda_stream)
+                     stream=stream.cuda_stream, flags=abi.FLAG_MM1_LOCKSTEP if a.kernel == "lockstep" else 0)
     ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -288,7 +292,7 @@ def run_b200(a):
     roofline = {
         "bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "thread-inst/s",
         "frac": issue_achieved / issue_peak, "traffic": traffic,
-        "kernel": "mm1_fused_kernel<FAST>", "kernel_ms": kernel_avg_ms,
+        "kernel": "mm1_ahead_kernel" if a.kernel == "ahead" else "mm1_fused_kernel<FAST>", "kernel_ms": kernel_avg_ms,
         "alg_per_unit": f"{I_ALG:.0f} thread-instructions per simulated event (SURVEY 8d)",
         "peak_source": f"{props.multi_processor_count} SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz, {peak_src}",
         "hbm": {"achieved": R * BYTES_PER_REP / (kernel_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -351,6 +355,7 @@ def run_b200(a):
 
 def main():
     a = parse()
+    CPU_LAMBDA[0] = a.lam
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -22,6 +22,7 @@ INHERIT64 = 2 ** 63 - 1          # priority_consts::inherit (defs.ipp:35)
  OP_MTX_RELEASE, OP_EV_WAIT, OP_EV_WAKE, OP_LOOP, OP_END_LOOP, OP_SET_REG_NOW, OP_STAT_SECONDS, OP_STAT_TICKS,
  OP_COUNT, OP_MARK) = range(28)
 FLAG_GENERIC_ENGINE = 1
+FLAG_MM1_LOCKSTEP = 2
 
 
 class Clock(C.Structure):

@@ -191,7 +191,7 @@ int plan(cxxdes_b200_ensemble *e) {
             const cxxdes_b200_mm1_params &p = e->params.mm1;
             if (!(p.lambda > 0.0) || !(p.mu > 0.0)) return fail(CXXDES_B200_ERR_INVALID, "mm1: rates must be > 0");
             e->use_fused = !(c.flags & CXXDES_B200_FLAG_GENERIC_ENGINE) && p.n_packets >= 2 &&
-                           p.n_packets < (1ULL << 31);
+                           p.n_packets < (1ULL << 30);
             if (e->use_fused) {
                 e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin);
                 e->ring_bytes = (size_t)e->mm1_plan.fb_blocks * e->mm1_plan.fb_threads * e->mm1_plan.fb_ring *
@@ -264,7 +264,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         case CXXDES_B200_MODEL_MM1:
             if (e->use_fused) {
                 CUDA_TRY(launch_mm1_fused(e->params.mm1, sh, e->cols, e->mm1_plan, e->ring, e->counters + 2,
-                                          e->stream, &launches));
+                                          e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
             } else {
                 CUDA_TRY(launch_mm1_engine(e->params.mm1, sh, e->cols, e->ring, e->engine_ring, e->engine_blocks,
                                            e->engine_threads, e->stream));
@@ -371,6 +371,7 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
         ce = cudaEventCreate(&e->ev_begin);
         if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_end);
         if (ce == cudaSuccess && e->use_fused) ce = configure_mm1_fused(e->mm1_plan);
+        if (ce == cudaSuccess && e->use_fused) ce = configure_mm1_ahead(e->mm1_plan);
         if (ce != cudaSuccess) rc = fail(CXXDES_B200_ERR_CUDA, "setup: %s", cudaGetErrorString(ce));
     }
     if (rc != CXXDES_B200_OK) {

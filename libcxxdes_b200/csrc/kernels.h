@@ -20,13 +20,24 @@ struct mm1_fused_plan {
     int fb_threads, fb_blocks;  // fallback kernel (global-memory ring, 64-bit ticks)
     uint32_t fb_ring;           // ring entries per fallback thread
     bool direct_global;         // skip the shared-memory kernel (high utilisation / huge queues)
+    // generate-ahead kernel (mm1_ahead.cu), the default first pass
+    int ah_threads, ah_blocks;
+    size_t ah_smem_bytes;
+    uint32_t ah_ring_cap;       // packets (queued + generated ahead) a replication's ring may hold
+    bool ah_direct_global;
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                               size_t smem_per_block_optin);
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             cudaStream_t stream, int *launches);
+                             cudaStream_t stream, int *launches, bool lockstep);
 cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
+
+// ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
+void plan_mm1_ahead(mm1_fused_plan &plan, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count);
+cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
+cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                             const mm1_fused_plan &plan, cudaStream_t stream);
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);

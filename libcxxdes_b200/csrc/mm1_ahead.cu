@@ -1,0 +1,166 @@
+// mm1_ahead.cu -- headline kernel: M/M/1 (examples/producer_consumer.cpp:9-59), one thread per
+// replication, variates generated ahead of the event loop (device/mm1_lane.cuh has the model).
+//
+// Per loop iteration every lane of the warp, together:
+//   1. generates two packets (one Philox block per stream, four log/divide/convert chains with
+//      no dependence between them) into its ring in shared memory -- convergent, no lane idles;
+//   2. runs SLOTS bookkeeping slots; a slot dispatches the lane's next event (a put that wakes
+//      the consumer takes the wake-up token along), so a packet costs two slots whatever the
+//      order of events.  A lane that has caught up with its generated packets skips a slot, a lane
+//      whose ring is full skips a generation; the ring between the two absorbs the difference.
+// Start-up and wind-down events (co_main, all_of handler, completions) go through a generic
+// two-slot heap, one per iteration.  A lane whose replication ends takes the next replication
+// from the global counter at once (replication-level work stealing).
+//
+// Replications the 32-bit/shared-memory representation cannot hold (queue longer than the ring,
+// ticks beyond 2^30) are appended to the retry list and redone by mm1_fused_kernel<false>.
+#include <cmath>
+
+#include "device/mm1_lane.cuh"
+#include "device/models_common.cuh"
+#include "kernels.h"
+
+namespace cxb {
+
+namespace {
+
+template <int SLOTS, int THREADS>
+struct smem_ring {
+    uint2 *base;  // this thread's column: entry j at base[(j % SLOTS) * THREADS]
+    // 8-byte entries, THREADS * 8 bytes between slots: a warp's access touches each bank pair
+    // once whatever slot each lane is at (two conflict-free wavefronts)
+    __device__ __forceinline__ mm1::ring_entry load(uint32_t j) const {
+        const uint2 v = base[(j & (SLOTS - 1)) * THREADS];
+        mm1::ring_entry e;
+        e.a = v.x;
+        e.s = v.y;
+        return e;
+    }
+    __device__ __forceinline__ uint32_t load_a(uint32_t j) const { return base[(j & (SLOTS - 1)) * THREADS].x; }
+    __device__ __forceinline__ void store(uint32_t j, const mm1::ring_entry &e) const {
+        base[(j & (SLOTS - 1)) * THREADS] = make_uint2(e.a, e.s);
+    }
+};
+
+}  // namespace
+
+template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    stage_log_table(table, sh.log_table);
+    smem_ring<RING_SLOTS, THREADS> ring;
+    ring.base = (uint2 *)(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x;
+
+    mm1::lane L;
+    L.init(0);
+    bool active = false, exhausted = false;
+    uint64_t rep = 0;
+
+    for (;;) {
+        if (!active && !exhausted) {
+            if (steal(sh, rep)) {
+                L.init(sh.first_replication + rep);
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+        // ---- 1. two more packets for every lane that has room for them ----
+        if (active && L.wants_packets(c)) {
+            if (L.has_room(c)) L.generate_pair(c, ring, table);
+            else if (L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+        }
+        __syncwarp();
+
+        // ---- 2. start-up / wind-down events ----
+        if (active && !L.fast) L.generic_step(c, ring);
+        __syncwarp();
+
+        // ---- 3. steady-state events ----
+#pragma unroll
+        for (int s = 0; s < EVENT_SLOTS; ++s) {
+            if (active) L.fast_slot(c, ring);
+        }
+
+        // ---- 4. end of this lane's replication? ----
+        if (active && L.finished(c)) {
+            active = false;
+            const uint32_t status = L.status;
+            if (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE)) {
+                // hand the replication to the fallback kernel; its row is written there
+                unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                sh.retry_list[at] = (uint32_t)rep;
+            } else {
+                rep_out o;
+                int64_t end = (int64_t)L.now;
+                o.status = status;
+                if (sh.run_until >= 0) {
+                    if (L.next_time() != mm1::EMPTY) o.status |= CXXDES_B200_REP_UNFINISHED;
+                    end = end > sh.run_until ? end : sh.run_until;  // now_ = max(now_, t), environment.ipp:194
+                }
+                o.end_time = end;
+                o.n_events = L.n_events;
+                o.trace_hash = L.hash;
+                o.f64[0] = L.k == c.n_packets ? L.total_latency / (double)prm.n_packets : 0.0;  // :46
+                o.f64[1] = L.total_latency;
+                o.i64[0] = (int64_t)L.k;
+                o.i64[1] = (int64_t)L.max_queue;
+                store_result(out, rep, o);
+            }
+            L.fast = false;
+        }
+    }
+}
+
+namespace {
+constexpr int AH_THREADS = 256;
+constexpr int AH_MIN_BLOCKS = 3;
+constexpr int AH_RING_SLOTS = 32;
+constexpr int AH_EVENT_SLOTS = 4;
+constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+}  // namespace
+
+void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count) {
+    p.ah_threads = AH_THREADS;
+    p.ah_blocks = sm_count * AH_MIN_BLOCKS;
+    p.ah_smem_bytes = TABLE_BYTES + (size_t)AH_RING_SLOTS * AH_THREADS * sizeof(uint2);
+    uint32_t cap = queue_capacity ? queue_capacity : AH_RING_SLOTS;
+    if (cap > AH_RING_SLOTS) cap = AH_RING_SLOTS;
+    if (cap < 2) cap = 2;
+    p.ah_ring_cap = cap;
+    // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the ring also holds the packets
+    // generated ahead (2 to 4).  If more than ~2% of the replications are expected to outgrow it,
+    // run everything on the global-memory kernel instead.
+    const double rho = prm.lambda / prm.mu;
+    const double q = (double)cap - 3.0;
+    const double p_over = rho >= 1.0 ? 1.0 : pow(rho, q > 0 ? q : 0.0) * (double)prm.n_packets;
+    p.ah_direct_global = !(p_over < 0.02);
+}
+
+cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
+    return cudaFuncSetAttribute(mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.ah_smem_bytes);
+}
+
+cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                             const mm1_fused_plan &plan, cudaStream_t stream) {
+    mm1::constants c;
+    c.lambda = make_divisor(prm.lambda);  // IEEE 1/d on the host: same bits as on the device
+    c.mu = make_divisor(prm.mu);
+    c.keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
+    c.ticks_per_unit = (double)sh.clk.ticks_per_unit;
+    c.sec_per_unit = sh.clk.seconds_per_tick_unit;
+    c.tick_mult = sh.clk.tick_mult;
+    c.n_packets = (uint32_t)prm.n_packets;
+    c.ring_cap = plan.ah_ring_cap;
+    c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
+    mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS>
+        <<<plan.ah_blocks, AH_THREADS, plan.ah_smem_bytes, stream>>>(c, prm, sh, out);
+    return cudaGetLastError();
+}
+
+}  // namespace cxb

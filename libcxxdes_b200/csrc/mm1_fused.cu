@@ -382,9 +382,10 @@ mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_
     double rho = prm.lambda / prm.mu;
     double p_over = rho >= 1.0 ? 1.0 : pow(rho, (double)p.smem_ring + 1.0) * (double)prm.n_packets;
     p.direct_global = !(p_over < 0.02);
+    plan_mm1_ahead(p, prm, queue_capacity, sm_count);
     p.fb_threads = FB_THREADS;
     uint64_t want = prm.n_packets;
-    if (p.direct_global) {
+    if (p.direct_global || p.ah_direct_global) {
         p.fb_blocks = sm_count * 8;
         // memory budget for the rings: 8 GiB
         uint64_t budget = (8ULL << 30) / ((uint64_t)p.fb_blocks * FB_THREADS * sizeof(int64_t));
@@ -408,20 +409,29 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan) {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
 }
 
+// First pass: mm1_ahead.cu (default) or, with `lockstep`, the draw-on-demand kernel above (kept
+// for A/B measurements); second pass: the retry list on the global-memory kernel.  Heavily
+// loaded queues skip the first pass.
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             cudaStream_t stream, int *launches) {
+                             cudaStream_t stream, int *launches, bool lockstep) {
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     mm1_rates rates;
     rates.lambda = make_divisor(prm.lambda);
     rates.mu = make_divisor(prm.mu);
     rates.keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
-    if (!plan.direct_global) {
-        mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>
-            <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, rates, sh, out, plan.smem_ring, nullptr,
-                                                                    nullptr, nullptr, nullptr);
+    const bool direct = lockstep ? plan.direct_global : plan.ah_direct_global;
+    if (!direct) {
+        cudaError_t e;
+        if (lockstep) {
+            mm1_fused_kernel<true, FAST_THREADS, FAST_MIN_BLOCKS>
+                <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, rates, sh, out, plan.smem_ring, nullptr,
+                                                                        nullptr, nullptr, nullptr);
+            e = cudaGetLastError();
+        } else {
+            e = launch_mm1_ahead(prm, sh, out, plan, stream);
+        }
         ++*launches;
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // retry list -> fallback kernel; exits at once when the list is empty
         mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(

@@ -1,0 +1,69 @@
+// tests/native/mm1_lane_host.cpp -- TEST INFRASTRUCTURE, never part of the product library.
+//
+// Compiles the device state machine of the headline kernel (libcxxdes_b200/csrc/device/mm1_lane.cuh,
+// a __host__ __device__ header) with g++ and drives one lane at a time through the same
+// iteration the kernel runs (generate a pair, one generic step, EVENT_SLOTS steady-state slots),
+// so the model logic can be checked against the oracle where there is no GPU.
+#include <vector>
+
+#include "device/mm1_lane.cuh"
+
+using namespace cxb;
+
+namespace {
+struct host_ring {
+    std::vector<mm1::ring_entry> slots;
+    explicit host_ring(uint32_t n) : slots(n) {}
+    mm1::ring_entry load(uint32_t j) const { return slots[j & (slots.size() - 1)]; }
+    uint32_t load_a(uint32_t j) const { return slots[j & (slots.size() - 1)].a; }
+    void store(uint32_t j, const mm1::ring_entry &e) { slots[j & (slots.size() - 1)] = e; }
+};
+}  // namespace
+
+extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t ticks_per_unit, int64_t tick_mult,
+                                 double sec_per_unit, uint64_t seed, uint64_t first, uint64_t n_reps,
+                                 int64_t until, uint32_t ring_cap, uint32_t ring_slots, int event_slots,
+                                 const cxxdes_b200_columns *out, uint64_t *iterations) {
+    mm1::constants c;
+    c.lambda = make_divisor(prm->lambda);
+    c.mu = make_divisor(prm->mu);
+    c.keys = philox_schedule_of((uint32_t)seed, (uint32_t)(seed >> 32));
+    c.ticks_per_unit = (double)ticks_per_unit;
+    c.sec_per_unit = sec_per_unit;
+    c.tick_mult = tick_mult;
+    c.n_packets = (uint32_t)prm->n_packets;
+    c.ring_cap = ring_cap;
+    c.until = (until < 0 || until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)until;
+    uint64_t iters = 0;
+    for (uint64_t r = 0; r < n_reps; ++r) {
+        host_ring ring(ring_slots);
+        mm1::lane L;
+        L.init(first + r);
+        for (;;) {
+            ++iters;
+            if (L.wants_packets(c)) {
+                if (L.has_room(c)) L.generate_pair(c, ring, LOG_TABLE_HOST);
+                else if (L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+            }
+            if (!L.fast) L.generic_step(c, ring);
+            for (int s = 0; s < event_slots; ++s) L.fast_slot(c, ring);
+            if (L.finished(c)) break;
+        }
+        uint32_t status = L.status;
+        int64_t end = (int64_t)L.now;
+        if (until >= 0) {
+            if (L.next_time() != mm1::EMPTY) status |= CXXDES_B200_REP_UNFINISHED;
+            end = end > until ? end : until;
+        }
+        out->end_time[r] = end;
+        out->n_events[r] = L.n_events;
+        out->trace_hash[r] = L.hash;
+        out->status[r] = status;
+        out->f64[0][r] = L.k == c.n_packets ? L.total_latency / (double)prm->n_packets : 0.0;
+        out->f64[1][r] = L.total_latency;
+        out->i64[0][r] = (int64_t)L.k;
+        out->i64[1][r] = (int64_t)L.max_queue;
+    }
+    if (iterations) *iterations = iters;
+    return 0;
+}

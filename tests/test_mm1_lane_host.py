@@ -1,0 +1,117 @@
+"""CPU unit test of the headline kernel's per-lane state machine.
+
+libcxxdes_b200/csrc/device/mm1_lane.cuh is a __host__ __device__ header; tests/native/mm1_lane_host.cpp
+compiles it with g++ and steps single lanes through the kernel's iteration.  The result must equal the
+oracle bit for bit wherever the lane did not ask for the fallback kernel (status 0)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import golden_util
+import oracles
+from libcxxdes_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "tests" / "native" / "mm1_lane_host.cpp"
+OUT = ROOT / "tests" / "native" / "libmm1_lane_host.so"
+
+
+@pytest.fixture(scope="module")
+def lane_lib():
+    hdr = ROOT / "libcxxdes_b200" / "csrc" / "device" / "mm1_lane.cuh"
+    if not OUT.exists() or OUT.stat().st_mtime < max(SRC.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-mfma", "-x", "c++",
+                        f"-I{ROOT / 'include'}", f"-I{ROOT / 'libcxxdes_b200' / 'csrc'}", "-shared",
+                        "-o", str(OUT), str(SRC)], check=True)
+    lib = C.CDLL(str(OUT))
+    lib.mm1_lane_host_run.restype = C.c_int
+    lib.mm1_lane_host_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_uint64,
+                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int,
+                                      C.POINTER(abi.Columns), C.POINTER(C.c_uint64)]
+    return lib
+
+
+def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=32, ring_slots=32, event_slots=4,
+              clock=(1000, 1, 1e-3)):
+    cols = abi.HostColumns(n_reps)
+    st = cols.as_struct()
+    iters = C.c_uint64()
+    rc = lib.mm1_lane_host_run(C.addressof(p), clock[0], clock[1], clock[2], seed, first, n_reps, until,
+                               ring_cap, ring_slots, event_slots, C.byref(st), C.byref(iters))
+    assert rc == 0
+    return cols, iters.value
+
+
+def masked_equal(got, want, what):
+    ok = (got.status & ~np.uint32(abi.REP_UNFINISHED)) == 0
+    for name in ("end_time", "n_events", "trace_hash"):
+        assert np.array_equal(getattr(got, name)[ok], getattr(want, name)[ok]), f"{what}: {name}"
+    for k in range(2):
+        assert np.array_equal(got.f64[k][ok].view(np.uint64), want.f64[k][ok].view(np.uint64)), f"{what}: f64[{k}]"
+        assert np.array_equal(got.i64[k][ok], want.i64[k][ok]), f"{what}: i64[{k}]"
+    return ok
+
+
+@pytest.mark.parametrize("lam,n_packets,n_reps", [(5.0, 2000, 300), (0.5, 1000, 200), (9.0, 1500, 200),
+                                                  (12.0, 300, 100), (5.0, 2, 50), (5.0, 3, 50), (5.0, 7, 50)])
+def test_lane_matches_oracle(lane_lib, port, lam, n_packets, n_reps):
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, _ = run_lanes(lane_lib, p, n_reps)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, n_reps, threads=oracles.os.cpu_count())
+    ok = masked_equal(got, want, f"lambda={lam} n={n_packets}")
+    if lam <= 5.0:
+        assert ok.all()                       # the 32-entry ring holds every queue at rho <= 0.5 here
+    bad = got.status[~ok]
+    assert ((bad & (abi.REP_QUEUE_OVERFLOW | abi.REP_TIME_RANGE)) != 0).all()   # only "redo me" flags
+
+
+@pytest.mark.parametrize("event_slots,ring_cap", [(1, 32), (2, 8), (3, 5), (6, 32), (4, 2), (4, 3)])
+def test_slot_and_ring_shapes_do_not_change_results(lane_lib, port, event_slots, ring_cap):
+    p = abi.MM1Params(6.0, 10.0, 600)
+    got, _ = run_lanes(lane_lib, p, 150, seed=3, ring_cap=ring_cap, event_slots=event_slots)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 3, 0, 150, threads=4)
+    ok = masked_equal(got, want, f"slots={event_slots} cap={ring_cap}")
+    if ring_cap >= 32:
+        assert ok.mean() > 0.9
+    # a replication is flagged exactly when its queue outgrew the ring (the pair-wise generation
+    # may give up one entry early)
+    assert (want.i64[1][~ok] >= ring_cap - 1).all()
+    assert (want.i64[1][ok] <= ring_cap).all()
+
+
+@pytest.mark.parametrize("until", [0, 1, 999, 20000, 10 ** 7])
+def test_lane_run_until(lane_lib, port, until):
+    p = abi.MM1Params(5.0, 10.0, 800)
+    got, _ = run_lanes(lane_lib, p, 128, seed=5, until=until)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 5, 0, 128, threads=4, until=until)
+    assert masked_equal(got, want, f"until={until}").all()
+
+
+def test_lane_tick_range_guard(lane_lib, port):
+    p = abi.MM1Params(0.00002, 0.001, 400)
+    got, _ = run_lanes(lane_lib, p, 64)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, 64, threads=4)
+    ok = masked_equal(got, want, "slow arrivals")
+    assert (got.status[~ok] & abi.REP_TIME_RANGE).all()
+    assert (want.end_time[ok] < 2 ** 30).all()
+    assert (~ok).sum() > 32
+
+
+def test_lane_other_clocks(lane_lib, port):
+    p = abi.MM1Params(5.0, 10.0, 300)
+    for unit, prec, folded in [((1, abi.MILLISECONDS), (1, abi.MICROSECONDS), (1000, 1, 1e-6)),
+                               ((2, abi.SECONDS), (5, abi.MILLISECONDS), (400, 5, 1e-3))]:
+        got, _ = run_lanes(lane_lib, p, 64, seed=9, clock=folded)
+        want = port.run(abi.MODEL_MM1, p, abi.Clock.of(unit, prec), 9, 0, 64)
+        assert masked_equal(got, want, f"clock {unit}/{prec}").all()
+
+
+def test_lane_efficiency_at_the_headline_load(lane_lib):
+    """Two packets per iteration is the design point: at rho = 0.5 a lane must need barely more than
+    n_packets / 2 iterations (start-up and wind-down included)."""
+    p = abi.MM1Params(5.0, 10.0, 10000)
+    _, iters = run_lanes(lane_lib, p, 20)
+    assert iters / 20 < 10000 / 2 * 1.02 + 20

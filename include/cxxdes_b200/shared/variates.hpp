@@ -80,11 +80,13 @@ static __device__ __constant__ unsigned long long CXB_LN2_DEV[2] = {CXB_LN2_HI_B
 // absolute error < 2^-54 everywhere (tests/test_shared_math.py).
 template <typename Table>
 CXB_HD double log_pos(double w, const Table *table) {
+    // CXB_LOG_OFF has a zero low word, so the index arithmetic only touches the high word.
     const uint64_t ix = double_as_bits(w);
-    const uint64_t tmp = ix - CXB_LOG_OFF;
-    const int i = (int)((tmp >> (52 - CXB_LOG_TABLE_BITS)) & ((1 << CXB_LOG_TABLE_BITS) - 1));
-    const int k = (int)((int64_t)tmp >> 52);
-    const uint64_t iz = ix - (tmp & 0xFFF0000000000000ULL);
+    const uint32_t hx = (uint32_t)(ix >> 32);
+    const uint32_t tmp = hx - (uint32_t)(CXB_LOG_OFF >> 32);
+    const int i = (int)((tmp >> (20 - CXB_LOG_TABLE_BITS)) & ((1 << CXB_LOG_TABLE_BITS) - 1));
+    const int k = (int)tmp >> 20;
+    const uint64_t iz = ((uint64_t)(hx - (tmp & 0xFFF00000u)) << 32) | (uint32_t)ix;
     const double z = bits_as_double(iz);
     const double invc = bits_as_double(table[i].invc_bits);
     const double logc = bits_as_double(table[i].logc_bits);
@@ -96,7 +98,12 @@ CXB_HD double log_pos(double w, const Table *table) {
     const double ln2_hi = bits_as_double(CXB_LN2_HI_BITS), ln2_lo = bits_as_double(CXB_LN2_LO_BITS);
 #endif
     const double r = fma_rn(z, invc, -1.0);
+#if defined(__CUDA_ARCH__)
+    // (double)k without the conversion unit: 2^52 + 2^31 + k sits exactly in the mantissa
+    const double kd = __hiloint2double(0x43300000, k ^ (int)0x80000000) - 4503601774854144.0;
+#else
     const double kd = (double)k;
+#endif
     const double t = fma_rn(kd, ln2_hi, logc);
     const double hi = t + r;
     const double lo = (t - hi) + r;

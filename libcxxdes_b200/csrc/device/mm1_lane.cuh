@@ -9,6 +9,7 @@
 // (producer_consumer.cpp:34,50).  So every lane generates packets in lock step -- two per
 // iteration, one Philox block per stream yielding both draws of the block -- and writes
 //      ring[j] = { A_j = tick at which the producer puts packet j,  s_j = service ticks }
+// (both stored as heap keys, see `lane`)
 // into its shared-memory ring.  The ring is the sync::queue<double> of the model extended by the
 // packets that are generated but not yet put:  entries [k, i) are queued, [i, g) are ahead.
 // The event loop (environment::step, environment.ipp:117-146) then only does bookkeeping:
@@ -24,6 +25,102 @@
 #include "cxxdes_b200/shared/philox.hpp"
 #include "cxxdes_b200/shared/trace_hash.hpp"
 #include "cxxdes_b200/shared/variates.hpp"
+
+// PTX text of one steady-state slot (lane::fast_slot_ptx below; the commented C++ twin is
+// lane::fast_slot).  Operands: %0 kp, %1 kc, %2 i, %3 k, %4 now, %5 n_events, %6 max_queue,
+// %7 x_tick, %8 hash, %9 total_latency | %10 glim, %11 g, %12 agk, %13 ring base, %14 sec_per_unit,
+// %15 n_packets, %16 4*until+3, %17 tick_mult, %18 slot mask, %19 slot stride in bytes.
+//   A    front token, can the lane dispatch (pc: consumer resumes, pp: producer puts)
+//   DUE  run_until horizon
+//   B    woke?, ring[i+1].ak and ring[k], environment::step (clock, count, fold) once or, when the
+//        put wakes the consumer, twice; now and x as doubles
+//   MULT time_precision().t
+//   C    total_latency += now_seconds() - x; put: i, max_queue, kp, tie bit; pop or park
+#define CXB_MM1_SLOT_A \
+    "{\n\t" \
+    ".reg .pred pc, pp, pw, pok, pa, ppop, ppark, pg, pdue;\n\t" \
+    ".reg .b32 key, t, i1, sl, addr, akn, eak, es4, cnt, hl, hh, rl, rh, bh, ml, mh, kb;\n\t" \
+    ".reg .b64 m;\n\t" \
+    ".reg .f64 dt, dx, lat;\n\t" \
+    "setp.lt.u32 pc, %1, %0;\n\t" \
+    "min.u32 key, %1, %0;\n\t" \
+    "setp.lt.and.u32 pp, %2, %10, !pc;\n\t"
+#define CXB_MM1_SLOT_DUE \
+    "setp.le.u32 pdue, key, %16;\n\t" \
+    "and.pred pc, pc, pdue;\n\t" \
+    "and.pred pp, pp, pdue;\n\t"
+#define CXB_MM1_SLOT_B \
+    "setp.eq.and.u32 pw, %1, 0xffffffff, pp;\n\t" \
+    "shr.u32 t, key, 2;\n\t" \
+    "add.u32 i1, %2, 1;\n\t" \
+    "and.b32 sl, i1, %18;\n\t" \
+    "mad.lo.u32 addr, sl, %19, %13;\n\t" \
+    "ld.shared.u32 akn, [addr];\n\t" \
+    "and.b32 sl, %3, %18;\n\t" \
+    "mad.lo.u32 addr, sl, %19, %13;\n\t" \
+    "ld.shared.v2.u32 {eak, es4}, [addr];\n\t" \
+    "or.pred pok, pc, pp;\n\t" \
+    "mov.b64 {hl, hh}, %8;\n\t" \
+    "shf.l.wrap.b32 rh, hl, hh, 5;\n\t" \
+    "shf.l.wrap.b32 rl, hh, hl, 5;\n\t" \
+    "selp.b32 bh, 0x200, 0x100, pc;\n\t" \
+    "xor.b32 rl, rl, t;\n\t" \
+    "xor.b32 rh, rh, bh;\n\t" \
+    "mul.wide.u32 m, rl, 0x7F4A7C15;\n\t" \
+    "mov.b64 {ml, mh}, m;\n\t" \
+    "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
+    "mad.lo.u32 mh, rh, 0x7F4A7C15, mh;\n\t" \
+    "@pok mov.b32 hl, ml;\n\t" \
+    "@pok mov.b32 hh, mh;\n\t" \
+    "@pok mov.b32 %4, t;\n\t" \
+    "@pok add.u32 %5, %5, 1;\n\t" \
+    "shf.l.wrap.b32 rh, hl, hh, 5;\n\t" \
+    "shf.l.wrap.b32 rl, hh, hl, 5;\n\t" \
+    "xor.b32 rl, rl, t;\n\t" \
+    "xor.b32 rh, rh, 0x200;\n\t" \
+    "mul.wide.u32 m, rl, 0x7F4A7C15;\n\t" \
+    "mov.b64 {ml, mh}, m;\n\t" \
+    "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
+    "mad.lo.u32 mh, rh, 0x7F4A7C15, mh;\n\t" \
+    "@pw mov.b32 hl, ml;\n\t" \
+    "@pw mov.b32 hh, mh;\n\t" \
+    "@pw add.u32 %5, %5, 1;\n\t" \
+    "mov.b64 %8, {hl, hh};\n\t" \
+    "mov.b64 dt, {t, 0x43300000};\n\t" \
+    "mov.b64 dx, {%7, 0x43300000};\n\t" \
+    "sub.rn.f64 dt, dt, 0d4330000000000000;\n\t" \
+    "sub.rn.f64 dx, dx, 0d4330000000000000;\n\t"
+#define CXB_MM1_SLOT_MULT \
+    "mul.rn.f64 dt, dt, %17;\n\t" \
+    "mul.rn.f64 dx, dx, %17;\n\t"
+#define CXB_MM1_SLOT_C \
+    "mul.rn.f64 dt, dt, %14;\n\t" \
+    "mul.rn.f64 dx, dx, %14;\n\t" \
+    "sub.rn.f64 lat, dt, dx;\n\t" \
+    "@pc add.rn.f64 %9, %9, lat;\n\t" \
+    "@pp mov.b32 %2, i1;\n\t" \
+    "sub.u32 cnt, i1, %3;\n\t" \
+    "max.u32 cnt, cnt, %6;\n\t" \
+    "@pp mov.b32 %6, cnt;\n\t" \
+    "setp.lt.u32 pg, i1, %11;\n\t" \
+    "selp.b32 akn, akn, %12, pg;\n\t" \
+    "@pp mov.b32 %0, akn;\n\t" \
+    "@pp and.b32 %1, %1, 0xfffffffd;\n\t" \
+    "or.pred pa, pc, pw;\n\t" \
+    "setp.ne.and.u32 ppop, %2, %3, pa;\n\t" \
+    "setp.eq.and.u32 ppark, %2, %3, pa;\n\t" \
+    "and.b32 kb, key, 0xfffffffc;\n\t" \
+    "@ppop shr.u32 %7, eak, 2;\n\t" \
+    "@ppop add.u32 %1, kb, es4;\n\t" \
+    "@ppop add.u32 %3, %3, 1;\n\t" \
+    "@ppark mov.b32 %1, 0xffffffff;\n\t" \
+    "}"
+#define CXB_MM1_SLOT_OPERANDS \
+    : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(now), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
+    "+l"(hash), "+d"(total_latency) \
+    : "r"(glim), "r"(g), "r"(agk), "r"(base), "d"(c.sec_per_unit), "r"(c.n_packets), "r"(ukey), "d"(mult), \
+    "n"(MASK), "n"(STRIDE) \
+    : "memory"
 
 namespace cxb {
 
@@ -50,13 +147,30 @@ CXB_HD uint64_t fold(uint64_t h, uint32_t t, uint64_t bits) {
     return (rotl64(h, 5) ^ ((uint64_t)t ^ bits)) * TRACE_HASH_MUL;
 }
 
-// double -> u32 ticks, truncating, saturating (environment::real_to_sim, environment.ipp:79-82,
-// for values the range guard accepts; anything >= 2^28 trips the guard on both sides alike).
-CXB_HD uint32_t ticks_u32(double x) {
+// Integer <-> double conversions without the XU pipe (I2F/F2I issue at a quarter of the FP64 rate):
+// adding 2^52 puts an integer below 2^52 into the low mantissa bits, exactly.
+constexpr double TWO52 = 4503599627370496.0;
+
+CXB_HD double u32_to_double(uint32_t x) {
 #if defined(__CUDA_ARCH__)
-    return __double2uint_rz(x);
+    return __hiloint2double(0x43300000, (int)x) - TWO52;
 #else
-    return x >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)x;
+    return (double)x;
+#endif
+}
+
+// double -> ticks, truncating toward zero (environment::real_to_sim, environment.ipp:79-82) for
+// 0 <= x < 2^28; `bad` is raised for anything else (the caller then redoes the replication with
+// 64-bit ticks), identically on host and device.
+CXB_HD uint32_t ticks_u32(double x, uint32_t &bad) {
+#if defined(__CUDA_ARCH__)
+    const double y = __dadd_rz(x, TWO52);  // round toward zero = truncate, x >= 0
+    const uint32_t hi = (uint32_t)__double2hiint(y), lo = (uint32_t)__double2loint(y);
+    bad |= (hi ^ 0x43300000u) | (lo >> 28);  // exponent moved (x >= 2^52, inf, nan, x < 0) or >= 2^28
+    return lo;
+#else
+    if (!(x >= 0.0 && x < 268435456.0)) { bad |= 1u; return 0u; }
+    return (uint32_t)x;
 #endif
 }
 
@@ -66,15 +180,27 @@ struct constants {
     philox_schedule keys;
     double ticks_per_unit;   // (double)clock.ticks_per_unit
     double sec_per_unit;     // clock.seconds_per_tick_unit
-    int64_t tick_mult;       // clock.tick_mult
+    double tick_mult;        // (double)clock.tick_mult, < 2^23 so tick * tick_mult is exact in a double
     uint32_t n_packets;      // 2 <= n < 2^30
     uint32_t ring_cap;       // packets the ring may hold, 2 <= ring_cap <= physical slots
     uint32_t until;          // run_until horizon in ticks, EMPTY when there is none
 };
 
+// Compile-time variants of the lane code.
+enum : int {
+    MODE_UNTIL = 1,      // a run_until horizon is set (else the check is compiled out)
+    MODE_TICK_MULT = 2   // time_precision().t != 1: now_seconds needs the extra multiply
+};
+
+// Steady-state tokens are compared as one 32-bit key that carries the tie rule of the two-entry
+// libstdc++ heap ("equal (time, priority): the earlier push pops first", stl_heap.h:135-148):
+//      producer's token          4 * time + 1
+//      consumer's token          4 * time + 2     pushed after the producer's current token
+//                                4 * time + 0     pushed before it (the producer re-armed since)
+// so "the consumer's token pops next" is kc < kp.  Times stay below 2^30 (range guard).
 struct ring_entry {
-    uint32_t a;  // put tick of the packet
-    uint32_t s;  // service ticks the consumer sleeps after popping it
+    uint32_t ak;  // 4 * A_j + 1: the producer's token that puts packet j
+    uint32_t s4;  // 4 * s_j + 2: added to 4 * now when the consumer starts serving packet j
 };
 
 // One replication.  `Ring` gives ring_entry load(j) / uint32_t load_a(j) / store(j, e) on slot
@@ -82,36 +208,45 @@ struct ring_entry {
 struct lane {
     uint32_t ctr2, ctr3;        // Philox counter words 2,3 = global replication id
     uint32_t g;                 // packets generated so far (even)
-    uint32_t a_gen;             // A_g
+    uint32_t agk;               // 4 * A_g + 1
     uint32_t budget;            // A_g + sum of s_j, j < g: bounds every event time from above
     uint32_t i, k;              // packets put / popped
-    uint32_t t0, t1;            // two-slot heap; in the steady state t0 = producer's token,
-    uint32_t m0, m1;            //   t1 = consumer's timeout (EMPTY while it waits on queue.event_)
+    // steady state: exactly one producer token and at most one consumer token (its service timeout)
+    uint32_t kp, kc;            // their keys; kc == EMPTY while the consumer waits on queue.event_;
+    uint32_t glim;              //   kp == kc == EMPTY and glim == 0 outside the steady state, else glim == g
+    // start-up / wind-down: explicit two-slot heap of (time, tag)
+    uint32_t t0, t1, m0, m1;
+    uint32_t main_pc, cons_pc, remaining, waiting;
     uint32_t now, x_tick;
     uint32_t n_events;
     uint32_t max_queue;
     uint32_t status;
-    uint32_t main_pc, cons_pc, remaining;
     uint64_t hash;
     double total_latency;
-    bool waiting;               // consumer parked in queue.event_ (event.hpp:136-139); generic mode
-    bool fast;                  // steady-state representation
-    bool cfirst;                // steady state: on equal times the consumer's token pops first
 
     CXB_HD void init(uint64_t global_replication) {
         ctr2 = (uint32_t)global_replication;
         ctr3 = (uint32_t)(global_replication >> 32);
-        g = 0; a_gen = 0; budget = 0;
+        g = 0; agk = 1; budget = 0;
         i = k = 0;
+        kp = kc = EMPTY; glim = 0;
         t0 = 0; m0 = M_MAIN;     // environment::bind(co_main): start token {0, 0, main}
         t1 = EMPTY; m1 = M_NOOP;
+        main_pc = cons_pc = 0; remaining = 2; waiting = 0;
         now = 0; x_tick = 0;
         n_events = 0; max_queue = 0; status = 0;
-        main_pc = cons_pc = 0; remaining = 2;
         hash = TRACE_HASH_INIT;
         total_latency = 0.0;
-        waiting = false; fast = false; cfirst = false;
     }
+
+    // A lane without a replication: every step below is a no-op for it.
+    CXB_HD void idle() {
+        kp = kc = EMPTY; glim = 0;
+        t0 = t1 = EMPTY;
+        g = 0xFFFFFFFEu;
+    }
+
+    CXB_HD bool is_fast() const { return kp != EMPTY; }
 
     // ---- generation -----------------------------------------------------------------
     CXB_HD bool wants_packets(const constants &c) const { return g < c.n_packets; }
@@ -124,109 +259,151 @@ struct lane {
         const philox_block bp = philox4x32_10_scheduled(g >> 1, 1u, ctr2, ctr3, c.keys);
         const philox_block bc = philox4x32_10_scheduled(g >> 1, 2u, ctr2, ctr3, c.keys);
         // env.timeout(exponential()): timeout.ipp:184-187 -> real_to_sim
-        const uint32_t ia0 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[1] << 32) | bp.w[0], c.lambda, table) * c.ticks_per_unit);
-        const uint32_t ia1 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[3] << 32) | bp.w[2], c.lambda, table) * c.ticks_per_unit);
-        const uint32_t s0 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[1] << 32) | bc.w[0], c.mu, table) * c.ticks_per_unit);
-        const uint32_t s1 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[3] << 32) | bc.w[2], c.mu, table) * c.ticks_per_unit);
+        uint32_t bad = 0;
+        const uint32_t ia0 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[1] << 32) | bp.w[0], c.lambda, table) * c.ticks_per_unit, bad);
+        const uint32_t ia1 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[3] << 32) | bp.w[2], c.lambda, table) * c.ticks_per_unit, bad);
+        const uint32_t s0 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[1] << 32) | bc.w[0], c.mu, table) * c.ticks_per_unit, bad);
+        const uint32_t s1 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[3] << 32) | bc.w[2], c.mu, table) * c.ticks_per_unit, bad);
         // range guard: each delay < 2^28 and the bound on the last event time < 2^30, so no
-        // 32-bit sum below can wrap; otherwise the replication is redone with 64-bit ticks
+        // 32-bit sum or key below can wrap; otherwise the replication is redone with 64-bit ticks
         const uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
-        if (((ia0 | ia1 | s0 | s1) >= DRAW_LIMIT) | (new_budget >= TIME_LIMIT)) {
+        if ((bad != 0) | (new_budget >= TIME_LIMIT)) {
             status |= CXXDES_B200_REP_TIME_RANGE;
             return;
         }
         budget = new_budget;
-        const uint32_t a1 = a_gen + ia0;
+        const uint32_t a1k = agk + 4u * ia0;
         ring_entry e0, e1;
-        e0.a = a_gen; e0.s = s0;
-        e1.a = a1; e1.s = s1;
+        e0.ak = agk; e0.s4 = 4u * s0 + 2u;
+        e1.ak = a1k; e1.s4 = 4u * s1 + 2u;
         ring.store(g, e0);
         ring.store(g + 1, e1);
-        a_gen = a1 + ia1;
+        agk = a1k + 4u * ia1;
         g += 2;
+        glim = is_fast() ? g : 0u;
     }
 
     // The producer's event is next, its packet is not generated and the ring has no room: the
     // model's queue is longer than this ring.
     CXB_HD bool ring_exhausted(const constants &c) const {
         if (!wants_packets(c) || has_room(c) || i != g) return false;
-        if (fast) return !((t1 < t0) | ((t1 == t0) & cfirst));
+        if (is_fast()) return !(kc < kp);
         return m0 == M_PROD;
     }
 
     // ---- time of the next scheduled token -------------------------------------------------
-    CXB_HD uint32_t next_time() const { return (fast && t1 < t0) ? t1 : t0; }
+    CXB_HD uint32_t next_time() const { return is_fast() ? (kc < kp ? kc : kp) >> 2 : t0; }
 
+    template <int MODE>
     CXB_HD double seconds(const constants &c, uint32_t tick) const {
-        // environment::now_seconds, environment.ipp:29-36
-        if (c.tick_mult == 1) return (double)tick * c.sec_per_unit;
-        return (double)((int64_t)tick * c.tick_mult) * c.sec_per_unit;
+        // environment::now_seconds, environment.ipp:29-36: (double)(now * prec.t) * conv[prec.u];
+        // tick * prec.t < 2^53, so the product of the two doubles is that integer exactly
+        if (MODE & MODE_TICK_MULT) return (u32_to_double(tick) * c.tick_mult) * c.sec_per_unit;
+        return u32_to_double(tick) * c.sec_per_unit;
     }
 
     // ---- steady state: one event (two when a put wakes the consumer) ---------------------------
-    // Exactly one producer token (t0) and at most one consumer token (t1, always a timeout).
-    // With <= 2 entries the libstdc++ heap keeps the earlier push in front on equal keys
-    // (stl_heap.h:135-148), which `cfirst` records.  Returns false when nothing could be done.
-    template <typename Ring>
-    CXB_HD bool fast_slot(const constants &c, Ring &ring) {
-        const uint32_t tp = t0, tc = t1;
-        const bool c_goes = (tc < tp) | ((tc == tp) & cfirst);   // parked: tc == EMPTY > tp
-        const uint32_t t = c_goes ? tc : tp;
-        // the producer's event needs A_{i+1}, i.e. packet i generated; run_until stops at `until`
-        if (!(fast & (c_goes | (i < g)) & (t <= c.until))) return false;
-        // environment::step: pop, advance the clock, count, fold (tokens are scheduled at
-        // now + d with d >= 0, so time never runs backwards here)
-        now = t;
-        ++n_events;
-        hash = fold(hash, t, c_goes ? CONS_BITS : PROD_BITS);
-        bool attempt = c_goes;  // the consumer runs its pop step
-        if (c_goes) {
-            // total_latency += now_seconds() - x   (producer_consumer.cpp:52)
-            total_latency += seconds(c, t) - seconds(c, x_tick);
-        } else {
-            // q.put(now_seconds()) (queue.hpp:48-53): packet i, already in the ring with a == now
-            ++i;
-            const uint32_t count = i - k;
+    // Which process a lane resumes differs from lane to lane, so this is one straight line of
+    // predicated updates: a branch would make the warp run the producer's and the consumer's side
+    // one after the other.  Both ring reads are unconditional (any index maps into the ring).
+    // Lanes outside the steady state (or without a replication) fall through untouched.
+    template <int MODE, typename Ring>
+    CXB_HD void fast_slot(const constants &c, Ring &ring) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (Ring::HAS_PTX_SLOT) {
+            fast_slot_ptx<MODE, Ring::MASK, Ring::STRIDE>(c, ring.base);
+            return;
+        }
+#endif
+        const uint32_t key = kc < kp ? kc : kp;   // the front token
+        // consumer resumes from its service timeout / producer resumes: q.put(now_seconds()),
+        // queue.hpp:48-53, which needs A_{i+1}, i.e. packet i generated
+        bool cons = kc < kp;
+        bool put = !cons & (i < glim);
+        if (MODE & MODE_UNTIL) {
+            const bool due = key <= 4u * c.until + 3u;  // run_until stops at `until`
+            cons &= due;
+            put &= due;
+        }
+        const bool woke = put & (kc == EMPTY);    // ... and wake() finds the consumer parked
+        const uint32_t t = key >> 2;
+        const uint32_t i1 = i + 1;
+        const uint32_t next_ak = ring.load_a(i1);
+        const ring_entry e = ring.load(k);
+        // environment::step: pop, advance the clock, count, fold (tokens are scheduled at now + d
+        // with d >= 0, so time never runs backwards here)
+        if (cons | put) {
+            now = t;
+            ++n_events;
+            hash = fold(hash, t, cons ? CONS_BITS : PROD_BITS);
+        }
+        // The woken consumer's token {0 + now} was pushed before the producer's timeout, so it is
+        // the very next event (event.hpp:125-134): it is dispatched in the same slot.
+        if (woke) {
+            ++n_events;
+            hash = fold(hash, t, CONS_BITS);
+        }
+        // total_latency += now_seconds() - x   (producer_consumer.cpp:52)
+        const double lat = seconds<MODE>(c, t) - seconds<MODE>(c, x_tick);
+        if (cons) total_latency += lat;
+        if (put) {
+            // packet i is already in the ring with A_i == now; env.timeout(exponential()) expires
+            // at A_{i+1}; a consumer asleep in its service keeps the front place on a tie
+            i = i1;
+            const uint32_t count = i1 - k;
             max_queue = count > max_queue ? count : max_queue;
-            const uint32_t next_a = ring.load_a(i);
-            t0 = i < g ? next_a : a_gen;  // env.timeout(exponential()) expires at A_{i+1}
-            if (tc == EMPTY) {
-                // wake(): the parked consumer's token {0 + now} is pushed before the producer's
-                // timeout, so it is the very next event (event.hpp:125-134); handled here
-                ++n_events;
-                hash = fold(hash, t, CONS_BITS);
-                attempt = true;
-            } else {
-                cfirst = true;  // the producer's new token is behind the consumer's on a tie
-            }
+            kp = i1 < g ? next_ak : agk;
+            kc &= ~2u;
         }
-        if (attempt) {
-            if (i != k) {
-                // q.pop() succeeds (queue.hpp:58-65); timeout(exponential()) = now + s_k, pushed last
-                const ring_entry e = ring.load(k);
-                x_tick = e.a;
-                t1 = t + e.s;
-                cfirst = false;
-                ++k;
-            } else {
-                t1 = EMPTY;  // the consumer waits on queue.event_
-            }
+        // consumer: q.pop() (queue.hpp:58-65) succeeds -> timeout(exponential()) = now + s_k, pushed
+        // after the producer's token; or the consumer waits on queue.event_
+        const bool attempt = cons | woke;
+        const bool pop = attempt & (i != k);
+        const bool park = attempt & (i == k);
+        if (pop) {
+            x_tick = e.ak >> 2;
+            kc = (key & ~3u) + e.s4;
+            ++k;
         }
-        if (i + 1 >= c.n_packets) leave_fast();
-        return true;
+        if (park) kc = EMPTY;
     }
 
-    // The producer's last put ends the steady state: rebuild the generic two-slot heap.
+#if defined(__CUDA_ARCH__)
+    // The same slot, instruction for instruction, for a ring in shared memory (`base` = shared
+    // address of this thread's column, entry j at base + (j & MASK) * STRIDE).  nvcc turns the C++
+    // above into ~100 instructions per slot because its eight short-lived conditions do not fit
+    // the seven predicate registers once four slots are interleaved; spelled out it is ~60.
+    // Checked against the C++ version by the GPU parity tests (the host unit tests run the C++).
+    template <int MODE, int MASK, int STRIDE>
+    __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base) {
+        const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * c.until + 3u : 0xFFFFFFFFu;
+        const double mult = (MODE & MODE_TICK_MULT) ? c.tick_mult : 1.0;
+        // (four texts: the run_until check and the tick_mult multiply are left out when unused)
+        if constexpr (MODE == 0) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
+        else if constexpr (MODE == MODE_UNTIL) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
+        else if constexpr (MODE == MODE_TICK_MULT) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
+        else asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
+    }
+#endif
+
+    // The steady state ends TAIL puts before the producer's last one (checked once per iteration,
+    // so an iteration may run up to TAIL steady-state slots): rebuild the generic two-slot heap.
+    static constexpr uint32_t TAIL = 8;
+    CXB_HD void leave_fast_near_end(const constants &c) {
+        if (is_fast() && i + 1 + TAIL >= c.n_packets) leave_fast();
+    }
     CXB_HD void leave_fast() {
-        const uint32_t tp = t0, tc = t1;
-        const bool c_front = (tc < tp) | ((tc == tp) & cfirst);
-        waiting = tc == EMPTY;
+        const uint32_t tp = kp >> 2;
+        const uint32_t tc = kc == EMPTY ? EMPTY : kc >> 2;
+        const bool c_front = kc < kp;
+        waiting = kc == EMPTY ? 1u : 0u;
         t0 = c_front ? tc : tp;
         m0 = c_front ? M_CONS : M_PROD;
         t1 = c_front ? tp : tc;
         m1 = c_front ? M_PROD : M_CONS;
         cons_pc = waiting ? 1u : 2u;
-        fast = false;
+        kp = kc = EMPTY;
+        glim = 0;
     }
 
     CXB_HD void push(uint32_t t, uint32_t m) {
@@ -241,9 +418,9 @@ struct lane {
     }
 
     // ---- start-up and wind-down: environment::step on the explicit two-slot heap ---------------
-    template <typename Ring>
+    template <int MODE, typename Ring>
     CXB_HD bool generic_step(const constants &c, Ring &ring) {
-        if (fast || t0 == EMPTY || t0 > c.until) return false;
+        if (is_fast() || t0 == EMPTY || t0 > c.until) return false;
         const uint32_t n = c.n_packets;
         if (m0 == M_PROD && i < n && i >= g) return false;  // A_{i+1} not generated yet
         const uint32_t t = t0;
@@ -255,28 +432,28 @@ struct lane {
         if (m == M_PROD) {
             // producer body, producer_consumer.cpp:31-37
             if (i < n) {
-                ++i;                                 // q.put(now_seconds()): ring entry i-1, a == now
+                ++i;                                 // q.put(now_seconds()): ring entry i-1, A == now
                 const uint32_t count = i - k;
                 max_queue = count > max_queue ? count : max_queue;
                 // wake(): the parked consumer's token goes in before the producer's own timeout
-                if (waiting) { push(now, M_CONS); waiting = false; }
-                const uint32_t next_a = ring.load_a(i);
-                push(i < g ? next_a : a_gen, M_PROD);
+                if (waiting) { push(now, M_CONS); waiting = 0; }
+                const uint32_t next_ak = ring.load_a(i);
+                push((i < g ? next_ak : agk) >> 2, M_PROD);
             } else {
                 push(now, M_HANDLER);                // co_return -> completion carrying the all_of handler
             }
         } else if (m == M_CONS) {
             // consumer body, producer_consumer.cpp:39-54
-            if (cons_pc == 2) total_latency += seconds(c, now) - seconds(c, x_tick);  // :52
+            if (cons_pc == 2) total_latency += seconds<MODE>(c, now) - seconds<MODE>(c, x_tick);  // :52
             if (i != k) {
                 const ring_entry e = ring.load(k);   // q.pop() succeeds, queue.hpp:58-65
-                x_tick = e.a;
+                x_tick = e.ak >> 2;
                 ++k;
                 cons_pc = 2;
                 if (k == n) push(now, M_HANDLER);    // consumer returns (:45-48)
-                else push(now + e.s, M_CONS);
+                else push(now + (e.s4 >> 2), M_CONS);
             } else {
-                waiting = true;                      // ... or waits on queue.event_
+                waiting = 1;                         // ... or waits on queue.event_
                 cons_pc = 1;
             }
         } else if (m == M_HANDLER) {
@@ -293,16 +470,15 @@ struct lane {
         }
         // both processes running, only their tokens scheduled, the consumer parked or asleep in
         // its service timeout: switch to the steady-state representation
-        if (status == 0 && main_pc == 1 && remaining == 2 && i >= 1 && i + 1 < n && t0 != EMPTY) {
-            const bool prod_front = m0 == M_PROD && (t1 == EMPTY ? waiting : (m1 == M_CONS && cons_pc == 2));
+        if (status == 0 && main_pc == 1 && remaining == 2 && i >= 1 && i + 1 + TAIL < n && t0 != EMPTY) {
+            const bool prod_front = m0 == M_PROD && (t1 == EMPTY ? waiting != 0 : (m1 == M_CONS && cons_pc == 2));
             const bool cons_front = m0 == M_CONS && cons_pc == 2 && t1 != EMPTY && m1 == M_PROD;
             if (prod_front || cons_front) {
                 const uint32_t tp = prod_front ? t0 : t1;
                 const uint32_t tc = prod_front ? t1 : t0;
-                t0 = tp;
-                t1 = tc;
-                cfirst = cons_front;
-                fast = true;
+                kp = 4u * tp + 1u;
+                kc = tc == EMPTY ? EMPTY : 4u * tc + (cons_front ? 0u : 2u);
+                glim = g;
             }
         }
         return true;

@@ -26,35 +26,44 @@ namespace {
 
 template <int SLOTS, int THREADS>
 struct smem_ring {
-    uint2 *base;  // this thread's column: entry j at base[(j % SLOTS) * THREADS]
+    uint32_t base;  // shared-window address of this thread's column: entry j at base + (j % SLOTS) * THREADS * 8
     // 8-byte entries, THREADS * 8 bytes between slots: a warp's access touches each bank pair
-    // once whatever slot each lane is at (two conflict-free wavefronts)
+    // once whatever slot each lane is at (two conflict-free wavefronts).  Explicit ld/st.shared
+    // on a 32-bit address: no generic-to-shared conversion per access.
+    static_assert((SLOTS & (SLOTS - 1)) == 0, "ring slots must be a power of two");
+    static constexpr bool HAS_PTX_SLOT = true;
+    static constexpr int MASK = SLOTS - 1;
+    static constexpr int STRIDE = THREADS * 8;
+    __device__ __forceinline__ uint32_t addr(uint32_t j) const { return base + (j & (SLOTS - 1)) * (THREADS * 8); }
     __device__ __forceinline__ mm1::ring_entry load(uint32_t j) const {
-        const uint2 v = base[(j & (SLOTS - 1)) * THREADS];
         mm1::ring_entry e;
-        e.a = v.x;
-        e.s = v.y;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.ak), "=r"(e.s4) : "r"(addr(j)));
         return e;
     }
-    __device__ __forceinline__ uint32_t load_a(uint32_t j) const { return base[(j & (SLOTS - 1)) * THREADS].x; }
+    __device__ __forceinline__ uint32_t load_a(uint32_t j) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr(j)));
+        return v;
+    }
     __device__ __forceinline__ void store(uint32_t j, const mm1::ring_entry &e) const {
-        base[(j & (SLOTS - 1)) * THREADS] = make_uint2(e.a, e.s);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr(j)), "r"(e.ak), "r"(e.s4) : "memory");
     }
 };
 
 }  // namespace
 
-template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS>
+template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     stage_log_table(table, sh.log_table);
     smem_ring<RING_SLOTS, THREADS> ring;
-    ring.base = (uint2 *)(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x;
+    ring.base = (uint32_t)__cvta_generic_to_shared(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x * 8u;
 
     mm1::lane L;
     L.init(0);
+    L.idle();
     bool active = false, exhausted = false;
     uint64_t rep = 0;
 
@@ -77,14 +86,14 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         __syncwarp();
 
         // ---- 2. start-up / wind-down events ----
-        if (active && !L.fast) L.generic_step(c, ring);
+        if (active && !L.is_fast()) L.template generic_step<MODE>(c, ring);
         __syncwarp();
 
         // ---- 3. steady-state events ----
+        static_assert(EVENT_SLOTS <= (int)mm1::lane::TAIL, "the end-of-steady-state check runs once per iteration");
+        L.leave_fast_near_end(c);
 #pragma unroll
-        for (int s = 0; s < EVENT_SLOTS; ++s) {
-            if (active) L.fast_slot(c, ring);
-        }
+        for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
 
         // ---- 4. end of this lane's replication? ----
         if (active && L.finished(c)) {
@@ -111,7 +120,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 o.i64[1] = (int64_t)L.max_queue;
                 store_result(out, rep, o);
             }
-            L.fast = false;
+            L.idle();
         }
     }
 }
@@ -124,7 +133,8 @@ constexpr int AH_EVENT_SLOTS = 4;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
 }  // namespace
 
-void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count) {
+void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
+                    int64_t tick_mult) {
     p.ah_threads = AH_THREADS;
     p.ah_blocks = sm_count * AH_MIN_BLOCKS;
     p.ah_smem_bytes = TABLE_BYTES + (size_t)AH_RING_SLOTS * AH_THREADS * sizeof(uint2);
@@ -138,12 +148,30 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
     const double rho = prm.lambda / prm.mu;
     const double q = (double)cap - 3.0;
     const double p_over = rho >= 1.0 ? 1.0 : pow(rho, q > 0 ? q : 0.0) * (double)prm.n_packets;
-    p.ah_direct_global = !(p_over < 0.02);
+    // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds())
+    p.ah_direct_global = !(p_over < 0.02) || tick_mult >= (1 << 23);
 }
 
-cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    return cudaFuncSetAttribute(mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS>,
+namespace {
+template <int MODE>
+cudaError_t configure_mode(const mm1_fused_plan &plan) {
+    return cudaFuncSetAttribute(mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS, MODE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.ah_smem_bytes);
+}
+template <int MODE>
+void launch_mode(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                 const mm1_fused_plan &plan, cudaStream_t stream) {
+    mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS, MODE>
+        <<<plan.ah_blocks, AH_THREADS, plan.ah_smem_bytes, stream>>>(c, prm, sh, out);
+}
+}  // namespace
+
+cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
+    cudaError_t e = configure_mode<0>(plan);
+    if (e == cudaSuccess) e = configure_mode<1>(plan);
+    if (e == cudaSuccess) e = configure_mode<2>(plan);
+    if (e == cudaSuccess) e = configure_mode<3>(plan);
+    return e;
 }
 
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
@@ -154,12 +182,17 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
     c.ticks_per_unit = (double)sh.clk.ticks_per_unit;
     c.sec_per_unit = sh.clk.seconds_per_tick_unit;
-    c.tick_mult = sh.clk.tick_mult;
+    c.tick_mult = (double)sh.clk.tick_mult;
     c.n_packets = (uint32_t)prm.n_packets;
     c.ring_cap = plan.ah_ring_cap;
     c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
-    mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS>
-        <<<plan.ah_blocks, AH_THREADS, plan.ah_smem_bytes, stream>>>(c, prm, sh, out);
+    const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
+    switch (mode) {
+        case 0: launch_mode<0>(c, prm, sh, out, plan, stream); break;
+        case 1: launch_mode<1>(c, prm, sh, out, plan, stream); break;
+        case 2: launch_mode<2>(c, prm, sh, out, plan, stream); break;
+        default: launch_mode<3>(c, prm, sh, out, plan, stream); break;
+    }
     return cudaGetLastError();
 }
 

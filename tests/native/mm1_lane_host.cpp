@@ -12,10 +12,11 @@ using namespace cxb;
 
 namespace {
 struct host_ring {
+    static constexpr bool HAS_PTX_SLOT = false;
     std::vector<mm1::ring_entry> slots;
     explicit host_ring(uint32_t n) : slots(n) {}
     mm1::ring_entry load(uint32_t j) const { return slots[j & (slots.size() - 1)]; }
-    uint32_t load_a(uint32_t j) const { return slots[j & (slots.size() - 1)].a; }
+    uint32_t load_a(uint32_t j) const { return slots[j & (slots.size() - 1)].ak; }
     void store(uint32_t j, const mm1::ring_entry &e) { slots[j & (slots.size() - 1)] = e; }
 };
 }  // namespace
@@ -23,14 +24,14 @@ struct host_ring {
 extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t ticks_per_unit, int64_t tick_mult,
                                  double sec_per_unit, uint64_t seed, uint64_t first, uint64_t n_reps,
                                  int64_t until, uint32_t ring_cap, uint32_t ring_slots, int event_slots,
-                                 const cxxdes_b200_columns *out, uint64_t *iterations) {
+                                 int general_mode, const cxxdes_b200_columns *out, uint64_t *iterations) {
     mm1::constants c;
     c.lambda = make_divisor(prm->lambda);
     c.mu = make_divisor(prm->mu);
     c.keys = philox_schedule_of((uint32_t)seed, (uint32_t)(seed >> 32));
     c.ticks_per_unit = (double)ticks_per_unit;
     c.sec_per_unit = sec_per_unit;
-    c.tick_mult = tick_mult;
+    c.tick_mult = (double)tick_mult;
     c.n_packets = (uint32_t)prm->n_packets;
     c.ring_cap = ring_cap;
     c.until = (until < 0 || until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)until;
@@ -45,8 +46,19 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
                 if (L.has_room(c)) L.generate_pair(c, ring, LOG_TABLE_HOST);
                 else if (L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
             }
-            if (!L.fast) L.generic_step(c, ring);
-            for (int s = 0; s < event_slots; ++s) L.fast_slot(c, ring);
+            // MODE 3 = run_until check + tick_mult multiply compiled in: same results as the
+            // specialised modes (a multiply by 1.0 and a compare with EMPTY change nothing)
+            if (!L.is_fast()) L.generic_step<3>(c, ring);
+            L.leave_fast_near_end(c);
+            for (int s = 0; s < event_slots; ++s) {
+                const int mode = general_mode ? 3 : (c.until != mm1::EMPTY ? 1 : 0) | (tick_mult != 1 ? 2 : 0);
+                switch (mode) {
+                    case 0: L.fast_slot<0>(c, ring); break;
+                    case 1: L.fast_slot<1>(c, ring); break;
+                    case 2: L.fast_slot<2>(c, ring); break;
+                    default: L.fast_slot<3>(c, ring); break;
+                }
+            }
             if (L.finished(c)) break;
         }
         uint32_t status = L.status;

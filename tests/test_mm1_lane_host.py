@@ -29,18 +29,18 @@ def lane_lib():
     lib = C.CDLL(str(OUT))
     lib.mm1_lane_host_run.restype = C.c_int
     lib.mm1_lane_host_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_uint64,
-                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int,
+                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                       C.POINTER(abi.Columns), C.POINTER(C.c_uint64)]
     return lib
 
 
 def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=32, ring_slots=32, event_slots=4,
-              clock=(1000, 1, 1e-3)):
+              clock=(1000, 1, 1e-3), general_mode=0):
     cols = abi.HostColumns(n_reps)
     st = cols.as_struct()
     iters = C.c_uint64()
     rc = lib.mm1_lane_host_run(C.addressof(p), clock[0], clock[1], clock[2], seed, first, n_reps, until,
-                               ring_cap, ring_slots, event_slots, C.byref(st), C.byref(iters))
+                               ring_cap, ring_slots, event_slots, general_mode, C.byref(st), C.byref(iters))
     assert rc == 0
     return cols, iters.value
 
@@ -107,6 +107,15 @@ def test_lane_other_clocks(lane_lib, port):
         got, _ = run_lanes(lane_lib, p, 64, seed=9, clock=folded)
         want = port.run(abi.MODEL_MM1, p, abi.Clock.of(unit, prec), 9, 0, 64)
         assert masked_equal(got, want, f"clock {unit}/{prec}").all()
+
+
+def test_compile_time_modes_agree(lane_lib):
+    """The specialised variants (no horizon, tick_mult == 1) compute what the general one does."""
+    p = abi.MM1Params(5.0, 10.0, 500)
+    for until, clock in [(-1, (1000, 1, 1e-3)), (30000, (1000, 1, 1e-3)), (-1, (400, 5, 1e-3)), (9000, (400, 5, 1e-3))]:
+        a, _ = run_lanes(lane_lib, p, 64, seed=11, until=until, clock=clock)
+        b, _ = run_lanes(lane_lib, p, 64, seed=11, until=until, clock=clock, general_mode=1)
+        golden_util.assert_columns_equal(a, b, what=f"until={until} clock={clock}")
 
 
 def test_lane_efficiency_at_the_headline_load(lane_lib):

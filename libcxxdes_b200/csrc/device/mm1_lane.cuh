@@ -27,100 +27,89 @@
 #include "cxxdes_b200/shared/variates.hpp"
 
 // PTX text of one steady-state slot (lane::fast_slot_ptx below; the commented C++ twin is
-// lane::fast_slot).  Operands: %0 kp, %1 kc, %2 i, %3 k, %4 now, %5 n_events, %6 max_queue,
-// %7 x_tick, %8 hash, %9 total_latency | %10 glim, %11 g, %12 agk, %13 ring base, %14 sec_per_unit,
-// %15 n_packets, %16 4*until+3, %17 tick_mult, %18 slot mask, %19 slot stride in bytes.
-//   A    front token, can the lane dispatch (pc: consumer resumes, pp: producer puts)
+// lane::fast_slot).  Operands: %0 kp, %1 kc, %2 i, %3 k, %4 n_events, %5 max_queue, %6 x_tick,
+// %7 hash, %8 total_latency | %9 glim, %10 ring base, %11 sec_per_unit, %12 4*until+3,
+// %13 tick_mult, %14 slot mask, %15 slot stride in bytes.
+//   A    front token; can the lane dispatch (pc: consumer resumes, pp: producer puts)
 //   DUE  run_until horizon
-//   B    woke?, ring[i+1].ak and ring[k], environment::step (clock, count, fold) once or, when the
-//        put wakes the consumer, twice; now and x as doubles
+//   B    woke?, ring[i+1].ak and ring[k], environment::step (fold) once or, when the put wakes
+//        the consumer, twice; now and x as doubles
 //   MULT time_precision().t
 //   C    total_latency += now_seconds() - x; put: i, max_queue, kp, tie bit; pop or park
+// The SM's integer ALU pipe issues one warp instruction every other cycle and is what bounds this
+// kernel, so shifts and selects are spelled as multiplies where the FMA pipe can do them:
+// key >> 2 = mulhi(key, 2^30); rotl64(h, 5) from two 32x32->64 multiplies by 32; the folded hash is
+// written by predicated multiplies instead of being selected.
 #define CXB_MM1_SLOT_A \
     "{\n\t" \
-    ".reg .pred pc, pp, pw, pok, pa, ppop, ppark, pg, pdue;\n\t" \
-    ".reg .b32 key, t, i1, sl, addr, akn, eak, es4, cnt, hl, hh, rl, rh, bh, ml, mh, kb;\n\t" \
+    ".reg .pred pc, pp, pw, pok, pa, ppop, pdue;\n\t" \
+    ".reg .b32 key, t, i1, sl, addr, akn, eak, es4, cnt, hl, hh, a0, a1, b0, b1, rl, rh, bh, mh, ts;\n\t" \
     ".reg .b64 m;\n\t" \
     ".reg .f64 dt, dx, lat;\n\t" \
     "setp.lt.u32 pc, %1, %0;\n\t" \
     "min.u32 key, %1, %0;\n\t" \
-    "setp.lt.and.u32 pp, %2, %10, !pc;\n\t"
+    "setp.lt.and.u32 pp, %2, %9, !pc;\n\t"
 #define CXB_MM1_SLOT_DUE \
-    "setp.le.u32 pdue, key, %16;\n\t" \
+    "setp.le.u32 pdue, key, %12;\n\t" \
     "and.pred pc, pc, pdue;\n\t" \
     "and.pred pp, pp, pdue;\n\t"
+#define CXB_MM1_SLOT_FOLD(PRED, BITS) \
+    "mul.wide.u32 m, hl, 32;\n\t" \
+    "mov.b64 {a0, a1}, m;\n\t" \
+    "mul.wide.u32 m, hh, 32;\n\t" \
+    "mov.b64 {b0, b1}, m;\n\t" \
+    "lop3.b32 rl, a0, b1, t, 0x56;\n\t" \
+    "lop3.b32 rh, b0, a1, " BITS ", 0x56;\n\t" \
+    "mul.hi.u32 mh, rl, 0x7F4A7C15;\n\t" \
+    "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
+    "@" PRED " mad.lo.u32 hh, rh, 0x7F4A7C15, mh;\n\t" \
+    "@" PRED " mul.lo.u32 hl, rl, 0x7F4A7C15;\n\t"
 #define CXB_MM1_SLOT_B \
     "setp.eq.and.u32 pw, %1, 0xffffffff, pp;\n\t" \
-    "shr.u32 t, key, 2;\n\t" \
+    "mul.hi.u32 t, key, 0x40000000;\n\t" \
     "add.u32 i1, %2, 1;\n\t" \
-    "and.b32 sl, i1, %18;\n\t" \
-    "mad.lo.u32 addr, sl, %19, %13;\n\t" \
+    "and.b32 sl, i1, %14;\n\t" \
+    "mad.lo.u32 addr, sl, %15, %10;\n\t" \
     "ld.shared.u32 akn, [addr];\n\t" \
-    "and.b32 sl, %3, %18;\n\t" \
-    "mad.lo.u32 addr, sl, %19, %13;\n\t" \
+    "and.b32 sl, %3, %14;\n\t" \
+    "mad.lo.u32 addr, sl, %15, %10;\n\t" \
     "ld.shared.v2.u32 {eak, es4}, [addr];\n\t" \
     "or.pred pok, pc, pp;\n\t" \
-    "mov.b64 {hl, hh}, %8;\n\t" \
-    "shf.l.wrap.b32 rh, hl, hh, 5;\n\t" \
-    "shf.l.wrap.b32 rl, hh, hl, 5;\n\t" \
+    "mov.b64 {hl, hh}, %7;\n\t" \
     "selp.b32 bh, 0x200, 0x100, pc;\n\t" \
-    "xor.b32 rl, rl, t;\n\t" \
-    "xor.b32 rh, rh, bh;\n\t" \
-    "mul.wide.u32 m, rl, 0x7F4A7C15;\n\t" \
-    "mov.b64 {ml, mh}, m;\n\t" \
-    "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
-    "mad.lo.u32 mh, rh, 0x7F4A7C15, mh;\n\t" \
-    "@pok mov.b32 hl, ml;\n\t" \
-    "@pok mov.b32 hh, mh;\n\t" \
-    "@pok mov.b32 %4, t;\n\t" \
-    "@pok add.u32 %5, %5, 1;\n\t" \
-    "shf.l.wrap.b32 rh, hl, hh, 5;\n\t" \
-    "shf.l.wrap.b32 rl, hh, hl, 5;\n\t" \
-    "xor.b32 rl, rl, t;\n\t" \
-    "xor.b32 rh, rh, 0x200;\n\t" \
-    "mul.wide.u32 m, rl, 0x7F4A7C15;\n\t" \
-    "mov.b64 {ml, mh}, m;\n\t" \
-    "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
-    "mad.lo.u32 mh, rh, 0x7F4A7C15, mh;\n\t" \
-    "@pw mov.b32 hl, ml;\n\t" \
-    "@pw mov.b32 hh, mh;\n\t" \
-    "@pw add.u32 %5, %5, 1;\n\t" \
-    "mov.b64 %8, {hl, hh};\n\t" \
-    "mov.b64 dt, {t, 0x43300000};\n\t" \
-    "mov.b64 dx, {%7, 0x43300000};\n\t" \
+    CXB_MM1_SLOT_FOLD("pok", "bh") \
+    CXB_MM1_SLOT_FOLD("pw", "0x200") \
+    "mov.b64 %7, {hl, hh};\n\t" \
+    "selp.b32 ts, t, %6, pc;\n\t" \
+    "mov.b64 dt, {ts, 0x43300000};\n\t" \
+    "mov.b64 dx, {%6, 0x43300000};\n\t" \
     "sub.rn.f64 dt, dt, 0d4330000000000000;\n\t" \
     "sub.rn.f64 dx, dx, 0d4330000000000000;\n\t"
 #define CXB_MM1_SLOT_MULT \
-    "mul.rn.f64 dt, dt, %17;\n\t" \
-    "mul.rn.f64 dx, dx, %17;\n\t"
+    "mul.rn.f64 dt, dt, %13;\n\t" \
+    "mul.rn.f64 dx, dx, %13;\n\t"
 #define CXB_MM1_SLOT_C \
-    "mul.rn.f64 dt, dt, %14;\n\t" \
-    "mul.rn.f64 dx, dx, %14;\n\t" \
+    "mul.rn.f64 dt, dt, %11;\n\t" \
+    "mul.rn.f64 dx, dx, %11;\n\t" \
     "sub.rn.f64 lat, dt, dx;\n\t" \
-    "@pc add.rn.f64 %9, %9, lat;\n\t" \
+    "add.rn.f64 %8, %8, lat;\n\t" \
     "@pp mov.b32 %2, i1;\n\t" \
-    "sub.u32 cnt, i1, %3;\n\t" \
-    "max.u32 cnt, cnt, %6;\n\t" \
-    "@pp mov.b32 %6, cnt;\n\t" \
-    "setp.lt.u32 pg, i1, %11;\n\t" \
-    "selp.b32 akn, akn, %12, pg;\n\t" \
+    "sub.u32 cnt, %2, %3;\n\t" \
+    "max.u32 %5, %5, cnt;\n\t" \
     "@pp mov.b32 %0, akn;\n\t" \
     "@pp and.b32 %1, %1, 0xfffffffd;\n\t" \
     "or.pred pa, pc, pw;\n\t" \
     "setp.ne.and.u32 ppop, %2, %3, pa;\n\t" \
-    "setp.eq.and.u32 ppark, %2, %3, pa;\n\t" \
-    "and.b32 kb, key, 0xfffffffc;\n\t" \
-    "@ppop shr.u32 %7, eak, 2;\n\t" \
-    "@ppop add.u32 %1, kb, es4;\n\t" \
+    "@pa add.u32 %4, %4, 1;\n\t" \
+    "@pa mov.b32 %1, 0xffffffff;\n\t" \
+    "@ppop mad.lo.u32 %1, t, 4, es4;\n\t" \
+    "@ppop mul.hi.u32 %6, eak, 0x40000000;\n\t" \
     "@ppop add.u32 %3, %3, 1;\n\t" \
-    "@ppark mov.b32 %1, 0xffffffff;\n\t" \
     "}"
 #define CXB_MM1_SLOT_OPERANDS \
-    : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(now), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
+    : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
     "+l"(hash), "+d"(total_latency) \
-    : "r"(glim), "r"(g), "r"(agk), "r"(base), "d"(c.sec_per_unit), "r"(c.n_packets), "r"(ukey), "d"(mult), \
-    "n"(MASK), "n"(STRIDE) \
-    : "memory"
+    : "r"(glim), "r"(base), "d"(c.sec_per_unit), "r"(ukey), "d"(mult), "n"(MASK), "n"(STRIDE)
 
 namespace cxb {
 
@@ -203,7 +192,7 @@ struct ring_entry {
     uint32_t s4;  // 4 * s_j + 2: added to 4 * now when the consumer starts serving packet j
 };
 
-// One replication.  `Ring` gives ring_entry load(j) / uint32_t load_a(j) / store(j, e) on slot
+// One replication.  `Ring` gives ring_entry load(j) / uint32_t load_a(j) / store_if(p, j, e) / store_a_if(p, j, ak) on slot
 // j modulo its physical size.
 struct lane {
     uint32_t ctr2, ctr3;        // Philox counter words 2,3 = global replication id
@@ -218,7 +207,7 @@ struct lane {
     uint32_t t0, t1, m0, m1;
     uint32_t main_pc, cons_pc, remaining, waiting;
     uint32_t now, x_tick;
-    uint32_t n_events;
+    uint32_t n_events;          // outside the steady state: events so far; inside: events - i (see events())
     uint32_t max_queue;
     uint32_t status;
     uint64_t hash;
@@ -248,14 +237,22 @@ struct lane {
 
     CXB_HD bool is_fast() const { return kp != EMPTY; }
 
+    // environment::step() calls so far.  In the steady state every put is one event, so only the
+    // consumer's events are counted there and the puts are taken from i.
+    CXB_HD uint32_t events() const { return is_fast() ? n_events + i : n_events; }
+
     // ---- generation -----------------------------------------------------------------
     CXB_HD bool wants_packets(const constants &c) const { return g < c.n_packets; }
+    // (one slot beyond the packets holds the next arrival time: ring_cap < physical slots)
     CXB_HD bool has_room(const constants &c) const { return g - k + 2 <= c.ring_cap; }
 
     // Packets g and g+1: inter-arrival draws g, g+1 of stream 1 and service draws g, g+1 of
     // stream 2 are the two halves of block g/2 of each stream (philox.hpp addressing).
+    // The arithmetic runs for every lane and only the commit is conditional (`enable`), so there
+    // is no branch here: the compiler may interleave these four long FP64 chains with the
+    // integer bookkeeping of the event slots in the same basic block.
     template <typename Ring, typename Table>
-    CXB_HD void generate_pair(const constants &c, Ring &ring, const Table *table) {
+    CXB_HD void generate_pair(const constants &c, Ring &ring, const Table *table, bool enable) {
         const philox_block bp = philox4x32_10_scheduled(g >> 1, 1u, ctr2, ctr3, c.keys);
         const philox_block bc = philox4x32_10_scheduled(g >> 1, 2u, ctr2, ctr3, c.keys);
         // env.timeout(exponential()): timeout.ipp:184-187 -> real_to_sim
@@ -267,19 +264,20 @@ struct lane {
         // range guard: each delay < 2^28 and the bound on the last event time < 2^30, so no
         // 32-bit sum or key below can wrap; otherwise the replication is redone with 64-bit ticks
         const uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
-        if ((bad != 0) | (new_budget >= TIME_LIMIT)) {
-            status |= CXXDES_B200_REP_TIME_RANGE;
-            return;
-        }
-        budget = new_budget;
+        const bool out_of_range = (bad != 0) | (new_budget >= TIME_LIMIT);
+        const bool commit = enable & !out_of_range;
+        status |= (enable & out_of_range) ? (uint32_t)CXXDES_B200_REP_TIME_RANGE : 0u;
         const uint32_t a1k = agk + 4u * ia0;
+        const uint32_t a2k = a1k + 4u * ia1;
         ring_entry e0, e1;
         e0.ak = agk; e0.s4 = 4u * s0 + 2u;
         e1.ak = a1k; e1.s4 = 4u * s1 + 2u;
-        ring.store(g, e0);
-        ring.store(g + 1, e1);
-        agk = a1k + 4u * ia1;
-        g += 2;
+        ring.store_if(commit, g, e0);
+        ring.store_if(commit, g + 1, e1);
+        ring.store_a_if(commit, g + 2, a2k);   // A_{g+2}: the producer's token after it puts packet g+1
+        budget = commit ? new_budget : budget;
+        agk = commit ? a2k : agk;
+        g += commit ? 2u : 0u;
         glim = is_fast() ? g : 0u;
     }
 
@@ -317,7 +315,7 @@ struct lane {
 #endif
         const uint32_t key = kc < kp ? kc : kp;   // the front token
         // consumer resumes from its service timeout / producer resumes: q.put(now_seconds()),
-        // queue.hpp:48-53, which needs A_{i+1}, i.e. packet i generated
+        // queue.hpp:48-53, whose packet i must have been generated
         bool cons = kc < kp;
         bool put = !cons & (i < glim);
         if (MODE & MODE_UNTIL) {
@@ -330,49 +328,46 @@ struct lane {
         const uint32_t i1 = i + 1;
         const uint32_t next_ak = ring.load_a(i1);
         const ring_entry e = ring.load(k);
-        // environment::step: pop, advance the clock, count, fold (tokens are scheduled at now + d
-        // with d >= 0, so time never runs backwards here)
-        if (cons | put) {
-            now = t;
-            ++n_events;
-            hash = fold(hash, t, cons ? CONS_BITS : PROD_BITS);
-        }
+        // environment::step: pop, fold (tokens are scheduled at now + d with d >= 0, so the clock
+        // is simply the time of the last token; `now` itself is only needed outside this state)
+        if (cons | put) hash = fold(hash, t, cons ? CONS_BITS : PROD_BITS);
         // The woken consumer's token {0 + now} was pushed before the producer's timeout, so it is
         // the very next event (event.hpp:125-134): it is dispatched in the same slot.
-        if (woke) {
-            ++n_events;
-            hash = fold(hash, t, CONS_BITS);
-        }
-        // total_latency += now_seconds() - x   (producer_consumer.cpp:52)
-        const double lat = seconds<MODE>(c, t) - seconds<MODE>(c, x_tick);
-        if (cons) total_latency += lat;
+        if (woke) hash = fold(hash, t, CONS_BITS);
+        // total_latency += now_seconds() - x   (producer_consumer.cpp:52); for the other lanes
+        // x - x = +0 is added, which leaves the (non-negative) sum as it is
+        const uint32_t ts = cons ? t : x_tick;
+        total_latency += seconds<MODE>(c, ts) - seconds<MODE>(c, x_tick);
         if (put) {
             // packet i is already in the ring with A_i == now; env.timeout(exponential()) expires
-            // at A_{i+1}; a consumer asleep in its service keeps the front place on a tie
+            // at A_{i+1} = ring[i + 1].ak; a consumer asleep in its service keeps the front place
+            // on a tie
             i = i1;
-            const uint32_t count = i1 - k;
-            max_queue = count > max_queue ? count : max_queue;
-            kp = i1 < g ? next_ak : agk;
+            kp = next_ak;
             kc &= ~2u;
         }
+        const uint32_t count = i - k;             // the put is in, the pop below is not
+        max_queue = count > max_queue ? count : max_queue;
         // consumer: q.pop() (queue.hpp:58-65) succeeds -> timeout(exponential()) = now + s_k, pushed
         // after the producer's token; or the consumer waits on queue.event_
         const bool attempt = cons | woke;
         const bool pop = attempt & (i != k);
-        const bool park = attempt & (i == k);
+        if (attempt) {
+            ++n_events;                           // counts consumer events; puts are counted by i
+            kc = EMPTY;
+        }
         if (pop) {
+            kc = 4u * t + e.s4;
             x_tick = e.ak >> 2;
-            kc = (key & ~3u) + e.s4;
             ++k;
         }
-        if (park) kc = EMPTY;
     }
 
 #if defined(__CUDA_ARCH__)
     // The same slot, instruction for instruction, for a ring in shared memory (`base` = shared
     // address of this thread's column, entry j at base + (j & MASK) * STRIDE).  nvcc turns the C++
-    // above into ~100 instructions per slot because its eight short-lived conditions do not fit
-    // the seven predicate registers once four slots are interleaved; spelled out it is ~60.
+    // above into ~100 instructions per slot because its short-lived conditions do not fit the seven
+    // predicate registers once four slots are interleaved; spelled out it is ~55.
     // Checked against the C++ version by the GPU parity tests (the host unit tests run the C++).
     template <int MODE, int MASK, int STRIDE>
     __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base) {
@@ -402,6 +397,7 @@ struct lane {
         t1 = c_front ? tp : tc;
         m1 = c_front ? M_PROD : M_CONS;
         cons_pc = waiting ? 1u : 2u;
+        n_events += i;
         kp = kc = EMPTY;
         glim = 0;
     }
@@ -437,8 +433,7 @@ struct lane {
                 max_queue = count > max_queue ? count : max_queue;
                 // wake(): the parked consumer's token goes in before the producer's own timeout
                 if (waiting) { push(now, M_CONS); waiting = 0; }
-                const uint32_t next_ak = ring.load_a(i);
-                push((i < g ? next_ak : agk) >> 2, M_PROD);
+                push(ring.load_a(i) >> 2, M_PROD);   // A_{i+1}
             } else {
                 push(now, M_HANDLER);                // co_return -> completion carrying the all_of handler
             }
@@ -479,6 +474,7 @@ struct lane {
                 kp = 4u * tp + 1u;
                 kc = tc == EMPTY ? EMPTY : 4u * tc + (cons_front ? 0u : 2u);
                 glim = g;
+                n_events -= i;
             }
         }
         return true;

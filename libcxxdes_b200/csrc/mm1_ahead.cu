@@ -35,6 +35,9 @@ struct smem_ring {
     static constexpr int MASK = SLOTS - 1;
     static constexpr int STRIDE = THREADS * 8;
     __device__ __forceinline__ uint32_t addr(uint32_t j) const { return base + (j & (SLOTS - 1)) * (THREADS * 8); }
+    // All ring accesses are volatile asm, which keeps their relative order; none has a "memory"
+    // clobber, so the arithmetic around them (and the read-only log table loads) can be scheduled
+    // freely across them.
     __device__ __forceinline__ mm1::ring_entry load(uint32_t j) const {
         mm1::ring_entry e;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.ak), "=r"(e.s4) : "r"(addr(j)));
@@ -45,8 +48,13 @@ struct smem_ring {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr(j)));
         return v;
     }
-    __device__ __forceinline__ void store(uint32_t j, const mm1::ring_entry &e) const {
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr(j)), "r"(e.ak), "r"(e.s4) : "memory");
+    __device__ __forceinline__ void store_if(bool p, uint32_t j, const mm1::ring_entry &e) const {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.u32 [%0], {%1, %2};\n\t}"
+                     ::"r"(addr(j)), "r"(e.ak), "r"(e.s4), "r"((uint32_t)p));
+    }
+    __device__ __forceinline__ void store_a_if(bool p, uint32_t j, uint32_t ak) const {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}"
+                     ::"r"(addr(j)), "r"(ak), "r"((uint32_t)p));
     }
 };
 
@@ -78,22 +86,20 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         }
         if (!__any_sync(0xFFFFFFFFu, active)) break;
 
-        // ---- 1. two more packets for every lane that has room for them ----
-        if (active && L.wants_packets(c)) {
-            if (L.has_room(c)) L.generate_pair(c, ring, table);
-            else if (L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-        }
-        __syncwarp();
-
-        // ---- 2. start-up / wind-down events ----
+        // ---- 1. start-up / wind-down events (rare) ----
         if (active && !L.is_fast()) L.template generic_step<MODE>(c, ring);
-        __syncwarp();
-
-        // ---- 3. steady-state events ----
         static_assert(EVENT_SLOTS <= (int)mm1::lane::TAIL, "the end-of-steady-state check runs once per iteration");
         L.leave_fast_near_end(c);
+        __syncwarp();
+
+        // ---- 2. one branch-free block: steady-state events on the packets generated so far,
+        //         and the next two packets for every lane that has room for them ----
 #pragma unroll
         for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
+        const bool want = active && L.status == 0 && L.wants_packets(c);
+        const bool room = L.has_room(c);
+        L.generate_pair(c, ring, table, want & room);
+        if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
 
         // ---- 4. end of this lane's replication? ----
         if (active && L.finished(c)) {
@@ -112,7 +118,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                     end = end > sh.run_until ? end : sh.run_until;  // now_ = max(now_, t), environment.ipp:194
                 }
                 o.end_time = end;
-                o.n_events = L.n_events;
+                o.n_events = L.events();
                 o.trace_hash = L.hash;
                 o.f64[0] = L.k == c.n_packets ? L.total_latency / (double)prm.n_packets : 0.0;  // :46
                 o.f64[1] = L.total_latency;
@@ -138,8 +144,9 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
     p.ah_threads = AH_THREADS;
     p.ah_blocks = sm_count * AH_MIN_BLOCKS;
     p.ah_smem_bytes = TABLE_BYTES + (size_t)AH_RING_SLOTS * AH_THREADS * sizeof(uint2);
-    uint32_t cap = queue_capacity ? queue_capacity : AH_RING_SLOTS;
-    if (cap > AH_RING_SLOTS) cap = AH_RING_SLOTS;
+    // one physical slot is kept for the arrival time after the last generated packet
+    uint32_t cap = queue_capacity ? queue_capacity : AH_RING_SLOTS - 1;
+    if (cap > AH_RING_SLOTS - 1) cap = AH_RING_SLOTS - 1;
     if (cap < 2) cap = 2;
     p.ah_ring_cap = cap;
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the ring also holds the packets

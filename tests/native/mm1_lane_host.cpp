@@ -17,7 +17,8 @@ struct host_ring {
     explicit host_ring(uint32_t n) : slots(n) {}
     mm1::ring_entry load(uint32_t j) const { return slots[j & (slots.size() - 1)]; }
     uint32_t load_a(uint32_t j) const { return slots[j & (slots.size() - 1)].ak; }
-    void store(uint32_t j, const mm1::ring_entry &e) { slots[j & (slots.size() - 1)] = e; }
+    void store_if(bool p, uint32_t j, const mm1::ring_entry &e) { if (p) slots[j & (slots.size() - 1)] = e; }
+    void store_a_if(bool p, uint32_t j, uint32_t ak) { if (p) slots[j & (slots.size() - 1)].ak = ak; }
 };
 }  // namespace
 
@@ -42,10 +43,7 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
         L.init(first + r);
         for (;;) {
             ++iters;
-            if (L.wants_packets(c)) {
-                if (L.has_room(c)) L.generate_pair(c, ring, LOG_TABLE_HOST);
-                else if (L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-            }
+            // same order as one iteration of mm1_ahead_kernel
             // MODE 3 = run_until check + tick_mult multiply compiled in: same results as the
             // specialised modes (a multiply by 1.0 and a compare with EMPTY change nothing)
             if (!L.is_fast()) L.generic_step<3>(c, ring);
@@ -59,6 +57,10 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
                     default: L.fast_slot<3>(c, ring); break;
                 }
             }
+            const bool want = L.status == 0 && L.wants_packets(c);
+            const bool room = L.has_room(c);
+            L.generate_pair(c, ring, LOG_TABLE_HOST, want && room);
+            if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
             if (L.finished(c)) break;
         }
         uint32_t status = L.status;
@@ -68,7 +70,7 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
             end = end > until ? end : until;
         }
         out->end_time[r] = end;
-        out->n_events[r] = L.n_events;
+        out->n_events[r] = L.events();
         out->trace_hash[r] = L.hash;
         out->status[r] = status;
         out->f64[0][r] = L.k == c.n_packets ? L.total_latency / (double)prm->n_packets : 0.0;

@@ -36,10 +36,6 @@
 //        the consumer, twice; now and x as doubles
 //   MULT time_precision().t
 //   C    total_latency += now_seconds() - x; put: i, max_queue, kp, tie bit; pop or park
-// The SM's integer ALU pipe issues one warp instruction every other cycle and is what bounds this
-// kernel, so shifts and selects are spelled as multiplies where the FMA pipe can do them:
-// key >> 2 = mulhi(key, 2^30); rotl64(h, 5) from two 32x32->64 multiplies by 32; the folded hash is
-// written by predicated multiplies instead of being selected.
 #define CXB_MM1_SLOT_A \
     "{\n\t" \
     ".reg .pred pc, pp, pw, pok, pa, ppop, pdue;\n\t" \
@@ -53,20 +49,43 @@
     "setp.le.u32 pdue, key, %12;\n\t" \
     "and.pred pc, pc, pdue;\n\t" \
     "and.pred pp, pp, pdue;\n\t"
-#define CXB_MM1_SLOT_FOLD(PRED, BITS) \
+// Instruction selection knobs (measured on B200): the integer ALU pipe takes a warp
+// instruction every 2 cycles; IMAD runs on the FMA-heavy pipe at 2 cycles, IMAD.WIDE / IMAD.HI at 4.
+#ifndef CXB_MM1_ROT_MUL
+#define CXB_MM1_ROT_MUL 0     /* rotl64(h, 5): 1 = two 32x32->64 multiplies by 32, 0 = two funnel shifts */
+#endif
+#ifndef CXB_MM1_SHIFT_MUL
+#define CXB_MM1_SHIFT_MUL 0   /* x >> 2: 1 = mulhi(x, 2^30), 0 = shift */
+#endif
+#if CXB_MM1_ROT_MUL
+#define CXB_MM1_SLOT_ROT(BITS) \
     "mul.wide.u32 m, hl, 32;\n\t" \
     "mov.b64 {a0, a1}, m;\n\t" \
     "mul.wide.u32 m, hh, 32;\n\t" \
     "mov.b64 {b0, b1}, m;\n\t" \
     "lop3.b32 rl, a0, b1, t, 0x56;\n\t" \
-    "lop3.b32 rh, b0, a1, " BITS ", 0x56;\n\t" \
+    "lop3.b32 rh, b0, a1, " BITS ", 0x56;\n\t"
+#else
+#define CXB_MM1_SLOT_ROT(BITS) \
+    "shf.l.wrap.b32 a1, hl, hh, 5;\n\t" \
+    "shf.l.wrap.b32 a0, hh, hl, 5;\n\t" \
+    "xor.b32 rl, a0, t;\n\t" \
+    "xor.b32 rh, a1, " BITS ";\n\t"
+#endif
+#if CXB_MM1_SHIFT_MUL
+#define CXB_MM1_SLOT_SHR2(PRED, DST, SRC) PRED "mul.hi.u32 " DST ", " SRC ", 0x40000000;\n\t"
+#else
+#define CXB_MM1_SLOT_SHR2(PRED, DST, SRC) PRED "shr.u32 " DST ", " SRC ", 2;\n\t"
+#endif
+#define CXB_MM1_SLOT_FOLD(PRED, BITS) \
+    CXB_MM1_SLOT_ROT(BITS) \
     "mul.hi.u32 mh, rl, 0x7F4A7C15;\n\t" \
     "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
     "@" PRED " mad.lo.u32 hh, rh, 0x7F4A7C15, mh;\n\t" \
     "@" PRED " mul.lo.u32 hl, rl, 0x7F4A7C15;\n\t"
 #define CXB_MM1_SLOT_B \
     "setp.eq.and.u32 pw, %1, 0xffffffff, pp;\n\t" \
-    "mul.hi.u32 t, key, 0x40000000;\n\t" \
+    CXB_MM1_SLOT_SHR2("", "t", "key") \
     "add.u32 i1, %2, 1;\n\t" \
     "and.b32 sl, i1, %14;\n\t" \
     "mad.lo.u32 addr, sl, %15, %10;\n\t" \
@@ -103,7 +122,7 @@
     "@pa add.u32 %4, %4, 1;\n\t" \
     "@pa mov.b32 %1, 0xffffffff;\n\t" \
     "@ppop mad.lo.u32 %1, t, 4, es4;\n\t" \
-    "@ppop mul.hi.u32 %6, eak, 0x40000000;\n\t" \
+    CXB_MM1_SLOT_SHR2("@ppop ", "%6", "eak") \
     "@ppop add.u32 %3, %3, 1;\n\t" \
     "}"
 #define CXB_MM1_SLOT_OPERANDS \

@@ -21,7 +21,9 @@ struct mm1_fused_plan {
     uint32_t fb_ring;           // ring entries per fallback thread
     bool direct_global;         // skip the shared-memory kernel (high utilisation / huge queues)
     // generate-ahead kernel (mm1_ahead.cu), the default first pass
+    int ah_geometry;            // which compiled (threads, blocks/SM, ring slots) variant
     int ah_threads, ah_blocks;
+    uint32_t ah_ring_slots;
     size_t ah_smem_bytes;
     uint32_t ah_ring_cap;       // packets (queued + generated ahead) a replication's ring may hold
     bool ah_direct_global;

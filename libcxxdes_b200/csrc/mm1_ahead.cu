@@ -15,6 +15,7 @@
 // Replications the 32-bit/shared-memory representation cannot hold (queue longer than the ring,
 // ticks beyond 2^30) are appended to the retry list and redone by mm1_fused_kernel<false>.
 #include <cmath>
+#include <cstdlib>
 
 #include "device/mm1_lane.cuh"
 #include "device/models_common.cuh"
@@ -132,21 +133,45 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 }
 
 namespace {
-constexpr int AH_THREADS = 256;
-constexpr int AH_MIN_BLOCKS = 3;
-constexpr int AH_RING_SLOTS = 32;
 constexpr int AH_EVENT_SLOTS = 4;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+
+// Launch geometries: threads per block, resident blocks per SM, physical ring slots per replication.
+// 0 is the default; the others exist to measure the occupancy / ring-depth trade-off and can be
+// selected with CXXDES_B200_MM1_GEOMETRY=<n> (a deeper ring holds longer queues, a shallower one
+// leaves room for more resident warps).
+template <int T, int B, int S>
+struct geometry {
+    static constexpr int THREADS = T, MIN_BLOCKS = B, RING_SLOTS = S;
+    static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
+};
+using geometry0 = geometry<256, 3, 32>;
+using geometry1 = geometry<256, 4, 16>;
+using geometry2 = geometry<128, 6, 32>;
+using geometry3 = geometry<128, 8, 16>;
+
+template <typename G>
+void fill_plan(mm1_fused_plan &p, int sm_count) {
+    p.ah_threads = G::THREADS;
+    p.ah_blocks = sm_count * G::MIN_BLOCKS;
+    p.ah_smem_bytes = G::SMEM;
+    p.ah_ring_slots = G::RING_SLOTS;
+}
 }  // namespace
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                     int64_t tick_mult) {
-    p.ah_threads = AH_THREADS;
-    p.ah_blocks = sm_count * AH_MIN_BLOCKS;
-    p.ah_smem_bytes = TABLE_BYTES + (size_t)AH_RING_SLOTS * AH_THREADS * sizeof(uint2);
+    const char *env = getenv("CXXDES_B200_MM1_GEOMETRY");
+    p.ah_geometry = env ? atoi(env) : 0;
+    switch (p.ah_geometry) {
+        case 1: fill_plan<geometry1>(p, sm_count); break;
+        case 2: fill_plan<geometry2>(p, sm_count); break;
+        case 3: fill_plan<geometry3>(p, sm_count); break;
+        default: p.ah_geometry = 0; fill_plan<geometry0>(p, sm_count); break;
+    }
     // one physical slot is kept for the arrival time after the last generated packet
-    uint32_t cap = queue_capacity ? queue_capacity : AH_RING_SLOTS - 1;
-    if (cap > AH_RING_SLOTS - 1) cap = AH_RING_SLOTS - 1;
+    uint32_t cap = queue_capacity ? queue_capacity : p.ah_ring_slots - 1;
+    if (cap > p.ah_ring_slots - 1) cap = p.ah_ring_slots - 1;
     if (cap < 2) cap = 2;
     p.ah_ring_cap = cap;
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the ring also holds the packets
@@ -160,25 +185,44 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
 }
 
 namespace {
-template <int MODE>
-cudaError_t configure_mode(const mm1_fused_plan &plan) {
-    return cudaFuncSetAttribute(mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS, MODE>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.ah_smem_bytes);
+template <typename G, int MODE>
+cudaError_t configure_mode() {
+    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
 }
-template <int MODE>
+template <typename G>
+cudaError_t configure_geometry() {
+    cudaError_t e = configure_mode<G, 0>();
+    if (e == cudaSuccess) e = configure_mode<G, 1>();
+    if (e == cudaSuccess) e = configure_mode<G, 2>();
+    if (e == cudaSuccess) e = configure_mode<G, 3>();
+    return e;
+}
+template <typename G, int MODE>
 void launch_mode(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                  const mm1_fused_plan &plan, cudaStream_t stream) {
-    mm1_ahead_kernel<AH_THREADS, AH_MIN_BLOCKS, AH_RING_SLOTS, AH_EVENT_SLOTS, MODE>
-        <<<plan.ah_blocks, AH_THREADS, plan.ah_smem_bytes, stream>>>(c, prm, sh, out);
+    mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE>
+        <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out);
+}
+template <typename G>
+void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh,
+                     const device_columns &out, const mm1_fused_plan &plan, cudaStream_t stream) {
+    switch (mode) {
+        case 0: launch_mode<G, 0>(c, prm, sh, out, plan, stream); break;
+        case 1: launch_mode<G, 1>(c, prm, sh, out, plan, stream); break;
+        case 2: launch_mode<G, 2>(c, prm, sh, out, plan, stream); break;
+        default: launch_mode<G, 3>(c, prm, sh, out, plan, stream); break;
+    }
 }
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    cudaError_t e = configure_mode<0>(plan);
-    if (e == cudaSuccess) e = configure_mode<1>(plan);
-    if (e == cudaSuccess) e = configure_mode<2>(plan);
-    if (e == cudaSuccess) e = configure_mode<3>(plan);
-    return e;
+    switch (plan.ah_geometry) {
+        case 1: return configure_geometry<geometry1>();
+        case 2: return configure_geometry<geometry2>();
+        case 3: return configure_geometry<geometry3>();
+        default: return configure_geometry<geometry0>();
+    }
 }
 
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
@@ -194,11 +238,11 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.ring_cap = plan.ah_ring_cap;
     c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
     const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
-    switch (mode) {
-        case 0: launch_mode<0>(c, prm, sh, out, plan, stream); break;
-        case 1: launch_mode<1>(c, prm, sh, out, plan, stream); break;
-        case 2: launch_mode<2>(c, prm, sh, out, plan, stream); break;
-        default: launch_mode<3>(c, prm, sh, out, plan, stream); break;
+    switch (plan.ah_geometry) {
+        case 1: launch_geometry<geometry1>(mode, c, prm, sh, out, plan, stream); break;
+        case 2: launch_geometry<geometry2>(mode, c, prm, sh, out, plan, stream); break;
+        case 3: launch_geometry<geometry3>(mode, c, prm, sh, out, plan, stream); break;
+        default: launch_geometry<geometry0>(mode, c, prm, sh, out, plan, stream); break;
     }
     return cudaGetLastError();
 }

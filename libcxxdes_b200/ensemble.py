@@ -15,7 +15,8 @@ import numpy as np
 
 from . import abi
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libcxxdes_b200.so"
+# CXXDES_B200_LIBRARY points at another build of the same CUDA library (kernel A/B measurements).
+_LIB_PATH = Path(os.environ.get("CXXDES_B200_LIBRARY") or Path(__file__).resolve().parent / "_lib" / "libcxxdes_b200.so")
 _lib = None
 
 

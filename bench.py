@@ -28,7 +28,8 @@ sys.path.insert(0, str(ROOT))
 
 LAMBDA, MU = 5.0, 10.0
 SEED = 0x5EED
-I_ALG = 256.0            # algorithmic thread-instructions per event, SURVEY 8(d) / BASELINE.md 5
+I_ALG = 82.0             # algorithmic thread-instructions per event of the generate-ahead algorithm
+I_ALG_SURVEY = 256.0     # SURVEY 8(d)'s estimate, made for draw-on-demand dispatch (one Philox block per draw)
 BYTES_PER_REP = 60.0     # algorithmic HBM bytes per replication: the result row (7 x 8 B + 4 B)
 CPU_LAMBDA = [LAMBDA]    # arrival rate of the CPU arm (follows --lam)
 METRIC = "simulated events/sec, 1M-replication M/M/1 ensemble at 1/2/4/8 B200"
@@ -286,14 +287,16 @@ def run_b200(a):
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("mm1_fused_dram_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get("mm1_ahead_dram_bytes_per_launch" if a.kernel == "ahead" else "mm1_fused_dram_bytes_per_launch")
         except (ValueError, OSError):
             traffic = None
     roofline = {
         "bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "thread-inst/s",
         "frac": issue_achieved / issue_peak, "traffic": traffic,
         "kernel": "mm1_ahead_kernel" if a.kernel == "ahead" else "mm1_fused_kernel<FAST>", "kernel_ms": kernel_avg_ms,
-        "alg_per_unit": f"{I_ALG:.0f} thread-instructions per simulated event (SURVEY 8d)",
+        "alg_per_unit": f"{I_ALG:.0f} thread-instructions per simulated event (DESIGN.md 5: 408 per packet pair / 5 events; "
+                        f"SURVEY 8d estimated {I_ALG_SURVEY:.0f} for draw-on-demand dispatch, which this kernel undercuts)",
+        "frac_with_survey_256": issue_achieved / I_ALG * I_ALG_SURVEY / issue_peak,
         "peak_source": f"{props.multi_processor_count} SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz, {peak_src}",
         "hbm": {"achieved": R * BYTES_PER_REP / (kernel_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": R * BYTES_PER_REP / (kernel_avg_ms * 1e-3) / 1e9 / hbm_peak,

@@ -85,6 +85,8 @@ struct cxxdes_b200_ensemble {
     log_entry *log_table = nullptr;
     int64_t *ring = nullptr;
     size_t ring_bytes = 0;
+    void *ahead_gring = nullptr;  // second ring level of the generate-ahead M/M/1 kernel
+    size_t ahead_gring_bytes = 0;
     cxxdes_b200_accumulators *acc = nullptr;
     void *reduce_scratch = nullptr;
 
@@ -127,6 +129,7 @@ int allocate(cxxdes_b200_ensemble *e) {
     CUDA_TRY(cudaMalloc(&e->acc, sizeof(cxxdes_b200_accumulators)));
     CUDA_TRY(cudaMalloc(&e->reduce_scratch, reduce_scratch_bytes(e->sm_count)));
     if (e->ring_bytes) CUDA_TRY(cudaMalloc(&e->ring, e->ring_bytes));
+    if (e->ahead_gring_bytes) CUDA_TRY(cudaMalloc(&e->ahead_gring, e->ahead_gring_bytes));
     return CXXDES_B200_OK;
 }
 
@@ -193,9 +196,11 @@ int plan(cxxdes_b200_ensemble *e) {
             e->use_fused = !(c.flags & CXXDES_B200_FLAG_GENERIC_ENGINE) && p.n_packets >= 2 &&
                            p.n_packets < (1ULL << 30);
             if (e->use_fused) {
-                e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin, e->clk.tick_mult);
+                e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin, e->clk.tick_mult,
+                                             (c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0);
                 e->ring_bytes = (size_t)e->mm1_plan.fb_blocks * e->mm1_plan.fb_threads * e->mm1_plan.fb_ring *
                                 sizeof(int64_t);
+                if (!(c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP)) e->ahead_gring_bytes = mm1_ahead_gring_bytes(e->mm1_plan);
             } else {
                 e->engine_threads = 128;
                 e->engine_blocks = e->sm_count * 4;
@@ -264,7 +269,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         case CXXDES_B200_MODEL_MM1:
             if (e->use_fused) {
                 CUDA_TRY(launch_mm1_fused(e->params.mm1, sh, e->cols, e->mm1_plan, e->ring, e->counters + 2,
-                                          e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
+                                          e->ahead_gring, e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
             } else {
                 CUDA_TRY(launch_mm1_engine(e->params.mm1, sh, e->cols, e->ring, e->engine_ring, e->engine_blocks,
                                            e->engine_threads, e->stream));
@@ -499,6 +504,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->retry_list);
     cudaFree(e->log_table);
     cudaFree(e->ring);
+    cudaFree(e->ahead_gring);
     cudaFree(e->acc);
     cudaFree(e->reduce_scratch);
     cudaFree(e->program_blob);

@@ -29,7 +29,8 @@
 // PTX text of one steady-state slot (lane::fast_slot_ptx below; the commented C++ twin is
 // lane::fast_slot).  Operands: %0 kp, %1 kc, %2 i, %3 k, %4 n_events, %5 max_queue, %6 x_tick,
 // %7 hash, %8 total_latency | %9 glim, %10 ring base, %11 sec_per_unit, %12 4*until+3,
-// %13 tick_mult, %14 slot mask, %15 slot stride in bytes.
+// %13 tick_mult, %14 slot mask (= window size), %15 slot stride in bytes | spilling ring: %16 g,
+// %17 global ring column, %18 its slot stride in bytes, %19 its slot mask.
 //   A    front token; can the lane dispatch (pc: consumer resumes, pp: producer puts)
 //   DUE  run_until horizon
 //   B    woke?, ring[i+1].ak and ring[k], environment::step (fold) once or, when the put wakes
@@ -83,7 +84,7 @@
     "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
     "@" PRED " mad.lo.u32 hh, rh, 0x7F4A7C15, mh;\n\t" \
     "@" PRED " mul.lo.u32 hl, rl, 0x7F4A7C15;\n\t"
-#define CXB_MM1_SLOT_B \
+#define CXB_MM1_SLOT_B(LOAD_K) \
     "setp.eq.and.u32 pw, %1, 0xffffffff, pp;\n\t" \
     CXB_MM1_SLOT_SHR2("", "t", "key") \
     "add.u32 i1, %2, 1;\n\t" \
@@ -92,7 +93,7 @@
     "ld.shared.u32 akn, [addr];\n\t" \
     "and.b32 sl, %3, %14;\n\t" \
     "mad.lo.u32 addr, sl, %15, %10;\n\t" \
-    "ld.shared.v2.u32 {eak, es4}, [addr];\n\t" \
+    LOAD_K \
     "or.pred pok, pc, pp;\n\t" \
     "mov.b64 {hl, hh}, %7;\n\t" \
     "selp.b32 bh, 0x200, 0x100, pc;\n\t" \
@@ -104,6 +105,21 @@
     "mov.b64 dx, {%6, 0x43300000};\n\t" \
     "sub.rn.f64 dt, dt, 0d4330000000000000;\n\t" \
     "sub.rn.f64 dx, dx, 0d4330000000000000;\n\t"
+/* ring[k]: in the shared-memory window, or (spilling ring) in global memory once the queue is
+   longer than the window: entry k is in the window iff g - k <= WINDOW */
+#define CXB_MM1_SLOT_LOAD_K "ld.shared.v2.u32 {eak, es4}, [addr];\n\t"
+#define CXB_MM1_SLOT_LOAD_K_SPILL \
+    "{\n\t" \
+    ".reg .pred pin;\n\t" \
+    ".reg .b32 d, gs;\n\t" \
+    ".reg .b64 ga;\n\t" \
+    "sub.u32 d, %16, %3;\n\t" \
+    "setp.le.u32 pin, d, %14;\n\t" \
+    "and.b32 gs, %3, %19;\n\t" \
+    "mad.wide.u32 ga, gs, %18, %17;\n\t" \
+    "@pin ld.shared.v2.u32 {eak, es4}, [addr];\n\t" \
+    "@!pin ld.global.v2.u32 {eak, es4}, [ga];\n\t" \
+    "}\n\t"
 #define CXB_MM1_SLOT_MULT \
     "mul.rn.f64 dt, dt, %13;\n\t" \
     "mul.rn.f64 dx, dx, %13;\n\t"
@@ -129,6 +145,7 @@
     : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
     "+l"(hash), "+d"(total_latency) \
     : "r"(glim), "r"(base), "d"(c.sec_per_unit), "r"(ukey), "d"(mult), "n"(MASK), "n"(STRIDE)
+#define CXB_MM1_SLOT_OPERANDS_SPILL CXB_MM1_SLOT_OPERANDS, "r"(g), "l"(gbase), "r"(gstride), "r"(gmask)
 
 namespace cxb {
 
@@ -190,7 +207,8 @@ struct constants {
     double sec_per_unit;     // clock.seconds_per_tick_unit
     double tick_mult;        // (double)clock.tick_mult, < 2^23 so tick * tick_mult is exact in a double
     uint32_t n_packets;      // 2 <= n < 2^30
-    uint32_t ring_cap;       // packets the ring may hold, 2 <= ring_cap <= physical slots
+    uint32_t ring_cap;       // packets (queued + generated ahead) the ring may hold, >= 2
+    uint32_t lead_cap;       // packets that may be generated ahead of the producer (spilling ring: the window)
     uint32_t until;          // run_until horizon in ticks, EMPTY when there is none
 };
 
@@ -211,8 +229,10 @@ struct ring_entry {
     uint32_t s4;  // 4 * s_j + 2: added to 4 * now when the consumer starts serving packet j
 };
 
-// One replication.  `Ring` gives ring_entry load(j) / uint32_t load_a(j) / store_if(p, j, e) / store_a_if(p, j, ak) on slot
-// j modulo its physical size.
+// One replication.  `Ring` gives ring_entry load(j, g) / uint32_t load_a(j) / store_if(p, j, e) /
+// store_a_if(p, j, ak) / spill_if(p, g).  Its first level is a window of WINDOW + 1 slots (j modulo
+// that size) holding the entries [g - WINDOW, g) and the arrival key of entry g; a spilling ring
+// (SPILL) keeps older queued entries in a second, larger level.
 struct lane {
     uint32_t ctr2, ctr3;        // Philox counter words 2,3 = global replication id
     uint32_t g;                 // packets generated so far (even)
@@ -263,7 +283,11 @@ struct lane {
     // ---- generation -----------------------------------------------------------------
     CXB_HD bool wants_packets(const constants &c) const { return g < c.n_packets; }
     // (one slot beyond the packets holds the next arrival time: ring_cap < physical slots)
-    CXB_HD bool has_room(const constants &c) const { return g - k + 2 <= c.ring_cap; }
+    template <bool SPILL>
+    CXB_HD bool has_room(const constants &c) const {
+        if (SPILL) return (g - k + 2 <= c.ring_cap) & (g - i + 2 <= c.lead_cap);
+        return g - k + 2 <= c.ring_cap;  // the window bounds the lead as well (i >= k)
+    }
 
     // Packets g and g+1: inter-arrival draws g, g+1 of stream 1 and service draws g, g+1 of
     // stream 2 are the two halves of block g/2 of each stream (philox.hpp addressing).
@@ -291,6 +315,9 @@ struct lane {
         ring_entry e0, e1;
         e0.ak = agk; e0.s4 = 4u * s0 + 2u;
         e1.ak = a1k; e1.s4 = 4u * s1 + 2u;
+        // spilling ring: the two oldest window entries are about to be overwritten; if they are
+        // still queued they move to global memory first
+        if (Ring::SPILL) ring.spill_if(commit & (g - k + 2 > (uint32_t)Ring::WINDOW), g);
         ring.store_if(commit, g, e0);
         ring.store_if(commit, g + 1, e1);
         ring.store_a_if(commit, g + 2, a2k);   // A_{g+2}: the producer's token after it puts packet g+1
@@ -303,7 +330,7 @@ struct lane {
     // The producer's event is next, its packet is not generated and the ring has no room: the
     // model's queue is longer than this ring.
     CXB_HD bool ring_exhausted(const constants &c) const {
-        if (!wants_packets(c) || has_room(c) || i != g) return false;
+        if (!wants_packets(c) || i != g) return false;   // (called when there is no room)
         if (is_fast()) return !(kc < kp);
         return m0 == M_PROD;
     }
@@ -328,7 +355,7 @@ struct lane {
     CXB_HD void fast_slot(const constants &c, Ring &ring) {
 #if defined(__CUDA_ARCH__)
         if constexpr (Ring::HAS_PTX_SLOT) {
-            fast_slot_ptx<MODE, Ring::MASK, Ring::STRIDE>(c, ring.base);
+            fast_slot_ptx<MODE, Ring::SPILL, Ring::MASK, Ring::STRIDE>(c, ring.base, ring.gbase, ring.gstride, ring.gmask);
             return;
         }
 #endif
@@ -346,7 +373,7 @@ struct lane {
         const uint32_t t = key >> 2;
         const uint32_t i1 = i + 1;
         const uint32_t next_ak = ring.load_a(i1);
-        const ring_entry e = ring.load(k);
+        const ring_entry e = ring.load(k, g);
         // environment::step: pop, fold (tokens are scheduled at now + d with d >= 0, so the clock
         // is simply the time of the last token; `now` itself is only needed outside this state)
         if (cons | put) hash = fold(hash, t, cons ? CONS_BITS : PROD_BITS);
@@ -388,15 +415,26 @@ struct lane {
     // above into ~100 instructions per slot because its short-lived conditions do not fit the seven
     // predicate registers once four slots are interleaved; spelled out it is ~55.
     // Checked against the C++ version by the GPU parity tests (the host unit tests run the C++).
-    template <int MODE, int MASK, int STRIDE>
-    __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base) {
+    template <int MODE, bool SPILL, int MASK, int STRIDE>
+    __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base, const void *gbase, uint32_t gstride,
+                                                  uint32_t gmask) {
         const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * c.until + 3u : 0xFFFFFFFFu;
         const double mult = (MODE & MODE_TICK_MULT) ? c.tick_mult : 1.0;
-        // (four texts: the run_until check and the tick_mult multiply are left out when unused)
-        if constexpr (MODE == 0) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
-        else if constexpr (MODE == MODE_UNTIL) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
-        else if constexpr (MODE == MODE_TICK_MULT) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
-        else asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C CXB_MM1_SLOT_OPERANDS);
+        // (the run_until check, the tick_mult multiply and the global-memory level are left out when unused)
+#define CXB_MM1_SLOT_TEXT(LOAD_K, OPERANDS)                                                                    \
+        if constexpr (MODE == 0) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);          \
+        else if constexpr (MODE == MODE_UNTIL)                                                                 \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);          \
+        else if constexpr (MODE == MODE_TICK_MULT)                                                             \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS);         \
+        else                                                                                                   \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS);
+        if constexpr (SPILL) {
+            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K_SPILL, CXB_MM1_SLOT_OPERANDS_SPILL)
+        } else {
+            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K, CXB_MM1_SLOT_OPERANDS)
+        }
+#undef CXB_MM1_SLOT_TEXT
     }
 #endif
 
@@ -460,7 +498,7 @@ struct lane {
             // consumer body, producer_consumer.cpp:39-54
             if (cons_pc == 2) total_latency += seconds<MODE>(c, now) - seconds<MODE>(c, x_tick);  // :52
             if (i != k) {
-                const ring_entry e = ring.load(k);   // q.pop() succeeds, queue.hpp:58-65
+                const ring_entry e = ring.load(k, g);   // q.pop() succeeds, queue.hpp:58-65
                 x_tick = e.ak >> 2;
                 ++k;
                 cons_pc = 2;

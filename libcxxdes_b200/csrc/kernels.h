@@ -26,21 +26,25 @@ struct mm1_fused_plan {
     uint32_t ah_ring_slots;
     size_t ah_smem_bytes;
     uint32_t ah_ring_cap;       // packets (queued + generated ahead) a replication's ring may hold
+    uint32_t ah_lead_cap;       // packets that may be generated ahead of the producer
+    bool ah_spill;              // ring has a second level in global memory (heavily loaded queues)
+    uint32_t ah_gring_slots;    // its slots per replication (power of two)
     bool ah_direct_global;
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                              size_t smem_per_block_optin, int64_t tick_mult);
+                              size_t smem_per_block_optin, int64_t tick_mult, bool lockstep);
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             cudaStream_t stream, int *launches, bool lockstep);
+                             void *ahead_gring, cudaStream_t stream, int *launches, bool lockstep);
 cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
 // ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
 void plan_mm1_ahead(mm1_fused_plan &plan, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                     int64_t tick_mult);
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
+size_t mm1_ahead_gring_bytes(const mm1_fused_plan &plan);
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, cudaStream_t stream);
+                             const mm1_fused_plan &plan, void *gring, cudaStream_t stream);
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);

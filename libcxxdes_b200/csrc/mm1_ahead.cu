@@ -25,24 +25,45 @@ namespace cxb {
 
 namespace {
 
-template <int SLOTS, int THREADS>
-struct smem_ring {
-    uint32_t base;  // shared-window address of this thread's column: entry j at base + (j % SLOTS) * THREADS * 8
-    // 8-byte entries, THREADS * 8 bytes between slots: a warp's access touches each bank pair
-    // once whatever slot each lane is at (two conflict-free wavefronts).  Explicit ld/st.shared
-    // on a 32-bit address: no generic-to-shared conversion per access.
+// Ring of one replication.  First level: SLOTS 8-byte entries per thread in shared memory,
+// THREADS * 8 bytes between slots, so a warp's access touches each bank pair once whatever slot
+// each lane is at.  Explicit ld/st.shared on a 32-bit address: no generic-to-shared conversion per
+// access.  Second level (SPILL): entries that leave the window while still queued go to a ring in
+// global memory, laid out [slot][thread] (lanes generate in lock step, so the spill stores of a
+// warp are contiguous); only heavily loaded queues ever touch it.
+// All ring accesses are volatile asm, which keeps their relative order; none has a "memory"
+// clobber, so the arithmetic around them (and the read-only log table loads) can be scheduled
+// freely across them.
+template <int SLOTS, int THREADS, bool SPILL_>
+struct lane_ring {
     static_assert((SLOTS & (SLOTS - 1)) == 0, "ring slots must be a power of two");
     static constexpr bool HAS_PTX_SLOT = true;
+    static constexpr bool SPILL = SPILL_;
     static constexpr int MASK = SLOTS - 1;
+    static constexpr int WINDOW = SLOTS - 1;
     static constexpr int STRIDE = THREADS * 8;
-    __device__ __forceinline__ uint32_t addr(uint32_t j) const { return base + (j & (SLOTS - 1)) * (THREADS * 8); }
-    // All ring accesses are volatile asm, which keeps their relative order; none has a "memory"
-    // clobber, so the arithmetic around them (and the read-only log table loads) can be scheduled
-    // freely across them.
-    __device__ __forceinline__ mm1::ring_entry load(uint32_t j) const {
+    uint32_t base;       // shared-window address of this thread's column
+    const void *gbase;   // global ring: this thread's column (entry j at gbase + (j & gmask) * gstride)
+    uint32_t gstride;    // bytes between global slots = total threads * 8
+    uint32_t gmask;
+
+    __device__ __forceinline__ uint32_t addr(uint32_t j) const { return base + (j & MASK) * STRIDE; }
+    __device__ __forceinline__ const char *gaddr(uint32_t j) const {
+        return (const char *)gbase + (uint64_t)(j & gmask) * gstride;
+    }
+    __device__ __forceinline__ mm1::ring_entry load_shared(uint32_t j) const {
         mm1::ring_entry e;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.ak), "=r"(e.s4) : "r"(addr(j)));
         return e;
+    }
+    // entry j of a lane that has generated g packets
+    __device__ __forceinline__ mm1::ring_entry load(uint32_t j, uint32_t g) const {
+        if (SPILL && g - j > (uint32_t)WINDOW) {
+            mm1::ring_entry e;
+            asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(e.ak), "=r"(e.s4) : "l"(gaddr(j)));
+            return e;
+        }
+        return load_shared(j);
     }
     __device__ __forceinline__ uint32_t load_a(uint32_t j) const {
         uint32_t v;
@@ -57,17 +78,29 @@ struct smem_ring {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}"
                      ::"r"(addr(j)), "r"(ak), "r"((uint32_t)p));
     }
+    // entries g - WINDOW and g - WINDOW + 1 (window slots g + 1 and g + 2) move to the global level
+    __device__ __forceinline__ void spill_if(bool p, uint32_t g) const {
+        const mm1::ring_entry e1 = load_shared(g + 1), e2 = load_shared(g + 2);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %6, 0;\n\t"
+                     "@p st.global.v2.u32 [%0], {%1, %2};\n\t@p st.global.v2.u32 [%3], {%4, %5};\n\t}"
+                     ::"l"(gaddr(g - WINDOW)), "r"(e1.ak), "r"(e1.s4), "l"(gaddr(g - WINDOW + 1)), "r"(e2.ak), "r"(e2.s4),
+                       "r"((uint32_t)p));
+    }
 };
 
 }  // namespace
 
-template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE>
+template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out) {
+mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint2 *gring,
+                 uint32_t gring_slots) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     stage_log_table(table, sh.log_table);
-    smem_ring<RING_SLOTS, THREADS> ring;
+    lane_ring<RING_SLOTS, THREADS, SPILL> ring;
+    ring.gbase = gring + ((size_t)blockIdx.x * THREADS + threadIdx.x);
+    ring.gstride = gridDim.x * THREADS * 8u;
+    ring.gmask = gring_slots - 1;
     ring.base = (uint32_t)__cvta_generic_to_shared(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x * 8u;
 
     mm1::lane L;
@@ -98,7 +131,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 #pragma unroll
         for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
         const bool want = active && L.status == 0 && L.wants_packets(c);
-        const bool room = L.has_room(c);
+        const bool room = L.template has_room<SPILL>(c);
         L.generate_pair(c, ring, table, want & room);
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
 
@@ -136,19 +169,17 @@ namespace {
 constexpr int AH_EVENT_SLOTS = 4;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
 
-// Launch geometries: threads per block, resident blocks per SM, physical ring slots per replication.
-// 0 is the default; the others exist to measure the occupancy / ring-depth trade-off and can be
-// selected with CXXDES_B200_MM1_GEOMETRY=<n> (a deeper ring holds longer queues, a shallower one
-// leaves room for more resident warps).
+// Launch geometries: threads per block, resident blocks per SM, window slots per replication.
+// 0 is the default; 1 exists to measure block-size sensitivity (CXXDES_B200_MM1_GEOMETRY=1).
+// (Shallower windows with more resident warps were measured slower: 16 slots x 32 warps/SM
+// 113.8 ms against 109.2 ms for 32 slots x 24 warps/SM at lambda = 1.)
 template <int T, int B, int S>
 struct geometry {
     static constexpr int THREADS = T, MIN_BLOCKS = B, RING_SLOTS = S;
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
 };
 using geometry0 = geometry<256, 3, 32>;
-using geometry1 = geometry<256, 4, 16>;
-using geometry2 = geometry<128, 6, 32>;
-using geometry3 = geometry<128, 8, 16>;
+using geometry1 = geometry<128, 6, 32>;
 
 template <typename G>
 void fill_plan(mm1_fused_plan &p, int sm_count) {
@@ -165,68 +196,82 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
     p.ah_geometry = env ? atoi(env) : 0;
     switch (p.ah_geometry) {
         case 1: fill_plan<geometry1>(p, sm_count); break;
-        case 2: fill_plan<geometry2>(p, sm_count); break;
-        case 3: fill_plan<geometry3>(p, sm_count); break;
         default: p.ah_geometry = 0; fill_plan<geometry0>(p, sm_count); break;
     }
-    // one physical slot is kept for the arrival time after the last generated packet
-    uint32_t cap = queue_capacity ? queue_capacity : p.ah_ring_slots - 1;
-    if (cap > p.ah_ring_slots - 1) cap = p.ah_ring_slots - 1;
-    if (cap < 2) cap = 2;
-    p.ah_ring_cap = cap;
-    // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the ring also holds the packets
-    // generated ahead (2 to 4).  If more than ~2% of the replications are expected to outgrow it,
-    // run everything on the global-memory kernel instead.
+    const uint32_t window = p.ah_ring_slots - 1;  // one slot holds the arrival key after the last packet
+    // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the window also holds the packets
+    // generated ahead (2 to 4).  If more than ~0.1% of the replications are expected to outgrow it,
+    // the ring gets its second level in global memory, sized so that overflowing THAT has
+    // probability < 1e-12 per arrival (what still overflows is redone by the fallback kernel).
     const double rho = prm.lambda / prm.mu;
-    const double q = (double)cap - 3.0;
-    const double p_over = rho >= 1.0 ? 1.0 : pow(rho, q > 0 ? q : 0.0) * (double)prm.n_packets;
+    const double q = (double)window - 3.0;
+    const double p_over = rho >= 1.0 ? 1.0 : pow(rho, q) * (double)prm.n_packets;
+    p.ah_spill = !queue_capacity && !(p_over < 1e-3);
+    p.ah_gring_slots = 0;
+    if (p.ah_spill) {
+        double need = rho < 1.0 ? ceil(log(1e-12 / (double)prm.n_packets) / log(rho)) + 64.0 : (double)prm.n_packets + 64.0;
+        if (need > (double)prm.n_packets + 64.0) need = (double)prm.n_packets + 64.0;
+        const uint64_t threads = (uint64_t)p.ah_blocks * p.ah_threads;
+        uint64_t budget = (8ULL << 30) / (threads * sizeof(uint2));  // 8 GiB of the 180
+        uint32_t slots = 64;
+        while (slots < need && slots * 2ULL <= budget) slots *= 2;
+        p.ah_gring_slots = slots;
+        p.ah_ring_cap = slots;
+        p.ah_lead_cap = window - 1;
+    } else {
+        uint32_t cap = queue_capacity ? queue_capacity : window;
+        if (cap > window) cap = window;
+        if (cap < 2) cap = 2;
+        p.ah_ring_cap = cap;
+        p.ah_lead_cap = cap;
+    }
     // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds())
-    p.ah_direct_global = !(p_over < 0.02) || tick_mult >= (1 << 23);
+    p.ah_direct_global = tick_mult >= (1 << 23);
+}
+
+size_t mm1_ahead_gring_bytes(const mm1_fused_plan &p) {
+    return p.ah_spill ? (size_t)p.ah_gring_slots * p.ah_blocks * p.ah_threads * sizeof(uint2) : 0;
 }
 
 namespace {
-template <typename G, int MODE>
-cudaError_t configure_mode() {
-    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE>,
+template <typename G, int MODE, bool SPILL>
+cudaError_t configure_one() {
+    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
 }
-template <typename G>
+template <typename G, bool SPILL>
 cudaError_t configure_geometry() {
-    cudaError_t e = configure_mode<G, 0>();
-    if (e == cudaSuccess) e = configure_mode<G, 1>();
-    if (e == cudaSuccess) e = configure_mode<G, 2>();
-    if (e == cudaSuccess) e = configure_mode<G, 3>();
+    cudaError_t e = configure_one<G, 0, SPILL>();
+    if (e == cudaSuccess) e = configure_one<G, 1, SPILL>();
+    if (e == cudaSuccess) e = configure_one<G, 2, SPILL>();
+    if (e == cudaSuccess) e = configure_one<G, 3, SPILL>();
     return e;
 }
-template <typename G, int MODE>
-void launch_mode(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                 const mm1_fused_plan &plan, cudaStream_t stream) {
-    mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE>
-        <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out);
+template <typename G, int MODE, bool SPILL>
+void launch_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                const mm1_fused_plan &plan, uint2 *gring, cudaStream_t stream) {
+    mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL>
+        <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots);
 }
-template <typename G>
+template <typename G, bool SPILL>
 void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh,
-                     const device_columns &out, const mm1_fused_plan &plan, cudaStream_t stream) {
+                     const device_columns &out, const mm1_fused_plan &plan, uint2 *gring, cudaStream_t stream) {
     switch (mode) {
-        case 0: launch_mode<G, 0>(c, prm, sh, out, plan, stream); break;
-        case 1: launch_mode<G, 1>(c, prm, sh, out, plan, stream); break;
-        case 2: launch_mode<G, 2>(c, prm, sh, out, plan, stream); break;
-        default: launch_mode<G, 3>(c, prm, sh, out, plan, stream); break;
+        case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, gring, stream); break;
+        case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, gring, stream); break;
+        case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, gring, stream); break;
+        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, gring, stream); break;
     }
 }
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    switch (plan.ah_geometry) {
-        case 1: return configure_geometry<geometry1>();
-        case 2: return configure_geometry<geometry2>();
-        case 3: return configure_geometry<geometry3>();
-        default: return configure_geometry<geometry0>();
-    }
+    if (plan.ah_geometry == 1) return plan.ah_spill ? configure_geometry<geometry1, true>() : configure_geometry<geometry1, false>();
+    return plan.ah_spill ? configure_geometry<geometry0, true>() : configure_geometry<geometry0, false>();
 }
 
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, cudaStream_t stream) {
+                             const mm1_fused_plan &plan, void *gring, cudaStream_t stream) {
     mm1::constants c;
     c.lambda = make_divisor(prm.lambda);  // IEEE 1/d on the host: same bits as on the device
     c.mu = make_divisor(prm.mu);
@@ -236,13 +281,16 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.tick_mult = (double)sh.clk.tick_mult;
     c.n_packets = (uint32_t)prm.n_packets;
     c.ring_cap = plan.ah_ring_cap;
+    c.lead_cap = plan.ah_lead_cap;
     c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
     const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
-    switch (plan.ah_geometry) {
-        case 1: launch_geometry<geometry1>(mode, c, prm, sh, out, plan, stream); break;
-        case 2: launch_geometry<geometry2>(mode, c, prm, sh, out, plan, stream); break;
-        case 3: launch_geometry<geometry3>(mode, c, prm, sh, out, plan, stream); break;
-        default: launch_geometry<geometry0>(mode, c, prm, sh, out, plan, stream); break;
+    uint2 *g = (uint2 *)gring;
+    if (plan.ah_geometry == 1) {
+        if (plan.ah_spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, g, stream);
+        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, g, stream);
+    } else {
+        if (plan.ah_spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, g, stream);
+        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, g, stream);
     }
     return cudaGetLastError();
 }

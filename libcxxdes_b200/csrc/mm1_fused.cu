@@ -365,7 +365,7 @@ constexpr int FAST_MIN_BLOCKS = 4;
 constexpr int FB_THREADS = 128;
 
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                              size_t smem_optin, int64_t tick_mult) {
+                              size_t smem_optin, int64_t tick_mult, bool lockstep) {
     mm1_fused_plan p{};
     p.threads = FAST_THREADS;
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -385,7 +385,7 @@ mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_
     plan_mm1_ahead(p, prm, queue_capacity, sm_count, tick_mult);
     p.fb_threads = FB_THREADS;
     uint64_t want = prm.n_packets;
-    if (p.direct_global || p.ah_direct_global) {
+    if (lockstep ? p.direct_global : p.ah_direct_global) {
         p.fb_blocks = sm_count * 8;
         // memory budget for the rings: 8 GiB
         uint64_t budget = (8ULL << 30) / ((uint64_t)p.fb_blocks * FB_THREADS * sizeof(int64_t));
@@ -414,7 +414,7 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan) {
 // loaded queues skip the first pass.
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             cudaStream_t stream, int *launches, bool lockstep) {
+                             void *ahead_gring, cudaStream_t stream, int *launches, bool lockstep) {
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     mm1_rates rates;
     rates.lambda = make_divisor(prm.lambda);
@@ -429,7 +429,7 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                                                                         nullptr, nullptr, nullptr);
             e = cudaGetLastError();
         } else {
-            e = launch_mm1_ahead(prm, sh, out, plan, stream);
+            e = launch_mm1_ahead(prm, sh, out, plan, ahead_gring, stream);
         }
         ++*launches;
         if (e != cudaSuccess) return e;

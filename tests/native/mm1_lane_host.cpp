@@ -11,20 +11,56 @@
 using namespace cxb;
 
 namespace {
+// Same two levels as the device ring: a window of `slots` entries (index modulo slots) and, when
+// `spill` is set, a larger second level that receives the entries leaving the window.
+template <bool SPILL_>
 struct host_ring {
     static constexpr bool HAS_PTX_SLOT = false;
-    std::vector<mm1::ring_entry> slots;
-    explicit host_ring(uint32_t n) : slots(n) {}
-    mm1::ring_entry load(uint32_t j) const { return slots[j & (slots.size() - 1)]; }
-    uint32_t load_a(uint32_t j) const { return slots[j & (slots.size() - 1)].ak; }
-    void store_if(bool p, uint32_t j, const mm1::ring_entry &e) { if (p) slots[j & (slots.size() - 1)] = e; }
-    void store_a_if(bool p, uint32_t j, uint32_t ak) { if (p) slots[j & (slots.size() - 1)].ak = ak; }
+    static constexpr bool SPILL = SPILL_;
+    static constexpr int WINDOW = 31;
+    std::vector<mm1::ring_entry> slots, global;
+    host_ring(uint32_t n_global) : slots(WINDOW + 1), global(n_global ? n_global : 1) {}
+    mm1::ring_entry load(uint32_t j, uint32_t g) const {
+        if (SPILL && g - j > (uint32_t)WINDOW) return global[j & (global.size() - 1)];
+        return slots[j & WINDOW];
+    }
+    uint32_t load_a(uint32_t j) const { return slots[j & WINDOW].ak; }
+    void store_if(bool p, uint32_t j, const mm1::ring_entry &e) { if (p) slots[j & WINDOW] = e; }
+    void store_a_if(bool p, uint32_t j, uint32_t ak) { if (p) slots[j & WINDOW].ak = ak; }
+    void spill_if(bool p, uint32_t g) {
+        if (!p) return;
+        global[(g - WINDOW) & (global.size() - 1)] = slots[(g + 1) & WINDOW];
+        global[(g - WINDOW + 1) & (global.size() - 1)] = slots[(g + 2) & WINDOW];
+    }
 };
+
+template <typename Ring>
+void run_one(const mm1::constants &c, Ring &ring, mm1::lane &L, int event_slots, int mode, uint64_t &iters) {
+    for (;;) {
+        ++iters;
+        // same order as one iteration of mm1_ahead_kernel
+        if (!L.is_fast()) L.generic_step<3>(c, ring);
+        L.leave_fast_near_end(c);
+        for (int s = 0; s < event_slots; ++s) {
+            switch (mode) {
+                case 0: L.fast_slot<0>(c, ring); break;
+                case 1: L.fast_slot<1>(c, ring); break;
+                case 2: L.fast_slot<2>(c, ring); break;
+                default: L.fast_slot<3>(c, ring); break;
+            }
+        }
+        const bool want = L.status == 0 && L.wants_packets(c);
+        const bool room = L.template has_room<Ring::SPILL>(c);
+        L.generate_pair(c, ring, LOG_TABLE_HOST, want && room);
+        if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
+        if (L.finished(c)) break;
+    }
+}
 }  // namespace
 
 extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t ticks_per_unit, int64_t tick_mult,
                                  double sec_per_unit, uint64_t seed, uint64_t first, uint64_t n_reps,
-                                 int64_t until, uint32_t ring_cap, uint32_t ring_slots, int event_slots,
+                                 int64_t until, uint32_t ring_cap, uint32_t global_slots, int event_slots,
                                  int general_mode, const cxxdes_b200_columns *out, uint64_t *iterations) {
     mm1::constants c;
     c.lambda = make_divisor(prm->lambda);
@@ -34,34 +70,23 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
     c.sec_per_unit = sec_per_unit;
     c.tick_mult = (double)tick_mult;
     c.n_packets = (uint32_t)prm->n_packets;
-    c.ring_cap = ring_cap;
+    // window only: ring_cap <= 31 packets; spilling ring: ring_cap = global_slots, lead limited to the window
+    c.ring_cap = global_slots ? global_slots : ring_cap;
+    c.lead_cap = global_slots ? 30 : ring_cap;
     c.until = (until < 0 || until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)until;
     uint64_t iters = 0;
+    // MODE 3 (generic step) = run_until check + tick_mult multiply compiled in: same results as the
+    // specialised modes (a multiply by 1.0 and a compare with EMPTY change nothing)
+    const int mode = general_mode ? 3 : (c.until != mm1::EMPTY ? 1 : 0) | (tick_mult != 1 ? 2 : 0);
     for (uint64_t r = 0; r < n_reps; ++r) {
-        host_ring ring(ring_slots);
         mm1::lane L;
         L.init(first + r);
-        for (;;) {
-            ++iters;
-            // same order as one iteration of mm1_ahead_kernel
-            // MODE 3 = run_until check + tick_mult multiply compiled in: same results as the
-            // specialised modes (a multiply by 1.0 and a compare with EMPTY change nothing)
-            if (!L.is_fast()) L.generic_step<3>(c, ring);
-            L.leave_fast_near_end(c);
-            for (int s = 0; s < event_slots; ++s) {
-                const int mode = general_mode ? 3 : (c.until != mm1::EMPTY ? 1 : 0) | (tick_mult != 1 ? 2 : 0);
-                switch (mode) {
-                    case 0: L.fast_slot<0>(c, ring); break;
-                    case 1: L.fast_slot<1>(c, ring); break;
-                    case 2: L.fast_slot<2>(c, ring); break;
-                    default: L.fast_slot<3>(c, ring); break;
-                }
-            }
-            const bool want = L.status == 0 && L.wants_packets(c);
-            const bool room = L.has_room(c);
-            L.generate_pair(c, ring, LOG_TABLE_HOST, want && room);
-            if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-            if (L.finished(c)) break;
+        if (global_slots) {
+            host_ring<true> ring(global_slots);
+            run_one(c, ring, L, event_slots, mode, iters);
+        } else {
+            host_ring<false> ring(0);
+            run_one(c, ring, L, event_slots, mode, iters);
         }
         uint32_t status = L.status;
         int64_t end = (int64_t)L.now;

@@ -34,13 +34,13 @@ def lane_lib():
     return lib
 
 
-def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=31, ring_slots=32, event_slots=4,
+def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=31, global_slots=0, event_slots=4,
               clock=(1000, 1, 1e-3), general_mode=0):
     cols = abi.HostColumns(n_reps)
     st = cols.as_struct()
     iters = C.c_uint64()
     rc = lib.mm1_lane_host_run(C.addressof(p), clock[0], clock[1], clock[2], seed, first, n_reps, until,
-                               ring_cap, ring_slots, event_slots, general_mode, C.byref(st), C.byref(iters))
+                               ring_cap, global_slots, event_slots, general_mode, C.byref(st), C.byref(iters))
     assert rc == 0
     return cols, iters.value
 
@@ -107,6 +107,22 @@ def test_lane_other_clocks(lane_lib, port):
         got, _ = run_lanes(lane_lib, p, 64, seed=9, clock=folded)
         want = port.run(abi.MODEL_MM1, p, abi.Clock.of(unit, prec), 9, 0, 64)
         assert masked_equal(got, want, f"clock {unit}/{prec}").all()
+
+
+@pytest.mark.parametrize("lam,n_packets,slots", [(9.0, 3000, 1024), (9.9, 2000, 2048), (12.0, 400, 512), (5.0, 800, 64),
+                                                   (9.5, 1500, 64)])
+def test_spilling_ring_matches_oracle(lane_lib, port, lam, n_packets, slots):
+    """Heavily loaded queues: entries leave the 31-packet window for the second ring level and come
+    back when the consumer reaches them; nothing but a queue beyond that level may be flagged."""
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, _ = run_lanes(lane_lib, p, 120, seed=21, global_slots=slots)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 21, 0, 120, threads=oracles.os.cpu_count())
+    ok = masked_equal(got, want, f"spill lambda={lam}")
+    assert (want.i64[1] > 40).mean() > 0.3 or lam <= 5.0     # the scenario really leaves the window
+    assert (want.i64[1][~ok] >= slots - 2).all()             # flagged only when the second level is full too
+    assert (got.status[~ok] & abi.REP_QUEUE_OVERFLOW).all()
+    if slots >= 1024:
+        assert ok.all()
 
 
 def test_compile_time_modes_agree(lane_lib):

@@ -196,7 +196,7 @@ int plan(cxxdes_b200_ensemble *e) {
             e->use_fused = !(c.flags & CXXDES_B200_FLAG_GENERIC_ENGINE) && p.n_packets >= 2 &&
                            p.n_packets < (1ULL << 30);
             if (e->use_fused) {
-                e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin, e->clk.tick_mult,
+                e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin, e->clk.tick_mult, e->clk.ticks_per_unit,
                                              (c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0);
                 e->ring_bytes = (size_t)e->mm1_plan.fb_blocks * e->mm1_plan.fb_threads * e->mm1_plan.fb_ring *
                                 sizeof(int64_t);

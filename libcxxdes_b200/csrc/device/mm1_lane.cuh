@@ -185,18 +185,19 @@ CXB_HD double u32_to_double(uint32_t x) {
 }
 
 // double -> ticks, truncating toward zero (environment::real_to_sim, environment.ipp:79-82) for
-// 0 <= x < 2^28; `bad` is raised for anything else (the caller then redoes the replication with
-// 64-bit ticks), identically on host and device.
-CXB_HD uint32_t ticks_u32(double x, uint32_t &bad) {
+// 0 <= x < 2^28.  No per-draw check: a variate is at most -log(2^-52) / rate = 36.05 / rate, and
+// the launcher only uses this representation when 36.05 * ticks_per_unit / rate < 2^28 for both
+// rates (draw_fits_u32 below); everything else runs on the 64-bit kernel.
+CXB_HD uint32_t ticks_u32(double x) {
 #if defined(__CUDA_ARCH__)
-    const double y = __dadd_rz(x, TWO52);  // round toward zero = truncate, x >= 0
-    const uint32_t hi = (uint32_t)__double2hiint(y), lo = (uint32_t)__double2loint(y);
-    bad |= (hi ^ 0x43300000u) | (lo >> 28);  // exponent moved (x >= 2^52, inf, nan, x < 0) or >= 2^28
-    return lo;
+    return (uint32_t)__double2loint(__dadd_rz(x, TWO52));  // round toward zero = truncate
 #else
-    if (!(x >= 0.0 && x < 268435456.0)) { bad |= 1u; return 0u; }
     return (uint32_t)x;
 #endif
+}
+
+inline bool draw_fits_u32(double rate, double ticks_per_unit) {
+    return 36.05 * ticks_per_unit / rate < (double)DRAW_LIMIT;
 }
 
 // Launch-invariant values (kernel parameters: read straight from the constant bank).
@@ -299,15 +300,15 @@ struct lane {
         const philox_block bp = philox4x32_10_scheduled(g >> 1, 1u, ctr2, ctr3, c.keys);
         const philox_block bc = philox4x32_10_scheduled(g >> 1, 2u, ctr2, ctr3, c.keys);
         // env.timeout(exponential()): timeout.ipp:184-187 -> real_to_sim
-        uint32_t bad = 0;
-        const uint32_t ia0 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[1] << 32) | bp.w[0], c.lambda, table) * c.ticks_per_unit, bad);
-        const uint32_t ia1 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[3] << 32) | bp.w[2], c.lambda, table) * c.ticks_per_unit, bad);
-        const uint32_t s0 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[1] << 32) | bc.w[0], c.mu, table) * c.ticks_per_unit, bad);
-        const uint32_t s1 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[3] << 32) | bc.w[2], c.mu, table) * c.ticks_per_unit, bad);
-        // range guard: each delay < 2^28 and the bound on the last event time < 2^30, so no
-        // 32-bit sum or key below can wrap; otherwise the replication is redone with 64-bit ticks
+        const uint32_t ia0 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[1] << 32) | bp.w[0], c.lambda, table) * c.ticks_per_unit);
+        const uint32_t ia1 = ticks_u32(exponential_from_bits(((uint64_t)bp.w[3] << 32) | bp.w[2], c.lambda, table) * c.ticks_per_unit);
+        const uint32_t s0 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[1] << 32) | bc.w[0], c.mu, table) * c.ticks_per_unit);
+        const uint32_t s1 = ticks_u32(exponential_from_bits(((uint64_t)bc.w[3] << 32) | bc.w[2], c.mu, table) * c.ticks_per_unit);
+        // range guard: each delay < 2^28 (draw_fits_u32) and the bound on the last event time
+        // < 2^30, so no 32-bit sum or key below can wrap; otherwise the replication is redone with
+        // 64-bit ticks
         const uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
-        const bool out_of_range = (bad != 0) | (new_budget >= TIME_LIMIT);
+        const bool out_of_range = new_budget >= TIME_LIMIT;
         const bool commit = enable & !out_of_range;
         status |= (enable & out_of_range) ? (uint32_t)CXXDES_B200_REP_TIME_RANGE : 0u;
         const uint32_t a1k = agk + 4u * ia0;

@@ -32,7 +32,7 @@ struct mm1_fused_plan {
     bool ah_direct_global;
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                              size_t smem_per_block_optin, int64_t tick_mult, bool lockstep);
+                              size_t smem_per_block_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep);
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
                              void *ahead_gring, cudaStream_t stream, int *launches, bool lockstep);
@@ -40,7 +40,7 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
 // ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
 void plan_mm1_ahead(mm1_fused_plan &plan, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                    int64_t tick_mult);
+                    int64_t tick_mult, int64_t ticks_per_unit);
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &plan);
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,

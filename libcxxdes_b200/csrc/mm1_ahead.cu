@@ -21,6 +21,12 @@
 #include "device/models_common.cuh"
 #include "kernels.h"
 
+// Generation + event-slot rounds per pass of the outer loop (work stealing, start-up/wind-down and
+// end-of-replication checks run once per pass).
+#ifndef CXB_MM1_UNROLL
+#define CXB_MM1_UNROLL 1
+#endif
+
 namespace cxb {
 
 namespace {
@@ -122,17 +128,23 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 
         // ---- 1. start-up / wind-down events (rare) ----
         if (active && !L.is_fast()) L.template generic_step<MODE>(c, ring);
-        static_assert(EVENT_SLOTS <= (int)mm1::lane::TAIL, "the end-of-steady-state check runs once per iteration");
+        static_assert(EVENT_SLOTS * CXB_MM1_UNROLL <= (int)mm1::lane::TAIL,
+                      "the end-of-steady-state check runs once per iteration");
         L.leave_fast_near_end(c);
         __syncwarp();
 
         // ---- 2. one branch-free block: steady-state events on the packets generated so far,
         //         and the next two packets for every lane that has room for them ----
+        bool want, room;
 #pragma unroll
-        for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
-        const bool want = active && L.status == 0 && L.wants_packets(c);
-        const bool room = L.template has_room<SPILL>(c);
-        L.generate_pair(c, ring, table, want & room);
+        for (int u = 0; u < CXB_MM1_UNROLL; ++u) {
+#pragma unroll
+            for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
+            want = active && L.status == 0 && L.wants_packets(c);
+            room = L.template has_room<SPILL>(c);
+            L.generate_pair(c, ring, table, want & room);
+        }
+        // (a ring that is truly exhausted stays so, checking after the last generation is enough)
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
 
         // ---- 4. end of this lane's replication? ----
@@ -191,7 +203,7 @@ void fill_plan(mm1_fused_plan &p, int sm_count) {
 }  // namespace
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                    int64_t tick_mult) {
+                    int64_t tick_mult, int64_t ticks_per_unit) {
     const char *env = getenv("CXXDES_B200_MM1_GEOMETRY");
     p.ah_geometry = env ? atoi(env) : 0;
     switch (p.ah_geometry) {
@@ -226,7 +238,9 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
         p.ah_lead_cap = cap;
     }
     // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds())
-    p.ah_direct_global = tick_mult >= (1 << 23);
+    // ... and every single delay must fit the 32-bit tick representation
+    p.ah_direct_global = tick_mult >= (1 << 23) || !mm1::draw_fits_u32(prm.lambda, (double)ticks_per_unit) ||
+                         !mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit);
 }
 
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &p) {

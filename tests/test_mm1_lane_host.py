@@ -91,7 +91,9 @@ def test_lane_run_until(lane_lib, port, until):
 
 
 def test_lane_tick_range_guard(lane_lib, port):
-    p = abi.MM1Params(0.00002, 0.001, 400)
+    """Slow arrivals (every delay still below 2^28 ticks, the launcher's precondition): the clock
+    passes 2^30 and the lane must ask for the 64-bit kernel instead of wrapping."""
+    p = abi.MM1Params(0.0002, 0.01, 400)
     got, _ = run_lanes(lane_lib, p, 64)
     want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0x5EED, 0, 64, threads=4)
     ok = masked_equal(got, want, "slow arrivals")

@@ -277,8 +277,8 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             break;
         case CXXDES_B200_MODEL_ALOHA:
-            CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->stream));
-            launches = 1;
+            CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
+                                  &launches));
             break;
         case CXXDES_B200_MODEL_MMC:
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->stream));

@@ -49,7 +49,8 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
-                         int sm_count, size_t smem_optin, cudaStream_t stream);
+                         int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
+                         int *launches);
 
 // ---- M/M/c with balking (models_mmc.cu) ----
 int mmc_blocks(int sm_count);

@@ -12,6 +12,7 @@
 //             shared all_of handler on their completion tokens (any_of.ipp:41-84,197-209)
 //   station   for i < pps: { collided = false; insert; check_collisions; timeout(frame_time);
 //                            erase; if (!collided) ++succ; timeout(exponential()) }
+#include "device/engine32.cuh"
 #include "device/models_common.cuh"
 #include "kernels.h"
 
@@ -45,8 +46,11 @@ __device__ __forceinline__ aloha_rep_params aloha_params_of(const cxxdes_b200_al
 
 }  // namespace
 
+// Generic-engine kernel: 64-bit keys, any parameter range.  Runs the whole shard, or (list != nullptr)
+// only the replications the compact kernel below handed back.
 __global__ void __launch_bounds__(ALOHA_THREADS)
-aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out) {
+aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, const uint32_t *list,
+             const unsigned long long *list_count, unsigned long long *list_cursor) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -61,7 +65,14 @@ aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out) {
     const uint32_t HANDLER_TAG = make_tag(0, 1);
 
     uint64_t rep;
-    while (steal(sh, rep)) {
+    for (;;) {
+        if (list) {
+            const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+            if (idx >= *list_count) break;
+            rep = list[idx];
+        } else if (!steal(sh, rep)) {
+            break;
+        }
         const uint64_t grep = sh.first_replication + rep;
         const aloha_rep_params rp = aloha_params_of(prm, grep);
         // exponential_rv{seed, cfg_.lambda / cfg_.num_stations}: float / size_t -> float -> double (:52)
@@ -151,14 +162,185 @@ aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compact kernel (the default): the same lowering on device/engine32.cuh.
+//   * tokens are {u32 time, u32 tag}; the tag's low 7 bits name the target (0 co_main, 1..64
+//     station, 65 the all_of handler, 66 a null-target completion) and, because every station
+//     has exactly one token scheduled at any time, its loop counter i rides in the upper 25
+//     bits -- no per-station arrays at all: 8 bytes x (N + 2) per replication, 384 resident
+//     threads per SM instead of 128;
+//   * one flat loop, one event per lane per iteration, and a lane whose replication ends takes
+//     the next one at once: replications of the load sweep differ 30x in length, a nested
+//     "while (events)" loop leaves the warp waiting for its longest lane;
+//   * Philox round keys come precomputed from the constant bank (the key is the seed).
+// Replications whose clock would pass 2^32 ticks are handed to aloha_kernel above.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int AF_THREADS = 128;
+constexpr int AF_BLOCKS_PER_SM = 3;
+constexpr uint32_t CODE_MAIN = 0, CODE_HANDLER = 65, CODE_NOOP = 66, CODE_MASK = 127;
+constexpr int COUNTER_SHIFT = 7;
+}  // namespace
+
+__global__ void __launch_bounds__(AF_THREADS, AF_BLOCKS_PER_SM)
+aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, philox_schedule keys, uint32_t until) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    stage_log_table(table, sh.log_table);
+    const int N = (int)prm.num_stations;
+    const int heap_cap = N + 2;
+    lane_array<uint32_t> hkey = carve<uint32_t>(cursor, heap_cap);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
+
+    const int64_t frame_ticks = real_to_sim_f32(prm.frame_time, sh.clk);  // env.timeout(float), aloha.cpp:60
+
+    environment32 env;
+    env.init(hkey, htag, heap_cap);
+    uint64_t rep = 0, active_set = 0, collided = 0, pc_tx = 0;
+    uint32_t successful = 0, main_pc = 0, remaining = 0, ctr2 = 0, ctr3 = 0;
+    bool armed = false;
+    aloha_rep_params rp{};
+    divisor rate{};
+    float s_result = 0.0f, g_result = 0.0f;
+    bool active = false, exhausted = false;
+
+    for (;;) {
+        if (!active && !exhausted) {
+            if (steal(sh, rep)) {
+                const uint64_t grep = sh.first_replication + rep;
+                rp = aloha_params_of(prm, grep);
+                // exponential_rv{seed, cfg_.lambda / cfg_.num_stations}: float / size_t -> float -> double (:52)
+                rate = make_divisor((double)(rp.lambda / (float)prm.num_stations));
+                ctr2 = (uint32_t)grep;
+                ctr3 = (uint32_t)(grep >> 32);
+                env.init(hkey, htag, heap_cap);
+                active_set = collided = pc_tx = 0;
+                successful = 0; main_pc = 0; remaining = 0; armed = false;
+                s_result = g_result = 0.0f;
+                env.schedule(0, CODE_MAIN);  // environment::bind(co_main)
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+        if (active) {
+            const token32 t = env.step_pop();  // environment::step, environment.ipp:117-126
+            const uint32_t code = t.tag & CODE_MASK;
+            if (code - 1u < 64u) {
+                // station, aloha.cpp:51-71
+                env.fold(t.time, TOKEN_RESUME, code);
+                const uint64_t bit = 1ULL << (code - 1);
+                const uint32_t i = t.tag >> COUNTER_SHIFT;
+                if (pc_tx & bit) {
+                    // frame finished: erase, count, draw the waiting time (:62-69); the for loop's ++i
+                    // happens when the station resumes, nothing looks at i before that
+                    pc_tx &= ~bit;
+                    active_set &= ~bit;
+                    if (!(collided & bit)) ++successful;
+                    const philox_block b = philox4x32_10_scheduled(i >> 1, code, ctr2, ctr3, keys);
+                    const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
+                    const double wait = exponential_from_bits(bits, rate, table);
+                    env.schedule_after(real_to_sim(wait, sh.clk), code | ((i + 1) << COUNTER_SHIFT));
+                } else if (i < rp.pps) {
+                    // collided = false; insert; check_collisions (:55-59,73-78)
+                    collided &= ~bit;
+                    active_set |= bit;
+                    if (__popcll(active_set) > 1) collided |= active_set;
+                    env.schedule_after(frame_ticks, t.tag);
+                    pc_tx |= bit;
+                } else {
+                    env.schedule(env.now, CODE_HANDLER);  // co_return -> completion token with the all_of handler
+                }
+            } else if (code == CODE_HANDLER) {
+                // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time
+                env.fold(t.time, TOKEN_HANDLER, 0);
+                --remaining;
+                if (armed && remaining == 0) {
+                    env.schedule(t.time, CODE_MAIN);
+                    armed = false;
+                }
+            } else if (code == CODE_MAIN) {
+                env.fold(t.time, TOKEN_RESUME, 0);
+                if (main_pc == 0) {
+                    // co_main, aloha.cpp:39-44: bind stations in index order, one all_of handler
+                    for (int s = 0; s < N; ++s) env.schedule(env.now, (uint32_t)(1 + s));
+                    remaining = (uint32_t)N;
+                    armed = true;
+                    main_pc = 1;
+                } else {
+                    // :46-47  S = succ / now_seconds() (size_t / double -> float), G = lambda * frame_time
+                    s_result = (float)((double)successful / sim_to_seconds((int64_t)env.now, sh.clk));
+                    g_result = rp.lambda * prm.frame_time;
+                    env.schedule(env.now, CODE_NOOP);  // co_main returns
+                }
+            } else {
+                env.fold(t.time, TOKEN_NOOP, PROC_NONE);
+            }
+
+            // environment::run / run_until (environment.ipp:179-196)
+            if (env.status || !env.has_event() || env.next_time() > until) {
+                active = false;
+                if (env.status & CXXDES_B200_REP_TIME_RANGE) {
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                } else {
+                    rep_out o;
+                    int64_t end = (int64_t)env.now;
+                    o.status = env.status;
+                    if (sh.run_until >= 0) {
+                        if (env.has_event()) o.status |= CXXDES_B200_REP_UNFINISHED;
+                        end = end > sh.run_until ? end : sh.run_until;
+                    }
+                    o.end_time = end;
+                    o.n_events = env.n_events;
+                    o.trace_hash = env.hash;
+                    o.f64[0] = (double)s_result;
+                    o.f64[1] = (double)g_result;
+                    o.i64[0] = (int64_t)successful;
+                    o.i64[1] = (int64_t)rp.pps;
+                    store_result(out, rep, o);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 size_t aloha_smem_bytes(uint32_t num_stations) {
     const size_t n = num_stations;
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
            (size_t)ALOHA_THREADS * ((n + 2) * (8 + 4) + n * 4);
 }
 
+namespace {
+size_t aloha_fast_smem_bytes(uint32_t num_stations) {
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + (size_t)AF_THREADS * (num_stations + 2) * 8;
+}
+
+// The compact kernel counts events and loop iterations in 32 / 25 bits and keeps every delay
+// below 2^31 ticks; anything else runs on the generic kernel.
+bool aloha_fast_applies(const cxxdes_b200_aloha_params &p, const shard &sh) {
+    double lam_lo = p.lambda_begin, lam_hi = p.lambda_begin;
+    double pps = (double)p.packets_per_station;
+    if (p.sweep_steps > 1) {
+        lam_lo = p.lambda_begin < p.lambda_end ? p.lambda_begin : p.lambda_end;
+        lam_hi = p.lambda_begin < p.lambda_end ? p.lambda_end : p.lambda_begin;
+        pps = lam_hi * (double)p.packets_scale;
+    }
+    if (!(lam_lo > 0.0) || !(pps < 8388608.0)) return false;
+    const double tpu = (double)sh.clk.ticks_per_unit;
+    // a variate is at most 36.05 / rate (rate = lambda / N)
+    if (!(36.05 * tpu * (double)p.num_stations / lam_lo < 1073741824.0)) return false;
+    return (double)p.frame_time * tpu < 1073741824.0;
+}
+}  // namespace
+
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
-                         int sm_count, size_t smem_optin, cudaStream_t stream) {
+                         int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
+                         int *launches) {
     const size_t smem = aloha_smem_bytes(prm.num_stations);
     if (smem > smem_optin) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(aloha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -166,7 +348,24 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    aloha_kernel<<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out);
+    if (aloha_fast_applies(prm, sh)) {
+        const size_t fsmem = aloha_fast_smem_bytes(prm.num_stations);
+        e = cudaFuncSetAttribute(aloha_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e != cudaSuccess) return e;
+        const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
+        const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
+        aloha_fast_kernel<<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // the replications it handed back (normally none): exits at once when the list is empty
+        aloha_kernel<<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, sh.retry_list, sh.retry_count,
+                                                                         list_cursor);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    aloha_kernel<<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, nullptr, nullptr, nullptr);
+    ++*launches;
     return cudaGetLastError();
 }
 

@@ -229,6 +229,12 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
         if (active) {
             const token32 t = env.step_pop();  // environment::step, environment.ipp:117-126
             const uint32_t code = t.tag & CODE_MASK;
+            // Every event but co_main's first pushes exactly one token; the branches below only
+            // decide which (delay, tag), and the push itself -- the sift through the heap -- is one
+            // piece of code all lanes run together.
+            int64_t delay = 0;
+            uint32_t push_tag = CODE_NOOP;
+            bool push = true;
             if (code - 1u < 64u) {
                 // station, aloha.cpp:51-71
                 env.fold(t.time, TOKEN_RESUME, code);
@@ -243,25 +249,27 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                     const philox_block b = philox4x32_10_scheduled(i >> 1, code, ctr2, ctr3, keys);
                     const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
                     const double wait = exponential_from_bits(bits, rate, table);
-                    env.schedule_after(real_to_sim(wait, sh.clk), code | ((i + 1) << COUNTER_SHIFT));
+                    delay = real_to_sim(wait, sh.clk);
+                    push_tag = code | ((i + 1) << COUNTER_SHIFT);
                 } else if (i < rp.pps) {
                     // collided = false; insert; check_collisions (:55-59,73-78)
                     collided &= ~bit;
                     active_set |= bit;
                     if (__popcll(active_set) > 1) collided |= active_set;
-                    env.schedule_after(frame_ticks, t.tag);
                     pc_tx |= bit;
+                    delay = frame_ticks;
+                    push_tag = t.tag;
                 } else {
-                    env.schedule(env.now, CODE_HANDLER);  // co_return -> completion token with the all_of handler
+                    push_tag = CODE_HANDLER;  // co_return -> completion token with the all_of handler
                 }
             } else if (code == CODE_HANDLER) {
                 // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time
+                // (== now: completions are scheduled at now + 0)
                 env.fold(t.time, TOKEN_HANDLER, 0);
                 --remaining;
-                if (armed && remaining == 0) {
-                    env.schedule(t.time, CODE_MAIN);
-                    armed = false;
-                }
+                push = armed && remaining == 0;
+                if (push) armed = false;
+                push_tag = CODE_MAIN;
             } else if (code == CODE_MAIN) {
                 env.fold(t.time, TOKEN_RESUME, 0);
                 if (main_pc == 0) {
@@ -270,15 +278,18 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                     remaining = (uint32_t)N;
                     armed = true;
                     main_pc = 1;
+                    push = false;
                 } else {
                     // :46-47  S = succ / now_seconds() (size_t / double -> float), G = lambda * frame_time
                     s_result = (float)((double)successful / sim_to_seconds((int64_t)env.now, sh.clk));
                     g_result = rp.lambda * prm.frame_time;
-                    env.schedule(env.now, CODE_NOOP);  // co_main returns
+                    // co_main returns: null-target completion
                 }
             } else {
                 env.fold(t.time, TOKEN_NOOP, PROC_NONE);
+                push = false;
             }
+            if (push) env.schedule_after(delay, push_tag);
 
             // environment::run / run_until (environment.ipp:179-196)
             if (env.status || !env.has_event() || env.next_time() > until) {

@@ -61,14 +61,18 @@ struct lane_array {
 };
 
 // Carve `count` elements per thread of type T out of the block's dynamic shared memory.
+// The cursor only ever moves by pointer arithmetic (the integer cast below computes the padding,
+// not the pointer), so the compiler keeps seeing a pointer into the __shared__ array and emits
+// LDS/STS; through an integer round trip it falls back to generic LD/ST, which costs latency
+// and sits on the long scoreboard.
 template <typename T>
 __device__ __forceinline__ lane_array<T> carve(unsigned char *&cursor, int count) {
-    uintptr_t p = (uintptr_t)cursor;
-    p = (p + alignof(T) - 1) & ~(uintptr_t)(alignof(T) - 1);
+    const size_t mis = (size_t)((uintptr_t)cursor & (alignof(T) - 1));
+    unsigned char *p = cursor + ((alignof(T) - mis) & (alignof(T) - 1));
     lane_array<T> a;
     a.base = (T *)p + threadIdx.x;
     a.stride = blockDim.x;
-    cursor = (unsigned char *)((T *)p + (size_t)count * blockDim.x);
+    cursor = p + sizeof(T) * (size_t)count * blockDim.x;
     return a;
 }
 

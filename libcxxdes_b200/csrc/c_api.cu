@@ -281,8 +281,8 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                                   &launches));
             break;
         case CXXDES_B200_MODEL_MMC:
-            CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->stream));
-            launches = 1;
+            CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
+                                &launches));
             break;
         case CXXDES_B200_MODEL_ARCHSIM:
             CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream));

@@ -56,7 +56,8 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
 int mmc_blocks(int sm_count);
 int mmc_threads();
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
-                       uint64_t *customer_state, int sm_count, cudaStream_t stream);
+                       uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
+                       int *launches);
 
 // ---- memory hierarchy (models_archsim.cu) ----
 bool archsim_supported(const cxxdes_b200_archsim_params &p);

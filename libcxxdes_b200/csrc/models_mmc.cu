@@ -11,6 +11,7 @@
 // A handler token always targets the customer whose any_of owns it, so the handler is found
 // from the target.  Per-customer state is one 64-bit word in global memory laid out
 // [customer][thread] (lanes walk the customers roughly in step, so accesses coalesce).
+#include "device/engine32.cuh"
 #include "device/models_common.cuh"
 #include "kernels.h"
 
@@ -29,8 +30,11 @@ constexpr int C_T0_SHIFT = 16;
 
 }  // namespace
 
+// Generic-engine kernel: 64-bit keys, 96-entry heap and waiter list.  Runs the whole shard, or
+// (list != nullptr) only the replications the compact kernel below handed back.
 __global__ void __launch_bounds__(MMC_THREADS)
-mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base) {
+mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, const uint32_t *list,
+           const unsigned long long *list_count, unsigned long long *list_cursor) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -48,7 +52,14 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
     const uint32_t NOOP_TAG = make_tag(TAG_NO_TARGET);
 
     uint64_t rep;
-    while (steal(sh, rep)) {
+    for (;;) {
+        if (list) {
+            const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+            if (idx >= *list_count) break;
+            rep = list[idx];
+        } else if (!steal(sh, rep)) {
+            break;
+        }
         const uint64_t grep = sh.first_replication + rep;
         stream_addr addr;
         addr.seed = sh.seed;
@@ -168,20 +179,253 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compact kernel (the default): the same lowering on device/engine32.cuh -- 8-byte tokens
+// {u32 time, u32 target | handler << 16}, 64-entry heap, 64 waiters as 16-bit process ordinals
+// (every waiter is an acquire_proc: priority 0, latency 0), i.e. 640 bytes of shared memory per
+// replication instead of 1920, so 352 threads are resident per SM instead of 96; one flat loop
+// with in-loop work stealing.  A replication that outgrows these capacities or the 32-bit clock
+// is handed to mmc_kernel above.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int MF_THREADS = 176;
+constexpr int MF_BLOCKS_PER_SM = 2;
+constexpr int MF_HEAP = 64;
+constexpr int MF_WAITERS = 64;
+constexpr uint32_t MF_HANDLER = 1u << 16;
+constexpr uint32_t MF_NOOP = TAG_NO_TARGET;
+
+struct wait_list16 {
+    lane_array<uint16_t> who;
+    int n;
+    // wait_awaitable::await_suspend, event.hpp:136-139
+    __device__ __forceinline__ void wait(environment32 &env, uint32_t proc) {
+        if (n >= MF_WAITERS) {
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return;
+        }
+        who[n++] = (uint16_t)proc;
+    }
+    // wake_awaitable::await_ready, event.hpp:125-134: schedule every waiter in list order
+    __device__ __forceinline__ void wake(environment32 &env) {
+        for (int i = 0; i < n; ++i) env.schedule(env.now, (uint32_t)who[i]);
+        n = 0;
+    }
+};
+}  // namespace
+
+__global__ void __launch_bounds__(MF_THREADS, MF_BLOCKS_PER_SM)
+mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, philox_schedule keys,
+                uint32_t until) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    log_entry *table = (log_entry *)smem;
+    unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
+    stage_log_table(table, sh.log_table);
+    lane_array<uint32_t> hkey = carve<uint32_t>(cursor, MF_HEAP);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, MF_HEAP);
+    wait_list16 waiters;
+    waiters.who = carve<uint16_t>(cursor, MF_WAITERS);
+    waiters.n = 0;
+
+    const uint64_t total_threads = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t *cust = cust_base + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t n = (uint32_t)prm.n_customers;
+    const int64_t patience_ticks = real_to_sim(prm.patience, sh.clk);  // env.timeout(patience)
+    const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
+
+    environment32 env;
+    env.init(hkey, htag, MF_HEAP);
+    uint64_t rep = 0;
+    uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
+    double total_wait = 0.0;
+    bool active = false, exhausted = false;
+
+    auto draw = [&](uint32_t stream, uint32_t index, const divisor &rate) {
+        const philox_block b = philox4x32_10_scheduled(index >> 1, stream, ctr2, ctr3, keys);
+        const uint64_t bits = (index & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
+        return real_to_sim(exponential_from_bits(bits, rate, table), sh.clk);
+    };
+
+    for (;;) {
+        if (!active && !exhausted) {
+            if (steal(sh, rep)) {
+                const uint64_t grep = sh.first_replication + rep;
+                ctr2 = (uint32_t)grep;
+                ctr3 = (uint32_t)(grep >> 32);
+                env.init(hkey, htag, MF_HEAP);
+                waiters.n = 0;
+                value = prm.servers;  // semaphore{c, c}
+                i = served = balked = 0;
+                main_pc = source_pc = 0;
+                total_wait = 0.0;
+                for (uint32_t c = 0; c < n; ++c) cust[(uint64_t)c * total_threads] = 0;
+                env.schedule(0, 0);  // environment::bind(co_main)
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+        if (active) {
+            const token32 t = env.step_pop();
+            const uint32_t target = t.tag & 0xFFFFu;
+            if (t.tag & MF_HANDLER) {
+                // any_of handler of customer (target - 2) / 2: any_of.ipp:9-26
+                env.fold(t.time, TOKEN_HANDLER, target);
+                uint64_t *w = &cust[(uint64_t)((target - 2) >> 1) * total_threads];
+                uint64_t s = *w;
+                const uint64_t remaining = ((s & C_REM) >> C_REM_SHIFT) - 1;
+                s = (s & ~C_REM) | (remaining << C_REM_SHIFT);
+                if ((s & C_ARMED) && remaining < 2) {
+                    env.schedule(t.time, target);  // output token
+                    s &= ~C_ARMED;
+                }
+                *w = s;
+            } else if (target == MF_NOOP) {
+                env.fold(t.time, TOKEN_NOOP, PROC_NONE);
+            } else {
+                env.fold(t.time, TOKEN_RESUME, target);
+                if (target == 0) {
+                    if (main_pc == 0) {
+                        env.schedule(env.now, 1);  // co_await source(): start token; completion targets main
+                        main_pc = 1;
+                    } else {
+                        env.schedule(env.now, MF_NOOP);
+                    }
+                } else if (target == 1) {
+                    // source: for i < n { co_await async(customer(i)); co_await env.timeout(arr()); }
+                    if (source_pc == 1) ++i;
+                    if (i < n) {
+                        env.schedule(env.now, 2 + 2 * i);  // async: start token (async.ipp:21-28)
+                        env.schedule_after(draw(1, i, d_lambda), 1);
+                        source_pc = 1;
+                    } else {
+                        env.schedule(env.now, 0);  // source returns -> completion resumes co_main
+                    }
+                } else {
+                    const uint32_t id = (target - 2) >> 1;
+                    uint64_t *w = &cust[(uint64_t)id * total_threads];
+                    uint64_t s = *w;
+                    if ((target & 1) == 0) {
+                        // ---- customer(id) ----
+                        const uint64_t pc = s & C_PC;
+                        if (pc == 0) {
+                            // t0 = now_seconds(); any_of(acquire_proc, env.timeout(patience))
+                            s = ((uint64_t)env.now << C_T0_SHIFT) | 1 | C_ARMED | (2ULL << C_REM_SHIFT);
+                            env.schedule(env.now, target + 1);                        // await_bind: start(acquire_proc)
+                            env.schedule_after(patience_ticks, target | MF_HANDLER);  // await_suspend: timeout + handler
+                        } else if (pc == 1) {
+                            if (!(s & C_ACQ_DONE)) {
+                                s = (s & ~C_PC) | 3 | C_BALKED;  // balked: co_return
+                                ++balked;
+                                env.schedule(env.now, MF_NOOP);  // async's null-target completion
+                            } else {
+                                const double t0 = sim_to_seconds((int64_t)(s >> C_T0_SHIFT), sh.clk);
+                                total_wait += sim_to_seconds((int64_t)env.now, sh.clk) - t0;
+                                env.schedule_after(draw(target, 0, d_mu), target);
+                                s = (s & ~C_PC) | 2;
+                            }
+                        } else {
+                            // release: semaphore::up -> ++value; wake  (semaphore.hpp:58-66)
+                            ++value;
+                            waiters.wake(env);
+                            ++served;
+                            s = (s & ~C_PC) | 3;
+                            env.schedule(env.now, MF_NOOP);
+                        }
+                    } else {
+                        // ---- acquire_proc(id): st.h = co_await servers.acquire(); if (balked) release ----
+                        if (value == 0) {
+                            waiters.wait(env, target);  // semaphore::down blocks (semaphore.hpp:70-78)
+                        } else {
+                            --value;
+                            waiters.wake(env);  // down() wakes every waiter even though it consumed a unit
+                            if (s & C_BALKED) {
+                                ++value;        // late acquisition is released at once
+                                waiters.wake(env);
+                            }
+                            s |= C_ACQ_DONE;
+                            env.schedule(env.now, (target - 1) | MF_HANDLER);  // completion token with the any_of handler
+                        }
+                    }
+                    *w = s;
+                }
+            }
+
+            if (env.status || !env.has_event() || env.next_time() > until) {
+                active = false;
+                if (env.status & (CXXDES_B200_REP_TIME_RANGE | CXXDES_B200_REP_HEAP_OVERFLOW | CXXDES_B200_REP_WAITER_OVERFLOW)) {
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                } else {
+                    rep_out o;
+                    int64_t end = (int64_t)env.now;
+                    o.status = env.status;
+                    if (sh.run_until >= 0) {
+                        if (env.has_event()) o.status |= CXXDES_B200_REP_UNFINISHED;
+                        end = end > sh.run_until ? end : sh.run_until;
+                    }
+                    o.end_time = end;
+                    o.n_events = env.n_events;
+                    o.trace_hash = env.hash;
+                    o.f64[0] = total_wait;
+                    o.f64[1] = 0.0;
+                    o.i64[0] = (int64_t)served;
+                    o.i64[1] = (int64_t)balked;
+                    store_result(out, rep, o);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 size_t mmc_smem_bytes() {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
            (size_t)MMC_THREADS * (MMC_HEAP * (8 + 4) + MMC_WAITERS * (4 + 4));
 }
 
-int mmc_blocks(int sm_count) { return sm_count; }
-int mmc_threads() { return MMC_THREADS; }
+namespace {
+size_t mmc_fast_smem_bytes() {
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + (size_t)MF_THREADS * (MF_HEAP * 8 + MF_WAITERS * 2);
+}
+// 32-bit event counter and clock: a variate is at most 36.05 / rate
+bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
+    const double tpu = (double)sh.clk.ticks_per_unit;
+    const double slow = p.lambda < p.mu ? p.lambda : p.mu;
+    return 36.05 * tpu / slow < 1073741824.0 && p.patience * tpu < 1073741824.0 && p.n_customers < 100000000ull &&
+           p.servers < 0xFFFFFFFFull;
+}
+}  // namespace
+
+// per-customer words are indexed [customer][global thread]: sized for the larger of the two grids
+int mmc_blocks(int sm_count) { return sm_count * MF_BLOCKS_PER_SM; }
+int mmc_threads() { return MF_THREADS > MMC_THREADS ? MF_THREADS : MMC_THREADS; }
 
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
-                       uint64_t *customer_state, int sm_count, cudaStream_t stream) {
+                       uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
+                       int *launches) {
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mmc_kernel<<<mmc_blocks(sm_count), MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state);
+    if (mmc_fast_applies(prm, sh)) {
+        const size_t fsmem = mmc_fast_smem_bytes();
+        e = cudaFuncSetAttribute(mmc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e != cudaSuccess) return e;
+        const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
+        const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
+        mmc_fast_kernel<<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        mmc_kernel<<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, sh.retry_list, sh.retry_count,
+                                                           list_cursor);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    mmc_kernel<<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr);
+    ++*launches;
     return cudaGetLastError();
 }
 

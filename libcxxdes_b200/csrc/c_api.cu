@@ -87,6 +87,8 @@ struct cxxdes_b200_ensemble {
     size_t ring_bytes = 0;
     void *ahead_gring = nullptr;  // second ring level of the generate-ahead M/M/1 kernel
     size_t ahead_gring_bytes = 0;
+    uint32_t *mm1_state = nullptr;  // per-replication state between run_until / run_for pieces (M/M/1)
+    bool mm1_state_valid = false;   // written by the previous launch of this handle
     cxxdes_b200_accumulators *acc = nullptr;
     void *reduce_scratch = nullptr;
 
@@ -268,8 +270,15 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     switch (e->cfg.model) {
         case CXXDES_B200_MODEL_MM1:
             if (e->use_fused) {
+                // run_until / run_for continue where the previous piece stopped (environment.ipp:190-214)
+                // when the generate-ahead kernel runs the model; otherwise a piece replays from tick 0
+                const bool resumable = !(e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) && !e->mm1_plan.ah_direct_global;
+                if (resumable && !e->mm1_state && (until >= 0 || e->mm1_state_valid)) {
+                    CUDA_TRY(cudaMalloc(&e->mm1_state, mm1_ahead_state_bytes(e->cfg.n_replications)));
+                }
+                const int resume = resumable && e->mm1_state && e->mm1_state_valid;
                 CUDA_TRY(launch_mm1_fused(e->params.mm1, sh, e->cols, e->mm1_plan, e->ring, e->counters + 2,
-                                          e->ahead_gring, e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
+                                          e->ahead_gring, resumable ? e->mm1_state : nullptr, resume, e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
             } else {
                 CUDA_TRY(launch_mm1_engine(e->params.mm1, sh, e->cols, e->ring, e->engine_ring, e->engine_blocks,
                                            e->engine_threads, e->stream));
@@ -299,6 +308,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->launches += launches;
     e->timed = true;
     e->used = true;
+    e->mm1_state_valid = e->mm1_state != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -392,9 +402,10 @@ int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
     return launch(e, -1);
 }
 
-// State is not written back between launches yet: a later horizon replays each replication from
-// tick 0 up to the new target, which yields exactly the state the reference reaches by continuing
-// (every replication is a deterministic function of its seed).
+// M/M/1 on the generate-ahead kernel keeps each replication's state between calls (128 bytes per
+// replication) and continues from it, as environment::run_until does.  The other kernels replay a
+// replication from tick 0 up to the new target, which yields exactly the state the reference
+// reaches by continuing (every replication is a deterministic function of its seed).
 int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {
     if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
     if (t < 0) return fail(CXXDES_B200_ERR_INVALID, "run_until: t must be >= 0");
@@ -492,6 +503,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->horizon = -1;
     e->used = false;
     e->timed = false;
+    e->mm1_state_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -505,6 +517,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->log_table);
     cudaFree(e->ring);
     cudaFree(e->ahead_gring);
+    cudaFree(e->mm1_state);
     cudaFree(e->acc);
     cudaFree(e->reduce_scratch);
     cudaFree(e->program_blob);

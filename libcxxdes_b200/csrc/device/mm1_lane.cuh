@@ -286,8 +286,9 @@ struct lane {
     // (one slot beyond the packets holds the next arrival time: ring_cap < physical slots)
     template <bool SPILL>
     CXB_HD bool has_room(const constants &c) const {
-        if (SPILL) return (g - k + 2 <= c.ring_cap) & (g - i + 2 <= c.lead_cap);
-        return g - k + 2 <= c.ring_cap;  // the window bounds the lead as well (i >= k)
+        // (sums, not differences: while a resumed lane regenerates its ring g may be below i, even k - 1)
+        if (SPILL) return (g + 2 <= k + c.ring_cap) & (g + 2 <= i + c.lead_cap);
+        return g + 2 <= k + c.ring_cap;  // the window bounds the lead as well (i >= k)
     }
 
     // Packets g and g+1: inter-arrival draws g, g+1 of stream 1 and service draws g, g+1 of
@@ -295,7 +296,9 @@ struct lane {
     // The arithmetic runs for every lane and only the commit is conditional (`enable`), so there
     // is no branch here: the compiler may interleave these four long FP64 chains with the
     // integer bookkeeping of the event slots in the same basic block.
-    template <typename Ring, typename Table>
+    // ANCHOR_SECOND (only when a saved replication is resumed at an odd k): agk is the key of
+    // packet g + 1 instead of packet g.
+    template <bool ANCHOR_SECOND = false, typename Ring, typename Table>
     CXB_HD void generate_pair(const constants &c, Ring &ring, const Table *table, bool enable) {
         const philox_block bp = philox4x32_10_scheduled(g >> 1, 1u, ctr2, ctr3, c.keys);
         const philox_block bc = philox4x32_10_scheduled(g >> 1, 2u, ctr2, ctr3, c.keys);
@@ -311,20 +314,65 @@ struct lane {
         const bool out_of_range = new_budget >= TIME_LIMIT;
         const bool commit = enable & !out_of_range;
         status |= (enable & out_of_range) ? (uint32_t)CXXDES_B200_REP_TIME_RANGE : 0u;
-        const uint32_t a1k = agk + 4u * ia0;
+        const uint32_t a0k = ANCHOR_SECOND ? agk - 4u * ia0 : agk;
+        const uint32_t a1k = a0k + 4u * ia0;
         const uint32_t a2k = a1k + 4u * ia1;
         ring_entry e0, e1;
-        e0.ak = agk; e0.s4 = 4u * s0 + 2u;
+        e0.ak = a0k; e0.s4 = 4u * s0 + 2u;
         e1.ak = a1k; e1.s4 = 4u * s1 + 2u;
         // spilling ring: the two oldest window entries are about to be overwritten; if they are
         // still queued they move to global memory first
-        if (Ring::SPILL) ring.spill_if(commit & (g - k + 2 > (uint32_t)Ring::WINDOW), g);
+        if (Ring::SPILL) ring.spill_if(commit & (g + 2 > k + (uint32_t)Ring::WINDOW), g);
         ring.store_if(commit, g, e0);
         ring.store_if(commit, g + 1, e1);
         ring.store_a_if(commit, g + 2, a2k);   // A_{g+2}: the producer's token after it puts packet g+1
         budget = commit ? new_budget : budget;
         agk = commit ? a2k : agk;
         g += commit ? 2u : 0u;
+        glim = is_fast() ? g : 0u;
+    }
+
+    // ---- run_until / run_for in pieces: state of a replication between two launches ---------------
+    // (environment::run_until returns with the tokens still scheduled, environment.ipp:190-196;
+    // the next call continues from there.)  Everything but the ring is saved; the ring entries
+    // [k, g) are a pure function of (seed, replication, k, A_k), so the resumed lane draws them
+    // again -- 8 words fewer than saving a window that may have a second level in global memory.
+    static constexpr int STATE_WORDS = 32;   // one 128-byte record per replication
+    enum : uint32_t { PHASE_NEW = 0, PHASE_RUNNING = 1, PHASE_DONE = 2, PHASE_REPLAY = 3 };
+
+    template <typename Ring>
+    CXB_HD void save(uint32_t *w, Ring &ring, uint32_t phase) const {
+        w[0] = phase;
+        w[1] = k < g ? ring.load(k, g).ak : agk;   // 4 * A_k + 1
+        w[2] = budget; w[3] = i; w[4] = k; w[5] = kp; w[6] = kc;
+        w[7] = t0; w[8] = t1; w[9] = m0; w[10] = m1;
+        w[11] = main_pc; w[12] = cons_pc; w[13] = remaining; w[14] = waiting;
+        w[15] = now; w[16] = x_tick; w[17] = n_events; w[18] = max_queue; w[19] = status;
+        w[20] = (uint32_t)hash; w[21] = (uint32_t)(hash >> 32);
+        const uint64_t tl = double_as_bits(total_latency);
+        w[22] = (uint32_t)tl; w[23] = (uint32_t)(tl >> 32);
+    }
+
+    // Counterpart of save(); leaves g <= k with agk anchored at packet k, regenerate() refills.
+    CXB_HD void restore(const uint32_t *w, uint64_t global_replication) {
+        ctr2 = (uint32_t)global_replication;
+        ctr3 = (uint32_t)(global_replication >> 32);
+        agk = w[1]; budget = w[2]; i = w[3]; k = w[4]; kp = w[5]; kc = w[6];
+        t0 = w[7]; t1 = w[8]; m0 = w[9]; m1 = w[10];
+        main_pc = w[11]; cons_pc = w[12]; remaining = w[13]; waiting = w[14];
+        now = w[15]; x_tick = w[16]; n_events = w[17]; max_queue = w[18]; status = w[19] & ~(uint32_t)CXXDES_B200_REP_UNFINISHED;
+        hash = ((uint64_t)w[21] << 32) | w[20];
+        total_latency = bits_as_double(((uint64_t)w[23] << 32) | w[22]);
+        g = k & ~1u;
+        glim = 0;
+    }
+
+    // Draw the ring entries of a restored replication again, up to the packet the producer puts
+    // next (the invariant of the event loop: g > i while there are packets left).
+    template <bool SPILL, typename Ring, typename Table>
+    CXB_HD void regenerate(const constants &c, Ring &ring, const Table *table) {
+        if ((k & 1u) && wants_packets(c)) generate_pair<true>(c, ring, table, true);   // agk is A_k = A_{g+1}
+        while (status == 0 && g <= i && wants_packets(c) && has_room<SPILL>(c)) generate_pair(c, ring, table, true);
         glim = is_fast() ? g : 0u;
     }
 

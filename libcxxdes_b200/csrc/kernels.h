@@ -35,7 +35,8 @@ mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_
                               size_t smem_per_block_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep);
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             void *ahead_gring, cudaStream_t stream, int *launches, bool lockstep);
+                             void *ahead_gring, uint32_t *ahead_state, int resume, cudaStream_t stream, int *launches,
+                             bool lockstep);
 cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
 // ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
@@ -43,8 +44,9 @@ void plan_mm1_ahead(mm1_fused_plan &plan, const cxxdes_b200_mm1_params &prm, uin
                     int64_t tick_mult, int64_t ticks_per_unit);
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &plan);
+size_t mm1_ahead_state_bytes(uint64_t n_replications);   // run_until in pieces: 128 B per replication
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, void *gring, cudaStream_t stream);
+                             const mm1_fused_plan &plan, void *gring, uint32_t *state, int resume, cudaStream_t stream);
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);

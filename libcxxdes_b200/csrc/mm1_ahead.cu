@@ -96,10 +96,10 @@ struct lane_ring {
 
 }  // namespace
 
-template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL>
+template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL, bool STATE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint2 *gring,
-                 uint32_t gring_slots) {
+                 uint32_t gring_slots, uint32_t *state, int resume) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     stage_log_table(table, sh.log_table);
@@ -117,11 +117,29 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 
     for (;;) {
         if (!active && !exhausted) {
-            if (steal(sh, rep)) {
-                L.init(sh.first_replication + rep);
-                active = true;
-            } else {
-                exhausted = true;
+            // `state` (run_until / run_for in pieces): one 128-byte record per replication, written
+            // when a replication stops at the horizon and read back by the next launch (`resume`)
+            for (int tries = 0; tries < 8 && !active && !exhausted; ++tries) {
+                if (!steal(sh, rep)) {
+                    exhausted = true;
+                    break;
+                }
+                const uint64_t grep = sh.first_replication + rep;
+                const uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
+                const uint32_t phase = (STATE && resume) ? w[0] : (uint32_t)mm1::lane::PHASE_NEW;
+                if (phase == mm1::lane::PHASE_RUNNING) {
+                    L.restore(w, grep);
+                    L.template regenerate<SPILL>(c, ring, table);
+                    active = true;
+                } else if (phase == mm1::lane::PHASE_NEW) {
+                    L.init(grep);
+                    active = true;
+                } else if (phase == mm1::lane::PHASE_REPLAY) {
+                    // left the 32-bit representation in an earlier piece: the fallback kernel
+                    // replays it from tick 0 to the new horizon
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                }   // PHASE_DONE: finished in an earlier piece, its row is final
             }
         }
         if (!__any_sync(0xFFFFFFFFu, active)) break;
@@ -151,10 +169,12 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         if (active && L.finished(c)) {
             active = false;
             const uint32_t status = L.status;
+            uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
             if (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE)) {
                 // hand the replication to the fallback kernel; its row is written there
                 unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
                 sh.retry_list[at] = (uint32_t)rep;
+                if (STATE) w[0] = mm1::lane::PHASE_REPLAY;
             } else {
                 rep_out o;
                 int64_t end = (int64_t)L.now;
@@ -171,6 +191,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 o.i64[0] = (int64_t)L.k;
                 o.i64[1] = (int64_t)L.max_queue;
                 store_result(out, rep, o);
+                if (STATE) L.save(w, ring, L.next_time() != mm1::EMPTY ? mm1::lane::PHASE_RUNNING : mm1::lane::PHASE_DONE);
             }
             L.idle();
         }
@@ -243,6 +264,8 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
                          !mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit);
 }
 
+size_t mm1_ahead_state_bytes(uint64_t n_replications) { return (size_t)n_replications * mm1::lane::STATE_WORDS * sizeof(uint32_t); }
+
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &p) {
     return p.ah_spill ? (size_t)p.ah_gring_slots * p.ah_blocks * p.ah_threads * sizeof(uint2) : 0;
 }
@@ -250,7 +273,10 @@ size_t mm1_ahead_gring_bytes(const mm1_fused_plan &p) {
 namespace {
 template <typename G, int MODE, bool SPILL>
 cudaError_t configure_one() {
-    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL>,
+    cudaError_t e = cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
 }
 template <typename G, bool SPILL>
@@ -263,18 +289,25 @@ cudaError_t configure_geometry() {
 }
 template <typename G, int MODE, bool SPILL>
 void launch_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                const mm1_fused_plan &plan, uint2 *gring, cudaStream_t stream) {
-    mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL>
-        <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots);
+                const mm1_fused_plan &plan, uint2 *gring, uint32_t *state, int resume, cudaStream_t stream) {
+    // (the state-keeping variant is a separate instantiation: its extra live values cost the plain
+    // run() path 4 % when they are only a run-time switch)
+    if (state)
+        mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>
+            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots, state, resume);
+    else
+        mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>
+            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots, nullptr, 0);
 }
 template <typename G, bool SPILL>
 void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh,
-                     const device_columns &out, const mm1_fused_plan &plan, uint2 *gring, cudaStream_t stream) {
+                     const device_columns &out, const mm1_fused_plan &plan, uint2 *gring, uint32_t *state, int resume,
+                     cudaStream_t stream) {
     switch (mode) {
-        case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, gring, stream); break;
-        case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, gring, stream); break;
-        case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, gring, stream); break;
-        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, gring, stream); break;
+        case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
+        case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
+        case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
+        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
     }
 }
 }  // namespace
@@ -285,7 +318,7 @@ cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
 }
 
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, void *gring, cudaStream_t stream) {
+                             const mm1_fused_plan &plan, void *gring, uint32_t *state, int resume, cudaStream_t stream) {
     mm1::constants c;
     c.lambda = make_divisor(prm.lambda);  // IEEE 1/d on the host: same bits as on the device
     c.mu = make_divisor(prm.mu);
@@ -300,11 +333,11 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
     uint2 *g = (uint2 *)gring;
     if (plan.ah_geometry == 1) {
-        if (plan.ah_spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, g, stream);
-        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, g, stream);
+        if (plan.ah_spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, g, state, resume, stream);
+        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, g, state, resume, stream);
     } else {
-        if (plan.ah_spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, g, stream);
-        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, g, stream);
+        if (plan.ah_spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, g, state, resume, stream);
+        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, g, state, resume, stream);
     }
     return cudaGetLastError();
 }

@@ -414,7 +414,8 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan) {
 // loaded queues skip the first pass.
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
-                             void *ahead_gring, cudaStream_t stream, int *launches, bool lockstep) {
+                             void *ahead_gring, uint32_t *ahead_state, int resume, cudaStream_t stream, int *launches,
+                             bool lockstep) {
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     mm1_rates rates;
     rates.lambda = make_divisor(prm.lambda);
@@ -429,7 +430,7 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                                                                         nullptr, nullptr, nullptr);
             e = cudaGetLastError();
         } else {
-            e = launch_mm1_ahead(prm, sh, out, plan, ahead_gring, stream);
+            e = launch_mm1_ahead(prm, sh, out, plan, ahead_gring, ahead_state, resume, stream);
         }
         ++*launches;
         if (e != cudaSuccess) return e;

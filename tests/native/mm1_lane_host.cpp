@@ -61,7 +61,7 @@ void run_one(const mm1::constants &c, Ring &ring, mm1::lane &L, int event_slots,
 extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t ticks_per_unit, int64_t tick_mult,
                                  double sec_per_unit, uint64_t seed, uint64_t first, uint64_t n_reps,
                                  int64_t until, uint32_t ring_cap, uint32_t global_slots, int event_slots,
-                                 int general_mode, const cxxdes_b200_columns *out, uint64_t *iterations) {
+                                 int general_mode, int64_t piece, const cxxdes_b200_columns *out, uint64_t *iterations) {
     mm1::constants c;
     c.lambda = make_divisor(prm->lambda);
     c.mu = make_divisor(prm->mu);
@@ -78,15 +78,35 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
     // MODE 3 (generic step) = run_until check + tick_mult multiply compiled in: same results as the
     // specialised modes (a multiply by 1.0 and a compare with EMPTY change nothing)
     const int mode = general_mode ? 3 : (c.until != mm1::EMPTY ? 1 : 0) | (tick_mult != 1 ? 2 : 0);
+    // `piece` > 0: run_for(piece) again and again up to `until` (or to exhaustion), saving the lane to
+    // a 128-byte record at every horizon and restoring + regenerating it, as the kernel does between
+    // two launches.  The ring object is new for every piece: nothing may survive in it.
+    auto horizon_of = [](int64_t h) { return (h < 0 || h >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)h; };
     for (uint64_t r = 0; r < n_reps; ++r) {
         mm1::lane L;
         L.init(first + r);
-        if (global_slots) {
-            host_ring<true> ring(global_slots);
-            run_one(c, ring, L, event_slots, mode, iters);
-        } else {
-            host_ring<false> ring(0);
-            run_one(c, ring, L, event_slots, mode, iters);
+        uint32_t record[mm1::lane::STATE_WORDS] = {0};
+        int64_t h = piece > 0 ? piece : until;
+        for (;;) {
+            if (piece > 0 && until >= 0 && h > until) h = until;
+            c.until = horizon_of(h);
+            const int mode_h = general_mode ? 3 : (c.until != mm1::EMPTY ? 1 : 0) | (tick_mult != 1 ? 2 : 0);
+            bool unfinished;
+            if (global_slots) {
+                host_ring<true> ring(global_slots);
+                if (record[0] == mm1::lane::PHASE_RUNNING) { L.restore(record, first + r); L.regenerate<true>(c, ring, LOG_TABLE_HOST); }
+                run_one(c, ring, L, event_slots, mode_h, iters);
+                unfinished = L.status == 0 && L.next_time() != mm1::EMPTY;
+                L.save(record, ring, unfinished ? mm1::lane::PHASE_RUNNING : mm1::lane::PHASE_DONE);
+            } else {
+                host_ring<false> ring(0);
+                if (record[0] == mm1::lane::PHASE_RUNNING) { L.restore(record, first + r); L.regenerate<false>(c, ring, LOG_TABLE_HOST); }
+                run_one(c, ring, L, event_slots, mode_h, iters);
+                unfinished = L.status == 0 && L.next_time() != mm1::EMPTY;
+                L.save(record, ring, unfinished ? mm1::lane::PHASE_RUNNING : mm1::lane::PHASE_DONE);
+            }
+            if (piece <= 0 || !unfinished || (until >= 0 && h >= until)) break;
+            h += piece;
         }
         uint32_t status = L.status;
         int64_t end = (int64_t)L.now;

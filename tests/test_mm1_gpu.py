@@ -111,6 +111,47 @@ def test_run_for_accumulates(port):
     golden_util.assert_columns_equal(b, want, what="run_for x2")
 
 
+@pytest.mark.parametrize("lam,n_packets,piece,n_pieces,kw", [
+    (5.0, 800, 3000, 12, {}),                       # steady state cut 12 times
+    (5.0, 800, 1, 40, {}),                          # horizons inside the start-up events
+    (9.0, 1500, 20000, 6, {}),                      # spilling ring: entries beyond the window are drawn again
+    (8.0, 1200, 15000, 8, {"queue_capacity": 4}),   # replications handed to the fallback kernel stay there
+    (5.0, 800, 3000, 5, {"flags": abi.FLAG_MM1_LOCKSTEP})])   # kernels without saved state replay from tick 0
+def test_run_for_in_pieces_matches_oracle(port, lam, n_packets, piece, n_pieces, kw):
+    """run_for(piece) x n (environment.ipp:209-214, tests/process.test.cpp:127-147 pattern): after every
+    piece the columns equal the oracle's run_until(k * piece); then run() finishes the replications."""
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    n_reps = 512
+    ens = L.Ensemble(p, n_reps, seed=31, **kw)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    for k in range(1, n_pieces + 1):
+        ens.run_for(piece)
+        if k in (1, 2, n_pieces // 2, n_pieces):
+            got = ens.fetch(strict=False)
+            want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 31, 0, n_reps, threads=oracles.os.cpu_count(),
+                            until=k * piece)
+            golden_util.assert_columns_equal(got, want, what=f"after piece {k}")
+    ens.run()
+    got = ens.fetch()
+    ens.close()
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 31, 0, n_reps, threads=oracles.os.cpu_count())
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="run() after the pieces")
+
+
+def test_reset_forgets_saved_state(port):
+    p = abi.MM1Params(5.0, 10.0, 600)
+    ens = L.Ensemble(p, 128, seed=8)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run_for(4000)
+    ens.reset()
+    ens.run_for(1000)
+    got = ens.fetch(strict=False)
+    ens.close()
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 8, 0, 128, threads=4, until=1000)
+    golden_util.assert_columns_equal(got, want, what="after reset")
+
+
 def test_other_clocks(port):
     p = abi.MM1Params(5.0, 10.0, 300)
     for unit, prec in [((1, L.MILLISECONDS), (1, L.MICROSECONDS)), ((2, L.SECONDS), (5, L.MILLISECONDS))]:

@@ -29,18 +29,18 @@ def lane_lib():
     lib = C.CDLL(str(OUT))
     lib.mm1_lane_host_run.restype = C.c_int
     lib.mm1_lane_host_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_uint64,
-                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int64,
                                       C.POINTER(abi.Columns), C.POINTER(C.c_uint64)]
     return lib
 
 
 def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=31, global_slots=0, event_slots=4,
-              clock=(1000, 1, 1e-3), general_mode=0):
+              clock=(1000, 1, 1e-3), general_mode=0, piece=0):
     cols = abi.HostColumns(n_reps)
     st = cols.as_struct()
     iters = C.c_uint64()
     rc = lib.mm1_lane_host_run(C.addressof(p), clock[0], clock[1], clock[2], seed, first, n_reps, until,
-                               ring_cap, global_slots, event_slots, general_mode, C.byref(st), C.byref(iters))
+                               ring_cap, global_slots, event_slots, general_mode, piece, C.byref(st), C.byref(iters))
     assert rc == 0
     return cols, iters.value
 
@@ -125,6 +125,18 @@ def test_spilling_ring_matches_oracle(lane_lib, port, lam, n_packets, slots):
     assert (got.status[~ok] & abi.REP_QUEUE_OVERFLOW).all()
     if slots >= 1024:
         assert ok.all()
+
+
+@pytest.mark.parametrize("lam,n_packets,piece,until,slots", [
+    (5.0, 800, 7000, -1, 0), (5.0, 800, 100, 30000, 0), (5.0, 800, 1, 300, 0), (0.5, 300, 2500, -1, 0),
+    (9.0, 1500, 9000, -1, 1024), (9.5, 1000, 333, 90000, 256), (5.0, 9, 50, -1, 0), (5.0, 2, 1, -1, 0)])
+def test_lane_run_in_pieces(lane_lib, port, lam, n_packets, piece, until, slots):
+    """run_for(piece) repeatedly == one run (environment.ipp:190-214): the lane is saved at every
+    horizon, restored into an empty ring and its ring entries are drawn again."""
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, _ = run_lanes(lane_lib, p, 96, seed=77, until=until, piece=piece, global_slots=slots)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 77, 0, 96, threads=4, until=until)
+    assert masked_equal(got, want, f"pieces of {piece}").all()
 
 
 def test_compile_time_modes_agree(lane_lib):

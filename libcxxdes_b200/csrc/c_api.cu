@@ -93,6 +93,7 @@ struct cxxdes_b200_ensemble {
     void *reduce_scratch = nullptr;
 
     unsigned char *program_blob = nullptr;  // device copy of a process program
+    uint32_t program_blob_bytes = 0;
     device_program dprog{};
 
     bool use_fused = false;
@@ -175,6 +176,7 @@ int upload_program(cxxdes_b200_ensemble *e) {
     if (ce == cudaSuccess) ce = cudaMemcpy(e->program_blob, host, total, cudaMemcpyHostToDevice);
     delete[] host;
     if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program upload: %s", cudaGetErrorString(ce));
+    e->program_blob_bytes = (uint32_t)total;
     device_program &d = e->dprog;
     d.ops = (const cxxdes_b200_op *)(e->program_blob + o_ops);
     d.procs = (const cxxdes_b200_process *)(e->program_blob + o_procs);
@@ -298,8 +300,8 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             launches = 1;
             break;
         case CXXDES_B200_MODEL_PROGRAM:
-            CUDA_TRY(launch_program(e->dprog, sh, e->cols, e->sm_count, e->stream));
-            launches = 1;
+            CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
+                                    &launches));
             break;
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);

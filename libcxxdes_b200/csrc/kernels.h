@@ -79,8 +79,9 @@ struct device_program {  // cxxdes_b200_program with device pointers; rates as {
     uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
 };
 const char *program_check(const cxxdes_b200_program &p);  // nullptr when the interpreter supports it
-cudaError_t launch_program(const device_program &prg, const shard &sh, const device_columns &out, int sm_count,
-                           cudaStream_t stream);
+// blob_bytes: size of the contiguous device copy of the program that starts at prg.ops
+cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
+                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches);
 
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);

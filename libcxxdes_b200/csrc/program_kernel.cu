@@ -281,7 +281,7 @@ struct interp {
                     }
                     self.reg = q.item[q.head];
                     q.head = (q.head + 1) % PRG_QUEUE_CAP;
-                    --q.count;
+                    if (--q.count == 0) q.head = 0;   // an empty ring restarts at slot 0: short queues stay in one cache line
                     wake(q_wait[op.a]);
                     ++self.pc;
                     break;
@@ -377,19 +377,50 @@ struct interp {
 
 }  // namespace
 
+// heap_cap: tokens a replication may have scheduled at once.  The first pass sizes it from the
+// program (2 per process + 8), which leaves shared memory for up to 1024 resident threads per SM --
+// the interpreter waits on its per-thread state in local memory most of the time, so resident warps
+// are what buys throughput; a replication that overflows the small heap is redone by a second pass
+// with PRG_HEAP entries (list != nullptr: only the replications on the retry list).
+// The program text (ops, process table, rates, limits) is staged into shared memory when it fits.
 __global__ void __launch_bounds__(PRG_THREADS)
-program_kernel(device_program prg, shard sh, device_columns out) {
+program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap, uint32_t staged_bytes,
+               const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
-    stage_log_table(table, sh.log_table);
-    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, PRG_HEAP);
-    lane_array<uint32_t> htag = carve<uint32_t>(cursor, PRG_HEAP);
+    device_program prg = prg_in;
+    if (staged_bytes) {
+        // one contiguous blob on the device (c_api.cu upload_program): ops first, 16-byte aligned pieces
+        const uint4 *src = (const uint4 *)prg_in.ops;
+        uint4 *dst = (uint4 *)cursor;
+        for (uint32_t k = threadIdx.x; k < staged_bytes / 16; k += blockDim.x) dst[k] = src[k];
+        const unsigned char *base = (const unsigned char *)prg_in.ops;
+        auto moved = [&](const void *ptr) { return (const void *)(cursor + ((const unsigned char *)ptr - base)); };
+        prg.ops = (const cxxdes_b200_op *)moved(prg_in.ops);
+        prg.procs = (const cxxdes_b200_process *)moved(prg_in.procs);
+        prg.roots = (const uint32_t *)moved(prg_in.roots);
+        prg.queue_max = (const uint64_t *)moved(prg_in.queue_max);
+        prg.sem_init = (const uint64_t *)moved(prg_in.sem_init);
+        prg.sem_max = (const uint64_t *)moved(prg_in.sem_max);
+        prg.rates = (const divisor *)moved(prg_in.rates);
+        cursor += staged_bytes;
+    }
+    stage_log_table(table, sh.log_table);   // ends with __syncthreads(): the staged program is visible too
+    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
+    lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
 
     uint64_t rep;
-    while (steal(sh, rep)) {
+    for (;;) {
+        if (list) {
+            const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+            if (idx >= *list_count) break;
+            rep = list[idx];
+        } else if (!steal(sh, rep)) {
+            break;
+        }
         interp it(prg, sh, table);
-        it.env.init(hkey, htag, PRG_HEAP);
+        it.env.init(hkey, htag, heap_cap);
         it.addr.seed = sh.seed;
         it.addr.replication = sh.first_replication + rep;
         it.next_serial = 0;
@@ -436,6 +467,11 @@ program_kernel(device_program prg, shard sh, device_columns out) {
         if (sh.run_until >= 0) {
             if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
             env.now = env.now > sh.run_until ? env.now : sh.run_until;
+        }
+        if (!list && heap_cap < PRG_HEAP && (env.status & CXXDES_B200_REP_HEAP_OVERFLOW)) {
+            const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);   // redo with the full-size heap
+            sh.retry_list[at] = (uint32_t)rep;
+            continue;
         }
         rep_out o;
         o.end_time = env.now;
@@ -509,17 +545,33 @@ const char *program_check(const cxxdes_b200_program &p) {
     return nullptr;
 }
 
-size_t program_smem_bytes() {
-    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + (size_t)PRG_THREADS * PRG_HEAP * 12;
+namespace {
+size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + staged_bytes + (size_t)PRG_THREADS * heap_cap * 12;
 }
+}  // namespace
 
-cudaError_t launch_program(const device_program &prg, const shard &sh, const device_columns &out, int sm_count,
-                           cudaStream_t stream) {
-    const size_t smem = program_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    program_kernel<<<sm_count * 2, PRG_THREADS, smem, stream>>>(prg, sh, out);
-    return cudaGetLastError();
+cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
+                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches) {
+    const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
+    int small = 2 * (int)prg.n_procs + 8;
+    if (small > PRG_HEAP) small = PRG_HEAP;
+    auto go = [&](int heap_cap, bool retry) -> cudaError_t {
+        const size_t smem = program_smem_bytes(heap_cap, staged);
+        cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        program_kernel<<<sm_count * per_sm, PRG_THREADS, smem, stream>>>(
+            prg, sh, out, heap_cap, staged, retry ? sh.retry_list : nullptr, retry ? sh.retry_count : nullptr,
+            retry ? list_cursor : nullptr);
+        ++*launches;
+        return cudaGetLastError();
+    };
+    cudaError_t e = go(small, false);
+    if (e != cudaSuccess || small == PRG_HEAP) return e;
+    return go(PRG_HEAP, true);   // exits at once when nothing overflowed
 }
 
 }  // namespace cxb

@@ -118,6 +118,27 @@ def test_gpu_mm1_program_matches_oracle_and_fused_kernel(port, lam, n):
     assert np.array_equal(fused.trace_hash, got.trace_hash)
 
 
+def _wide_program():
+    """One process, all_of over 24 timeouts inside a loop: needs 24 heap entries, more than the
+    first-pass heap of 2 * n_procs + 8 = 10."""
+    prog = L.Program()
+    main = prog.process(0, root=True)
+    with prog.body(main) as b:
+        with b.loop(5):
+            b.all_of(*[L.Delay(3 + (7 * j) % 11) for j in range(24)])
+            b.mark(1, 0)
+    return prog
+
+
+@pytest.mark.gpu
+def test_gpu_small_heap_overflow_takes_the_retry_pass(port):
+    prog = _wide_program()
+    got = _run_gpu(prog, 300)
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of((1, 0), (1, 0)), 1, 0, 300, threads=4)
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="wide all_of")
+
+
 @pytest.mark.gpu
 def test_gpu_rejects_bad_programs(built):
     prog = L.Program()

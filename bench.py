@@ -140,7 +140,8 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+            # no --id: one process watches every GPU of the node (per-GPU medians explain N > 1 runs)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -161,20 +162,28 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
+        per_gpu = {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
+                gpu = int(f[0])
+                per_gpu.setdefault(gpu, []).append(float(f[1]))
+                if gpu != self.index:
+                    continue
                 sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+               "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if len(per_gpu) > 1:
+            out["per_gpu_sm_mhz"] = [float(np.median(per_gpu[g])) for g in sorted(per_gpu)]
+        return out
 
 
 def measured_peaks():
@@ -249,6 +258,9 @@ def run_b200(a):
     elapsed_ms = ev0.elapsed_time(ev1)
     last_kernel_ms = ens.last_run_ms()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks and world == 1:
+        clocks.pop("per_gpu_sm_mhz", None)
+    own_elapsed_ms = elapsed_ms
     launches = ens.launch_count() - launches_before
 
     # events processed by this rank in one step (every step simulates the same replications)
@@ -332,6 +344,16 @@ def run_b200(a):
     e2e = {"value": e2e_events / e2e_dt, "unit": "events/s", "h2d_bytes_per_step": params_bytes * world,
            "d2h_bytes_per_step": host.nbytes() * world}
 
+    # per-rank view (which GPU, if any, holds the others back at N > 1)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([kernel_avg_ms, own_elapsed_ms / a.steps], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [round(float(t[0]), 3) for t in allr], "step_ms": [round(float(t[1]), 3) for t in allr]}
+        if clocks and clocks.get("per_gpu_sm_mhz"):
+            per_rank["sm_mhz"] = clocks.pop("per_gpu_sm_mhz")
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a.packets, a.cpu_seconds)
@@ -351,6 +373,8 @@ def run_b200(a):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -80,7 +80,7 @@ struct cxxdes_b200_ensemble {
     // device memory
     unsigned char *col_block = nullptr;  // all result columns, one allocation
     device_columns cols{};
-    unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor
+    unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor, [3] list A count, [4] list A cursor
     uint32_t *retry_list = nullptr;
     log_entry *log_table = nullptr;
     int64_t *ring = nullptr;
@@ -124,8 +124,8 @@ int allocate(cxxdes_b200_ensemble *e) {
     for (int k = 0; k < CXXDES_B200_N_F64; ++k) { e->cols.f64[k] = (double *)p; p += col8; }
     for (int k = 0; k < CXXDES_B200_N_I64; ++k) { e->cols.i64[k] = (int64_t *)p; p += col8; }
     e->cols.status = (uint32_t *)p;
-    CUDA_TRY(cudaMalloc(&e->counters, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&e->retry_list, sizeof(uint32_t) * (n ? n : 1)));
+    CUDA_TRY(cudaMalloc(&e->counters, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&e->retry_list, 2 * sizeof(uint32_t) * (n ? n : 1)));  // two lists (models_common.cuh)
     CUDA_TRY(cudaMalloc(&e->log_table, sizeof(LOG_TABLE_HOST)));
     CUDA_TRY(cudaMemcpyAsync(e->log_table, LOG_TABLE_HOST, sizeof(LOG_TABLE_HOST), cudaMemcpyHostToDevice,
                              e->stream));
@@ -256,7 +256,7 @@ int plan(cxxdes_b200_ensemble *e) {
 int launch(cxxdes_b200_ensemble *e, int64_t until) {
     int rc = set_device(e);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(e->counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->counters, 0, 8 * sizeof(unsigned long long), e->stream));
     shard sh{};
     sh.seed = e->cfg.seed;
     sh.first_replication = e->cfg.first_replication;
@@ -266,6 +266,9 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     sh.work_counter = e->counters + 0;
     sh.retry_count = e->counters + 1;
     sh.retry_list = e->retry_list;
+    sh.retry_a_count = e->counters + 3;
+    sh.retry_a_cursor = e->counters + 4;
+    sh.retry_a_list = e->retry_list + e->cfg.n_replications;
     sh.log_table = e->log_table;
     CUDA_TRY(cudaEventRecord(e->ev_begin, e->stream));
     int launches = 0;

@@ -208,8 +208,9 @@ struct constants {
     double sec_per_unit;     // clock.seconds_per_tick_unit
     double tick_mult;        // (double)clock.tick_mult, < 2^23 so tick * tick_mult is exact in a double
     uint32_t n_packets;      // 2 <= n < 2^30
-    uint32_t ring_cap;       // packets (queued + generated ahead) the ring may hold, >= 2
-    uint32_t lead_cap;       // packets that may be generated ahead of the producer (spilling ring: the window)
+    uint32_t ring_cap;       // packets (queued + generated ahead) the shared-memory window may hold, >= 2
+    uint32_t spill_cap;      // ... and the ring with its global-memory level (spilling path)
+    uint32_t lead_cap;       // spilling path: packets that may be generated ahead of the producer
     uint32_t until;          // run_until horizon in ticks, EMPTY when there is none
 };
 
@@ -287,7 +288,7 @@ struct lane {
     template <bool SPILL>
     CXB_HD bool has_room(const constants &c) const {
         // (sums, not differences: while a resumed lane regenerates its ring g may be below i, even k - 1)
-        if (SPILL) return (g + 2 <= k + c.ring_cap) & (g + 2 <= i + c.lead_cap);
+        if (SPILL) return (g + 2 <= k + c.spill_cap) & (g + 2 <= i + c.lead_cap);
         return g + 2 <= k + c.ring_cap;  // the window bounds the lead as well (i >= k)
     }
 

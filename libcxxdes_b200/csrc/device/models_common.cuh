@@ -25,6 +25,10 @@ struct shard {
     const log_entry *log_table;  // global copy of the log table
     unsigned long long *retry_count;   // number of entries in retry_list
     uint32_t *retry_list;        // local replication ids that must be re-run by the fallback kernel
+    // M/M/1 runs in up to three passes: list A (queue outgrew the shared-memory window -> second pass
+    // of the fast kernel with the two-level ring), then retry_list above (-> 64-bit fallback kernel)
+    unsigned long long *retry_a_count, *retry_a_cursor;
+    uint32_t *retry_a_list;
 };
 
 struct rep_out {

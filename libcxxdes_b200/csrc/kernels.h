@@ -27,7 +27,8 @@ struct mm1_fused_plan {
     size_t ah_smem_bytes;
     uint32_t ah_ring_cap;       // packets (queued + generated ahead) a replication's ring may hold
     uint32_t ah_lead_cap;       // packets that may be generated ahead of the producer
-    bool ah_spill;              // ring has a second level in global memory (heavily loaded queues)
+    bool ah_spill;              // the FIRST pass already uses the two-level ring (heavily loaded queues)
+    uint32_t ah_spill_cap;      // packets the two-level ring may hold
     uint32_t ah_gring_slots;    // its slots per replication (power of two)
     bool ah_direct_global;
 };
@@ -46,7 +47,9 @@ cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &plan);
 size_t mm1_ahead_state_bytes(uint64_t n_replications);   // run_until in pieces: 128 B per replication
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, void *gring, uint32_t *state, int resume, cudaStream_t stream);
+                             const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
+                             const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
+                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream);
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);

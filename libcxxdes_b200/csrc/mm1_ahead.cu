@@ -96,10 +96,20 @@ struct lane_ring {
 
 }  // namespace
 
+// One round of the spilling path (event slots + generation) as a function of its own, for the
+// adaptive kernel.
+// SPILL: the ring has its second level in global memory (heavily loaded queues, and the second pass).
+// Passes of one run (launch_mm1_fused): this kernel over the whole shard; this kernel with SPILL
+// over the replications whose queue outgrew the window (`list`: about one in two million at
+// rho = 0.5, but a lone replication on the 64-bit fallback kernel takes 13 ms, on this one 2 ms);
+// the fallback kernel over what is left (clock beyond 2^30 ticks, queue beyond both levels).
+// A replication this kernel cannot finish goes to `fail_list`.
 template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL, bool STATE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint2 *gring,
-                 uint32_t gring_slots, uint32_t *state, int resume) {
+                 uint32_t gring_slots, uint32_t *state, int resume, const uint32_t *list,
+                 const unsigned long long *list_count, unsigned long long *list_cursor, uint32_t *fail_list,
+                 unsigned long long *fail_count) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     stage_log_table(table, sh.log_table);
@@ -120,13 +130,22 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
             // `state` (run_until / run_for in pieces): one 128-byte record per replication, written
             // when a replication stops at the horizon and read back by the next launch (`resume`)
             for (int tries = 0; tries < 8 && !active && !exhausted; ++tries) {
-                if (!steal(sh, rep)) {
+                bool got;
+                if (list) {
+                    const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+                    got = idx < *list_count;
+                    if (got) rep = list[idx];
+                } else {
+                    got = steal(sh, rep);
+                }
+                if (!got) {
                     exhausted = true;
                     break;
                 }
                 const uint64_t grep = sh.first_replication + rep;
                 const uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
-                const uint32_t phase = (STATE && resume) ? w[0] : (uint32_t)mm1::lane::PHASE_NEW;
+                // (a second-pass replication starts over: phase REPLAY in its record, or no record at all)
+                const uint32_t phase = (STATE && resume && !list) ? w[0] : (uint32_t)mm1::lane::PHASE_NEW;
                 if (phase == mm1::lane::PHASE_RUNNING) {
                     L.restore(w, grep);
                     L.template regenerate<SPILL>(c, ring, table);
@@ -137,8 +156,8 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 } else if (phase == mm1::lane::PHASE_REPLAY) {
                     // left the 32-bit representation in an earlier piece: the fallback kernel
                     // replays it from tick 0 to the new horizon
-                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
-                    sh.retry_list[at] = (uint32_t)rep;
+                    const unsigned long long at = atomicAdd(fail_count, 1ULL);
+                    fail_list[at] = (uint32_t)rep;
                 }   // PHASE_DONE: finished in an earlier piece, its row is final
             }
         }
@@ -171,9 +190,9 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
             const uint32_t status = L.status;
             uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
             if (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE)) {
-                // hand the replication to the fallback kernel; its row is written there
-                unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
-                sh.retry_list[at] = (uint32_t)rep;
+                // hand the replication to the next pass; its row is written there
+                unsigned long long at = atomicAdd(fail_count, 1ULL);
+                fail_list[at] = (uint32_t)rep;
                 if (STATE) w[0] = mm1::lane::PHASE_REPLAY;
             } else {
                 rep_out o;
@@ -233,15 +252,20 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
     }
     const uint32_t window = p.ah_ring_slots - 1;  // one slot holds the arrival key after the last packet
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the window also holds the packets
-    // generated ahead (2 to 4).  If more than ~0.1% of the replications are expected to outgrow it,
-    // the ring gets its second level in global memory, sized so that overflowing THAT has
+    // generated ahead (2 to 4).  When more than ~0.1% of the replications are expected to outgrow
+    // the window, the first pass already runs with the spilling ring (ah_spill); otherwise it runs
+    // on the window alone and the few replications that outgrow it are redone by a second pass
+    // with the spilling ring.  The global-memory level is sized so that overflowing it has
     // probability < 1e-12 per arrival (what still overflows is redone by the fallback kernel).
     const double rho = prm.lambda / prm.mu;
     const double q = (double)window - 3.0;
     const double p_over = rho >= 1.0 ? 1.0 : pow(rho, q) * (double)prm.n_packets;
     p.ah_spill = !queue_capacity && !(p_over < 1e-3);
-    p.ah_gring_slots = 0;
-    if (p.ah_spill) {
+    uint32_t cap = queue_capacity ? queue_capacity : window;
+    if (cap > window) cap = window;
+    if (cap < 2) cap = 2;
+    p.ah_ring_cap = cap;
+    {
         double need = rho < 1.0 ? ceil(log(1e-12 / (double)prm.n_packets) / log(rho)) + 64.0 : (double)prm.n_packets + 64.0;
         if (need > (double)prm.n_packets + 64.0) need = (double)prm.n_packets + 64.0;
         const uint64_t threads = (uint64_t)p.ah_blocks * p.ah_threads;
@@ -249,14 +273,8 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
         uint32_t slots = 64;
         while (slots < need && slots * 2ULL <= budget) slots *= 2;
         p.ah_gring_slots = slots;
-        p.ah_ring_cap = slots;
+        p.ah_spill_cap = slots;
         p.ah_lead_cap = window - 1;
-    } else {
-        uint32_t cap = queue_capacity ? queue_capacity : window;
-        if (cap > window) cap = window;
-        if (cap < 2) cap = 2;
-        p.ah_ring_cap = cap;
-        p.ah_lead_cap = cap;
     }
     // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds())
     // ... and every single delay must fit the 32-bit tick representation
@@ -267,10 +285,21 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
 size_t mm1_ahead_state_bytes(uint64_t n_replications) { return (size_t)n_replications * mm1::lane::STATE_WORDS * sizeof(uint32_t); }
 
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &p) {
-    return p.ah_spill ? (size_t)p.ah_gring_slots * p.ah_blocks * p.ah_threads * sizeof(uint2) : 0;
+    return (size_t)p.ah_gring_slots * p.ah_blocks * p.ah_threads * sizeof(uint2);
 }
 
 namespace {
+struct pass_args {
+    uint2 *gring;
+    uint32_t *state;
+    int resume;
+    const uint32_t *list;
+    const unsigned long long *list_count;
+    unsigned long long *list_cursor;
+    uint32_t *fail_list;
+    unsigned long long *fail_count;
+};
+
 template <typename G, int MODE, bool SPILL>
 cudaError_t configure_one() {
     cudaError_t e = cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>,
@@ -279,46 +308,55 @@ cudaError_t configure_one() {
     return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
 }
-template <typename G, bool SPILL>
+template <typename G>
 cudaError_t configure_geometry() {
-    cudaError_t e = configure_one<G, 0, SPILL>();
-    if (e == cudaSuccess) e = configure_one<G, 1, SPILL>();
-    if (e == cudaSuccess) e = configure_one<G, 2, SPILL>();
-    if (e == cudaSuccess) e = configure_one<G, 3, SPILL>();
+    cudaError_t e = configure_one<G, 0, false>();
+    if (e == cudaSuccess) e = configure_one<G, 1, false>();
+    if (e == cudaSuccess) e = configure_one<G, 2, false>();
+    if (e == cudaSuccess) e = configure_one<G, 3, false>();
+    if (e == cudaSuccess) e = configure_one<G, 0, true>();
+    if (e == cudaSuccess) e = configure_one<G, 1, true>();
+    if (e == cudaSuccess) e = configure_one<G, 2, true>();
+    if (e == cudaSuccess) e = configure_one<G, 3, true>();
     return e;
 }
 template <typename G, int MODE, bool SPILL>
 void launch_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                const mm1_fused_plan &plan, uint2 *gring, uint32_t *state, int resume, cudaStream_t stream) {
+                const mm1_fused_plan &plan, const pass_args &a, cudaStream_t stream) {
     // (the state-keeping variant is a separate instantiation: its extra live values cost the plain
     // run() path 4 % when they are only a run-time switch)
-    if (state)
+    if (a.state)
         mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>
-            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots, state, resume);
+            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, a.state, a.resume,
+                                                              a.list, a.list_count, a.list_cursor, a.fail_list, a.fail_count);
     else
         mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>
-            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, gring, plan.ah_gring_slots, nullptr, 0);
+            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
+                                                              a.list_count, a.list_cursor, a.fail_list, a.fail_count);
 }
 template <typename G, bool SPILL>
 void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh,
-                     const device_columns &out, const mm1_fused_plan &plan, uint2 *gring, uint32_t *state, int resume,
-                     cudaStream_t stream) {
+                     const device_columns &out, const mm1_fused_plan &plan, const pass_args &a, cudaStream_t stream) {
     switch (mode) {
-        case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
-        case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
-        case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
-        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, gring, state, resume, stream); break;
+        case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, a, stream); break;
     }
 }
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    if (plan.ah_geometry == 1) return plan.ah_spill ? configure_geometry<geometry1, true>() : configure_geometry<geometry1, false>();
-    return plan.ah_spill ? configure_geometry<geometry0, true>() : configure_geometry<geometry0, false>();
+    return plan.ah_geometry == 1 ? configure_geometry<geometry1>() : configure_geometry<geometry0>();
 }
 
+// One pass of the generate-ahead kernel.  spill: with the two-level ring.  list == nullptr: the whole
+// shard (work counter); else the replications on `list`.  Replications it cannot finish are appended
+// to fail_list.
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, void *gring, uint32_t *state, int resume, cudaStream_t stream) {
+                             const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
+                             const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
+                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream) {
     mm1::constants c;
     c.lambda = make_divisor(prm.lambda);  // IEEE 1/d on the host: same bits as on the device
     c.mu = make_divisor(prm.mu);
@@ -328,16 +366,17 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.tick_mult = (double)sh.clk.tick_mult;
     c.n_packets = (uint32_t)prm.n_packets;
     c.ring_cap = plan.ah_ring_cap;
+    c.spill_cap = plan.ah_spill_cap;
     c.lead_cap = plan.ah_lead_cap;
     c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
     const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
-    uint2 *g = (uint2 *)gring;
+    pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
     if (plan.ah_geometry == 1) {
-        if (plan.ah_spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, g, state, resume, stream);
-        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, g, state, resume, stream);
+        if (spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, a, stream);
+        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, a, stream);
     } else {
-        if (plan.ah_spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, g, state, resume, stream);
-        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, g, state, resume, stream);
+        if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
+        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
     }
     return cudaGetLastError();
 }

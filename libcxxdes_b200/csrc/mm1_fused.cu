@@ -429,10 +429,23 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                 <<<plan.blocks, FAST_THREADS, plan.smem_bytes, stream>>>(prm, rates, sh, out, plan.smem_ring, nullptr,
                                                                         nullptr, nullptr, nullptr);
             e = cudaGetLastError();
+            ++*launches;
+        } else if (plan.ah_spill) {
+            // heavily loaded queue: two-level ring from the start; failures go straight to the fallback
+            e = launch_mm1_ahead(prm, sh, out, plan, true, ahead_gring, ahead_state, resume, nullptr, nullptr, nullptr,
+                                 sh.retry_list, sh.retry_count, stream);
+            ++*launches;
         } else {
-            e = launch_mm1_ahead(prm, sh, out, plan, ahead_gring, ahead_state, resume, stream);
+            // window-only first pass; what outgrows the window is redone with the two-level ring
+            // (a lone replication takes ~2 ms there, 13 ms on the fallback kernel)
+            e = launch_mm1_ahead(prm, sh, out, plan, false, ahead_gring, ahead_state, resume, nullptr, nullptr, nullptr,
+                                 sh.retry_a_list, sh.retry_a_count, stream);
+            ++*launches;
+            if (e != cudaSuccess) return e;
+            e = launch_mm1_ahead(prm, sh, out, plan, true, ahead_gring, nullptr, 0, sh.retry_a_list, sh.retry_a_count,
+                                 sh.retry_a_cursor, sh.retry_list, sh.retry_count, stream);
+            ++*launches;
         }
-        ++*launches;
         if (e != cudaSuccess) return e;
         // retry list -> fallback kernel; exits at once when the list is empty
         mm1_fused_kernel<false, FB_THREADS, 1><<<plan.fb_blocks, FB_THREADS, table_bytes, stream>>>(

@@ -71,7 +71,8 @@ extern "C" int mm1_lane_host_run(const cxxdes_b200_mm1_params *prm, int64_t tick
     c.tick_mult = (double)tick_mult;
     c.n_packets = (uint32_t)prm->n_packets;
     // window only: ring_cap <= 31 packets; spilling ring: ring_cap = global_slots, lead limited to the window
-    c.ring_cap = global_slots ? global_slots : ring_cap;
+    c.ring_cap = ring_cap;
+    c.spill_cap = global_slots ? global_slots : ring_cap;
     c.lead_cap = global_slots ? 30 : ring_cap;
     c.until = (until < 0 || until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)until;
     uint64_t iters = 0;

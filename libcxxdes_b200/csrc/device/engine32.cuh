@@ -17,6 +17,10 @@ struct token32 {
     uint32_t tag;
 };
 
+// Heap entries are one 8-byte word {time, tag} per slot, slot-major with the thread index as the
+// fastest dimension (STRIDE = threads per block, a compile-time constant so that slot addresses
+// are shifts and adds): one LDS.64 / STS.64 per entry moved.
+template <int STRIDE>
 struct environment32 {
     uint32_t now;
     uint32_t n_events;
@@ -24,32 +28,36 @@ struct environment32 {
     uint32_t status;
     int n;    // heap size
     int cap;  // heap capacity
-    lane_array<uint32_t> hkey;
-    lane_array<uint32_t> htag;
+    uint2 *heap;  // this thread's column: entry i at heap[i * STRIDE]
 
-    __device__ __forceinline__ void init(lane_array<uint32_t> k, lane_array<uint32_t> t, int capacity) {
+    __device__ __forceinline__ void init(uint2 *column, int capacity) {
         now = 0;
         n_events = 0;
         hash = TRACE_HASH_INIT;
         status = 0;
         n = 0;
         cap = capacity;
-        hkey = k;
-        htag = t;
+        heap = column;
+    }
+
+    // Carve the heap of `capacity` entries per thread out of the block's dynamic shared memory.
+    static __device__ __forceinline__ uint2 *carve_heap(unsigned char *&cursor, int capacity) {
+        const size_t mis = (size_t)((uintptr_t)cursor & 7);
+        unsigned char *p = cursor + ((8 - mis) & 7);
+        cursor = p + sizeof(uint2) * (size_t)capacity * STRIDE;
+        return (uint2 *)p + threadIdx.x;
     }
 
     // std::__push_heap, stl_heap.h:135-148; comp(parent, value) = parent strictly later.
     __device__ __forceinline__ void sift_up(int hole, uint32_t key, uint32_t tag) {
         while (hole > 0) {
             const int parent = (hole - 1) >> 1;
-            const uint32_t pk = hkey[parent];
-            if (!(pk > key)) break;
-            hkey[hole] = pk;
-            htag[hole] = htag[parent];
+            const uint2 pe = heap[parent * STRIDE];
+            if (!(pe.x > key)) break;
+            heap[hole * STRIDE] = pe;
             hole = parent;
         }
-        hkey[hole] = key;
-        htag[hole] = tag;
+        heap[hole * STRIDE] = make_uint2(key, tag);
     }
 
     // environment::schedule_token, environment.ipp:94-98 (vector::push_back + push_heap).
@@ -71,35 +79,33 @@ struct environment32 {
 
     // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back.
     __device__ __forceinline__ token32 pop_top() {
+        const uint2 first = heap[0];
         token32 top;
-        top.time = hkey[0];
-        top.tag = htag[0];
+        top.time = first.x;
+        top.tag = first.y;
         const int last = n - 1;
         if (last > 0) {
-            const uint32_t vkey = hkey[last];
-            const uint32_t vtag = htag[last];
+            const uint2 v = heap[last * STRIDE];
             const int len = last;
             int hole = 0;
             int child = 0;
             while (child < (len - 1) / 2) {
                 child = 2 * (child + 1);
-                uint32_t kr = hkey[child];
-                const uint32_t kl = hkey[child - 1];
-                if (kr > kl) {  // right strictly later than left -> take left; tie -> right
+                uint2 er = heap[child * STRIDE];
+                const uint2 el = heap[(child - 1) * STRIDE];
+                if (er.x > el.x) {  // right strictly later than left -> take left; tie -> right
                     --child;
-                    kr = kl;
+                    er = el;
                 }
-                hkey[hole] = kr;
-                htag[hole] = htag[child];
+                heap[hole * STRIDE] = er;
                 hole = child;
             }
             if ((len & 1) == 0 && child == (len - 2) / 2) {
                 child = 2 * (child + 1);
-                hkey[hole] = hkey[child - 1];
-                htag[hole] = htag[child - 1];
+                heap[hole * STRIDE] = heap[(child - 1) * STRIDE];
                 hole = child - 1;
             }
-            sift_up(hole, vkey, vtag);
+            sift_up(hole, v.x, v.y);
         }
         n = last;
         return top;
@@ -119,7 +125,7 @@ struct environment32 {
     }
 
     __device__ __forceinline__ bool has_event() const { return n > 0; }
-    __device__ __forceinline__ uint32_t next_time() const { return hkey[0]; }
+    __device__ __forceinline__ uint32_t next_time() const { return heap[0].x; }
 };
 
 }  // namespace cxb

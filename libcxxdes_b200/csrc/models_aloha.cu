@@ -190,13 +190,12 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
     stage_log_table(table, sh.log_table);
     const int N = (int)prm.num_stations;
     const int heap_cap = N + 2;
-    lane_array<uint32_t> hkey = carve<uint32_t>(cursor, heap_cap);
-    lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
+    uint2 *heap = environment32<AF_THREADS>::carve_heap(cursor, heap_cap);
 
     const int64_t frame_ticks = real_to_sim_f32(prm.frame_time, sh.clk);  // env.timeout(float), aloha.cpp:60
 
-    environment32 env;
-    env.init(hkey, htag, heap_cap);
+    environment32<AF_THREADS> env;
+    env.init(heap, heap_cap);
     uint64_t rep = 0, active_set = 0, collided = 0, pc_tx = 0;
     uint32_t successful = 0, main_pc = 0, remaining = 0, ctr2 = 0, ctr3 = 0;
     bool armed = false;
@@ -214,7 +213,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                 rate = make_divisor((double)(rp.lambda / (float)prm.num_stations));
                 ctr2 = (uint32_t)grep;
                 ctr3 = (uint32_t)(grep >> 32);
-                env.init(hkey, htag, heap_cap);
+                env.init(heap, heap_cap);
                 active_set = collided = pc_tx = 0;
                 successful = 0; main_pc = 0; remaining = 0; armed = false;
                 s_result = g_result = 0.0f;

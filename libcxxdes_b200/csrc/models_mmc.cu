@@ -199,7 +199,8 @@ struct wait_list16 {
     lane_array<uint16_t> who;
     int n;
     // wait_awaitable::await_suspend, event.hpp:136-139
-    __device__ __forceinline__ void wait(environment32 &env, uint32_t proc) {
+    template <typename Env>
+    __device__ __forceinline__ void wait(Env &env, uint32_t proc) {
         if (n >= MF_WAITERS) {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
@@ -207,7 +208,8 @@ struct wait_list16 {
         who[n++] = (uint16_t)proc;
     }
     // wake_awaitable::await_ready, event.hpp:125-134: schedule every waiter in list order
-    __device__ __forceinline__ void wake(environment32 &env) {
+    template <typename Env>
+    __device__ __forceinline__ void wake(Env &env) {
         for (int i = 0; i < n; ++i) env.schedule(env.now, (uint32_t)who[i]);
         n = 0;
     }
@@ -221,8 +223,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     stage_log_table(table, sh.log_table);
-    lane_array<uint32_t> hkey = carve<uint32_t>(cursor, MF_HEAP);
-    lane_array<uint32_t> htag = carve<uint32_t>(cursor, MF_HEAP);
+    uint2 *heap = environment32<MF_THREADS>::carve_heap(cursor, MF_HEAP);
     wait_list16 waiters;
     waiters.who = carve<uint16_t>(cursor, MF_WAITERS);
     waiters.n = 0;
@@ -233,8 +234,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     const int64_t patience_ticks = real_to_sim(prm.patience, sh.clk);  // env.timeout(patience)
     const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
 
-    environment32 env;
-    env.init(hkey, htag, MF_HEAP);
+    environment32<MF_THREADS> env;
+    env.init(heap, MF_HEAP);
     uint64_t rep = 0;
     uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
     double total_wait = 0.0;
@@ -252,7 +253,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 const uint64_t grep = sh.first_replication + rep;
                 ctr2 = (uint32_t)grep;
                 ctr3 = (uint32_t)(grep >> 32);
-                env.init(hkey, htag, MF_HEAP);
+                env.init(heap, MF_HEAP);
                 waiters.n = 0;
                 value = prm.servers;  // semaphore{c, c}
                 i = served = balked = 0;

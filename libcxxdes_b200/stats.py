@@ -52,3 +52,31 @@ def mm1_sweep_table(run_point, lambdas, mu):
         mean, ci = mean_and_ci(acc, 0)
         lines.append(f"{lam:.3f}, {mu:.3f}, {lam / mu:.3f}, {mean:.6f}, {ci:.6f}, {1.0 / (mu - lam):.6f}")
     return "\n".join(lines)
+
+
+def time_series(ens, piece, n_pieces, stat=1, count=0):
+    """Ensemble time series from run_for in pieces: after every piece of `piece` ticks the
+    on-device reduction gives the cumulative sums; their differences are the per-interval statistics.
+
+    Returns a list of dicts, one per interval: t_end (ticks), events (all replications), d_stat (increase of
+    f64[stat] summed over replications, e.g. total latency), d_count (increase of i64[count], e.g. packets
+    consumed), mean (= d_stat / d_count: e.g. the mean latency of the packets finished in the interval)."""
+    rows = []
+    prev_ev, prev_stat, prev_count = 0, 0.0, 0
+    for j in range(1, n_pieces + 1):
+        ens.run_for(piece)
+        acc, _ = ens.reduce()
+        ev, st, ct = acc.n_events, acc.f64_sum[stat], acc.i64_sum[count]
+        rows.append({"t_end": j * piece, "events": ev - prev_ev, "d_stat": st - prev_stat, "d_count": ct - prev_count,
+                     "mean": (st - prev_stat) / (ct - prev_count) if ct != prev_count else float("nan")})
+        prev_ev, prev_stat, prev_count = ev, st, ct
+    return rows
+
+
+def batch_means(rows, warmup=1, z=1.959964):
+    """Batch-means estimate from time_series() rows: the first `warmup` intervals are dropped (initial
+    transient), the remaining interval means are treated as one sample each.  Returns (mean, half-width)."""
+    xs = np.array([r["mean"] for r in rows[warmup:] if r["d_count"]], dtype=np.float64)
+    if len(xs) < 2:
+        return (float(xs[0]) if len(xs) else float("nan")), float("nan")
+    return float(xs.mean()), float(z * xs.std(ddof=1) / math.sqrt(len(xs)))

@@ -139,6 +139,27 @@ def test_run_for_in_pieces_matches_oracle(port, lam, n_packets, piece, n_pieces,
     golden_util.assert_columns_equal(got, want, what="run() after the pieces")
 
 
+def test_time_series_from_pieces(port):
+    """stats.time_series: per-interval statistics from run_for pieces equal the differences of the oracle's
+    run_until columns; batch means with the transient dropped land on the M/M/1 latency 1/(mu - lambda)."""
+    from libcxxdes_b200 import stats
+    p = abi.MM1Params(5.0, 10.0, 4000)
+    n_reps, piece, n_pieces = 2048, 50000, 10
+    ens = L.Ensemble(p, n_reps, seed=13)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    rows = stats.time_series(ens, piece, n_pieces)
+    ens.close()
+    prev = None
+    for j in (1, 2, 7):
+        want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 13, 0, n_reps, threads=oracles.os.cpu_count(), until=j * piece)
+        cum_events = sum(r["events"] for r in rows[:j])
+        cum_count = sum(r["d_count"] for r in rows[:j])
+        assert cum_events == int(want.n_events.sum()) and cum_count == int(want.i64[0].sum())
+        assert abs(sum(r["d_stat"] for r in rows[:j]) - want.f64[1].sum()) <= 1e-9 * want.f64[1].sum()
+    mean, half = stats.batch_means(rows, warmup=1)
+    assert abs(mean - 0.2) < 0.01 and half < 0.01
+
+
 def test_reset_forgets_saved_state(port):
     p = abi.MM1Params(5.0, 10.0, 600)
     ens = L.Ensemble(p, 128, seed=8)

@@ -37,3 +37,9 @@ def test_sweep_table_shape():
     rows = text.splitlines()
     assert rows[0].startswith("lambda, mu, rho, avg_latency") and len(rows) == 3
     assert rows[2].split(", ")[3] == rows[2].split(", ")[5]
+
+
+def test_batch_means_drops_the_transient():
+    rows = [{"mean": 9.0, "d_count": 5}] + [{"mean": m, "d_count": 5} for m in (1.0, 1.2, 0.8, 1.0)]
+    mean, half = stats.batch_means(rows, warmup=1)
+    assert abs(mean - 1.0) < 1e-12 and 0.0 < half < 0.5

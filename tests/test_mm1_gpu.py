@@ -56,6 +56,28 @@ def test_gpu_matches_oracle(port, lam, n_packets, n_reps, flags):
     assert abs(acc.f64_sumsq[0] - (want.f64[0] ** 2).sum()) <= 1e-12 * (want.f64[0] ** 2).sum()
 
 
+def test_config1_single_long_replication(port):
+    """BASELINE config 1 through the GPU path: examples/producer_consumer.cpp with n_packets = 100000,
+    avg_latency near 1/(mu - lambda) = 0.2 s and bit-equal to the CPU run."""
+    p = abi.MM1Params(5.0, 10.0, 100000)
+    got, _ = run_gpu(p, 3, seed=0)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 0, 0, 3, threads=3)
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="config 1")
+    assert abs(got.f64[0][0] - 0.2) < 0.006
+
+
+def test_heavy_load_full_length_uses_the_second_ring_level(port):
+    """rho = 0.95 at the full 10000 packets: queues of 50-150 packets live in the global-memory
+    level of the ring for most of the run."""
+    p = abi.MM1Params(9.5, 10.0, 10000)
+    got, _ = run_gpu(p, 192, seed=4)
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 4, 0, 192, threads=oracles.os.cpu_count())
+    assert (want.i64[1] > 40).mean() > 0.9          # every queue leaves the 31-packet window
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="rho 0.95")
+
+
 def test_small_ring_takes_the_retry_path(port):
     """A 4-entry shared ring overflows in most replications: they are re-run by the global-ring
     kernel and must still match the oracle bit for bit."""

@@ -248,6 +248,98 @@ CXXDES_SIMULATION(kat_event) {
     coroutine<> co_main() { return tr.named(body(), 0); }
 };
 
+// 11 -- examples/debug.cpp: at t = 5 the timeout with explicit priority -1 pops before the one with 0
+CXXDES_SIMULATION(kat_debug) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_debug(tracer &t) : tr{t} { bind(); }
+    coroutine<> p1() {
+        co_await timeout(5);
+        marks.push_back(now() * 10 + 1);  // 5
+        co_await timeout(5);
+        marks.push_back(now() * 10 + 1);  // 10
+    }
+    coroutine<> p2() {
+        co_await timeout(2);
+        marks.push_back(now() * 10 + 2);  // 2
+        co_await timeout(3, -1);
+        marks.push_back(now() * 10 + 2);  // 5, before p1's
+    }
+    coroutine<> body() { co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2)); }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 12 -- examples/raii_trick.cpp: resource{1}, _Co_with(res) { timeout(wait) }, priorities 0 -1 -2 -3:
+//       ids 3, 2, 1, 0 finish at 8, 16, 21, 31
+CXXDES_SIMULATION(kat_raii_trick) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    cxxdes::sync::resource res{1};
+    explicit kat_raii_trick(tracer &t) : tr{t} { bind(); }
+    coroutine<> p(int id, time_integral wait_time) {
+        _Co_with(res) {
+            co_await timeout(wait_time);
+            marks.push_back(now() * 10 + id);
+        };
+    }
+    coroutine<> body() {
+        co_await all_of(tr.named(p(0, 10), 1).priority(0), tr.named(p(1, 5), 2).priority(-1),
+                        tr.named(p(2, 8), 3).priority(-2), tr.named(p(3, 8), 4).priority(-3));
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
+// 13 -- examples/get_environment.cpp: two roots bound with env.bind, the second with priority -10000
+//       runs its four yield() rounds before the first one's body starts; this_environment() is no event
+struct kat_get_environment {
+    environment env;
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_get_environment(tracer &t) : tr{t} {
+        env.bind(tr.named(p1(), 1));
+        env.bind(tr.named(p2(), 2).priority(-10000));
+    }
+    coroutine<> p1() {
+        marks.push_back(env.now() * 10 + 1);
+        auto e = co_await this_environment();  // does not yield control
+        marks.push_back(e->now() * 10 + 1);
+        co_await timeout(4);
+        marks.push_back(e->now() * 10 + 1);  // 4
+        co_await e->timeout(4);
+        marks.push_back(e->now() * 10 + 1);  // 8
+    }
+    coroutine<> p2() {
+        for (int k = 0; k < 4; ++k) {
+            marks.push_back(env.now() * 10 + 2);
+            co_await yield();
+        }
+    }
+    time_integral now() const { return env.now(); }
+};
+
+// 14 -- examples/lazy_timeout.cpp: a lazy_timeout fixes its deadline when created; awaiting it after
+//       the deadline does not suspend: 10, 30, 30
+CXXDES_SIMULATION(kat_lazy_timeout) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_lazy_timeout(tracer &t) : tr{t} { bind(); }
+    coroutine<> body() {
+        {
+            auto t = co_await lazy_timeout(10);
+            co_await t;
+            marks.push_back(now());  // 10
+        }
+        {
+            auto t = co_await lazy_timeout(10);
+            co_await timeout(20);
+            marks.push_back(now());  // 30
+            co_await t;
+            marks.push_back(now());  // 30
+        }
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
 // Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
 // application-level observations are compared too, not only the token trace.
 inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
@@ -282,6 +374,10 @@ inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::ve
         case 8: return run_kat_sim<kat_semaphore>(tr, until);
         case 9: return run_kat_sim<kat_queue>(tr, until);
         case 10: return run_kat_sim<kat_event>(tr, until);
+        case 11: return run_kat_sim<kat_debug>(tr, until);
+        case 12: return run_kat_sim<kat_raii_trick>(tr, until);
+        case 13: return run_kat_sim<kat_get_environment>(tr, until);
+        case 14: return run_kat_sim<kat_lazy_timeout>(tr, until);
         default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
     }
 }

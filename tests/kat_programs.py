@@ -158,11 +158,63 @@ def event():                 # 10: examples/event.cpp
     return prog, -1
 
 
+def debug():                 # 11: examples/debug.cpp
+    prog = Program()
+    main = prog.process(0, root=True)
+    p1, p2 = prog.process(1), prog.process(2)
+    with prog.body(p1) as b:
+        b.delay(5); b.mark(10, 1); b.delay(5); b.mark(10, 1)
+    with prog.body(p2) as b:
+        b.delay(2); b.mark(10, 2); b.delay(3, priority=-1); b.mark(10, 2)
+    with prog.body(main) as b:
+        b.all_of(p1, p2)
+    return prog, -1
+
+
+def raii_trick():            # 12: examples/raii_trick.cpp
+    prog = Program()
+    res = prog.resource(1)
+    main = prog.process(0, root=True)
+    ps = []
+    for ordinal, (ident, wait, prio) in enumerate(((0, 10, 0), (1, 5, -1), (2, 8, -2), (3, 8, -3)), start=1):
+        p = prog.process(ordinal, priority=prio)
+        helper = prog.process(0x8000 | ordinal)    # _Co_with(res) { ... }: co_with.ipp:27-35
+        with prog.body(helper) as b:
+            b.down(res); b.delay(wait); b.mark(10, ident); b.up(res)
+        with prog.body(p) as b:
+            b.await_(helper)
+        ps.append(p)
+    with prog.body(main) as b:
+        b.all_of(*ps)
+    return prog, -1
+
+
+def get_environment():       # 13: examples/get_environment.cpp
+    prog = Program()
+    p1 = prog.process(1, root=True)
+    p2 = prog.process(2, priority=-10000, root=True)
+    with prog.body(p1) as b:
+        b.mark(10, 1); b.mark(10, 1); b.delay(4); b.mark(10, 1); b.delay(4); b.mark(10, 1)
+    with prog.body(p2) as b:
+        with b.loop(4):
+            b.mark(10, 2); b.delay(0)              # yield() == delay(0), timeout.ipp:180-182
+    return prog, -1
+
+
+def lazy_timeout():          # 14: examples/lazy_timeout.cpp (a lazy_timeout(d) created at t is until(t + d) when awaited)
+    prog = Program()
+    main = prog.process(0, root=True)
+    with prog.body(main) as b:
+        b.until(10); b.mark(1, 0)
+        b.delay(20); b.mark(1, 0); b.until(20); b.mark(1, 0)
+    return prog, -1
+
+
 SCENARIOS = {1: compositions, 2: latencies, 3: out_of_scope, 4: priorities, 5: clocks, 6: resource, 7: mutex,
-             8: semaphore, 9: queue, 10: event}
+             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout}
 # end time of every scenario on the reference engine (the reference's tests / examples document the
 # observation times; scenario 1 ends at 40 because the loser of any_of(timeout(10), timeout(20)) still fires)
-EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602}
+EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30}
 
 
 def mm1_program(lam, mu, n_packets):

@@ -26,6 +26,10 @@
 #ifndef CXB_MM1_UNROLL
 #define CXB_MM1_UNROLL 1
 #endif
+// Source order of the event slots and the generation inside the branch-free block (measured: see DESIGN.md)
+#ifndef CXB_MM1_ORDER
+#define CXB_MM1_ORDER 0
+#endif
 
 namespace cxb {
 
@@ -175,11 +179,27 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         bool want, room;
 #pragma unroll
         for (int u = 0; u < CXB_MM1_UNROLL; ++u) {
+#if CXB_MM1_ORDER == 1
+            want = active && L.status == 0 && L.wants_packets(c);
+            room = L.template has_room<SPILL>(c);
+            L.generate_pair(c, ring, table, want & room);
+#pragma unroll
+            for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);
+#elif CXB_MM1_ORDER == 2
+#pragma unroll
+            for (int s = 0; s < EVENT_SLOTS / 2; ++s) L.template fast_slot<MODE>(c, ring);
+            want = active && L.status == 0 && L.wants_packets(c);
+            room = L.template has_room<SPILL>(c);
+            L.generate_pair(c, ring, table, want & room);
+#pragma unroll
+            for (int s = EVENT_SLOTS / 2; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);
+#else
 #pragma unroll
             for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
             want = active && L.status == 0 && L.wants_packets(c);
             room = L.template has_room<SPILL>(c);
             L.generate_pair(c, ring, table, want & room);
+#endif
         }
         // (a ring that is truly exhausted stays so, checking after the last generation is enough)
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;

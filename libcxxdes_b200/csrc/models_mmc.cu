@@ -271,6 +271,21 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
         if (active) {
             const token32 t = env.step_pop();
             const uint32_t target = t.tag & 0xFFFFu;
+            // An event pushes at most two tokens of its own (wake-ups aside).  The branches below only
+            // note which; the pushes -- the sifts through the heap -- run after them, in one piece of
+            // code for all lanes, in the order they were noted (push order decides ties).
+            uint32_t p_time[2], p_tag[2];
+            int n_push = 0;
+            auto push_at = [&](uint32_t time, uint32_t tag) {
+                p_time[n_push] = time;
+                p_tag[n_push] = tag;
+                ++n_push;
+            };
+            auto push_after = [&](int64_t delay, uint32_t tag) {
+                const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
+                if ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull) env.status |= CXXDES_B200_REP_TIME_RANGE;
+                push_at((uint32_t)when, tag);
+            };
             if (t.tag & MF_HANDLER) {
                 // any_of handler of customer (target - 2) / 2: any_of.ipp:9-26
                 env.fold(t.time, TOKEN_HANDLER, target);
@@ -279,7 +294,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 const uint64_t remaining = ((s & C_REM) >> C_REM_SHIFT) - 1;
                 s = (s & ~C_REM) | (remaining << C_REM_SHIFT);
                 if ((s & C_ARMED) && remaining < 2) {
-                    env.schedule(t.time, target);  // output token
+                    push_at(t.time, target);  // output token
                     s &= ~C_ARMED;
                 }
                 *w = s;
@@ -289,20 +304,20 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 env.fold(t.time, TOKEN_RESUME, target);
                 if (target == 0) {
                     if (main_pc == 0) {
-                        env.schedule(env.now, 1);  // co_await source(): start token; completion targets main
+                        push_at(env.now, 1);  // co_await source(): start token; completion targets main
                         main_pc = 1;
                     } else {
-                        env.schedule(env.now, MF_NOOP);
+                        push_at(env.now, MF_NOOP);
                     }
                 } else if (target == 1) {
                     // source: for i < n { co_await async(customer(i)); co_await env.timeout(arr()); }
                     if (source_pc == 1) ++i;
                     if (i < n) {
-                        env.schedule(env.now, 2 + 2 * i);  // async: start token (async.ipp:21-28)
-                        env.schedule_after(draw(1, i, d_lambda), 1);
+                        push_at(env.now, 2 + 2 * i);  // async: start token (async.ipp:21-28)
+                        push_after(draw(1, i, d_lambda), 1);
                         source_pc = 1;
                     } else {
-                        env.schedule(env.now, 0);  // source returns -> completion resumes co_main
+                        push_at(env.now, 0);  // source returns -> completion resumes co_main
                     }
                 } else {
                     const uint32_t id = (target - 2) >> 1;
@@ -314,17 +329,17 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         if (pc == 0) {
                             // t0 = now_seconds(); any_of(acquire_proc, env.timeout(patience))
                             s = ((uint64_t)env.now << C_T0_SHIFT) | 1 | C_ARMED | (2ULL << C_REM_SHIFT);
-                            env.schedule(env.now, target + 1);                        // await_bind: start(acquire_proc)
-                            env.schedule_after(patience_ticks, target | MF_HANDLER);  // await_suspend: timeout + handler
+                            push_at(env.now, target + 1);                        // await_bind: start(acquire_proc)
+                            push_after(patience_ticks, target | MF_HANDLER);     // await_suspend: timeout + handler
                         } else if (pc == 1) {
                             if (!(s & C_ACQ_DONE)) {
                                 s = (s & ~C_PC) | 3 | C_BALKED;  // balked: co_return
                                 ++balked;
-                                env.schedule(env.now, MF_NOOP);  // async's null-target completion
+                                push_at(env.now, MF_NOOP);  // async's null-target completion
                             } else {
                                 const double t0 = sim_to_seconds((int64_t)(s >> C_T0_SHIFT), sh.clk);
                                 total_wait += sim_to_seconds((int64_t)env.now, sh.clk) - t0;
-                                env.schedule_after(draw(target, 0, d_mu), target);
+                                push_after(draw(target, 0, d_mu), target);
                                 s = (s & ~C_PC) | 2;
                             }
                         } else {
@@ -333,7 +348,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             waiters.wake(env);
                             ++served;
                             s = (s & ~C_PC) | 3;
-                            env.schedule(env.now, MF_NOOP);
+                            push_at(env.now, MF_NOOP);
                         }
                     } else {
                         // ---- acquire_proc(id): st.h = co_await servers.acquire(); if (balked) release ----
@@ -347,12 +362,14 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                                 waiters.wake(env);
                             }
                             s |= C_ACQ_DONE;
-                            env.schedule(env.now, (target - 1) | MF_HANDLER);  // completion token with the any_of handler
+                            push_at(env.now, (target - 1) | MF_HANDLER);  // completion token with the any_of handler
                         }
                     }
                     *w = s;
                 }
             }
+            if (n_push > 0) env.schedule(p_time[0], p_tag[0]);
+            if (n_push > 1) env.schedule(p_time[1], p_tag[1]);
 
             if (env.status || !env.has_event() || env.next_time() > until) {
                 active = false;

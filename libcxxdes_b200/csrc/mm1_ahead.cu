@@ -296,10 +296,16 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
         p.ah_spill_cap = slots;
         p.ah_lead_cap = window - 1;
     }
-    // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds())
-    // ... and every single delay must fit the 32-bit tick representation
+    // tick_mult < 2^23 keeps tick * tick_mult exact in a double (mm1_lane.cuh seconds()),
+    // every single delay must fit the 32-bit tick representation,
+    // and so must the clock at the end of the run: the lane's bound is A_n + sum of the service
+    // times, n (1/lambda + 1/mu) ticks_per_unit on average.  A run that is going to pass 2^30 ticks
+    // anyway goes to the 64-bit kernel at once (1 us precision with a 1 s unit: 272 ms instead of
+    // 890 ms spent failing late in both fast passes first).
+    const double expected_bound = (double)prm.n_packets * (1.0 / prm.lambda + 1.0 / prm.mu) * (double)ticks_per_unit;
     p.ah_direct_global = tick_mult >= (1 << 23) || !mm1::draw_fits_u32(prm.lambda, (double)ticks_per_unit) ||
-                         !mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit);
+                         !mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit) ||
+                         !(1.25 * expected_bound < (double)mm1::TIME_LIMIT);
 }
 
 size_t mm1_ahead_state_bytes(uint64_t n_replications) { return (size_t)n_replications * mm1::lane::STATE_WORDS * sizeof(uint32_t); }

@@ -168,8 +168,8 @@ CXB_HD uint64_t tag_hash_bits(uint32_t m) {
 constexpr uint64_t PROD_BITS = (uint64_t)M_PROD << 40;
 constexpr uint64_t CONS_BITS = (uint64_t)M_CONS << 40;
 
-CXB_HD uint64_t fold(uint64_t h, uint32_t t, uint64_t bits) {
-    return (rotl64(h, 5) ^ ((uint64_t)t ^ bits)) * TRACE_HASH_MUL;
+CXB_HD uint64_t fold(uint64_t h, uint64_t t, uint64_t bits) {
+    return (rotl64(h, 5) ^ (t ^ bits)) * TRACE_HASH_MUL;
 }
 
 // Integer <-> double conversions without the XU pipe (I2F/F2I issue at a quarter of the FP64 rate):
@@ -179,6 +179,14 @@ constexpr double TWO52 = 4503599627370496.0;
 CXB_HD double u32_to_double(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(0x43300000, (int)x) - TWO52;
+#else
+    return (double)x;
+#endif
+}
+
+CXB_HD double u64_to_double(uint64_t x) {   // x < 2^52
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)(0x43300000u | (uint32_t)(x >> 32)), (int)(uint32_t)x) - TWO52;
 #else
     return (double)x;
 #endif
@@ -211,14 +219,17 @@ struct constants {
     uint32_t ring_cap;       // packets (queued + generated ahead) the shared-memory window may hold, >= 2
     uint32_t spill_cap;      // ... and the ring with its global-memory level (spilling path)
     uint32_t lead_cap;       // spilling path: packets that may be generated ahead of the producer
-    uint32_t until;          // run_until horizon in ticks, EMPTY when there is none
+    uint32_t until;          // run_until horizon in ticks, EMPTY when there is none (or beyond 2^30)
+    int64_t until64;         // the same horizon as given, < 0 when there is none (MODE_WIDE)
 };
 
 // Compile-time variants of the lane code.
 enum : int {
     MODE_UNTIL = 1,      // a run_until horizon is set (else the check is compiled out)
-    MODE_TICK_MULT = 2   // time_precision().t != 1: now_seconds needs the extra multiply
+    MODE_TICK_MULT = 2,  // time_precision().t != 1: now_seconds needs the extra multiply
+    MODE_WIDE = 4        // the clock passes 2^30 ticks: 32-bit times are relative to a per-lane epoch
 };
+constexpr uint32_t REBASE_LIMIT = 1u << 29;   // MODE_WIDE: move the epoch when the bound on the live times passes this
 
 // Steady-state tokens are compared as one 32-bit key that carries the tie rule of the two-entry
 // libstdc++ heap ("equal (time, priority): the earlier push pops first", stl_heap.h:135-148):
@@ -232,7 +243,7 @@ struct ring_entry {
 };
 
 // One replication.  `Ring` gives ring_entry load(j, g) / uint32_t load_a(j) / store_if(p, j, e) /
-// store_a_if(p, j, ak) / spill_if(p, g).  Its first level is a window of WINDOW + 1 slots (j modulo
+// store_a_if(p, j, ak) / spill_if(p, g) / store_level(j, g, e) (rewrite entry j where load(j, g) finds it).  Its first level is a window of WINDOW + 1 slots (j modulo
 // that size) holding the entries [g - WINDOW, g) and the arrival key of entry g; a spilling ring
 // (SPILL) keeps older queued entries in a second, larger level.
 struct lane {
@@ -253,8 +264,15 @@ struct lane {
     uint32_t status;
     uint64_t hash;
     double total_latency;
+    // MODE_WIDE (fine time precision: the clock passes 2^30 ticks although the live tokens span far
+    // less): every 32-bit time / key above is relative to `epoch`, which is moved forward
+    // (rebase()) whenever the bound on the live times passes 2^29.  Otherwise epoch stays 0.
+    uint64_t epoch;
+    uint32_t until_rel;         // run_until horizon relative to epoch, EMPTY when none / out of reach
 
-    CXB_HD void init(uint64_t global_replication) {
+    CXB_HD void init(uint64_t global_replication, const constants &c) {
+        epoch = 0;
+        until_rel = c.until;
         ctr2 = (uint32_t)global_replication;
         ctr3 = (uint32_t)(global_replication >> 32);
         g = 0; agk = 1; budget = 0;
@@ -299,7 +317,7 @@ struct lane {
     // integer bookkeeping of the event slots in the same basic block.
     // ANCHOR_SECOND (only when a saved replication is resumed at an odd k): agk is the key of
     // packet g + 1 instead of packet g.
-    template <bool ANCHOR_SECOND = false, typename Ring, typename Table>
+    template <int MODE, bool ANCHOR_SECOND = false, typename Ring, typename Table>
     CXB_HD void generate_pair(const constants &c, Ring &ring, const Table *table, bool enable) {
         const philox_block bp = philox4x32_10_scheduled(g >> 1, 1u, ctr2, ctr3, c.keys);
         const philox_block bc = philox4x32_10_scheduled(g >> 1, 2u, ctr2, ctr3, c.keys);
@@ -311,7 +329,15 @@ struct lane {
         // range guard: each delay < 2^28 (draw_fits_u32) and the bound on the last event time
         // < 2^30, so no 32-bit sum or key below can wrap; otherwise the replication is redone with
         // 64-bit ticks
-        const uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
+        uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
+        if (MODE & MODE_WIDE) {
+            // relative times: move the epoch up to the oldest live time and retry (rare: once per
+            // ~2^29 ticks of simulated time); only a window that itself spans 2^30 ticks is out of range
+            if (enable && new_budget >= REBASE_LIMIT) {
+                rebase<MODE>(c, ring);
+                new_budget = budget + ia0 + ia1 + s0 + s1;
+            }
+        }
         const bool out_of_range = new_budget >= TIME_LIMIT;
         const bool commit = enable & !out_of_range;
         status |= (enable & out_of_range) ? (uint32_t)CXXDES_B200_REP_TIME_RANGE : 0u;
@@ -333,6 +359,67 @@ struct lane {
         glim = is_fast() ? g : 0u;
     }
 
+    // ---- MODE_WIDE: absolute time of a relative tick, and moving the epoch -----------------------
+    template <int MODE>
+    CXB_HD uint64_t abs_time(uint32_t tick) const {
+        return (MODE & MODE_WIDE) ? epoch + tick : (uint64_t)tick;
+    }
+
+    CXB_HD void set_until_rel(const constants &c) {
+        if (c.until64 < 0 || (uint64_t)c.until64 < epoch || (uint64_t)c.until64 - epoch >= TIME_LIMIT) until_rel = EMPTY;
+        else until_rel = (uint32_t)((uint64_t)c.until64 - epoch);
+        // (a horizon already behind the epoch cannot happen: the lane stops at the horizon)
+    }
+
+    // Subtract the oldest live time from every relative time and key of the lane (tokens, ring
+    // entries, clock, generation frontier) and add it to the epoch; the bound on the live times is
+    // recomputed exactly: latest live time + the service times still queued.
+    template <int MODE, typename Ring>
+    CXB_HD void rebase(const constants &c, Ring &ring) {
+        uint32_t lo = agk >> 2, hi = agk >> 2;
+        auto see = [&](uint32_t t) { lo = t < lo ? t : lo; hi = t > hi ? t : hi; };
+        bool serving;
+        if (is_fast()) {
+            see(kp >> 2);
+            serving = kc != EMPTY;
+            if (serving) see(kc >> 2);
+        } else {
+            if (t0 != EMPTY) see(t0);
+            if (t1 != EMPTY) see(t1);
+            see(now);
+            serving = cons_pc == 2;
+        }
+        if (serving) see(x_tick);
+        uint32_t sum_s = 0;
+        for (uint32_t j = k; j < g; ++j) {
+            const ring_entry e = ring.load(j, g);
+            if (j == k) see(e.ak >> 2);
+            sum_s += e.s4 >> 2;
+        }
+        const uint32_t d = lo, d4 = 4u * lo;
+        for (uint32_t j = k; j < g; ++j) {
+            ring_entry e = ring.load(j, g);
+            e.ak -= d4;
+            ring.store_level(j, g, e);
+        }
+        agk -= d4;
+        ring.store_a_if(true, g, agk);
+        if (is_fast()) {
+            kp -= d4;
+            if (kc != EMPTY) kc -= d4;
+        } else {
+            if (t0 != EMPTY) t0 -= d;
+            if (t1 != EMPTY) t1 -= d;
+        }
+        now = now > d ? now - d : 0u;          // (stale in the steady state, live otherwise)
+        x_tick = x_tick > d ? x_tick - d : 0u; // (stale unless a packet is in service)
+        epoch += d;
+        budget = (hi - d) + sum_s;
+        set_until_rel(c);
+        // absolute ticks (times tick_mult) must stay exact in a double
+        if ((double)(epoch + TIME_LIMIT) * c.tick_mult >= TWO52) status |= CXXDES_B200_REP_TIME_RANGE;
+    }
+
     // ---- run_until / run_for in pieces: state of a replication between two launches ---------------
     // (environment::run_until returns with the tokens still scheduled, environment.ipp:190-196;
     // the next call continues from there.)  Everything but the ring is saved; the ring entries
@@ -352,10 +439,11 @@ struct lane {
         w[20] = (uint32_t)hash; w[21] = (uint32_t)(hash >> 32);
         const uint64_t tl = double_as_bits(total_latency);
         w[22] = (uint32_t)tl; w[23] = (uint32_t)(tl >> 32);
+        w[24] = (uint32_t)epoch; w[25] = (uint32_t)(epoch >> 32);
     }
 
     // Counterpart of save(); leaves g <= k with agk anchored at packet k, regenerate() refills.
-    CXB_HD void restore(const uint32_t *w, uint64_t global_replication) {
+    CXB_HD void restore(const uint32_t *w, uint64_t global_replication, const constants &c) {
         ctr2 = (uint32_t)global_replication;
         ctr3 = (uint32_t)(global_replication >> 32);
         agk = w[1]; budget = w[2]; i = w[3]; k = w[4]; kp = w[5]; kc = w[6];
@@ -364,16 +452,19 @@ struct lane {
         now = w[15]; x_tick = w[16]; n_events = w[17]; max_queue = w[18]; status = w[19] & ~(uint32_t)CXXDES_B200_REP_UNFINISHED;
         hash = ((uint64_t)w[21] << 32) | w[20];
         total_latency = bits_as_double(((uint64_t)w[23] << 32) | w[22]);
+        epoch = ((uint64_t)w[25] << 32) | w[24];
+        set_until_rel(c);
+        if (c.until64 < 0 || epoch == 0) until_rel = c.until;   // (no horizon, or not a wide-clock run)
         g = k & ~1u;
         glim = 0;
     }
 
     // Draw the ring entries of a restored replication again, up to the packet the producer puts
     // next (the invariant of the event loop: g > i while there are packets left).
-    template <bool SPILL, typename Ring, typename Table>
+    template <int MODE, bool SPILL, typename Ring, typename Table>
     CXB_HD void regenerate(const constants &c, Ring &ring, const Table *table) {
-        if ((k & 1u) && wants_packets(c)) generate_pair<true>(c, ring, table, true);   // agk is A_k = A_{g+1}
-        while (status == 0 && g <= i && wants_packets(c) && has_room<SPILL>(c)) generate_pair(c, ring, table, true);
+        if ((k & 1u) && wants_packets(c)) generate_pair<MODE, true>(c, ring, table, true);   // agk is A_k = A_{g+1}
+        while (status == 0 && g <= i && wants_packets(c) && has_room<SPILL>(c)) generate_pair<MODE>(c, ring, table, true);
         glim = is_fast() ? g : 0u;
     }
 
@@ -392,8 +483,9 @@ struct lane {
     CXB_HD double seconds(const constants &c, uint32_t tick) const {
         // environment::now_seconds, environment.ipp:29-36: (double)(now * prec.t) * conv[prec.u];
         // tick * prec.t < 2^53, so the product of the two doubles is that integer exactly
-        if (MODE & MODE_TICK_MULT) return (u32_to_double(tick) * c.tick_mult) * c.sec_per_unit;
-        return u32_to_double(tick) * c.sec_per_unit;
+        const double ticks = (MODE & MODE_WIDE) ? u64_to_double(epoch + tick) : u32_to_double(tick);
+        if (MODE & MODE_TICK_MULT) return (ticks * c.tick_mult) * c.sec_per_unit;
+        return ticks * c.sec_per_unit;
     }
 
     // ---- steady state: one event (two when a put wakes the consumer) ---------------------------
@@ -404,7 +496,7 @@ struct lane {
     template <int MODE, typename Ring>
     CXB_HD void fast_slot(const constants &c, Ring &ring) {
 #if defined(__CUDA_ARCH__)
-        if constexpr (Ring::HAS_PTX_SLOT) {
+        if constexpr (Ring::HAS_PTX_SLOT && !(MODE & MODE_WIDE)) {   // (wide clocks run the C++ below)
             fast_slot_ptx<MODE, Ring::SPILL, Ring::MASK, Ring::STRIDE>(c, ring.base, ring.gbase, ring.gstride, ring.gmask);
             return;
         }
@@ -415,7 +507,7 @@ struct lane {
         bool cons = kc < kp;
         bool put = !cons & (i < glim);
         if (MODE & MODE_UNTIL) {
-            const bool due = key <= 4u * c.until + 3u;  // run_until stops at `until`
+            const bool due = key <= 4u * until_rel + 3u;  // run_until stops at `until` (EMPTY wraps to all ones)
             cons &= due;
             put &= due;
         }
@@ -426,10 +518,10 @@ struct lane {
         const ring_entry e = ring.load(k, g);
         // environment::step: pop, fold (tokens are scheduled at now + d with d >= 0, so the clock
         // is simply the time of the last token; `now` itself is only needed outside this state)
-        if (cons | put) hash = fold(hash, t, cons ? CONS_BITS : PROD_BITS);
+        if (cons | put) hash = fold(hash, abs_time<MODE>(t), cons ? CONS_BITS : PROD_BITS);
         // The woken consumer's token {0 + now} was pushed before the producer's timeout, so it is
         // the very next event (event.hpp:125-134): it is dispatched in the same slot.
-        if (woke) hash = fold(hash, t, CONS_BITS);
+        if (woke) hash = fold(hash, abs_time<MODE>(t), CONS_BITS);
         // total_latency += now_seconds() - x   (producer_consumer.cpp:52); for the other lanes
         // x - x = +0 is added, which leaves the (non-negative) sum as it is
         const uint32_t ts = cons ? t : x_tick;
@@ -468,7 +560,7 @@ struct lane {
     template <int MODE, bool SPILL, int MASK, int STRIDE>
     __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base, const void *gbase, uint32_t gstride,
                                                   uint32_t gmask) {
-        const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * c.until + 3u : 0xFFFFFFFFu;
+        const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * until_rel + 3u : 0xFFFFFFFFu;
         const double mult = (MODE & MODE_TICK_MULT) ? c.tick_mult : 1.0;
         // (the run_until check, the tick_mult multiply and the global-memory level are left out when unused)
 #define CXB_MM1_SLOT_TEXT(LOAD_K, OPERANDS)                                                                    \
@@ -523,7 +615,7 @@ struct lane {
     // ---- start-up and wind-down: environment::step on the explicit two-slot heap ---------------
     template <int MODE, typename Ring>
     CXB_HD bool generic_step(const constants &c, Ring &ring) {
-        if (is_fast() || t0 == EMPTY || t0 > c.until) return false;
+        if (is_fast() || t0 == EMPTY || ((MODE & MODE_UNTIL) && t0 > until_rel)) return false;
         const uint32_t n = c.n_packets;
         if (m0 == M_PROD && i < n && i >= g) return false;  // A_{i+1} not generated yet
         const uint32_t t = t0;
@@ -531,7 +623,7 @@ struct lane {
         t0 = t1; m0 = m1; t1 = EMPTY; m1 = M_NOOP;   // pop_heap on <= 2 entries
         now = t > now ? t : now;                     // environment.ipp:126
         ++n_events;
-        hash = fold(hash, t, tag_hash_bits(m));
+        hash = fold(hash, abs_time<MODE>(t), tag_hash_bits(m));
         if (m == M_PROD) {
             // producer body, producer_consumer.cpp:31-37
             if (i < n) {
@@ -588,9 +680,10 @@ struct lane {
     }
 
     // environment::run / run_until (environment.ipp:179-196): nothing left, or nothing due.
-    CXB_HD bool finished(const constants &c) const {
+    template <int MODE>
+    CXB_HD bool finished() const {
         const uint32_t next = next_time();
-        return status != 0 || next == EMPTY || next > c.until;
+        return status != 0 || next == EMPTY || ((MODE & MODE_UNTIL) && next > until_rel);
     }
 };
 

@@ -30,6 +30,7 @@ struct mm1_fused_plan {
     bool ah_spill;              // the FIRST pass already uses the two-level ring (heavily loaded queues)
     uint32_t ah_spill_cap;      // packets the two-level ring may hold
     uint32_t ah_gring_slots;    // its slots per replication (power of two)
+    bool ah_wide;               // the clock passes 2^30 ticks: lanes keep times relative to an epoch (MODE_WIDE)
     bool ah_direct_global;
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,

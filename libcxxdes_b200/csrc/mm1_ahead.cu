@@ -75,6 +75,13 @@ struct lane_ring {
         }
         return load_shared(j);
     }
+    // rewrite entry j at the level load(j, g) reads it from (MODE_WIDE rebase)
+    __device__ __forceinline__ void store_level(uint32_t j, uint32_t g, const mm1::ring_entry &e) const {
+        if (SPILL && g - j > (uint32_t)WINDOW)
+            asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(gaddr(j)), "r"(e.ak), "r"(e.s4));
+        else
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr(j)), "r"(e.ak), "r"(e.s4));
+    }
     __device__ __forceinline__ uint32_t load_a(uint32_t j) const {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr(j)));
@@ -124,7 +131,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
     ring.base = (uint32_t)__cvta_generic_to_shared(smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS)) + threadIdx.x * 8u;
 
     mm1::lane L;
-    L.init(0);
+    L.init(0, c);
     L.idle();
     bool active = false, exhausted = false;
     uint64_t rep = 0;
@@ -151,11 +158,11 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 // (a second-pass replication starts over: phase REPLAY in its record, or no record at all)
                 const uint32_t phase = (STATE && resume && !list) ? w[0] : (uint32_t)mm1::lane::PHASE_NEW;
                 if (phase == mm1::lane::PHASE_RUNNING) {
-                    L.restore(w, grep);
-                    L.template regenerate<SPILL>(c, ring, table);
+                    L.restore(w, grep, c);
+                    L.template regenerate<MODE, SPILL>(c, ring, table);
                     active = true;
                 } else if (phase == mm1::lane::PHASE_NEW) {
-                    L.init(grep);
+                    L.init(grep, c);
                     active = true;
                 } else if (phase == mm1::lane::PHASE_REPLAY) {
                     // left the 32-bit representation in an earlier piece: the fallback kernel
@@ -182,7 +189,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 #if CXB_MM1_ORDER == 1
             want = active && L.status == 0 && L.wants_packets(c);
             room = L.template has_room<SPILL>(c);
-            L.generate_pair(c, ring, table, want & room);
+            L.template generate_pair<MODE>(c, ring, table, want & room);
 #pragma unroll
             for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);
 #elif CXB_MM1_ORDER == 2
@@ -190,7 +197,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
             for (int s = 0; s < EVENT_SLOTS / 2; ++s) L.template fast_slot<MODE>(c, ring);
             want = active && L.status == 0 && L.wants_packets(c);
             room = L.template has_room<SPILL>(c);
-            L.generate_pair(c, ring, table, want & room);
+            L.template generate_pair<MODE>(c, ring, table, want & room);
 #pragma unroll
             for (int s = EVENT_SLOTS / 2; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);
 #else
@@ -198,14 +205,14 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
             for (int s = 0; s < EVENT_SLOTS; ++s) L.template fast_slot<MODE>(c, ring);  // no-op for idle lanes
             want = active && L.status == 0 && L.wants_packets(c);
             room = L.template has_room<SPILL>(c);
-            L.generate_pair(c, ring, table, want & room);
+            L.template generate_pair<MODE>(c, ring, table, want & room);
 #endif
         }
         // (a ring that is truly exhausted stays so, checking after the last generation is enough)
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
 
         // ---- 4. end of this lane's replication? ----
-        if (active && L.finished(c)) {
+        if (active && L.template finished<MODE>()) {
             active = false;
             const uint32_t status = L.status;
             uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
@@ -216,7 +223,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 if (STATE) w[0] = mm1::lane::PHASE_REPLAY;
             } else {
                 rep_out o;
-                int64_t end = (int64_t)L.now;
+                int64_t end = (int64_t)L.template abs_time<MODE>(L.now);
                 o.status = status;
                 if (sh.run_until >= 0) {
                     if (L.next_time() != mm1::EMPTY) o.status |= CXXDES_B200_REP_UNFINISHED;
@@ -303,9 +310,14 @@ void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32
     // anyway goes to the 64-bit kernel at once (1 us precision with a 1 s unit: 272 ms instead of
     // 890 ms spent failing late in both fast passes first).
     const double expected_bound = (double)prm.n_packets * (1.0 / prm.lambda + 1.0 / prm.mu) * (double)ticks_per_unit;
-    p.ah_direct_global = tick_mult >= (1 << 23) || !mm1::draw_fits_u32(prm.lambda, (double)ticks_per_unit) ||
-                         !mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit) ||
-                         !(1.25 * expected_bound < (double)mm1::TIME_LIMIT);
+    const bool draws_fit = mm1::draw_fits_u32(prm.lambda, (double)ticks_per_unit) && mm1::draw_fits_u32(prm.mu, (double)ticks_per_unit);
+    // A clock that passes 2^30 ticks (fine time precision) is no obstacle as long as the LIVE tokens
+    // span far less: MODE_WIDE keeps 32-bit times relative to a per-lane epoch.  The live span is a
+    // window of ~64 inter-arrival / service times; 16x the mean must stay below 2^29.
+    p.ah_wide = !(1.25 * expected_bound < (double)mm1::TIME_LIMIT);
+    const double span = 64.0 * 16.0 * (1.0 / prm.lambda + 1.0 / prm.mu) * (double)ticks_per_unit;
+    p.ah_direct_global = tick_mult >= (1 << 23) || !draws_fit || (p.ah_wide && !(span < (double)mm1::REBASE_LIMIT)) ||
+                         expected_bound * (double)tick_mult >= 1e15;
 }
 
 size_t mm1_ahead_state_bytes(uint64_t n_replications) { return (size_t)n_replications * mm1::lane::STATE_WORDS * sizeof(uint32_t); }
@@ -336,14 +348,13 @@ cudaError_t configure_one() {
 }
 template <typename G>
 cudaError_t configure_geometry() {
-    cudaError_t e = configure_one<G, 0, false>();
-    if (e == cudaSuccess) e = configure_one<G, 1, false>();
-    if (e == cudaSuccess) e = configure_one<G, 2, false>();
-    if (e == cudaSuccess) e = configure_one<G, 3, false>();
-    if (e == cudaSuccess) e = configure_one<G, 0, true>();
-    if (e == cudaSuccess) e = configure_one<G, 1, true>();
-    if (e == cudaSuccess) e = configure_one<G, 2, true>();
-    if (e == cudaSuccess) e = configure_one<G, 3, true>();
+    cudaError_t e = cudaSuccess;
+#define CXB_CONFIGURE(M)                                              \
+    if (e == cudaSuccess) e = configure_one<G, M, false>();           \
+    if (e == cudaSuccess) e = configure_one<G, M, true>();
+    CXB_CONFIGURE(0) CXB_CONFIGURE(1) CXB_CONFIGURE(2) CXB_CONFIGURE(3)
+    CXB_CONFIGURE(4) CXB_CONFIGURE(5) CXB_CONFIGURE(6) CXB_CONFIGURE(7)
+#undef CXB_CONFIGURE
     return e;
 }
 template <typename G, int MODE, bool SPILL>
@@ -367,7 +378,11 @@ void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_pa
         case 0: launch_one<G, 0, SPILL>(c, prm, sh, out, plan, a, stream); break;
         case 1: launch_one<G, 1, SPILL>(c, prm, sh, out, plan, a, stream); break;
         case 2: launch_one<G, 2, SPILL>(c, prm, sh, out, plan, a, stream); break;
-        default: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 3: launch_one<G, 3, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 4: launch_one<G, 4, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 5: launch_one<G, 5, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        case 6: launch_one<G, 6, SPILL>(c, prm, sh, out, plan, a, stream); break;
+        default: launch_one<G, 7, SPILL>(c, prm, sh, out, plan, a, stream); break;
     }
 }
 }  // namespace
@@ -395,7 +410,11 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.spill_cap = plan.ah_spill_cap;
     c.lead_cap = plan.ah_lead_cap;
     c.until = (sh.run_until < 0 || sh.run_until >= (int64_t)mm1::TIME_LIMIT) ? mm1::EMPTY : (uint32_t)sh.run_until;
-    const int mode = (c.until != mm1::EMPTY ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0);
+    c.until64 = sh.run_until;
+    // (with a wide clock a horizon beyond 2^30 ticks is still a horizon: the lanes watch until64 - epoch)
+    const bool has_until = plan.ah_wide ? sh.run_until >= 0 : c.until != mm1::EMPTY;
+    const int mode = (has_until ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0) |
+                     (plan.ah_wide ? mm1::MODE_WIDE : 0);
     pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
     if (plan.ah_geometry == 1) {
         if (spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, a, stream);

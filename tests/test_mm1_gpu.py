@@ -78,6 +78,31 @@ def test_heavy_load_full_length_uses_the_second_ring_level(port):
     golden_util.assert_columns_equal(got, want, what="rho 0.95")
 
 
+@pytest.mark.parametrize("lam,n_packets", [(5.0, 12000), (9.0, 14000)])
+def test_fine_time_precision_stays_on_the_fast_kernel(port, lam, n_packets):
+    """time_unit 1 s with time_precision 1 us: the clock passes 2^30 ticks, the generate-ahead kernel
+    keeps its 32-bit times relative to a per-lane epoch (MODE_WIDE); run(), a horizon beyond 2^30 and
+    run_for pieces across the moves of the epoch all equal the oracle."""
+    clock = ((1, L.SECONDS), (1, L.MICROSECONDS))
+    oclock = abi.Clock.of(*clock)
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, _ = run_gpu(p, 256, seed=23, clock=clock)
+    want = port.run(abi.MODEL_MM1, p, oclock, 23, 0, 256, threads=oracles.os.cpu_count())
+    assert want.end_time.max() > 2 ** 30 and not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="us precision, run()")
+    got, _ = run_gpu(p, 256, seed=23, clock=clock, until=1_500_000_000, strict=False)
+    want = port.run(abi.MODEL_MM1, p, oclock, 23, 0, 256, threads=oracles.os.cpu_count(), until=1_500_000_000)
+    golden_util.assert_columns_equal(got, want, what="us precision, run_until(1.5e9)")
+    ens = L.Ensemble(p, 256, seed=23)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for _ in range(4):
+        ens.run_for(400_000_000)
+    got = ens.fetch(strict=False)
+    ens.close()
+    want = port.run(abi.MODEL_MM1, p, oclock, 23, 0, 256, threads=oracles.os.cpu_count(), until=1_600_000_000)
+    golden_util.assert_columns_equal(got, want, what="us precision, 4 x run_for(4e8)")
+
+
 def test_small_ring_takes_the_retry_path(port):
     """A 4-entry shared ring overflows in most replications: they are re-run by the global-ring
     kernel and must still match the oracle bit for bit."""

@@ -29,18 +29,18 @@ def lane_lib():
     lib = C.CDLL(str(OUT))
     lib.mm1_lane_host_run.restype = C.c_int
     lib.mm1_lane_host_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_uint64,
-                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int64,
+                                      C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_int,
                                       C.POINTER(abi.Columns), C.POINTER(C.c_uint64)]
     return lib
 
 
 def run_lanes(lib, p, n_reps, seed=0x5EED, first=0, until=-1, ring_cap=31, global_slots=0, event_slots=4,
-              clock=(1000, 1, 1e-3), general_mode=0, piece=0):
+              clock=(1000, 1, 1e-3), general_mode=0, piece=0, wide=0):
     cols = abi.HostColumns(n_reps)
     st = cols.as_struct()
     iters = C.c_uint64()
     rc = lib.mm1_lane_host_run(C.addressof(p), clock[0], clock[1], clock[2], seed, first, n_reps, until,
-                               ring_cap, global_slots, event_slots, general_mode, piece, C.byref(st), C.byref(iters))
+                               ring_cap, global_slots, event_slots, general_mode, piece, wide, C.byref(st), C.byref(iters))
     assert rc == 0
     return cols, iters.value
 
@@ -137,6 +137,35 @@ def test_lane_run_in_pieces(lane_lib, port, lam, n_packets, piece, until, slots)
     got, _ = run_lanes(lane_lib, p, 96, seed=77, until=until, piece=piece, global_slots=slots)
     want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 77, 0, 96, threads=4, until=until)
     assert masked_equal(got, want, f"pieces of {piece}").all()
+
+
+US = (1000000, 1, 1e-6)     # time_unit 1 s, time_precision 1 us, folded as ensemble.py does
+
+
+@pytest.mark.parametrize("lam,n_packets,until,piece,slots", [
+    (5.0, 12000, -1, 0, 0),               # clock ends at 2.4e9 ticks: two moves of the epoch
+    (5.0, 12000, 1500000000, 0, 0),       # horizon beyond 2^30
+    (5.0, 9000, -1, 400000000, 0),        # run_for pieces across the moves of the epoch
+    (9.0, 14000, -1, 0, 1024),            # spilling ring: entries in the second level are rebased too
+    (9.0, 14000, 1300000000, 350000000, 1024),
+    (5.0, 300, -1, 0, 0)])                # short run: wide mode without ever moving the epoch
+def test_lane_wide_clock_matches_oracle(lane_lib, port, lam, n_packets, until, piece, slots):
+    """1 us precision with a 1 s unit: the clock passes 2^30 ticks; the lane keeps its 32-bit times relative
+    to an epoch that it moves forward (MODE_WIDE) and must still match the oracle bit for bit."""
+    p = abi.MM1Params(lam, 10.0, n_packets)
+    got, _ = run_lanes(lane_lib, p, 48, seed=19, until=until, piece=piece, global_slots=slots, clock=US, wide=1)
+    want = port.run(abi.MODEL_MM1, p, abi.Clock.of((1, abi.SECONDS), (1, abi.MICROSECONDS)), 19, 0, 48,
+                    threads=oracles.os.cpu_count(), until=until)
+    assert masked_equal(got, want, "wide clock").all()
+    if until < 0 and n_packets > 5000:
+        assert want.end_time.max() > 2 ** 30
+
+
+def test_wide_mode_equals_plain_mode_on_a_small_clock(lane_lib):
+    p = abi.MM1Params(5.0, 10.0, 700)
+    a, _ = run_lanes(lane_lib, p, 64, seed=3)
+    b, _ = run_lanes(lane_lib, p, 64, seed=3, wide=1)
+    golden_util.assert_columns_equal(a, b, what="wide vs plain")
 
 
 def test_compile_time_modes_agree(lane_lib):

@@ -29,8 +29,9 @@
 // PTX text of one steady-state slot (lane::fast_slot_ptx below; the commented C++ twin is
 // lane::fast_slot).  Operands: %0 kp, %1 kc, %2 i, %3 k, %4 n_events, %5 max_queue, %6 x_tick,
 // %7 hash, %8 total_latency | %9 glim, %10 ring base, %11 sec_per_unit, %12 4*until+3,
-// %13 tick_mult, %14 slot mask (= window size), %15 slot stride in bytes | spilling ring: %16 g,
-// %17 global ring column, %18 its slot stride in bytes, %19 its slot mask.
+// %13 tick_mult, %14 slot mask (= window size), %15 slot stride in bytes, %16/%17 epoch (low/high
+// word; wide clocks) | spilling ring: %18 g, %19 global ring column, %20 its slot stride in bytes,
+// %21 its slot mask.
 //   A    front token; can the lane dispatch (pc: consumer resumes, pp: producer puts)
 //   DUE  run_until horizon
 //   B    woke?, ring[i+1].ak and ring[k], environment::step (fold) once or, when the put wakes
@@ -59,18 +60,18 @@
 #define CXB_MM1_SHIFT_MUL 0   /* x >> 2: 1 = mulhi(x, 2^30), 0 = shift */
 #endif
 #if CXB_MM1_ROT_MUL
-#define CXB_MM1_SLOT_ROT(BITS) \
+#define CXB_MM1_SLOT_ROT(TLOW, BITS) \
     "mul.wide.u32 m, hl, 32;\n\t" \
     "mov.b64 {a0, a1}, m;\n\t" \
     "mul.wide.u32 m, hh, 32;\n\t" \
     "mov.b64 {b0, b1}, m;\n\t" \
-    "lop3.b32 rl, a0, b1, t, 0x56;\n\t" \
+    "lop3.b32 rl, a0, b1, " TLOW ", 0x56;\n\t" \
     "lop3.b32 rh, b0, a1, " BITS ", 0x56;\n\t"
 #else
-#define CXB_MM1_SLOT_ROT(BITS) \
+#define CXB_MM1_SLOT_ROT(TLOW, BITS) \
     "shf.l.wrap.b32 a1, hl, hh, 5;\n\t" \
     "shf.l.wrap.b32 a0, hh, hl, 5;\n\t" \
-    "xor.b32 rl, a0, t;\n\t" \
+    "xor.b32 rl, a0, " TLOW ";\n\t" \
     "xor.b32 rh, a1, " BITS ";\n\t"
 #endif
 #if CXB_MM1_SHIFT_MUL
@@ -78,15 +79,36 @@
 #else
 #define CXB_MM1_SLOT_SHR2(PRED, DST, SRC) PRED "shr.u32 " DST ", " SRC ", 2;\n\t"
 #endif
-#define CXB_MM1_SLOT_FOLD(PRED, BITS) \
-    CXB_MM1_SLOT_ROT(BITS) \
+#define CXB_MM1_SLOT_FOLD(PRED, TLOW, BITS) \
+    CXB_MM1_SLOT_ROT(TLOW, BITS) \
     "mul.hi.u32 mh, rl, 0x7F4A7C15;\n\t" \
     "mad.lo.u32 mh, rl, 0x9E3779B9, mh;\n\t" \
     "@" PRED " mad.lo.u32 hh, rh, 0x7F4A7C15, mh;\n\t" \
     "@" PRED " mul.lo.u32 hl, rl, 0x7F4A7C15;\n\t"
-#define CXB_MM1_SLOT_B(LOAD_K) \
+/* The time of the event as the digest and now_seconds() see it: the tick itself (NARROW), or
+   epoch + tick as a 64-bit value (WIDE: fine time precision, see lane::epoch). */
+#define CXB_MM1_SLOT_TABS_NARROW ""
+#define CXB_MM1_SLOT_TABS_WIDE \
+    ".reg .b32 tl, th, bw, tsl, tsh, xl, xh;\n\t" \
+    "add.cc.u32 tl, t, %16;\n\t" \
+    "addc.u32 th, 0, %17;\n\t" \
+    "xor.b32 bw, th, 0x200;\n\t"
+#define CXB_MM1_SLOT_DTDX_NARROW \
+    "mov.b64 dt, {ts, 0x43300000};\n\t" \
+    "mov.b64 dx, {%6, 0x43300000};\n\t"
+#define CXB_MM1_SLOT_DTDX_WIDE \
+    "add.cc.u32 tsl, ts, %16;\n\t" \
+    "addc.u32 tsh, 0, %17;\n\t" \
+    "or.b32 tsh, tsh, 0x43300000;\n\t" \
+    "add.cc.u32 xl, %6, %16;\n\t" \
+    "addc.u32 xh, 0, %17;\n\t" \
+    "or.b32 xh, xh, 0x43300000;\n\t" \
+    "mov.b64 dt, {tsl, tsh};\n\t" \
+    "mov.b64 dx, {xl, xh};\n\t"
+#define CXB_MM1_SLOT_B_ANY(LOAD_K, TABS, TLOW, BH_FIX, BITS2, DTDX) \
     "setp.eq.and.u32 pw, %1, 0xffffffff, pp;\n\t" \
     CXB_MM1_SLOT_SHR2("", "t", "key") \
+    TABS \
     "add.u32 i1, %2, 1;\n\t" \
     "and.b32 sl, i1, %14;\n\t" \
     "mad.lo.u32 addr, sl, %15, %10;\n\t" \
@@ -97,14 +119,18 @@
     "or.pred pok, pc, pp;\n\t" \
     "mov.b64 {hl, hh}, %7;\n\t" \
     "selp.b32 bh, 0x200, 0x100, pc;\n\t" \
-    CXB_MM1_SLOT_FOLD("pok", "bh") \
-    CXB_MM1_SLOT_FOLD("pw", "0x200") \
+    BH_FIX \
+    CXB_MM1_SLOT_FOLD("pok", TLOW, "bh") \
+    CXB_MM1_SLOT_FOLD("pw", TLOW, BITS2) \
     "mov.b64 %7, {hl, hh};\n\t" \
     "selp.b32 ts, t, %6, pc;\n\t" \
-    "mov.b64 dt, {ts, 0x43300000};\n\t" \
-    "mov.b64 dx, {%6, 0x43300000};\n\t" \
+    DTDX \
     "sub.rn.f64 dt, dt, 0d4330000000000000;\n\t" \
     "sub.rn.f64 dx, dx, 0d4330000000000000;\n\t"
+#define CXB_MM1_SLOT_B(LOAD_K) \
+    CXB_MM1_SLOT_B_ANY(LOAD_K, CXB_MM1_SLOT_TABS_NARROW, "t", "", "0x200", CXB_MM1_SLOT_DTDX_NARROW)
+#define CXB_MM1_SLOT_B_WIDE(LOAD_K) \
+    CXB_MM1_SLOT_B_ANY(LOAD_K, CXB_MM1_SLOT_TABS_WIDE, "tl", "xor.b32 bh, bh, th;\n\t", "bw", CXB_MM1_SLOT_DTDX_WIDE)
 /* ring[k]: in the shared-memory window, or (spilling ring) in global memory once the queue is
    longer than the window: entry k is in the window iff g - k <= WINDOW */
 #define CXB_MM1_SLOT_LOAD_K "ld.shared.v2.u32 {eak, es4}, [addr];\n\t"
@@ -113,10 +139,10 @@
     ".reg .pred pin;\n\t" \
     ".reg .b32 d, gs;\n\t" \
     ".reg .b64 ga;\n\t" \
-    "sub.u32 d, %16, %3;\n\t" \
+    "sub.u32 d, %18, %3;\n\t" \
     "setp.le.u32 pin, d, %14;\n\t" \
-    "and.b32 gs, %3, %19;\n\t" \
-    "mad.wide.u32 ga, gs, %18, %17;\n\t" \
+    "and.b32 gs, %3, %21;\n\t" \
+    "mad.wide.u32 ga, gs, %20, %19;\n\t" \
     "@pin ld.shared.v2.u32 {eak, es4}, [addr];\n\t" \
     "@!pin ld.global.v2.u32 {eak, es4}, [ga];\n\t" \
     "}\n\t"
@@ -144,8 +170,15 @@
 #define CXB_MM1_SLOT_OPERANDS \
     : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
     "+l"(hash), "+d"(total_latency) \
-    : "r"(glim), "r"(base), "d"(c.sec_per_unit), "r"(ukey), "d"(mult), "n"(MASK), "n"(STRIDE)
+    : "r"(glim), "r"(base), "d"(c.sec_per_unit), "r"(ukey), "d"(mult), "n"(MASK), "n"(STRIDE), "n"(0), "n"(0)
 #define CXB_MM1_SLOT_OPERANDS_SPILL CXB_MM1_SLOT_OPERANDS, "r"(g), "l"(gbase), "r"(gstride), "r"(gmask)
+/* wide clocks: %16/%17 are the epoch (narrow: two immediates that no text refers to, so that the
+   state of a narrow lane does not carry two more live registers into every slot) */
+#define CXB_MM1_SLOT_OPERANDS_WIDE \
+    : "+r"(kp), "+r"(kc), "+r"(i), "+r"(k), "+r"(n_events), "+r"(max_queue), "+r"(x_tick), \
+    "+l"(hash), "+d"(total_latency) \
+    : "r"(glim), "r"(base), "d"(c.sec_per_unit), "r"(ukey), "d"(mult), "n"(MASK), "n"(STRIDE), "r"(ep_lo), "r"(ep_hi)
+#define CXB_MM1_SLOT_OPERANDS_WIDE_SPILL CXB_MM1_SLOT_OPERANDS_WIDE, "r"(g), "l"(gbase), "r"(gstride), "r"(gmask)
 
 namespace cxb {
 
@@ -330,7 +363,7 @@ struct lane {
         // < 2^30, so no 32-bit sum or key below can wrap; otherwise the replication is redone with
         // 64-bit ticks
         uint32_t new_budget = budget + ia0 + ia1 + s0 + s1;
-        if (MODE & MODE_WIDE) {
+        if constexpr ((MODE & MODE_WIDE) != 0) {
             // relative times: move the epoch up to the oldest live time and retry (rare: once per
             // ~2^29 ticks of simulated time); only a window that itself spans 2^30 ticks is out of range
             if (enable && new_budget >= REBASE_LIMIT) {
@@ -360,6 +393,12 @@ struct lane {
     }
 
     // ---- MODE_WIDE: absolute time of a relative tick, and moving the epoch -----------------------
+    // the run_until horizon as the lane's relative ticks (EMPTY: none)
+    template <int MODE>
+    CXB_HD uint32_t horizon(const constants &c) const {
+        return (MODE & MODE_WIDE) ? until_rel : c.until;
+    }
+
     template <int MODE>
     CXB_HD uint64_t abs_time(uint32_t tick) const {
         return (MODE & MODE_WIDE) ? epoch + tick : (uint64_t)tick;
@@ -496,7 +535,7 @@ struct lane {
     template <int MODE, typename Ring>
     CXB_HD void fast_slot(const constants &c, Ring &ring) {
 #if defined(__CUDA_ARCH__)
-        if constexpr (Ring::HAS_PTX_SLOT && !(MODE & MODE_WIDE)) {   // (wide clocks run the C++ below)
+        if constexpr (Ring::HAS_PTX_SLOT) {
             fast_slot_ptx<MODE, Ring::SPILL, Ring::MASK, Ring::STRIDE>(c, ring.base, ring.gbase, ring.gstride, ring.gmask);
             return;
         }
@@ -507,7 +546,7 @@ struct lane {
         bool cons = kc < kp;
         bool put = !cons & (i < glim);
         if (MODE & MODE_UNTIL) {
-            const bool due = key <= 4u * until_rel + 3u;  // run_until stops at `until` (EMPTY wraps to all ones)
+            const bool due = key <= 4u * horizon<MODE>(c) + 3u;  // run_until stops at `until` (EMPTY wraps to all ones)
             cons &= due;
             put &= due;
         }
@@ -560,21 +599,31 @@ struct lane {
     template <int MODE, bool SPILL, int MASK, int STRIDE>
     __device__ __forceinline__ void fast_slot_ptx(const constants &c, uint32_t base, const void *gbase, uint32_t gstride,
                                                   uint32_t gmask) {
-        const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * until_rel + 3u : 0xFFFFFFFFu;
+        const uint32_t ukey = (MODE & MODE_UNTIL) ? 4u * horizon<MODE>(c) + 3u : 0xFFFFFFFFu;
         const double mult = (MODE & MODE_TICK_MULT) ? c.tick_mult : 1.0;
-        // (the run_until check, the tick_mult multiply and the global-memory level are left out when unused)
-#define CXB_MM1_SLOT_TEXT(LOAD_K, OPERANDS)                                                                    \
-        if constexpr (MODE == 0) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);          \
-        else if constexpr (MODE == MODE_UNTIL)                                                                 \
-            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);          \
-        else if constexpr (MODE == MODE_TICK_MULT)                                                             \
-            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS);         \
-        else                                                                                                   \
-            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS);
+        [[maybe_unused]] const uint32_t ep_lo = (uint32_t)epoch, ep_hi = (uint32_t)(epoch >> 32);
+        // (the run_until check, the tick_mult multiply, the epoch and the global-memory level are left out when unused)
+#define CXB_MM1_SLOT_TEXT(LOAD_K, OPERANDS, OPERANDS_WIDE)                                                         \
+        if constexpr (MODE == 0) asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);              \
+        else if constexpr (MODE == 1)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_C OPERANDS);              \
+        else if constexpr (MODE == 2)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS);             \
+        else if constexpr (MODE == 3)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS); \
+        else if constexpr (MODE == 4)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B_WIDE(LOAD_K) CXB_MM1_SLOT_C OPERANDS_WIDE);                    \
+        else if constexpr (MODE == 5)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B_WIDE(LOAD_K) CXB_MM1_SLOT_C OPERANDS_WIDE);    \
+        else if constexpr (MODE == 6)                                                                              \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_B_WIDE(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C OPERANDS_WIDE);   \
+        else                                                                                                       \
+            asm volatile(CXB_MM1_SLOT_A CXB_MM1_SLOT_DUE CXB_MM1_SLOT_B_WIDE(LOAD_K) CXB_MM1_SLOT_MULT CXB_MM1_SLOT_C  \
+                             OPERANDS_WIDE);
         if constexpr (SPILL) {
-            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K_SPILL, CXB_MM1_SLOT_OPERANDS_SPILL)
+            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K_SPILL, CXB_MM1_SLOT_OPERANDS_SPILL, CXB_MM1_SLOT_OPERANDS_WIDE_SPILL)
         } else {
-            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K, CXB_MM1_SLOT_OPERANDS)
+            CXB_MM1_SLOT_TEXT(CXB_MM1_SLOT_LOAD_K, CXB_MM1_SLOT_OPERANDS, CXB_MM1_SLOT_OPERANDS_WIDE)
         }
 #undef CXB_MM1_SLOT_TEXT
     }
@@ -615,7 +664,7 @@ struct lane {
     // ---- start-up and wind-down: environment::step on the explicit two-slot heap ---------------
     template <int MODE, typename Ring>
     CXB_HD bool generic_step(const constants &c, Ring &ring) {
-        if (is_fast() || t0 == EMPTY || ((MODE & MODE_UNTIL) && t0 > until_rel)) return false;
+        if (is_fast() || t0 == EMPTY || t0 > horizon<MODE>(c)) return false;
         const uint32_t n = c.n_packets;
         if (m0 == M_PROD && i < n && i >= g) return false;  // A_{i+1} not generated yet
         const uint32_t t = t0;
@@ -681,8 +730,11 @@ struct lane {
 
     // environment::run / run_until (environment.ipp:179-196): nothing left, or nothing due.
     template <int MODE>
-    CXB_HD bool finished() const {
+    CXB_HD bool finished(const constants &c) const {
         const uint32_t next = next_time();
+        // (narrow modes compare with the launch constant, which is EMPTY when there is no horizon:
+        // keeping until_rel out of them keeps a register out of the hot loop)
+        if (!(MODE & MODE_WIDE)) return status != 0 || next == EMPTY || next > c.until;
         return status != 0 || next == EMPTY || ((MODE & MODE_UNTIL) && next > until_rel);
     }
 };

@@ -212,7 +212,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
 
         // ---- 4. end of this lane's replication? ----
-        if (active && L.template finished<MODE>()) {
+        if (active && L.template finished<MODE>(c)) {
             active = false;
             const uint32_t status = L.status;
             uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
@@ -223,7 +223,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 if (STATE) w[0] = mm1::lane::PHASE_REPLAY;
             } else {
                 rep_out o;
-                int64_t end = (int64_t)L.template abs_time<MODE>(L.now);
+                int64_t end = (MODE & mm1::MODE_WIDE) ? (int64_t)(L.epoch + L.now) : (int64_t)L.now;
                 o.status = status;
                 if (sh.run_until >= 0) {
                     if (L.next_time() != mm1::EMPTY) o.status |= CXXDES_B200_REP_UNFINISHED;

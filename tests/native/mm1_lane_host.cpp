@@ -50,7 +50,7 @@ void run_mode(const mm1::constants &c, Ring &ring, mm1::lane &L, int event_slots
         const bool room = L.template has_room<Ring::SPILL>(c);
         L.generate_pair<MODE>(c, ring, LOG_TABLE_HOST, want && room);
         if (want && !room && L.ring_exhausted(c)) L.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
-        if (L.finished<MODE>()) break;
+        if (L.finished<MODE>(c)) break;
     }
 }
 

@@ -15,7 +15,6 @@
 // Replications the 32-bit/shared-memory representation cannot hold (queue longer than the ring,
 // ticks beyond 2^30) are appended to the retry list and redone by mm1_fused_kernel<false>.
 #include <cmath>
-#include <cstdlib>
 
 #include "device/mm1_lane.cuh"
 #include "device/models_common.cuh"
@@ -248,17 +247,15 @@ namespace {
 constexpr int AH_EVENT_SLOTS = 4;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
 
-// Launch geometries: threads per block, resident blocks per SM, window slots per replication.
-// 0 is the default; 1 exists to measure block-size sensitivity (CXXDES_B200_MM1_GEOMETRY=1).
-// (Shallower windows with more resident warps were measured slower: 16 slots x 32 warps/SM
-// 113.8 ms against 109.2 ms for 32 slots x 24 warps/SM at lambda = 1.)
+// Launch geometry: threads per block, resident blocks per SM, window slots per replication.
+// (Measured alternatives: 128-thread blocks x 6 per SM: the same time; shallower windows with more
+// resident warps, 16 slots x 32 warps/SM: 113.8 ms against 109.2 ms at lambda = 1.)
 template <int T, int B, int S>
 struct geometry {
     static constexpr int THREADS = T, MIN_BLOCKS = B, RING_SLOTS = S;
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
 };
 using geometry0 = geometry<256, 3, 32>;
-using geometry1 = geometry<128, 6, 32>;
 
 template <typename G>
 void fill_plan(mm1_fused_plan &p, int sm_count) {
@@ -271,12 +268,8 @@ void fill_plan(mm1_fused_plan &p, int sm_count) {
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                     int64_t tick_mult, int64_t ticks_per_unit) {
-    const char *env = getenv("CXXDES_B200_MM1_GEOMETRY");
-    p.ah_geometry = env ? atoi(env) : 0;
-    switch (p.ah_geometry) {
-        case 1: fill_plan<geometry1>(p, sm_count); break;
-        default: p.ah_geometry = 0; fill_plan<geometry0>(p, sm_count); break;
-    }
+    p.ah_geometry = 0;
+    fill_plan<geometry0>(p, sm_count);
     const uint32_t window = p.ah_ring_slots - 1;  // one slot holds the arrival key after the last packet
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the window also holds the packets
     // generated ahead (2 to 4).  When more than ~0.1% of the replications are expected to outgrow
@@ -388,7 +381,8 @@ void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_pa
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    return plan.ah_geometry == 1 ? configure_geometry<geometry1>() : configure_geometry<geometry0>();
+    (void)plan;
+    return configure_geometry<geometry0>();
 }
 
 // One pass of the generate-ahead kernel.  spill: with the two-level ring.  list == nullptr: the whole
@@ -416,13 +410,8 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     const int mode = (has_until ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0) |
                      (plan.ah_wide ? mm1::MODE_WIDE : 0);
     pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
-    if (plan.ah_geometry == 1) {
-        if (spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, a, stream);
-        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, a, stream);
-    } else {
-        if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
-        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
-    }
+    if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
+    else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
     return cudaGetLastError();
 }
 

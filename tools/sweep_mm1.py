@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Kernel-time sweep of the M/M/1 ensemble over launch geometries and loads (device events around the run).
+"""Kernel-time sweep of the M/M/1 ensemble over loads (device events around the run).
 
 usage: tools/sweep_mm1.py [replications] [packets]   -> one line per (geometry, lambda)
 """
@@ -12,10 +12,9 @@ import libcxxdes_b200 as L  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 packets = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
-geoms = [int(x) for x in os.environ.get("SWEEP_GEOMETRIES", "0,1,2,3").split(",")]
+geoms = [0]   # (one launch geometry is built; earlier sweeps compared several)
 lams = [float(x) for x in os.environ.get("SWEEP_LAMBDAS", "1,5").split(",")]
 for geom in geoms:
-    os.environ["CXXDES_B200_MM1_GEOMETRY"] = str(geom)
     for lam in lams:
         ens = L.Ensemble(L.MM1Params(lam, 10.0, packets), reps, seed=0x5EED)
         ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)

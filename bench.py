@@ -296,10 +296,14 @@ def run_b200(a):
     issue_peak = props.multi_processor_count * 4 * 32 * sm_max_mhz * 1e6
     issue_achieved = local_events / (kernel_avg_ms * 1e-3) * I_ALG
     traffic = None
+    measured_inst = None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("mm1_ahead_dram_bytes_per_launch" if a.kernel == "ahead" else "mm1_fused_dram_bytes_per_launch")
+            prof = json.loads(tp.read_text())
+            traffic = prof.get("mm1_ahead_dram_bytes_per_launch" if a.kernel == "ahead" else "mm1_fused_dram_bytes_per_launch")
+            if a.kernel == "ahead":
+                measured_inst = prof.get("mm1_ahead_thread_inst_per_event")
         except (ValueError, OSError):
             traffic = None
     roofline = {
@@ -309,6 +313,7 @@ def run_b200(a):
         "alg_per_unit": f"{I_ALG:.0f} thread-instructions per simulated event (DESIGN.md 5: 408 per packet pair / 5 events; "
                         f"SURVEY 8d estimated {I_ALG_SURVEY:.0f} for draw-on-demand dispatch, which this kernel undercuts)",
         "frac_with_survey_256": issue_achieved / I_ALG * I_ALG_SURVEY / issue_peak,
+        "measured_thread_inst_per_event": measured_inst,   # smsp__thread_inst_executed / events, from the committed ncu capture
         "peak_source": f"{props.multi_processor_count} SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz, {peak_src}",
         "hbm": {"achieved": R * BYTES_PER_REP / (kernel_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": R * BYTES_PER_REP / (kernel_avg_ms * 1e-3) / 1e9 / hbm_peak,

@@ -44,7 +44,11 @@ def main():
                     lines.append(f"{k:95s} {d[k]:>22s} {u[k]}")
         if events:
             try:
-                ti = float(d["smsp__thread_inst_executed.sum"]); wi = float(d["smsp__inst_executed.sum"])
+                wi = float(d["smsp__inst_executed.sum"])
+                if d.get("smsp__thread_inst_executed.sum", "") not in ("", "0"):
+                    ti = float(d["smsp__thread_inst_executed.sum"])
+                else:   # not collected by this set: warp instructions x average active lanes
+                    ti = wi * float(d["smsp__thread_inst_executed_per_inst_executed.ratio"])
                 ns = float(d["gpu__time_duration.sum"]) * {"ms": 1e6, "us": 1e3, "ns": 1.0, "s": 1e9}[u["gpu__time_duration.sum"]]
                 lines.append(f"-- derived: {ti / events:.1f} thread-inst/event, {wi * 32 / events:.1f} issued lane-slots/event, "
                              f"{events / ns:.2f} Gevents/s under ncu (cold, serialised; do not quote as a bench number)")

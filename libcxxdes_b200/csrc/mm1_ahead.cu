@@ -168,7 +168,11 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                     // replays it from tick 0 to the new horizon
                     const unsigned long long at = atomicAdd(fail_count, 1ULL);
                     fail_list[at] = (uint32_t)rep;
-                }   // PHASE_DONE: finished in an earlier piece, its row is final
+                } else if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) {
+                    // PHASE_DONE: finished in an earlier piece, its row is final -- except the clock:
+                    // run_until sets now_ = max(now_, t) even when nothing is left (environment.ipp:194)
+                    out.end_time[rep] = sh.run_until;
+                }
             }
         }
         if (!__any_sync(0xFFFFFFFFu, active)) break;

@@ -207,6 +207,21 @@ def test_time_series_from_pieces(port):
     assert abs(mean - 0.2) < 0.01 and half < 0.01
 
 
+def test_finished_replications_follow_later_horizons(port):
+    """run_until(t) sets now_ = max(now_, t) even when no event is left (environment.ipp:194): a replication
+    that finished in an earlier piece still reports the later horizon as its end time."""
+    p = abi.MM1Params(9.0, 10.0, 3)
+    ens = L.Ensemble(p, 64, seed=2)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run_for(5000)
+    ens.run_for(5000)
+    got = ens.fetch(strict=False)
+    ens.close()
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 2, 0, 64, threads=4, until=10000)
+    assert (want.end_time == 10000).all()
+    golden_util.assert_columns_equal(got, want, what="finished earlier")
+
+
 def test_reset_forgets_saved_state(port):
     p = abi.MM1Params(5.0, 10.0, 600)
     ens = L.Ensemble(p, 128, seed=8)

@@ -1,0 +1,357 @@
+// cxxdes_b200/program.hpp -- host C++ builder for process programs (cxxdes_b200_program).
+//
+// A libcxxdes model is a set of coroutine bodies made of `co_await <awaitable>` statements.  A model that
+// has no hand-written kernel is handed to the B200 engine as a *process program*: the same bodies, written
+// once more as calls on a `body` object -- one call per co_await, with the reference's own names for the
+// awaitables -- and interpreted on the device for every replication (csrc/program_kernel.cu).
+//
+//     reference (examples/producer_consumer.cpp:31-58)        this header
+//     -----------------------------------------------        -----------------------------------------------
+//     sync::queue<double> q;                                  auto q = prog.queue();
+//     coroutine<> producer() {                                prog.body(producer, [&](body &co) {
+//       for (i = 0; i < n_packets; ++i) {                       co.loop(n_packets, [&] {
+//         co_await q.put(now_seconds());                          co.await(q.put());
+//         co_await env.timeout(lambda()); } }                     co.await(env_timeout(exponential(lam))); }); });
+//     coroutine<> co_main() {                                 prog.body(co_main, [&](body &co) {
+//       co_await (producer() && consumer()); }                  co.await(producer && consumer); });
+//
+// `program` only records; nothing here runs a simulation on the host (there is no CPU path).  Give the
+// program to ensemble<models::process_program> (ensemble.hpp) to run it.  Errors are std::runtime_error /
+// std::invalid_argument as in the reference (environment.ipp:44-45).  Header-only, C++17, plain g++.
+#pragma once
+#include <cstring>
+#include <initializer_list>
+#include <limits>
+#include <utility>
+
+#include "cxxdes_b200/ensemble.hpp"
+
+namespace cxxdes {
+namespace b200 {
+
+// priority_consts::inherit (defs.ipp:31-40): "take the priority of the awaiting process"
+constexpr priority_type inherit = std::numeric_limits<priority_type>::max();
+
+class program;
+class body;
+
+namespace detail {
+inline std::int32_t prio32(priority_type p) {
+    if (p == inherit) return CXXDES_B200_INHERIT;
+    if (p < std::numeric_limits<std::int32_t>::min() || p >= CXXDES_B200_INHERIT)
+        throw std::invalid_argument("cxxdes_b200: explicit awaitable priorities must fit 32 bits");
+    return (std::int32_t)p;
+}
+}  // namespace detail
+
+// ---- awaitable descriptors (what the reference's factory functions return) ----------------------------
+struct delay_t {  // delay(t) / timeout(t) / yield(): timeout.ipp:106-143,180-182
+    time_integral ticks;
+    priority_type prio = inherit;
+    delay_t priority(priority_type p) const { return {ticks, p}; }
+};
+struct until_t {  // until(t): timeout.ipp:14-29
+    time_integral ticks;
+    priority_type prio = inherit;
+    until_t priority(priority_type p) const { return {ticks, p}; }
+};
+inline delay_t delay(time_integral ticks) { return {ticks}; }
+inline delay_t timeout(time_integral ticks) { return {ticks}; }
+inline delay_t yield() { return {0}; }
+inline until_t until(time_integral ticks) { return {ticks}; }
+
+struct exponential {  // examples/random_variable.hpp:17-40, drawn from the Philox stream of the awaiting process
+    double rate;
+};
+struct env_timeout_t {  // env.timeout(double seconds) / env.timeout(random variable): timeout.ipp:184-187
+    bool random;
+    double value;
+};
+inline env_timeout_t env_timeout(double seconds) { return {false, seconds}; }
+inline env_timeout_t env_timeout(exponential rv) { return {true, rv.rate}; }
+
+struct process {  // a coroutine<> object of the model
+    std::uint32_t id;
+};
+struct async_t {  // async(p): async.ipp:9-49
+    process p;
+};
+inline async_t async(process p) { return {p}; }
+
+struct child {  // an operand of all_of / any_of / && / ||
+    enum kind_t { PROC, DELAY, UNTIL } kind;
+    std::uint32_t proc;
+    time_integral ticks;
+    priority_type prio;
+    child(process p) : kind(PROC), proc(p.id), ticks(0), prio(inherit) {}
+    child(delay_t d) : kind(DELAY), proc(0), ticks(d.ticks), prio(d.prio) {}
+    child(until_t u) : kind(UNTIL), proc(0), ticks(u.ticks), prio(u.prio) {}
+};
+struct composition {  // any_of.ipp:233-247; compositions.ipp (operator&&, operator||)
+    bool all;
+    std::vector<child> children;
+};
+template <typename... C>
+composition all_of(C... c) { return {true, {child(c)...}}; }
+template <typename... C>
+composition any_of(C... c) { return {false, {child(c)...}}; }
+inline composition all_of_range(const std::vector<process> &ps) {  // all_of.range(first, last)
+    composition c{true, {}};
+    for (process p : ps) c.children.emplace_back(p);
+    return c;
+}
+inline composition any_of_range(const std::vector<process> &ps) {
+    composition c{false, {}};
+    for (process p : ps) c.children.emplace_back(p);
+    return c;
+}
+// a && b, a || b: flat n-ary like the reference's operator overloads
+inline composition operator&&(child a, child b) { return {true, {a, b}}; }
+inline composition operator||(child a, child b) { return {false, {a, b}}; }
+inline composition operator&&(composition a, child b) {
+    if (!a.all) throw std::invalid_argument("cxxdes_b200: nested compositions are not supported; use a helper process");
+    a.children.push_back(b);
+    return a;
+}
+inline composition operator||(composition a, child b) {
+    if (a.all) throw std::invalid_argument("cxxdes_b200: nested compositions are not supported; use a helper process");
+    a.children.push_back(b);
+    return a;
+}
+
+// sync objects hand out awaitable descriptors the way sync::queue / semaphore / mutex / event do
+struct simple_op {
+    std::uint16_t code, a;
+    std::int32_t b;
+    std::int64_t imm;
+};
+struct queue {  // sync::queue<T>: sync/queue.hpp:38-90
+    std::uint16_t id;
+    simple_op put() const { return {CXXDES_B200_OP_Q_PUT, id, 0, 0}; }           // q.put(now)
+    simple_op put_register() const { return {CXXDES_B200_OP_Q_PUT, id, 1, 0}; }  // q.put(<process register>)
+    simple_op pop() const { return {CXXDES_B200_OP_Q_POP, id, 0, 0}; }           // register = q.pop()
+};
+struct semaphore {  // sync::semaphore: sync/semaphore.hpp:58-78
+    std::uint16_t id;
+    simple_op up() const { return {CXXDES_B200_OP_SEM_UP, id, 0, 0}; }
+    simple_op down() const { return {CXXDES_B200_OP_SEM_DOWN, id, 0, 0}; }
+};
+struct resource {  // sync::resource{count}: acquire = down, handle.release = up (sync/resource.hpp:37-100)
+    std::uint16_t id;
+    simple_op acquire() const { return {CXXDES_B200_OP_SEM_DOWN, id, 0, 0}; }
+    simple_op release() const { return {CXXDES_B200_OP_SEM_UP, id, 0, 0}; }
+};
+struct mutex {  // sync::mutex: sync/mutex.hpp:31-109
+    std::uint16_t id;
+    simple_op acquire() const { return {CXXDES_B200_OP_MTX_ACQUIRE, id, 0, 0}; }
+    simple_op release() const { return {CXXDES_B200_OP_MTX_RELEASE, id, 0, 0}; }
+};
+struct event {  // sync::event: sync/event.hpp:87-139
+    std::uint16_t id;
+    simple_op wait(time_integral latency = 0, priority_type prio = inherit) const {
+        return {CXXDES_B200_OP_EV_WAIT, id, detail::prio32(prio), latency};
+    }
+    simple_op wake() const { return {CXXDES_B200_OP_EV_WAKE, id, 0, 0}; }
+};
+
+// ---- the program ---------------------------------------------------------------------------------------
+class program {
+public:
+    struct options {  // coroutine<>::priority / latency / return_latency / return_priority (coroutine.ipp:106-176)
+        priority_type priority = inherit;
+        time_integral latency = 0;
+        time_integral return_latency = 0;
+        priority_type return_priority = inherit;
+    };
+
+    // A coroutine<> object.  `ordinal` names it in the trace digest and selects its Philox stream.
+    process add_process(std::uint32_t ordinal, options o) {
+        procs_.push_back({NO_ENTRY, ordinal, o.priority, o.latency, o.return_latency, o.return_priority});
+        return {(std::uint32_t)procs_.size() - 1};
+    }
+    process add_process(std::uint32_t ordinal) { return add_process(ordinal, options{}); }
+    process add_process(std::uint32_t ordinal, priority_type priority) {
+        options o;
+        o.priority = priority;
+        return add_process(ordinal, o);
+    }
+    // env.bind(p): simulation<> binds co_main; several roots are allowed (examples/clocks.cpp)
+    void bind(process p) { roots_.push_back(p.id); }
+
+    queue add_queue(std::uint64_t max_size = 0) {
+        queue_max_.push_back(max_size);
+        return {(std::uint16_t)(queue_max_.size() - 1)};
+    }
+    semaphore add_semaphore(std::uint64_t value = 0, std::uint64_t max = std::numeric_limits<std::uint64_t>::max()) {
+        sem_init_.push_back(value);
+        sem_max_.push_back(max);
+        return {(std::uint16_t)(sem_init_.size() - 1)};
+    }
+    resource add_resource(std::uint64_t count) { return {add_semaphore(count, count).id}; }
+    mutex add_mutex() { return {(std::uint16_t)n_mutexes_++}; }
+    event add_event() { return {(std::uint16_t)n_events_++}; }
+
+    // Define the body of process p: `fn(body &)` issues the co_await statements in order; co_return is implied.
+    template <typename F>
+    void body_of(process p, F &&fn);
+
+    // The C-ABI view (pointers into this object: keep it alive and unmodified while the view is in use).
+    cxxdes_b200_program c_struct() const {
+        for (std::size_t i = 0; i < procs_.size(); ++i)
+            if (procs_[i].entry == NO_ENTRY)
+                throw std::runtime_error("cxxdes_b200: process " + std::to_string(i) + " has no body");
+        if (roots_.empty()) throw std::runtime_error("cxxdes_b200: no process bound to the environment (program::bind)");
+        cxxdes_b200_program p{};
+        p.ops = ops_.data();
+        p.procs = procs_.data();
+        p.roots = roots_.data();
+        p.queue_max = queue_max_.empty() ? &zero_ : queue_max_.data();
+        p.sem_init = sem_init_.empty() ? &zero_ : sem_init_.data();
+        p.sem_max = sem_max_.empty() ? &zero_ : sem_max_.data();
+        p.rates = rates_.empty() ? &zero_rate_ : rates_.data();
+        p.n_ops = (std::uint32_t)ops_.size();
+        p.n_procs = (std::uint32_t)procs_.size();
+        p.n_roots = (std::uint32_t)roots_.size();
+        p.n_queues = (std::uint32_t)queue_max_.size();
+        p.n_sems = (std::uint32_t)sem_init_.size();
+        p.n_mutexes = n_mutexes_;
+        p.n_events = n_events_;
+        p.n_rates = (std::uint32_t)rates_.size();
+        return p;
+    }
+
+    const std::vector<cxxdes_b200_op> &ops() const { return ops_; }
+    const std::vector<cxxdes_b200_process> &processes() const { return procs_; }
+
+private:
+    friend class body;
+    static constexpr std::uint32_t NO_ENTRY = 0xFFFFFFFFu;
+    std::uint32_t emit(std::uint16_t code, std::uint16_t a = 0, std::int32_t b = 0, std::int64_t imm = 0) {
+        ops_.push_back({code, a, b, imm});
+        return (std::uint32_t)ops_.size() - 1;
+    }
+    std::uint16_t rate(double value) {
+        rates_.push_back(value);
+        return (std::uint16_t)(rates_.size() - 1);
+    }
+    std::vector<cxxdes_b200_op> ops_;
+    std::vector<cxxdes_b200_process> procs_;
+    std::vector<std::uint32_t> roots_;
+    std::vector<std::uint64_t> queue_max_, sem_init_, sem_max_;
+    std::vector<double> rates_;
+    std::uint32_t n_mutexes_ = 0, n_events_ = 0;
+    std::uint64_t zero_ = 0;
+    double zero_rate_ = 0.0;
+};
+
+// One coroutine body being written.  Every await() is one `co_await` of the reference.
+class body {
+public:
+    body &await(delay_t d) {  // co_await delay(t) / timeout(t) / yield()
+        prog_.emit(CXXDES_B200_OP_DELAY, 0, detail::prio32(d.prio), d.ticks);
+        return *this;
+    }
+    body &await(until_t u) {  // co_await until(t)
+        prog_.emit(CXXDES_B200_OP_UNTIL, 0, detail::prio32(u.prio), u.ticks);
+        return *this;
+    }
+    body &await(env_timeout_t t) {  // co_await env.timeout(x)
+        if (t.random) {
+            prog_.emit(CXXDES_B200_OP_DELAY_EXP, prog_.rate(t.value), CXXDES_B200_INHERIT, 0);
+        } else {
+            std::int64_t bits;
+            std::memcpy(&bits, &t.value, sizeof bits);
+            prog_.emit(CXXDES_B200_OP_DELAY_REAL, 0, CXXDES_B200_INHERIT, bits);
+        }
+        return *this;
+    }
+    body &await(process p) {  // co_await p
+        prog_.emit(CXXDES_B200_OP_AWAIT, (std::uint16_t)p.id);
+        return *this;
+    }
+    body &await(async_t a) {  // co_await async(p)
+        prog_.emit(CXXDES_B200_OP_ASYNC, (std::uint16_t)a.p.id);
+        return *this;
+    }
+    body &await(const composition &c) {  // co_await all_of(...) / any_of(...) / (a && b) / (a || b)
+        if (c.children.empty() || c.children.size() > 32)
+            throw std::invalid_argument("cxxdes_b200: a composition takes 1..32 children");
+        prog_.emit(c.all ? CXXDES_B200_OP_ALL_OF : CXXDES_B200_OP_ANY_OF, (std::uint16_t)c.children.size());
+        for (const child &ch : c.children) {
+            if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);
+            else
+                prog_.emit(ch.kind == child::DELAY ? CXXDES_B200_OP_CHILD_DELAY : CXXDES_B200_OP_CHILD_UNTIL, 0,
+                           detail::prio32(ch.prio), ch.ticks);
+        }
+        return *this;
+    }
+    body &await(simple_op op) {  // co_await q.put(..) / q.pop() / sem.up() / mtx.acquire() / evt.wait() ...
+        prog_.emit(op.code, op.a, op.b, op.imm);
+        return *this;
+    }
+
+    // for (k = 0; k < count; ++k) { fn(); }   (at most two levels deep per process)
+    template <typename F>
+    body &loop(std::int64_t count, F &&fn) {
+        const std::uint32_t head = prog_.emit(CXXDES_B200_OP_LOOP, 0, 0, count);
+        fn();
+        const std::uint32_t end = prog_.emit(CXXDES_B200_OP_END_LOOP, 0, (std::int32_t)(head + 1), 0);
+        prog_.ops_[head].b = (std::int32_t)(end + 1);
+        return *this;
+    }
+
+    // the same coroutine function called again: p becomes a new, unstarted coroutine object
+    body &fresh(process p) {
+        prog_.emit(CXXDES_B200_OP_FRESH, (std::uint16_t)p.id);
+        return *this;
+    }
+    // model statistics (the plain C++ statements between the co_awaits of the examples)
+    body &set_register_now() {  // x = now()
+        prog_.emit(CXXDES_B200_OP_SET_REG_NOW);
+        return *this;
+    }
+    body &stat_seconds(int k) {  // f64[k] += now_seconds() - seconds(register): producer_consumer.cpp:52
+        prog_.emit(CXXDES_B200_OP_STAT_SECONDS, (std::uint16_t)k);
+        return *this;
+    }
+    body &stat_ticks(int k) {  // f64[k] += now() - register
+        prog_.emit(CXXDES_B200_OP_STAT_TICKS, (std::uint16_t)k);
+        return *this;
+    }
+    body &count(int k, std::int64_t amount = 1) {  // i64[k] += amount
+        prog_.emit(CXXDES_B200_OP_COUNT, (std::uint16_t)k, 0, amount);
+        return *this;
+    }
+    body &mark(std::int64_t scale, std::int32_t tag) {  // an observation (the prints of the examples)
+        prog_.emit(CXXDES_B200_OP_MARK, 0, tag, scale);
+        return *this;
+    }
+
+private:
+    friend class program;
+    explicit body(program &p) : prog_(p) {}
+    program &prog_;
+};
+
+template <typename F>
+void program::body_of(process p, F &&fn) {
+    if (p.id >= procs_.size()) throw std::invalid_argument("cxxdes_b200: unknown process");
+    if (procs_[p.id].entry != NO_ENTRY) throw std::runtime_error("cxxdes_b200: process body defined twice");
+    procs_[p.id].entry = (std::uint32_t)ops_.size();
+    body b(*this);
+    fn(b);
+    emit(CXXDES_B200_OP_RETURN);
+}
+
+namespace models {
+// Any model given as a process program; runs on the interpreter kernel.
+struct process_program {
+    static constexpr int id = CXXDES_B200_MODEL_PROGRAM;
+    using params_type = cxxdes_b200_program;
+    program prog;
+    params_type params() const { return prog.c_struct(); }
+};
+}  // namespace models
+
+}  // namespace b200
+}  // namespace cxxdes

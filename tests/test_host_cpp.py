@@ -8,11 +8,11 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def build_example(tmp_path):
-    exe = tmp_path / "mm1_ensemble"
+def build_example(tmp_path, name="mm1_ensemble"):
+    exe = tmp_path / name
     lib_dir = ROOT / "libcxxdes_b200" / "_lib"
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}",
-                    str(ROOT / "examples" / "mm1_ensemble.cpp"), f"-L{lib_dir}", "-lcxxdes_b200",
+                    str(ROOT / "examples" / f"{name}.cpp"), f"-L{lib_dir}", "-lcxxdes_b200",
                     f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
     return exe
 
@@ -40,3 +40,42 @@ def test_cpp_example_runs_on_gpu(built, tmp_path):
             assert abs(avg - 1.0 / (mu - lam)) < 0.15 / (mu - lam)   # M/M/1 sojourn time 1/(mu-lambda)
         else:
             assert avg > 0.3
+
+
+# ------------------------------------------------------------------ host C++ builder for process programs
+def _python_tables(prog):
+    prog.to_params()
+    return {"ops": [list(o) for o in prog._ops],
+            "procs": [[p["entry"], p["ordinal"], p["priority"], p["latency"], p["return_latency"], p["return_priority"]]
+                      for p in prog._procs],
+            "roots": list(prog._roots), "queue_max": list(prog._queue_max), "sems": [list(x) for x in prog._sems],
+            "rates": list(prog._rates), "n_mutexes": prog._n_mutexes, "n_events": prog._n_events}
+
+
+def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
+    """include/cxxdes_b200/program.hpp against the Python builder: the same models (M/M/1 and nine of the
+    reference's own test/example scenarios, whose Python programs are pinned on the reference engine by
+    tests/test_programs.py) must lower to identical cxxdes_b200_program tables.  Built as C++17 and C++20
+    (the reference's users compile as C++20, where `co_await` is a keyword)."""
+    import json
+    import kat_programs as K
+    src = ROOT / "tests" / "native" / "program_builder_dump.cpp"
+    subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src)], check=True)
+    exe = tmp_path / "program_builder_dump"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(src),
+                    "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0           # also: the three misuse cases threw
+    got = json.loads(r.stdout)
+    assert got.pop("mm1") == _python_tables(K.mm1_program(5.0, 10.0, 300))
+    assert sorted(got) == sorted(str(k) for k in (1, 2, 4, 5, 6, 7, 9, 10, 11))
+    for k, tables in got.items():
+        assert tables == _python_tables(K.SCENARIOS[int(k)]()[0]), K.SCENARIOS[int(k)].__name__
+
+
+@pytest.mark.gpu
+def test_cpp_program_example_matches_the_fused_kernel(built, tmp_path):
+    exe = build_example(tmp_path, "program_mm1")
+    r = subprocess.run([str(exe), "4096", "400"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "differing replications 0" in r.stdout

@@ -95,6 +95,8 @@ struct cxxdes_b200_ensemble {
     unsigned char *program_blob = nullptr;  // device copy of a process program
     uint32_t program_blob_bytes = 0;
     device_program dprog{};
+    program_fast_layout prog_fast{};        // shared-memory first pass (program_fast.cu), sized from the program
+    int64_t *prog_queue_items = nullptr;    // its queue payloads, [queue][slot][thread]
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -177,6 +179,11 @@ int upload_program(cxxdes_b200_ensemble *e) {
     delete[] host;
     if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program upload: %s", cudaGetErrorString(ce));
     e->program_blob_bytes = (uint32_t)total;
+    e->prog_fast = program_fast_plan(p, (uint32_t)total, e->smem_optin);
+    if (const size_t qb = program_fast_queue_bytes(e->prog_fast, e->sm_count)) {
+        ce = cudaMalloc(&e->prog_queue_items, qb);
+        if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program queues: %s", cudaGetErrorString(ce));
+    }
     device_program &d = e->dprog;
     d.ops = (const cxxdes_b200_op *)(e->program_blob + o_ops);
     d.procs = (const cxxdes_b200_process *)(e->program_blob + o_procs);
@@ -304,7 +311,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             break;
         case CXXDES_B200_MODEL_PROGRAM:
             CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
-                                    &launches));
+                                    &launches, e->prog_fast, e->prog_queue_items));
             break;
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);
@@ -526,6 +533,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->acc);
     cudaFree(e->reduce_scratch);
     cudaFree(e->program_blob);
+    cudaFree(e->prog_queue_items);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);

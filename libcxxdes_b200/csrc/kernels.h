@@ -83,9 +83,28 @@ struct device_program {  // cxxdes_b200_program with device pointers; rates as {
     uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
 };
 const char *program_check(const cxxdes_b200_program &p);  // nullptr when the interpreter supports it
+// First pass with the per-replication state in shared memory (program_fast.cu): word offsets sized from the program.
+struct program_fast_layout {
+    bool valid;                 // false: program_kernel.cu alone runs the program
+    int heap_cap;               // tokens a replication may have scheduled at once
+    int n_words, n_dwords;      // 32-bit / 64-bit state words per replication
+    int w_serial, w_mtx, w_handlers, w_queues, w_sems, w_procs, w_qwait, w_swait, w_mwait, w_ewait;
+    int pw, o_draws, o_loop, loop_words;      // words per process, offsets of the optional ones
+    int wait_cap, wait_words, ewait_words;    // wait lists: count word + entries
+    int d_regs;                 // first 64-bit word of the per-process registers
+    uint32_t staged_bytes;      // program text staged into shared memory
+    size_t smem_bytes;
+    int blocks_per_sm;
+    size_t queue_item_bytes_per_thread;
+};
+program_fast_layout program_fast_plan(const cxxdes_b200_program &host_program, uint32_t blob_bytes, size_t smem_optin);
+size_t program_fast_queue_bytes(const program_fast_layout &L, int sm_count);
+cudaError_t launch_program_fast(const device_program &prg, const program_fast_layout &L, const shard &sh,
+                                const device_columns &out, int64_t *queue_items, int sm_count, cudaStream_t stream);
 // blob_bytes: size of the contiguous device copy of the program that starts at prg.ops
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
-                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches);
+                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
+                           const program_fast_layout &fast, int64_t *queue_items);
 
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);

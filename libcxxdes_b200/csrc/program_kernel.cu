@@ -554,7 +554,8 @@ size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
 }  // namespace
 
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
-                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches) {
+                           int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
+                           const program_fast_layout &fast, int64_t *queue_items) {
     const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
     int small = 2 * (int)prg.n_procs + 8;
     if (small > PRG_HEAP) small = PRG_HEAP;
@@ -574,6 +575,13 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
         ++*launches;
         return cudaGetLastError();
     };
+    if (fast.valid) {
+        // shared-memory interpreter first (program_fast.cu); what its layout cannot hold comes back on the retry list
+        cudaError_t ef = launch_program_fast(prg, fast, sh, out, queue_items, sm_count, stream);
+        ++*launches;
+        if (ef != cudaSuccess) return ef;
+        return go(PRG_HEAP, true);
+    }
     cudaError_t e = go(small, false);
     if (e != cudaSuccess || small == PRG_HEAP) return e;
     return go(PRG_HEAP, true);   // exits at once when nothing overflowed

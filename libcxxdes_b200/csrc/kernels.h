@@ -87,6 +87,7 @@ const char *program_check(const cxxdes_b200_program &p);  // nullptr when the in
 struct program_fast_layout {
     bool valid;                 // false: program_kernel.cu alone runs the program
     int heap_cap;               // tokens a replication may have scheduled at once
+    int n_handlers;             // any_of / all_of handler pool
     int n_words, n_dwords;      // 32-bit / 64-bit state words per replication
     int w_serial, w_mtx, w_handlers, w_queues, w_sems, w_procs, w_qwait, w_swait, w_mwait, w_ewait;
     int pw, o_draws, o_loop, loop_words;      // words per process, offsets of the optional ones

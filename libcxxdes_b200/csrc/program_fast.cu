@@ -34,7 +34,7 @@ namespace cxb {
 namespace {
 
 constexpr int PF_THREADS = 128;
-constexpr int PF_HANDLERS = 8;     // live any_of/all_of handlers per replication (pool, by serial)
+constexpr int PF_HANDLERS = 8;     // at most: live any_of/all_of handlers per replication (pool, by serial)
 constexpr int PF_QUEUE_CAP = 128;  // items per queue (global memory)
 constexpr uint32_t PF_NONE = 0xFFFFFFFFu;
 constexpr int32_t INHERIT32 = INT32_MAX;
@@ -190,7 +190,7 @@ struct machine {
             env.status |= CXXDES_B200_REP_BAD_PROGRAM;
             return true;
         }
-        const int hw = L.w_handlers + (int)(serial % PF_HANDLERS);
+        const int hw = L.w_handlers + (int)(serial % (uint32_t)L.n_handlers);
         if (w(hw) & H_ARMED) env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;  // a still-armed handler would be overwritten
         w(hw) = (serial + 1) | (total << 16) | (remaining << 22) | (is_all ? H_ALL : 0u) | H_ARMED;
         const uint32_t tag = make_tag(self, serial + 1);
@@ -209,7 +209,7 @@ struct machine {
     // custom_handler::invoke, any_of.ipp:9-26
     __device__ void invoke_handler(const token &t) {
         const uint32_t hp1 = tag_handler_plus1(t.tag);
-        const int hw = L.w_handlers + (int)((hp1 - 1) % PF_HANDLERS);
+        const int hw = L.w_handlers + (int)((hp1 - 1) % (uint32_t)L.n_handlers);
         uint32_t h = w(hw);
         if ((h & 0xFFFFu) != hp1) return;  // the handler already fired and its slot was reused
         const uint32_t total = (h >> 16) & 63u;
@@ -580,7 +580,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     if (getenv("CXXDES_B200_PRG_NO_FAST")) return L;
     if (blob_bytes > 16 * 1024) return L;
     bool uses_reg = false, uses_draws = false;
-    int depth = 0, max_depth = 0, max_timers = 0;
+    int depth = 0, max_depth = 0, max_timers = 0, n_compositions = 0;
     for (uint32_t i = 0; i < p.n_ops; ++i) {
         const cxxdes_b200_op &op = p.ops[i];
         switch (op.code) {
@@ -605,6 +605,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
                 break;
             case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF: {
                 int timers = 0;
+                ++n_compositions;
                 for (uint32_t c = 1; c <= op.a && i + c < p.n_ops; ++c)
                     if (p.ops[i + c].code != CXXDES_B200_OP_CHILD_PROC) ++timers;
                 if (timers > max_timers) max_timers = timers;
@@ -623,8 +624,13 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
         if (p.sem_init[s] > 0xFFFFFFFEull) return L;
     if (p.n_mutexes > 32) return L;
 
-    L.heap_cap = (int)p.n_procs + 2 * max_timers + 4;
+    // one resume / start token per process, the roots' completion tokens, timers of compositions (live + stale)
+    L.heap_cap = (int)p.n_procs + 2 * max_timers + 2;
+    if (L.heap_cap < 4) L.heap_cap = 4;
     if (L.heap_cap > 64) L.heap_cap = 64;
+    L.n_handlers = 2 * n_compositions;   // a composition inside a loop: the previous round's handler may still be live
+    if (L.n_handlers < 1) L.n_handlers = 1;
+    if (L.n_handlers > PF_HANDLERS) L.n_handlers = PF_HANDLERS;
     L.wait_cap = (int)p.n_procs;
     L.wait_words = 1 + L.wait_cap;
     L.ewait_words = 1 + 2 * L.wait_cap;
@@ -636,7 +642,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     int w = 0;
     L.w_serial = w++;
     L.w_mtx = w++;
-    L.w_handlers = w; w += PF_HANDLERS;
+    L.w_handlers = w; w += L.n_handlers;
     L.w_queues = w; w += (int)p.n_queues;
     L.w_sems = w; w += (int)p.n_sems;
     L.w_procs = w; w += pw * (int)p.n_procs;

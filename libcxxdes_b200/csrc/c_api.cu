@@ -97,6 +97,9 @@ struct cxxdes_b200_ensemble {
     device_program dprog{};
     program_fast_layout prog_fast{};        // shared-memory first pass (program_fast.cu), sized from the program
     int64_t *prog_queue_items = nullptr;    // its queue payloads, [queue][slot][thread]
+    uint32_t *prog_state = nullptr;         // replications between run_until / run_for pieces (program_fast.cu)
+    int64_t *prog_state_queues = nullptr;
+    bool prog_state_valid = false;          // written by the previous launch of this handle
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -309,10 +312,25 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream));
             launches = 1;
             break;
-        case CXXDES_B200_MODEL_PROGRAM:
+        case CXXDES_B200_MODEL_PROGRAM: {
+            // run_until / run_for continue where the previous piece stopped (environment.ipp:190-214): the
+            // shared-memory interpreter saves what is still running at the horizon and resumes it
+            program_fast_state st{};
+            if (e->prog_fast.valid && (until >= 0 || e->prog_state_valid)) {
+                if (!e->prog_state) {
+                    CUDA_TRY(cudaMalloc(&e->prog_state, program_fast_state_words(e->prog_fast) * 4 * e->cfg.n_replications));
+                    if (const size_t qb = program_fast_state_queue_bytes(e->prog_fast, e->cfg.n_replications))
+                        CUDA_TRY(cudaMalloc(&e->prog_state_queues, qb));
+                }
+                st.words = e->prog_state;
+                st.queue_items = e->prog_state_queues;
+                st.n_replications = e->cfg.n_replications;
+                st.resume = e->prog_state_valid ? 1 : 0;
+            }
             CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
-                                    &launches, e->prog_fast, e->prog_queue_items));
+                                    &launches, e->prog_fast, e->prog_queue_items, st));
             break;
+        }
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);
     }
@@ -321,6 +339,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->timed = true;
     e->used = true;
     e->mm1_state_valid = e->mm1_state != nullptr;
+    e->prog_state_valid = e->prog_state != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -516,6 +535,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->used = false;
     e->timed = false;
     e->mm1_state_valid = false;
+    e->prog_state_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -534,6 +554,8 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->reduce_scratch);
     cudaFree(e->program_blob);
     cudaFree(e->prog_queue_items);
+    cudaFree(e->prog_state);
+    cudaFree(e->prog_state_queues);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);

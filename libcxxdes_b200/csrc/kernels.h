@@ -98,14 +98,24 @@ struct program_fast_layout {
     int blocks_per_sm;
     size_t queue_item_bytes_per_thread;
 };
+// run_until / run_for in pieces: replications saved between launches (nullptr words = the plain run() kernel)
+struct program_fast_state {
+    uint32_t *words;          // [word][replication], word 0 = phase
+    int64_t *queue_items;     // [queue][slot][replication]
+    uint64_t n_replications;
+    int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
+};
+size_t program_fast_state_words(const program_fast_layout &L);
+size_t program_fast_state_queue_bytes(const program_fast_layout &L, uint64_t n_replications);
 program_fast_layout program_fast_plan(const cxxdes_b200_program &host_program, uint32_t blob_bytes, size_t smem_optin);
 size_t program_fast_queue_bytes(const program_fast_layout &L, int sm_count);
 cudaError_t launch_program_fast(const device_program &prg, const program_fast_layout &L, const shard &sh,
-                                const device_columns &out, int64_t *queue_items, int sm_count, cudaStream_t stream);
+                                const device_columns &out, int64_t *queue_items, const program_fast_state &st,
+                                int sm_count, cudaStream_t stream);
 // blob_bytes: size of the contiguous device copy of the program that starts at prg.ops
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
                            int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
-                           const program_fast_layout &fast, int64_t *queue_items);
+                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state);
 
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "device/models_common.cuh"
+#include "device/program_tags.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -39,12 +40,14 @@ constexpr int PF_QUEUE_CAP = 128;  // items per queue (global memory)
 constexpr uint32_t PF_NONE = 0xFFFFFFFFu;
 constexpr int32_t INHERIT32 = INT32_MAX;
 constexpr int64_t INHERIT64 = INT64_MAX;
+constexpr uint32_t PF_PHASE_SAVED = 1, PF_PHASE_DONE = 2, PF_PHASE_REPLAY = 3;   // word 0 of a saved state; 0 = not started
 constexpr int PF_MAX_OPS_PER_EVENT = 100000;  // a body that never suspends (same guard as program_kernel.cu)
 
 // process word 0: pc | loop_depth << 16 | n_comp << 18 | bound << 20 | complete << 21
 constexpr uint32_t P_PC = 0xFFFFu, P_DEPTH_SHIFT = 16, P_NCOMP_SHIFT = 18, P_BOUND = 1u << 20, P_COMPLETE = 1u << 21;
-// handler word: serial+1 | total << 16 | remaining << 22 | is_all << 28 | armed << 29
-constexpr uint32_t H_ALL = 1u << 28, H_ARMED = 1u << 29;
+// handler word: serial+1 (24 bits) | remaining << 24 (6 bits) | is_all << 30 | armed << 31.  `total` is not kept:
+// a handler only exists when no child was ready, so any_of fires on the first token and all_of on the last.
+constexpr uint32_t H_SERIAL = 0xFFFFFFu, H_REM_SHIFT = 24, H_ALL = 1u << 30, H_ARMED = 1u << 31;
 
 struct machine {
     environment env;
@@ -83,7 +86,7 @@ struct machine {
             pr = inherited;
             w(b + 1) = (uint32_t)(int32_t)pr;
         }
-        env.schedule(env.now + prg.procs[p].latency, pr, make_tag(p));
+        env.schedule(env.now + prg.procs[p].latency, pr, ptag(p));
     }
 
     // coroutine::await_suspend, coroutine.ipp:194-207 (the completion token's priority and latency are
@@ -131,7 +134,7 @@ struct machine {
         if (n == 0) return;
         for (uint32_t k = 0; k < n; ++k) {
             const uint32_t p = w(list + 1 + (int)k);
-            env.schedule(env.now, prio_of(p), make_tag(p));
+            env.schedule(env.now, prio_of(p), ptag(p));
         }
         w(list) = 0;
     }
@@ -151,7 +154,7 @@ struct machine {
         for (uint32_t k = 0; k < n; ++k) {
             const uint32_t e = w(list + 1 + 2 * (int)k);
             const int64_t lat = (int64_t)(int32_t)w(list + 2 + 2 * (int)k);
-            env.schedule(env.now + lat, (int64_t)(e >> 16) - 32768, make_tag(e & 0xFFFFu));
+            env.schedule(env.now + lat, (int64_t)(e >> 16) - 32768, ptag(e & 0xFFFFu));
         }
         w(list) = 0;
     }
@@ -186,14 +189,23 @@ struct machine {
         // await_suspend: a new handler holds the output token; non-ready children in order
         const uint32_t serial = w(L.w_serial);
         w(L.w_serial) = serial + 1;
-        if (serial + 1 >= 0xFFFFu) {
+        if (serial + 1 > PTAG_MAX_SERIAL) {
             env.status |= CXXDES_B200_REP_BAD_PROGRAM;
             return true;
         }
-        const int hw = L.w_handlers + (int)(serial % (uint32_t)L.n_handlers);
-        if (w(hw) & H_ARMED) env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;  // a still-armed handler would be overwritten
-        w(hw) = (serial + 1) | (total << 16) | (remaining << 22) | (is_all ? H_ALL : 0u) | H_ARMED;
-        const uint32_t tag = make_tag(self, serial + 1);
+        // storage: any handler that has fired (its late tokens are recognised by serial, device/program_tags.cuh)
+        int hw = -1;
+        for (int k = 0; k < L.n_handlers; ++k)
+            if (!(w(L.w_handlers + k) & H_ARMED)) {
+                hw = L.w_handlers + k;
+                break;
+            }
+        if (hw < 0) {   // more live compositions than the pool holds
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return true;
+        }
+        w(hw) = (serial + 1) | (remaining << H_REM_SHIFT) | (is_all ? H_ALL : 0u) | H_ARMED;
+        const uint32_t tag = ptag(self, serial + 1);
         for (uint32_t c = 0; c < total; ++c) {
             if (ready_mask & (1u << c)) continue;
             const cxxdes_b200_op &ch = prg.ops[first_child + c];
@@ -208,16 +220,22 @@ struct machine {
 
     // custom_handler::invoke, any_of.ipp:9-26
     __device__ void invoke_handler(const token &t) {
-        const uint32_t hp1 = tag_handler_plus1(t.tag);
-        const int hw = L.w_handlers + (int)((hp1 - 1) % (uint32_t)L.n_handlers);
-        uint32_t h = w(hw);
-        if ((h & 0xFFFFu) != hp1) return;  // the handler already fired and its slot was reused
-        const uint32_t total = (h >> 16) & 63u;
-        const uint32_t remaining = ((h >> 22) & 63u) - 1u;
-        h = (h & ~(63u << 22)) | ((remaining & 63u) << 22);
-        const bool cond = (h & H_ALL) ? remaining == 0 : remaining < total;
-        if ((h & H_ARMED) && cond) {
-            env.schedule(key_time(t.key), key_prio(t.key), make_tag(tag_target(t.tag)));
+        const uint32_t hp1 = ptag_serial_plus1(t.tag);
+        int hw = -1;
+        uint32_t h = 0;
+        for (int k = 0; k < L.n_handlers; ++k) {
+            const uint32_t x = w(L.w_handlers + k);
+            if ((x & H_SERIAL) == hp1) {
+                hw = L.w_handlers + k;
+                h = x;
+            }
+        }
+        if (hw < 0 || !(h & H_ARMED)) return;  // the handler already fired (and its storage may have been reused)
+        const uint32_t remaining = ((h >> H_REM_SHIFT) & 63u) - 1u;
+        h = (h & ~(63u << H_REM_SHIFT)) | ((remaining & 63u) << H_REM_SHIFT);
+        const bool cond = (h & H_ALL) ? remaining == 0 : true;
+        if (cond) {
+            env.schedule(key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
             h &= ~H_ARMED;
         }
         w(hw) = h;
@@ -287,7 +305,7 @@ struct machine {
                 w(b) = w0;
                 bind(op.a, prio_of(p));
                 if (!(w(pbase(op.a)) & P_COMPLETE)) {
-                    register_completion(op.a, make_tag(p));
+                    register_completion(op.a, ptag(p));
                     running = false;
                 }
                 w0 = w(b);
@@ -295,7 +313,7 @@ struct machine {
             case CXXDES_B200_OP_ASYNC:
                 w(b) = w0;
                 bind(op.a, prio_of(p));
-                if (!(w(pbase(op.a)) & P_COMPLETE)) register_completion(op.a, make_tag(TAG_NO_TARGET));
+                if (!(w(pbase(op.a)) & P_COMPLETE)) register_completion(op.a, ptag(PTAG_NONE));
                 w0 = w(b);
                 break;
             case CXXDES_B200_OP_ALL_OF:
@@ -451,15 +469,87 @@ struct machine {
         for (uint32_t r = 0; r < prg.n_roots; ++r) {
             const uint32_t p = prg.roots[r];
             bind(p, 0);
-            if (!(w(pbase(p)) & P_COMPLETE)) register_completion(p, make_tag(TAG_NO_TARGET));
+            if (!(w(pbase(p)) & P_COMPLETE)) register_completion(p, ptag(PTAG_NONE));
+        }
+    }
+
+    // ---- run_until / run_for in pieces (environment.ipp:190-214): a replication that stops at the horizon
+    // with tokens still scheduled is written to global memory and the next launch continues from it.
+    // Saved state, `[word][replication]`: 8 header words {phase, heap size, now, n_events, digest}, the 32-bit
+    // state words, the 64-bit ones, the live heap entries; queue payloads `[queue][slot][replication]`.
+    __device__ __forceinline__ int heap_words_at() const { return 8 + L.n_words + 2 * L.n_dwords; }
+
+    __device__ void save(const program_fast_state &st, uint64_t rep) {
+        uint32_t *s = st.words + rep;
+        const size_t n = st.n_replications;
+        s[1 * n] = (uint32_t)env.n;
+        s[2 * n] = (uint32_t)env.now;
+        s[3 * n] = (uint32_t)((uint64_t)env.now >> 32);
+        s[4 * n] = (uint32_t)env.n_events;
+        s[5 * n] = (uint32_t)(env.n_events >> 32);
+        s[6 * n] = (uint32_t)env.hash;
+        s[7 * n] = (uint32_t)(env.hash >> 32);
+        for (int k = 0; k < L.n_words; ++k) s[(size_t)(8 + k) * n] = w(k);
+        for (int k = 0; k < L.n_dwords; ++k) {
+            const uint64_t v = d(k);
+            s[(size_t)(8 + L.n_words + 2 * k) * n] = (uint32_t)v;
+            s[(size_t)(8 + L.n_words + 2 * k + 1) * n] = (uint32_t)(v >> 32);
+        }
+        const int hw = heap_words_at();
+        for (int k = 0; k < env.n; ++k) {
+            const uint64_t key = env.hkey[k];
+            s[(size_t)(hw + 3 * k) * n] = (uint32_t)key;
+            s[(size_t)(hw + 3 * k + 1) * n] = (uint32_t)(key >> 32);
+            s[(size_t)(hw + 3 * k + 2) * n] = env.htag[k];
+        }
+        for (uint32_t q = 0; q < prg.n_queues; ++q) {
+            const uint32_t qw = w(L.w_queues + (int)q);
+            const uint32_t head = qw & 0xFFFFu, count = qw >> 16;
+            for (uint32_t k = 0; k < count; ++k) {
+                const size_t slot = (size_t)q * PF_QUEUE_CAP + (head + k) % PF_QUEUE_CAP;
+                st.queue_items[slot * n + rep] = items[slot * item_stride];
+            }
+        }
+        s[0] = PF_PHASE_SAVED;
+    }
+
+    __device__ void restore(const program_fast_state &st, uint64_t rep) {
+        const uint32_t *s = st.words + rep;
+        const size_t n = st.n_replications;
+        env.n = (int)s[1 * n];
+        env.now = (int64_t)((uint64_t)s[2 * n] | ((uint64_t)s[3 * n] << 32));
+        env.n_events = (uint64_t)s[4 * n] | ((uint64_t)s[5 * n] << 32);
+        env.hash = (uint64_t)s[6 * n] | ((uint64_t)s[7 * n] << 32);
+        env.status = 0;
+        addr.seed = sh.seed;
+        addr.replication = sh.first_replication + rep;
+        for (int k = 0; k < L.n_words; ++k) w(k) = s[(size_t)(8 + k) * n];
+        for (int k = 0; k < L.n_dwords; ++k)
+            d(k) = (uint64_t)s[(size_t)(8 + L.n_words + 2 * k) * n] | ((uint64_t)s[(size_t)(8 + L.n_words + 2 * k + 1) * n] << 32);
+        const int hw = heap_words_at();
+        for (int k = 0; k < env.n; ++k) {
+            env.hkey[k] = (uint64_t)s[(size_t)(hw + 3 * k) * n] | ((uint64_t)s[(size_t)(hw + 3 * k + 1) * n] << 32);
+            env.htag[k] = s[(size_t)(hw + 3 * k + 2) * n];
+        }
+        for (uint32_t q = 0; q < prg.n_queues; ++q) {
+            const uint32_t qw = w(L.w_queues + (int)q);
+            const uint32_t head = qw & 0xFFFFu, count = qw >> 16;
+            for (uint32_t k = 0; k < count; ++k) {
+                const size_t slot = (size_t)q * PF_QUEUE_CAP + (head + k) % PF_QUEUE_CAP;
+                items[slot * item_stride] = st.queue_items[slot * n + rep];
+            }
         }
     }
 };
 
 }  // namespace
 
+// STATEFUL: the run_until / run_for variant that keeps replications in global memory between launches (a separate
+// instantiation, so that the plain run() path carries none of it).
+template <bool STATEFUL>
 __global__ void __launch_bounds__(PF_THREADS)
-program_fast_kernel(device_program prg_in, shard sh, device_columns out, program_fast_layout L, int64_t *queue_items) {
+program_fast_kernel(device_program prg_in, shard sh, device_columns out, program_fast_layout L, int64_t *queue_items,
+                    program_fast_state st) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -499,7 +589,22 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
     for (;;) {
         if (!active) {
             if (!steal(sh, rep)) break;
-            m.start(rep);
+            if (STATEFUL) {
+                const uint32_t phase = st.resume ? st.words[rep] : 0u;
+                if (phase == PF_PHASE_DONE) {   // finished in an earlier piece: now_ = max(now_, t), environment.ipp:194
+                    if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) out.end_time[rep] = sh.run_until;
+                    continue;
+                }
+                if (phase == PF_PHASE_REPLAY) {   // left this layout earlier: the full-size kernel replays it from tick 0
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                    continue;
+                }
+                if (phase == PF_PHASE_SAVED) m.restore(st, rep);
+                else m.start(rep);
+            } else {
+                m.start(rep);
+            }
             active = true;
         }
         const bool more = !env.status && env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until);
@@ -507,10 +612,15 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
             if (env.status) {   // this layout could not hold the replication: the full-size kernel redoes it
                 const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
                 sh.retry_list[at] = (uint32_t)rep;
+                if (STATEFUL) st.words[rep] = PF_PHASE_REPLAY;
             } else {
                 if (sh.run_until >= 0) {
                     if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
                     env.now = env.now > sh.run_until ? env.now : sh.run_until;
+                }
+                if (STATEFUL) {
+                    if (env.status & CXXDES_B200_REP_UNFINISHED) m.save(st, rep);
+                    else st.words[rep] = PF_PHASE_DONE;
                 }
                 rep_out o;
                 o.end_time = env.now;
@@ -529,16 +639,16 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
         const int64_t time = key_time(t.key);
         env.now = time > env.now ? time : env.now;
         ++env.n_events;
-        const uint32_t target = tag_target(t.tag);
-        const uint32_t hp1 = tag_handler_plus1(t.tag);
-        const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != TAG_NO_TARGET ? TOKEN_RESUME : TOKEN_NOOP);
-        const uint32_t ordinal = target != TAG_NO_TARGET ? prg.procs[target].ordinal : PROC_NONE;
+        const uint32_t target = ptag_target(t.tag);
+        const uint32_t hp1 = ptag_serial_plus1(t.tag);
+        const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != PTAG_NONE ? TOKEN_RESUME : TOKEN_NOOP);
+        const uint32_t ordinal = target != PTAG_NONE ? prg.procs[target].ordinal : PROC_NONE;
         env.hash = trace_hash_step(env.hash, time, key_prio(t.key), kind, ordinal);
         machine::timer_note timer;
         timer.kind = 0;
         if (hp1) {
             m.invoke_handler(t);
-        } else if (target != TAG_NO_TARGET) {
+        } else if (target != PTAG_NONE) {
             // coroutine_data::resume: run the body until it suspends or returns
             const int b = m.pbase(target);
             uint32_t w0 = m.w(b);
@@ -568,7 +678,7 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
                 }
                 ticks = real_to_sim(v, sh.clk);
             }
-            env.schedule(env.now + ticks, timer.prio, make_tag(target));
+            env.schedule(env.now + ticks, timer.prio, ptag(target));
         }
     }
 }
@@ -628,7 +738,8 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     L.heap_cap = (int)p.n_procs + 2 * max_timers + 2;
     if (L.heap_cap < 4) L.heap_cap = 4;
     if (L.heap_cap > 64) L.heap_cap = 64;
-    L.n_handlers = 2 * n_compositions;   // a composition inside a loop: the previous round's handler may still be live
+    // a process waits in one composition at a time, and a handler that has fired gives its storage back at once
+    L.n_handlers = n_compositions < (int)p.n_procs ? n_compositions : (int)p.n_procs;
     if (L.n_handlers < 1) L.n_handlers = 1;
     if (L.n_handlers > PF_HANDLERS) L.n_handlers = PF_HANDLERS;
     L.wait_cap = (int)p.n_procs;
@@ -673,12 +784,23 @@ size_t program_fast_queue_bytes(const program_fast_layout &L, int sm_count) {
     return L.queue_item_bytes_per_thread * (size_t)sm_count * L.blocks_per_sm * PF_THREADS;
 }
 
+size_t program_fast_state_words(const program_fast_layout &L) {
+    return 8 + (size_t)L.n_words + 2 * (size_t)L.n_dwords + 3 * (size_t)L.heap_cap;
+}
+size_t program_fast_state_queue_bytes(const program_fast_layout &L, uint64_t n_replications) {
+    return L.queue_item_bytes_per_thread * n_replications;
+}
+
 cudaError_t launch_program_fast(const device_program &prg, const program_fast_layout &L, const shard &sh,
-                                const device_columns &out, int64_t *queue_items, int sm_count, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(program_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
-    if (e != cudaSuccess) return e;
-    program_fast_kernel<<<sm_count * L.blocks_per_sm, PF_THREADS, L.smem_bytes, stream>>>(prg, sh, out, L, queue_items);
-    return cudaGetLastError();
+                                const device_columns &out, int64_t *queue_items, const program_fast_state &st,
+                                int sm_count, cudaStream_t stream) {
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kernel<<<sm_count * L.blocks_per_sm, PF_THREADS, L.smem_bytes, stream>>>(prg, sh, out, L, queue_items, st);
+        return cudaGetLastError();
+    };
+    return st.words ? go(program_fast_kernel<true>) : go(program_fast_kernel<false>);
 }
 
 }  // namespace cxb

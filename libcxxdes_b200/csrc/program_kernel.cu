@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "device/models_common.cuh"
+#include "device/program_tags.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -91,7 +92,7 @@ struct interp {
         if (r.bound) return;
         r.bound = true;
         if (r.prio == INHERIT64) r.prio = inherited;
-        env.schedule(env.now + prg.procs[p].latency, r.prio, make_tag(p));
+        env.schedule(env.now + prg.procs[p].latency, r.prio, ptag(p));
     }
 
     // coroutine::await_suspend, coroutine.ipp:194-207
@@ -129,7 +130,7 @@ struct interp {
 
     // wake_awaitable::await_ready, event.hpp:125-134
     __device__ void wake(waiters_rt &w) {
-        for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], make_tag(w.who[k]));
+        for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], ptag(w.who[k]));
         w.n = 0;
     }
 
@@ -166,12 +167,22 @@ struct interp {
         if (is_all ? remaining == 0 : remaining < total) return false;
         // await_suspend: output token {0, priority, self} held by a new handler; non-ready children in order
         const uint32_t serial = next_serial++;
-        if (serial + 1 >= 0xFFFFu) {
+        if (serial + 1 > PTAG_MAX_SERIAL) {
             env.status |= CXXDES_B200_REP_BAD_PROGRAM;
             return true;
         }
-        handler_rt &h = handlers[serial % PRG_HANDLERS];
-        if (h.armed) env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;  // a still-armed handler would be overwritten
+        // storage: any handler that has fired (its late tokens are recognised by serial, device/program_tags.cuh)
+        int slot = -1;
+        for (int k = 0; k < PRG_HANDLERS; ++k)
+            if (!handlers[k].armed) {
+                slot = k;
+                break;
+            }
+        if (slot < 0) {   // more live compositions than the pool holds
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return true;
+        }
+        handler_rt &h = handlers[slot];
         h.serial_plus1 = serial + 1;
         h.total = total;
         h.remaining = remaining;
@@ -180,7 +191,7 @@ struct interp {
         for (uint32_t c = 0; c < total; ++c) {
             if (ready_mask & (1u << c)) continue;
             const cxxdes_b200_op &ch = prg.ops[first_child + c];
-            const uint32_t tag = make_tag(self_id, serial + 1);
+            const uint32_t tag = ptag(self_id, serial + 1);
             if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
             else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) env.schedule(env.now + ch.imm, op_priority(ch, self), tag);
             else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) env.schedule(ch.imm, op_priority(ch, self), tag);
@@ -191,13 +202,16 @@ struct interp {
 
     // custom_handler::invoke, any_of.ipp:9-26
     __device__ void invoke_handler(const token &t) {
-        const uint32_t hp1 = tag_handler_plus1(t.tag);
-        handler_rt &h = handlers[(hp1 - 1) % PRG_HANDLERS];
-        if (h.serial_plus1 != hp1) return;  // the handler already fired and its slot was reused: nothing left to do
+        const uint32_t hp1 = ptag_serial_plus1(t.tag);
+        int slot = -1;
+        for (int k = 0; k < PRG_HANDLERS; ++k)
+            if (handlers[k].serial_plus1 == hp1) slot = k;
+        if (slot < 0) return;  // the handler already fired and its storage was reused: nothing left to do
+        handler_rt &h = handlers[slot];
         --h.remaining;
         const bool cond = h.is_all ? h.remaining == 0 : h.remaining < h.total;
         if (h.armed && cond) {
-            env.schedule(key_time(t.key), key_prio(t.key), make_tag(tag_target(t.tag)));
+            env.schedule(key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
             h.armed = false;
         }
     }
@@ -216,24 +230,24 @@ struct interp {
                     do_return(p);
                     return;
                 case CXXDES_B200_OP_DELAY:
-                    env.schedule(env.now + op.imm, op_priority(op, self), make_tag(p));
+                    env.schedule(env.now + op.imm, op_priority(op, self), ptag(p));
                     ++self.pc;
                     return;
                 case CXXDES_B200_OP_UNTIL:
                     ++self.pc;
                     if (env.now >= op.imm) break;
-                    env.schedule(op.imm, op_priority(op, self), make_tag(p));
+                    env.schedule(op.imm, op_priority(op, self), ptag(p));
                     return;
                 case CXXDES_B200_OP_DELAY_EXP: {
                     addr.stream = prg.procs[p].ordinal;
                     const double v = exponential(addr, (uint64_t)self.draws++, prg.rates[op.a], table);
-                    env.schedule(env.now + real_to_sim(v, sh.clk), op_priority(op, self), make_tag(p));
+                    env.schedule(env.now + real_to_sim(v, sh.clk), op_priority(op, self), ptag(p));
                     ++self.pc;
                     return;
                 }
                 case CXXDES_B200_OP_DELAY_REAL:
                     env.schedule(env.now + real_to_sim(bits_as_double((uint64_t)op.imm), sh.clk), op_priority(op, self),
-                                 make_tag(p));
+                                 ptag(p));
                     ++self.pc;
                     return;
                 case CXXDES_B200_OP_FRESH:
@@ -244,11 +258,11 @@ struct interp {
                     bind(op.a, self.prio);
                     ++self.pc;
                     if (procs[op.a].complete) break;
-                    register_completion(op.a, make_tag(p));
+                    register_completion(op.a, ptag(p));
                     return;
                 case CXXDES_B200_OP_ASYNC:
                     bind(op.a, self.prio);
-                    if (!procs[op.a].complete) register_completion(op.a, make_tag(TAG_NO_TARGET));
+                    if (!procs[op.a].complete) register_completion(op.a, ptag(PTAG_NONE));
                     ++self.pc;
                     break;
                 case CXXDES_B200_OP_ALL_OF:
@@ -447,7 +461,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
         for (uint32_t r = 0; r < prg.n_roots; ++r) {
             const uint32_t p = prg.roots[r];
             it.bind(p, 0);
-            if (!it.procs[p].complete) it.register_completion(p, make_tag(TAG_NO_TARGET));
+            if (!it.procs[p].complete) it.register_completion(p, ptag(PTAG_NONE));
         }
 
         environment &env = it.env;
@@ -457,13 +471,13 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             const int64_t time = key_time(t.key);
             env.now = time > env.now ? time : env.now;
             ++env.n_events;
-            const uint32_t target = tag_target(t.tag);
-            const uint32_t hp1 = tag_handler_plus1(t.tag);
-            const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != TAG_NO_TARGET ? TOKEN_RESUME : TOKEN_NOOP);
-            const uint32_t ordinal = target != TAG_NO_TARGET ? prg.procs[target].ordinal : PROC_NONE;
+            const uint32_t target = ptag_target(t.tag);
+            const uint32_t hp1 = ptag_serial_plus1(t.tag);
+            const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != PTAG_NONE ? TOKEN_RESUME : TOKEN_NOOP);
+            const uint32_t ordinal = target != PTAG_NONE ? prg.procs[target].ordinal : PROC_NONE;
             env.hash = trace_hash_step(env.hash, time, key_prio(t.key), kind, ordinal);
             if (hp1) it.invoke_handler(t);
-            else if (target != TAG_NO_TARGET) it.resume(target);
+            else if (target != PTAG_NONE) it.resume(target);
             if (env.status) break;
         }
         if (sh.run_until >= 0) {
@@ -555,7 +569,7 @@ size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
 
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
                            int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
-                           const program_fast_layout &fast, int64_t *queue_items) {
+                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state) {
     const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
     int small = 2 * (int)prg.n_procs + 8;
     if (small > PRG_HEAP) small = PRG_HEAP;
@@ -577,7 +591,7 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
     };
     if (fast.valid) {
         // shared-memory interpreter first (program_fast.cu); what its layout cannot hold comes back on the retry list
-        cudaError_t ef = launch_program_fast(prg, fast, sh, out, queue_items, sm_count, stream);
+        cudaError_t ef = launch_program_fast(prg, fast, sh, out, queue_items, fast_state, sm_count, stream);
         ++*launches;
         if (ef != cudaSuccess) return ef;
         return go(PRG_HEAP, true);

@@ -147,3 +147,138 @@ def test_gpu_rejects_bad_programs(built):
         b.await_(5)                            # process 5 does not exist
     with pytest.raises(L.CxxdesError):
         L.Ensemble(prog, 4).run()
+
+
+# ---------------------------------------------------------------- run_until / run_for in pieces
+def _rich_program():
+    """Every kind of state a replication can be saved with: semaphore waiters, a bounded queue with a blocked
+    producer, event waiters with latencies, armed and stale any_of handlers, loops, registers, draws."""
+    prog = L.Program()
+    res = prog.resource(2)
+    q = prog.queue(2)
+    evt = prog.event()
+    main = prog.process(0, root=True)
+    r_fast, r_slow = prog.rate(0.2), prog.rate(0.05)
+    members = []
+    for k in range(4):                                   # workers contending for the resource
+        p = prog.process(1 + k, priority=k - 1)
+        with prog.body(p) as b:
+            with b.loop(40):
+                b.delay_exp(r_fast); b.down(res); b.set_reg_now(); b.delay_exp(r_slow); b.stat_ticks(0); b.up(res); b.count(0)
+        members.append(p)
+    ticker = prog.process(10)
+    with prog.body(ticker) as b:
+        with b.loop(60):
+            b.delay(7); b.wake(evt)
+    members.append(ticker)
+    for k in range(2):                                   # event waiters, one with a wake-up latency
+        p = prog.process(11 + k)
+        with prog.body(p) as b:
+            with b.loop(25):
+                b.wait(evt, latency=3 * k, priority=-5 if k else None); b.mark(10, 1 + k)
+        members.append(p)
+    producer, consumer = prog.process(20), prog.process(21)
+    with prog.body(producer) as b:
+        with b.loop(50):
+            b.put(q); b.delay_exp(r_fast)
+    with prog.body(consumer) as b:
+        with b.loop(50):
+            b.pop(q); b.delay_exp(r_slow); b.stat_seconds(1)
+    members += [producer, consumer]
+    watch = prog.process(30)
+    with prog.body(watch) as b:
+        with b.loop(20):
+            b.any_of(L.Delay(13), L.Delay(29)); b.mark(10, 3)
+    members.append(watch)
+    with prog.body(main) as b:
+        b.all_of(*members)
+    return prog
+
+
+def _stale_timer_program():
+    """any_of(delay(1), delay(1000)) in a loop leaves 30 stale tokens scheduled: more than the shared-memory
+    interpreter's heap holds, so every replication is handed to the full-size kernel -- and stays there."""
+    prog = L.Program()
+    main = prog.process(0, root=True)
+    with prog.body(main) as b:
+        with b.loop(30):
+            b.any_of(L.Delay(1), L.Delay(1000)); b.mark(1, 0)
+    return prog
+
+
+PIECE_CASES = {
+    "mm1": (lambda: K.mm1_program(5.0, 10.0, 600), ((1, L.SECONDS), (1, L.MILLISECONDS)), 9000, 8),
+    "mm1_heavy": (lambda: K.mm1_program(9.0, 10.0, 500), ((1, L.SECONDS), (1, L.MILLISECONDS)), 5000, 12),
+    "rich": (_rich_program, ((1, 0), (1, 0)), 61, 9),
+    "rich_fine": (_rich_program, ((1, L.SECONDS), (1, L.MILLISECONDS)), 97000, 7),
+    "stale_timers": (_stale_timer_program, ((1, 0), (1, 0)), 7, 6),
+    "clocks": (lambda: K.SCENARIOS[5]()[0], ((1, 0), (1, 0)), 3, 7),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PIECE_CASES))
+def test_cpu_interpreter_pieces_are_prefixes(port, name):
+    """Oracle-side sanity for the cases below: run_until(t) columns are consistent across horizons
+    (events and clock never decrease) and the rich program exercises what it claims to."""
+    make, clock, piece, n_pieces = PIECE_CASES[name]
+    prog = make()
+    prev = None
+    for k in (1, n_pieces):
+        cols = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 31, 0, 16, until=k * piece)
+        assert (cols.end_time == k * piece).all() or name != "clocks"
+        if prev is not None:
+            assert (cols.n_events >= prev.n_events).all()
+        prev = cols
+    if name != "clocks":                                   # the last horizon still cuts replications short
+        full = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 31, 0, 16)
+        assert (full.n_events > prev.n_events).any() and not full.status.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(PIECE_CASES))
+def test_gpu_program_run_for_in_pieces_matches_oracle(port, name):
+    """run_for(piece) x n on the interpreter kernels: the shared-memory interpreter saves every replication that
+    stops at the horizon and the next launch continues from it (environment.ipp:190-214).  After every piece
+    the columns equal the oracle's run_until(k * piece); run() then finishes the replications."""
+    make, clock, piece, n_pieces = PIECE_CASES[name]
+    prog = make()
+    n_reps = 700
+    ens = L.Ensemble(prog, n_reps, seed=31)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for k in range(1, n_pieces + 1):
+        ens.run_for(piece)
+        got = ens.fetch(strict=False)
+        want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 31, 0, n_reps, threads=os.cpu_count(),
+                        until=k * piece)
+        assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+        golden_util.assert_columns_equal(got, want, what=f"{name} after piece {k}")
+    if name != "clocks":                                   # the clocks never stop
+        ens.run()
+        got = ens.fetch()
+        want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 31, 0, n_reps, threads=os.cpu_count())
+        assert not got.status.any()
+        # a replication that had finished before the last horizon T was left at now_ = T by run_until (environment.ipp:194)
+        want.end_time[:] = np.maximum(want.end_time, n_pieces * piece)
+        golden_util.assert_columns_equal(got, want, what=f"{name}: run() after the pieces")
+        ens.run_for(1000)                                  # exhausted: nothing left to run, nothing changes
+        golden_util.assert_columns_equal(ens.fetch(), want, what=f"{name}: run_for after exhaustion")
+    ens.close()
+
+
+@pytest.mark.gpu
+def test_gpu_program_pieces_finished_replications_follow_the_horizon_and_reset_starts_over(port):
+    prog = K.mm1_program(5.0, 10.0, 40)                    # ends near tick 8000; later horizons lie beyond that
+    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
+    n_reps = 300
+    ens = L.Ensemble(prog, n_reps, seed=5)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for t in (3000, 9000, 20000, 50000):
+        ens.run_until(t)
+        want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n_reps, until=t)
+        golden_util.assert_columns_equal(ens.fetch(strict=False), want, what=f"run_until({t})")
+    assert (ens.fetch(strict=False).end_time == 50000).all()
+    ens.reset()                                            # environment::reset: replications start over
+    ens.run_until(3000)
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n_reps, until=3000)
+    golden_util.assert_columns_equal(ens.fetch(strict=False), want, what="after reset")
+    ens.close()

@@ -252,13 +252,9 @@ struct machine {
     // One operation of process p (one step of coroutine_data::resume, coroutine_data.ipp:20-29).  w0 is the
     // process's word 0, kept in a register by the caller while the body runs.
     // Returns true while p keeps running, false when it suspended or returned.
-    __device__ bool exec(uint32_t p, uint32_t &w0, timer_note &timer) {
+    __device__ bool exec(uint32_t p, uint32_t &w0, timer_note &timer, int &jumps_left) {
         const int b = pbase(p);
-        const uint32_t pc = w0 & P_PC;
-        if (pc >= prg.n_ops) {
-            env.status |= CXXDES_B200_REP_BAD_PROGRAM;
-            return false;
-        }
+        const uint32_t pc = w0 & P_PC;   // in range: program_check() proves that no path runs off the end of the program
         const cxxdes_b200_op op = prg.ops[pc];
         bool running = true;
         uint32_t next_pc = pc + 1;
@@ -337,7 +333,7 @@ struct machine {
                     return false;
                 }
                 const int64_t v = op.b ? (int64_t)d(L.d_regs + (int)p) : env.now;
-                items[(size_t)(op.a * PF_QUEUE_CAP + (int)((head + count) % PF_QUEUE_CAP)) * item_stride] = v;
+                items[(uint32_t)(op.a * PF_QUEUE_CAP + (int)((head + count) % PF_QUEUE_CAP)) * item_stride] = v;
                 w(qw) = head | ((count + 1) << 16);
                 wake_plain(L.w_qwait + op.a * L.wait_words);
                 break;
@@ -350,7 +346,7 @@ struct machine {
                     wait_plain(L.w_qwait + op.a * L.wait_words, p);
                     return false;
                 }
-                d(L.d_regs + (int)p) = (uint64_t)items[(size_t)(op.a * PF_QUEUE_CAP + (int)head) * item_stride];
+                d(L.d_regs + (int)p) = (uint64_t)items[(uint32_t)(op.a * PF_QUEUE_CAP + (int)head) * item_stride];
                 head = (head + 1) % PF_QUEUE_CAP;
                 if (--count == 0) head = 0;   // an empty ring restarts at slot 0: short queues stay in one line
                 w(qw) = head | (count << 16);
@@ -419,8 +415,14 @@ struct machine {
                 const int lw = b + L.o_loop + (int)depth - 1;
                 const uint32_t left = w(lw) - 1;
                 w(lw) = left;
-                if (left > 0) next_pc = (uint32_t)op.b;
-                else w0 -= 1u << P_DEPTH_SHIFT;
+                if (left > 0) {
+                    next_pc = (uint32_t)op.b;
+                    // a body that loops without ever suspending (same guard as program_kernel.cu; only a backward
+                    // jump can keep a body running for more than n_ops operations)
+                    if (--jumps_left == 0) env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                } else {
+                    w0 -= 1u << P_DEPTH_SHIFT;
+                }
                 break;
             }
             case CXXDES_B200_OP_SET_REG_NOW:
@@ -577,6 +579,8 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
     lane_array<uint32_t> words = carve<uint32_t>(cursor, L.n_words);
 
     machine m(prg, sh, L, table);
+    hkey.stride = PF_THREADS;   // compile-time stride: heap slot addresses become shifts folded into the LDS/STS
+    htag.stride = PF_THREADS;
     m.env.init(hkey, htag, L.heap_cap);
     m.W = words.base;
     m.D = dwords.base;
@@ -652,13 +656,9 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
             // coroutine_data::resume: run the body until it suspends or returns
             const int b = m.pbase(target);
             uint32_t w0 = m.w(b);
-            int ops_left = PF_MAX_OPS_PER_EVENT;
-            while (m.exec(target, w0, timer)) {
+            int jumps_left = PF_MAX_OPS_PER_EVENT;
+            while (m.exec(target, w0, timer, jumps_left)) {
                 if (env.status) break;
-                if (--ops_left == 0) {
-                    env.status |= CXXDES_B200_REP_BAD_PROGRAM;
-                    break;
-                }
             }
             m.w(b) = w0;
         }

@@ -508,6 +508,8 @@ const char *program_check(const cxxdes_b200_program &p) {
         return "program: at most 4 sync objects of each kind";
     if (p.n_rates > 16) return "program: at most 16 rates";
     if (!p.ops || !p.procs || !p.roots) return "program: ops/procs/roots must not be NULL";
+    // no path may run off the end of the program: the last body ends with co_return, jump targets lie inside
+    if (p.ops[p.n_ops - 1].code != CXXDES_B200_OP_RETURN) return "program: the last op must be RETURN";
     for (uint32_t i = 0; i < p.n_procs; ++i) {
         if (p.procs[i].entry >= p.n_ops) return "program: process entry out of range";
         if (p.procs[i].ordinal >= 0xFFFF) return "program: ordinal must be < 0xFFFF";
@@ -522,7 +524,7 @@ const char *program_check(const cxxdes_b200_program &p) {
                 if (op.a >= p.n_procs) return "program: process operand out of range";
                 break;
             case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF:
-                if (op.a < 1 || op.a > 32 || i + op.a >= p.n_ops) return "program: bad composition";
+                if (op.a < 1 || op.a > 32 || i + op.a + 1 >= p.n_ops) return "program: bad composition";
                 for (uint32_t c = 1; c <= op.a; ++c) {
                     uint16_t cc = p.ops[i + c].code;
                     if (cc != CXXDES_B200_OP_CHILD_PROC && cc != CXXDES_B200_OP_CHILD_DELAY &&
@@ -546,7 +548,7 @@ const char *program_check(const cxxdes_b200_program &p) {
                 if (op.a >= p.n_rates) return "program: rate operand out of range";
                 break;
             case CXXDES_B200_OP_LOOP: case CXXDES_B200_OP_END_LOOP:
-                if (op.b < 0 || (uint32_t)op.b > p.n_ops) return "program: loop target out of range";
+                if (op.b < 0 || (uint32_t)op.b >= p.n_ops) return "program: loop target out of range";
                 break;
             case CXXDES_B200_OP_STAT_SECONDS: case CXXDES_B200_OP_STAT_TICKS:
                 if (op.a >= CXXDES_B200_N_F64) return "program: statistic index out of range";

@@ -334,6 +334,10 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         default:
             return fail(CXXDES_B200_ERR_INVALID, "model %d is not available in this build", e->cfg.model);
     }
+    if (until < 0 && e->horizon >= 0 && e->horizon != INT64_MAX) {   // run() after run_until(horizon)
+        CUDA_TRY(launch_clock_floor(e->cols.end_time, e->cfg.n_replications, e->horizon, e->sm_count, e->stream));
+        ++launches;
+    }
     CUDA_TRY(cudaEventRecord(e->ev_end, e->stream));
     e->launches += launches;
     e->timed = true;
@@ -434,7 +438,8 @@ int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
 }
 
 // M/M/1 on the generate-ahead kernel keeps each replication's state between calls (128 bytes per
-// replication) and continues from it, as environment::run_until does.  The other kernels replay a
+// replication) and continues from it, as environment::run_until does; so do process programs on the
+// shared-memory interpreter (program_fast.cu).  The other kernels replay a
 // replication from tick 0 up to the new target, which yields exactly the state the reference
 // reaches by continuing (every replication is a deterministic function of its seed).
 int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {

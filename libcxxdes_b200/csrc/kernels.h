@@ -123,4 +123,6 @@ cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_ac
                           void *scratch, int sm_count, cudaStream_t stream);
 
 
+cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream);
+
 }  // namespace cxb

@@ -122,4 +122,17 @@ cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_ac
     return cudaGetLastError();
 }
 
+// run() after run_until(T): the reference left every replication at now_ >= T (environment.ipp:194), and the
+// events that run() then dispatches are all later than T, so the final clock is max(natural end, T).  The
+// kernels that replay a replication from tick 0 report the natural end; this pass applies the floor.
+__global__ void clock_floor_kernel(int64_t *end_time, uint64_t n, int64_t floor) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+        if (end_time[r] < floor) end_time[r] = floor;
+}
+
+cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream) {
+    clock_floor_kernel<<<sm_count * 4, 256, 0, stream>>>(end_time, n, floor);
+    return cudaGetLastError();
+}
+
 }  // namespace cxb

@@ -93,3 +93,34 @@ def test_invalid_model_parameters(built):
         L.Ensemble(abi.MMCParams(9.0, 1.0, 0.5, 0, 0, 10), 4).run()
     with pytest.raises(L.CxxdesError):
         L.Ensemble(abi.ArchSimParams(1, 10, 16, 32, 17, 0, 10), 4).run()
+
+
+@pytest.mark.parametrize("name,fields", [
+    ("aloha", (24, 50, 0.1, 3.0, 1.0, 100.0, 0)),
+    ("mmc", (9.0, 1.0, 0.5, 8, 0, 120)),
+    ("archsim", (1, 10, 16, 32, 4, 0, 64))])
+def test_run_until_pieces_then_run(port, name, fields):
+    """The kernels that replay a replication from tick 0: run_until(t1), run_until(t2), ... equal the oracle's
+    run_until at every horizon, and a final run() leaves the clock at max(natural end, last horizon) --
+    run_until had left now_ there (environment.ipp:194) and run() only moves it forward."""
+    model, cls, fname = MODELS[name]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    n_reps = 600
+    clock = clock_pairs(g)
+    ends = port.run(model, p, clock_of(g), 77, 0, n_reps, threads=os.cpu_count()).end_time
+    horizons = (int(ends.min()) // 2, int(np.quantile(ends, 0.3)), int(np.quantile(ends, 0.7)))   # the last two straddle the ends
+    ens = L.Ensemble(p, n_reps, seed=77)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for t in horizons:
+        ens.run_until(t)
+        got = ens.fetch(strict=False)
+        want = port.run(model, p, clock_of(g), 77, 0, n_reps, threads=os.cpu_count(), until=t)
+        assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+        golden_util.assert_columns_equal(got, want, what=f"{name} run_until({t})")
+    got = ens.run().fetch()
+    want = port.run(model, p, clock_of(g), 77, 0, n_reps, threads=os.cpu_count())
+    assert (want.end_time < horizons[-1]).any() and (want.end_time > horizons[0]).any()   # the case straddles the ends
+    want.end_time[:] = np.maximum(want.end_time, horizons[-1])
+    golden_util.assert_columns_equal(got, want, what=f"{name} run() after run_until")
+    ens.close()

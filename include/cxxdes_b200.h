@@ -145,8 +145,11 @@ enum {
     CXXDES_B200_OP_STAT_SECONDS = 24,/* f64[a] += now_seconds() - seconds(reg)   (producer_consumer.cpp:52)    */
     CXXDES_B200_OP_STAT_TICKS = 25, /* f64[a] += (double)(now() - reg)                                          */
     CXXDES_B200_OP_COUNT = 26,      /* i64[a] += imm                                                             */
-    CXXDES_B200_OP_MARK = 27        /* observation point (the prints of the reference examples): ++i64[0];
+    CXXDES_B200_OP_MARK = 27,       /* observation point (the prints of the reference examples): ++i64[0];
                                        i64[1] = i64[1] * 1000003 + (now() * imm + b)   (wrapping)              */
+    CXXDES_B200_OP_LAZY_TIMEOUT = 28,/* reg = now() + imm: `auto t = co_await lazy_timeout(imm)` fixes an absolute
+                                       deadline without suspending (timeout.ipp:104-172)                        */
+    CXXDES_B200_OP_UNTIL_REG = 29   /* co_await t / co_await instant(reg): until(reg), b = priority or INHERIT    */
 };
 #define CXXDES_B200_INHERIT INT32_MAX /* priority_consts::inherit (defs.ipp:35) in the 32-bit b field */
 

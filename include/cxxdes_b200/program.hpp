@@ -3,16 +3,16 @@
 // A libcxxdes model is a set of coroutine bodies made of `co_await <awaitable>` statements.  A model that
 // has no hand-written kernel is handed to the B200 engine as a *process program*: the same bodies, written
 // once more as calls on a `body` object -- one call per co_await, with the reference's own names for the
-// awaitables -- and interpreted on the device for every replication (csrc/program_kernel.cu).
+// awaitables -- and interpreted on the device for every replication (csrc/program_fast.cu, program_kernel.cu).
 //
 //     reference (examples/producer_consumer.cpp:31-58)        this header
 //     -----------------------------------------------        -----------------------------------------------
-//     sync::queue<double> q;                                  auto q = prog.queue();
-//     coroutine<> producer() {                                prog.body(producer, [&](body &co) {
+//     sync::queue<double> q;                                  queue q = prog.add_queue();
+//     coroutine<> producer() {                                prog.body_of(producer, [&](body &co) {
 //       for (i = 0; i < n_packets; ++i) {                       co.loop(n_packets, [&] {
 //         co_await q.put(now_seconds());                          co.await(q.put());
-//         co_await env.timeout(lambda()); } }                     co.await(env_timeout(exponential(lam))); }); });
-//     coroutine<> co_main() {                                 prog.body(co_main, [&](body &co) {
+//         co_await env.timeout(lambda()); } }                     co.await(env_timeout(exponential{lam})); }); });
+//     coroutine<> co_main() {                                 prog.body_of(co_main, [&](body &co) {
 //       co_await (producer() && consumer()); }                  co.await(producer && consumer); });
 //
 // `program` only records; nothing here runs a simulation on the host (there is no CPU path).  Give the
@@ -59,6 +59,17 @@ inline delay_t delay(time_integral ticks) { return {ticks}; }
 inline delay_t timeout(time_integral ticks) { return {ticks}; }
 inline delay_t yield() { return {0}; }
 inline until_t until(time_integral ticks) { return {ticks}; }
+inline until_t instant(time_integral ticks) { return {ticks}; }  // one functor in the reference (timeout.ipp:101)
+struct lazy_timeout_t {  // lazy_timeout(t) / lazy_delay(t): timeout.ipp:104-172
+    time_integral ticks;
+};
+inline lazy_timeout_t lazy_timeout(time_integral ticks) { return {ticks}; }
+inline lazy_timeout_t lazy_delay(time_integral ticks) { return {ticks}; }
+struct lazy_instant_t {  // what `co_await lazy_timeout(t)` returned: the instant kept in the process register
+    priority_type prio = inherit;
+    lazy_instant_t priority(priority_type p) const { return {p}; }
+};
+constexpr lazy_instant_t lazy_instant{};
 
 struct exponential {  // examples/random_variable.hpp:17-40, drawn from the Philox stream of the awaiting process
     double rate;
@@ -253,6 +264,14 @@ public:
     }
     body &await(until_t u) {  // co_await until(t)
         prog_.emit(CXXDES_B200_OP_UNTIL, 0, detail::prio32(u.prio), u.ticks);
+        return *this;
+    }
+    body &await(lazy_timeout_t t) {  // auto t = co_await lazy_timeout(x): fixes the deadline now() + x, no event
+        prog_.emit(CXXDES_B200_OP_LAZY_TIMEOUT, 0, 0, t.ticks);
+        return *this;
+    }
+    body &await(lazy_instant_t t) {  // co_await t
+        prog_.emit(CXXDES_B200_OP_UNTIL_REG, 0, detail::prio32(t.prio), 0);
         return *this;
     }
     body &await(env_timeout_t t) {  // co_await env.timeout(x)

@@ -428,6 +428,19 @@ struct machine {
             case CXXDES_B200_OP_SET_REG_NOW:
                 d(L.d_regs + (int)p) = (uint64_t)env.now;
                 break;
+            case CXXDES_B200_OP_LAZY_TIMEOUT:   // timeout.ipp:106-163: the deadline is fixed, nothing is scheduled
+                d(L.d_regs + (int)p) = (uint64_t)(env.now + op.imm);
+                break;
+            case CXXDES_B200_OP_UNTIL_REG: {
+                const int64_t at = (int64_t)d(L.d_regs + (int)p);
+                if (env.now < at) {
+                    timer.kind = 1;
+                    timer.value = at - env.now;
+                    timer.prio = op_priority(op, p);
+                    running = false;
+                }
+                break;
+            }
             case CXXDES_B200_OP_STAT_SECONDS: {
                 const double x = bits_as_double(d(op.a));
                 d(op.a) = double_bits(x + (sim_to_seconds(env.now, sh.clk) - sim_to_seconds((int64_t)d(L.d_regs + (int)p), sh.clk)));
@@ -695,7 +708,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
         const cxxdes_b200_op &op = p.ops[i];
         switch (op.code) {
             case CXXDES_B200_OP_Q_POP: case CXXDES_B200_OP_SET_REG_NOW: case CXXDES_B200_OP_STAT_SECONDS:
-            case CXXDES_B200_OP_STAT_TICKS:
+            case CXXDES_B200_OP_STAT_TICKS: case CXXDES_B200_OP_LAZY_TIMEOUT: case CXXDES_B200_OP_UNTIL_REG:
                 uses_reg = true;
                 break;
             case CXXDES_B200_OP_Q_PUT:

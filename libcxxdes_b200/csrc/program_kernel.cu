@@ -364,6 +364,15 @@ struct interp {
                     self.reg = env.now;
                     ++self.pc;
                     break;
+                case CXXDES_B200_OP_LAZY_TIMEOUT:   // timeout.ipp:106-163: the deadline is fixed, nothing is scheduled
+                    self.reg = env.now + op.imm;
+                    ++self.pc;
+                    break;
+                case CXXDES_B200_OP_UNTIL_REG:
+                    ++self.pc;
+                    if (env.now >= self.reg) break;
+                    env.schedule(self.reg, op_priority(op, self), ptag(p));
+                    return;
                 case CXXDES_B200_OP_STAT_SECONDS:
                     f64[op.a] += sim_to_seconds(env.now, sh.clk) - sim_to_seconds(self.reg, sh.clk);
                     ++self.pc;
@@ -557,7 +566,7 @@ const char *program_check(const cxxdes_b200_program &p) {
                 if (op.a >= CXXDES_B200_N_I64) return "program: counter index out of range";
                 break;
             default:
-                if (op.code > CXXDES_B200_OP_MARK) return "program: unknown op code";
+                if (op.code > CXXDES_B200_OP_UNTIL_REG) return "program: unknown op code";
         }
     }
     return nullptr;

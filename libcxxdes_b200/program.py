@@ -68,6 +68,14 @@ class Body:
     def until(self, ticks, priority=None):       # co_await until(t)
         self._emit(abi.OP_UNTIL, 0, _prio32(priority), int(ticks))
 
+    instant = until                              # `instant` and `until` are one functor (timeout.ipp:101)
+
+    def lazy_timeout(self, ticks):               # auto t = co_await lazy_timeout(ticks): reg = now() + ticks, no event
+        self._emit(abi.OP_LAZY_TIMEOUT, 0, 0, int(ticks))
+
+    def await_lazy(self, priority=None):         # co_await t  (the instant the lazy_timeout returned)
+        self._emit(abi.OP_UNTIL_REG, 0, _prio32(priority), 0)
+
     def delay_exp(self, rate_index):             # co_await env.timeout(exponential(rate))
         self._emit(abi.OP_DELAY_EXP, rate_index, abi.INHERIT32, 0)
 

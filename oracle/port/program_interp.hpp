@@ -242,6 +242,18 @@ struct program_model {
                     r.reg = eng.now;
                     ++r.pc;
                     break;
+                case CXXDES_B200_OP_LAZY_TIMEOUT:   // lazy_timeout: await_bind fixes tsim = now + t, await_ready is
+                    r.reg = eng.now + op.imm;       // true (timeout.ipp:106-163): no token
+                    ++r.pc;
+                    break;
+                case CXXDES_B200_OP_UNTIL_REG: {    // co_await instant(tsim, priority): timeout_base, timeout.ipp:14-32
+                    ++r.pc;
+                    if (eng.now >= r.reg) break;
+                    int64_t pr = prio_of(op);
+                    if (pr == PRIO_INHERIT) pr = me.priority;
+                    eng.schedule(token{r.reg, pr, p, NO_HANDLER});
+                    return;
+                }
                 case CXXDES_B200_OP_STAT_SECONDS:
                     f64[op.a] += cxxdes_b200::sim_to_seconds(eng.now, clk) - cxxdes_b200::sim_to_seconds(r.reg, clk);
                     ++r.pc;

@@ -201,12 +201,12 @@ def get_environment():       # 13: examples/get_environment.cpp
     return prog, -1
 
 
-def lazy_timeout():          # 14: examples/lazy_timeout.cpp (a lazy_timeout(d) created at t is until(t + d) when awaited)
+def lazy_timeout():          # 14: examples/lazy_timeout.cpp
     prog = Program()
     main = prog.process(0, root=True)
     with prog.body(main) as b:
-        b.until(10); b.mark(1, 0)
-        b.delay(20); b.mark(1, 0); b.until(20); b.mark(1, 0)
+        b.lazy_timeout(10); b.await_lazy(); b.mark(1, 0)                       # auto t = co_await lazy_timeout(10); co_await t;
+        b.lazy_timeout(10); b.delay(20); b.mark(1, 0); b.await_lazy(); b.mark(1, 0)   # ... co_await timeout(20); co_await t;
     return prog, -1
 
 

@@ -232,6 +232,21 @@ static program clocks_example() {
     return prog;
 }
 
+// examples/lazy_timeout.cpp
+static program lazy_timeout_example() {
+    program prog;
+    process co_main = prog.add_process(0);
+    prog.bind(co_main);
+    prog.body_of(co_main, [&](body &co) {
+        co.await(lazy_timeout(10));       // auto t = co_await lazy_timeout(10_x);
+        co.await(lazy_instant).mark(1, 0);  // co_await t;
+        co.await(lazy_timeout(10));
+        co.await(timeout(20)).mark(1, 0);
+        co.await(lazy_instant).mark(1, 0);
+    });
+    return prog;
+}
+
 int main() {
     std::printf("{\n");
     dump("mm1", mm1(5.0, 10.0, 300));
@@ -243,7 +258,8 @@ int main() {
     dump("7", mutex_example());
     dump("9", queue_example());
     dump("10", event_example());
-    dump("11", debug_example(), true);
+    dump("11", debug_example());
+    dump("14", lazy_timeout_example(), true);
     std::printf("}\n");
     // error behaviour: the reference throws std::runtime_error on misuse (environment.ipp:44-45)
     int caught = 0;

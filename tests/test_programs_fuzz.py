@@ -86,6 +86,8 @@ def random_program(seed):
             budget[0] -= 1
             h = helper(depth)
             (b.await_ if rng.random() < 0.6 else b.async_)(h)
+        elif k < 0.915:
+            b.lazy_timeout(rng.randint(0, 50)); timer(b); b.await_lazy(priority=prio())
         elif k < 0.93:
             b.set_reg_now()
         elif k < 0.96:

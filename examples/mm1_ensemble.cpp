@@ -17,7 +17,7 @@ int main(int argc, char **argv) {
     const double lambda_start = 0.5, lambda_end = 10.0, mu = lambda_end;
     const int n_steps = 5;
     try {
-        std::printf("lambda, mu, rho, avg_latency (mean over %llu replications), events/s\n",
+        std::printf("lambda, mu, rho, avg_latency (mean over %llu replications), ci95, events/s\n",
                     (unsigned long long)replications);
         for (int i = 0; i < n_steps; ++i) {
             double lambda = lambda_start + (lambda_end - 0.5 - lambda_start) * i / (n_steps - 1);
@@ -26,8 +26,9 @@ int main(int argc, char **argv) {
             ens.env.time_precision(1_ms);
             ens.run();
             auto acc = ens.reduce();
-            std::printf("%.3f, %.3f, %.3f, %.6f, %.3e\n", lambda, mu, lambda / mu,
-                        acc.f64_sum[0] / (double)acc.n_replications, acc.n_events / (ens.last_run_ms() * 1e-3));
+            const estimate latency = mean_ci(acc, 0);
+            std::printf("%.3f, %.3f, %.3f, %.6f, %.6f, %.3e\n", lambda, mu, lambda / mu, latency.mean, latency.ci95,
+                        acc.n_events / (ens.last_run_ms() * 1e-3));
         }
     } catch (std::runtime_error const &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

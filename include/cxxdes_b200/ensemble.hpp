@@ -14,6 +14,7 @@
 // parse the reference headers, and does not need to see this one).  Errors follow the reference's
 // convention: std::runtime_error (environment.ipp:44-45,61-62).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -80,6 +81,21 @@ struct memory_hierarchy {  // examples/basic_arch_sim.cpp:83-109
     params_type params() const { return {l2_latency, l1_latency, l2_capacity, addr_space, n_requesters, 0, n_loads}; }
 };
 }  // namespace models
+
+// Ensemble estimate of statistic k from the reduced accumulators: mean over the replications and the half-width
+// of its 95 % normal-approximation interval (what the examples' main() would compute by looping over runs).
+struct estimate {
+    double mean, ci95;
+};
+inline estimate mean_ci(const cxxdes_b200_accumulators &acc, int k, double z = 1.959964) {
+    const double n = (double)acc.n_replications;
+    if (acc.n_replications == 0) return {0.0 / 0.0, 0.0 / 0.0};
+    const double mean = acc.f64_sum[k] / n;
+    if (acc.n_replications < 2) return {mean, 0.0 / 0.0};
+    double var = (acc.f64_sumsq[k] - n * mean * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    return {mean, z * std::sqrt(var / n)};
+}
 
 namespace detail {
 inline void check(int rc) {

@@ -54,6 +54,61 @@ def mm1_sweep_table(run_point, lambdas, mu):
     return "\n".join(lines)
 
 
+def aloha_sweep_table(columns, sweep_steps, qs=(0.05, 0.95)):
+    """The table of examples/aloha.cpp:93-109 ("G [Erlang], S [Erlang]", one row per offered load) from ONE ensemble
+    run: replication r ran load point r mod sweep_steps (cxxdes_b200_aloha_params.sweep_steps), f64[0] = S and
+    f64[1] = G as the example computes them.  Every row is the mean over the replications of its load point, with
+    the half-width of the 95 % interval and two quantiles of S next to it."""
+    S, G = np.asarray(columns.f64[0]), np.asarray(columns.f64[1])
+    lines = ["G [Erlang], S [Erlang], ci95, " + ", ".join(f"q{int(round(100 * q)):02d}" for q in qs) + ", replications"]
+    for step in range(sweep_steps):
+        sel = np.arange(len(S)) % sweep_steps == step
+        if not sel.any():
+            continue
+        s = S[sel]
+        half = 1.959964 * s.std(ddof=1) / math.sqrt(len(s)) if len(s) > 1 else float("nan")
+        lines.append(f"{G[sel][0]:.6g}, {s.mean():.6g}, {half:.3g}, " + ", ".join(f"{x:.6g}" for x in np.quantile(s, qs)) +
+                     f", {len(s)}")
+    return "\n".join(lines)
+
+
+def summary(acc, names_f64=("f64[0]", "f64[1]"), names_i64=("i64[0]", "i64[1]"), run_ms=None):
+    """A JSON-ready dict of one ensemble run: counts, checksum of checksums, and per statistic the ensemble mean
+    with its 95 % interval (from the reduced accumulators alone)."""
+    n = acc.n_replications
+    out = {"n_replications": int(n), "n_events": int(acc.n_events), "n_errors": int(acc.n_errors),
+           "trace_hash_sum": f"{acc.trace_hash_sum:016x}", "mean_end_time": acc.end_time_sum / n if n else float("nan")}
+    for k, name in enumerate(names_f64):
+        mean, half = mean_and_ci(acc, k)
+        out[name] = {"mean": mean, "ci95": half}
+    for k, name in enumerate(names_i64):
+        out[name] = {"sum": int(acc.i64_sum[k]), "mean": acc.i64_sum[k] / n if n else float("nan")}
+    if run_ms is not None:
+        out["run_ms"] = float(run_ms)
+        out["events_per_s"] = acc.n_events / (run_ms * 1e-3) if run_ms > 0 else float("nan")
+    return out
+
+
+def write_json(path, obj):
+    import json
+    with open(path, "w") as f:
+        json.dump(obj, f, indent=1, sort_keys=True)
+        f.write("\n")
+
+
+def write_columns_csv(path, columns, names_f64=("f64_0", "f64_1"), names_i64=("i64_0", "i64_1")):
+    """Per-replication results as CSV (one row per replication): what a user of the examples would otherwise
+    collect by running the simulation object once per row."""
+    hdr = ["replication", "end_time", "n_events", "trace_hash", "status", *names_f64, *names_i64]
+    with open(path, "w") as f:
+        f.write(", ".join(hdr) + "\n")
+        for r in range(len(columns.end_time)):
+            f.write(", ".join([str(r), str(int(columns.end_time[r])), str(int(columns.n_events[r])),
+                               f"{int(columns.trace_hash[r]):016x}", str(int(columns.status[r])),
+                               *[repr(float(columns.f64[k][r])) for k in range(abi.N_F64)],
+                               *[str(int(columns.i64[k][r])) for k in range(abi.N_I64)]]) + "\n")
+
+
 def time_series(ens, piece, n_pieces, stat=1, count=0):
     """Ensemble time series from run_for in pieces: after every piece of `piece` ticks the
     on-device reduction gives the cumulative sums; their differences are the per-interval statistics.

@@ -34,8 +34,9 @@ def test_cpp_example_runs_on_gpu(built, tmp_path):
     assert r.returncode == 0, r.stderr
     rows = [line.split(",") for line in r.stdout.strip().splitlines()[1:]]
     assert len(rows) == 5
-    for lam, mu, rho, avg, _ in rows:
+    for lam, mu, rho, avg, ci, _ in rows:
         lam, mu, avg = float(lam), float(mu), float(avg)
+        assert 0.0 < float(ci) < 0.1 * avg
         if lam <= 7.5:   # heavier loads have not reached steady state within 2000 packets
             assert abs(avg - 1.0 / (mu - lam)) < 0.15 / (mu - lam)   # M/M/1 sojourn time 1/(mu-lambda)
         else:
@@ -79,3 +80,17 @@ def test_cpp_program_example_matches_the_fused_kernel(built, tmp_path):
     r = subprocess.run([str(exe), "4096", "400"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "differing replications 0" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_aloha_sweep_example(built, tmp_path):
+    """examples/aloha_sweep.cpp prints the table of the reference's examples/aloha.cpp from one ensemble run."""
+    import math
+    exe = build_example(tmp_path, "aloha_sweep")
+    r = subprocess.run([str(exe), "1000", "16", "200"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0].startswith("G [Erlang], S [Erlang]") and len(lines) == 51
+    for line in lines[1:]:
+        G, S, ci = (float(x) for x in line.split(", ")[:3])
+        assert abs(S - G * math.exp(-2 * G)) < 0.04 and ci < 0.05      # pure ALOHA throughput

@@ -43,3 +43,34 @@ def test_batch_means_drops_the_transient():
     rows = [{"mean": 9.0, "d_count": 5}] + [{"mean": m, "d_count": 5} for m in (1.0, 1.2, 0.8, 1.0)]
     mean, half = stats.batch_means(rows, warmup=1)
     assert abs(mean - 1.0) < 1e-12 and 0.0 < half < 0.5
+
+
+def test_aloha_sweep_table_and_writers(port, tmp_path):
+    """examples/aloha.cpp:93-109 from one ensemble: rows follow the sweep, S tracks G exp(-2G) for pure ALOHA."""
+    import json
+    import golden_util
+    from model_cases import MODELS, clock_of
+    model, cls, fname = MODELS["aloha"]
+    g = golden_util.load(fname)
+    steps = 5
+    p = cls(16, steps, 0.2, 1.0, 1.0, 200.0, 0)
+    cols = port.run(model, p, clock_of(g), 3, 0, 40, threads=4)
+    rows = stats.aloha_sweep_table(cols, steps).splitlines()
+    assert rows[0].startswith("G [Erlang], S [Erlang], ci95") and len(rows) == 1 + steps
+    prev = 0.0
+    for line in rows[1:]:
+        G, S, half, lo, hi, n = (float(x) for x in line.split(", "))
+        assert G > prev and n == 8 and lo <= S <= hi
+        assert abs(S - G * np.exp(-2 * G)) < 0.08
+        prev = G
+    acc = _host_accumulators(cols)
+    js = stats.summary(acc, names_f64=("S", "G"), names_i64=("successful", "packets_per_station"), run_ms=2.0)
+    assert js["n_replications"] == 40 and js["events_per_s"] == acc.n_events / 2e-3
+    assert abs(js["S"]["mean"] - cols.f64[0].mean()) < 1e-12 and js["successful"]["sum"] == int(cols.i64[0].sum())
+    stats.write_json(tmp_path / "run.json", js)
+    assert json.loads((tmp_path / "run.json").read_text())["trace_hash_sum"] == js["trace_hash_sum"]
+    stats.write_columns_csv(tmp_path / "cols.csv", cols, names_f64=("S", "G"))
+    lines = (tmp_path / "cols.csv").read_text().splitlines()
+    assert len(lines) == 41 and lines[0].split(", ")[5] == "S"
+    r7 = lines[8].split(", ")
+    assert int(r7[1]) == cols.end_time[7] and float(r7[5]) == cols.f64[0][7] and int(r7[3], 16) == cols.trace_hash[7]

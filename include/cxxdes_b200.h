@@ -285,6 +285,14 @@ int cxxdes_b200_device_columns(cxxdes_b200_ensemble *e, cxxdes_b200_columns *dev
 int cxxdes_b200_reduce(cxxdes_b200_ensemble *e, cxxdes_b200_accumulators *host_out,
                        void **device_accumulators);
 
+/* cxxdes_b200_reduce, then sum the accumulators of all shards: one ncclAllReduce pair (7 x 64-bit integer
+ * words, 4 x double) over `nccl_comm` -- an ncclComm_t of the caller with one rank per shard -- on the handle's
+ * stream, in place on the device struct; `host_out` receives the ensemble totals (every rank the same).  This is
+ * the only exchange of the path: replications share nothing.  NCCL is resolved when this is first
+ * called (the libnccl.so.2 already loaded in the process, else the system one): the library itself does not
+ * link against it.  Every rank of the communicator must make the call. */
+int cxxdes_b200_reduce_allgpus(cxxdes_b200_ensemble *e, void *nccl_comm, cxxdes_b200_accumulators *host_out);
+
 /* Device time of the most recent run/run_until launch in milliseconds (CUDA
  * events recorded on the launching stream), and how many kernels this library
  * launched on the handle so far. */

@@ -184,6 +184,15 @@ public:
         return acc;
     }
 
+    // Totals over ALL shards: the one collective of a multi-GPU run (an ncclAllReduce of the 88-byte accumulator
+    // struct over `nccl_comm`, an ncclComm_t with one rank per shard).  Every rank must call it.
+    cxxdes_b200_accumulators reduce_allgpus(void *nccl_comm) {
+        bind();
+        cxxdes_b200_accumulators acc;
+        detail::check(cxxdes_b200_reduce_allgpus(handle_, nccl_comm, &acc));
+        return acc;
+    }
+
     float last_run_ms() {
         float ms = 0;
         detail::check(cxxdes_b200_last_run_ms(handle_, &ms));

@@ -5,8 +5,10 @@
 // same stream.  No CPU implementation of the dispatch loop exists on this side of the boundary:
 // if no CUDA device is present every entry point fails with CXXDES_B200_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -511,6 +513,62 @@ int cxxdes_b200_reduce(cxxdes_b200_ensemble *e, cxxdes_b200_accumulators *host_o
     CUDA_TRY(launch_reduce(e->cols, e->cfg.n_replications, e->acc, e->reduce_scratch, e->sm_count, e->stream));
     e->launches += 2;
     if (device_acc) *device_acc = e->acc;
+    if (host_out) {
+        CUDA_TRY(cudaMemcpyAsync(host_out, e->acc, sizeof(*host_out), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return CXXDES_B200_OK;
+}
+
+// The final exchange of a multi-GPU run.  NCCL entry points are looked up at the first call, so that a process
+// which never calls this (or which already carries its own NCCL, e.g. the one bundled with PyTorch) is untouched.
+namespace {
+struct nccl_api {
+    int (*all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*group_start)() = nullptr;
+    int (*group_end)() = nullptr;
+    const char *(*error_string)(int) = nullptr;
+    bool ok = false;
+};
+const nccl_api &nccl() {
+    static nccl_api api = [] {
+        nccl_api a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.all_reduce = (decltype(a.all_reduce))dlsym(h, "ncclAllReduce");
+        a.group_start = (decltype(a.group_start))dlsym(h, "ncclGroupStart");
+        a.group_end = (decltype(a.group_end))dlsym(h, "ncclGroupEnd");
+        a.error_string = (decltype(a.error_string))dlsym(h, "ncclGetErrorString");
+        a.ok = a.all_reduce && a.group_start && a.group_end && a.error_string;
+        return a;
+    }();
+    return api;
+}
+constexpr int NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+static_assert(offsetof(cxxdes_b200_accumulators, f64_sum) == 7 * 8, "accumulator layout: 7 integer words first");
+static_assert(sizeof(cxxdes_b200_accumulators) == 11 * 8, "accumulator layout: then 4 doubles");
+}  // namespace
+
+int cxxdes_b200_reduce_allgpus(cxxdes_b200_ensemble *e, void *nccl_comm, cxxdes_b200_accumulators *host_out) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    if (!nccl_comm) return fail(CXXDES_B200_ERR_INVALID, "reduce_allgpus: nccl_comm is NULL");
+    if (!e->used) return fail(CXXDES_B200_ERR_STATE, "reduce before run");
+    const nccl_api &api = nccl();
+    if (!api.ok) return fail(CXXDES_B200_ERR_CUDA, "reduce_allgpus: libnccl.so.2 not found: %s", dlerror());
+    int rc = set_device(e);
+    if (rc) return rc;
+    CUDA_TRY(launch_reduce(e->cols, e->cfg.n_replications, e->acc, e->reduce_scratch, e->sm_count, e->stream));
+    e->launches += 2;
+    // integer words sum exactly (the digest sum wraps, as on one GPU); the FP64 sums are order dependent at 1e-16
+    unsigned char *acc = (unsigned char *)e->acc;
+    int nrc = api.group_start();
+    if (nrc == 0) nrc = api.all_reduce(acc, acc, 7, NCCL_UINT64, NCCL_SUM, nccl_comm, e->stream);
+    if (nrc == 0) nrc = api.all_reduce(acc + 7 * 8, acc + 7 * 8, 4, NCCL_FLOAT64, NCCL_SUM, nccl_comm, e->stream);
+    const int erc = api.group_end();
+    if (nrc == 0) nrc = erc;
+    if (nrc != 0) return fail(CXXDES_B200_ERR_CUDA, "reduce_allgpus: NCCL: %s", api.error_string(nrc));
     if (host_out) {
         CUDA_TRY(cudaMemcpyAsync(host_out, e->acc, sizeof(*host_out), cudaMemcpyDeviceToHost, e->stream));
         CUDA_TRY(cudaStreamSynchronize(e->stream));

@@ -55,12 +55,13 @@ def load_library():
     lib.cxxdes_b200_fetch.argtypes = [H, C.POINTER(abi.Columns)]
     lib.cxxdes_b200_device_columns.argtypes = [H, C.POINTER(abi.Columns)]
     lib.cxxdes_b200_reduce.argtypes = [H, C.POINTER(abi.Accumulators), C.POINTER(C.c_void_p)]
+    lib.cxxdes_b200_reduce_allgpus.argtypes = [H, C.c_void_p, C.POINTER(abi.Accumulators)]
     lib.cxxdes_b200_last_run_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
     for name in ("device_count", "version", "create", "run", "run_until", "run_for", "sync", "fetch",
-                 "device_columns", "reduce", "last_run_ms", "launch_count", "reset", "destroy"):
+                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
     return lib
@@ -69,7 +70,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
-    "cxxdes_b200_reduce", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_reset",
+    "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",
 ]
 

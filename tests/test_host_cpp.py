@@ -94,3 +94,37 @@ def test_cpp_aloha_sweep_example(built, tmp_path):
     for line in lines[1:]:
         G, S, ci = (float(x) for x in line.split(", ")[:3])
         assert abs(S - G * math.exp(-2 * G)) < 0.04 and ci < 0.05      # pure ALOHA throughput
+
+
+def build_multi_gpu_example(tmp_path):
+    exe = tmp_path / "mm1_multi_gpu"
+    lib_dir = ROOT / "libcxxdes_b200" / "_lib"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", f"-I{ROOT / 'include'}",
+                    "-I/usr/local/cuda/include", str(ROOT / "examples" / "mm1_multi_gpu.cpp"), f"-L{lib_dir}",
+                    "-lcxxdes_b200", "-lnccl", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_reduce_allgpus_rejects_misuse_without_touching_nccl(cuda_lib):
+    """The collective entry point validates its arguments before it looks for NCCL (the library does not link it)."""
+    import libcxxdes_b200 as L
+    assert cuda_lib.cxxdes_b200_reduce_allgpus(None, None, None) == L.abi.ERR_INVALID
+    assert b"handle is NULL" in cuda_lib.cxxdes_b200_last_error()
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_example_allreduces_over_nccl(built, tmp_path):
+    """One thread per GPU, shards by first_replication, ensemble::reduce_allgpus over an ncclComm_t: the totals are
+    the sums of the shard accumulators on every rank -- and the same digest sum whatever the number of GPUs."""
+    import torch
+    exe = build_multi_gpu_example(tmp_path)
+    n = torch.cuda.device_count()
+    outs = []
+    for gpus, per_gpu in ((n, 4096 // n * 2), (1, 4096 // n * 2 * n)):   # same global replications, n shards vs 1
+        r = subprocess.run([str(exe), str(per_gpu), "300", str(gpus)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "inconsistent ranks 0" in r.stdout
+        outs.append(r.stdout)
+    field = lambda s, key: s.split(key)[1].split(",")[0].strip()
+    assert field(outs[0], "digest sum") == field(outs[1], "digest sum")
+    assert field(outs[0], "events") == field(outs[1], "events")

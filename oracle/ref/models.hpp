@@ -9,6 +9,7 @@
 #pragma once
 #include "harness.hpp"
 #include "kat_models.hpp"
+#include "program_runner.hpp"
 
 #include <cxxdes/sync/queue.hpp>
 
@@ -427,6 +428,7 @@ inline rep_result run_model(int model, const void *params, cxxdes_b200_clock con
         case CXXDES_B200_MODEL_MMC: r = run_mmc(params, clock, seed, rep, until, tr); break;
         case CXXDES_B200_MODEL_ARCHSIM: r = run_archsim(params, clock, seed, rep, until, tr); break;
         case ORACLE_MODEL_KAT: r = run_kat(params, until, tr, nullptr); break;
+        case CXXDES_B200_MODEL_PROGRAM: r = run_program(params, clock, seed, rep, until, tr); break;
         default: throw std::runtime_error("ref_oracle: unknown model");
     }
     r.n_events = tr.n_events;

@@ -40,6 +40,18 @@ def test_cpu_interpreter_matches_reference_live(port, ref, k):
     golden_util.assert_columns_equal(a, b, what=K.SCENARIOS[k].__name__)
 
 
+@pytest.mark.parametrize("k", sorted(K.SCENARIOS))
+def test_reference_engine_runs_the_program_itself(ref, k):
+    """oracle/ref/program_runner.hpp executes the PROGRAM with the reference's own awaitables; the result equals
+    the scenario written natively on the reference engine (the golden vectors), trace included."""
+    prog, until = K.SCENARIOS[k]()
+    case = _golden(k)
+    got = ref.run(abi.MODEL_PROGRAM, prog.to_params(), CLK, 1, 0, 1, until=until)
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(case), what=case["name"])
+    total, events = ref.trace(abi.MODEL_PROGRAM, prog.to_params(), CLK, 1, 0, until=until, max_events=1000)
+    assert total == case["n_events"] and [list(e) for e in events] == case["trace"]
+
+
 def test_known_event_counts(port):
     """examples/resource.cpp = 16 events, examples/mutex.cpp = 38 events."""
     for k, n in ((6, 16), (7, 38)):

@@ -1,6 +1,7 @@
-"""Randomised process programs: the CUDA interpreters (shared-memory first pass + full-size retry kernel, and the
-full-size kernel alone) against the independent CPU interpreter of the oracle, bit for bit, run() and run_for
-pieces.  The generator only emits programs every side can finish: each loop body contains a delay, a process is
+"""Randomised process programs, three ways: the UNMODIFIED REFERENCE ENGINE executing each operation with its own
+awaitables (oracle/ref/program_runner.hpp; committed as tests/golden/programs_random_reference.json, and live
+where oracle/_ref exists) == the restated CPU interpreter of the oracle == the CUDA interpreters (shared-memory
+first pass + full-size retry kernel, and the full-size kernel alone), bit for bit, run() and run_for pieces.  The generator only emits programs every side can finish: each loop body contains a delay, a process is
 awaited at most once, and nothing depends on capacities the device bounds differently from the oracle."""
 import os
 import random
@@ -145,6 +146,56 @@ def test_generator_makes_programs_the_oracle_finishes(port, case):
     assert not cols.status.any() and (cols.n_events > 0).all()
     again = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*UNIT), 7, 0, 8)
     golden_util.assert_columns_equal(cols, again, what="determinism")
+
+
+def _golden_case(case):
+    g = golden_util.load("programs_random_reference.json")
+    return next(c for c in g["cases"] if c["program_seed"] == case)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cpu_interpreter_matches_reference_engine_golden(port, case):
+    """The committed vectors were produced by the reference engine running the program itself."""
+    prog = random_program(case)
+    c = _golden_case(case)
+    clk = abi.Clock.of(*UNIT)
+    got = port.run(abi.MODEL_PROGRAM, prog.to_params(), clk, c["seed"], 0, c["n_replications"])
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(c), what=f"program {case}")
+    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), clk, c["seed"], 0, c["n_replications"], until=c["run_until"])
+    golden_util.assert_columns_equal(part, golden_util.golden_columns({**c, "columns": c["columns_until"]}),
+                                     what=f"program {case} run_until")
+    total, events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), clk, c["seed"], 0, max_events=64)
+    assert total == c["n_events"] and [list(e) for e in events] == c["trace"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cpu_interpreter_matches_reference_engine_live(port, ref, case):
+    prog = random_program(case)
+    clk = abi.Clock.of(*UNIT)
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 77 + case, 5, 24, threads=4)
+    b = ref.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 77 + case, 5, 24, threads=4)
+    golden_util.assert_columns_equal(a, b, what=f"program {case}")
+    for frac in (0.25, 0.7):
+        until = int(a.end_time.max() * frac)
+        golden_util.assert_columns_equal(
+            port.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 77 + case, 5, 24, threads=4, until=until),
+            ref.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 77 + case, 5, 24, threads=4, until=until),
+            what=f"program {case} run_until({until})")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_gpu_random_programs_match_the_reference_engine_golden(built, case):
+    prog = random_program(case)
+    c = _golden_case(case)
+    ens = L.Ensemble(prog, c["n_replications"], seed=c["seed"])
+    ens.time_unit(*UNIT[0]).time_precision(*UNIT[1])
+    _compare(ens.run().fetch(strict=False), golden_util.golden_columns(c), f"program {case} vs reference engine")
+    ens.reset()
+    ens.run_until(c["run_until"])
+    _compare(ens.fetch(strict=False), golden_util.golden_columns({**c, "columns": c["columns_until"]}),
+             f"program {case} run_until vs reference engine")
+    ens.close()
 
 
 @pytest.mark.gpu

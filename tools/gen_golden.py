@@ -148,6 +148,23 @@ def kat_cases(ref):
     return {"model": "kat", "clock": CLOCK_S_S, "cases": cases}
 
 
+def program_cases(ref):
+    """Random process programs (tests/test_programs_fuzz.py random_program, by seed) run by the reference engine
+    itself through oracle/ref/program_runner.hpp: run() columns and the first events of replication 0."""
+    import test_programs_fuzz as F
+    cases = []
+    for case in F.CASES:
+        prog = F.random_program(case)
+        clk = abi.Clock.of(*F.UNIT)
+        cols = ref.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 1000 + case, 0, 8, threads=4)
+        until = int(cols.end_time.max()) // 2
+        part = ref.run(abi.MODEL_PROGRAM, prog.to_params(), clk, 1000 + case, 0, 8, threads=4, until=until)
+        total, tr = ref.trace(abi.MODEL_PROGRAM, prog.to_params(), clk, 1000 + case, 0, max_events=64)
+        cases.append({"program_seed": case, "seed": 1000 + case, "n_replications": 8, "columns": columns_to_json(cols),
+                      "run_until": until, "columns_until": columns_to_json(part), "n_events": total, "trace": tr})
+    return {"model": "program", "clock": CLOCK_S_MS, "cases": cases}
+
+
 def main():
     ref = oracles.ref_oracle()
     if ref is None:
@@ -156,7 +173,8 @@ def main():
     out = mm1_cases(ref)
     (GOLDEN / "mm1_reference.json").write_text(json.dumps(out, indent=0, separators=(",", ":")))
     print("wrote", GOLDEN / "mm1_reference.json")
-    for name, fn in (("aloha", aloha_cases), ("mmc", mmc_cases), ("archsim", archsim_cases), ("kat", kat_cases)):
+    for name, fn in (("aloha", aloha_cases), ("mmc", mmc_cases), ("archsim", archsim_cases), ("kat", kat_cases),
+                     ("programs_random", program_cases)):
         (GOLDEN / f"{name}_reference.json").write_text(json.dumps(fn(ref), indent=0, separators=(",", ":")))
         print("wrote", GOLDEN / f"{name}_reference.json")
 

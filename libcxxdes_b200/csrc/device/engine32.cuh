@@ -49,13 +49,22 @@ struct environment32 {
     }
 
     // std::__push_heap, stl_heap.h:135-148; comp(parent, value) = parent strictly later.
+    // The loop's loads form a dependent chain (each parent index comes from the previous compare), and with a few
+    // resident warps per scheduler that latency is what the heap kernels wait on.  The indices of parent AND
+    // grandparent are known up front, so both are loaded in one round trip and two levels are decided per trip;
+    // the moves are exactly those of the one-level loop.
     __device__ __forceinline__ void sift_up(int hole, uint32_t key, uint32_t tag) {
         while (hole > 0) {
             const int parent = (hole - 1) >> 1;
+            const int grand = parent > 0 ? (parent - 1) >> 1 : 0;
             const uint2 pe = heap[parent * STRIDE];
+            const uint2 ge = heap[grand * STRIDE];
             if (!(pe.x > key)) break;
             heap[hole * STRIDE] = pe;
             hole = parent;
+            if (parent == 0 || !(ge.x > key)) break;
+            heap[hole * STRIDE] = ge;
+            hole = grand;
         }
         heap[hole * STRIDE] = make_uint2(key, tag);
     }
@@ -89,11 +98,36 @@ struct environment32 {
             const int len = last;
             int hole = 0;
             int child = 0;
-            while (child < (len - 1) / 2) {
+            const int two_children = (len - 1) / 2;   // holes below this index have two children
+            while (child < two_children) {
                 child = 2 * (child + 1);
                 uint2 er = heap[child * STRIDE];
                 const uint2 el = heap[(child - 1) * STRIDE];
-                if (er.x > el.x) {  // right strictly later than left -> take left; tie -> right
+                if (child < two_children) {
+                    // both children have two children themselves: fetch the four grandchildren in the same round
+                    // trip and decide two levels (same moves as two turns of the one-level loop).  [Clamping the
+                    // indices so that the last levels take this path too measured no better.]
+                    const uint2 grr = heap[(2 * child + 2) * STRIDE], grl = heap[(2 * child + 1) * STRIDE];
+                    const uint2 glr = heap[(2 * child) * STRIDE], gll = heap[(2 * child - 1) * STRIDE];
+                    uint2 gr = grr, gl = grl;
+                    if (er.x > el.x) {  // right strictly later than left -> take left; tie -> right
+                        --child;
+                        er = el;
+                        gr = glr;
+                        gl = gll;
+                    }
+                    heap[hole * STRIDE] = er;
+                    hole = child;
+                    child = 2 * (child + 1);
+                    if (gr.x > gl.x) {
+                        --child;
+                        gr = gl;
+                    }
+                    heap[hole * STRIDE] = gr;
+                    hole = child;
+                    continue;
+                }
+                if (er.x > el.x) {
                     --child;
                     er = el;
                 }

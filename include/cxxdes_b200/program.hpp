@@ -202,6 +202,11 @@ public:
     mutex add_mutex() { return {(std::uint16_t)n_mutexes_++}; }
     event add_event() { return {(std::uint16_t)n_events_++}; }
 
+    // sequential(a, b, ...) / the comma operator: an unnamed coroutine that awaits its arguments in order
+    // (sequential.ipp:1-20).  Await the returned process or use it as a child of all_of / any_of; it is named
+    // `parent_ordinal | 0x8000`, the way the oracle harness reports library-created coroutines.
+    process sequential(std::uint32_t parent_ordinal, std::initializer_list<child> steps);
+
     // Define the body of process p: `fn(body &)` issues the co_await statements in order; co_return is implied.
     template <typename F>
     void body_of(process p, F &&fn);
@@ -360,6 +365,18 @@ void program::body_of(process p, F &&fn) {
     body b(*this);
     fn(b);
     emit(CXXDES_B200_OP_RETURN);
+}
+
+inline process program::sequential(std::uint32_t parent_ordinal, std::initializer_list<child> steps) {
+    process p = add_process(parent_ordinal | 0x8000u);
+    body_of(p, [&](body &co) {
+        for (const child &st : steps) {
+            if (st.kind == child::PROC) co.await(process{st.proc});
+            else if (st.kind == child::DELAY) co.await(delay_t{st.ticks, st.prio});
+            else co.await(until_t{st.ticks, st.prio});
+        }
+    });
+    return p;
 }
 
 namespace models {

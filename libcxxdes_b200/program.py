@@ -188,6 +188,22 @@ class Program:
             self._roots.append(pid)
         return pid
 
+    def sequential(self, parent_ordinal, *steps, priority=None):
+        """sequential(a, b, ...) / the comma operator: an unnamed coroutine that awaits its arguments in order
+        (sequential.ipp:1-20).  Returns the process; await it, or use it as a child of all_of / any_of.
+        `steps` are Delay / Until objects or process ids; the helper is named `parent_ordinal | 0x8000`, the way
+        the oracle harness reports library-created coroutines."""
+        p = self.process(int(parent_ordinal) | 0x8000, priority=priority)
+        with self.body(p) as b:
+            for st in steps:
+                if isinstance(st, Delay):
+                    b.delay(st.ticks, st.priority)
+                elif isinstance(st, Until):
+                    b.until(st.ticks, st.priority)
+                else:
+                    b.await_(int(st))
+        return p
+
     def root(self, proc):
         """env.bind(proc) -- simulation::bind binds co_main; several roots are allowed (examples/clocks.cpp)."""
         self._roots.append(proc)

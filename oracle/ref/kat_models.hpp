@@ -340,6 +340,23 @@ CXXDES_SIMULATION(kat_lazy_timeout) {
     coroutine<> co_main() { return tr.named(body(), 0); }
 };
 
+// 15 -- sequential composition: sequential(a, b) and the comma operator are an unnamed coroutine that awaits its
+//       arguments in order (sequential.ipp:1-20, compositions.ipp:25-27): 7, 10, 20
+CXXDES_SIMULATION(kat_sequential) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_sequential(tracer &t) : tr{t} { bind(); }
+    coroutine<> body() {
+        co_await sequential(delay(3), delay(4));
+        marks.push_back(now());  // 7
+        co_await (delay(1), delay(2));
+        marks.push_back(now());  // 10
+        co_await all_of(sequential(delay(5), delay(5)), delay(7));
+        marks.push_back(now());  // 20
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
 // Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
 // application-level observations are compared too, not only the token trace.
 inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
@@ -378,6 +395,7 @@ inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::ve
         case 12: return run_kat_sim<kat_raii_trick>(tr, until);
         case 13: return run_kat_sim<kat_get_environment>(tr, until);
         case 14: return run_kat_sim<kat_lazy_timeout>(tr, until);
+        case 15: return run_kat_sim<kat_sequential>(tr, until);
         default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
     }
 }

@@ -210,11 +210,24 @@ def lazy_timeout():          # 14: examples/lazy_timeout.cpp
     return prog, -1
 
 
+def sequential():             # 15: sequential(a, b), the comma operator, a sequential as a child of all_of
+    prog = Program()
+    main = prog.process(0, root=True)
+    s1 = prog.sequential(0, Delay(3), Delay(4))
+    s2 = prog.sequential(0, Delay(1), Delay(2))
+    s3 = prog.sequential(0, Delay(5), Delay(5))
+    with prog.body(main) as b:
+        b.await_(s1); b.mark(1, 0)
+        b.await_(s2); b.mark(1, 0)
+        b.all_of(s3, Delay(7)); b.mark(1, 0)
+    return prog, -1
+
+
 SCENARIOS = {1: compositions, 2: latencies, 3: out_of_scope, 4: priorities, 5: clocks, 6: resource, 7: mutex,
-             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout}
+             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout, 15: sequential}
 # end time of every scenario on the reference engine (the reference's tests / examples document the
 # observation times; scenario 1 ends at 40 because the loser of any_of(timeout(10), timeout(20)) still fires)
-EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30}
+EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30, 15: 20}
 
 
 def mm1_program(lam, mu, n_packets):

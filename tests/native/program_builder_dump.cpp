@@ -247,6 +247,22 @@ static program lazy_timeout_example() {
     return prog;
 }
 
+// sequential(a, b), the comma operator, a sequential as a child of all_of (sequential.ipp:1-20)
+static program sequential_example() {
+    program prog;
+    process co_main = prog.add_process(0);
+    prog.bind(co_main);
+    process s1 = prog.sequential(0, {delay(3), delay(4)});
+    process s2 = prog.sequential(0, {delay(1), delay(2)});
+    process s3 = prog.sequential(0, {delay(5), delay(5)});
+    prog.body_of(co_main, [&](body &co) {
+        co.await(s1).mark(1, 0);
+        co.await(s2).mark(1, 0);
+        co.await(all_of(s3, delay(7))).mark(1, 0);
+    });
+    return prog;
+}
+
 int main() {
     std::printf("{\n");
     dump("mm1", mm1(5.0, 10.0, 300));
@@ -259,7 +275,8 @@ int main() {
     dump("9", queue_example());
     dump("10", event_example());
     dump("11", debug_example());
-    dump("14", lazy_timeout_example(), true);
+    dump("14", lazy_timeout_example());
+    dump("15", sequential_example(), true);
     std::printf("}\n");
     // error behaviour: the reference throws std::runtime_error on misuse (environment.ipp:44-45)
     int caught = 0;

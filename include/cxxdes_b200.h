@@ -235,7 +235,8 @@ typedef struct cxxdes_b200_config {
     size_t params_size;
     void *stream;                /* cudaStream_t to launch on, NULL = a stream owned by the handle */
     uint32_t flags;              /* CXXDES_B200_FLAG_*                                      */
-    uint32_t queue_capacity;     /* 0 = default; ring entries per replication               */
+    uint32_t queue_capacity;     /* 0 = default; ring entries per replication (M/M/1), items per
+                                    sync::queue of a process program (default 128)           */
 } cxxdes_b200_config;
 
 enum {

@@ -184,7 +184,7 @@ int upload_program(cxxdes_b200_ensemble *e) {
     delete[] host;
     if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program upload: %s", cudaGetErrorString(ce));
     e->program_blob_bytes = (uint32_t)total;
-    e->prog_fast = program_fast_plan(p, (uint32_t)total, e->smem_optin);
+    e->prog_fast = program_fast_plan(p, (uint32_t)total, e->smem_optin, e->cfg.queue_capacity);
     if (const size_t qb = program_fast_queue_bytes(e->prog_fast, e->sm_count)) {
         ce = cudaMalloc(&e->prog_queue_items, qb);
         if (ce != cudaSuccess) return fail(CXXDES_B200_ERR_CUDA, "program queues: %s", cudaGetErrorString(ce));

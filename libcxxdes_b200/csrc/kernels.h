@@ -93,6 +93,7 @@ struct program_fast_layout {
     int pw, o_draws, o_loop, loop_words;      // words per process, offsets of the optional ones
     int wait_cap, wait_words, ewait_words;    // wait lists: count word + entries
     int d_regs;                 // first 64-bit word of the per-process registers
+    int queue_cap;              // items per queue (power of two), payloads in global memory
     uint32_t staged_bytes;      // program text staged into shared memory
     size_t smem_bytes;
     int blocks_per_sm;
@@ -107,7 +108,8 @@ struct program_fast_state {
 };
 size_t program_fast_state_words(const program_fast_layout &L);
 size_t program_fast_state_queue_bytes(const program_fast_layout &L, uint64_t n_replications);
-program_fast_layout program_fast_plan(const cxxdes_b200_program &host_program, uint32_t blob_bytes, size_t smem_optin);
+program_fast_layout program_fast_plan(const cxxdes_b200_program &host_program, uint32_t blob_bytes, size_t smem_optin,
+                                      uint32_t queue_capacity);
 size_t program_fast_queue_bytes(const program_fast_layout &L, int sm_count);
 cudaError_t launch_program_fast(const device_program &prg, const program_fast_layout &L, const shard &sh,
                                 const device_columns &out, int64_t *queue_items, const program_fast_state &st,

@@ -36,7 +36,7 @@ namespace {
 
 constexpr int PF_THREADS = 128;
 constexpr int PF_HANDLERS = 8;     // at most: live any_of/all_of handlers per replication (pool, by serial)
-constexpr int PF_QUEUE_CAP = 128;  // items per queue (global memory)
+constexpr int PF_QUEUE_CAP = 128;  // items per queue (global memory) unless cxxdes_b200_config.queue_capacity asks for more
 constexpr uint32_t PF_NONE = 0xFFFFFFFFu;
 constexpr int32_t INHERIT32 = INT32_MAX;
 constexpr int64_t INHERIT64 = INT64_MAX;
@@ -328,12 +328,12 @@ struct machine {
                     wait_plain(L.w_qwait + op.a * L.wait_words, p);
                     return false;   // pc unchanged: the put is retried after the wake-up
                 }
-                if (count >= PF_QUEUE_CAP) {
+                if (count >= (uint32_t)L.queue_cap) {
                     env.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
                     return false;
                 }
                 const int64_t v = op.b ? (int64_t)d(L.d_regs + (int)p) : env.now;
-                items[(uint32_t)(op.a * PF_QUEUE_CAP + (int)((head + count) % PF_QUEUE_CAP)) * item_stride] = v;
+                items[(uint32_t)(op.a * L.queue_cap + (int)((head + count) & (uint32_t)(L.queue_cap - 1))) * item_stride] = v;
                 w(qw) = head | ((count + 1) << 16);
                 wake_plain(L.w_qwait + op.a * L.wait_words);
                 break;
@@ -346,8 +346,8 @@ struct machine {
                     wait_plain(L.w_qwait + op.a * L.wait_words, p);
                     return false;
                 }
-                d(L.d_regs + (int)p) = (uint64_t)items[(uint32_t)(op.a * PF_QUEUE_CAP + (int)head) * item_stride];
-                head = (head + 1) % PF_QUEUE_CAP;
+                d(L.d_regs + (int)p) = (uint64_t)items[(uint32_t)(op.a * L.queue_cap + (int)head) * item_stride];
+                head = (head + 1) & (uint32_t)(L.queue_cap - 1);
                 if (--count == 0) head = 0;   // an empty ring restarts at slot 0: short queues stay in one line
                 w(qw) = head | (count << 16);
                 wake_plain(L.w_qwait + op.a * L.wait_words);
@@ -521,7 +521,7 @@ struct machine {
             const uint32_t qw = w(L.w_queues + (int)q);
             const uint32_t head = qw & 0xFFFFu, count = qw >> 16;
             for (uint32_t k = 0; k < count; ++k) {
-                const size_t slot = (size_t)q * PF_QUEUE_CAP + (head + k) % PF_QUEUE_CAP;
+                const size_t slot = (size_t)q * L.queue_cap + ((head + k) & (uint32_t)(L.queue_cap - 1));
                 st.queue_items[slot * n + rep] = items[slot * item_stride];
             }
         }
@@ -550,7 +550,7 @@ struct machine {
             const uint32_t qw = w(L.w_queues + (int)q);
             const uint32_t head = qw & 0xFFFFu, count = qw >> 16;
             for (uint32_t k = 0; k < count; ++k) {
-                const size_t slot = (size_t)q * PF_QUEUE_CAP + (head + k) % PF_QUEUE_CAP;
+                const size_t slot = (size_t)q * L.queue_cap + ((head + k) & (uint32_t)(L.queue_cap - 1));
                 items[slot * item_stride] = st.queue_items[slot * n + rep];
             }
         }
@@ -697,7 +697,8 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
 }
 
 // Size the shared-memory state from the (host copy of the) program.  valid = false: run program_kernel.cu alone.
-program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blob_bytes, size_t smem_optin) {
+program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blob_bytes, size_t smem_optin,
+                                      uint32_t queue_capacity) {
     program_fast_layout L{};
     L.valid = false;
     if (getenv("CXXDES_B200_PRG_NO_FAST")) return L;
@@ -787,7 +788,11 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     if (const char *env = getenv("CXXDES_B200_PRG_BLOCKS")) { int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
     if (per_sm < 2) return L;       // too few resident warps to be worth it: the full-size kernel alone
     L.blocks_per_sm = per_sm;
-    L.queue_item_bytes_per_thread = (size_t)p.n_queues * PF_QUEUE_CAP * sizeof(int64_t);
+    // queue payloads live in global memory, so a heavily loaded model can ask for deeper queues than the
+    // full-size kernel's 128 (power of two, at most 32768: head and count share one 32-bit word)
+    L.queue_cap = PF_QUEUE_CAP;
+    while (L.queue_cap < (int)queue_capacity && L.queue_cap < 32768) L.queue_cap *= 2;
+    L.queue_item_bytes_per_thread = (size_t)p.n_queues * L.queue_cap * sizeof(int64_t);
     L.valid = true;
     return L;
 }

@@ -294,3 +294,31 @@ def test_gpu_program_pieces_finished_replications_follow_the_horizon_and_reset_s
     want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n_reps, until=3000)
     golden_util.assert_columns_equal(ens.fetch(strict=False), want, what="after reset")
     ens.close()
+
+
+@pytest.mark.gpu
+def test_gpu_program_deep_queues_on_request(port):
+    """A heavily loaded queue outgrows the default 128 items per sync::queue (reported per replication, never a
+    different trace); cxxdes_b200_config.queue_capacity gives the shared-memory interpreter deeper queues."""
+    prog = K.mm1_program(9.9, 10.0, 6000)
+    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
+    n_reps = 256
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count())
+    ens = L.Ensemble(prog, n_reps, seed=3)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    got = ens.run().fetch(strict=False)
+    ens.close()
+    overflowed = (got.status & abi.REP_QUEUE_OVERFLOW) != 0
+    assert overflowed.any() and not (got.status & ~np.uint32(abi.REP_QUEUE_OVERFLOW)).any()
+    assert np.array_equal(got.trace_hash[~overflowed], want.trace_hash[~overflowed])
+    ens = L.Ensemble(prog, n_reps, seed=3, queue_capacity=2000)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    got = ens.run().fetch()
+    assert not got.status.any()
+    golden_util.assert_columns_equal(got, want, what="deep queues")
+    ens.reset()
+    ens.run_for(200000)
+    ens.run_for(200000)
+    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count(), until=400000)
+    golden_util.assert_columns_equal(ens.fetch(strict=False), part, what="deep queues, two pieces")
+    ens.close()

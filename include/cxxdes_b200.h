@@ -126,7 +126,8 @@ enum {
     CXXDES_B200_OP_FRESH = 5,       /* process a becomes a new, unstarted coroutine object again               */
     CXXDES_B200_OP_AWAIT = 6,       /* co_await process a (coroutine.ipp:179-207, environment.ipp:281-307)     */
     CXXDES_B200_OP_ASYNC = 7,       /* co_await async(process a): async.ipp:21-28                              */
-    CXXDES_B200_OP_ALL_OF = 8,      /* co_await all_of(children...): a = child count, children follow          */
+    CXXDES_B200_OP_ALL_OF = 8,      /* co_await all_of(children...): a = child count, children follow;
+                                       b = .priority(p) or INHERIT (what the children inherit), imm = .return_latency() */
     CXXDES_B200_OP_ANY_OF = 9,      /* co_await any_of(children...)            (any_of.ipp:3-92,233-247)       */
     CXXDES_B200_OP_CHILD_PROC = 10, /*   child: process a                                                      */
     CXXDES_B200_OP_CHILD_DELAY = 11,/*   child: delay(imm), b = priority or INHERIT                            */

@@ -101,11 +101,23 @@ struct child {  // an operand of all_of / any_of / && / ||
 struct composition {  // any_of.ipp:233-247; compositions.ipp (operator&&, operator||)
     bool all;
     std::vector<child> children;
+    priority_type prio = inherit;      // .priority(p): what the children inherit (any_of.ipp:30-33,41-48)
+    time_integral latency = 0;         // .return_latency(l): added to the token that resumes the awaiting process
+    composition priority(priority_type p) const {
+        composition c = *this;
+        c.prio = p;
+        return c;
+    }
+    composition return_latency(time_integral l) const {
+        composition c = *this;
+        c.latency = l;
+        return c;
+    }
 };
 template <typename... C>
-composition all_of(C... c) { return {true, {child(c)...}}; }
+composition all_of(C... c) { return composition{true, {child(c)...}}; }
 template <typename... C>
-composition any_of(C... c) { return {false, {child(c)...}}; }
+composition any_of(C... c) { return composition{false, {child(c)...}}; }
 inline composition all_of_range(const std::vector<process> &ps) {  // all_of.range(first, last)
     composition c{true, {}};
     for (process p : ps) c.children.emplace_back(p);
@@ -117,8 +129,8 @@ inline composition any_of_range(const std::vector<process> &ps) {
     return c;
 }
 // a && b, a || b: flat n-ary like the reference's operator overloads
-inline composition operator&&(child a, child b) { return {true, {a, b}}; }
-inline composition operator||(child a, child b) { return {false, {a, b}}; }
+inline composition operator&&(child a, child b) { return composition{true, {a, b}}; }
+inline composition operator||(child a, child b) { return composition{false, {a, b}}; }
 inline composition operator&&(composition a, child b) {
     if (!a.all) throw std::invalid_argument("cxxdes_b200: nested compositions are not supported; use a helper process");
     a.children.push_back(b);
@@ -300,7 +312,8 @@ public:
     body &await(const composition &c) {  // co_await all_of(...) / any_of(...) / (a && b) / (a || b)
         if (c.children.empty() || c.children.size() > 32)
             throw std::invalid_argument("cxxdes_b200: a composition takes 1..32 children");
-        prog_.emit(c.all ? CXXDES_B200_OP_ALL_OF : CXXDES_B200_OP_ANY_OF, (std::uint16_t)c.children.size());
+        prog_.emit(c.all ? CXXDES_B200_OP_ALL_OF : CXXDES_B200_OP_ANY_OF, (std::uint16_t)c.children.size(),
+                   detail::prio32(c.prio), c.latency);
         for (const child &ch : c.children) {
             if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);
             else

@@ -167,8 +167,9 @@ struct machine {
     __device__ bool composition(uint32_t self, const cxxdes_b200_op &head, uint32_t first_child) {
         const bool is_all = head.code == CXXDES_B200_OP_ALL_OF;
         const uint32_t total = head.a;
-        const int64_t self_prio = prio_of(self);
-        // await_bind: every child in argument order (coroutine children get their start token here)
+        // await_bind: every child in argument order (coroutine children get their start token here); what they
+        // inherit is the composition's priority: .priority(p), else the awaiting process's (any_of.ipp:41-48)
+        const int64_t self_prio = head.b == CXXDES_B200_INHERIT ? prio_of(self) : (int64_t)head.b;
         for (uint32_t c = 0; c < total; ++c) {
             const cxxdes_b200_op &ch = prg.ops[first_child + c];
             if (ch.code == CXXDES_B200_OP_CHILD_PROC) bind(ch.a, self_prio);
@@ -204,7 +205,12 @@ struct machine {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return true;
         }
+        if (head.imm < 0 || head.imm > INT32_MAX) {   // .return_latency() beyond the 32-bit word of this layout
+            env.status |= CXXDES_B200_REP_TIME_RANGE;
+            return true;
+        }
         w(hw) = (serial + 1) | (remaining << H_REM_SHIFT) | (is_all ? H_ALL : 0u) | H_ARMED;
+        w(hw + L.n_handlers) = (uint32_t)head.imm;   // .return_latency(): added to the satisfying child token's time
         const uint32_t tag = ptag(self, serial + 1);
         for (uint32_t c = 0; c < total; ++c) {
             if (ready_mask & (1u << c)) continue;
@@ -235,7 +241,7 @@ struct machine {
         h = (h & ~(63u << H_REM_SHIFT)) | ((remaining & 63u) << H_REM_SHIFT);
         const bool cond = (h & H_ALL) ? remaining == 0 : true;
         if (cond) {
-            env.schedule(key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
+            env.schedule((int64_t)w(hw + L.n_handlers) + key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
             h &= ~H_ARMED;
         }
         w(hw) = h;
@@ -767,7 +773,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     int w = 0;
     L.w_serial = w++;
     L.w_mtx = w++;
-    L.w_handlers = w; w += L.n_handlers;
+    L.w_handlers = w; w += 2 * L.n_handlers;   // handler word + return latency
     L.w_queues = w; w += (int)p.n_queues;
     L.w_sems = w; w += (int)p.n_sems;
     L.w_procs = w; w += pw * (int)p.n_procs;

@@ -48,6 +48,7 @@ struct waiters_rt {  // sync::event: FIFO of {latency, priority, process}  (even
 };
 
 struct handler_rt {  // any_all_helper::custom_handler (any_of.ipp:3-27)
+    int64_t out_latency;     // .return_latency(): added to the satisfying child token's time
     uint32_t serial_plus1;
     uint32_t total, remaining;
     bool is_all, armed;
@@ -147,10 +148,12 @@ struct interp {
             env.status |= CXXDES_B200_REP_BAD_PROGRAM;
             return true;
         }
-        // await_bind: every child in argument order (coroutine children get their start token here)
+        // await_bind: every child in argument order (coroutine children get their start token here); what they
+        // inherit is the composition's priority: .priority(p), else the awaiting process's (any_of.ipp:41-48)
+        const int64_t comp_prio = head.b == CXXDES_B200_INHERIT ? self.prio : (int64_t)head.b;
         for (uint32_t c = 0; c < total; ++c) {
             const cxxdes_b200_op &ch = prg.ops[first_child + c];
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) bind(ch.a, self.prio);
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) bind(ch.a, comp_prio);
         }
         // await_ready: collect ready flags
         uint32_t ready_mask = 0, remaining = total;
@@ -188,13 +191,16 @@ struct interp {
         h.remaining = remaining;
         h.is_all = is_all;
         h.armed = true;
+        h.out_latency = head.imm;
         for (uint32_t c = 0; c < total; ++c) {
             if (ready_mask & (1u << c)) continue;
             const cxxdes_b200_op &ch = prg.ops[first_child + c];
             const uint32_t tag = ptag(self_id, serial + 1);
             if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
-            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) env.schedule(env.now + ch.imm, op_priority(ch, self), tag);
-            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) env.schedule(ch.imm, op_priority(ch, self), tag);
+            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY)
+                env.schedule(env.now + ch.imm, ch.b == CXXDES_B200_INHERIT ? comp_prio : (int64_t)ch.b, tag);
+            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL)
+                env.schedule(ch.imm, ch.b == CXXDES_B200_INHERIT ? comp_prio : (int64_t)ch.b, tag);
             else env.status |= CXXDES_B200_REP_BAD_PROGRAM;
         }
         return true;
@@ -211,7 +217,7 @@ struct interp {
         --h.remaining;
         const bool cond = h.is_all ? h.remaining == 0 : h.remaining < h.total;
         if (h.armed && cond) {
-            env.schedule(key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
+            env.schedule(h.out_latency + key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
             h.armed = false;
         }
     }

@@ -92,8 +92,8 @@ class Body:
     def async_(self, proc):                      # co_await async(p)
         self._emit(abi.OP_ASYNC, proc)
 
-    def _composition(self, code, children):
-        self._emit(code, len(children))
+    def _composition(self, code, children, priority=None, return_latency=0):
+        self._emit(code, len(children), _prio32(priority), int(return_latency))
         for c in children:
             if isinstance(c, Delay):
                 self._emit(abi.OP_CHILD_DELAY, 0, _prio32(c.priority), c.ticks)
@@ -102,11 +102,13 @@ class Body:
             else:
                 self._emit(abi.OP_CHILD_PROC, int(c))
 
-    def all_of(self, *children):                 # co_await all_of(...) / (a && b)
-        self._composition(abi.OP_ALL_OF, children)
+    # priority / return_latency: all_of(...).priority(p).return_latency(l) (any_of.ipp:30-38) -- the priority the
+    # children inherit, and a delay added to the token that resumes the awaiting process
+    def all_of(self, *children, priority=None, return_latency=0):   # co_await all_of(...) / (a && b)
+        self._composition(abi.OP_ALL_OF, children, priority, return_latency)
 
-    def any_of(self, *children):                 # co_await any_of(...) / (a || b)
-        self._composition(abi.OP_ANY_OF, children)
+    def any_of(self, *children, priority=None, return_latency=0):   # co_await any_of(...) / (a || b)
+        self._composition(abi.OP_ANY_OF, children, priority, return_latency)
 
     # --- sync primitives ---
     def put(self, queue, from_reg=False):        # co_await q.put(now) (or the process register)

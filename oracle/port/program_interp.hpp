@@ -76,10 +76,13 @@ struct program_model {
         process &me = eng.procs[self];
         const bool is_all = head.code == CXXDES_B200_OP_ALL_OF;
         const size_t total = head.a;
-        // await_bind (any_of.ipp:41-48)
+        // await_bind (any_of.ipp:41-48): the composition's own priority (.priority(p), else the awaiting process's)
+        // is what the children inherit
+        int64_t comp_prio = prio_of(head);
+        if (comp_prio == PRIO_INHERIT) comp_prio = me.priority;
         for (size_t c = 0; c < total; ++c) {
             const cxxdes_b200_op &ch = prg.ops[first + c];
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) eng.bind(ch.a, me.priority);
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) eng.bind(ch.a, comp_prio);
         }
         // await_ready (:50-64)
         std::vector<bool> ready;
@@ -94,16 +97,17 @@ struct program_model {
         }
         if (is_all ? remaining == 0 : remaining < total) return false;
         // await_suspend (:66-84)
-        int32_t h = eng.add_handler(is_all, total, remaining, token{0, me.priority, self, NO_HANDLER});
+        // the output token {return latency, priority, self} (:67); its time and priority are completed by the
+        // child token that satisfies the condition (:19-23)
+        int32_t h = eng.add_handler(is_all, total, remaining, token{head.imm, comp_prio, self, NO_HANDLER});
         for (size_t c = 0; c < total; ++c) {
             if (ready[c]) continue;
             const cxxdes_b200_op &ch = prg.ops[first + c];
             if (ch.code == CXXDES_B200_OP_CHILD_PROC) await_completion(ch.a, self, h);
-            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) eng.timeout(self, ch.imm, prio_of(ch), h);
             else {
                 int64_t pr = prio_of(ch);
-                if (pr == PRIO_INHERIT) pr = me.priority;
-                eng.schedule(token{ch.imm, pr, self, h});
+                if (pr == PRIO_INHERIT) pr = comp_prio;
+                eng.schedule(token{ch.code == CXXDES_B200_OP_CHILD_DELAY ? eng.now + ch.imm : ch.imm, pr, self, h});
             }
         }
         return true;

@@ -156,8 +156,17 @@ struct program_sim {
                         else
                             children.push_back(any_child{until((time_integral)ch.imm, prio_of(ch.b))});
                     }
-                    if (op.code == CXXDES_B200_OP_ALL_OF) co_await all_of.range(children.begin(), children.end());
-                    else co_await any_of.range(children.begin(), children.end());
+                    if (op.code == CXXDES_B200_OP_ALL_OF) {
+                        auto comp = all_of.range(children.begin(), children.end());
+                        if (op.b != CXXDES_B200_INHERIT) comp.priority((priority_type)op.b);
+                        comp.return_latency((time_integral)op.imm);
+                        co_await std::move(comp);
+                    } else {
+                        auto comp = any_of.range(children.begin(), children.end());
+                        if (op.b != CXXDES_B200_INHERIT) comp.priority((priority_type)op.b);
+                        comp.return_latency((time_integral)op.imm);
+                        co_await std::move(comp);
+                    }
                     pc += op.a;
                     break;
                 }

@@ -82,7 +82,8 @@ def random_program(seed):
             if budget[0] > 0 and depth == 0 and rng.random() < 0.5:
                 budget[0] -= 1
                 children.insert(rng.randint(0, len(children)), helper(depth))
-            (b.all_of if rng.random() < 0.5 else b.any_of)(*children)
+            (b.all_of if rng.random() < 0.5 else b.any_of)(*children, priority=prio() if rng.random() < 0.4 else None,
+                                                             return_latency=rng.choice((0, 0, 0, 1, 4)))
         elif k < 0.90 and budget[0] > 0 and depth == 0:
             budget[0] -= 1
             h = helper(depth)

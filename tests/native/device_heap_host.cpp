@@ -1,0 +1,121 @@
+// tests/native/device_heap_host.cpp -- TEST INFRASTRUCTURE, never part of the product library.
+//
+// Compiles the DEVICE event heaps (libcxxdes_b200/csrc/device/engine.cuh and engine32.cuh, the code the CUDA
+// kernels run -- including the two-level look-ahead of the compact heap) with g++ and checks them against
+// std::priority_queue with the reference's comparator (environment.ipp:247-263) on random push/pop sequences
+// with heavy key ties: every popped token must be the SAME token (the tag identifies it), i.e. the tie order
+// is libstdc++'s.  The CUDA keywords are defined away; one "thread", stride 1.
+#include <cstdint>
+#include <cstdio>
+#include <queue>
+#include <random>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __forceinline__ inline
+struct fake_dim3 { unsigned x, y, z; };
+static fake_dim3 threadIdx{0, 0, 0}, blockDim{1, 1, 1};
+static inline void __syncthreads() {}
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+using std::min;
+
+#include "device/engine32.cuh"
+
+using namespace cxb;
+
+namespace {
+
+struct ref_token {
+    uint64_t time;
+    int64_t priority;
+    uint32_t tag;
+};
+struct ref_comp {   // token_comp: a is "less" (pops later) when it is strictly later / lower priority
+    bool operator()(const ref_token &a, const ref_token &b) const {
+        return a.time > b.time || (a.time == b.time && a.priority > b.priority);
+    }
+};
+
+int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span) {
+    std::mt19937 rng(seed);
+    std::vector<uint2> storage(capacity);
+    environment32<1> env;
+    env.init(storage.data(), capacity);
+    std::priority_queue<ref_token, std::vector<ref_token>, ref_comp> ref;
+    uint32_t next_tag = 1, now = 0;
+    for (int k = 0; k < n_ops; ++k) {
+        const bool push = ref.empty() || ((int)ref.size() < capacity && rng() % 100 < 55);
+        if (push) {
+            const uint32_t t = now + rng() % time_span;       // few distinct times: many ties
+            env.schedule(t, next_tag);
+            ref.push(ref_token{t, 0, next_tag});
+            ++next_tag;
+        } else {
+            const token32 got = env.step_pop();
+            const ref_token want = ref.top();
+            ref.pop();
+            if (got.time != want.time || got.tag != want.tag) {
+                std::fprintf(stderr, "engine32: seed %u op %d: popped (%u, %u), std::priority_queue (%llu, %u)\n", seed, k,
+                             got.time, got.tag, (unsigned long long)want.time, want.tag);
+                return 1;
+            }
+            now = got.time;
+        }
+        if (env.n != (int)ref.size() || env.status) return 1;
+    }
+    return 0;
+}
+
+int check64(uint32_t seed, int capacity, int n_ops, uint32_t time_span) {
+    std::mt19937 rng(seed);
+    std::vector<uint64_t> keys(capacity);
+    std::vector<uint32_t> tags(capacity);
+    environment env;
+    lane_array<uint64_t> k{keys.data(), 1};
+    lane_array<uint32_t> t{tags.data(), 1};
+    env.init(k, t, capacity);
+    std::priority_queue<ref_token, std::vector<ref_token>, ref_comp> ref;
+    uint32_t next_tag = 1;
+    int64_t now = 0;
+    for (int op = 0; op < n_ops; ++op) {
+        const bool push = ref.empty() || ((int)ref.size() < capacity && rng() % 100 < 55);
+        if (push) {
+            const int64_t time = now + rng() % time_span;
+            const int64_t prio = (int64_t)(rng() % 3) - 1;    // priorities -1, 0, 1: ties on (time, priority)
+            env.schedule(time, prio, next_tag);
+            ref.push(ref_token{(uint64_t)time, prio, next_tag});
+            ++next_tag;
+        } else {
+            const token got = env.pop_top();
+            const ref_token want = ref.top();
+            ref.pop();
+            if ((uint64_t)key_time(got.key) != want.time || key_prio(got.key) != want.priority || got.tag != want.tag) {
+                std::fprintf(stderr, "engine: seed %u op %d: wrong token popped\n", seed, op);
+                return 1;
+            }
+            now = key_time(got.key);
+        }
+        if (env.n != (int)ref.size() || env.status) return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int main() {
+    int bad = 0;
+    long ops = 0;
+    for (uint32_t seed = 1; seed <= 40; ++seed) {
+        for (int capacity : {2, 3, 7, 8, 33, 64, 66, 200}) {
+            for (uint32_t span : {1u, 2u, 5u, 1000u}) {
+                bad += check32(seed * 7919u + capacity, capacity, 3000, span);
+                bad += check64(seed * 104729u + capacity, capacity, 3000, span);
+                ops += 6000;
+            }
+        }
+    }
+    std::printf("device heaps vs std::priority_queue: %ld operations, %d mismatching runs\n", ops, bad);
+    return bad ? 1 : 0;
+}

@@ -129,3 +129,19 @@ def test_restated_heap_matches_libstdcxx(port):
     f.restype = C.c_uint64
     for seed, key_range, max_size in [(1, 4, 3), (2, 8, 64), (3, 3, 65), (4, 1000, 48), (5, 2, 7), (6, 16, 200)]:
         assert f(C.c_uint64(seed), C.c_uint64(200000), C.c_uint32(key_range), C.c_uint32(max_size)) == 0
+
+
+def test_device_heaps_match_std_priority_queue(tmp_path):
+    """The event heaps the CUDA kernels run (csrc/device/engine.cuh, engine32.cuh with its two-level look-ahead),
+    compiled with g++: every pop returns the same token as std::priority_queue with the reference's comparator
+    (environment.ipp:247-263) on 7.7 M random operations with heavy key ties -- the tie order is libstdc++'s."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "device_heap_host"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
+                    f"-I{root / 'include'}", f"-I{root / 'libcxxdes_b200' / 'csrc'}",
+                    str(root / "tests" / "native" / "device_heap_host.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatching runs" in r.stdout

@@ -178,8 +178,12 @@ typedef struct cxxdes_b200_program {
     const uint64_t *queue_max;  /* per queue: max_size, 0 = unbounded (sync/queue.hpp:38)                 */
     const uint64_t *sem_init;   /* per semaphore: initial value                                           */
     const uint64_t *sem_max;    /* per semaphore: max (resource{c} = {c, c}, sync/resource.hpp:78)        */
-    const double *rates;        /* rates of the exponential draws                                         */
+    const double *rates;        /* rates of the exponential draws: max(1, sweep_steps) rows of n_rates     */
     uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
+    uint32_t sweep_steps;       /* parameter sweep inside ONE ensemble (the loop of the examples' main(),
+                                   producer_consumer.cpp:67-73, aloha.cpp:93-103): replication r draws with row
+                                   (first_replication + r) % sweep_steps of `rates`; 0 = one row              */
+    uint32_t reserved;
 } cxxdes_b200_program;
 
 /* ---- per-replication results, structure of arrays (one entry per replication) ----

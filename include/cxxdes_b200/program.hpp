@@ -73,13 +73,17 @@ constexpr lazy_instant_t lazy_instant{};
 
 struct exponential {  // examples/random_variable.hpp:17-40, drawn from the Philox stream of the awaiting process
     double rate;
+    std::vector<double> per_point;   // a swept rate: one value per sweep point (program::sweep)
+    exponential(double r) : rate(r) {}
+    exponential(std::vector<double> points) : rate(0), per_point(std::move(points)) {}
 };
 struct env_timeout_t {  // env.timeout(double seconds) / env.timeout(random variable): timeout.ipp:184-187
     bool random;
     double value;
+    std::vector<double> per_point;
 };
-inline env_timeout_t env_timeout(double seconds) { return {false, seconds}; }
-inline env_timeout_t env_timeout(exponential rv) { return {true, rv.rate}; }
+inline env_timeout_t env_timeout(double seconds) { return {false, seconds, {}}; }
+inline env_timeout_t env_timeout(exponential rv) { return {true, rv.rate, std::move(rv.per_point)}; }
 
 struct process {  // a coroutine<> object of the model
     std::uint32_t id;
@@ -198,6 +202,11 @@ public:
         o.priority = priority;
         return add_process(ordinal, o);
     }
+    // A parameter sweep inside ONE ensemble -- the loop over load points of the examples' main()
+    // (producer_consumer.cpp:67-73, aloha.cpp:93-103): replication r uses point r % steps of every rate that was
+    // given one value per point, `exponential{std::vector<double>}`.
+    void sweep(std::uint32_t steps) { sweep_steps_ = steps; }
+
     // env.bind(p): simulation<> binds co_main; several roots are allowed (examples/clocks.cpp)
     void bind(process p) { roots_.push_back(p.id); }
 
@@ -236,7 +245,16 @@ public:
         p.queue_max = queue_max_.empty() ? &zero_ : queue_max_.data();
         p.sem_init = sem_init_.empty() ? &zero_ : sem_init_.data();
         p.sem_max = sem_max_.empty() ? &zero_ : sem_max_.data();
-        p.rates = rates_.empty() ? &zero_rate_ : rates_.data();
+        const std::size_t rows = sweep_steps_ ? sweep_steps_ : 1;
+        rate_table_.clear();
+        for (std::size_t step = 0; step < rows; ++step)
+            for (const std::vector<double> &r : rates_) {
+                if (r.size() != 1 && r.size() != rows)
+                    throw std::runtime_error("cxxdes_b200: a swept rate needs one value per sweep point");
+                rate_table_.push_back(r.size() == 1 ? r[0] : r[step]);
+            }
+        p.rates = rate_table_.empty() ? &zero_rate_ : rate_table_.data();
+        p.sweep_steps = sweep_steps_;
         p.n_ops = (std::uint32_t)ops_.size();
         p.n_procs = (std::uint32_t)procs_.size();
         p.n_roots = (std::uint32_t)roots_.size();
@@ -259,14 +277,20 @@ private:
         return (std::uint32_t)ops_.size() - 1;
     }
     std::uint16_t rate(double value) {
-        rates_.push_back(value);
+        rates_.push_back({value});
+        return (std::uint16_t)(rates_.size() - 1);
+    }
+    std::uint16_t rate(const std::vector<double> &per_point) {
+        rates_.push_back(per_point);
         return (std::uint16_t)(rates_.size() - 1);
     }
     std::vector<cxxdes_b200_op> ops_;
     std::vector<cxxdes_b200_process> procs_;
     std::vector<std::uint32_t> roots_;
     std::vector<std::uint64_t> queue_max_, sem_init_, sem_max_;
-    std::vector<double> rates_;
+    std::vector<std::vector<double>> rates_;      // one value, or one per sweep point
+    mutable std::vector<double> rate_table_;      // [sweep point][rate], built by c_struct()
+    std::uint32_t sweep_steps_ = 0;
     std::uint32_t n_mutexes_ = 0, n_events_ = 0;
     std::uint64_t zero_ = 0;
     double zero_rate_ = 0.0;
@@ -293,7 +317,8 @@ public:
     }
     body &await(env_timeout_t t) {  // co_await env.timeout(x)
         if (t.random) {
-            prog_.emit(CXXDES_B200_OP_DELAY_EXP, prog_.rate(t.value), CXXDES_B200_INHERIT, 0);
+            prog_.emit(CXXDES_B200_OP_DELAY_EXP, t.per_point.empty() ? prog_.rate(t.value) : prog_.rate(t.per_point),
+                       CXXDES_B200_INHERIT, 0);
         } else {
             std::int64_t bits;
             std::memcpy(&bits, &t.value, sizeof bits);

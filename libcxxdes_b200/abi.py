@@ -76,7 +76,8 @@ class ProgramParams(C.Structure):
                 ("queue_max", C.POINTER(C.c_uint64)), ("sem_init", C.POINTER(C.c_uint64)),
                 ("sem_max", C.POINTER(C.c_uint64)), ("rates", C.POINTER(C.c_double)),
                 ("n_ops", C.c_uint32), ("n_procs", C.c_uint32), ("n_roots", C.c_uint32), ("n_queues", C.c_uint32),
-                ("n_sems", C.c_uint32), ("n_mutexes", C.c_uint32), ("n_events", C.c_uint32), ("n_rates", C.c_uint32)]
+                ("n_sems", C.c_uint32), ("n_mutexes", C.c_uint32), ("n_events", C.c_uint32), ("n_rates", C.c_uint32),
+                ("sweep_steps", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Columns(C.Structure):

@@ -153,7 +153,7 @@ int upload_program(cxxdes_b200_ensemble *e) {
     auto pad = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const size_t s_ops = pad(sizeof(cxxdes_b200_op) * p.n_ops), s_procs = pad(sizeof(cxxdes_b200_process) * p.n_procs),
                  s_roots = pad(4 * p.n_roots), s_q = pad(8 * p.n_queues), s_s = pad(8 * p.n_sems),
-                 s_r = pad(sizeof(divisor) * p.n_rates);
+                 s_r = pad(sizeof(divisor) * p.n_rates * (p.sweep_steps ? p.sweep_steps : 1));
     const size_t total = s_ops + s_procs + s_roots + s_q + 2 * s_s + s_r + 16;
     unsigned char *host = new (std::nothrow) unsigned char[total]();
     if (!host) return fail(CXXDES_B200_ERR_INVALID, "out of host memory");
@@ -171,7 +171,7 @@ int upload_program(cxxdes_b200_ensemble *e) {
     const size_t o_si = put(p.sem_init, 8 * p.n_sems, s_s);
     const size_t o_sm = put(p.sem_max, 8 * p.n_sems, s_s);
     const size_t o_r = off;
-    for (uint32_t k = 0; k < p.n_rates; ++k) {
+    for (uint32_t k = 0; k < p.n_rates * (p.sweep_steps ? p.sweep_steps : 1); ++k) {
         if (!(p.rates[k] > 0.0)) {
             delete[] host;
             return fail(CXXDES_B200_ERR_INVALID, "program: rates must be > 0");
@@ -199,6 +199,7 @@ int upload_program(cxxdes_b200_ensemble *e) {
     d.rates = (const divisor *)(e->program_blob + o_r);
     d.n_ops = p.n_ops; d.n_procs = p.n_procs; d.n_roots = p.n_roots; d.n_queues = p.n_queues;
     d.n_sems = p.n_sems; d.n_mutexes = p.n_mutexes; d.n_events = p.n_events; d.n_rates = p.n_rates;
+    d.sweep_steps = p.sweep_steps;
     memset(&e->params.program, 0, sizeof(e->params.program));  // the host pointers are not ours to keep
     return CXXDES_B200_OK;
 }

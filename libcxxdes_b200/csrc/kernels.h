@@ -81,6 +81,7 @@ struct device_program {  // cxxdes_b200_program with device pointers; rates as {
     const uint64_t *sem_max;
     const divisor *rates;
     uint32_t n_ops, n_procs, n_roots, n_queues, n_sems, n_mutexes, n_events, n_rates;
+    uint32_t sweep_steps;   // rows of `rates` (0 = 1): replication r draws with row (first_replication + r) % sweep_steps
 };
 const char *program_check(const cxxdes_b200_program &p);  // nullptr when the interpreter supports it
 // First pass with the per-replication state in shared memory (program_fast.cu): word offsets sized from the program.

@@ -60,6 +60,7 @@ struct machine {
     int64_t *items; // queue payloads in global memory, this thread's column
     uint32_t item_stride;
     stream_addr addr;
+    uint32_t rate_base;   // parameter sweep: first rate of this replication's row
 
     __device__ machine(const device_program &p, const shard &s, const program_fast_layout &l, const log_entry *t)
         : prg(p), sh(s), L(l), table(t) {}
@@ -482,6 +483,7 @@ struct machine {
         env.n = 0;
         addr.seed = sh.seed;
         addr.replication = sh.first_replication + rep;
+        rate_base = prg.sweep_steps ? (uint32_t)((sh.first_replication + rep) % prg.sweep_steps) * prg.n_rates : 0u;
         for (int k = 0; k < L.n_words; ++k) w(k) = 0;
         for (int k = 0; k < L.n_dwords; ++k) d(k) = 0;
         for (uint32_t p = 0; p < prg.n_procs; ++p) fresh(p);
@@ -544,6 +546,7 @@ struct machine {
         env.status = 0;
         addr.seed = sh.seed;
         addr.replication = sh.first_replication + rep;
+        rate_base = prg.sweep_steps ? (uint32_t)((sh.first_replication + rep) % prg.sweep_steps) * prg.n_rates : 0u;
         for (int k = 0; k < L.n_words; ++k) w(k) = s[(size_t)(8 + k) * n];
         for (int k = 0; k < L.n_dwords; ++k)
             d(k) = (uint64_t)s[(size_t)(8 + L.n_words + 2 * k) * n] | ((uint64_t)s[(size_t)(8 + L.n_words + 2 * k + 1) * n] << 32);
@@ -691,7 +694,7 @@ program_fast_kernel(device_program prg_in, shard sh, device_columns out, program
                     const uint32_t draw = m.w(b + L.o_draws);
                     m.w(b + L.o_draws) = draw + 1;
                     m.addr.stream = prg.procs[target].ordinal;
-                    v = exponential(m.addr, (uint64_t)draw, prg.rates[timer.a], table);
+                    v = exponential(m.addr, (uint64_t)draw, prg.rates[m.rate_base + timer.a], table);
                 } else {
                     v = bits_as_double((uint64_t)timer.value);
                 }

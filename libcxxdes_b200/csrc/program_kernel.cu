@@ -74,6 +74,7 @@ struct interp {
     double f64[CXXDES_B200_N_F64];
     int64_t i64[CXXDES_B200_N_I64];
     stream_addr addr;
+    uint32_t rate_base;   // parameter sweep: first rate of this replication's row
 
     __device__ interp(const device_program &p, const shard &s, const log_entry *t) : prg(p), sh(s), table(t) {}
 
@@ -246,7 +247,7 @@ struct interp {
                     return;
                 case CXXDES_B200_OP_DELAY_EXP: {
                     addr.stream = prg.procs[p].ordinal;
-                    const double v = exponential(addr, (uint64_t)self.draws++, prg.rates[op.a], table);
+                    const double v = exponential(addr, (uint64_t)self.draws++, prg.rates[rate_base + op.a], table);
                     env.schedule(env.now + real_to_sim(v, sh.clk), op_priority(op, self), ptag(p));
                     ++self.pc;
                     return;
@@ -454,6 +455,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
         it.env.init(hkey, htag, heap_cap);
         it.addr.seed = sh.seed;
         it.addr.replication = sh.first_replication + rep;
+        it.rate_base = prg.sweep_steps ? (uint32_t)((sh.first_replication + rep) % prg.sweep_steps) * prg.n_rates : 0u;
         it.next_serial = 0;
         for (int k = 0; k < CXXDES_B200_N_F64; ++k) it.f64[k] = 0.0;
         for (int k = 0; k < CXXDES_B200_N_I64; ++k) it.i64[k] = 0;
@@ -522,6 +524,7 @@ const char *program_check(const cxxdes_b200_program &p) {
     if (p.n_queues > PRG_MAX_OBJ || p.n_sems > PRG_MAX_OBJ || p.n_mutexes > PRG_MAX_OBJ || p.n_events > PRG_MAX_OBJ)
         return "program: at most 4 sync objects of each kind";
     if (p.n_rates > 16) return "program: at most 16 rates";
+    if (p.sweep_steps > 4096) return "program: at most 4096 sweep points";
     if (!p.ops || !p.procs || !p.roots) return "program: ops/procs/roots must not be NULL";
     // no path may run off the end of the program: the last body ends with co_return, jump targets lie inside
     if (p.ops[p.n_ops - 1].code != CXXDES_B200_OP_RETURN) return "program: the last op must be RETURN";

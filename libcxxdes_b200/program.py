@@ -177,6 +177,7 @@ class Program:
         self._n_mutexes = 0
         self._n_events = 0
         self._rates = []
+        self._sweep_steps = 0
         self._keep = None
 
     def process(self, ordinal, priority=None, latency=0, return_latency=0, return_priority=None, root=False):
@@ -232,8 +233,15 @@ class Program:
         self._n_events += 1
         return self._n_events - 1
 
+    def sweep(self, steps):
+        """A parameter sweep inside one ensemble -- the loop over load points in the examples' main()
+        (producer_consumer.cpp:67-73, aloha.cpp:93-103): replication r uses point r % steps of every rate given
+        as a sequence of `steps` values."""
+        self._sweep_steps = int(steps)
+
     def rate(self, value):
-        self._rates.append(float(value))
+        """One rate, or one per sweep point (a sequence of sweep() values)."""
+        self._rates.append([float(v) for v in value] if hasattr(value, "__len__") else float(value))
         return len(self._rates) - 1
 
     def to_params(self):
@@ -250,8 +258,18 @@ class Program:
         qmax = (C.c_uint64 * max(1, len(self._queue_max)))(*self._queue_max)
         sinit = (C.c_uint64 * max(1, len(self._sems)))(*[s[0] for s in self._sems])
         smax = (C.c_uint64 * max(1, len(self._sems)))(*[s[1] for s in self._sems])
-        rates = (C.c_double * max(1, len(self._rates)))(*self._rates)
+        rows = max(1, self._sweep_steps)
+        table = []
+        for step in range(rows):
+            for r in self._rates:
+                if isinstance(r, list):
+                    if len(r) != rows:
+                        raise ValueError("a swept rate needs one value per sweep point")
+                    table.append(r[step])
+                else:
+                    table.append(r)
+        rates = (C.c_double * max(1, len(table)))(*table)
         self._keep = (ops, procs, roots, qmax, sinit, smax, rates)
         return abi.ProgramParams(ops, procs, roots, qmax, sinit, smax, rates, len(self._ops), len(self._procs),
                                  len(self._roots), len(self._queue_max), len(self._sems), self._n_mutexes,
-                                 self._n_events, len(self._rates))
+                                 self._n_events, len(self._rates), self._sweep_steps, 0)

@@ -72,6 +72,22 @@ def aloha_sweep_table(columns, sweep_steps, qs=(0.05, 0.95)):
     return "\n".join(lines)
 
 
+def sweep_table(columns, sweep_steps, stat=0, scale=1.0, labels=None, first_replication=0, name="stat"):
+    """One row per point of a parameter sweep run as ONE ensemble (Program.sweep / cxxdes_b200_program.sweep_steps:
+    replication r ran point (first_replication + r) % sweep_steps): mean of f64[stat] * scale over the
+    replications of the point and the half-width of its 95 % interval."""
+    x = np.asarray(columns.f64[stat], dtype=np.float64) * scale
+    point = (first_replication + np.arange(len(x))) % sweep_steps
+    lines = [f"point, {name}, ci95, replications"]
+    for step in range(sweep_steps):
+        v = x[point == step]
+        if not len(v):
+            continue
+        half = 1.959964 * v.std(ddof=1) / math.sqrt(len(v)) if len(v) > 1 else float("nan")
+        lines.append(f"{labels[step] if labels is not None else step}, {v.mean():.6g}, {half:.3g}, {len(v)}")
+    return "\n".join(lines)
+
+
 def summary(acc, names_f64=("f64[0]", "f64[1]"), names_i64=("i64[0]", "i64[1]"), run_ms=None):
     """A JSON-ready dict of one ensemble run: counts, checksum of checksums, and per statistic the ensemble mean
     with its 95 % interval (from the reduced accumulators alone)."""

@@ -17,6 +17,7 @@ struct program_model {
     cxxdes_b200::clock_config clk;
     const cxxdes_b200_program &prg;
     cxxdes_b200::stream_addr addr;
+    uint64_t rate_row;   // parameter sweep: this replication's row of prg.rates (cxxdes_b200.h, sweep_steps)
 
     struct runtime {
         uint32_t pc = 0;
@@ -34,7 +35,7 @@ struct program_model {
     uint32_t status = 0;
 
     program_model(const cxxdes_b200_program &p, const cxxdes_b200_clock &c, uint64_t seed, uint64_t rep)
-        : clk(fold_clock(c)), prg(p), addr{seed, rep, 0} {
+        : clk(fold_clock(c)), prg(p), addr{seed, rep, 0}, rate_row(p.sweep_steps ? rep % p.sweep_steps : 0) {
         rt.resize(p.n_procs);
         for (uint32_t i = 0; i < p.n_procs; ++i) {
             eng.add_process(p.procs[i].ordinal, p.procs[i].priority, p.procs[i].latency);
@@ -136,7 +137,7 @@ struct program_model {
                 }
                 case CXXDES_B200_OP_DELAY_EXP: {
                     addr.stream = prg.procs[p].ordinal;
-                    double v = cxxdes_b200::exponential(addr, (uint64_t)r.draws++, cxxdes_b200::make_divisor(prg.rates[op.a]),
+                    double v = cxxdes_b200::exponential(addr, (uint64_t)r.draws++, cxxdes_b200::make_divisor(prg.rates[rate_row * prg.n_rates + op.a]),
                                                         cxxdes_b200::LOG_TABLE_HOST);
                     eng.timeout(p, cxxdes_b200::real_to_sim(v, clk), prio_of(op));
                     ++r.pc;

@@ -86,7 +86,8 @@ struct program_sim {
             handles.emplace_back();
         }
         for (uint32_t e = 0; e < p.n_events; ++e) events.emplace_back();
-        for (uint32_t r = 0; r < p.n_rates; ++r) rates.push_back(cxxdes_b200::make_divisor(p.rates[r]));
+        const uint64_t row = p.sweep_steps ? rep_ % p.sweep_steps : 0;   // parameter sweep: this replication's rates
+        for (uint32_t r = 0; r < p.n_rates; ++r) rates.push_back(cxxdes_b200::make_divisor(p.rates[row * p.n_rates + r]));
         for (uint32_t k = 0; k < p.n_procs; ++k) fresh(k);
         for (uint32_t r = 0; r < p.n_roots; ++r) env.bind(*procs[p.roots[r]].co);   // coroutine.ipp:352-357
     }

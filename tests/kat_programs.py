@@ -232,8 +232,11 @@ EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10
 
 def mm1_program(lam, mu, n_packets):
     """examples/producer_consumer.cpp:31-58 as a process program (same ordinals / streams as the
-    hand-written kernels: co_main 0, producer 1, consumer 2); f64[1] = total_latency, i64[0] = packets consumed."""
+    hand-written kernels: co_main 0, producer 1, consumer 2); f64[1] = total_latency, i64[0] = packets consumed.
+    `lam` may be a sequence: the load sweep of the example's main() inside one ensemble (Program.sweep)."""
     prog = Program()
+    if hasattr(lam, "__len__"):
+        prog.sweep(len(lam))
     q = prog.queue()
     main = prog.process(0, root=True)
     prod, cons = prog.process(1), prog.process(2)

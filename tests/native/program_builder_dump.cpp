@@ -27,8 +27,10 @@ static void dump(const char *name, const program &prog, bool last = false) {
     for (std::uint32_t i = 0; i < p.n_sems; ++i)
         std::printf("%s[%" PRIu64 ", %" PRIu64 "]", i ? ", " : "", p.sem_init[i], p.sem_max[i]);
     std::printf("], \"rates\": [");
-    for (std::uint32_t i = 0; i < p.n_rates; ++i) std::printf("%s%.17g", i ? ", " : "", p.rates[i]);
-    std::printf("], \"n_mutexes\": %u, \"n_events\": %u}%s\n", p.n_mutexes, p.n_events, last ? "" : ",");
+    for (std::uint32_t i = 0; i < p.n_rates * (p.sweep_steps ? p.sweep_steps : 1); ++i)
+        std::printf("%s%.17g", i ? ", " : "", p.rates[i]);
+    std::printf("], \"sweep_steps\": %u, \"n_mutexes\": %u, \"n_events\": %u}%s\n", p.sweep_steps, p.n_mutexes, p.n_events,
+                last ? "" : ",");
 }
 
 // examples/producer_consumer.cpp:31-58
@@ -41,6 +43,30 @@ static program mm1(double lam, double mu, std::int64_t n_packets) {
         co.loop(n_packets, [&] {
             co.await(q.put());
             co.await(env_timeout(exponential{lam}));
+        });
+    });
+    prog.body_of(consumer, [&](body &co) {
+        co.loop(n_packets - 1, [&] {
+            co.await(q.pop()).count(0);
+            co.await(env_timeout(exponential{mu})).stat_seconds(1);
+        });
+        co.await(q.pop()).count(0);
+    });
+    prog.body_of(co_main, [&](body &co) { co.await(producer && consumer); });
+    return prog;
+}
+
+// the load sweep of examples/producer_consumer.cpp:61-75 inside one ensemble: lambda differs per sweep point
+static program mm1_sweep(const std::vector<double> &lambdas, double mu, std::int64_t n_packets) {
+    program prog;
+    prog.sweep((std::uint32_t)lambdas.size());
+    queue q = prog.add_queue();
+    process co_main = prog.add_process(0), producer = prog.add_process(1), consumer = prog.add_process(2);
+    prog.bind(co_main);
+    prog.body_of(producer, [&](body &co) {
+        co.loop(n_packets, [&] {
+            co.await(q.put());
+            co.await(env_timeout(exponential{lambdas}));
         });
     });
     prog.body_of(consumer, [&](body &co) {
@@ -266,6 +292,7 @@ static program sequential_example() {
 int main() {
     std::printf("{\n");
     dump("mm1", mm1(5.0, 10.0, 300));
+    dump("mm1_sweep", mm1_sweep({1.0, 3.0, 5.0, 7.0, 9.0}, 10.0, 300));
     dump("1", compositions());
     dump("2", latencies());
     dump("4", priorities());

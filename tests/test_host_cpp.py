@@ -50,7 +50,8 @@ def _python_tables(prog):
             "procs": [[p["entry"], p["ordinal"], p["priority"], p["latency"], p["return_latency"], p["return_priority"]]
                       for p in prog._procs],
             "roots": list(prog._roots), "queue_max": list(prog._queue_max), "sems": [list(x) for x in prog._sems],
-            "rates": list(prog._rates), "n_mutexes": prog._n_mutexes, "n_events": prog._n_events}
+            "rates": [r[step] if isinstance(r, list) else r for step in range(max(1, prog._sweep_steps)) for r in prog._rates],
+            "sweep_steps": prog._sweep_steps, "n_mutexes": prog._n_mutexes, "n_events": prog._n_events}
 
 
 def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
@@ -69,6 +70,7 @@ def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
     assert r.returncode == 0           # also: the three misuse cases threw
     got = json.loads(r.stdout)
     assert got.pop("mm1") == _python_tables(K.mm1_program(5.0, 10.0, 300))
+    assert got.pop("mm1_sweep") == _python_tables(K.mm1_program([1.0, 3.0, 5.0, 7.0, 9.0], 10.0, 300))
     assert sorted(got) == sorted(str(k) for k in (1, 2, 4, 5, 6, 7, 9, 10, 11, 14, 15))
     for k, tables in got.items():
         assert tables == _python_tables(K.SCENARIOS[int(k)]()[0]), K.SCENARIOS[int(k)].__name__

@@ -68,6 +68,45 @@ def test_mm1_program_equals_hand_lowered_model(port):
         assert np.array_equal(a.f64[1].view(np.uint64), b.f64[1].view(np.uint64))
 
 
+SWEEP = [1.0, 3.0, 5.0, 7.0, 9.0]
+
+
+def test_parameter_sweep_inside_one_ensemble(port, ref):
+    """Program.sweep: replication r runs load point (first_replication + r) % steps -- the loop over lambda of
+    examples/producer_consumer.cpp:67-73 as one ensemble.  Reference engine == CPU interpreter, every point equals
+    the single-rate program of that lambda, and the split into shards does not matter."""
+    prog = K.mm1_program(SWEEP, 10.0, 200)
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 11, 3, 30, threads=4)
+    b = ref.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 11, 3, 30, threads=4)
+    golden_util.assert_columns_equal(a, b, what="sweep: reference engine")
+    for r in (0, 1, 7, 29):
+        lam = SWEEP[(3 + r) % len(SWEEP)]
+        one = port.run(abi.MODEL_PROGRAM, K.mm1_program(lam, 10.0, 200).to_params(), oracles.MM1_CLOCK, 11, 3 + r, 1)
+        assert one.trace_hash[0] == a.trace_hash[r] and one.end_time[0] == a.end_time[r]
+
+
+@pytest.mark.gpu
+def test_gpu_parameter_sweep_matches_oracle_and_theory(port):
+    prog = K.mm1_program(SWEEP, 10.0, 3000)
+    n_reps = 2000
+    for no_fast in (False, True):
+        if no_fast:
+            os.environ["CXXDES_B200_PRG_NO_FAST"] = "1"
+        try:
+            ens = L.Ensemble(prog, n_reps, seed=11, first_replication=3)
+            ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+            got = ens.run().fetch()
+            ens.close()
+        finally:
+            os.environ.pop("CXXDES_B200_PRG_NO_FAST", None)
+        want = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 11, 3, n_reps, threads=os.cpu_count())
+        golden_util.assert_columns_equal(got, want, what=f"sweep (full-size kernel only: {no_fast})")
+    for step, lam in enumerate(SWEEP[:4]):              # rho <= 0.7: steady state within 3000 packets
+        sel = (3 + np.arange(n_reps)) % len(SWEEP) == step
+        latency = got.f64[1][sel].mean() / 3000
+        assert abs(latency - 1.0 / (10.0 - lam)) < 0.08 / (10.0 - lam)
+
+
 def test_builder_rejects_incomplete_programs():
     prog = L.Program()
     prog.process(0, root=True)

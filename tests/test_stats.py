@@ -74,3 +74,15 @@ def test_aloha_sweep_table_and_writers(port, tmp_path):
     assert len(lines) == 41 and lines[0].split(", ")[5] == "S"
     r7 = lines[8].split(", ")
     assert int(r7[1]) == cols.end_time[7] and float(r7[5]) == cols.f64[0][7] and int(r7[3], 16) == cols.trace_hash[7]
+
+
+def test_sweep_table_groups_by_point(port):
+    import kat_programs as K
+    lams = [2.0, 5.0, 8.0]
+    prog = K.mm1_program(lams, 10.0, 400)
+    cols = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 5, 1, 60, threads=4)
+    rows = stats.sweep_table(cols, 3, stat=1, scale=1.0 / 400, labels=lams, first_replication=1, name="latency").splitlines()
+    assert rows[0] == "point, latency, ci95, replications" and len(rows) == 4
+    means = [float(r.split(", ")[1]) for r in rows[1:]]
+    assert [r.split(", ")[0] for r in rows[1:]] == ["2.0", "5.0", "8.0"] and means[0] < means[1] < means[2]
+    assert abs(means[1] - 0.2) < 0.03 and all(r.endswith(", 20") for r in rows[1:])

@@ -150,8 +150,21 @@ enum {
                                        i64[1] = i64[1] * 1000003 + (now() * imm + b)   (wrapping)              */
     CXXDES_B200_OP_LAZY_TIMEOUT = 28,/* reg = now() + imm: `auto t = co_await lazy_timeout(imm)` fixes an absolute
                                        deadline without suspending (timeout.ipp:104-172)                        */
-    CXXDES_B200_OP_UNTIL_REG = 29   /* co_await t / co_await instant(reg): until(reg), b = priority or INHERIT    */
+    CXXDES_B200_OP_UNTIL_REG = 29,  /* co_await t / co_await instant(reg): until(reg), b = priority or INHERIT    */
+    CXXDES_B200_OP_IF = 30,         /* if (!(value cmp imm)) goto b: structured if / else on the model's own state.
+                                       a = index | source << 8 | comparison << 12 (CXXDES_B200_SRC_*, _CMP_*);
+                                       b = first op after the then-block (forward)                               */
+    CXXDES_B200_OP_JUMP = 31        /* goto b (forward): the end of a then-block jumps over the else-block       */
 };
+enum {  /* what an IF looks at: plain reads of public state, no events */
+    CXXDES_B200_SRC_COUNTER = 0,    /* i64[index]                                        */
+    CXXDES_B200_SRC_QUEUE_SIZE = 1, /* queue[index].size()        (sync/queue.hpp:68-70) */
+    CXXDES_B200_SRC_SEM_VALUE = 2,  /* semaphore[index].value()   (semaphore.hpp:52-54)  */
+    CXXDES_B200_SRC_NOW = 3,        /* now()                                             */
+    CXXDES_B200_SRC_REGISTER = 4,   /* the process register                              */
+    CXXDES_B200_SRC_MUTEX = 5       /* mutex[index].is_acquired() (mutex.hpp:101-104)    */
+};
+enum { CXXDES_B200_CMP_EQ = 0, CXXDES_B200_CMP_NE, CXXDES_B200_CMP_LT, CXXDES_B200_CMP_LE, CXXDES_B200_CMP_GT, CXXDES_B200_CMP_GE };
 #define CXXDES_B200_INHERIT INT32_MAX /* priority_consts::inherit (defs.ipp:35) in the 32-bit b field */
 
 typedef struct cxxdes_b200_op {

@@ -146,6 +146,25 @@ inline composition operator||(composition a, child b) {
     return a;
 }
 
+// ---- conditions of if_then / if_then_else: plain reads of the model's own state (no events) --------------
+struct condition {
+    std::uint16_t a;     // index | source << 8 | comparison << 12 (cxxdes_b200.h)
+    std::int64_t value;
+};
+struct operand {         // something an `if` can look at; compare it with an integer to get a condition
+    std::uint16_t src, index;
+    condition cmp(int c, std::int64_t v) const { return {(std::uint16_t)(index | (src << 8) | (c << 12)), v}; }
+    condition operator==(std::int64_t v) const { return cmp(CXXDES_B200_CMP_EQ, v); }
+    condition operator!=(std::int64_t v) const { return cmp(CXXDES_B200_CMP_NE, v); }
+    condition operator<(std::int64_t v) const { return cmp(CXXDES_B200_CMP_LT, v); }
+    condition operator<=(std::int64_t v) const { return cmp(CXXDES_B200_CMP_LE, v); }
+    condition operator>(std::int64_t v) const { return cmp(CXXDES_B200_CMP_GT, v); }
+    condition operator>=(std::int64_t v) const { return cmp(CXXDES_B200_CMP_GE, v); }
+};
+inline operand counter(int k) { return {CXXDES_B200_SRC_COUNTER, (std::uint16_t)k}; }   // i64[k], what co.count(k) adds to
+inline operand now() { return {CXXDES_B200_SRC_NOW, 0}; }                                // env.now()
+inline operand process_register() { return {CXXDES_B200_SRC_REGISTER, 0}; }
+
 // sync objects hand out awaitable descriptors the way sync::queue / semaphore / mutex / event do
 struct simple_op {
     std::uint16_t code, a;
@@ -157,21 +176,25 @@ struct queue {  // sync::queue<T>: sync/queue.hpp:38-90
     simple_op put() const { return {CXXDES_B200_OP_Q_PUT, id, 0, 0}; }           // q.put(now)
     simple_op put_register() const { return {CXXDES_B200_OP_Q_PUT, id, 1, 0}; }  // q.put(<process register>)
     simple_op pop() const { return {CXXDES_B200_OP_Q_POP, id, 0, 0}; }           // register = q.pop()
+    operand size() const { return {CXXDES_B200_SRC_QUEUE_SIZE, id}; }            // q.size() in a condition
 };
 struct semaphore {  // sync::semaphore: sync/semaphore.hpp:58-78
     std::uint16_t id;
     simple_op up() const { return {CXXDES_B200_OP_SEM_UP, id, 0, 0}; }
     simple_op down() const { return {CXXDES_B200_OP_SEM_DOWN, id, 0, 0}; }
+    operand value() const { return {CXXDES_B200_SRC_SEM_VALUE, id}; }            // sem.value() in a condition
 };
 struct resource {  // sync::resource{count}: acquire = down, handle.release = up (sync/resource.hpp:37-100)
     std::uint16_t id;
     simple_op acquire() const { return {CXXDES_B200_OP_SEM_DOWN, id, 0, 0}; }
     simple_op release() const { return {CXXDES_B200_OP_SEM_UP, id, 0, 0}; }
+    operand available() const { return {CXXDES_B200_SRC_SEM_VALUE, id}; }        // free units in a condition
 };
 struct mutex {  // sync::mutex: sync/mutex.hpp:31-109
     std::uint16_t id;
     simple_op acquire() const { return {CXXDES_B200_OP_MTX_ACQUIRE, id, 0, 0}; }
     simple_op release() const { return {CXXDES_B200_OP_MTX_RELEASE, id, 0, 0}; }
+    operand is_acquired() const { return {CXXDES_B200_SRC_MUTEX, id}; }          // m.is_acquired() in a condition (0 / 1)
 };
 struct event {  // sync::event: sync/event.hpp:87-139
     std::uint16_t id;
@@ -359,6 +382,26 @@ public:
         fn();
         const std::uint32_t end = prog_.emit(CXXDES_B200_OP_END_LOOP, 0, (std::int32_t)(head + 1), 0);
         prog_.ops_[head].b = (std::int32_t)(end + 1);
+        return *this;
+    }
+
+    // if (cond) { then_(); } [else { else_(); }] -- the plain C++ control flow between the awaits, on the model's
+    // own state: co.if_then(q.size() < 5, [&] { co.await(q.put()); });
+    template <typename Then>
+    body &if_then(condition c, Then &&then_) {
+        const std::uint32_t at = prog_.emit(CXXDES_B200_OP_IF, c.a, 0, c.value);
+        then_();
+        prog_.ops_[at].b = (std::int32_t)prog_.ops_.size();
+        return *this;
+    }
+    template <typename Then, typename Else>
+    body &if_then_else(condition c, Then &&then_, Else &&else_) {
+        const std::uint32_t at = prog_.emit(CXXDES_B200_OP_IF, c.a, 0, c.value);
+        then_();
+        const std::uint32_t jump = prog_.emit(CXXDES_B200_OP_JUMP);
+        prog_.ops_[at].b = (std::int32_t)prog_.ops_.size();
+        else_();
+        prog_.ops_[jump].b = (std::int32_t)prog_.ops_.size();
         return *this;
     }
 

@@ -461,6 +461,24 @@ struct machine {
             case CXXDES_B200_OP_COUNT:
                 d(CXXDES_B200_N_F64 + op.a) += (uint64_t)op.imm;
                 break;
+            case CXXDES_B200_OP_IF: {   // plain C++ between the awaits: a read of the model's own state, no token
+                const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu, cmp = (op.a >> 12) & 0x7u;
+                int64_t v;
+                if (src == CXXDES_B200_SRC_COUNTER) v = (int64_t)d(CXXDES_B200_N_F64 + (int)idx);
+                else if (src == CXXDES_B200_SRC_QUEUE_SIZE) v = (int64_t)(w(L.w_queues + (int)idx) >> 16);
+                else if (src == CXXDES_B200_SRC_SEM_VALUE) v = (int64_t)w(L.w_sems + (int)idx);
+                else if (src == CXXDES_B200_SRC_NOW) v = env.now;
+                else if (src == CXXDES_B200_SRC_REGISTER) v = (int64_t)d(L.d_regs + (int)p);
+                else v = (w(L.w_mtx) >> idx) & 1u;
+                const bool taken = cmp == CXXDES_B200_CMP_EQ ? v == op.imm : cmp == CXXDES_B200_CMP_NE ? v != op.imm
+                                 : cmp == CXXDES_B200_CMP_LT ? v < op.imm : cmp == CXXDES_B200_CMP_LE ? v <= op.imm
+                                 : cmp == CXXDES_B200_CMP_GT ? v > op.imm : v >= op.imm;
+                if (!taken) next_pc = (uint32_t)op.b;
+                break;
+            }
+            case CXXDES_B200_OP_JUMP:
+                next_pc = (uint32_t)op.b;
+                break;
             case CXXDES_B200_OP_MARK:
                 d(CXXDES_B200_N_F64 + 0) += 1;
                 d(CXXDES_B200_N_F64 + 1) = d(CXXDES_B200_N_F64 + 1) * 1000003ULL + (uint64_t)(env.now * op.imm + (int64_t)op.b);
@@ -723,6 +741,9 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
                 break;
             case CXXDES_B200_OP_Q_PUT:
                 if (op.b) uses_reg = true;
+                break;
+            case CXXDES_B200_OP_IF:
+                if (((op.a >> 8) & 0xFu) == CXXDES_B200_SRC_REGISTER) uses_reg = true;
                 break;
             case CXXDES_B200_OP_DELAY_EXP:
                 uses_draws = true;

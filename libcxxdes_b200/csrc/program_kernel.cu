@@ -59,6 +59,11 @@ struct queue_rt {
     uint32_t head, count;
 };
 
+__device__ __forceinline__ bool branch_taken(uint32_t cmp, int64_t v, int64_t imm) {
+    return cmp == CXXDES_B200_CMP_EQ ? v == imm : cmp == CXXDES_B200_CMP_NE ? v != imm : cmp == CXXDES_B200_CMP_LT ? v < imm
+         : cmp == CXXDES_B200_CMP_LE ? v <= imm : cmp == CXXDES_B200_CMP_GT ? v > imm : v >= imm;
+}
+
 struct interp {
     environment env;
     const device_program &prg;
@@ -392,6 +397,21 @@ struct interp {
                     i64[op.a] += op.imm;
                     ++self.pc;
                     break;
+                case CXXDES_B200_OP_IF: {
+                    const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu;
+                    int64_t v;
+                    if (src == CXXDES_B200_SRC_COUNTER) v = i64[idx & (CXXDES_B200_N_I64 - 1)];
+                    else if (src == CXXDES_B200_SRC_QUEUE_SIZE) v = (int64_t)queues[idx & (PRG_MAX_OBJ - 1)].count;
+                    else if (src == CXXDES_B200_SRC_SEM_VALUE) v = (int64_t)sem_value[idx & (PRG_MAX_OBJ - 1)];
+                    else if (src == CXXDES_B200_SRC_NOW) v = env.now;
+                    else if (src == CXXDES_B200_SRC_REGISTER) v = self.reg;
+                    else v = mtx_owned[idx & (PRG_MAX_OBJ - 1)] ? 1 : 0;
+                    self.pc = branch_taken((op.a >> 12) & 0x7u, v, op.imm) ? self.pc + 1 : (uint32_t)op.b;
+                    break;
+                }
+                case CXXDES_B200_OP_JUMP:
+                    self.pc = (uint32_t)op.b;
+                    break;
                 case CXXDES_B200_OP_MARK:
                     ++i64[0];
                     i64[1] = (int64_t)((uint64_t)i64[1] * 1000003ULL + (uint64_t)(env.now * op.imm + (int64_t)op.b));
@@ -574,8 +594,19 @@ const char *program_check(const cxxdes_b200_program &p) {
             case CXXDES_B200_OP_COUNT:
                 if (op.a >= CXXDES_B200_N_I64) return "program: counter index out of range";
                 break;
+            case CXXDES_B200_OP_IF: {
+                const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu, cmp = (op.a >> 12) & 0x7u;
+                if (src > CXXDES_B200_SRC_MUTEX || cmp > CXXDES_B200_CMP_GE || (op.a >> 15)) return "program: bad IF operand";
+                if ((src == CXXDES_B200_SRC_COUNTER && idx >= CXXDES_B200_N_I64) ||
+                    (src == CXXDES_B200_SRC_QUEUE_SIZE && idx >= p.n_queues) || (src == CXXDES_B200_SRC_SEM_VALUE && idx >= p.n_sems) ||
+                    (src == CXXDES_B200_SRC_MUTEX && idx >= p.n_mutexes))
+                    return "program: IF operand index out of range";
+            }   // fall through: the target is checked like a jump's
+            case CXXDES_B200_OP_JUMP:
+                if (op.b <= (int64_t)i || (uint32_t)op.b >= p.n_ops) return "program: IF / JUMP target must lie ahead, inside the program";
+                break;
             default:
-                if (op.code > CXXDES_B200_OP_UNTIL_REG) return "program: unknown op code";
+                if (op.code > CXXDES_B200_OP_JUMP) return "program: unknown op code";
         }
     }
     return nullptr;

@@ -151,6 +151,42 @@ class Body:
 
         return _Loop()
 
+    # --- structured if / else on the model's own state (plain reads, no events) ---
+    def if_(self, source, index, cmp, value):
+        """`if (<source> <cmp> value) { ... }`: source is "counter" (i64[index]), "queue_size", "sem_value", "now",
+        "register" or "mutex" (is_acquired); use as `with b.if_("queue_size", q, "<", 5): ...`, optionally followed
+        at once by `with b.else_(): ...`."""
+        src = {"counter": abi.SRC_COUNTER, "queue_size": abi.SRC_QUEUE_SIZE, "sem_value": abi.SRC_SEM_VALUE,
+               "now": abi.SRC_NOW, "register": abi.SRC_REGISTER, "mutex": abi.SRC_MUTEX}[source]
+        body = self
+
+        class _If:
+            def __enter__(self_inner):
+                self_inner.at = body._emit(abi.OP_IF, int(index) | (src << 8) | (abi.CMP[cmp] << 12), 0, int(value))
+
+            def __exit__(self_inner, exc_type, *_):
+                if exc_type is None:
+                    body.prog._ops[self_inner.at][2] = len(body.prog._ops)
+                    body._last_if = self_inner.at
+        return _If()
+
+    def else_(self):
+        body = self
+        if_at = getattr(self, "_last_if", None)
+        if if_at is None or self.prog._ops[if_at][2] != len(self.prog._ops):
+            raise ValueError("else_() must follow its if_() block at once")
+
+        class _Else:
+            def __enter__(self_inner):
+                self_inner.at = body._emit(abi.OP_JUMP)           # the then-block ends by jumping over the else-block
+                body.prog._ops[if_at][2] = len(body.prog._ops)
+                body._last_if = None
+
+            def __exit__(self_inner, exc_type, *_):
+                if exc_type is None:
+                    body.prog._ops[self_inner.at][2] = len(body.prog._ops)
+        return _Else()
+
     def set_reg_now(self):                       # reg = now()
         self._emit(abi.OP_SET_REG_NOW)
 

@@ -271,6 +271,26 @@ struct program_model {
                     i64[op.a] += op.imm;
                     ++r.pc;
                     break;
+                case CXXDES_B200_OP_IF: {   // plain C++ between the awaits: no token
+                    const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu, cmp = (op.a >> 12) & 0x7u;
+                    int64_t v = 0;
+                    switch (src) {
+                        case CXXDES_B200_SRC_COUNTER: v = i64[idx]; break;
+                        case CXXDES_B200_SRC_QUEUE_SIZE: v = (int64_t)queues[idx].size(); break;
+                        case CXXDES_B200_SRC_SEM_VALUE: v = (int64_t)sem_value[idx]; break;
+                        case CXXDES_B200_SRC_NOW: v = eng.now; break;
+                        case CXXDES_B200_SRC_REGISTER: v = r.reg; break;
+                        default: v = mtx_owned[idx] ? 1 : 0; break;
+                    }
+                    const bool t = cmp == CXXDES_B200_CMP_EQ ? v == op.imm : cmp == CXXDES_B200_CMP_NE ? v != op.imm
+                                 : cmp == CXXDES_B200_CMP_LT ? v < op.imm : cmp == CXXDES_B200_CMP_LE ? v <= op.imm
+                                 : cmp == CXXDES_B200_CMP_GT ? v > op.imm : v >= op.imm;
+                    r.pc = t ? r.pc + 1 : (uint32_t)op.b;
+                    break;
+                }
+                case CXXDES_B200_OP_JUMP:
+                    r.pc = (uint32_t)op.b;
+                    break;
                 case CXXDES_B200_OP_MARK:
                     ++i64[0];
                     i64[1] = (int64_t)((uint64_t)i64[1] * 1000003ULL + (uint64_t)(eng.now * op.imm + (int64_t)op.b));

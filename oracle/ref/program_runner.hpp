@@ -232,6 +232,29 @@ struct program_sim {
                     ++i64[0];
                     i64[1] = (int64_t)((uint64_t)i64[1] * 1000003ULL + (uint64_t)((int64_t)env.now() * op.imm + (int64_t)op.b));
                     break;
+                case CXXDES_B200_OP_IF: {   // plain C++ between the awaits, on the library's own accessors
+                    const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu, cmp = (op.a >> 12) & 0x7u;
+                    int64_t v = 0;
+                    switch (src) {
+                        case CXXDES_B200_SRC_COUNTER: v = i64[idx]; break;
+                        case CXXDES_B200_SRC_QUEUE_SIZE: v = (int64_t)queues[idx].size(); break;
+                        case CXXDES_B200_SRC_SEM_VALUE: v = (int64_t)sems[idx].value(); break;
+                        case CXXDES_B200_SRC_NOW: v = (int64_t)env.now(); break;
+                        case CXXDES_B200_SRC_REGISTER: v = me.reg; break;
+                        default: v = mutexes[idx].is_acquired() ? 1 : 0; break;
+                    }
+                    const bool t = cmp == CXXDES_B200_CMP_EQ ? v == op.imm : cmp == CXXDES_B200_CMP_NE ? v != op.imm
+                                 : cmp == CXXDES_B200_CMP_LT ? v < op.imm : cmp == CXXDES_B200_CMP_LE ? v <= op.imm
+                                 : cmp == CXXDES_B200_CMP_GT ? v > op.imm : v >= op.imm;
+                    if (!t) {
+                        pc = (uint32_t)op.b;
+                        continue;
+                    }
+                    break;
+                }
+                case CXXDES_B200_OP_JUMP:
+                    pc = (uint32_t)op.b;
+                    continue;
                 case CXXDES_B200_OP_LAZY_TIMEOUT: {
                     auto t = co_await lazy_timeout((time_integral)op.imm);   // no event; t is an `instant`
                     procs[p].reg = (int64_t)t.time();

@@ -251,3 +251,27 @@ def mm1_program(lam, mu, n_packets):
     with prog.body(main) as b:
         b.all_of(prod, cons)
     return prog
+
+
+def mm1k_program(lam, mu, n_packets, k):
+    """M/M/1/K loss system: the producer drops a packet when the buffer already holds k (the textbook use of an `if`
+    between awaits: `if (q.size() < k) co_await q.put(...); else ++dropped;`).  i64[0] = served, i64[1] = dropped."""
+    prog = Program()
+    q = prog.queue()
+    main = prog.process(0, root=True)
+    prod, cons = prog.process(1), prog.process(2)
+    r_lam, r_mu = prog.rate(lam), prog.rate(mu)
+    with prog.body(prod) as b:
+        with b.loop(n_packets):
+            with b.if_("queue_size", q, "<", k):
+                b.put(q)
+            with b.else_():
+                b.count(1)
+            b.delay_exp(r_lam)
+    with prog.body(cons) as b:
+        with b.loop(1 << 30):                      # serves until the run ends
+            b.pop(q); b.delay_exp(r_mu); b.count(0); b.stat_seconds(1)
+    with prog.body(main) as b:
+        b.async_(cons)
+        b.await_(prod)
+    return prog

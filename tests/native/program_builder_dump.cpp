@@ -80,6 +80,31 @@ static program mm1_sweep(const std::vector<double> &lambdas, double mu, std::int
     return prog;
 }
 
+// M/M/1/K: if (q.size() < k) co_await q.put(..); else ++dropped;
+static program mm1k(double lam, double mu, std::int64_t n_packets, std::int64_t k) {
+    program prog;
+    queue q = prog.add_queue();
+    process co_main = prog.add_process(0), producer = prog.add_process(1), consumer = prog.add_process(2);
+    prog.bind(co_main);
+    prog.body_of(producer, [&](body &co) {
+        co.loop(n_packets, [&] {
+            co.if_then_else(q.size() < k, [&] { co.await(q.put()); }, [&] { co.count(1); });
+            co.await(env_timeout(exponential{lam}));
+        });
+    });
+    prog.body_of(consumer, [&](body &co) {
+        co.loop(1 << 30, [&] {
+            co.await(q.pop());
+            co.await(env_timeout(exponential{mu})).count(0).stat_seconds(1);
+        });
+    });
+    prog.body_of(co_main, [&](body &co) {
+        co.await(async(consumer));
+        co.await(producer);
+    });
+    return prog;
+}
+
 // tests/controlflow.test.cpp:60-72,126-137
 static program compositions() {
     program prog;
@@ -292,6 +317,7 @@ static program sequential_example() {
 int main() {
     std::printf("{\n");
     dump("mm1", mm1(5.0, 10.0, 300));
+    dump("mm1k", mm1k(8.0, 10.0, 400, 4));
     dump("mm1_sweep", mm1_sweep({1.0, 3.0, 5.0, 7.0, 9.0}, 10.0, 300));
     dump("1", compositions());
     dump("2", latencies());

@@ -70,6 +70,7 @@ def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
     assert r.returncode == 0           # also: the three misuse cases threw
     got = json.loads(r.stdout)
     assert got.pop("mm1") == _python_tables(K.mm1_program(5.0, 10.0, 300))
+    assert got.pop("mm1k") == _python_tables(K.mm1k_program(8.0, 10.0, 400, 4))
     assert got.pop("mm1_sweep") == _python_tables(K.mm1_program([1.0, 3.0, 5.0, 7.0, 9.0], 10.0, 300))
     assert sorted(got) == sorted(str(k) for k in (1, 2, 4, 5, 6, 7, 9, 10, 11, 14, 15))
     for k, tables in got.items():

@@ -107,6 +107,32 @@ def test_gpu_parameter_sweep_matches_oracle_and_theory(port):
         assert abs(latency - 1.0 / (10.0 - lam)) < 0.08 / (10.0 - lam)
 
 
+def test_if_else_between_awaits_reference_engine_equals_cpu_interpreter(port, ref):
+    """M/M/1/K: `if (q.size() < k) co_await q.put(..); else ++dropped;` -- the branch reads the real queue on the
+    reference engine (oracle/ref/program_runner.hpp) and the interpreters' own state elsewhere."""
+    prog = K.mm1k_program(8.0, 10.0, 400, 4)
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 21, 0, 40, threads=4)
+    b = ref.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 21, 0, 40, threads=4)
+    golden_util.assert_columns_equal(a, b, what="M/M/1/K")
+    assert (a.i64[1] > 0).all() and ((a.i64[0] + a.i64[1]) == 400).all()      # some dropped; served + dropped = offered
+
+
+@pytest.mark.gpu
+def test_gpu_finite_buffer_queue_matches_oracle_and_theory(port):
+    lam, mu, k, n = 8.0, 10.0, 4, 2500
+    prog = K.mm1k_program(lam, mu, n, k)
+    n_reps = 1500
+    ens = L.Ensemble(prog, n_reps, seed=21)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    got = ens.run().fetch()
+    ens.close()
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 21, 0, n_reps, threads=os.cpu_count())
+    golden_util.assert_columns_equal(got, want, what="M/M/1/K")
+    rho, cap = lam / mu, k + 1                                  # k waiting + one in service
+    p_loss = (1 - rho) * rho ** cap / (1 - rho ** (cap + 1))    # M/M/1/N blocking probability (PASTA)
+    assert abs(got.i64[1].sum() / (n_reps * n) - p_loss) < 0.004
+
+
 def test_builder_rejects_incomplete_programs():
     prog = L.Program()
     prog.process(0, root=True)

@@ -88,6 +88,21 @@ def random_program(seed):
             budget[0] -= 1
             h = helper(depth)
             (b.await_ if rng.random() < 0.6 else b.async_)(h)
+        elif k < 0.905 and depth < 2:
+            # if / else on the model's own state, with statements (awaits included) inside
+            kinds = ["counter", "now", "register"] + (["queue_size"] if queues else []) + (["sem_value"] if sems else []) + \
+                    (["mutex"] if mutexes else [])
+            src = rng.choice(kinds)
+            index = {"counter": rng.randint(0, 1), "queue_size": rng.choice(queues) if queues else 0,
+                     "sem_value": rng.choice(sems) if sems else 0, "mutex": rng.choice(mutexes) if mutexes else 0}.get(src, 0)
+            value = {"now": rng.randint(0, 4000), "register": rng.randint(0, 4000), "counter": rng.randint(0, 6),
+                     "mutex": rng.randint(0, 1)}.get(src, rng.randint(0, 3))
+            with b.if_(src, index, rng.choice(("==", "!=", "<", "<=", ">", ">=")), value):
+                for _ in range(rng.randint(1, 2)):
+                    statement(b, 2)
+            if rng.random() < 0.5:
+                with b.else_():
+                    statement(b, 2)
         elif k < 0.915:
             b.lazy_timeout(rng.randint(0, 50)); timer(b); b.await_lazy(priority=prio())
         elif k < 0.93:

@@ -405,6 +405,12 @@ public:
         return *this;
     }
 
+    // co_return in the middle of a body: `while (true) { ...; if (n == n_packets) co_return; ... }`
+    body &co_return_() {
+        prog_.emit(CXXDES_B200_OP_RETURN);
+        return *this;
+    }
+
     // the same coroutine function called again: p becomes a new, unstarted coroutine object
     body &fresh(process p) {
         prog_.emit(CXXDES_B200_OP_FRESH, (std::uint16_t)p.id);

@@ -187,6 +187,9 @@ class Body:
                     body.prog._ops[self_inner.at][2] = len(body.prog._ops)
         return _Else()
 
+    def return_(self):                           # co_return in the middle of a body (e.g. inside an if_ inside a loop)
+        self._emit(abi.OP_RETURN)
+
     def set_reg_now(self):                       # reg = now()
         self._emit(abi.OP_SET_REG_NOW)
 

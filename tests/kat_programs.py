@@ -275,3 +275,26 @@ def mm1k_program(lam, mu, n_packets, k):
         b.async_(cons)
         b.await_(prod)
     return prog
+
+
+def mm1_program_as_written(lam, mu, n_packets):
+    """examples/producer_consumer.cpp:40-58 with the consumer's control flow as the example writes it:
+    `while (true) { x = co_await q.pop(); ++n; if (n == n_packets) co_return; co_await env.timeout(mu()); total += .. }`
+    -- same trace as mm1_program(), whose consumer loop is unrolled instead."""
+    prog = Program()
+    q = prog.queue()
+    main = prog.process(0, root=True)
+    prod, cons = prog.process(1), prog.process(2)
+    r_lam, r_mu = prog.rate(lam), prog.rate(mu)
+    with prog.body(prod) as b:
+        with b.loop(n_packets):
+            b.put(q); b.delay_exp(r_lam)
+    with prog.body(cons) as b:
+        with b.loop(1 << 30):                               # while (true)
+            b.pop(q); b.count(0)
+            with b.if_("counter", 0, "==", n_packets):
+                b.return_()
+            b.delay_exp(r_mu); b.stat_seconds(1)
+    with prog.body(main) as b:
+        b.all_of(prod, cons)
+    return prog

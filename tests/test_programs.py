@@ -133,6 +133,29 @@ def test_gpu_finite_buffer_queue_matches_oracle_and_theory(port):
     assert abs(got.i64[1].sum() / (n_reps * n) - p_loss) < 0.004
 
 
+def test_consumer_loop_as_the_example_writes_it(port, ref):
+    """`while (true) { ...; if (n == n_packets) co_return; ... }` (producer_consumer.cpp:42-53): same event trace as
+    the hand-lowered M/M/1 model, on the CPU interpreter and on the reference engine."""
+    prog = K.mm1_program_as_written(5.0, 10.0, 250)
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 0x5EED, 0, 24, threads=4)
+    b = port.run(abi.MODEL_MM1, abi.MM1Params(5.0, 10.0, 250), oracles.MM1_CLOCK, 0x5EED, 0, 24, threads=4)
+    c = ref.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 0x5EED, 0, 24, threads=4)
+    for other in (b, c):
+        assert np.array_equal(a.trace_hash, other.trace_hash) and np.array_equal(a.end_time, other.end_time)
+        assert np.array_equal(a.n_events, other.n_events) and np.array_equal(a.i64[0], other.i64[0])
+        assert np.array_equal(a.f64[1].view(np.uint64), other.f64[1].view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_gpu_consumer_loop_as_the_example_writes_it(port):
+    prog = K.mm1_program_as_written(5.0, 10.0, 600)
+    got = _run_gpu(prog, 512, clock=((1, L.SECONDS), (1, L.MILLISECONDS)), seed=0x5EED)
+    want = port.run(abi.MODEL_MM1, abi.MM1Params(5.0, 10.0, 600), oracles.MM1_CLOCK, 0x5EED, 0, 512, threads=os.cpu_count())
+    assert not got.status.any()
+    assert np.array_equal(got.trace_hash, want.trace_hash) and np.array_equal(got.end_time, want.end_time)
+    assert np.array_equal(got.f64[1].view(np.uint64), want.f64[1].view(np.uint64))
+
+
 def test_builder_rejects_incomplete_programs():
     prog = L.Program()
     prog.process(0, root=True)

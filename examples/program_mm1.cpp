@@ -26,12 +26,13 @@ static program producer_consumer_example(double lambda, double mu, std::int64_t 
         });
     });
     prog.body_of(consumer, [&](body &co) {                   // coroutine<> consumer() {
-        co.loop(n_packets - 1, [&] {                         //   while (true) {
+        co.loop(1 << 30, [&] {                               //   while (true) {
             co.await(q.pop()).count(0);                      //     auto x = co_await q.pop(); ++n;
-            co.await(env_timeout(exponential{mu}));          //     if (n == n_packets) break; co_await env.timeout(mu());
+            co.if_then(counter(0) == n_packets,              //     if (n == n_packets) {
+                       [&] { co.co_return_(); });            //       avg_latency = total_latency / n; co_return; }
+            co.await(env_timeout(exponential{mu}));          //     co_await env.timeout(mu());
             co.stat_seconds(1);                              //     total_latency += now_seconds() - x; }
         });
-        co.await(q.pop()).count(0);
     });
     prog.body_of(co_main, [&](body &co) {                    // coroutine<> co_main() {
         co.await(producer && consumer);                      //   co_await (producer() && consumer()); }

@@ -48,6 +48,10 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
     auto set_pc = [&](int q, int which, uint32_t v) { pcs[q] = (pcs[q] & ~(0xFu << (4 * which))) | (v << (4 * which)); };
     enum { PC_REQ = 0, PC_LOAD2 = 1, PC_WITH2 = 2, PC_LOAD1 = 3, PC_WITH1 = 4 };
 
+    // One requester and a positive mem2 latency: every load starts later than the one before, so last_access
+    // stamps are unique and the "lowest position on ties" rule of the eviction never applies.
+    const bool unique_stamps = K == 1 && prm.l2_latency > 0;
+
     uint64_t rep;
     while (steal(sh, rep)) {
         const uint64_t grep = sh.first_replication + rep;
@@ -62,6 +66,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
         wait1.init(w1who, w1lat, K);
         bool owned2 = false, owned1 = false;
         int n_blocks = 0;
+        int held_slot = -1;   // block found by the look-up of the load that holds mem2's mutex (-1: a miss)
         uint32_t main_pc = 0;
         any_all all;
         double total_latency = 0.0;
@@ -137,22 +142,30 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                                 bool miss = false;
                                 if (lvl == 2) {
                                     const uint32_t a = cur_addr[q];
-                                    bool found = false;
-                                    for (int b = 0; b < n_blocks; ++b) found |= blk_addr[b] == a;
-                                    miss = !found;
+                                    int at = -1;
+                                    for (int b = 0; b < n_blocks; ++b) at = blk_addr[b] == a ? b : at;
+                                    miss = at < 0;
+                                    held_slot = at;   // this requester holds mem2's mutex until it stamps the block
                                     if (miss) {
                                         ++misses;
                                         if (n_blocks == CAP) {
-                                            // evict: least last_access, lowest position on ties; erase keeps order
+                                            // evict: least last_access, lowest position on ties
                                             int victim = 0;
                                             int64_t best = blk_last[0];
                                             for (int b = 1; b < n_blocks; ++b) {
                                                 int64_t v = blk_last[b];
                                                 if (v < best) { best = v; victim = b; }
                                             }
-                                            for (int b = victim; b + 1 < n_blocks; ++b) {
-                                                blk_addr[b] = blk_addr[b + 1];
-                                                blk_last[b] = blk_last[b + 1];
+                                            if (unique_stamps) {
+                                                // stamps never tie, so positions never decide: the last block moves
+                                                // into the hole instead of every later block moving down one
+                                                blk_addr[victim] = blk_addr[n_blocks - 1];
+                                                blk_last[victim] = blk_last[n_blocks - 1];
+                                            } else {
+                                                for (int b = victim; b + 1 < n_blocks; ++b) {   // erase keeps order
+                                                    blk_addr[b] = blk_addr[b + 1];
+                                                    blk_last[b] = blk_last[b + 1];
+                                                }
                                             }
                                             --n_blocks;
                                         }
@@ -175,13 +188,12 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                         } else {
                             if (lvl == 2) {
                                 // blocks_[addr].last_access = timestamp
-                                const uint32_t a = cur_addr[q];
+                                // (nobody else touched mem2's blocks since the look-up: the mutex was held)
                                 const int64_t ts = stamp2[q];
-                                bool found = false;
-                                for (int b = 0; b < n_blocks; ++b)
-                                    if (!found && blk_addr[b] == a) { blk_last[b] = ts; found = true; }
-                                if (!found) {
-                                    blk_addr[n_blocks] = a;
+                                if (held_slot >= 0) {
+                                    blk_last[held_slot] = ts;
+                                } else {
+                                    blk_addr[n_blocks] = cur_addr[q];
                                     blk_last[n_blocks] = ts;
                                     ++n_blocks;
                                 }

@@ -80,6 +80,17 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
 
         while (env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until)) {
             token t = env.step_pop();
+            // An event pushes at most one token of its own (co_main's start and the mutex wake-ups aside).  The
+            // branches only note it; the push -- range checks and the sift -- runs once after them for all lanes.
+            // Order is kept: wherever an event also wakes waiters, the wake-ups come first (mutex.hpp:70-79).
+            int64_t p_time = 0;
+            uint32_t p_tag = 0;
+            bool has_push = false;
+            auto note = [&](int64_t time, uint32_t tag) {
+                p_time = time;
+                p_tag = tag;
+                has_push = true;
+            };
             const uint32_t target = tag_target(t.tag);
             if (tag_handler_plus1(t.tag)) {
                 all.invoke(env, t);
@@ -90,7 +101,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                     all.arm(true, (uint32_t)K, (uint32_t)K);
                     main_pc = 1;
                 } else {
-                    env.schedule(env.now, 0, make_tag(TAG_NO_TARGET));
+                    note(env.now, make_tag(TAG_NO_TARGET));
                 }
             } else if (target != TAG_NO_TARGET) {
                 if (target < 0x100) {
@@ -106,10 +117,10 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                         cur_addr[q] = (uint32_t)(stream_draw_bits(addr, j) % prm.addr_space);
                         t1[q] = env.now;
                         set_pc(q, PC_LOAD2, 0);
-                        env.schedule(env.now, 0, make_tag(0x100 + q));  // start(mem2.load); completion targets the requester
+                        note(env.now, make_tag(0x100 + q));  // start(mem2.load); completion targets the requester
                         set_pc(q, PC_REQ, 1);
                     } else {
-                        env.schedule(env.now, 0, make_tag(0, 1));  // co_return -> completion with the all_of handler
+                        note(env.now, make_tag(0, 1));  // co_return -> completion with the all_of handler
                     }
                 } else {
                     const int q = (int)(target & 0xFF);
@@ -121,11 +132,11 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                         if (get_pc(q, which) == 0) {
                             if (lvl == 2) stamp2[q] = env.now;  // timestamp = env.now()
                             set_pc(q, lvl == 2 ? PC_WITH2 : PC_WITH1, 0);
-                            env.schedule(env.now, 0, make_tag(target | 0x8000u));  // start(_Co_with coroutine)
+                            note(env.now, make_tag(target | 0x8000u));  // start(_Co_with coroutine)
                             set_pc(q, which, 1);
                         } else {
                             // load returns: completion resumes the awaiter (requester, or mem2's _Co_with)
-                            env.schedule(env.now, 0, make_tag(lvl == 2 ? 1 + q : 0x8100 + q));
+                            note(env.now, make_tag(lvl == 2 ? 1 + q : 0x8100 + q));
                         }
                     } else {
                         // ---- operator+(mutex&, body): acquire; body(); release  (co_with.ipp:27-33) ----
@@ -175,15 +186,15 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                                 }
                                 if (miss) {
                                     set_pc(q, PC_LOAD1, 0);
-                                    env.schedule(env.now, 0, make_tag(0x200 + q));  // co_await next_->load(addr)
+                                    note(env.now, make_tag(0x200 + q));  // co_await next_->load(addr)
                                     set_pc(q, which, 1);
                                 } else {
-                                    env.schedule(env.now + latency, 0, make_tag(target));  // co_await timeout(latency_)
+                                    note(env.now + latency, make_tag(target));  // co_await timeout(latency_)
                                     set_pc(q, which, 2);
                                 }
                             }
                         } else if (pc == 1) {
-                            env.schedule(env.now + latency, 0, make_tag(target));
+                            note(env.now + latency, make_tag(target));
                             set_pc(q, which, 2);
                         } else {
                             if (lvl == 2) {
@@ -200,11 +211,12 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
                             }
                             owned = false;      // handle.release(): owned_ = false; wake (mutex.hpp:70-79)
                             waiters.wake(env);
-                            env.schedule(env.now, 0, make_tag(target & 0x7FFFu));  // _Co_with returns -> resumes load
+                            note(env.now, make_tag(target & 0x7FFFu));  // _Co_with returns -> resumes load
                         }
                     }
                 }
             }
+            if (has_push) env.schedule(p_time, 0, p_tag);
             if (env.status) break;
         }
         if (sh.run_until >= 0) {

@@ -21,24 +21,44 @@ constexpr int ARCH_THREADS = 128;
 constexpr int ARCH_MAX_REQ = 16;
 constexpr int ARCH_MAX_CAP = 64;
 
+// Per-requester state: one entry per requester in shared memory -- or, in the instantiation for the shipped
+// sequential driver (one requester), a register.
+template <typename T, bool SINGLE>
+struct per_requester {
+    lane_array<T> many;
+    T one;
+    __device__ __forceinline__ T &operator[](int q) {
+        if constexpr (SINGLE) return one;
+        else return many[q];
+    }
+};
+
 }  // namespace
 
+// SINGLE: exactly one requester (examples/basic_arch_sim.cpp as shipped, BASELINE config 5).
+template <bool SINGLE>
 __global__ void __launch_bounds__(ARCH_THREADS)
 archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char *cursor = smem;
-    const int K = (int)prm.n_requesters;
+    const int K = SINGLE ? 1 : (int)prm.n_requesters;
     const int CAP = (int)prm.l2_capacity;
     const int heap_cap = K + 3;
     lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
     lane_array<int64_t> blk_last = carve<int64_t>(cursor, CAP);
-    lane_array<int64_t> t1 = carve<int64_t>(cursor, K);
-    lane_array<int64_t> stamp2 = carve<int64_t>(cursor, K);
+    per_requester<int64_t, SINGLE> t1, stamp2;
+    per_requester<uint32_t, SINGLE> loop_j, cur_addr, pcs;  // pcs: nibble 0 requester, 1 load2, 2 with2, 3 load1, 4 with1
+    if (!SINGLE) {
+        t1.many = carve<int64_t>(cursor, K);
+        stamp2.many = carve<int64_t>(cursor, K);
+    }
     lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
     lane_array<uint32_t> blk_addr = carve<uint32_t>(cursor, CAP);
-    lane_array<uint32_t> loop_j = carve<uint32_t>(cursor, K);
-    lane_array<uint32_t> cur_addr = carve<uint32_t>(cursor, K);
-    lane_array<uint32_t> pcs = carve<uint32_t>(cursor, K);  // byte 0 requester, 1 load2, 2 with2, 3: with1 (low nibble) | load1 (high nibble)
+    if (!SINGLE) {
+        loop_j.many = carve<uint32_t>(cursor, K);
+        cur_addr.many = carve<uint32_t>(cursor, K);
+        pcs.many = carve<uint32_t>(cursor, K);
+    }
     lane_array<uint32_t> w2who = carve<uint32_t>(cursor, K);
     lane_array<int32_t> w2lat = carve<int32_t>(cursor, K);
     lane_array<uint32_t> w1who = carve<uint32_t>(cursor, K);
@@ -250,12 +270,14 @@ size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p) {
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
                            int sm_count, cudaStream_t stream) {
     const size_t smem = archsim_smem_bytes(prm);
-    cudaError_t e = cudaFuncSetAttribute(archsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(archsim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(archsim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    archsim_kernel<<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
+    if (prm.n_requesters == 1) archsim_kernel<true><<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
+    else archsim_kernel<false><<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
     return cudaGetLastError();
 }
 

@@ -132,18 +132,17 @@ inline composition any_of_range(const std::vector<process> &ps) {
     for (process p : ps) c.children.emplace_back(p);
     return c;
 }
-// a && b, a || b: flat n-ary like the reference's operator overloads
+// a && b, a || b (compositions.ipp): two operands.  A chain `a && b && c` is all_of(all_of(a, b), c) in the
+// reference -- a nested composition whose inner handler adds an event of its own -- and is NOT the same trace as
+// the flat all_of(a, b, c).  Nested compositions are not supported by the interpreters, so a chain is rejected
+// here rather than silently flattened: write all_of(a, b, c) for the flat form.
 inline composition operator&&(child a, child b) { return composition{true, {a, b}}; }
 inline composition operator||(child a, child b) { return composition{false, {a, b}}; }
-inline composition operator&&(composition a, child b) {
-    if (!a.all) throw std::invalid_argument("cxxdes_b200: nested compositions are not supported; use a helper process");
-    a.children.push_back(b);
-    return a;
+inline composition operator&&(const composition &, child) {
+    throw std::invalid_argument("cxxdes_b200: a && b && c nests compositions in the reference; use all_of(a, b, c) for the flat form");
 }
-inline composition operator||(composition a, child b) {
-    if (a.all) throw std::invalid_argument("cxxdes_b200: nested compositions are not supported; use a helper process");
-    a.children.push_back(b);
-    return a;
+inline composition operator||(const composition &, child) {
+    throw std::invalid_argument("cxxdes_b200: a || b || c nests compositions in the reference; use any_of(a, b, c) for the flat form");
 }
 
 // ---- conditions of if_then / if_then_else: plain reads of the model's own state (no events) --------------

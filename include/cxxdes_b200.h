@@ -154,7 +154,12 @@ enum {
     CXXDES_B200_OP_IF = 30,         /* if (!(value cmp imm)) goto b: structured if / else on the model's own state.
                                        a = index | source << 8 | comparison << 12 (CXXDES_B200_SRC_*, _CMP_*);
                                        b = first op after the then-block (forward)                               */
-    CXXDES_B200_OP_JUMP = 31        /* goto b (forward): the end of a then-block jumps over the else-block       */
+    CXXDES_B200_OP_JUMP = 31,       /* goto b (forward): the end of a then-block jumps over the else-block       */
+    CXXDES_B200_OP_CHILD_ALL_OF = 32,/*   child: a nested all_of -- `(a && b) || c`, `a && b && c` = all_of(all_of(a, b), c)
+                                       in the reference (compositions.ipp); a = its own child count, its children
+                                       follow in place (pre-order), b / imm as for ALL_OF.  When the inner condition
+                                       holds, its output token goes to the OUTER handler (any_of.ipp:66-84)        */
+    CXXDES_B200_OP_CHILD_ANY_OF = 33 /*   child: a nested any_of                                                   */
 };
 enum {  /* what an IF looks at: plain reads of public state, no events */
     CXXDES_B200_SRC_COUNTER = 0,    /* i64[index]                                        */

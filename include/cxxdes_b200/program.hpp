@@ -21,6 +21,7 @@
 #pragma once
 #include <cstring>
 #include <initializer_list>
+#include <memory>
 #include <limits>
 #include <utility>
 
@@ -93,14 +94,17 @@ struct async_t {  // async(p): async.ipp:9-49
 };
 inline async_t async(process p) { return {p}; }
 
-struct child {  // an operand of all_of / any_of / && / ||
-    enum kind_t { PROC, DELAY, UNTIL } kind;
+struct composition;
+struct child {  // an operand of all_of / any_of / && / ||: a process, a timer, or another composition
+    enum kind_t { PROC, DELAY, UNTIL, NESTED } kind;
     std::uint32_t proc;
     time_integral ticks;
     priority_type prio;
+    std::shared_ptr<const composition> nested;
     child(process p) : kind(PROC), proc(p.id), ticks(0), prio(inherit) {}
     child(delay_t d) : kind(DELAY), proc(0), ticks(d.ticks), prio(d.prio) {}
     child(until_t u) : kind(UNTIL), proc(0), ticks(u.ticks), prio(u.prio) {}
+    child(const composition &c);
 };
 struct composition {  // any_of.ipp:233-247; compositions.ipp (operator&&, operator||)
     bool all;
@@ -132,18 +136,18 @@ inline composition any_of_range(const std::vector<process> &ps) {
     for (process p : ps) c.children.emplace_back(p);
     return c;
 }
-// a && b, a || b (compositions.ipp): two operands.  A chain `a && b && c` is all_of(all_of(a, b), c) in the
-// reference -- a nested composition whose inner handler adds an event of its own -- and is NOT the same trace as
-// the flat all_of(a, b, c).  Nested compositions are not supported by the interpreters, so a chain is rejected
-// here rather than silently flattened: write all_of(a, b, c) for the flat form.
+inline child::child(const composition &c) : kind(NESTED), proc(0), ticks(0), prio(inherit), nested(std::make_shared<composition>(c)) {}
+// a && b, a || b (compositions.ipp).  A chain nests exactly as in the reference: `a && b && c` is
+// all_of(all_of(a, b), c) -- the inner composition has a handler of its own, which is an event more than the flat
+// all_of(a, b, c).  Write all_of(a, b, c) when the flat form is meant.
 inline composition operator&&(child a, child b) { return composition{true, {a, b}}; }
 inline composition operator||(child a, child b) { return composition{false, {a, b}}; }
-inline composition operator&&(const composition &, child) {
-    throw std::invalid_argument("cxxdes_b200: a && b && c nests compositions in the reference; use all_of(a, b, c) for the flat form");
-}
-inline composition operator||(const composition &, child) {
-    throw std::invalid_argument("cxxdes_b200: a || b || c nests compositions in the reference; use any_of(a, b, c) for the flat form");
-}
+inline composition operator&&(const composition &a, child b) { return composition{true, {child(a), b}}; }
+inline composition operator||(const composition &a, child b) { return composition{false, {child(a), b}}; }
+inline composition operator&&(const composition &a, const composition &b) { return composition{true, {child(a), child(b)}}; }
+inline composition operator||(const composition &a, const composition &b) { return composition{false, {child(a), child(b)}}; }
+inline composition operator&&(child a, const composition &b) { return composition{true, {a, child(b)}}; }
+inline composition operator||(child a, const composition &b) { return composition{false, {a, child(b)}}; }
 
 // ---- conditions of if_then / if_then_else: plain reads of the model's own state (no events) --------------
 struct condition {
@@ -356,17 +360,8 @@ public:
         prog_.emit(CXXDES_B200_OP_ASYNC, (std::uint16_t)a.p.id);
         return *this;
     }
-    body &await(const composition &c) {  // co_await all_of(...) / any_of(...) / (a && b) / (a || b)
-        if (c.children.empty() || c.children.size() > 32)
-            throw std::invalid_argument("cxxdes_b200: a composition takes 1..32 children");
-        prog_.emit(c.all ? CXXDES_B200_OP_ALL_OF : CXXDES_B200_OP_ANY_OF, (std::uint16_t)c.children.size(),
-                   detail::prio32(c.prio), c.latency);
-        for (const child &ch : c.children) {
-            if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);
-            else
-                prog_.emit(ch.kind == child::DELAY ? CXXDES_B200_OP_CHILD_DELAY : CXXDES_B200_OP_CHILD_UNTIL, 0,
-                           detail::prio32(ch.prio), ch.ticks);
-        }
+    body &await(const composition &c) {  // co_await all_of(...) / any_of(...) / (a && b) / (a || b), nested or not
+        emit_composition(c, c.all ? CXXDES_B200_OP_ALL_OF : CXXDES_B200_OP_ANY_OF);
         return *this;
     }
     body &await(simple_op op) {  // co_await q.put(..) / q.pop() / sem.up() / mtx.acquire() / evt.wait() ...
@@ -440,6 +435,19 @@ public:
 private:
     friend class program;
     explicit body(program &p) : prog_(p) {}
+    void emit_composition(const composition &c, std::uint16_t code) {   // children follow in place, pre-order
+        if (c.children.empty() || c.children.size() > 32)
+            throw std::invalid_argument("cxxdes_b200: a composition takes 1..32 children");
+        prog_.emit(code, (std::uint16_t)c.children.size(), detail::prio32(c.prio), c.latency);
+        for (const child &ch : c.children) {
+            if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);
+            else if (ch.kind == child::NESTED)
+                emit_composition(*ch.nested, ch.nested->all ? CXXDES_B200_OP_CHILD_ALL_OF : CXXDES_B200_OP_CHILD_ANY_OF);
+            else
+                prog_.emit(ch.kind == child::DELAY ? CXXDES_B200_OP_CHILD_DELAY : CXXDES_B200_OP_CHILD_UNTIL, 0,
+                           detail::prio32(ch.prio), ch.ticks);
+        }
+    }
     program &prog_;
 };
 

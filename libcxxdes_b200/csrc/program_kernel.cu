@@ -19,6 +19,7 @@ namespace {
 constexpr int PRG_THREADS = 128;
 constexpr int PRG_HEAP = 64;
 constexpr int PRG_MAX_PROCS = 24;
+constexpr int PRG_MAX_NODES = 8;  // compositions in one co_await (the outer one and those nested in it)
 constexpr int PRG_HANDLERS = 8;   // live any_of/all_of handlers per replication (pool, by serial)
 constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind
 constexpr int PRG_WAITERS = 16;
@@ -49,6 +50,7 @@ struct waiters_rt {  // sync::event: FIFO of {latency, priority, process}  (even
 
 struct handler_rt {  // any_all_helper::custom_handler (any_of.ipp:3-27)
     int64_t out_latency;     // .return_latency(): added to the satisfying child token's time
+    uint32_t out_serial_plus1;   // a nested composition: its output token goes to the parent's handler (0: resumes the process)
     uint32_t serial_plus1;
     uint32_t total, remaining;
     bool is_all, armed;
@@ -145,69 +147,123 @@ struct interp {
         return op.b == CXXDES_B200_INHERIT ? self.prio : (int64_t)op.b;
     }
 
-    // any_of / all_of: any_of.ipp:41-92.  Returns true when the awaiting process suspends.
-    __device__ bool composition(uint32_t self_id, const cxxdes_b200_op &head, uint32_t first_child) {
+    // any_of / all_of, possibly nested: any_of.ipp:41-92.  The children of the composition at `head` follow it in
+    // pre-order; a nested composition is a child that has children of its own.  Returns true when the awaiting
+    // process suspends; `span` = number of child operations (so the caller can step over them).
+    __device__ bool composition(uint32_t self_id, const cxxdes_b200_op &head, uint32_t first_child, uint32_t &span) {
         proc_rt &self = procs[self_id];
-        const bool is_all = head.code == CXXDES_B200_OP_ALL_OF;
-        const uint32_t total = head.a;
-        if (total > 32) {
-            env.status |= CXXDES_B200_REP_BAD_PROGRAM;
-            return true;
-        }
-        // await_bind: every child in argument order (coroutine children get their start token here); what they
-        // inherit is the composition's priority: .priority(p), else the awaiting process's (any_of.ipp:41-48)
-        const int64_t comp_prio = head.b == CXXDES_B200_INHERIT ? self.prio : (int64_t)head.b;
-        for (uint32_t c = 0; c < total; ++c) {
-            const cxxdes_b200_op &ch = prg.ops[first_child + c];
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) bind(ch.a, comp_prio);
-        }
-        // await_ready: collect ready flags
-        uint32_t ready_mask = 0, remaining = total;
-        for (uint32_t c = 0; c < total; ++c) {
-            const cxxdes_b200_op &ch = prg.ops[first_child + c];
-            bool ready = false;
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) ready = procs[ch.a].complete;
-            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) ready = env.now >= ch.imm;
-            if (ready) {
-                ready_mask |= 1u << c;
-                --remaining;
+        struct node_rt {
+            int64_t prio;            // what the node's children inherit
+            uint32_t serial_plus1;   // its handler, once suspended
+            int16_t parent;
+            uint8_t total, n_ready, left;
+            bool is_all, ready, suspended;
+        } nodes[PRG_MAX_NODES];
+        int n_nodes = 1;
+        nodes[0].prio = head.b == CXXDES_B200_INHERIT ? self.prio : (int64_t)head.b;
+        nodes[0].parent = -1;
+        nodes[0].total = nodes[0].left = (uint8_t)head.a;
+        nodes[0].n_ready = 0;
+        nodes[0].is_all = head.code == CXXDES_B200_OP_ALL_OF;
+        // 1. await_bind + the ready flags of the leaves, children in argument order (pre-order walk)
+        uint64_t leaf_ready = 0;
+        uint32_t pos = first_child;
+        for (int cur = 0;;) {
+            while (cur >= 0 && nodes[cur].left == 0) cur = nodes[cur].parent;
+            if (cur < 0) break;
+            --nodes[cur].left;
+            const cxxdes_b200_op &ch = prg.ops[pos];
+            if (ch.code == CXXDES_B200_OP_CHILD_ALL_OF || ch.code == CXXDES_B200_OP_CHILD_ANY_OF) {
+                if (n_nodes >= PRG_MAX_NODES) {
+                    env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                    span = 0;
+                    return true;
+                }
+                node_rt &nd = nodes[n_nodes];
+                nd.prio = ch.b == CXXDES_B200_INHERIT ? nodes[cur].prio : (int64_t)ch.b;   // priority_ = inherited
+                nd.parent = (int16_t)cur;
+                nd.total = nd.left = (uint8_t)ch.a;
+                nd.n_ready = 0;
+                nd.is_all = ch.code == CXXDES_B200_OP_CHILD_ALL_OF;
+                cur = n_nodes++;
+            } else {
+                bool ready = false;
+                if (ch.code == CXXDES_B200_OP_CHILD_PROC) {
+                    bind(ch.a, nodes[cur].prio);
+                    ready = procs[ch.a].complete;
+                } else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) {
+                    ready = env.now >= ch.imm;
+                }
+                if (ready) {
+                    leaf_ready |= 1ULL << ((pos - first_child) & 63u);
+                    ++nodes[cur].n_ready;
+                }
             }
+            ++pos;
         }
-        if (is_all ? remaining == 0 : remaining < total) return false;
-        // await_suspend: output token {0, priority, self} held by a new handler; non-ready children in order
-        const uint32_t serial = next_serial++;
-        if (serial + 1 > PTAG_MAX_SERIAL) {
-            env.status |= CXXDES_B200_REP_BAD_PROGRAM;
-            return true;
+        span = pos - first_child;
+        // 2. await_ready of every composition, innermost first (children have larger numbers than their parent)
+        for (int i = n_nodes - 1; i >= 0; --i) {
+            const uint32_t remaining = (uint32_t)nodes[i].total - nodes[i].n_ready;
+            nodes[i].ready = nodes[i].is_all ? remaining == 0 : remaining < nodes[i].total;
+            if (nodes[i].ready && nodes[i].parent >= 0) ++nodes[nodes[i].parent].n_ready;
         }
-        // storage: any handler that has fired (its late tokens are recognised by serial, device/program_tags.cuh)
-        int slot = -1;
-        for (int k = 0; k < PRG_HANDLERS; ++k)
-            if (!handlers[k].armed) {
-                slot = k;
-                break;
+        if (nodes[0].ready) return false;
+        // 3. await_suspend, outermost first: a handler per non-ready composition (its output token goes to the
+        //    parent's handler, or resumes the process), then its non-ready children in order
+        auto make_handler = [&](int i, const cxxdes_b200_op &op) -> bool {
+            const uint32_t serial = next_serial++;
+            if (serial + 1 > PTAG_MAX_SERIAL) {
+                env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                return false;
             }
-        if (slot < 0) {   // more live compositions than the pool holds
-            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            // storage: any handler that has fired (its late tokens are recognised by serial, device/program_tags.cuh)
+            int slot = -1;
+            for (int k = 0; k < PRG_HANDLERS; ++k)
+                if (!handlers[k].armed) {
+                    slot = k;
+                    break;
+                }
+            if (slot < 0) {   // more live compositions than the pool holds
+                env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+                return false;
+            }
+            handler_rt &h = handlers[slot];
+            h.serial_plus1 = serial + 1;
+            h.total = nodes[i].total;
+            h.remaining = (uint32_t)nodes[i].total - nodes[i].n_ready;
+            h.is_all = nodes[i].is_all;
+            h.armed = true;
+            h.out_latency = op.imm;
+            h.out_serial_plus1 = nodes[i].parent >= 0 ? nodes[nodes[i].parent].serial_plus1 : 0u;
+            nodes[i].serial_plus1 = serial + 1;
+            nodes[i].suspended = true;
             return true;
-        }
-        handler_rt &h = handlers[slot];
-        h.serial_plus1 = serial + 1;
-        h.total = total;
-        h.remaining = remaining;
-        h.is_all = is_all;
-        h.armed = true;
-        h.out_latency = head.imm;
-        for (uint32_t c = 0; c < total; ++c) {
-            if (ready_mask & (1u << c)) continue;
-            const cxxdes_b200_op &ch = prg.ops[first_child + c];
-            const uint32_t tag = ptag(self_id, serial + 1);
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
-            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY)
-                env.schedule(env.now + ch.imm, ch.b == CXXDES_B200_INHERIT ? comp_prio : (int64_t)ch.b, tag);
-            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL)
-                env.schedule(ch.imm, ch.b == CXXDES_B200_INHERIT ? comp_prio : (int64_t)ch.b, tag);
-            else env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+        };
+        if (!make_handler(0, head)) return true;
+        nodes[0].left = nodes[0].total;
+        pos = first_child;
+        int next_node = 1;
+        for (int cur = 0;;) {
+            while (cur >= 0 && nodes[cur].left == 0) cur = nodes[cur].parent;
+            if (cur < 0) break;
+            --nodes[cur].left;
+            const cxxdes_b200_op &ch = prg.ops[pos];
+            if (ch.code == CXXDES_B200_OP_CHILD_ALL_OF || ch.code == CXXDES_B200_OP_CHILD_ANY_OF) {
+                const int id = next_node++;
+                nodes[id].left = nodes[id].total;
+                nodes[id].suspended = false;
+                if (nodes[cur].suspended && !nodes[id].ready && !make_handler(id, ch)) return true;
+                cur = id;
+            } else if (nodes[cur].suspended && !(leaf_ready & (1ULL << ((pos - first_child) & 63u)))) {
+                const uint32_t tag = ptag(self_id, nodes[cur].serial_plus1);
+                const int64_t pr = ch.b == CXXDES_B200_INHERIT ? nodes[cur].prio : (int64_t)ch.b;
+                if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
+                else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) env.schedule(env.now + ch.imm, pr, tag);
+                else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) env.schedule(ch.imm, pr, tag);
+                else env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+            }
+            ++pos;
         }
         return true;
     }
@@ -223,7 +279,7 @@ struct interp {
         --h.remaining;
         const bool cond = h.is_all ? h.remaining == 0 : h.remaining < h.total;
         if (h.armed && cond) {
-            env.schedule(h.out_latency + key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag)));
+            env.schedule(h.out_latency + key_time(t.key), key_prio(t.key), ptag(ptag_target(t.tag), h.out_serial_plus1));
             h.armed = false;
         }
     }
@@ -280,8 +336,10 @@ struct interp {
                 case CXXDES_B200_OP_ALL_OF:
                 case CXXDES_B200_OP_ANY_OF: {
                     const uint32_t first_child = self.pc + 1;
-                    self.pc += 1 + op.a;
-                    if (composition(p, op, first_child)) return;
+                    uint32_t span = 0;
+                    const bool suspended = composition(p, op, first_child, span);
+                    self.pc = first_child + span;
+                    if (suspended) return;
                     break;
                 }
                 case CXXDES_B200_OP_Q_PUT: {
@@ -561,15 +619,29 @@ const char *program_check(const cxxdes_b200_program &p) {
             case CXXDES_B200_OP_CHILD_PROC:
                 if (op.a >= p.n_procs) return "program: process operand out of range";
                 break;
-            case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF:
-                if (op.a < 1 || op.a > 32 || i + op.a + 1 >= p.n_ops) return "program: bad composition";
-                for (uint32_t c = 1; c <= op.a; ++c) {
-                    uint16_t cc = p.ops[i + c].code;
-                    if (cc != CXXDES_B200_OP_CHILD_PROC && cc != CXXDES_B200_OP_CHILD_DELAY &&
-                        cc != CXXDES_B200_OP_CHILD_UNTIL)
+            case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF: {
+                // the children follow in pre-order; a nested composition has children of its own
+                uint32_t pending = op.a, pos = i + 1, nodes = 1, leaves = 0;
+                if (op.a < 1 || op.a > 32) return "program: bad composition";
+                while (pending > 0) {
+                    if (pos >= p.n_ops) return "program: bad composition";
+                    const cxxdes_b200_op &ch = p.ops[pos];
+                    --pending;
+                    if (ch.code == CXXDES_B200_OP_CHILD_ALL_OF || ch.code == CXXDES_B200_OP_CHILD_ANY_OF) {
+                        if (ch.a < 1 || ch.a > 32 || ++nodes > 8) return "program: bad nested composition (at most 8 compositions in one co_await)";
+                        pending += ch.a;
+                    } else if (ch.code == CXXDES_B200_OP_CHILD_PROC || ch.code == CXXDES_B200_OP_CHILD_DELAY ||
+                               ch.code == CXXDES_B200_OP_CHILD_UNTIL) {
+                        if (++leaves > 64) return "program: at most 64 awaitables in one co_await";
+                        if (ch.code == CXXDES_B200_OP_CHILD_PROC && ch.a >= p.n_procs) return "program: process operand out of range";
+                    } else {
                         return "program: composition children must be CHILD_* ops";
+                    }
+                    ++pos;
                 }
+                if (pos >= p.n_ops) return "program: bad composition";
                 break;
+            }
             case CXXDES_B200_OP_Q_PUT: case CXXDES_B200_OP_Q_POP:
                 if (op.a >= p.n_queues) return "program: queue operand out of range";
                 break;
@@ -606,7 +678,7 @@ const char *program_check(const cxxdes_b200_program &p) {
                 if (op.b <= (int64_t)i || (uint32_t)op.b >= p.n_ops) return "program: IF / JUMP target must lie ahead, inside the program";
                 break;
             default:
-                if (op.code > CXXDES_B200_OP_JUMP) return "program: unknown op code";
+                if (op.code > CXXDES_B200_OP_CHILD_ANY_OF) return "program: unknown op code";
         }
     }
     return nullptr;

@@ -38,6 +38,20 @@ class Until:
         self.ticks, self.priority = int(ticks), priority
 
 
+class AllOf:
+    """all_of(...) used as a CHILD of another composition -- `(a && b) || c`, and what the reference makes of a chain
+    `a && b && c` = all_of(all_of(a, b), c) (compositions.ipp).  Children: Delay / Until / process ids / AllOf / AnyOf."""
+    code = abi.OP_CHILD_ALL_OF
+
+    def __init__(self, *children, priority=None, return_latency=0):
+        self.children, self.priority, self.return_latency = children, priority, int(return_latency)
+
+
+class AnyOf(AllOf):
+    """any_of(...) used as a child of another composition."""
+    code = abi.OP_CHILD_ANY_OF
+
+
 def _prio32(priority):
     return abi.INHERIT32 if priority is None else int(priority)
 
@@ -95,7 +109,9 @@ class Body:
     def _composition(self, code, children, priority=None, return_latency=0):
         self._emit(code, len(children), _prio32(priority), int(return_latency))
         for c in children:
-            if isinstance(c, Delay):
+            if isinstance(c, AllOf):                 # nested: its children follow in place (pre-order)
+                self._composition(c.code, c.children, c.priority, c.return_latency)
+            elif isinstance(c, Delay):
                 self._emit(abi.OP_CHILD_DELAY, 0, _prio32(c.priority), c.ticks)
             elif isinstance(c, Until):
                 self._emit(abi.OP_CHILD_UNTIL, 0, _prio32(c.priority), c.ticks)

@@ -73,44 +73,88 @@ struct program_model {
         rt[p].loops.clear();
     }
 
-    bool composition(int32_t self, const cxxdes_b200_op &head, uint32_t first) {
-        process &me = eng.procs[self];
-        const bool is_all = head.code == CXXDES_B200_OP_ALL_OF;
-        const size_t total = head.a;
-        // await_bind (any_of.ipp:41-48): the composition's own priority (.priority(p), else the awaiting process's)
-        // is what the children inherit
-        int64_t comp_prio = prio_of(head);
-        if (comp_prio == PRIO_INHERIT) comp_prio = me.priority;
-        for (size_t c = 0; c < total; ++c) {
-            const cxxdes_b200_op &ch = prg.ops[first + c];
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) eng.bind(ch.a, comp_prio);
+    // all_of / any_of, possibly nested (any_of.ipp:41-92).  Restated recursively, the way the reference's awaitables
+    // call each other: await_bind, await_ready, await_suspend of a composition call the same function of every
+    // child.  `pos` walks the children, which follow the head in pre-order.
+    struct comp_node {
+        bool is_all = false, ready = false;
+        size_t total = 0, remaining = 0;
+        int64_t prio = 0, latency = 0;
+        std::vector<int> kids;        // >= 0: index into nodes, < 0: ~op position of a leaf
+        std::vector<bool> kid_ready;
+    };
+    std::vector<comp_node> nodes;
+
+    int parse(const cxxdes_b200_op &head, bool is_all, int64_t inherited, uint32_t &pos) {
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        nodes[id].is_all = is_all;
+        nodes[id].total = head.a;
+        nodes[id].latency = head.imm;
+        int64_t pr = prio_of(head);
+        nodes[id].prio = pr == PRIO_INHERIT ? inherited : pr;     // await_bind: priority_ = inherited (:44-45)
+        for (uint32_t c = 0; c < head.a; ++c) {
+            const cxxdes_b200_op &ch = prg.ops[pos];
+            if (ch.code == CXXDES_B200_OP_CHILD_ALL_OF || ch.code == CXXDES_B200_OP_CHILD_ANY_OF) {
+                ++pos;
+                const int kid = parse(ch, ch.code == CXXDES_B200_OP_CHILD_ALL_OF, nodes[id].prio, pos);
+                nodes[id].kids.push_back(kid);
+            } else {
+                if (ch.code == CXXDES_B200_OP_CHILD_PROC) eng.bind(ch.a, nodes[id].prio);   // await_bind of a coroutine child
+                nodes[id].kids.push_back(~(int)pos);
+                ++pos;
+            }
         }
-        // await_ready (:50-64)
-        std::vector<bool> ready;
-        size_t remaining = total;
-        for (size_t c = 0; c < total; ++c) {
-            const cxxdes_b200_op &ch = prg.ops[first + c];
-            bool r = false;
-            if (ch.code == CXXDES_B200_OP_CHILD_PROC) r = eng.procs[ch.a].complete;
-            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) r = eng.now >= ch.imm;
-            ready.push_back(r);
-            if (r) --remaining;
+        return id;
+    }
+
+    bool ready_of(int id) {   // await_ready (:50-64)
+        comp_node &n = nodes[id];
+        n.remaining = n.total;
+        n.kid_ready.clear();
+        for (int k : n.kids) {
+            bool r;
+            if (k >= 0) r = ready_of(k);
+            else {
+                const cxxdes_b200_op &ch = prg.ops[~k];
+                r = ch.code == CXXDES_B200_OP_CHILD_PROC ? (bool)eng.procs[ch.a].complete
+                    : ch.code == CXXDES_B200_OP_CHILD_UNTIL ? eng.now >= ch.imm : false;
+            }
+            nodes[id].kid_ready.push_back(r);
+            if (r) --nodes[id].remaining;
         }
-        if (is_all ? remaining == 0 : remaining < total) return false;
-        // await_suspend (:66-84)
-        // the output token {return latency, priority, self} (:67); its time and priority are completed by the
-        // child token that satisfies the condition (:19-23)
-        int32_t h = eng.add_handler(is_all, total, remaining, token{head.imm, comp_prio, self, NO_HANDLER});
-        for (size_t c = 0; c < total; ++c) {
-            if (ready[c]) continue;
-            const cxxdes_b200_op &ch = prg.ops[first + c];
+        comp_node &m = nodes[id];
+        m.ready = m.is_all ? m.remaining == 0 : m.remaining < m.total;
+        return m.ready;
+    }
+
+    void suspend(int id, int32_t self, int32_t out_handler) {   // await_suspend (:66-84)
+        // the output token {return latency, priority, self}; its handler is the enclosing composition's (:79-80)
+        const int32_t h = eng.add_handler(nodes[id].is_all, nodes[id].total, nodes[id].remaining,
+                                          token{nodes[id].latency, nodes[id].prio, self, out_handler});
+        for (size_t c = 0; c < nodes[id].kids.size(); ++c) {
+            if (nodes[id].kid_ready[c]) continue;
+            const int k = nodes[id].kids[c];
+            if (k >= 0) {
+                suspend(k, self, h);
+                continue;
+            }
+            const cxxdes_b200_op &ch = prg.ops[~k];
             if (ch.code == CXXDES_B200_OP_CHILD_PROC) await_completion(ch.a, self, h);
             else {
                 int64_t pr = prio_of(ch);
-                if (pr == PRIO_INHERIT) pr = comp_prio;
+                if (pr == PRIO_INHERIT) pr = nodes[id].prio;
                 eng.schedule(token{ch.code == CXXDES_B200_OP_CHILD_DELAY ? eng.now + ch.imm : ch.imm, pr, self, h});
             }
         }
+    }
+
+    // returns true when the awaiting process suspends; `pos` ends behind the last child
+    bool composition(int32_t self, const cxxdes_b200_op &head, uint32_t &pos) {
+        nodes.clear();
+        const int root = parse(head, head.code == CXXDES_B200_OP_ALL_OF, eng.procs[self].priority, pos);
+        if (ready_of(root)) return false;
+        suspend(root, self, NO_HANDLER);
         return true;
     }
 
@@ -164,9 +208,10 @@ struct program_model {
                     break;
                 case CXXDES_B200_OP_ALL_OF:
                 case CXXDES_B200_OP_ANY_OF: {
-                    uint32_t first = r.pc + 1;
-                    r.pc += 1 + op.a;
-                    if (composition(p, op, first)) return;
+                    uint32_t pos = r.pc + 1;
+                    const bool suspended = composition(p, op, pos);
+                    rt[p].pc = pos;
+                    if (suspended) return;
                     break;
                 }
                 case CXXDES_B200_OP_Q_PUT: {

@@ -357,6 +357,25 @@ CXXDES_SIMULATION(kat_sequential) {
     coroutine<> co_main() { return tr.named(body(), 0); }
 };
 
+// 16 -- examples/any_of.cpp: nested compositions -- (a && b) || (c && d), and a chain a && b && c, which the
+//       operators build as all_of(all_of(a, b), c): 100, 120, 130, 133
+CXXDES_SIMULATION(kat_any_of_example) {
+    tracer &tr;
+    std::vector<time_integral> marks;
+    explicit kat_any_of_example(tracer &t) : tr{t} { bind(); }
+    coroutine<> body() {
+        co_await ((timeout(1000) && timeout(5)) || (timeout(100) && timeout(1)));
+        marks.push_back(now());  // 100
+        co_await all_of(timeout(10), timeout(20));
+        marks.push_back(now());  // 120
+        co_await any_of(timeout(10), timeout(20));
+        marks.push_back(now());  // 130
+        co_await (delay(1) && delay(2) && delay(3));
+        marks.push_back(now());  // 133
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
 // Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
 // application-level observations are compared too, not only the token trace.
 inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
@@ -396,6 +415,7 @@ inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::ve
         case 13: return run_kat_sim<kat_get_environment>(tr, until);
         case 14: return run_kat_sim<kat_lazy_timeout>(tr, until);
         case 15: return run_kat_sim<kat_sequential>(tr, until);
+        case 16: return run_kat_sim<kat_any_of_example>(tr, until);
         default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
     }
 }

@@ -26,30 +26,55 @@ namespace ref_oracle {
 // One child of a composition whose arity and child kinds are only known at run time: a user-level awaitable
 // (it satisfies the library's `awaitable` concept, awaitable.ipp:14-27) that forwards every call to the real
 // awaitable it holds, so `all_of.range(first, last)` (any_of.ipp:200-213) can take a mixed list.
+struct nested_child;   // a composition used as a child: the library's own all_of / any_of object over any_child's
+
 struct any_child {
     using delay_type = decltype(delay(time_integral{}, priority_type{}));
     using until_type = decltype(until(time_integral{}, priority_type{}));
-    std::variant<coroutine<>, delay_type, until_type> v;
+    std::variant<coroutine<>, delay_type, until_type, std::shared_ptr<nested_child>> v;
 
-    void await_bind(environment *env, priority_type priority) {
-        std::visit([&](auto &a) { a.await_bind(env, priority); }, v);
-    }
-    bool await_ready() {
-        return std::visit([](auto &a) -> bool { return a.await_ready(); }, v);
-    }
-    void await_suspend(coroutine_data_ptr coro_data) {
-        std::visit([&](auto &a) { a.await_suspend(coro_data); }, v);
-    }
-    token *await_token() {
-        return std::visit([](auto &a) -> token * { return a.await_token(); }, v);
-    }
-    void await_resume() {
-        std::visit([](auto &a) { a.await_resume(no_return_value_tag{}); }, v);
-    }
-    void await_resume(no_return_value_tag) {
-        std::visit([](auto &a) { a.await_resume(no_return_value_tag{}); }, v);
-    }
+    void await_bind(environment *env, priority_type priority);
+    bool await_ready();
+    void await_suspend(coroutine_data_ptr coro_data);
+    token *await_token();
+    void await_resume() { await_resume(no_return_value_tag{}); }
+    void await_resume(no_return_value_tag);
 };
+
+struct nested_child {
+    using all_type = decltype(all_of.range(std::declval<std::vector<any_child>::iterator>(),
+                                           std::declval<std::vector<any_child>::iterator>()));
+    using any_type = decltype(any_of.range(std::declval<std::vector<any_child>::iterator>(),
+                                           std::declval<std::vector<any_child>::iterator>()));
+    std::variant<all_type, any_type> comp;
+};
+
+template <typename F>
+inline auto visit_child(any_child &c, F &&f) {
+    return std::visit(
+        [&](auto &a) {
+            if constexpr (std::is_same_v<std::remove_reference_t<decltype(a)>, std::shared_ptr<nested_child>>)
+                return std::visit([&](auto &inner) { return f(inner); }, a->comp);
+            else
+                return f(a);
+        },
+        c.v);
+}
+inline void any_child::await_bind(environment *env, priority_type priority) {
+    visit_child(*this, [&](auto &a) { a.await_bind(env, priority); });
+}
+inline bool any_child::await_ready() {
+    return visit_child(*this, [](auto &a) -> bool { return a.await_ready(); });
+}
+inline void any_child::await_suspend(coroutine_data_ptr coro_data) {
+    visit_child(*this, [&](auto &a) { a.await_suspend(coro_data); });
+}
+inline token *any_child::await_token() {
+    return visit_child(*this, [](auto &a) -> token * { return a.await_token(); });
+}
+inline void any_child::await_resume(no_return_value_tag) {
+    visit_child(*this, [](auto &a) { a.await_resume(no_return_value_tag{}); });
+}
 static_assert(awaitable<any_child>);
 
 struct program_sim {
@@ -109,6 +134,37 @@ struct program_sim {
         procs[p].co.emplace(std::move(co));
     }
 
+    // the children of a composition, built from the operations that follow it in pre-order; a nested composition
+    // becomes the library's own all_of / any_of object (with its options) wrapped as a child
+    std::vector<any_child> children_of(const cxxdes_b200_op &head, uint32_t &pos) {
+        std::vector<any_child> children;
+        for (uint32_t c = 0; c < head.a; ++c) {
+            const cxxdes_b200_op ch = prg.ops[pos++];
+            if (ch.code == CXXDES_B200_OP_CHILD_PROC) children.push_back(any_child{*procs[ch.a].co});
+            else if (ch.code == CXXDES_B200_OP_CHILD_DELAY)
+                children.push_back(any_child{delay((time_integral)ch.imm, prio_of(ch.b))});
+            else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL)
+                children.push_back(any_child{until((time_integral)ch.imm, prio_of(ch.b))});
+            else {
+                std::vector<any_child> inner = children_of(ch, pos);
+                std::shared_ptr<nested_child> nested;
+                if (ch.code == CXXDES_B200_OP_CHILD_ALL_OF) {
+                    auto comp = all_of.range(inner.begin(), inner.end());
+                    if (ch.b != CXXDES_B200_INHERIT) comp.priority((priority_type)ch.b);
+                    comp.return_latency((time_integral)ch.imm);
+                    nested.reset(new nested_child{std::move(comp)});
+                } else {
+                    auto comp = any_of.range(inner.begin(), inner.end());
+                    if (ch.b != CXXDES_B200_INHERIT) comp.priority((priority_type)ch.b);
+                    comp.return_latency((time_integral)ch.imm);
+                    nested.reset(new nested_child{std::move(comp)});
+                }
+                children.push_back(any_child{nested});
+            }
+        }
+        return children;
+    }
+
     coroutine<> body(uint32_t p) {
         uint32_t pc = prg.procs[p].entry;
         int64_t loops[8];
@@ -148,15 +204,8 @@ struct program_sim {
                     break;
                 case CXXDES_B200_OP_ALL_OF:
                 case CXXDES_B200_OP_ANY_OF: {
-                    std::vector<any_child> children;
-                    for (uint32_t c = 1; c <= op.a; ++c) {
-                        const cxxdes_b200_op &ch = prg.ops[pc + c];
-                        if (ch.code == CXXDES_B200_OP_CHILD_PROC) children.push_back(any_child{*procs[ch.a].co});
-                        else if (ch.code == CXXDES_B200_OP_CHILD_DELAY)
-                            children.push_back(any_child{delay((time_integral)ch.imm, prio_of(ch.b))});
-                        else
-                            children.push_back(any_child{until((time_integral)ch.imm, prio_of(ch.b))});
-                    }
+                    uint32_t pos = pc + 1;
+                    std::vector<any_child> children = children_of(op, pos);
                     if (op.code == CXXDES_B200_OP_ALL_OF) {
                         auto comp = all_of.range(children.begin(), children.end());
                         if (op.b != CXXDES_B200_INHERIT) comp.priority((priority_type)op.b);
@@ -168,7 +217,7 @@ struct program_sim {
                         comp.return_latency((time_integral)op.imm);
                         co_await std::move(comp);
                     }
-                    pc += op.a;
+                    pc = pos - 1;
                     break;
                 }
                 case CXXDES_B200_OP_Q_PUT:

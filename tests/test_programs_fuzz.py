@@ -79,6 +79,13 @@ def random_program(seed):
             children = [L.Delay(rng.randint(0, 60), priority=prio()) for _ in range(rng.randint(1, 3))]
             if rng.random() < 0.3:
                 children.append(L.Until(rng.randint(0, 2000)))
+            if rng.random() < 0.35:      # a nested composition: (a && b) || c, a && b && c
+                inner = [L.Delay(rng.randint(0, 60), priority=prio()) for _ in range(rng.randint(1, 3))]
+                if rng.random() < 0.3:
+                    inner.append(L.AnyOf(L.Delay(rng.randint(0, 30)), L.Until(rng.randint(0, 1500))))
+                nested = (L.AllOf if rng.random() < 0.5 else L.AnyOf)(*inner, priority=prio() if rng.random() < 0.3 else None,
+                                                                      return_latency=rng.choice((0, 0, 2)))
+                children.insert(rng.randint(0, len(children)), nested)
             if budget[0] > 0 and depth == 0 and rng.random() < 0.5:
                 budget[0] -= 1
                 children.insert(rng.randint(0, len(children)), helper(depth))

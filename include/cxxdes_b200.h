@@ -159,7 +159,10 @@ enum {
                                        in the reference (compositions.ipp); a = its own child count, its children
                                        follow in place (pre-order), b / imm as for ALL_OF.  When the inner condition
                                        holds, its output token goes to the OUTER handler (any_of.ipp:66-84)        */
-    CXXDES_B200_OP_CHILD_ANY_OF = 33 /*   child: a nested any_of                                                   */
+    CXXDES_B200_OP_CHILD_ANY_OF = 33,/*   child: a nested any_of                                                   */
+    CXXDES_B200_OP_CHILD_EV_WAIT = 34/*   child: event[a].wait(imm latency, b priority) -- `evt.wait() || timeout(t)`, waiting
+                                       for a signal with a time limit (sync/event.hpp:27-74,136-139): the waiter token
+                                       carries the composition's handler                                           */
 };
 enum {  /* what an IF looks at: plain reads of public state, no events */
     CXXDES_B200_SRC_COUNTER = 0,    /* i64[index]                                        */

@@ -95,8 +95,9 @@ struct async_t {  // async(p): async.ipp:9-49
 inline async_t async(process p) { return {p}; }
 
 struct composition;
+struct simple_op;
 struct child {  // an operand of all_of / any_of / && / ||: a process, a timer, or another composition
-    enum kind_t { PROC, DELAY, UNTIL, NESTED } kind;
+    enum kind_t { PROC, DELAY, UNTIL, NESTED, EV_WAIT } kind;
     std::uint32_t proc;
     time_integral ticks;
     priority_type prio;
@@ -105,6 +106,7 @@ struct child {  // an operand of all_of / any_of / && / ||: a process, a timer, 
     child(delay_t d) : kind(DELAY), proc(0), ticks(d.ticks), prio(d.prio) {}
     child(until_t u) : kind(UNTIL), proc(0), ticks(u.ticks), prio(u.prio) {}
     child(const composition &c);
+    child(const simple_op &op);          // evt.wait(latency, priority): `evt.wait() || timeout(t)`
 };
 struct composition {  // any_of.ipp:233-247; compositions.ipp (operator&&, operator||)
     bool all;
@@ -174,6 +176,10 @@ struct simple_op {
     std::int32_t b;
     std::int64_t imm;
 };
+inline child::child(const simple_op &op) : kind(EV_WAIT), proc(op.a), ticks(op.imm), prio(op.b == CXXDES_B200_INHERIT ? inherit : (priority_type)op.b) {
+    if (op.code != CXXDES_B200_OP_EV_WAIT)
+        throw std::invalid_argument("cxxdes_b200: of the sync operations only evt.wait() can be a child of all_of / any_of");
+}
 struct queue {  // sync::queue<T>: sync/queue.hpp:38-90
     std::uint16_t id;
     simple_op put() const { return {CXXDES_B200_OP_Q_PUT, id, 0, 0}; }           // q.put(now)
@@ -443,6 +449,8 @@ private:
             if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);
             else if (ch.kind == child::NESTED)
                 emit_composition(*ch.nested, ch.nested->all ? CXXDES_B200_OP_CHILD_ALL_OF : CXXDES_B200_OP_CHILD_ANY_OF);
+            else if (ch.kind == child::EV_WAIT)
+                prog_.emit(CXXDES_B200_OP_CHILD_EV_WAIT, (std::uint16_t)ch.proc, detail::prio32(ch.prio), ch.ticks);
             else
                 prog_.emit(ch.kind == child::DELAY ? CXXDES_B200_OP_CHILD_DELAY : CXXDES_B200_OP_CHILD_UNTIL, 0,
                            detail::prio32(ch.prio), ch.ticks);

@@ -6,10 +6,10 @@ when the in-tree CUDA library (libcxxdes_b200/_lib/libcxxdes_b200.so) is missing
 from . import abi
 from .abi import (AlohaParams, ArchSimParams, Clock, HostColumns, MM1Params, MMCParams,
                   MILLISECONDS, MICROSECONDS, NANOSECONDS, PICOSECONDS, SECONDS)
-from .program import AllOf, AnyOf, Delay, Program, Until
+from .program import AllOf, AnyOf, Delay, Program, Until, Wait
 from .ensemble import (CxxdesError, Ensemble, EXPORTED_SYMBOLS, device_count, library_path,
                        load_library)
 
 __all__ = ["abi", "AlohaParams", "ArchSimParams", "Clock", "HostColumns", "MM1Params", "MMCParams",
            "SECONDS", "MILLISECONDS", "MICROSECONDS", "NANOSECONDS", "PICOSECONDS", "CxxdesError",
-           "Ensemble", "EXPORTED_SYMBOLS", "device_count", "library_path", "load_library", "Program", "Delay", "Until", "AllOf", "AnyOf"]
+           "Ensemble", "EXPORTED_SYMBOLS", "device_count", "library_path", "load_library", "Program", "Delay", "Until", "AllOf", "AnyOf", "Wait"]

@@ -20,7 +20,7 @@ INHERIT64 = 2 ** 63 - 1          # priority_consts::inherit (defs.ipp:35)
 (OP_RETURN, OP_DELAY, OP_UNTIL, OP_DELAY_EXP, OP_DELAY_REAL, OP_FRESH, OP_AWAIT, OP_ASYNC, OP_ALL_OF, OP_ANY_OF,
  OP_CHILD_PROC, OP_CHILD_DELAY, OP_CHILD_UNTIL, OP_Q_PUT, OP_Q_POP, OP_SEM_DOWN, OP_SEM_UP, OP_MTX_ACQUIRE,
  OP_MTX_RELEASE, OP_EV_WAIT, OP_EV_WAKE, OP_LOOP, OP_END_LOOP, OP_SET_REG_NOW, OP_STAT_SECONDS, OP_STAT_TICKS,
- OP_COUNT, OP_MARK, OP_LAZY_TIMEOUT, OP_UNTIL_REG, OP_IF, OP_JUMP, OP_CHILD_ALL_OF, OP_CHILD_ANY_OF) = range(34)
+ OP_COUNT, OP_MARK, OP_LAZY_TIMEOUT, OP_UNTIL_REG, OP_IF, OP_JUMP, OP_CHILD_ALL_OF, OP_CHILD_ANY_OF, OP_CHILD_EV_WAIT) = range(35)
 (SRC_COUNTER, SRC_QUEUE_SIZE, SRC_SEM_VALUE, SRC_NOW, SRC_REGISTER, SRC_MUTEX) = range(6)
 CMP = {"==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
 FLAG_GENERIC_ENGINE = 1

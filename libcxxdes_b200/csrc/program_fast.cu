@@ -745,8 +745,8 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
             case CXXDES_B200_OP_IF:
                 if (((op.a >> 8) & 0xFu) == CXXDES_B200_SRC_REGISTER) uses_reg = true;
                 break;
-            case CXXDES_B200_OP_CHILD_ALL_OF: case CXXDES_B200_OP_CHILD_ANY_OF:
-                return L;   // nested compositions: the full-size kernel alone (valid stays false)
+            case CXXDES_B200_OP_CHILD_ALL_OF: case CXXDES_B200_OP_CHILD_ANY_OF: case CXXDES_B200_OP_CHILD_EV_WAIT:
+                return L;   // nested compositions, event waits inside compositions: the full-size kernel alone
             case CXXDES_B200_OP_DELAY_EXP:
                 uses_draws = true;
                 break;

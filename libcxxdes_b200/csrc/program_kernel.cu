@@ -43,6 +43,7 @@ struct proc_rt {
 
 struct waiters_rt {  // sync::event: FIFO of {latency, priority, process}  (event.hpp:87-139)
     uint32_t who[PRG_WAITERS];
+    uint32_t hser[PRG_WAITERS];   // handler serial + 1 when the wait is a child of any_of / all_of, else 0
     int32_t lat[PRG_WAITERS];
     int16_t prio[PRG_WAITERS];
     int n;
@@ -126,12 +127,13 @@ struct interp {
         r.complete = true;
     }
 
-    __device__ void wait_on(waiters_rt &w, uint32_t p, int64_t latency, int64_t prio) {
+    __device__ void wait_on(waiters_rt &w, uint32_t p, int64_t latency, int64_t prio, uint32_t handler_serial_plus1 = 0) {
         if (w.n >= PRG_WAITERS || prio < -32768 || prio > 32767 || latency < 0 || latency > INT32_MAX) {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
         }
         w.who[w.n] = p;
+        w.hser[w.n] = handler_serial_plus1;
         w.lat[w.n] = (int32_t)latency;
         w.prio[w.n] = (int16_t)prio;
         ++w.n;
@@ -139,7 +141,7 @@ struct interp {
 
     // wake_awaitable::await_ready, event.hpp:125-134
     __device__ void wake(waiters_rt &w) {
-        for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], ptag(w.who[k]));
+        for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], ptag(w.who[k], w.hser[k]));
         w.n = 0;
     }
 
@@ -261,6 +263,8 @@ struct interp {
                 if (ch.code == CXXDES_B200_OP_CHILD_PROC) register_completion(ch.a, tag);
                 else if (ch.code == CXXDES_B200_OP_CHILD_DELAY) env.schedule(env.now + ch.imm, pr, tag);
                 else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL) env.schedule(ch.imm, pr, tag);
+                else if (ch.code == CXXDES_B200_OP_CHILD_EV_WAIT)   // the waiter token carries the handler (event.hpp:136-139)
+                    wait_on(e_wait[ch.a], self_id, ch.imm, pr, nodes[cur].serial_plus1);
                 else env.status |= CXXDES_B200_REP_BAD_PROGRAM;
             }
             ++pos;
@@ -631,9 +635,10 @@ const char *program_check(const cxxdes_b200_program &p) {
                         if (ch.a < 1 || ch.a > 32 || ++nodes > 8) return "program: bad nested composition (at most 8 compositions in one co_await)";
                         pending += ch.a;
                     } else if (ch.code == CXXDES_B200_OP_CHILD_PROC || ch.code == CXXDES_B200_OP_CHILD_DELAY ||
-                               ch.code == CXXDES_B200_OP_CHILD_UNTIL) {
+                               ch.code == CXXDES_B200_OP_CHILD_UNTIL || ch.code == CXXDES_B200_OP_CHILD_EV_WAIT) {
                         if (++leaves > 64) return "program: at most 64 awaitables in one co_await";
                         if (ch.code == CXXDES_B200_OP_CHILD_PROC && ch.a >= p.n_procs) return "program: process operand out of range";
+                        if (ch.code == CXXDES_B200_OP_CHILD_EV_WAIT && ch.a >= p.n_events) return "program: event operand out of range";
                     } else {
                         return "program: composition children must be CHILD_* ops";
                     }
@@ -678,7 +683,7 @@ const char *program_check(const cxxdes_b200_program &p) {
                 if (op.b <= (int64_t)i || (uint32_t)op.b >= p.n_ops) return "program: IF / JUMP target must lie ahead, inside the program";
                 break;
             default:
-                if (op.code > CXXDES_B200_OP_CHILD_ANY_OF) return "program: unknown op code";
+                if (op.code > CXXDES_B200_OP_CHILD_EV_WAIT) return "program: unknown op code";
         }
     }
     return nullptr;

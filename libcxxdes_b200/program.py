@@ -52,6 +52,14 @@ class AnyOf(AllOf):
     code = abi.OP_CHILD_ANY_OF
 
 
+class Wait:
+    """evt.wait(latency, priority) as a child of all_of / any_of: `evt.wait() || timeout(t)`, waiting for a signal with
+    a time limit (sync/event.hpp:136-139)."""
+
+    def __init__(self, event, latency=0, priority=None):
+        self.event, self.latency, self.priority = int(event), int(latency), priority
+
+
 def _prio32(priority):
     return abi.INHERIT32 if priority is None else int(priority)
 
@@ -111,6 +119,8 @@ class Body:
         for c in children:
             if isinstance(c, AllOf):                 # nested: its children follow in place (pre-order)
                 self._composition(c.code, c.children, c.priority, c.return_latency)
+            elif isinstance(c, Wait):
+                self._emit(abi.OP_CHILD_EV_WAIT, c.event, _prio32(c.priority), c.latency)
             elif isinstance(c, Delay):
                 self._emit(abi.OP_CHILD_DELAY, 0, _prio32(c.priority), c.ticks)
             elif isinstance(c, Until):

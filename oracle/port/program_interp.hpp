@@ -144,7 +144,10 @@ struct program_model {
             else {
                 int64_t pr = prio_of(ch);
                 if (pr == PRIO_INHERIT) pr = nodes[id].prio;
-                eng.schedule(token{ch.code == CXXDES_B200_OP_CHILD_DELAY ? eng.now + ch.imm : ch.imm, pr, self, h});
+                if (ch.code == CXXDES_B200_OP_CHILD_EV_WAIT)   // wait_awaitable::await_suspend; the token gets the handler
+                    e_event[ch.a].waiters.push_back(token{ch.imm, pr, self, h});
+                else
+                    eng.schedule(token{ch.code == CXXDES_B200_OP_CHILD_DELAY ? eng.now + ch.imm : ch.imm, pr, self, h});
             }
         }
     }

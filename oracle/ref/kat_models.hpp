@@ -376,6 +376,36 @@ CXXDES_SIMULATION(kat_any_of_example) {
     coroutine<> co_main() { return tr.named(body(), 0); }
 };
 
+// 17 -- examples/complicated.cpp p1 / p2: waiting for a signal with a time limit, `evt.wait() || timeout(t)`.
+//       First the wake wins (5), then the timeout does (8) and the waiter left behind is woken for nothing (12),
+//       then a wait with latency inside all_of: 12, woken at 20 + 2 = 22
+CXXDES_SIMULATION(kat_wait_or_timeout) {
+    tracer &tr;
+    cxxdes::sync::event evt;
+    std::vector<time_integral> marks;
+    explicit kat_wait_or_timeout(tracer &t) : tr{t} { bind(); }
+    coroutine<> p1() {
+        co_await timeout(5);
+        co_await evt.wake();
+        co_await timeout(7);
+        co_await evt.wake();      // 12: wakes the waiter the second any_of left behind
+        co_await timeout(8);
+        co_await evt.wake();      // 20
+    }
+    coroutine<> p2() {
+        co_await (evt.wait() || timeout(8));
+        marks.push_back(now());   // 5
+        co_await (evt.wait() || timeout(3));
+        marks.push_back(now());   // 8
+        co_await timeout(4);
+        marks.push_back(now());   // 12
+        co_await all_of(evt.wait(2), timeout(1));
+        marks.push_back(now());   // 22
+    }
+    coroutine<> body() { co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2)); }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
 // Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
 // application-level observations are compared too, not only the token trace.
 inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
@@ -416,6 +446,7 @@ inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::ve
         case 14: return run_kat_sim<kat_lazy_timeout>(tr, until);
         case 15: return run_kat_sim<kat_sequential>(tr, until);
         case 16: return run_kat_sim<kat_any_of_example>(tr, until);
+        case 17: return run_kat_sim<kat_wait_or_timeout>(tr, until);
         default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
     }
 }

@@ -31,7 +31,8 @@ struct nested_child;   // a composition used as a child: the library's own all_o
 struct any_child {
     using delay_type = decltype(delay(time_integral{}, priority_type{}));
     using until_type = decltype(until(time_integral{}, priority_type{}));
-    std::variant<coroutine<>, delay_type, until_type, std::shared_ptr<nested_child>> v;
+    using wait_type = decltype(std::declval<cxxdes::sync::event &>().wait(time_integral{}, priority_type{}));
+    std::variant<coroutine<>, delay_type, until_type, std::shared_ptr<nested_child>, wait_type> v;
 
     void await_bind(environment *env, priority_type priority);
     bool await_ready();
@@ -145,6 +146,8 @@ struct program_sim {
                 children.push_back(any_child{delay((time_integral)ch.imm, prio_of(ch.b))});
             else if (ch.code == CXXDES_B200_OP_CHILD_UNTIL)
                 children.push_back(any_child{until((time_integral)ch.imm, prio_of(ch.b))});
+            else if (ch.code == CXXDES_B200_OP_CHILD_EV_WAIT)
+                children.push_back(any_child{events[ch.a].wait((time_integral)ch.imm, prio_of(ch.b))});
             else {
                 std::vector<any_child> inner = children_of(ch, pos);
                 std::shared_ptr<nested_child> nested;

@@ -5,7 +5,7 @@ the names given with tracer::named() on the reference side; a `_Co_with` helper 
 ordinal of its parent | 0x8000 (how the reference harness reports unnamed library coroutines)."""
 import ctypes as C
 
-from libcxxdes_b200 import AllOf, AnyOf, Delay, Program, Until
+from libcxxdes_b200 import AllOf, AnyOf, Delay, Program, Until, Wait
 
 ORACLE_MODEL_KAT = 100
 
@@ -234,11 +234,28 @@ def any_of_example():         # 16: examples/any_of.cpp -- nested compositions, 
     return prog, -1
 
 
+def wait_or_timeout():        # 17: examples/complicated.cpp p1 / p2 -- evt.wait() || timeout(t)
+    prog = Program()
+    evt = prog.event()
+    main = prog.process(0, root=True)
+    p1, p2 = prog.process(1), prog.process(2)
+    with prog.body(p1) as b:
+        b.delay(5); b.wake(evt); b.delay(7); b.wake(evt); b.delay(8); b.wake(evt)
+    with prog.body(p2) as b:
+        b.any_of(Wait(evt), Delay(8)); b.mark(1, 0)
+        b.any_of(Wait(evt), Delay(3)); b.mark(1, 0)
+        b.delay(4); b.mark(1, 0)
+        b.all_of(Wait(evt, 2), Delay(1)); b.mark(1, 0)
+    with prog.body(main) as b:
+        b.all_of(p1, p2)
+    return prog, -1
+
+
 SCENARIOS = {1: compositions, 2: latencies, 3: out_of_scope, 4: priorities, 5: clocks, 6: resource, 7: mutex,
-             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout, 15: sequential, 16: any_of_example}
+             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout, 15: sequential, 16: any_of_example, 17: wait_or_timeout}
 # end time of every scenario on the reference engine (the reference's tests / examples document the
 # observation times; scenario 1 ends at 40 because the loser of any_of(timeout(10), timeout(20)) still fires)
-EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30, 15: 20, 16: 1000}
+EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30, 15: 20, 16: 1000, 17: 22}
 
 
 def mm1_program(lam, mu, n_packets):

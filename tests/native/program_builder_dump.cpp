@@ -312,6 +312,26 @@ static program any_of_example() {
     return prog;
 }
 
+// examples/complicated.cpp p1 / p2: evt.wait() || timeout(t)
+static program wait_or_timeout_example() {
+    program prog;
+    event evt = prog.add_event();
+    process co_main = prog.add_process(0);
+    prog.bind(co_main);
+    process p1 = prog.add_process(1), p2 = prog.add_process(2);
+    prog.body_of(p1, [&](body &co) {
+        co.await(delay(5)).await(evt.wake()).await(delay(7)).await(evt.wake()).await(delay(8)).await(evt.wake());
+    });
+    prog.body_of(p2, [&](body &co) {
+        co.await(evt.wait() || timeout(8)).mark(1, 0);
+        co.await(evt.wait() || timeout(3)).mark(1, 0);
+        co.await(delay(4)).mark(1, 0);
+        co.await(all_of(evt.wait(2), timeout(1))).mark(1, 0);
+    });
+    prog.body_of(co_main, [&](body &co) { co.await(p1 && p2); });
+    return prog;
+}
+
 // sequential(a, b), the comma operator, a sequential as a child of all_of (sequential.ipp:1-20)
 static program sequential_example() {
     program prog;
@@ -344,7 +364,8 @@ int main() {
     dump("11", debug_example());
     dump("14", lazy_timeout_example());
     dump("15", sequential_example());
-    dump("16", any_of_example(), true);
+    dump("16", any_of_example());
+    dump("17", wait_or_timeout_example(), true);
     std::printf("}\n");
     // error behaviour: the reference throws std::runtime_error on misuse (environment.ipp:44-45)
     int caught = 0;

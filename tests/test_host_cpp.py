@@ -55,7 +55,7 @@ def _python_tables(prog):
 
 
 def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
-    """include/cxxdes_b200/program.hpp against the Python builder: the same models (M/M/1 and twelve of the
+    """include/cxxdes_b200/program.hpp against the Python builder: the same models (M/M/1 and thirteen of the
     reference's own test/example scenarios, whose Python programs are pinned on the reference engine by
     tests/test_programs.py) must lower to identical cxxdes_b200_program tables.  Built as C++17 and C++20
     (the reference's users compile as C++20, where `co_await` is a keyword)."""
@@ -72,7 +72,7 @@ def test_cpp_program_builder_emits_the_pinned_programs(tmp_path):
     assert got.pop("mm1") == _python_tables(K.mm1_program(5.0, 10.0, 300))
     assert got.pop("mm1k") == _python_tables(K.mm1k_program(8.0, 10.0, 400, 4))
     assert got.pop("mm1_sweep") == _python_tables(K.mm1_program([1.0, 3.0, 5.0, 7.0, 9.0], 10.0, 300))
-    assert sorted(got) == sorted(str(k) for k in (1, 2, 4, 5, 6, 7, 9, 10, 11, 14, 15, 16))
+    assert sorted(got) == sorted(str(k) for k in (1, 2, 4, 5, 6, 7, 9, 10, 11, 14, 15, 16, 17))
     for k, tables in got.items():
         assert tables == _python_tables(K.SCENARIOS[int(k)]()[0]), K.SCENARIOS[int(k)].__name__
 

@@ -79,6 +79,8 @@ def random_program(seed):
             children = [L.Delay(rng.randint(0, 60), priority=prio()) for _ in range(rng.randint(1, 3))]
             if rng.random() < 0.3:
                 children.append(L.Until(rng.randint(0, 2000)))
+            if events and rng.random() < 0.3:          # evt.wait() || timeout(t)
+                children.insert(rng.randint(0, len(children)), L.Wait(rng.choice(events), rng.randint(0, 4), prio()))
             if rng.random() < 0.35:      # a nested composition: (a && b) || c, a && b && c
                 inner = [L.Delay(rng.randint(0, 60), priority=prio()) for _ in range(rng.randint(1, 3))]
                 if rng.random() < 0.3:

@@ -102,6 +102,8 @@ struct cxxdes_b200_ensemble {
     uint32_t *prog_state = nullptr;         // replications between run_until / run_for pieces (program_fast.cu)
     int64_t *prog_state_queues = nullptr;
     bool prog_state_valid = false;          // written by the previous launch of this handle
+    uint32_t *aloha_state = nullptr;        // replications between run_until / run_for pieces (models_aloha.cu)
+    bool aloha_state_valid = false;
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -304,9 +306,20 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             break;
         case CXXDES_B200_MODEL_ALOHA:
+        {
+            // run_until / run_for continue where the previous piece stopped when the 32-bit kernel runs the model
+            aloha_saved st{};
+            if (aloha_keeps_state(e->params.aloha, sh) && (until >= 0 || e->aloha_state_valid)) {
+                if (!e->aloha_state)
+                    CUDA_TRY(cudaMalloc(&e->aloha_state, aloha_saved_words(e->params.aloha) * 4 * e->cfg.n_replications));
+                st.words = e->aloha_state;
+                st.n_replications = e->cfg.n_replications;
+                st.resume = e->aloha_state_valid ? 1 : 0;
+            }
             CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
-                                  &launches));
+                                  &launches, st));
             break;
+        }
         case CXXDES_B200_MODEL_MMC:
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
                                 &launches));
@@ -347,6 +360,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->used = true;
     e->mm1_state_valid = e->mm1_state != nullptr;
     e->prog_state_valid = e->prog_state != nullptr;
+    e->aloha_state_valid = e->aloha_state != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -600,6 +614,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->timed = false;
     e->mm1_state_valid = false;
     e->prog_state_valid = false;
+    e->aloha_state_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -619,6 +634,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->program_blob);
     cudaFree(e->prog_queue_items);
     cudaFree(e->prog_state);
+    cudaFree(e->aloha_state);
     cudaFree(e->prog_state_queues);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);

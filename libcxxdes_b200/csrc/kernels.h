@@ -54,9 +54,16 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);
+struct aloha_saved {          // run_until / run_for in pieces (nullptr words = the plain run() kernel)
+    uint32_t *words;          // [word][replication], word 0 = phase
+    uint64_t n_replications;
+    int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
+};
+size_t aloha_saved_words(const cxxdes_b200_aloha_params &prm);
+bool aloha_keeps_state(const cxxdes_b200_aloha_params &prm, const shard &sh);   // the 32-bit kernel runs the model
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                          int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
-                         int *launches);
+                         int *launches, const aloha_saved &st);
 
 // ---- M/M/c with balking (models_mmc.cu) ----
 int mmc_blocks(int sm_count);

@@ -179,11 +179,20 @@ namespace {
 constexpr int AF_THREADS = 128;
 constexpr int AF_BLOCKS_PER_SM = 3;
 constexpr uint32_t CODE_MAIN = 0, CODE_HANDLER = 65, CODE_NOOP = 66, CODE_MASK = 127;
+constexpr uint32_t AF_PHASE_SAVED = 1, AF_PHASE_DONE = 2, AF_PHASE_REPLAY = 3;   // word 0 of a saved replication
 constexpr int COUNTER_SHIFT = 7;
 }  // namespace
 
+// STATEFUL: run_until / run_for in pieces (environment.ipp:190-214).  A replication that stops at the horizon with
+// tokens still scheduled is written to global memory, `[word][replication]`: 16 header words {phase, heap size,
+// clock, event count, digest, the three station masks, counters} and its live heap entries; the next launch
+// restores it.  Finished replications keep phase DONE (their end_time follows later horizons); replications the
+// 32-bit kernel handed to aloha_kernel get phase REPLAY and are replayed from tick 0 on every later piece.  A
+// separate instantiation, so that the plain run() path carries none of it.
+template <bool STATEFUL>
 __global__ void __launch_bounds__(AF_THREADS, AF_BLOCKS_PER_SM)
-aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, philox_schedule keys, uint32_t until) {
+aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, philox_schedule keys, uint32_t until,
+                  aloha_saved st) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -207,18 +216,52 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
     for (;;) {
         if (!active && !exhausted) {
             if (steal(sh, rep)) {
-                const uint64_t grep = sh.first_replication + rep;
-                rp = aloha_params_of(prm, grep);
-                // exponential_rv{seed, cfg_.lambda / cfg_.num_stations}: float / size_t -> float -> double (:52)
-                rate = make_divisor((double)(rp.lambda / (float)prm.num_stations));
-                ctr2 = (uint32_t)grep;
-                ctr3 = (uint32_t)(grep >> 32);
-                env.init(heap, heap_cap);
-                active_set = collided = pc_tx = 0;
-                successful = 0; main_pc = 0; remaining = 0; armed = false;
-                s_result = g_result = 0.0f;
-                env.schedule(0, CODE_MAIN);  // environment::bind(co_main)
-                active = true;
+                const uint32_t phase = STATEFUL && st.resume ? st.words[rep] : 0u;
+                if (STATEFUL && phase == AF_PHASE_DONE) {   // now_ = max(now_, t), environment.ipp:194
+                    if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) out.end_time[rep] = sh.run_until;
+                } else if (STATEFUL && phase == AF_PHASE_REPLAY) {
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                } else {
+                    const uint64_t grep = sh.first_replication + rep;
+                    rp = aloha_params_of(prm, grep);
+                    // exponential_rv{seed, cfg_.lambda / cfg_.num_stations}: float / size_t -> float -> double (:52)
+                    rate = make_divisor((double)(rp.lambda / (float)prm.num_stations));
+                    ctr2 = (uint32_t)grep;
+                    ctr3 = (uint32_t)(grep >> 32);
+                    env.init(heap, heap_cap);
+                    s_result = g_result = 0.0f;
+                    if (STATEFUL && phase == AF_PHASE_SAVED) {
+                        const uint32_t *sv = st.words + rep;
+                        const size_t n = st.n_replications;
+                        env.n = (int)sv[1 * n];
+                        env.now = sv[2 * n];
+                        env.n_events = sv[3 * n];
+                        env.hash = (uint64_t)sv[4 * n] | ((uint64_t)sv[5 * n] << 32);
+                        active_set = (uint64_t)sv[6 * n] | ((uint64_t)sv[7 * n] << 32);
+                        collided = (uint64_t)sv[8 * n] | ((uint64_t)sv[9 * n] << 32);
+                        pc_tx = (uint64_t)sv[10 * n] | ((uint64_t)sv[11 * n] << 32);
+                        successful = sv[12 * n];
+                        main_pc = sv[13 * n] & 0xFFu;
+                        armed = (sv[13 * n] >> 8) != 0;
+                        remaining = sv[14 * n];
+                        for (int k = 0; k < env.n; ++k)
+                            heap[k * AF_THREADS] = make_uint2(sv[(size_t)(16 + 2 * k) * n], sv[(size_t)(17 + 2 * k) * n]);
+                    } else {
+                        active_set = collided = pc_tx = 0;
+                        successful = 0; main_pc = 0; remaining = 0; armed = false;
+                        env.schedule(0, CODE_MAIN);  // environment::bind(co_main)
+                    }
+                    active = true;
+                    if (STATEFUL && phase == AF_PHASE_SAVED && env.next_time() > until) {
+                        // nothing of this replication falls into the piece: only its clock moves (environment.ipp:194)
+                        if (sh.run_until > (int64_t)env.now) {
+                            out.end_time[rep] = sh.run_until;
+                            st.words[2 * st.n_replications + rep] = (uint32_t)sh.run_until;
+                        }
+                        active = false;
+                    }
+                }
             } else {
                 exhausted = true;
             }
@@ -296,6 +339,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                 if (env.status & CXXDES_B200_REP_TIME_RANGE) {
                     const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
                     sh.retry_list[at] = (uint32_t)rep;
+                    if (STATEFUL) st.words[rep] = AF_PHASE_REPLAY;
                 } else {
                     rep_out o;
                     int64_t end = (int64_t)env.now;
@@ -303,6 +347,34 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                     if (sh.run_until >= 0) {
                         if (env.has_event()) o.status |= CXXDES_B200_REP_UNFINISHED;
                         end = end > sh.run_until ? end : sh.run_until;
+                    }
+                    if (STATEFUL) {
+                        uint32_t *sv = st.words + rep;
+                        const size_t n = st.n_replications;
+                        if (o.status & CXXDES_B200_REP_UNFINISHED) {
+                            sv[1 * n] = (uint32_t)env.n;
+                            sv[2 * n] = (uint32_t)end;      // run_until leaves now_ at the horizon
+                            sv[3 * n] = env.n_events;
+                            sv[4 * n] = (uint32_t)env.hash;
+                            sv[5 * n] = (uint32_t)(env.hash >> 32);
+                            sv[6 * n] = (uint32_t)active_set;
+                            sv[7 * n] = (uint32_t)(active_set >> 32);
+                            sv[8 * n] = (uint32_t)collided;
+                            sv[9 * n] = (uint32_t)(collided >> 32);
+                            sv[10 * n] = (uint32_t)pc_tx;
+                            sv[11 * n] = (uint32_t)(pc_tx >> 32);
+                            sv[12 * n] = successful;
+                            sv[13 * n] = main_pc | ((armed ? 1u : 0u) << 8);
+                            sv[14 * n] = remaining;
+                            for (int k = 0; k < env.n; ++k) {
+                                const uint2 e = heap[k * AF_THREADS];
+                                sv[(size_t)(16 + 2 * k) * n] = e.x;
+                                sv[(size_t)(17 + 2 * k) * n] = e.y;
+                            }
+                            sv[0] = AF_PHASE_SAVED;
+                        } else {
+                            sv[0] = AF_PHASE_DONE;
+                        }
                     }
                     o.end_time = end;
                     o.n_events = env.n_events;
@@ -348,9 +420,13 @@ bool aloha_fast_applies(const cxxdes_b200_aloha_params &p, const shard &sh) {
 }
 }  // namespace
 
+bool aloha_keeps_state(const cxxdes_b200_aloha_params &prm, const shard &sh) { return aloha_fast_applies(prm, sh); }
+
+size_t aloha_saved_words(const cxxdes_b200_aloha_params &prm) { return 16 + 2 * ((size_t)prm.num_stations + 2); }
+
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                          int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
-                         int *launches) {
+                         int *launches, const aloha_saved &st) {
     const size_t smem = aloha_smem_bytes(prm.num_stations);
     if (smem > smem_optin) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(aloha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -360,11 +436,13 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
     if (per_sm > 8) per_sm = 8;
     if (aloha_fast_applies(prm, sh)) {
         const size_t fsmem = aloha_fast_smem_bytes(prm.num_stations);
-        e = cudaFuncSetAttribute(aloha_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        e = cudaFuncSetAttribute(aloha_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(aloha_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
         if (e != cudaSuccess) return e;
         const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
         const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
-        aloha_fast_kernel<<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until);
+        if (st.words) aloha_fast_kernel<true><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
+        else aloha_fast_kernel<false><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

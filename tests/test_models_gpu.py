@@ -124,3 +124,30 @@ def test_run_until_pieces_then_run(port, name, fields):
     want.end_time[:] = np.maximum(want.end_time, horizons[-1])
     golden_util.assert_columns_equal(got, want, what=f"{name} run() after run_until")
     ens.close()
+
+
+def test_aloha_run_for_in_many_pieces_continues_from_saved_state(port):
+    """run_for(piece) x 12 on the compact ALOHA kernel: every replication that stops at the horizon is saved (heap,
+    station masks, counters: 16 + 2 (N + 2) words) and the next launch continues from it (environment.ipp:190-214);
+    columns equal the oracle's run_until(k * piece) after every piece, run() finishes the rest."""
+    model, cls, fname = MODELS["aloha"]
+    g = golden_util.load(fname)
+    p = cls(24, 50, 0.1, 3.0, 1.0, 60.0, 0)
+    n_reps = 500
+    clock = clock_pairs(g)
+    ends = port.run(model, p, clock_of(g), 9, 0, n_reps, threads=os.cpu_count()).end_time
+    piece = int(ends.max()) // 11
+    ens = L.Ensemble(p, n_reps, seed=9)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for k in range(1, 13):
+        ens.run_for(piece)
+        got = ens.fetch(strict=False)
+        want = port.run(model, p, clock_of(g), 9, 0, n_reps, threads=os.cpu_count(), until=k * piece)
+        assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+        golden_util.assert_columns_equal(got, want, what=f"aloha after piece {k}")
+    assert not ens.fetch(strict=False).status.any()          # 12 pieces reach past the longest replication
+    ens.reset()
+    ens.run_for(piece)
+    want = port.run(model, p, clock_of(g), 9, 0, n_reps, threads=os.cpu_count(), until=piece)
+    golden_util.assert_columns_equal(ens.fetch(strict=False), want, what="aloha after reset")
+    ens.close()

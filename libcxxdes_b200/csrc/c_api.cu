@@ -104,6 +104,8 @@ struct cxxdes_b200_ensemble {
     bool prog_state_valid = false;          // written by the previous launch of this handle
     uint32_t *aloha_state = nullptr;        // replications between run_until / run_for pieces (models_aloha.cu)
     bool aloha_state_valid = false;
+    uint32_t *arch_state = nullptr;         // ... of the memory-hierarchy model (models_archsim.cu)
+    bool arch_state_valid = false;
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -324,10 +326,19 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
                                 &launches));
             break;
-        case CXXDES_B200_MODEL_ARCHSIM:
-            CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream));
+        case CXXDES_B200_MODEL_ARCHSIM: {
+            archsim_saved st{};
+            if (until >= 0 || e->arch_state_valid) {
+                if (!e->arch_state)
+                    CUDA_TRY(cudaMalloc(&e->arch_state, archsim_saved_words(e->params.arch) * 4 * e->cfg.n_replications));
+                st.words = e->arch_state;
+                st.n_replications = e->cfg.n_replications;
+                st.resume = e->arch_state_valid ? 1 : 0;
+            }
+            CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream, st));
             launches = 1;
             break;
+        }
         case CXXDES_B200_MODEL_PROGRAM: {
             // run_until / run_for continue where the previous piece stopped (environment.ipp:190-214): the
             // shared-memory interpreter saves what is still running at the horizon and resumes it
@@ -361,6 +372,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->mm1_state_valid = e->mm1_state != nullptr;
     e->prog_state_valid = e->prog_state != nullptr;
     e->aloha_state_valid = e->aloha_state != nullptr;
+    e->arch_state_valid = e->arch_state != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -615,6 +627,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->mm1_state_valid = false;
     e->prog_state_valid = false;
     e->aloha_state_valid = false;
+    e->arch_state_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -635,6 +648,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->prog_queue_items);
     cudaFree(e->prog_state);
     cudaFree(e->aloha_state);
+    cudaFree(e->arch_state);
     cudaFree(e->prog_state_queues);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);

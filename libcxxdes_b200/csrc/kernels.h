@@ -75,8 +75,14 @@ cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const
 // ---- memory hierarchy (models_archsim.cu) ----
 bool archsim_supported(const cxxdes_b200_archsim_params &p);
 size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p);
+struct archsim_saved {        // run_until / run_for in pieces (nullptr words = the plain run() kernel)
+    uint32_t *words;          // [word][replication], word 0 = phase
+    uint64_t n_replications;
+    int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
+};
+size_t archsim_saved_words(const cxxdes_b200_archsim_params &p);
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
-                           int sm_count, cudaStream_t stream);
+                           int sm_count, cudaStream_t stream, const archsim_saved &st);
 
 // ---- process programs (program_kernel.cu) ----
 struct device_program {  // cxxdes_b200_program with device pointers; rates as {d, RN(1/d)}

@@ -35,10 +35,18 @@ struct per_requester {
 
 }  // namespace
 
+constexpr uint32_t ARCH_PHASE_SAVED = 1, ARCH_PHASE_DONE = 2;   // word 0 of a saved replication (0 = not started)
+constexpr int ARCH_SAVED_HEADER = 24;
+
 // SINGLE: exactly one requester (examples/basic_arch_sim.cpp as shipped, BASELINE config 5).
-template <bool SINGLE>
+// STATEFUL: run_until / run_for in pieces (environment.ipp:190-214): a replication that stops at the horizon with
+// tokens still scheduled is written to global memory, `[word][replication]` -- header (clock, counters, mutex flags,
+// the all_of handler, statistics), the heap, the block store, the per-requester words and both wait lists -- and the
+// next launch continues from it; finished replications keep phase DONE.  Separate instantiations, so that the plain
+// run() path carries none of it.
+template <bool SINGLE, bool STATEFUL>
 __global__ void __launch_bounds__(ARCH_THREADS)
-archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
+archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, archsim_saved st) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char *cursor = smem;
     const int K = SINGLE ? 1 : (int)prm.n_requesters;
@@ -91,12 +99,61 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
         any_all all;
         double total_latency = 0.0;
         uint64_t hits = 0, misses = 0;
-        for (int q = 0; q < K; ++q) {
-            pcs[q] = 0;
-            loop_j[q] = 0;
+        const uint32_t phase = STATEFUL && st.resume ? st.words[rep] : 0u;
+        if (STATEFUL && phase == ARCH_PHASE_DONE) {   // now_ = max(now_, t), environment.ipp:194
+            if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) out.end_time[rep] = sh.run_until;
+            continue;
         }
-
-        env.schedule(0, 0, make_tag(0));
+        if (STATEFUL && phase == ARCH_PHASE_SAVED) {
+            const uint32_t *sv = st.words + rep;
+            const size_t n = st.n_replications;
+            auto u64 = [&](int k) { return (uint64_t)sv[(size_t)k * n] | ((uint64_t)sv[(size_t)(k + 1) * n] << 32); };
+            env.n = (int)sv[1 * n];
+            env.now = (int64_t)u64(2);
+            env.n_events = u64(4);
+            env.hash = u64(6);
+            const uint32_t flags = sv[8 * n];
+            owned2 = flags & 1u; owned1 = (flags >> 1) & 1u; all.is_all = (flags >> 2) & 1u; all.armed = (flags >> 3) & 1u;
+            main_pc = flags >> 8;
+            n_blocks = (int)sv[9 * n];
+            held_slot = (int)sv[10 * n];
+            all.total = sv[11 * n];
+            all.remaining = sv[12 * n];
+            all.out_latency = 0;
+            total_latency = bits_as_double(u64(13));
+            hits = u64(15);
+            misses = u64(17);
+            wait2.n = (int)sv[19 * n];
+            wait1.n = (int)sv[20 * n];
+            int at = ARCH_SAVED_HEADER;
+            for (int k = 0; k < env.n; ++k, at += 3) {
+                hkey[k] = u64(at);
+                htag[k] = sv[(size_t)(at + 2) * n];
+            }
+            at = ARCH_SAVED_HEADER + 3 * heap_cap;
+            for (int b = 0; b < n_blocks; ++b, at += 3) {
+                blk_addr[b] = sv[(size_t)at * n];
+                blk_last[b] = (int64_t)u64(at + 1);
+            }
+            at = ARCH_SAVED_HEADER + 3 * heap_cap + 3 * CAP;
+            for (int q = 0; q < K; ++q, at += 11) {
+                t1[q] = (int64_t)u64(at);
+                stamp2[q] = (int64_t)u64(at + 2);
+                loop_j[q] = sv[(size_t)(at + 4) * n];
+                cur_addr[q] = sv[(size_t)(at + 5) * n];
+                pcs[q] = sv[(size_t)(at + 6) * n];
+                w2who[q] = sv[(size_t)(at + 7) * n];
+                w2lat[q] = (int32_t)sv[(size_t)(at + 8) * n];
+                w1who[q] = sv[(size_t)(at + 9) * n];
+                w1lat[q] = (int32_t)sv[(size_t)(at + 10) * n];
+            }
+        } else {
+            for (int q = 0; q < K; ++q) {
+                pcs[q] = 0;
+                loop_j[q] = 0;
+            }
+            env.schedule(0, 0, make_tag(0));
+        }
 
         while (env.has_event() && (sh.run_until < 0 || env.next_time() <= sh.run_until)) {
             token t = env.step_pop();
@@ -243,6 +300,55 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out) {
             if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
             env.now = env.now > sh.run_until ? env.now : sh.run_until;
         }
+        if (STATEFUL) {
+            uint32_t *sv = st.words + rep;
+            const size_t n = st.n_replications;
+            if (env.status == CXXDES_B200_REP_UNFINISHED) {
+                auto put64 = [&](int k, uint64_t v) {
+                    sv[(size_t)k * n] = (uint32_t)v;
+                    sv[(size_t)(k + 1) * n] = (uint32_t)(v >> 32);
+                };
+                sv[1 * n] = (uint32_t)env.n;
+                put64(2, (uint64_t)env.now);
+                put64(4, env.n_events);
+                put64(6, env.hash);
+                sv[8 * n] = (owned2 ? 1u : 0u) | (owned1 ? 2u : 0u) | (all.is_all ? 4u : 0u) | (all.armed ? 8u : 0u) | (main_pc << 8);
+                sv[9 * n] = (uint32_t)n_blocks;
+                sv[10 * n] = (uint32_t)held_slot;
+                sv[11 * n] = all.total;
+                sv[12 * n] = all.remaining;
+                put64(13, (uint64_t)__double_as_longlong(total_latency));
+                put64(15, hits);
+                put64(17, misses);
+                sv[19 * n] = (uint32_t)wait2.n;
+                sv[20 * n] = (uint32_t)wait1.n;
+                int at = ARCH_SAVED_HEADER;
+                for (int k = 0; k < env.n; ++k, at += 3) {
+                    put64(at, hkey[k]);
+                    sv[(size_t)(at + 2) * n] = htag[k];
+                }
+                at = ARCH_SAVED_HEADER + 3 * heap_cap;
+                for (int b = 0; b < n_blocks; ++b, at += 3) {
+                    sv[(size_t)at * n] = blk_addr[b];
+                    put64(at + 1, (uint64_t)blk_last[b]);
+                }
+                at = ARCH_SAVED_HEADER + 3 * heap_cap + 3 * CAP;
+                for (int q = 0; q < K; ++q, at += 11) {
+                    put64(at, (uint64_t)t1[q]);
+                    put64(at + 2, (uint64_t)stamp2[q]);
+                    sv[(size_t)(at + 4) * n] = loop_j[q];
+                    sv[(size_t)(at + 5) * n] = cur_addr[q];
+                    sv[(size_t)(at + 6) * n] = pcs[q];
+                    sv[(size_t)(at + 7) * n] = w2who[q];
+                    sv[(size_t)(at + 8) * n] = (uint32_t)w2lat[q];
+                    sv[(size_t)(at + 9) * n] = w1who[q];
+                    sv[(size_t)(at + 10) * n] = (uint32_t)w1lat[q];
+                }
+                sv[0] = ARCH_PHASE_SAVED;
+            } else {
+                sv[0] = ARCH_PHASE_DONE;   // finished -- or failed: the status column says so, nothing to continue
+            }
+        }
         rep_out o;
         o.end_time = env.now;
         o.n_events = env.n_events;
@@ -267,18 +373,24 @@ size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p) {
     return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * 12 + k * (8 + 8 + 4 + 4 + 4 + 16));
 }
 
+size_t archsim_saved_words(const cxxdes_b200_archsim_params &p) {
+    return ARCH_SAVED_HEADER + 3 * ((size_t)p.n_requesters + 3) + 3 * (size_t)p.l2_capacity + 11 * (size_t)p.n_requesters;
+}
+
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
-                           int sm_count, cudaStream_t stream) {
+                           int sm_count, cudaStream_t stream, const archsim_saved &st) {
     const size_t smem = archsim_smem_bytes(prm);
-    cudaError_t e = cudaFuncSetAttribute(archsim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(archsim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    auto go = [&](auto kernel, int per_sm) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out, st);
+        return cudaGetLastError();
+    };
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    if (prm.n_requesters == 1) archsim_kernel<true><<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
-    else archsim_kernel<false><<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out);
-    return cudaGetLastError();
+    if (prm.n_requesters == 1) return st.words ? go(archsim_kernel<true, true>, per_sm) : go(archsim_kernel<true, false>, per_sm);
+    return st.words ? go(archsim_kernel<false, true>, per_sm) : go(archsim_kernel<false, false>, per_sm);
 }
 
 }  // namespace cxb

@@ -151,3 +151,30 @@ def test_aloha_run_for_in_many_pieces_continues_from_saved_state(port):
     want = port.run(model, p, clock_of(g), 9, 0, n_reps, threads=os.cpu_count(), until=piece)
     golden_util.assert_columns_equal(ens.fetch(strict=False), want, what="aloha after reset")
     ens.close()
+
+
+@pytest.mark.parametrize("fields", [(1, 10, 16, 32, 4, 0, 96), (1, 10, 16, 32, 1, 0, 300), (0, 0, 4, 8, 3, 0, 60)])
+def test_archsim_run_for_in_many_pieces_continues_from_saved_state(port, fields):
+    """run_for(piece) x 12 on the memory-hierarchy kernel (one and several requesters, zero latencies): a replication
+    that stops at the horizon is saved -- heap, block store, per-requester words, both mutex wait lists -- and the
+    next launch continues from it; columns equal the oracle's run_until(k * piece) after every piece."""
+    model, cls, fname = MODELS["archsim"]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    n_reps = 400
+    clock = clock_pairs(g)
+    ends = port.run(model, p, clock_of(g), 4, 0, n_reps, threads=os.cpu_count()).end_time
+    piece = max(1, int(ends.max()) // 11)
+    ens = L.Ensemble(p, n_reps, seed=4)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for k in range(1, 13):
+        ens.run_for(piece)
+        got = ens.fetch(strict=False)
+        want = port.run(model, p, clock_of(g), 4, 0, n_reps, threads=os.cpu_count(), until=k * piece)
+        assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+        golden_util.assert_columns_equal(got, want, what=f"archsim {fields} after piece {k}")
+    ens.run()
+    want = port.run(model, p, clock_of(g), 4, 0, n_reps, threads=os.cpu_count())
+    want.end_time[:] = np.maximum(want.end_time, 12 * piece)
+    golden_util.assert_columns_equal(ens.fetch(), want, what=f"archsim {fields}: run() after the pieces")
+    ens.close()

@@ -287,10 +287,10 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
 int cxxdes_b200_run(cxxdes_b200_ensemble *e);
 
 /* environment::run_until(t) / run_for(dt) in ticks for every replication
- * (environment.ipp:190-214).  M/M/1, ALOHA, the memory hierarchy and process programs
- * keep every replication's state on the device between calls and continue from it
- * (so does a later cxxdes_b200_run); M/M/c replays from tick 0 to the new horizon,
- * with identical results. */
+ * (environment.ipp:190-214).  Every model keeps its replications' state on the device
+ * between calls and continues from it (so does a later cxxdes_b200_run); only the
+ * replications a kernel hands to its retry kernel are replayed from tick 0 to the new
+ * horizon, with identical results. */
 int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t);
 int cxxdes_b200_run_for(cxxdes_b200_ensemble *e, int64_t dt);
 

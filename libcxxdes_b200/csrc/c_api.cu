@@ -106,6 +106,8 @@ struct cxxdes_b200_ensemble {
     bool aloha_state_valid = false;
     uint32_t *arch_state = nullptr;         // ... of the memory-hierarchy model (models_archsim.cu)
     bool arch_state_valid = false;
+    uint32_t *mmc_state = nullptr;          // ... of M/M/c (models_mmc.cu)
+    bool mmc_state_valid = false;
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -322,10 +324,19 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                                   &launches, st));
             break;
         }
-        case CXXDES_B200_MODEL_MMC:
+        case CXXDES_B200_MODEL_MMC: {
+            mmc_saved st{};
+            if (mmc_keeps_state(e->params.mmc, sh) && (until >= 0 || e->mmc_state_valid)) {
+                if (!e->mmc_state)
+                    CUDA_TRY(cudaMalloc(&e->mmc_state, mmc_saved_words(e->params.mmc) * 4 * e->cfg.n_replications));
+                st.words = e->mmc_state;
+                st.n_replications = e->cfg.n_replications;
+                st.resume = e->mmc_state_valid ? 1 : 0;
+            }
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
-                                &launches));
+                                &launches, st));
             break;
+        }
         case CXXDES_B200_MODEL_ARCHSIM: {
             archsim_saved st{};
             if (until >= 0 || e->arch_state_valid) {
@@ -373,6 +384,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->prog_state_valid = e->prog_state != nullptr;
     e->aloha_state_valid = e->aloha_state != nullptr;
     e->arch_state_valid = e->arch_state != nullptr;
+    e->mmc_state_valid = e->mmc_state != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -466,9 +478,9 @@ int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
     return launch(e, -1);
 }
 
-// M/M/1 on the generate-ahead kernel keeps each replication's state between calls (128 bytes per
-// replication) and continues from it, as environment::run_until does; so do process programs on the
-// shared-memory interpreter (program_fast.cu).  The other kernels replay a
+// Every first-pass kernel keeps each replication's state between calls and continues from it, as
+// environment::run_until does (M/M/1: 128 bytes per replication; programs, ALOHA, M/M/c, arch-sim: their
+// heap and model state).  The retry kernels replay a
 // replication from tick 0 up to the new target, which yields exactly the state the reference
 // reaches by continuing (every replication is a deterministic function of its seed).
 int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {
@@ -628,6 +640,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->prog_state_valid = false;
     e->aloha_state_valid = false;
     e->arch_state_valid = false;
+    e->mmc_state_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -649,6 +662,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->prog_state);
     cudaFree(e->aloha_state);
     cudaFree(e->arch_state);
+    cudaFree(e->mmc_state);
     cudaFree(e->prog_state_queues);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);

@@ -68,9 +68,16 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
 // ---- M/M/c with balking (models_mmc.cu) ----
 int mmc_blocks(int sm_count);
 int mmc_threads();
+struct mmc_saved {            // run_until / run_for in pieces (nullptr words = the plain run() kernel)
+    uint32_t *words;          // [word][replication], word 0 = phase
+    uint64_t n_replications;
+    int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
+};
+bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh);   // the 32-bit kernel runs the model
+size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm);
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches);
+                       int *launches, const mmc_saved &st);
 
 // ---- memory hierarchy (models_archsim.cu) ----
 bool archsim_supported(const cxxdes_b200_archsim_params &p);

@@ -216,9 +216,20 @@ struct wait_list16 {
 };
 }  // namespace
 
+namespace {
+constexpr uint32_t MF_PHASE_SAVED = 1, MF_PHASE_DONE = 2, MF_PHASE_REPLAY = 3;   // word 0 of a saved replication
+constexpr int MF_SAVED_HEADER = 16;
+}  // namespace
+
+// STATEFUL: run_until / run_for in pieces (environment.ipp:190-214).  A replication that stops at the horizon with
+// tokens still scheduled is written to global memory, `[word][replication]`: header (clock, counters, semaphore),
+// heap, wait list, and the words of the customers created so far (8 bytes each -- this is the large part, 8 KB per
+// replication for 1000 customers; HBM capacity is not a constraint); the next launch restores it.  DONE / REPLAY as
+// in the other kernels.  A separate instantiation, so that the plain run() path carries none of it.
+template <bool STATEFUL>
 __global__ void __launch_bounds__(MF_THREADS, MF_BLOCKS_PER_SM)
 mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, philox_schedule keys,
-                uint32_t until) {
+                uint32_t until, mmc_saved st) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -250,18 +261,60 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     for (;;) {
         if (!active && !exhausted) {
             if (steal(sh, rep)) {
-                const uint64_t grep = sh.first_replication + rep;
-                ctr2 = (uint32_t)grep;
-                ctr3 = (uint32_t)(grep >> 32);
-                env.init(heap, MF_HEAP);
-                waiters.n = 0;
-                value = prm.servers;  // semaphore{c, c}
-                i = served = balked = 0;
-                main_pc = source_pc = 0;
-                total_wait = 0.0;
-                for (uint32_t c = 0; c < n; ++c) cust[(uint64_t)c * total_threads] = 0;
-                env.schedule(0, 0);  // environment::bind(co_main)
-                active = true;
+                const uint32_t phase = STATEFUL && st.resume ? st.words[rep] : 0u;
+                if (STATEFUL && phase == MF_PHASE_DONE) {   // now_ = max(now_, t), environment.ipp:194
+                    if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) out.end_time[rep] = sh.run_until;
+                } else if (STATEFUL && phase == MF_PHASE_REPLAY) {
+                    const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
+                    sh.retry_list[at] = (uint32_t)rep;
+                } else {
+                    const uint64_t grep = sh.first_replication + rep;
+                    ctr2 = (uint32_t)grep;
+                    ctr3 = (uint32_t)(grep >> 32);
+                    env.init(heap, MF_HEAP);
+                    if (STATEFUL && phase == MF_PHASE_SAVED) {
+                        const uint32_t *sv = st.words + rep;
+                        const size_t m = st.n_replications;
+                        env.n = (int)sv[1 * m];
+                        env.now = sv[2 * m];
+                        env.n_events = sv[3 * m];
+                        env.hash = (uint64_t)sv[4 * m] | ((uint64_t)sv[5 * m] << 32);
+                        value = sv[6 * m];
+                        i = sv[7 * m];
+                        served = sv[8 * m];
+                        balked = sv[9 * m];
+                        main_pc = sv[10 * m] & 0xFFu;
+                        source_pc = sv[10 * m] >> 8;
+                        total_wait = bits_as_double((uint64_t)sv[11 * m] | ((uint64_t)sv[12 * m] << 32));
+                        waiters.n = (int)sv[13 * m];
+                        int at = MF_SAVED_HEADER;
+                        for (int k = 0; k < env.n; ++k) heap[k * MF_THREADS] = make_uint2(sv[(size_t)(at + 2 * k) * m], sv[(size_t)(at + 2 * k + 1) * m]);
+                        at += 2 * MF_HEAP;
+                        for (int k = 0; k < waiters.n; ++k) waiters.who[k] = (uint16_t)sv[(size_t)(at + k) * m];
+                        at += MF_WAITERS;
+                        const uint32_t created = i + 1 < n ? i + 1 : n;
+                        for (uint32_t c = 0; c < n; ++c)
+                            cust[(uint64_t)c * total_threads] =
+                                c < created ? ((uint64_t)sv[(size_t)(at + 2 * c) * m] | ((uint64_t)sv[(size_t)(at + 2 * c + 1) * m] << 32)) : 0ull;
+                    } else {
+                        waiters.n = 0;
+                        value = prm.servers;  // semaphore{c, c}
+                        i = served = balked = 0;
+                        main_pc = source_pc = 0;
+                        total_wait = 0.0;
+                        for (uint32_t c = 0; c < n; ++c) cust[(uint64_t)c * total_threads] = 0;
+                        env.schedule(0, 0);  // environment::bind(co_main)
+                    }
+                    active = true;
+                    if (STATEFUL && phase == MF_PHASE_SAVED && env.next_time() > until) {
+                        // nothing of this replication falls into the piece: only its clock moves (environment.ipp:194)
+                        if (sh.run_until > (int64_t)env.now) {
+                            out.end_time[rep] = sh.run_until;
+                            st.words[2 * st.n_replications + rep] = (uint32_t)sh.run_until;
+                        }
+                        active = false;
+                    }
+                }
             } else {
                 exhausted = true;
             }
@@ -376,6 +429,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 if (env.status & (CXXDES_B200_REP_TIME_RANGE | CXXDES_B200_REP_HEAP_OVERFLOW | CXXDES_B200_REP_WAITER_OVERFLOW)) {
                     const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
                     sh.retry_list[at] = (uint32_t)rep;
+                    if (STATEFUL) st.words[rep] = MF_PHASE_REPLAY;
                 } else {
                     rep_out o;
                     int64_t end = (int64_t)env.now;
@@ -383,6 +437,44 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     if (sh.run_until >= 0) {
                         if (env.has_event()) o.status |= CXXDES_B200_REP_UNFINISHED;
                         end = end > sh.run_until ? end : sh.run_until;
+                    }
+                    if (STATEFUL) {
+                        uint32_t *sv = st.words + rep;
+                        const size_t m = st.n_replications;
+                        if (o.status == CXXDES_B200_REP_UNFINISHED) {
+                            sv[1 * m] = (uint32_t)env.n;
+                            sv[2 * m] = (uint32_t)end;      // run_until leaves now_ at the horizon
+                            sv[3 * m] = env.n_events;
+                            sv[4 * m] = (uint32_t)env.hash;
+                            sv[5 * m] = (uint32_t)(env.hash >> 32);
+                            sv[6 * m] = value;
+                            sv[7 * m] = i;
+                            sv[8 * m] = served;
+                            sv[9 * m] = balked;
+                            sv[10 * m] = main_pc | (source_pc << 8);
+                            const uint64_t tw = (uint64_t)__double_as_longlong(total_wait);
+                            sv[11 * m] = (uint32_t)tw;
+                            sv[12 * m] = (uint32_t)(tw >> 32);
+                            sv[13 * m] = (uint32_t)waiters.n;
+                            int at = MF_SAVED_HEADER;
+                            for (int k = 0; k < env.n; ++k) {
+                                const uint2 e = heap[k * MF_THREADS];
+                                sv[(size_t)(at + 2 * k) * m] = e.x;
+                                sv[(size_t)(at + 2 * k + 1) * m] = e.y;
+                            }
+                            at += 2 * MF_HEAP;
+                            for (int k = 0; k < waiters.n; ++k) sv[(size_t)(at + k) * m] = waiters.who[k];
+                            at += MF_WAITERS;
+                            const uint32_t created = i + 1 < n ? i + 1 : n;
+                            for (uint32_t c = 0; c < created; ++c) {
+                                const uint64_t wv = cust[(uint64_t)c * total_threads];
+                                sv[(size_t)(at + 2 * c) * m] = (uint32_t)wv;
+                                sv[(size_t)(at + 2 * c + 1) * m] = (uint32_t)(wv >> 32);
+                            }
+                            sv[0] = MF_PHASE_SAVED;
+                        } else {
+                            sv[0] = MF_PHASE_DONE;
+                        }
                     }
                     o.end_time = end;
                     o.n_events = env.n_events;
@@ -421,19 +513,26 @@ bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
 int mmc_blocks(int sm_count) { return sm_count * MF_BLOCKS_PER_SM; }
 int mmc_threads() { return MF_THREADS > MMC_THREADS ? MF_THREADS : MMC_THREADS; }
 
+bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh) { return mmc_fast_applies(prm, sh); }
+size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {
+    return MF_SAVED_HEADER + 2 * (size_t)MF_HEAP + MF_WAITERS + 2 * (size_t)prm.n_customers;
+}
+
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches) {
+                       int *launches, const mmc_saved &st) {
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (mmc_fast_applies(prm, sh)) {
         const size_t fsmem = mmc_fast_smem_bytes();
-        e = cudaFuncSetAttribute(mmc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        e = cudaFuncSetAttribute(mmc_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mmc_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
         if (e != cudaSuccess) return e;
         const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
         const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
-        mmc_fast_kernel<<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until);
+        if (st.words) mmc_fast_kernel<true><<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
+        else mmc_fast_kernel<false><<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

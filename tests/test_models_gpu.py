@@ -178,3 +178,30 @@ def test_archsim_run_for_in_many_pieces_continues_from_saved_state(port, fields)
     want.end_time[:] = np.maximum(want.end_time, 12 * piece)
     golden_util.assert_columns_equal(ens.fetch(), want, what=f"archsim {fields}: run() after the pieces")
     ens.close()
+
+
+@pytest.mark.parametrize("fields", [(9.0, 1.0, 0.5, 8, 0, 150), (3.0, 1.0, 0.2, 2, 0, 120)])
+def test_mmc_run_for_in_many_pieces_continues_from_saved_state(port, fields):
+    """run_for(piece) x 12 on the compact M/M/c kernel: a replication that stops at the horizon is saved -- heap,
+    semaphore and its wait list, counters, the words of the customers created so far -- and the next launch
+    continues from it; columns equal the oracle's run_until(k * piece) after every piece, run() finishes the rest."""
+    model, cls, fname = MODELS["mmc"]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    n_reps = 400
+    clock = clock_pairs(g)
+    ends = port.run(model, p, clock_of(g), 6, 0, n_reps, threads=os.cpu_count()).end_time
+    piece = max(1, int(ends.max()) // 11)
+    ens = L.Ensemble(p, n_reps, seed=6)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for k in range(1, 13):
+        ens.run_for(piece)
+        got = ens.fetch(strict=False)
+        want = port.run(model, p, clock_of(g), 6, 0, n_reps, threads=os.cpu_count(), until=k * piece)
+        assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+        golden_util.assert_columns_equal(got, want, what=f"mmc {fields} after piece {k}")
+    ens.run()
+    want = port.run(model, p, clock_of(g), 6, 0, n_reps, threads=os.cpu_count())
+    want.end_time[:] = np.maximum(want.end_time, 12 * piece)
+    golden_util.assert_columns_equal(ens.fetch(), want, what=f"mmc {fields}: run() after the pieces")
+    ens.close()

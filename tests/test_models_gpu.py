@@ -205,3 +205,40 @@ def test_mmc_run_for_in_many_pieces_continues_from_saved_state(port, fields):
     want.end_time[:] = np.maximum(want.end_time, 12 * piece)
     golden_util.assert_columns_equal(ens.fetch(), want, what=f"mmc {fields}: run() after the pieces")
     ens.close()
+
+
+@pytest.mark.parametrize("name,fields", [
+    ("aloha", (32, 50, 0.1, 3.0, 1.0, 80.0, 0)),
+    ("mmc", (9.0, 1.0, 0.5, 8, 0, 150)),
+    ("archsim", (1, 10, 16, 32, 4, 0, 96))])
+def test_sharding_is_invisible_for_every_model(built, name, fields):
+    """Replications carry their GLOBAL id in the Philox key (and in the load sweep), so splitting an ensemble into
+    shards -- one per GPU -- changes nothing: shard columns concatenate to the unsplit ensemble's, bit for bit."""
+    model, cls, fname = MODELS[name]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    whole, acc = run_gpu(p, 700, clock_pairs(g), seed=12, first=5)
+    parts = [run_gpu(p, n, clock_pairs(g), seed=12, first=5 + first) for first, n in ((0, 123), (123, 400), (523, 177))]
+    for column in ("end_time", "n_events", "trace_hash"):
+        assert np.array_equal(np.concatenate([getattr(c, column) for c, _ in parts]), getattr(whole, column)), column
+    for k in range(abi.N_F64):
+        assert np.array_equal(np.concatenate([c.f64[k] for c, _ in parts]).view(np.uint64), whole.f64[k].view(np.uint64))
+    assert sum(a.n_events for _, a in parts) == acc.n_events
+    assert sum(a.trace_hash_sum for _, a in parts) % (1 << 64) == acc.trace_hash_sum
+
+
+def test_archsim_full_size_properties(built):
+    """BASELINE config 5 at its full size on one GPU (4 Mi replications x 1024 loads, the shipped sequential driver):
+    every load is a hit or a miss, a miss costs mem1 + mem2 latency and a hit mem2's, and the event count is a
+    function of the two (a hit takes 5 events, a miss 10; 5 more frame the replication)."""
+    p = abi.ArchSimParams(1, 10, 16, 32, 1, 0, 1024)
+    got, acc = run_gpu(p, 1 << 22, ((1, L.SECONDS), (1, L.SECONDS)))
+    assert not got.status.any()
+    hits, misses = got.i64[0], got.i64[1]
+    assert ((hits + misses) == 1024).all()
+    assert (got.f64[0] == (hits * 1 + misses * 11).astype(np.float64)).all()       # sum of load latencies in ticks
+    assert (got.end_time == hits * 1 + misses * 11).all()                          # one requester: loads back to back
+    assert (got.n_events.astype(np.int64) == 5 * hits + 10 * misses + 5).all()
+    assert acc.n_events == int(got.n_events.sum())
+    # addresses are uniform over 32 with a 16-block LRU store: the hit rate is near (but below) one half
+    assert 0.40 < hits.mean() / 1024 < 0.5

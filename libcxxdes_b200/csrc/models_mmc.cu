@@ -223,8 +223,8 @@ constexpr int MF_SAVED_HEADER = 16;
 
 // STATEFUL: run_until / run_for in pieces (environment.ipp:190-214).  A replication that stops at the horizon with
 // tokens still scheduled is written to global memory, `[word][replication]`: header (clock, counters, semaphore),
-// heap, wait list, and the words of the customers created so far (8 bytes each -- this is the large part, 8 KB per
-// replication for 1000 customers; HBM capacity is not a constraint); the next launch restores it.  DONE / REPLAY as
+// heap, wait list, and the words of the customers that a scheduled token or a waiter still refers to (nobody else
+// can be touched again; at most heap + wait-list entries instead of 8 KB for all 1000); the next launch restores it.  DONE / REPLAY as
 // in the other kernels.  A separate instantiation, so that the plain run() path carries none of it.
 template <bool STATEFUL>
 __global__ void __launch_bounds__(MF_THREADS, MF_BLOCKS_PER_SM)
@@ -292,10 +292,14 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         at += 2 * MF_HEAP;
                         for (int k = 0; k < waiters.n; ++k) waiters.who[k] = (uint16_t)sv[(size_t)(at + k) * m];
                         at += MF_WAITERS;
-                        const uint32_t created = i + 1 < n ? i + 1 : n;
-                        for (uint32_t c = 0; c < n; ++c)
-                            cust[(uint64_t)c * total_threads] =
-                                c < created ? ((uint64_t)sv[(size_t)(at + 2 * c) * m] | ((uint64_t)sv[(size_t)(at + 2 * c + 1) * m] << 32)) : 0ull;
+                        // customer words: only the customers a scheduled token or a waiter still refers to were saved
+                        for (uint32_t c = 0; c < n; ++c) cust[(uint64_t)c * total_threads] = 0ull;
+                        const uint32_t n_pairs = sv[14 * m];
+                        for (uint32_t k = 0; k < n_pairs; ++k) {
+                            const uint32_t id = sv[(size_t)(at + 3 * k) * m];
+                            cust[(uint64_t)id * total_threads] =
+                                (uint64_t)sv[(size_t)(at + 3 * k + 1) * m] | ((uint64_t)sv[(size_t)(at + 3 * k + 2) * m] << 32);
+                        }
                     } else {
                         waiters.n = 0;
                         value = prm.servers;  // semaphore{c, c}
@@ -465,12 +469,22 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             at += 2 * MF_HEAP;
                             for (int k = 0; k < waiters.n; ++k) sv[(size_t)(at + k) * m] = waiters.who[k];
                             at += MF_WAITERS;
-                            const uint32_t created = i + 1 < n ? i + 1 : n;
-                            for (uint32_t c = 0; c < created; ++c) {
-                                const uint64_t wv = cust[(uint64_t)c * total_threads];
-                                sv[(size_t)(at + 2 * c) * m] = (uint32_t)wv;
-                                sv[(size_t)(at + 2 * c + 1) * m] = (uint32_t)(wv >> 32);
-                            }
+                            // Only a customer that a scheduled token or a waiter refers to can be touched again
+                            // (targets >= 2 name customer (target - 2) / 2 or its acquire_proc); the customers still
+                            // to come start from zero.  At most heap + wait-list entries, against 8 KB for them all.
+                            uint32_t n_pairs = 0;
+                            auto save_customer = [&](uint32_t target) {
+                                if (target < 2 || target == MF_NOOP) return;
+                                const uint32_t id = (target - 2) >> 1;
+                                const uint64_t wv = cust[(uint64_t)id * total_threads];
+                                sv[(size_t)(at + 3 * n_pairs) * m] = id;
+                                sv[(size_t)(at + 3 * n_pairs + 1) * m] = (uint32_t)wv;
+                                sv[(size_t)(at + 3 * n_pairs + 2) * m] = (uint32_t)(wv >> 32);
+                                ++n_pairs;
+                            };
+                            for (int k = 0; k < env.n; ++k) save_customer(heap[k * MF_THREADS].y & 0xFFFFu);
+                            for (int k = 0; k < waiters.n; ++k) save_customer(waiters.who[k]);
+                            sv[14 * m] = n_pairs;
                             sv[0] = MF_PHASE_SAVED;
                         } else {
                             sv[0] = MF_PHASE_DONE;
@@ -515,7 +529,7 @@ int mmc_threads() { return MF_THREADS > MMC_THREADS ? MF_THREADS : MMC_THREADS; 
 
 bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh) { return mmc_fast_applies(prm, sh); }
 size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {
-    return MF_SAVED_HEADER + 2 * (size_t)MF_HEAP + MF_WAITERS + 2 * (size_t)prm.n_customers;
+    return MF_SAVED_HEADER + 2 * (size_t)MF_HEAP + MF_WAITERS + 3 * (size_t)(MF_HEAP + MF_WAITERS);
 }
 
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,

@@ -99,15 +99,11 @@ struct cxxdes_b200_ensemble {
     device_program dprog{};
     program_fast_layout prog_fast{};        // shared-memory first pass (program_fast.cu), sized from the program
     int64_t *prog_queue_items = nullptr;    // its queue payloads, [queue][slot][thread]
-    uint32_t *prog_state = nullptr;         // replications between run_until / run_for pieces (program_fast.cu)
-    int64_t *prog_state_queues = nullptr;
-    bool prog_state_valid = false;          // written by the previous launch of this handle
-    uint32_t *aloha_state = nullptr;        // replications between run_until / run_for pieces (models_aloha.cu)
-    bool aloha_state_valid = false;
-    uint32_t *arch_state = nullptr;         // ... of the memory-hierarchy model (models_archsim.cu)
-    bool arch_state_valid = false;
-    uint32_t *mmc_state = nullptr;          // ... of M/M/c (models_mmc.cu)
-    bool mmc_state_valid = false;
+    // replications between run_until / run_for pieces, `[word][replication]` as the handle's model kernel defines it
+    // (program_fast.cu, models_aloha.cu, models_mmc.cu, models_archsim.cu); allocated by the first piece
+    uint32_t *saved_words = nullptr;
+    int64_t *saved_queue_items = nullptr;   // process programs: queue payloads
+    bool saved_valid = false;               // written by the previous launch of this handle
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -272,6 +268,18 @@ int plan(cxxdes_b200_ensemble *e) {
     }
 }
 
+// State kept between pieces: wanted from the first run_until / run_for on (and by a run() that follows one).
+// Returns the buffer (nullptr: the plain run() kernels) and whether it holds the previous launch's replications.
+int saved_state_for(cxxdes_b200_ensemble *e, int64_t until, size_t words_per_replication, uint32_t **words, int *resume) {
+    *words = nullptr;
+    *resume = 0;
+    if (until < 0 && !e->saved_valid) return CXXDES_B200_OK;
+    if (!e->saved_words) CUDA_TRY(cudaMalloc(&e->saved_words, words_per_replication * 4 * e->cfg.n_replications));
+    *words = e->saved_words;
+    *resume = e->saved_valid ? 1 : 0;
+    return CXXDES_B200_OK;
+}
+
 int launch(cxxdes_b200_ensemble *e, int64_t until) {
     int rc = set_device(e);
     if (rc) return rc;
@@ -313,12 +321,10 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         {
             // run_until / run_for continue where the previous piece stopped when the 32-bit kernel runs the model
             aloha_saved st{};
-            if (aloha_keeps_state(e->params.aloha, sh) && (until >= 0 || e->aloha_state_valid)) {
-                if (!e->aloha_state)
-                    CUDA_TRY(cudaMalloc(&e->aloha_state, aloha_saved_words(e->params.aloha) * 4 * e->cfg.n_replications));
-                st.words = e->aloha_state;
-                st.n_replications = e->cfg.n_replications;
-                st.resume = e->aloha_state_valid ? 1 : 0;
+            st.n_replications = e->cfg.n_replications;
+            if (aloha_keeps_state(e->params.aloha, sh)) {
+                rc = saved_state_for(e, until, aloha_saved_words(e->params.aloha), &st.words, &st.resume);
+                if (rc) return rc;
             }
             CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
                                   &launches, st));
@@ -326,12 +332,10 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         }
         case CXXDES_B200_MODEL_MMC: {
             mmc_saved st{};
-            if (mmc_keeps_state(e->params.mmc, sh) && (until >= 0 || e->mmc_state_valid)) {
-                if (!e->mmc_state)
-                    CUDA_TRY(cudaMalloc(&e->mmc_state, mmc_saved_words(e->params.mmc) * 4 * e->cfg.n_replications));
-                st.words = e->mmc_state;
-                st.n_replications = e->cfg.n_replications;
-                st.resume = e->mmc_state_valid ? 1 : 0;
+            st.n_replications = e->cfg.n_replications;
+            if (mmc_keeps_state(e->params.mmc, sh)) {
+                rc = saved_state_for(e, until, mmc_saved_words(e->params.mmc), &st.words, &st.resume);
+                if (rc) return rc;
             }
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
                                 &launches, st));
@@ -339,13 +343,9 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
         }
         case CXXDES_B200_MODEL_ARCHSIM: {
             archsim_saved st{};
-            if (until >= 0 || e->arch_state_valid) {
-                if (!e->arch_state)
-                    CUDA_TRY(cudaMalloc(&e->arch_state, archsim_saved_words(e->params.arch) * 4 * e->cfg.n_replications));
-                st.words = e->arch_state;
-                st.n_replications = e->cfg.n_replications;
-                st.resume = e->arch_state_valid ? 1 : 0;
-            }
+            st.n_replications = e->cfg.n_replications;
+            rc = saved_state_for(e, until, archsim_saved_words(e->params.arch), &st.words, &st.resume);
+            if (rc) return rc;
             CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream, st));
             launches = 1;
             break;
@@ -354,16 +354,14 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             // run_until / run_for continue where the previous piece stopped (environment.ipp:190-214): the
             // shared-memory interpreter saves what is still running at the horizon and resumes it
             program_fast_state st{};
-            if (e->prog_fast.valid && (until >= 0 || e->prog_state_valid)) {
-                if (!e->prog_state) {
-                    CUDA_TRY(cudaMalloc(&e->prog_state, program_fast_state_words(e->prog_fast) * 4 * e->cfg.n_replications));
+            st.n_replications = e->cfg.n_replications;
+            if (e->prog_fast.valid) {
+                rc = saved_state_for(e, until, program_fast_state_words(e->prog_fast), &st.words, &st.resume);
+                if (rc) return rc;
+                if (st.words && !e->saved_queue_items)
                     if (const size_t qb = program_fast_state_queue_bytes(e->prog_fast, e->cfg.n_replications))
-                        CUDA_TRY(cudaMalloc(&e->prog_state_queues, qb));
-                }
-                st.words = e->prog_state;
-                st.queue_items = e->prog_state_queues;
-                st.n_replications = e->cfg.n_replications;
-                st.resume = e->prog_state_valid ? 1 : 0;
+                        CUDA_TRY(cudaMalloc(&e->saved_queue_items, qb));
+                st.queue_items = e->saved_queue_items;
             }
             CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
                                     &launches, e->prog_fast, e->prog_queue_items, st));
@@ -381,10 +379,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->timed = true;
     e->used = true;
     e->mm1_state_valid = e->mm1_state != nullptr;
-    e->prog_state_valid = e->prog_state != nullptr;
-    e->aloha_state_valid = e->aloha_state != nullptr;
-    e->arch_state_valid = e->arch_state != nullptr;
-    e->mmc_state_valid = e->mmc_state != nullptr;
+    e->saved_valid = e->saved_words != nullptr;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -637,10 +632,7 @@ int cxxdes_b200_reset(cxxdes_b200_ensemble *e) {
     e->used = false;
     e->timed = false;
     e->mm1_state_valid = false;
-    e->prog_state_valid = false;
-    e->aloha_state_valid = false;
-    e->arch_state_valid = false;
-    e->mmc_state_valid = false;
+    e->saved_valid = false;
     return CXXDES_B200_OK;
 }
 
@@ -659,11 +651,8 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->reduce_scratch);
     cudaFree(e->program_blob);
     cudaFree(e->prog_queue_items);
-    cudaFree(e->prog_state);
-    cudaFree(e->aloha_state);
-    cudaFree(e->arch_state);
-    cudaFree(e->mmc_state);
-    cudaFree(e->prog_state_queues);
+    cudaFree(e->saved_words);
+    cudaFree(e->saved_queue_items);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);

@@ -406,6 +406,54 @@ CXXDES_SIMULATION(kat_wait_or_timeout) {
     coroutine<> co_main() { return tr.named(body(), 0); }
 };
 
+// 18 -- examples/complicated.cpp, examples 1, 2, 3 and 5: a wait with a time limit, a process awaited in the middle
+//       of a body, sequential(...) with a process among its arguments, a coroutine that awaits itself recursively
+//       (p4(4) here instead of p4(20)), and the dynamic all_of.range / any_of.range
+CXXDES_SIMULATION(kat_complicated) {
+    tracer &tr;
+    cxxdes::sync::event evt;
+    std::vector<time_integral> marks;
+    explicit kat_complicated(tracer &t) : tr{t} { bind(); }
+    coroutine<> p0() { co_await timeout(5); }
+    coroutine<> p1() {
+        co_await timeout(5);
+        co_await evt.wake();
+    }
+    coroutine<> p2() {
+        marks.push_back(now());
+        co_await (evt.wait() || timeout(8));
+        marks.push_back(now());
+        co_await tr.named(p0(), 10);
+        marks.push_back(now());
+        co_await sequential(timeout(5), timeout(5));
+        marks.push_back(now());
+    }
+    coroutine<> p3() {
+        co_await sequential(timeout(5), timeout(10), tr.named(p0(), 11));
+        marks.push_back(now());
+    }
+    coroutine<> p4(unsigned k) {
+        if (k == 0) co_return;
+        co_await timeout(5);
+        marks.push_back(now());
+        co_await tr.named(p4(k - 1), 20 + k - 1);
+    }
+    coroutine<> p5() {
+        auto to_wait = std::vector{timeout(5), timeout(10), timeout(20)};
+        co_await all_of.range(to_wait.begin(), to_wait.end());
+        marks.push_back(now());
+        co_await any_of.range(to_wait.begin(), to_wait.end());
+        marks.push_back(now());
+    }
+    coroutine<> body() {
+        co_await all_of(tr.named(p1(), 1), tr.named(p2(), 2));
+        co_await tr.named(p3(), 3);
+        co_await tr.named(p4(4), 24);
+        co_await tr.named(p5(), 5);
+    }
+    coroutine<> co_main() { return tr.named(body(), 0); }
+};
+
 // Every scenario folds its marks into i64[0] (count) and i64[1] (order-sensitive checksum) so the
 // application-level observations are compared too, not only the token trace.
 inline void fold_marks(const std::vector<time_integral> &marks, rep_result &r) {
@@ -447,6 +495,7 @@ inline rep_result run_kat(const void *params, int64_t until, tracer &tr, std::ve
         case 15: return run_kat_sim<kat_sequential>(tr, until);
         case 16: return run_kat_sim<kat_any_of_example>(tr, until);
         case 17: return run_kat_sim<kat_wait_or_timeout>(tr, until);
+        case 18: return run_kat_sim<kat_complicated>(tr, until);
         default: throw std::runtime_error("ref_oracle: unknown KAT scenario");
     }
 }

@@ -251,11 +251,44 @@ def wait_or_timeout():        # 17: examples/complicated.cpp p1 / p2 -- evt.wait
     return prog, -1
 
 
+def complicated():            # 18: examples/complicated.cpp, examples 1, 2, 3 (p4(4)) and 5
+    prog = Program()
+    evt = prog.event()
+    main = prog.process(0, root=True)
+    p1, p2, p3, p5 = prog.process(1), prog.process(2), prog.process(3), prog.process(5)
+    p0a, p0b = prog.process(10), prog.process(11)
+    for p0 in (p0a, p0b):
+        with prog.body(p0) as b:
+            b.delay(5)
+    with prog.body(p1) as b:
+        b.delay(5); b.wake(evt)
+    seq2 = prog.sequential(2, Delay(5), Delay(5))
+    with prog.body(p2) as b:
+        b.mark(1, 0); b.any_of(Wait(evt), Delay(8)); b.mark(1, 0)
+        b.await_(p0a); b.mark(1, 0)
+        b.await_(seq2); b.mark(1, 0)
+    seq3 = prog.sequential(3, Delay(5), Delay(10), p0b)
+    with prog.body(p3) as b:
+        b.await_(seq3); b.mark(1, 0)
+    p4 = [prog.process(20 + k) for k in range(5)]             # p4(k): `if (k == 0) co_return; ...; co_await p4(k - 1);`
+    with prog.body(p4[0]) as b:
+        pass
+    for k in range(1, 5):
+        with prog.body(p4[k]) as b:
+            b.delay(5); b.mark(1, 0); b.await_(p4[k - 1])
+    with prog.body(p5) as b:
+        b.all_of(Delay(5), Delay(10), Delay(20)); b.mark(1, 0)
+        b.any_of(Delay(5), Delay(10), Delay(20)); b.mark(1, 0)
+    with prog.body(main) as b:
+        b.all_of(p1, p2); b.await_(p3); b.await_(p4[4]); b.await_(p5)
+    return prog, -1
+
+
 SCENARIOS = {1: compositions, 2: latencies, 3: out_of_scope, 4: priorities, 5: clocks, 6: resource, 7: mutex,
-             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout, 15: sequential, 16: any_of_example, 17: wait_or_timeout}
+             8: semaphore, 9: queue, 10: event, 11: debug, 12: raii_trick, 13: get_environment, 14: lazy_timeout, 15: sequential, 16: any_of_example, 17: wait_or_timeout, 18: complicated}
 # end time of every scenario on the reference engine (the reference's tests / examples document the
 # observation times; scenario 1 ends at 40 because the loser of any_of(timeout(10), timeout(20)) still fires)
-EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30, 15: 20, 16: 1000, 17: 22}
+EXPECTED_END = {1: 40, 2: 19, 3: 10, 4: 4, 5: 20, 6: 12, 7: 25, 8: 10, 9: 12, 10: 602, 11: 10, 12: 31, 13: 8, 14: 30, 15: 20, 16: 1000, 17: 22, 18: 100}
 
 
 def mm1_program(lam, mu, n_packets):

@@ -131,3 +131,13 @@ def test_cpp_multi_gpu_example_allreduces_over_nccl(built, tmp_path):
     field = lambda s, key: s.split(key)[1].split(",")[0].strip()
     assert field(outs[0], "digest sum") == field(outs[1], "digest sum")
     assert field(outs[0], "events") == field(outs[1], "events")
+
+
+@pytest.mark.gpu
+def test_cpp_loss_system_example_matches_theory(built, tmp_path):
+    """examples/mm1k_loss.cpp: an `if / else` between awaits and a load sweep inside one ensemble, from the C++
+    builder; the dropped fraction follows the M/M/1/K blocking probability at every load point (exit code 0)."""
+    exe = build_example(tmp_path, "mm1k_loss")
+    r = subprocess.run([str(exe), "20000", "4000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert len(r.stdout.strip().splitlines()) == 6

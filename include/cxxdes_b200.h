@@ -281,6 +281,11 @@ int cxxdes_b200_device_count(int *count);
  * (environment.ipp:43-70).  Copies `params` to the device. */
 int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out);
 
+/* Validate a process program without a GPU: CXXDES_B200_OK, or CXXDES_B200_ERR_INVALID with the reason in
+ * cxxdes_b200_last_error() (operand ranges, composition structure, forward-only IF / JUMP targets, the last
+ * operation a RETURN, ...).  cxxdes_b200_create applies the same check. */
+int cxxdes_b200_check_program(const cxxdes_b200_program *program);
+
 /* simulation::run() for every replication: bind co_main once, then
  * `while (step());` (core/simulation.hpp:51-54,76-81; environment.ipp:117-146,179-182).
  * Asynchronous on the handle's stream. */

@@ -298,6 +298,12 @@ public:
         return p;
     }
 
+    // Validate against the interpreters' rules without a GPU; throws std::runtime_error with the reason.
+    void check() const {
+        const cxxdes_b200_program p = c_struct();
+        detail::check(cxxdes_b200_check_program(&p));
+    }
+
     const std::vector<cxxdes_b200_op> &ops() const { return ops_; }
     const std::vector<cxxdes_b200_process> &processes() const { return procs_; }
 

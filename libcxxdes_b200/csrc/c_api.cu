@@ -468,6 +468,17 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
     return CXXDES_B200_OK;
 }
 
+int cxxdes_b200_check_program(const cxxdes_b200_program *program) {
+    if (!program) return fail(CXXDES_B200_ERR_INVALID, "program is NULL");
+    if (const char *why = program_check(*program)) return fail(CXXDES_B200_ERR_INVALID, "%s", why);
+    if ((program->n_queues && !program->queue_max) || (program->n_sems && (!program->sem_init || !program->sem_max)) ||
+        (program->n_rates && !program->rates))
+        return fail(CXXDES_B200_ERR_INVALID, "program: a counted array is NULL");
+    for (uint32_t k = 0; k < program->n_rates * (program->sweep_steps ? program->sweep_steps : 1); ++k)
+        if (!(program->rates[k] > 0.0)) return fail(CXXDES_B200_ERR_INVALID, "program: rates must be > 0");
+    return CXXDES_B200_OK;
+}
+
 int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
     if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
     return launch(e, -1);

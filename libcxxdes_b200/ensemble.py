@@ -48,6 +48,7 @@ def load_library():
     lib.cxxdes_b200_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.cxxdes_b200_version.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.cxxdes_b200_create.argtypes = [C.POINTER(abi.Config), C.POINTER(H)]
+    lib.cxxdes_b200_check_program.argtypes = [C.POINTER(abi.ProgramParams)]
     lib.cxxdes_b200_run.argtypes = [H]
     lib.cxxdes_b200_run_until.argtypes = [H, C.c_int64]
     lib.cxxdes_b200_run_for.argtypes = [H, C.c_int64]
@@ -60,7 +61,7 @@ def load_library():
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
-    for name in ("device_count", "version", "create", "run", "run_until", "run_for", "sync", "fetch",
+    for name in ("device_count", "version", "create", "check_program", "run", "run_until", "run_for", "sync", "fetch",
                  "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
@@ -68,7 +69,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_run", "cxxdes_b200_run_until",
+    "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_check_program", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
     "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",

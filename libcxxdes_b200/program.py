@@ -309,6 +309,16 @@ class Program:
         self._rates.append([float(v) for v in value] if hasattr(value, "__len__") else float(value))
         return len(self._rates) - 1
 
+    def check(self):
+        """Validate against the interpreters' rules without a GPU (cxxdes_b200_check_program); raises CxxdesError."""
+        from . import ensemble
+        lib = ensemble.load_library()
+        pp = self.to_params()
+        rc = lib.cxxdes_b200_check_program(C.byref(pp))
+        if rc != abi.OK:
+            raise ensemble.CxxdesError(rc, lib.cxxdes_b200_last_error().decode())
+        return self
+
     def to_params(self):
         for i, p in enumerate(self._procs):
             if p["entry"] is None:

@@ -1,6 +1,7 @@
 """Process programs (generic lowering): the reference's own known-answer scenarios
 (tests/controlflow.test.cpp, tests/process.test.cpp, examples/{clocks,resource,mutex,semaphore,queue,event}.cpp)
 run natively on the reference engine == as process programs on the CPU interpreter == on the CUDA interpreter."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -410,3 +411,54 @@ def test_gpu_program_deep_queues_on_request(port):
     part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count(), until=400000)
     golden_util.assert_columns_equal(ens.fetch(strict=False), part, what="deep queues, two pieces")
     ens.close()
+
+
+# ------------------------------------------------------------------ validation without a GPU
+def _raw(ops, procs=((0, 0),), roots=(0,), **counts):
+    """A hand-made program: ops as (code, a, b, imm), procs as (entry, ordinal)."""
+    ops_arr = (abi.Op * len(ops))(*[abi.Op(*o) for o in ops])
+    procs_arr = (abi.Process * len(procs))(*[abi.Process(e, o, abi.INHERIT64, 0, 0, abi.INHERIT64) for e, o in procs])
+    roots_arr = (C.c_uint32 * len(roots))(*roots)
+    one = (C.c_uint64 * 1)(0)
+    rates = (C.c_double * 1)(1.0)
+    pp = abi.ProgramParams(ops_arr, procs_arr, roots_arr, one, one, one, rates, len(ops), len(procs), len(roots),
+                           counts.get("n_queues", 0), counts.get("n_sems", 0), counts.get("n_mutexes", 0),
+                           counts.get("n_events", 0), counts.get("n_rates", 0), 0, 0)
+    pp._keep = (ops_arr, procs_arr, roots_arr, one, rates)
+    return pp
+
+
+def test_check_program_without_a_gpu(cuda_lib):
+    """cxxdes_b200_check_program: what cxxdes_b200_create would reject, with the reason, no device needed."""
+    import ctypes
+    R, DELAY, ALL, CH_DELAY, CH_ALL, IF, JUMP, QPUT = (abi.OP_RETURN, abi.OP_DELAY, abi.OP_ALL_OF, abi.OP_CHILD_DELAY,
+                                                      abi.OP_CHILD_ALL_OF, abi.OP_IF, abi.OP_JUMP, abi.OP_Q_PUT)
+    ok = [
+        [(DELAY, 0, abi.INHERIT32, 5), (R, 0, 0, 0)],
+        [(ALL, 2, abi.INHERIT32, 0), (CH_ALL, 2, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (CH_DELAY, 0, abi.INHERIT32, 2),
+         (CH_DELAY, 0, abi.INHERIT32, 3), (R, 0, 0, 0)],
+        [(IF, abi.SRC_NOW << 8 | abi.CMP["<"] << 12, 2, 10), (DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
+    ]
+    bad = {
+        "last op must be RETURN": [(DELAY, 0, abi.INHERIT32, 5)],
+        "bad composition": [(ALL, 40, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
+        "CHILD_": [(ALL, 3, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
+        "must lie ahead": [(JUMP, 0, 0, 0), (R, 0, 0, 0)],
+        "IF operand": [(IF, 7 << 8, 1, 0), (R, 0, 0, 0)],
+        "queue operand": [(QPUT, 0, 0, 0), (R, 0, 0, 0)],
+        "unknown op": [(99, 0, 0, 0), (R, 0, 0, 0)],
+    }
+    for ops in ok:
+        assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(_raw(ops))) == abi.OK, cuda_lib.cxxdes_b200_last_error()
+    for reason, ops in bad.items():
+        assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(_raw(ops))) == abi.ERR_INVALID
+        assert reason.encode() in cuda_lib.cxxdes_b200_last_error(), (reason, cuda_lib.cxxdes_b200_last_error())
+    assert cuda_lib.cxxdes_b200_check_program(None) == abi.ERR_INVALID
+    for k in sorted(K.SCENARIOS):                       # everything the builders emit passes, and Program.check() says so
+        K.SCENARIOS[k]()[0].check()
+    with pytest.raises(L.CxxdesError):
+        prog = L.Program()
+        p = prog.process(0, root=True)
+        with prog.body(p) as b:
+            b.await_(9)
+        prog.check()

@@ -331,6 +331,13 @@ int cxxdes_b200_reduce_allgpus(cxxdes_b200_ensemble *e, void *nccl_comm, cxxdes_
 int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms);
 int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
 
+/* Diagnostics of the most recent run / run_until / run_for launch: how many replications left the first-pass
+ * kernel's compact representation and were redone (results are identical either way; this only tells where the
+ * time went).  counts[0] = redone by the model's second pass (M/M/1: queue outgrew the shared-memory window ->
+ * two-level ring), counts[1] = of those, taken by the helper grid that runs next to the first pass,
+ * counts[2] = redone by the full-size 64-bit kernel, counts[3] = 0 (reserved).  Implies a sync. */
+int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]);
+
 /* environment::reset() (environment.ipp:154-176) + rebind: replications start over. */
 int cxxdes_b200_reset(cxxdes_b200_ensemble *e);
 

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -82,7 +83,8 @@ struct cxxdes_b200_ensemble {
     // device memory
     unsigned char *col_block = nullptr;  // all result columns, one allocation
     device_columns cols{};
-    unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor, [3] list A count, [4] list A cursor
+    unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor, [3] list A count, [4] list A cursor,
+                                             // [5] M/M/1 first pass done (flag), [6] list A entries taken by the overlapped helper
     uint32_t *retry_list = nullptr;
     log_entry *log_table = nullptr;
     int64_t *ring = nullptr;
@@ -104,6 +106,10 @@ struct cxxdes_b200_ensemble {
     uint32_t *saved_words = nullptr;
     int64_t *saved_queue_items = nullptr;   // process programs: queue payloads
     bool saved_valid = false;               // written by the previous launch of this handle
+
+    // M/M/1: the second pass runs next to the first one on a stream of the handle's own (mm1_fused.cu)
+    cudaStream_t helper_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     bool use_fused = false;
     mm1_fused_plan mm1_plan{};
@@ -299,6 +305,10 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     sh.log_table = e->log_table;
     CUDA_TRY(cudaEventRecord(e->ev_begin, e->stream));
     int launches = 0;
+    // whether THIS launch was given the state buffers (and so leaves them describing its replications): a run() on
+    // the plain kernels after reset(), or a piece that ran on a kernel without saved state, must not make a later
+    // call resume from records an earlier launch wrote
+    bool wrote_mm1_state = false, wrote_saved = false;
     switch (e->cfg.model) {
         case CXXDES_B200_MODEL_MM1:
             if (e->use_fused) {
@@ -309,8 +319,11 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                     CUDA_TRY(cudaMalloc(&e->mm1_state, mm1_ahead_state_bytes(e->cfg.n_replications)));
                 }
                 const int resume = resumable && e->mm1_state && e->mm1_state_valid;
+                wrote_mm1_state = resumable && e->mm1_state != nullptr;
+                const mm1_overlap overlap{e->helper_stream, e->ev_fork, e->ev_join, (unsigned int *)(e->counters + 5)};
                 CUDA_TRY(launch_mm1_fused(e->params.mm1, sh, e->cols, e->mm1_plan, e->ring, e->counters + 2,
-                                          e->ahead_gring, resumable ? e->mm1_state : nullptr, resume, e->stream, &launches, (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0));
+                                          e->ahead_gring, resumable ? e->mm1_state : nullptr, resume, e->stream, &launches,
+                                          (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0, overlap));
             } else {
                 CUDA_TRY(launch_mm1_engine(e->params.mm1, sh, e->cols, e->ring, e->engine_ring, e->engine_blocks,
                                            e->engine_threads, e->stream));
@@ -326,6 +339,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                 rc = saved_state_for(e, until, aloha_saved_words(e->params.aloha), &st.words, &st.resume);
                 if (rc) return rc;
             }
+            wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
                                   &launches, st));
             break;
@@ -337,6 +351,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                 rc = saved_state_for(e, until, mmc_saved_words(e->params.mmc), &st.words, &st.resume);
                 if (rc) return rc;
             }
+            wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
                                 &launches, st));
             break;
@@ -346,6 +361,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             st.n_replications = e->cfg.n_replications;
             rc = saved_state_for(e, until, archsim_saved_words(e->params.arch), &st.words, &st.resume);
             if (rc) return rc;
+            wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream, st));
             launches = 1;
             break;
@@ -363,6 +379,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
                         CUDA_TRY(cudaMalloc(&e->saved_queue_items, qb));
                 st.queue_items = e->saved_queue_items;
             }
+            wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
                                     &launches, e->prog_fast, e->prog_queue_items, st));
             break;
@@ -378,8 +395,8 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
     e->launches += launches;
     e->timed = true;
     e->used = true;
-    e->mm1_state_valid = e->mm1_state != nullptr;
-    e->saved_valid = e->saved_words != nullptr;
+    e->mm1_state_valid = wrote_mm1_state;
+    e->saved_valid = wrote_saved;
     e->horizon = until < 0 ? INT64_MAX : until;
     return CXXDES_B200_OK;
 }
@@ -458,6 +475,13 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
         if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev_end);
         if (ce == cudaSuccess && e->use_fused) ce = configure_mm1_fused(e->mm1_plan);
         if (ce == cudaSuccess && e->use_fused) ce = configure_mm1_ahead(e->mm1_plan);
+        // (CXXDES_B200_MM1_NO_OVERLAP=1: second pass after the first one, as before -- for A/B measurements)
+        const char *no_overlap = getenv("CXXDES_B200_MM1_NO_OVERLAP");
+        if (ce == cudaSuccess && e->use_fused && !(cfg->flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) && !(no_overlap && no_overlap[0] == '1')) {
+            ce = cudaStreamCreateWithFlags(&e->helper_stream, cudaStreamNonBlocking);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
+        }
         if (ce != cudaSuccess) rc = fail(CXXDES_B200_ERR_CUDA, "setup: %s", cudaGetErrorString(ce));
     }
     if (rc != CXXDES_B200_OK) {
@@ -492,7 +516,15 @@ int cxxdes_b200_run(cxxdes_b200_ensemble *e) {
 int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {
     if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
     if (t < 0) return fail(CXXDES_B200_ERR_INVALID, "run_until: t must be >= 0");
-    if (e->horizon == INT64_MAX) return CXXDES_B200_OK;  // already exhausted: nothing left to run
+    if (e->horizon == INT64_MAX) {
+        // already exhausted: nothing left to dispatch, but the clock still follows, now_ = max(now_, t)
+        // (environment.ipp:194)
+        int rc = set_device(e);
+        if (rc) return rc;
+        CUDA_TRY(launch_clock_floor(e->cols.end_time, e->cfg.n_replications, t, e->sm_count, e->stream));
+        ++e->launches;
+        return CXXDES_B200_OK;
+    }
     if (e->horizon > t) t = e->horizon;                  // now_ = max(now_, t), environment.ipp:194
     return launch(e, t);
 }
@@ -501,7 +533,15 @@ int cxxdes_b200_run_for(cxxdes_b200_ensemble *e, int64_t dt) {
     if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
     if (dt < 0) return fail(CXXDES_B200_ERR_INVALID, "run_for: dt must be >= 0");
     int64_t base = e->horizon < 0 ? 0 : e->horizon;
-    if (base == INT64_MAX) return CXXDES_B200_OK;
+    if (base == INT64_MAX) {
+        // exhausted: run_until(now() + dt) with each replication's own now() (environment.ipp:205-209)
+        int rc = set_device(e);
+        if (rc) return rc;
+        CUDA_TRY(launch_clock_add(e->cols.end_time, e->cfg.n_replications, dt, e->sm_count, e->stream));
+        ++e->launches;
+        return CXXDES_B200_OK;
+    }
+    if (dt > INT64_MAX - 1 - base) return fail(CXXDES_B200_ERR_INVALID, "run_for: now() + dt overflows the 64-bit clock");
     return cxxdes_b200_run_until(e, base + dt);
 }
 
@@ -631,6 +671,21 @@ int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms) {
     return CXXDES_B200_OK;
 }
 
+int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]) {
+    if (!e || !counts) return fail(CXXDES_B200_ERR_INVALID, "handle/counts is NULL");
+    if (!e->used) return fail(CXXDES_B200_ERR_STATE, "pass_counts before run");
+    int rc = set_device(e);
+    if (rc) return rc;
+    unsigned long long c[8];
+    CUDA_TRY(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    counts[0] = c[3];
+    counts[1] = c[6] & 0xFFFFFFFFull;
+    counts[2] = c[1];
+    counts[3] = 0;
+    return CXXDES_B200_OK;
+}
+
 int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches) {
     if (!e || !launches) return fail(CXXDES_B200_ERR_INVALID, "handle/launches is NULL");
     *launches = e->launches;
@@ -666,6 +721,9 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->saved_queue_items);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->helper_stream) { cudaStreamSynchronize(e->helper_stream); cudaStreamDestroy(e->helper_stream); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return CXXDES_B200_OK;

@@ -31,6 +31,10 @@ struct shard {
     uint32_t *retry_a_list;
 };
 
+// A retry-list entry that has not been written (yet): lists read while they are still being appended to
+// (mm1_ahead.cu, POLL) are filled with this value before the launch.  Local replication ids are < 2^32 - 1.
+constexpr uint32_t LIST_UNSET = 0xFFFFFFFFu;
+
 struct rep_out {
     int64_t end_time;
     uint64_t n_events;

@@ -35,10 +35,17 @@ struct mm1_fused_plan {
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                               size_t smem_per_block_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep);
+// What the second pass needs to run NEXT TO the first one instead of after it (helper_stream == nullptr: after it).
+struct mm1_overlap {
+    cudaStream_t helper_stream;     // a stream of the handle's own
+    cudaEvent_t fork, join;         // main stream -> helper stream before the first pass, and back after the helper
+    unsigned int *done_flag;        // device word: 0 while the first pass runs, non-zero after it; done_flag[2]
+                                    // counts the replications the helper took
+};
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
                              void *ahead_gring, uint32_t *ahead_state, int resume, cudaStream_t stream, int *launches,
-                             bool lockstep);
+                             bool lockstep, const mm1_overlap &overlap);
 cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
 // ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
@@ -51,6 +58,11 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
                              const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
                              const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
                              uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream);
+
+cudaError_t launch_mm1_ahead_helper(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                                    const mm1_fused_plan &plan, void *gring, const uint32_t *list, uint32_t list_capacity,
+                                    unsigned long long *list_cursor, unsigned int *done_flag, uint32_t *fail_list,
+                                    unsigned long long *fail_count, cudaStream_t stream);
 
 // ---- ALOHA (models_aloha.cu) ----
 size_t aloha_smem_bytes(uint32_t num_stations);
@@ -147,5 +159,6 @@ cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_ac
 
 
 cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream);
+cudaError_t launch_clock_add(int64_t *end_time, uint64_t n, int64_t dt, int sm_count, cudaStream_t stream);
 
 }  // namespace cxb

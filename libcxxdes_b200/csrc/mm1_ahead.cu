@@ -114,12 +114,18 @@ struct lane_ring {
 // rho = 0.5, but a lone replication on the 64-bit fallback kernel takes 13 ms, on this one 2 ms);
 // the fallback kernel over what is left (clock beyond 2^30 ticks, queue beyond both levels).
 // A replication this kernel cannot finish goes to `fail_list`.
-template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL, bool STATE>
+// POLL (the helper of the first pass, launch_mm1_ahead_helper): the kernel runs WHILE the first pass is still
+// appending to `list`.  A lane reserves the next list index and waits for that entry to appear (entries start as
+// LIST_UNSET) or for `*done_flag` to become non-zero -- set by a memset that follows the first pass in its stream --
+// after which an entry that is still unset will never be written.  So the one-in-two-million replication whose
+// queue outgrows the window is redone next to the first pass instead of after it.  (done_flag[2] counts what the
+// helper took: done_flag is the low word of counters[5], done_flag + 2 the low word of counters[6].)
+template <int THREADS, int MIN_BLOCKS, int RING_SLOTS, int EVENT_SLOTS, int MODE, bool SPILL, bool STATE, bool POLL = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_columns out, uint2 *gring,
                  uint32_t gring_slots, uint32_t *state, int resume, const uint32_t *list,
                  const unsigned long long *list_count, unsigned long long *list_cursor, uint32_t *fail_list,
-                 unsigned long long *fail_count) {
+                 unsigned long long *fail_count, unsigned int *done_flag = nullptr, uint32_t list_capacity = 0) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     stage_log_table(table, sh.log_table);
@@ -134,6 +140,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
     L.idle();
     bool active = false, exhausted = false;
     uint64_t rep = 0;
+    [[maybe_unused]] unsigned long long poll_idx = ~0ULL;   // POLL: the list index this lane has reserved
 
     for (;;) {
         if (!active && !exhausted) {
@@ -141,7 +148,30 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
             // when a replication stops at the horizon and read back by the next launch (`resume`)
             for (int tries = 0; tries < 8 && !active && !exhausted; ++tries) {
                 bool got;
-                if (list) {
+                if constexpr (POLL) {
+                    const volatile uint32_t *vlist = list;
+                    const bool finished = *(volatile unsigned int *)done_flag != 0;   // read BEFORE the entry
+                    if (finished) __threadfence();
+                    if (poll_idx == ~0ULL) {
+                        if (finished) {   // the rest of the list belongs to the pass that follows
+                            exhausted = true;
+                            break;
+                        }
+                        poll_idx = atomicAdd(list_cursor, 1ULL);
+                    }
+                    const uint32_t v = poll_idx < list_capacity ? vlist[poll_idx] : LIST_UNSET;
+                    got = v != LIST_UNSET;
+                    if (got) {
+                        rep = v;
+                        poll_idx = ~0ULL;
+                        atomicAdd(done_flag + 2, 1u);   // diagnostics (cxxdes_b200_pass_counts): taken by the helper
+                    } else if (finished) {
+                        exhausted = true;   // the first pass ended without writing this entry
+                        break;
+                    } else {
+                        break;              // not yet: look again on the next turn of the loop
+                    }
+                } else if (list) {
                     const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
                     got = idx < *list_count;
                     if (got) rep = list[idx];
@@ -175,7 +205,18 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        // (a claimed replication can leave the lane inactive -- finished in an earlier piece, handed to the
+        // retry list, nothing due in this piece -- so the warp only leaves when every lane has seen the end of the work list)
+        if constexpr (STATE || POLL) {
+            if (!__any_sync(0xFFFFFFFFu, active)) {
+                if (__all_sync(0xFFFFFFFFu, exhausted)) break;
+                if constexpr (POLL) __nanosleep(4000);   // nothing to redo yet: leave the issue slots to the first pass
+                continue;
+            }
+        } else {
+            // (without saved state every claimed replication makes its lane active: no lane is idle before the list ends)
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+        }
 
         // ---- 1. start-up / wind-down events (rare) ----
         if (active && !L.is_fast()) L.template generic_step<MODE>(c, ring);
@@ -249,6 +290,10 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 
 namespace {
 constexpr int AH_EVENT_SLOTS = 4;
+// Helper of the first pass: a few one-warp blocks that fit next to its three 256-thread blocks on an SM (registers:
+// 65536 - 3 * 256 * 80 = 4096 = 32 threads x 128, which is what __launch_bounds__(32, 16) allows; shared memory:
+// 2 KB table + 8 KB ring against ~29 KB left).
+constexpr int AH_HELPER_THREADS = 32, AH_HELPER_MIN_BLOCKS = 16, AH_HELPER_BLOCKS = 8;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
 
 // Launch geometry: threads per block, resident blocks per SM, window slots per replication.
@@ -354,6 +399,17 @@ cudaError_t configure_geometry() {
 #undef CXB_CONFIGURE
     return e;
 }
+using helper_geometry = geometry<AH_HELPER_THREADS, AH_HELPER_MIN_BLOCKS, 32>;
+template <int MODE>
+void launch_helper_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                       const mm1_fused_plan &plan, const pass_args &a, unsigned int *done_flag, uint32_t list_capacity,
+                       cudaStream_t stream) {
+    using G = helper_geometry;
+    mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, true, false, true>
+        <<<AH_HELPER_BLOCKS, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
+                                                            a.list_count, a.list_cursor, a.fail_list, a.fail_count, done_flag,
+                                                            list_capacity);
+}
 template <typename G, int MODE, bool SPILL>
 void launch_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                 const mm1_fused_plan &plan, const pass_args &a, cudaStream_t stream) {
@@ -392,11 +448,8 @@ cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
 // One pass of the generate-ahead kernel.  spill: with the two-level ring.  list == nullptr: the whole
 // shard (work counter); else the replications on `list`.  Replications it cannot finish are appended
 // to fail_list.
-cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
-                             const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
-                             const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
-                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream) {
-    mm1::constants c;
+namespace {
+int constants_and_mode(mm1::constants &c, const cxxdes_b200_mm1_params &prm, const shard &sh, const mm1_fused_plan &plan) {
     c.lambda = make_divisor(prm.lambda);  // IEEE 1/d on the host: same bits as on the device
     c.mu = make_divisor(prm.mu);
     c.keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
@@ -411,8 +464,41 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     c.until64 = sh.run_until;
     // (with a wide clock a horizon beyond 2^30 ticks is still a horizon: the lanes watch until64 - epoch)
     const bool has_until = plan.ah_wide ? sh.run_until >= 0 : c.until != mm1::EMPTY;
-    const int mode = (has_until ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0) |
-                     (plan.ah_wide ? mm1::MODE_WIDE : 0);
+    return (has_until ? mm1::MODE_UNTIL : 0) | (sh.clk.tick_mult != 1 ? mm1::MODE_TICK_MULT : 0) |
+           (plan.ah_wide ? mm1::MODE_WIDE : 0);
+}
+}  // namespace
+
+// The helper of a window-only first pass (see POLL above): AH_HELPER_BLOCKS one-warp blocks with the two-level ring
+// that redo the replications on `list` while the first pass is still producing it.  `done_flag` must become non-zero
+// (in stream order) after the first pass; `list` must have been filled with LIST_UNSET.
+cudaError_t launch_mm1_ahead_helper(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                                    const mm1_fused_plan &plan, void *gring, const uint32_t *list, uint32_t list_capacity,
+                                    unsigned long long *list_cursor, unsigned int *done_flag, uint32_t *fail_list,
+                                    unsigned long long *fail_count, cudaStream_t stream) {
+    mm1::constants c;
+    const int mode = constants_and_mode(c, prm, sh, plan);
+    // the helper's two-level ring uses its own (small) thread count as the column count of the global level
+    pass_args a{(uint2 *)gring, nullptr, 0, list, nullptr, list_cursor, fail_list, fail_count};
+    switch (mode) {
+        case 0: launch_helper_one<0>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 1: launch_helper_one<1>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 2: launch_helper_one<2>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 3: launch_helper_one<3>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 4: launch_helper_one<4>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 5: launch_helper_one<5>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        case 6: launch_helper_one<6>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+        default: launch_helper_one<7>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
+                             const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
+                             const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
+                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream) {
+    mm1::constants c;
+    const int mode = constants_and_mode(c, prm, sh, plan);
     pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
     if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
     else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);

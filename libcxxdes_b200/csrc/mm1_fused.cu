@@ -415,7 +415,7 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan) {
 cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, int64_t *fb_ring, unsigned long long *fb_counter,
                              void *ahead_gring, uint32_t *ahead_state, int resume, cudaStream_t stream, int *launches,
-                             bool lockstep) {
+                             bool lockstep, const mm1_overlap &overlap) {
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     mm1_rates rates;
     rates.lambda = make_divisor(prm.lambda);
@@ -437,11 +437,35 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
             ++*launches;
         } else {
             // window-only first pass; what outgrows the window is redone with the two-level ring
-            // (a lone replication takes ~2 ms there, 13 ms on the fallback kernel)
+            // (a lone replication takes ~4.5 ms there, 13 ms on the fallback kernel) -- by a helper grid that runs
+            // NEXT TO the first pass and polls its list, so that the one-in-two-million replication is done when the
+            // first pass ends instead of holding the step (and, at N GPUs, every other rank) for those 4.5 ms.
+            // Host order matters: first pass, then the memset that raises the flag behind it, then the helper --
+            // if something serialises the launches (a profiler, CUDA_LAUNCH_BLOCKING) the helper finds the flag
+            // set and the list complete instead of waiting for a kernel that has not been issued.
+            if (overlap.helper_stream) {
+                e = cudaMemsetAsync(sh.retry_a_list, 0xFF, sizeof(uint32_t) * sh.n_replications, stream);
+                if (e == cudaSuccess) e = cudaMemsetAsync(overlap.done_flag, 0, sizeof(unsigned int), stream);
+                if (e == cudaSuccess) e = cudaEventRecord(overlap.fork, stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(overlap.helper_stream, overlap.fork, 0);
+                if (e != cudaSuccess) return e;
+            }
             e = launch_mm1_ahead(prm, sh, out, plan, false, ahead_gring, ahead_state, resume, nullptr, nullptr, nullptr,
                                  sh.retry_a_list, sh.retry_a_count, stream);
             ++*launches;
             if (e != cudaSuccess) return e;
+            if (overlap.helper_stream) {
+                e = cudaMemsetAsync(overlap.done_flag, 0xFF, sizeof(unsigned int), stream);
+                if (e == cudaSuccess)
+                    e = launch_mm1_ahead_helper(prm, sh, out, plan, ahead_gring, sh.retry_a_list, (uint32_t)sh.n_replications,
+                                                sh.retry_a_cursor, overlap.done_flag, sh.retry_list, sh.retry_count,
+                                                overlap.helper_stream);
+                ++*launches;
+                if (e == cudaSuccess) e = cudaEventRecord(overlap.join, overlap.helper_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, overlap.join, 0);
+                if (e != cudaSuccess) return e;
+            }
+            // what the helper left (a list longer than its few warps could take during the first pass)
             e = launch_mm1_ahead(prm, sh, out, plan, true, ahead_gring, nullptr, 0, sh.retry_a_list, sh.retry_a_count,
                                  sh.retry_a_cursor, sh.retry_list, sh.retry_count, stream);
             ++*launches;

@@ -266,7 +266,12 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                 exhausted = true;
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        // (a claimed replication can leave the lane inactive -- finished in an earlier piece, handed to the
+        // retry list, nothing due in this piece -- so the warp only leaves when every lane has seen the end of the work list)
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (__all_sync(0xFFFFFFFFu, exhausted)) break;
+            continue;
+        }
 
         if (active) {
             const token32 t = env.step_pop();  // environment::step, environment.ipp:117-126

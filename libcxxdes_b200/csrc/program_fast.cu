@@ -419,6 +419,10 @@ struct machine {
             }
             case CXXDES_B200_OP_END_LOOP: {
                 const uint32_t depth = (w0 >> P_DEPTH_SHIFT) & 3u;
+                if (depth == 0) {   // (program_check pairs the loops; never touch the word below the counters)
+                    env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                    return false;
+                }
                 const int lw = b + L.o_loop + (int)depth - 1;
                 const uint32_t left = w(lw) - 1;
                 w(lw) = left;

@@ -6,6 +6,7 @@
 //  on top of the same engine the model kernels use (device/engine.cuh: libstdc++-exact
 // heap, clock, trace digest).  Thread per replication; the event heap is in shared memory, the
 // (small) process table, sync objects and handler pool are per-thread local arrays.
+#include <new>
 #include <cstdlib>
 
 #include "device/models_common.cuh"
@@ -427,6 +428,10 @@ struct interp {
                     }
                     break;
                 case CXXDES_B200_OP_END_LOOP:
+                    if (self.loop_depth == 0) {   // (program_check pairs the loops; never index below the counters)
+                        env.status |= CXXDES_B200_REP_BAD_PROGRAM;
+                        return;
+                    }
                     if (--self.loop[self.loop_depth - 1] > 0) {
                         self.pc = (uint32_t)op.b;
                     } else {
@@ -664,6 +669,8 @@ const char *program_check(const cxxdes_b200_program &p) {
                 break;
             case CXXDES_B200_OP_LOOP: case CXXDES_B200_OP_END_LOOP:
                 if (op.b < 0 || (uint32_t)op.b >= p.n_ops) return "program: loop target out of range";
+                if (op.code == CXXDES_B200_OP_LOOP && (op.imm < 0 || op.imm > 0xFFFFFFFFLL))
+                    return "program: LOOP count must be in [0, 2^32)";
                 break;
             case CXXDES_B200_OP_STAT_SECONDS: case CXXDES_B200_OP_STAT_TICKS:
                 if (op.a >= CXXDES_B200_N_F64) return "program: statistic index out of range";
@@ -685,6 +692,43 @@ const char *program_check(const cxxdes_b200_program &p) {
             default:
                 if (op.code > CXXDES_B200_OP_CHILD_EV_WAIT) return "program: unknown op code";
         }
+    }
+    // Structure of the loops (`for` in a coroutine body): every END_LOOP closes the innermost open LOOP and the two
+    // name each other (LOOP.b = END + 1, END.b = LOOP + 1); at most two deep (the interpreters keep two counters per
+    // process); no body starts inside another body's loop; an IF / JUMP stays inside the loop body it is in -- jumping
+    // out would leave the loop counter on the process's stack, jumping in would run END_LOOP on an empty one.
+    {
+        uint32_t open[2];
+        int depth = 0;
+        int32_t *nest = new (std::nothrow) int32_t[p.n_ops];   // innermost enclosing LOOP of each op, -1 = none
+        if (!nest) return "program: out of host memory";
+        const char *why = nullptr;
+        for (uint32_t i = 0; i < p.n_ops && !why; ++i) {
+            const cxxdes_b200_op &op = p.ops[i];
+            if (op.code == CXXDES_B200_OP_END_LOOP) {
+                if (depth == 0) { why = "program: END_LOOP without a LOOP"; break; }
+                const uint32_t head = open[depth - 1];
+                if ((uint32_t)p.ops[head].b != i + 1 || (uint32_t)op.b != head + 1) { why = "program: LOOP / END_LOOP do not pair up"; break; }
+                nest[i] = (int32_t)head;
+                --depth;
+                continue;
+            }
+            nest[i] = depth ? (int32_t)open[depth - 1] : -1;
+            if (op.code == CXXDES_B200_OP_LOOP) {
+                if (depth >= 2) { why = "program: loops nest at most two deep"; break; }
+                open[depth++] = i;
+            }
+        }
+        if (!why && depth != 0) why = "program: LOOP without an END_LOOP";
+        for (uint32_t i = 0; i < p.n_procs && !why; ++i)
+            if (nest[p.procs[i].entry] != -1) why = "program: a process body starts inside a loop";
+        for (uint32_t i = 0; i < p.n_ops && !why; ++i) {
+            const cxxdes_b200_op &op = p.ops[i];
+            if ((op.code == CXXDES_B200_OP_IF || op.code == CXXDES_B200_OP_JUMP) && nest[i] != nest[op.b])
+                why = "program: IF / JUMP must stay inside its loop body";
+        }
+        delete[] nest;
+        if (why) return why;
     }
     return nullptr;
 }

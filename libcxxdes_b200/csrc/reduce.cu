@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_columns_kernel(device_colu
     zero(p);
     for (uint64_t r = begin + threadIdx.x; r < end; r += RED_THREADS) {
         p.n_events += c.n_events[r];
-        p.n_errors += c.status[r] != 0;
+        // (a replication that run_until / run_for stopped at the horizon is not an error: cxxdes_b200_fetch ignores
+        // the UNFINISHED bit the same way)
+        p.n_errors += (c.status[r] & ~(uint32_t)CXXDES_B200_REP_UNFINISHED) != 0;
         p.hash_sum += c.trace_hash[r];
         p.end_sum += c.end_time[r];
         for (int k = 0; k < CXXDES_B200_N_I64; ++k) p.i64_sum[k] += c.i64[k][r];
@@ -132,6 +134,20 @@ __global__ void clock_floor_kernel(int64_t *end_time, uint64_t n, int64_t floor)
 
 cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream) {
     clock_floor_kernel<<<sm_count * 4, 256, 0, stream>>>(end_time, n, floor);
+    return cudaGetLastError();
+}
+
+// run_for(dt) when nothing is scheduled any more: run_until(now() + dt) only moves each replication's own clock
+// (environment.ipp:190-196,205-209); saturates instead of wrapping.
+__global__ void clock_add_kernel(int64_t *end_time, uint64_t n, int64_t dt) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t t = end_time[r];
+        end_time[r] = t > INT64_MAX - dt ? INT64_MAX : t + dt;
+    }
+}
+
+cudaError_t launch_clock_add(int64_t *end_time, uint64_t n, int64_t dt, int sm_count, cudaStream_t stream) {
+    clock_add_kernel<<<sm_count * 4, 256, 0, stream>>>(end_time, n, dt);
     return cudaGetLastError();
 }
 

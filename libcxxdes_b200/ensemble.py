@@ -59,10 +59,11 @@ def load_library():
     lib.cxxdes_b200_reduce_allgpus.argtypes = [H, C.c_void_p, C.POINTER(abi.Accumulators)]
     lib.cxxdes_b200_last_run_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
+    lib.cxxdes_b200_pass_counts.argtypes = [H, C.POINTER(C.c_uint64 * 4)]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
     for name in ("device_count", "version", "create", "check_program", "run", "run_until", "run_for", "sync", "fetch",
-                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "reset", "destroy"):
+                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
     return lib
@@ -71,7 +72,8 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_check_program", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
-    "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_reset",
+    "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_pass_counts",
+    "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",
 ]
 
@@ -221,6 +223,13 @@ class Ensemble:
         n = C.c_uint64()
         _check(self._lib, self._lib.cxxdes_b200_launch_count(self._handle, C.byref(n)))
         return n.value
+
+    def pass_counts(self):
+        """{second_pass, helper, fallback}: replications of the last launch that were redone outside the first-pass
+        kernel's compact representation (diagnostics; results do not depend on it)."""
+        c = (C.c_uint64 * 4)()
+        _check(self._lib, self._lib.cxxdes_b200_pass_counts(self._handle, C.byref(c)))
+        return {"second_pass": int(c[0]), "helper": int(c[1]), "fallback": int(c[2])}
 
     def reset(self):
         if self._handle is not None:

@@ -270,3 +270,156 @@ def test_errors_are_reported():
     with pytest.raises(L.CxxdesError):
         ens.fetch()                                    # fetch before run
     ens.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[1] EXACTLY as benchmarked: lambda = 5, mu = 10, 10 000 packets, seed 0x5EED, 1 ms precision,
+# 1 048 576 replications -- i.e. with more replications than resident lanes (work stealing, the second-pass
+# list and its helper all engaged), not a reduced copy of it.
+# ---------------------------------------------------------------------------------------------
+def _window_vs_oracle(port, p, cols, base, first, n, seed, what):
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, seed, first, n, threads=oracles.os.cpu_count())
+    lo = first - base
+    got = abi.HostColumns(n)
+    got.end_time[:] = cols.end_time[lo:lo + n]
+    got.n_events[:] = cols.n_events[lo:lo + n]
+    got.trace_hash[:] = cols.trace_hash[lo:lo + n]
+    for k in range(abi.N_F64):
+        got.f64[k][:] = cols.f64[k][lo:lo + n]
+    for k in range(abi.N_I64):
+        got.i64[k][:] = cols.i64[k][lo:lo + n]
+    golden_util.assert_columns_equal(got, want, what=what)
+
+
+def test_headline_config_full_size_against_the_oracle(port):
+    """All 1 048 576 replications of the headline run: (1) the device accumulators equal the checksum of checksums
+    the CPU oracle produced for every replication (tests/golden/mm1_config2_full.json, tools/gen_full_parity.py);
+    (2) so does every one of its 64 blocks of 16 384 replications, from the fetched columns; (3) 5 632 replications
+    in windows of global ids -- the first lanes' first replications, the ids around 113 664 where lanes start to
+    steal their second replication, the longest queue of the shard, the last ids -- are compared column by column,
+    bit for bit, with the oracle run here."""
+    full = golden_util.load("mm1_config2_full.json")
+    n, seed = full["n_replications"], full["seed"]
+    p = abi.MM1Params(full["lambda"], full["mu"], full["n_packets"])
+    ens = L.Ensemble(p, n, seed=seed)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run()
+    cols = ens.fetch()
+    acc, _ = ens.reduce()
+    ens.close()
+    assert not cols.status.any() and acc.n_errors == 0
+    assert acc.n_events == full["n_events_sum"]
+    assert acc.end_time_sum == full["end_time_sum"]
+    assert acc.trace_hash_sum == full["trace_hash_sum"]
+    assert acc.i64_sum[0] == full["packets_sum"] and acc.i64_sum[1] == full["max_queue_sum"]
+    for b in full["blocks"]:
+        s = slice(b["first"], b["first"] + b["n"])
+        assert int(cols.n_events[s].sum(dtype=np.uint64)) == b["n_events_sum"], f"block at {b['first']}: n_events"
+        assert int(cols.end_time[s].sum()) == b["end_time_sum"], f"block at {b['first']}: end_time"
+        assert int(cols.trace_hash[s].sum(dtype=np.uint64)) == b["trace_hash_sum"], f"block at {b['first']}: digest"
+    for q in full["long_queue"]:
+        assert int(cols.i64[1][q["replication"]]) == q["max_queue"]
+    longest = max(full["long_queue"], key=lambda q: q["max_queue"])["replication"]
+    for first, cnt in [(0, 1536), (113664 - 512, 1536), (longest - 256, 512), (n // 2, 1024), (n - 1024, 1024)]:
+        _window_vs_oracle(port, p, cols, 0, first, cnt, seed, what=f"headline window at {first}")
+
+
+def test_headline_second_pass_runs_next_to_the_first(port):
+    """The replications of the headline ensemble whose queue outgrows the 31-packet window (ids 3 850 044 and
+    4 042 079 of the 1 Mi..4 Mi shard a rank 3 of the weak-scaling bench owns: max queue 32 and 33) are redone with
+    the two-level ring -- by the helper grid, while the first pass runs -- and equal the oracle bit for bit."""
+    p = abi.MM1Params(5.0, 10.0, 10000)
+    first, n = 3_800_000, 262_144          # 2.3 rounds of the 113 664 resident lanes
+    ens = L.Ensemble(p, n, seed=0x5EED, first_replication=first)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run()
+    cols = ens.fetch()
+    counts = ens.pass_counts()
+    ens.close()
+    assert not cols.status.any()
+    assert counts["second_pass"] >= 2 and counts["fallback"] == 0
+    assert counts["helper"] == counts["second_pass"]       # nothing was left for after the first pass
+    for rep in (3_850_044, 4_042_079):
+        _window_vs_oracle(port, p, cols, first, rep - 64, 128, 0x5EED, what=f"around replication {rep}")
+        assert cols.i64[1][rep - first] >= 32
+    _window_vs_oracle(port, p, cols, first, first, 256, 0x5EED, what="first ids of the shard")
+
+
+def test_second_pass_list_longer_than_the_helper(port):
+    """Many replications outgrow a small window: the helper takes what it can while the first pass runs and the
+    pass that follows takes the rest of the same list; every replication is done exactly once."""
+    p = abi.MM1Params(7.0, 10.0, 3000)
+    n = 150_000
+    ens = L.Ensemble(p, n, seed=77, queue_capacity=16)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run()
+    cols = ens.fetch()
+    counts = ens.pass_counts()
+    acc, _ = ens.reduce()
+    ens.close()
+    assert counts["second_pass"] > 1000 and counts["helper"] >= 1
+    assert not cols.status.any() and acc.n_errors == 0
+    assert (cols.i64[0] == 3000).all()
+    want = port.run(abi.MODEL_MM1, p, oracles.MM1_CLOCK, 77, 0, 4096, threads=oracles.os.cpu_count())
+    assert (want.i64[1] > 16).sum() > 20
+    _window_vs_oracle(port, p, cols, 0, 0, 4096, 77, what="small window")
+    _window_vs_oracle(port, p, cols, 0, n - 2048, 2048, 77, what="small window, last ids")
+
+
+def test_pieces_on_an_ensemble_larger_than_the_grid(port):
+    """run_until(past the end), run_for, run() on more replications than resident lanes: every lane of a warp can
+    claim a replication that needs nothing in this piece (finished earlier) while the work list still holds
+    replications further on -- the warp must keep claiming.  Compared with one plain run() and the oracle."""
+    p = abi.MM1Params(5.0, 10.0, 12)
+    n = 1_000_000                                      # more than 8 claims x the 113 664 resident lanes
+    ref = L.Ensemble(p, n, seed=3)
+    ref.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    want = ref.run().fetch()
+    ref.close()
+    ens = L.Ensemble(p, n, seed=3)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run_until(2400)                                # about half of the replications are finished by now
+    half = ens.fetch(strict=False)
+    assert 0.2 < (half.status & abi.REP_UNFINISHED).astype(bool).mean() < 0.8
+    ens.run_until(10 ** 6)                             # past every end: the rest finishes, clocks go to 10^6
+    a = ens.fetch(strict=False)
+    assert not (a.status & abi.REP_UNFINISHED).any() and (a.end_time == 10 ** 6).all()
+    assert np.array_equal(a.trace_hash, want.trace_hash) and np.array_equal(a.n_events, want.n_events)
+    ens.run_for(500)
+    b = ens.fetch(strict=False)
+    assert (b.end_time == 10 ** 6 + 500).all() and np.array_equal(b.trace_hash, want.trace_hash)
+    ens.run()
+    c = ens.fetch()
+    acc, _ = ens.reduce()
+    ens.close()
+    assert np.array_equal(c.trace_hash, want.trace_hash) and (c.end_time == 10 ** 6 + 500).all()
+    assert acc.n_errors == 0
+    _window_vs_oracle(port, p, want, 0, n - 4096, 4096, 3, what="last ids")
+
+
+def test_clock_follows_run_until_after_the_end(port):
+    """run(); run_until(t); run_for(dt): nothing is left to dispatch, but now_ = max(now_, t) and run_for adds to
+    each replication's own clock (environment.ipp:190-196,205-209)."""
+    p = abi.MM1Params(5.0, 10.0, 30)
+    ens = L.Ensemble(p, 300, seed=4)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    natural = ens.run().fetch().end_time.copy()
+    t = int(np.median(natural))
+    after = ens.run_until(t).fetch().end_time
+    assert np.array_equal(after, np.maximum(natural, t))
+    later = ens.run_for(250).fetch().end_time
+    assert np.array_equal(later, np.maximum(natural, t) + 250)
+    with pytest.raises(L.CxxdesError):
+        L.Ensemble(p, 4).run_until(5).run_for(2 ** 63 - 3)
+    ens.close()
+
+
+def test_unfinished_replications_are_not_errors():
+    p = abi.MM1Params(5.0, 10.0, 500)
+    ens = L.Ensemble(p, 256, seed=6)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
+    ens.run_until(2000)
+    cols = ens.fetch(strict=False)
+    acc, _ = ens.reduce()
+    ens.close()
+    assert (cols.status & abi.REP_UNFINISHED).all() and acc.n_errors == 0

@@ -242,3 +242,36 @@ def test_archsim_full_size_properties(built):
     assert acc.n_events == int(got.n_events.sum())
     # addresses are uniform over 32 with a 16-block LRU store: the hit rate is near (but below) one half
     assert 0.40 < hits.mean() / 1024 < 0.5
+
+
+@pytest.mark.parametrize("name,fields", [
+    ("aloha", (4, 0, 2.0, 2.0, 1.0, 1000.0, 3)),       # 56 832 resident lanes
+    ("mmc", (9.0, 1.0, 0.5, 8, 0, 6))])                 # 52 096 resident lanes
+def test_pieces_on_an_ensemble_larger_than_the_grid(port, name, fields):
+    """run_until / run_for / run() in pieces on several times more replications than resident lanes: in a later piece
+    a lane can claim a replication that needs nothing (finished earlier, or nothing due) while the work list still
+    holds replications further on; a warp whose 32 lanes all drew such replications must keep claiming, or the tail of
+    the ensemble is never visited (finished rows miss the later horizon, running rows never finish)."""
+    model, cls, fname = MODELS[name]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    n = 400_000
+    clock = clock_pairs(g)
+    want, _ = run_gpu(p, n, clock, seed=21)
+    ends = np.sort(want.end_time)
+    t_half, t_most, t_all = int(ends[n // 2]), int(ends[(n * 97) // 100]), int(ends[-1]) + 10
+    ens = L.Ensemble(p, n, seed=21)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    ens.run_until(t_half)
+    ens.run_until(t_most)                       # 97 % are finished: most claims of the next pieces find nothing to do
+    ens.run_for(1)
+    got = ens.run_until(t_all).fetch(strict=False)
+    assert not got.status.any() and (got.end_time == t_all).all()
+    assert np.array_equal(got.trace_hash, want.trace_hash) and np.array_equal(got.n_events, want.n_events)
+    ens.run_for(7)
+    got = ens.run().fetch()
+    ens.close()
+    assert (got.end_time == t_all + 7).all() and np.array_equal(got.trace_hash, want.trace_hash)
+    tail = port.run(model, p, clock_of(g), 21, n - 2048, 2048, threads=os.cpu_count())
+    assert np.array_equal(tail.trace_hash, want.trace_hash[n - 2048:])
+    assert np.array_equal(tail.end_time, want.end_time[n - 2048:])

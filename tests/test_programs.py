@@ -433,11 +433,17 @@ def test_check_program_without_a_gpu(cuda_lib):
     import ctypes
     R, DELAY, ALL, CH_DELAY, CH_ALL, IF, JUMP, QPUT = (abi.OP_RETURN, abi.OP_DELAY, abi.OP_ALL_OF, abi.OP_CHILD_DELAY,
                                                       abi.OP_CHILD_ALL_OF, abi.OP_IF, abi.OP_JUMP, abi.OP_Q_PUT)
+    LOOP, END = abi.OP_LOOP, abi.OP_END_LOOP
+    D = (DELAY, 0, abi.INHERIT32, 1)
     ok = [
         [(DELAY, 0, abi.INHERIT32, 5), (R, 0, 0, 0)],
         [(ALL, 2, abi.INHERIT32, 0), (CH_ALL, 2, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (CH_DELAY, 0, abi.INHERIT32, 2),
          (CH_DELAY, 0, abi.INHERIT32, 3), (R, 0, 0, 0)],
         [(IF, abi.SRC_NOW << 8 | abi.CMP["<"] << 12, 2, 10), (DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
+        # for (3) { for (2) { delay } if (now < 10) delay }   -- the IF lands on the outer END_LOOP, inside its own body
+        [(LOOP, 0, 7, 3), (LOOP, 0, 4, 2), D, (END, 0, 2, 0), (IF, abi.SRC_NOW << 8 | abi.CMP["<"] << 12, 6, 10), D,
+         (END, 0, 1, 0), (R, 0, 0, 0)],
+        [(LOOP, 0, 3, 0), D, (END, 0, 1, 0), (R, 0, 0, 0)],          # zero iterations
     ]
     bad = {
         "last op must be RETURN": [(DELAY, 0, abi.INHERIT32, 5)],
@@ -447,6 +453,15 @@ def test_check_program_without_a_gpu(cuda_lib):
         "IF operand": [(IF, 7 << 8, 1, 0), (R, 0, 0, 0)],
         "queue operand": [(QPUT, 0, 0, 0), (R, 0, 0, 0)],
         "unknown op": [(99, 0, 0, 0), (R, 0, 0, 0)],
+        # loop structure (the interpreters keep two counters per process and trust the pairing)
+        "END_LOOP without": [D, (END, 0, 0, 0), (R, 0, 0, 0)],
+        "LOOP without": [(LOOP, 0, 2, 3), D, (R, 0, 0, 0)],
+        "do not pair up": [(LOOP, 0, 2, 3), D, (END, 0, 0, 0), (R, 0, 0, 0)],
+        "two deep": [(LOOP, 0, 7, 2), (LOOP, 0, 6, 2), (LOOP, 0, 5, 2), D, (END, 0, 3, 0), (END, 0, 2, 0), (END, 0, 1, 0), (R, 0, 0, 0)],
+        "LOOP count": [(LOOP, 0, 3, 1 << 32), D, (END, 0, 1, 0), (R, 0, 0, 0)],
+        "[0, 2^32)": [(LOOP, 0, 3, -1), D, (END, 0, 1, 0), (R, 0, 0, 0)],
+        "stay inside its loop": [(LOOP, 0, 4, 3), (JUMP, 0, 4, 0), D, (END, 0, 1, 0), D, (R, 0, 0, 0)],            # out of the body
+        "inside its loop body": [(JUMP, 0, 2, 0), (LOOP, 0, 4, 3), D, (END, 0, 2, 0), (R, 0, 0, 0)],                # into the body
     }
     for ops in ok:
         assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(_raw(ops))) == abi.OK, cuda_lib.cxxdes_b200_last_error()
@@ -454,6 +469,10 @@ def test_check_program_without_a_gpu(cuda_lib):
         assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(_raw(ops))) == abi.ERR_INVALID
         assert reason.encode() in cuda_lib.cxxdes_b200_last_error(), (reason, cuda_lib.cxxdes_b200_last_error())
     assert cuda_lib.cxxdes_b200_check_program(None) == abi.ERR_INVALID
+    # a second body that would start inside the first one's loop
+    inside = _raw([(LOOP, 0, 3, 2), D, (END, 0, 1, 0), (R, 0, 0, 0)], procs=((0, 0), (1, 1)))
+    assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(inside)) == abi.ERR_INVALID
+    assert b"starts inside a loop" in cuda_lib.cxxdes_b200_last_error()
     for k in sorted(K.SCENARIOS):                       # everything the builders emit passes, and Program.check() says so
         K.SCENARIOS[k]()[0].check()
     with pytest.raises(L.CxxdesError):

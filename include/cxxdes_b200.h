@@ -338,6 +338,11 @@ int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
  * counts[2] = redone by the full-size 64-bit kernel, counts[3] = 0 (reserved).  Implies a sync. */
 int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]);
 
+/* Name of the first-pass kernel instantiation a plain run() of this handle launches, e.g.
+ * "mm1_ahead_kernel<256,3,32,4,0,0,0>+helper<32,16,32,4>" (template arguments as in csrc/): the key under which
+ * profiles/ stores measured per-kernel figures.  NUL-terminated, truncated to buf_size. */
+int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size);
+
 /* environment::reset() (environment.ipp:154-176) + rebind: replications start over. */
 int cxxdes_b200_reset(cxxdes_b200_ensemble *e);
 

@@ -222,7 +222,7 @@ int plan(cxxdes_b200_ensemble *e) {
                            p.n_packets < (1ULL << 30);
             if (e->use_fused) {
                 e->mm1_plan = plan_mm1_fused(p, c.queue_capacity, e->sm_count, e->smem_optin, e->clk.tick_mult, e->clk.ticks_per_unit,
-                                             (c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0);
+                                             (c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) != 0, c.n_replications);
                 e->ring_bytes = (size_t)e->mm1_plan.fb_blocks * e->mm1_plan.fb_threads * e->mm1_plan.fb_ring *
                                 sizeof(int64_t);
                 if (!(c.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP)) e->ahead_gring_bytes = mm1_ahead_gring_bytes(e->mm1_plan);
@@ -668,6 +668,44 @@ int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms) {
     if (rc) return rc;
     CUDA_TRY(cudaEventSynchronize(e->ev_end));
     CUDA_TRY(cudaEventElapsedTime(ms, e->ev_begin, e->ev_end));
+    return CXXDES_B200_OK;
+}
+
+// Which first-pass kernel instantiation the handle's runs use (profiles are keyed by this string).
+int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size) {
+    if (!e || !buf || !buf_size) return fail(CXXDES_B200_ERR_INVALID, "handle/buf is NULL");
+    shard sh{};
+    sh.clk = e->clk;
+    sh.run_until = -1;
+    switch (e->cfg.model) {
+        case CXXDES_B200_MODEL_MM1:
+            if (!e->use_fused) snprintf(buf, buf_size, "mm1_engine_kernel");
+            else if (e->cfg.flags & CXXDES_B200_FLAG_MM1_LOCKSTEP)
+                snprintf(buf, buf_size, e->mm1_plan.direct_global ? "mm1_fused_kernel<false,128,1>" : "mm1_fused_kernel<true,256,4>");
+            else if (e->mm1_plan.ah_direct_global) snprintf(buf, buf_size, "mm1_fused_kernel<false,128,1>");
+            else {
+                // <THREADS, MIN_BLOCKS, RING_SLOTS, EVENT_SLOTS, MODE, SPILL, STATE> of a plain run()
+                const mm1_fused_plan &p = e->mm1_plan;
+                const int mode = (e->clk.tick_mult != 1 ? 2 : 0) | (p.ah_wide ? 4 : 0);
+                snprintf(buf, buf_size, "mm1_ahead_kernel<%d,%d,%u,4,%d,%d,0>%s", p.ah_threads, p.ah_blocks / e->sm_count,
+                         p.ah_ring_slots, mode, p.ah_spill ? 1 : 0, (!p.ah_spill && e->helper_stream) ? "+helper<32,16,32,4>" : "");
+            }
+            break;
+        case CXXDES_B200_MODEL_ALOHA:
+            snprintf(buf, buf_size, aloha_keeps_state(e->params.aloha, sh) ? "aloha_fast_kernel<false>" : "aloha_kernel");
+            break;
+        case CXXDES_B200_MODEL_MMC:
+            snprintf(buf, buf_size, mmc_keeps_state(e->params.mmc, sh) ? "mmc_fast_kernel<false>" : "mmc_kernel");
+            break;
+        case CXXDES_B200_MODEL_ARCHSIM:
+            snprintf(buf, buf_size, "archsim_kernel<%s>", e->params.arch.n_requesters == 1 ? "1 requester" : "k requesters");
+            break;
+        case CXXDES_B200_MODEL_PROGRAM:
+            snprintf(buf, buf_size, e->prog_fast.valid ? "program_fast_kernel<false>" : "program_kernel");
+            break;
+        default:
+            return fail(CXXDES_B200_ERR_INVALID, "unknown model");
+    }
     return CXXDES_B200_OK;
 }
 

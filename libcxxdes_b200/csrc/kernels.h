@@ -34,7 +34,8 @@ struct mm1_fused_plan {
     bool ah_direct_global;
 };
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                              size_t smem_per_block_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep);
+                              size_t smem_per_block_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep,
+                              uint64_t n_replications);
 // What the second pass needs to run NEXT TO the first one instead of after it (helper_stream == nullptr: after it).
 struct mm1_overlap {
     cudaStream_t helper_stream;     // a stream of the handle's own
@@ -50,7 +51,7 @@ cudaError_t configure_mm1_fused(const mm1_fused_plan &plan);
 
 // ---- fused M/M/1, variates generated ahead of the event loop (mm1_ahead.cu) ----
 void plan_mm1_ahead(mm1_fused_plan &plan, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                    int64_t tick_mult, int64_t ticks_per_unit);
+                    int64_t tick_mult, int64_t ticks_per_unit, uint64_t n_replications);
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan);
 size_t mm1_ahead_gring_bytes(const mm1_fused_plan &plan);
 size_t mm1_ahead_state_bytes(uint64_t n_replications);   // run_until in pieces: 128 B per replication

@@ -15,6 +15,7 @@
 // Replications the 32-bit/shared-memory representation cannot hold (queue longer than the ring,
 // ticks beyond 2^30) are appended to the retry list and redone by mm1_fused_kernel<false>.
 #include <cmath>
+#include <cstdlib>
 
 #include "device/mm1_lane.cuh"
 #include "device/models_common.cuh"
@@ -305,6 +306,12 @@ struct geometry {
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
 };
 using geometry0 = geometry<256, 3, 32>;
+// One wave for a shard a little larger than geometry0's 113 664 resident lanes (a 1 Mi ensemble split over 8 GPUs is
+// 131 072 replications per GPU: 1.15 waves on geometry0, i.e. the time of two): 7 x 128 threads per SM = 132 608
+// lanes with a 16-slot window and the two-level ring from the start.
+using geometry1 = geometry<128, 7, 16>;
+// ... and up to 151 552 lanes
+using geometry2 = geometry<256, 4, 16>;
 
 template <typename G>
 void fill_plan(mm1_fused_plan &p, int sm_count) {
@@ -313,12 +320,26 @@ void fill_plan(mm1_fused_plan &p, int sm_count) {
     p.ah_smem_bytes = G::SMEM;
     p.ah_ring_slots = G::RING_SLOTS;
 }
+template <typename G>
+uint64_t lanes_of(int sm_count) { return (uint64_t)sm_count * G::MIN_BLOCKS * G::THREADS; }
 }  // namespace
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                    int64_t tick_mult, int64_t ticks_per_unit) {
-    p.ah_geometry = 0;
-    fill_plan<geometry0>(p, sm_count);
+                    int64_t tick_mult, int64_t ticks_per_unit, uint64_t n_replications) {
+    // Geometry from the shard size: whatever fits geometry0's lanes in one wave, or needs several waves anyway, runs
+    // on geometry0 (deepest window, fastest per replication); a shard between one and 1.33 waves gets the geometry
+    // whose lanes hold it in one wave.  CXXDES_B200_MM1_GEOMETRY=0|1|2 forces one (A/B measurements).
+    int geo = 0;
+    if (n_replications > lanes_of<geometry0>(sm_count)) {
+        if (n_replications <= lanes_of<geometry1>(sm_count)) geo = 1;
+        else if (n_replications <= lanes_of<geometry2>(sm_count)) geo = 2;
+    }
+    if (const char *force = getenv("CXXDES_B200_MM1_GEOMETRY"))
+        if (force[0] >= '0' && force[0] <= '2' && !force[1]) geo = force[0] - '0';
+    p.ah_geometry = geo;
+    if (geo == 1) fill_plan<geometry1>(p, sm_count);
+    else if (geo == 2) fill_plan<geometry2>(p, sm_count);
+    else fill_plan<geometry0>(p, sm_count);
     const uint32_t window = p.ah_ring_slots - 1;  // one slot holds the arrival key after the last packet
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the window also holds the packets
     // generated ahead (2 to 4).  When more than ~0.1% of the replications are expected to outgrow
@@ -441,7 +462,8 @@ void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_pa
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    (void)plan;
+    if (plan.ah_geometry == 1) return configure_geometry<geometry1>();
+    if (plan.ah_geometry == 2) return configure_geometry<geometry2>();
     return configure_geometry<geometry0>();
 }
 
@@ -500,8 +522,16 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     mm1::constants c;
     const int mode = constants_and_mode(c, prm, sh, plan);
     pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
-    if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
-    else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
+    if (plan.ah_geometry == 1) {
+        if (spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, a, stream);
+        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, a, stream);
+    } else if (plan.ah_geometry == 2) {
+        if (spill) launch_geometry<geometry2, true>(mode, c, prm, sh, out, plan, a, stream);
+        else launch_geometry<geometry2, false>(mode, c, prm, sh, out, plan, a, stream);
+    } else {
+        if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
+        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
+    }
     return cudaGetLastError();
 }
 

@@ -365,7 +365,8 @@ constexpr int FAST_MIN_BLOCKS = 4;
 constexpr int FB_THREADS = 128;
 
 mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
-                              size_t smem_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep) {
+                              size_t smem_optin, int64_t tick_mult, int64_t ticks_per_unit, bool lockstep,
+                              uint64_t n_replications) {
     mm1_fused_plan p{};
     p.threads = FAST_THREADS;
     const size_t table_bytes = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -382,7 +383,7 @@ mm1_fused_plan plan_mm1_fused(const cxxdes_b200_mm1_params &prm, uint32_t queue_
     double rho = prm.lambda / prm.mu;
     double p_over = rho >= 1.0 ? 1.0 : pow(rho, (double)p.smem_ring + 1.0) * (double)prm.n_packets;
     p.direct_global = !(p_over < 0.02);
-    plan_mm1_ahead(p, prm, queue_capacity, sm_count, tick_mult, ticks_per_unit);
+    plan_mm1_ahead(p, prm, queue_capacity, sm_count, tick_mult, ticks_per_unit, n_replications);
     p.fb_threads = FB_THREADS;
     uint64_t want = prm.n_packets;
     if (lockstep ? p.direct_global : p.ah_direct_global) {

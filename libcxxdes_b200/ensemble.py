@@ -60,10 +60,11 @@ def load_library():
     lib.cxxdes_b200_last_run_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_pass_counts.argtypes = [H, C.POINTER(C.c_uint64 * 4)]
+    lib.cxxdes_b200_kernel_name.argtypes = [H, C.c_char_p, C.c_size_t]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
     for name in ("device_count", "version", "create", "check_program", "run", "run_until", "run_for", "sync", "fetch",
-                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "reset", "destroy"):
+                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "kernel_name", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
     return lib
@@ -73,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_check_program", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
     "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_pass_counts",
-    "cxxdes_b200_reset",
+    "cxxdes_b200_kernel_name", "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",
 ]
 
@@ -223,6 +224,23 @@ class Ensemble:
         n = C.c_uint64()
         _check(self._lib, self._lib.cxxdes_b200_launch_count(self._handle, C.byref(n)))
         return n.value
+
+    def kernel_name(self):
+        """The first-pass kernel instantiation a plain run() of this handle launches."""
+        self._ensure()
+        buf = C.create_string_buffer(160)
+        _check(self._lib, self._lib.cxxdes_b200_kernel_name(self._handle, buf, len(buf)))
+        return buf.value.decode()
+
+    def reduce_allgpus(self, comm, want_host=True):
+        """reduce(), then one NCCL all-reduce of the 88-byte accumulator struct over `comm` (an ncclComm_t with one
+        rank per shard, e.g. from libcxxdes_b200.nccl) on the handle's stream, in place on the device.  Returns the
+        ensemble totals, or None with want_host=False (no host sync: the call only enqueues)."""
+        self._ensure()
+        acc = abi.Accumulators() if want_host else None
+        _check(self._lib, self._lib.cxxdes_b200_reduce_allgpus(self._handle, C.c_void_p(int(comm)),
+                                                               C.byref(acc) if want_host else None))
+        return acc
 
     def pass_counts(self):
         """{second_pass, helper, fallback}: replications of the last launch that were redone outside the first-pass

@@ -228,13 +228,22 @@ def load_gates(a, first_rep, n_local, world, rank):
     except (OSError, ValueError):
         pass
     if a.config == "mm1" and standard:
-        try:
-            shards = json.loads((g / "mm1_config2_shards.json").read_text())["shards"]
-            for sh in shards:
+        try:   # a whole 1 Mi shard (weak scaling, or one GPU)
+            for sh in json.loads((g / "mm1_config2_shards.json").read_text())["shards"]:
                 if sh["first_replication"] == first_rep and sh["n_replications"] == n_local:
                     full = sh
         except (OSError, ValueError, KeyError):
             pass
+        if full is None:
+            try:   # a strong-scaling shard of the first 1 Mi replications: whole blocks of the per-block sums
+                blocks = json.loads((g / "mm1_config2_full.json").read_text())["blocks"]
+                mine = [b for b in blocks if first_rep <= b["first"] and b["first"] + b["n"] <= first_rep + n_local]
+                if mine and sum(b["n"] for b in mine) == n_local:
+                    full = {k: sum(b[k] for b in mine) for k in ("n_events_sum", "end_time_sum", "trace_hash_sum",
+                                                                 "packets_sum", "max_queue_sum")}
+                    full["trace_hash_sum"] &= (1 << 64) - 1
+            except (OSError, ValueError, KeyError):
+                pass
     return window, full
 
 

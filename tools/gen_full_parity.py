@@ -42,7 +42,24 @@ def main():
     ap.add_argument("--block", type=int, default=16384)
     ap.add_argument("--window", type=int, default=31, help="packets the shared-memory ring window holds")
     ap.add_argument("--out", default=str(ROOT / "tests" / "golden" / "mm1_config2_full.json"))
+    ap.add_argument("--merge", nargs="+", metavar="JSON",
+                    help="instead of running anything: merge per-shard outputs of this tool (the 1 Mi shards the ranks of a "
+                         "weak-scaling bench own) into one file of shard totals, --out tests/golden/mm1_config2_shards.json")
     a = ap.parse_args()
+    if a.merge:
+        shards = []
+        for path in a.merge:
+            d = json.loads(Path(path).read_text())
+            shards.append({k: d[k] for k in ("first_replication", "n_replications", "n_events_sum", "end_time_sum",
+                                             "trace_hash_sum", "packets_sum", "max_queue_sum")})
+            shards[-1]["long_queue"] = [q for q in d["long_queue"] if q["max_queue"] >= a.window - 1]
+        shards.sort(key=lambda x: x["first_replication"])
+        out = {"model": "mm1", "lambda": LAMBDA, "mu": MU, "n_packets": PACKETS, "seed": SEED,
+               "clock": "unit 1 s, precision 1 ms", "generator": "tools/gen_full_parity.py (--first rank<<20, then --merge)",
+               "oracle": "oracle/port", "shards": shards}
+        Path(a.out).write_text(json.dumps(out, indent=1) + "\n")
+        print(f"wrote {a.out}: {len(shards)} shards")
+        return
 
     import oracles
     from libcxxdes_b200 import abi

@@ -338,6 +338,20 @@ int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
  * counts[2] = redone by the full-size 64-bit kernel, counts[3] = 0 (reserved).  Implies a sync. */
 int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]);
 
+/* Event trace of ONE replication (index within this shard): the replication is run again from tick 0 -- to the end,
+ * or to `until` >= 0 as environment::run_until would -- on the model's full-size kernel with a sink attached to
+ * environment::step (environment.ipp:117-146), and the first `max_events` popped tokens are returned in order as
+ * (time, priority, kind = CXXDES_B200_TOKEN_*, process ordinal or 0xFFFF for a null-target token): the four public
+ * token fields (token.ipp:23-35) the trace digest folds, i.e. what the reference would print under
+ * CXXDES_DEBUG_TOKEN (token.ipp:50-60).  *n_events = events of the whole run, *trace_hash = its digest: equal to the
+ * replication's trace_hash column means the list IS the sequence the ensemble's kernel dispatched; a digest mismatch
+ * against a CPU run is localised by diffing the two lists.  Host arrays of max_events entries; result columns and
+ * saved state of the handle are not touched.  Implies a sync. */
+enum { CXXDES_B200_TOKEN_RESUME = 0, CXXDES_B200_TOKEN_HANDLER = 1, CXXDES_B200_TOKEN_NOOP = 2 };
+int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t until, uint64_t max_events, int64_t *time,
+                      int64_t *priority, uint32_t *kind, uint32_t *proc, uint64_t *n_written, uint64_t *n_events,
+                      uint64_t *trace_hash);
+
 /* Name of the first-pass kernel instantiation a plain run() of this handle launches, e.g.
  * "mm1_ahead_kernel<256,3,32,4,0,0,0>+helper<32,16,32,4>" (template arguments as in csrc/): the key under which
  * profiles/ stores measured per-kernel figures.  NUL-terminated, truncated to buf_size. */

@@ -671,6 +671,101 @@ int cxxdes_b200_last_run_ms(cxxdes_b200_ensemble *e, float *ms) {
     return CXXDES_B200_OK;
 }
 
+// Event trace of one replication: a one-replication shard re-run from tick 0 on the model's full-size kernel
+// (64-bit ticks, generic heap) with a sink attached to environment::step.  Temporary device buffers, freed before
+// returning; the handle's result columns and saved state are not touched.
+int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t until, uint64_t max_events, int64_t *time,
+                      int64_t *priority, uint32_t *kind, uint32_t *proc, uint64_t *n_written, uint64_t *n_events,
+                      uint64_t *trace_hash) {
+    if (!e) return fail(CXXDES_B200_ERR_INVALID, "handle is NULL");
+    if (replication >= e->cfg.n_replications) return fail(CXXDES_B200_ERR_INVALID, "trace: replication out of range");
+    if (max_events && (!time || !priority || !kind || !proc)) return fail(CXXDES_B200_ERR_INVALID, "trace: a column is NULL");
+    int rc = set_device(e);
+    if (rc) return rc;
+    struct buffers {
+        unsigned char *cols = nullptr, *rows = nullptr;
+        int64_t *ring = nullptr;
+        unsigned long long *counters = nullptr;
+        ~buffers() { cudaFree(cols); cudaFree(rows); cudaFree(ring); cudaFree(counters); }
+    } b;
+    const size_t rows_bytes = (max_events ? max_events : 1) * 24;
+    CUDA_TRY(cudaMalloc(&b.cols, 8 * 256));
+    CUDA_TRY(cudaMalloc(&b.rows, rows_bytes));
+    CUDA_TRY(cudaMalloc(&b.counters, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(b.cols, 0, 8 * 256, e->stream));
+    CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(unsigned long long), e->stream));
+    device_columns out{};
+    out.end_time = (int64_t *)(b.cols + 0 * 256);
+    out.n_events = (uint64_t *)(b.cols + 1 * 256);
+    out.trace_hash = (uint64_t *)(b.cols + 2 * 256);
+    out.status = (uint32_t *)(b.cols + 3 * 256);
+    for (int k = 0; k < CXXDES_B200_N_F64; ++k) out.f64[k] = (double *)(b.cols + (4 + k) * 256);
+    for (int k = 0; k < CXXDES_B200_N_I64; ++k) out.i64[k] = (int64_t *)(b.cols + (6 + k) * 256);
+    trace_sink sink{};
+    sink.time = (int64_t *)b.rows;
+    sink.priority = sink.time + max_events;
+    sink.kind = (uint32_t *)(sink.priority + max_events);
+    sink.proc = sink.kind + max_events;
+    sink.max_events = max_events;
+    shard sh{};
+    sh.seed = e->cfg.seed;
+    sh.first_replication = e->cfg.first_replication + replication;
+    sh.n_replications = 1;
+    sh.clk = e->clk;
+    sh.run_until = until < 0 ? -1 : until;
+    sh.work_counter = b.counters + 0;
+    sh.retry_count = b.counters + 1;
+    sh.retry_list = (uint32_t *)(b.counters + 6);
+    sh.retry_a_count = b.counters + 3;
+    sh.retry_a_cursor = b.counters + 4;
+    sh.retry_a_list = (uint32_t *)(b.counters + 7);
+    sh.log_table = e->log_table;
+    switch (e->cfg.model) {
+        case CXXDES_B200_MODEL_MM1: {
+            uint64_t cap = e->params.mm1.n_packets < 4096 ? e->params.mm1.n_packets : 4096;   // sync::queue ring of the engine kernel
+            if (cap < 2) cap = 2;
+            CUDA_TRY(cudaMalloc(&b.ring, cap * 32 * sizeof(int64_t)));
+            CUDA_TRY(launch_mm1_trace(e->params.mm1, sh, out, b.ring, (uint32_t)cap, sink, e->stream));
+            break;
+        }
+        case CXXDES_B200_MODEL_ALOHA:
+            CUDA_TRY(launch_aloha_trace(e->params.aloha, sh, out, sink, e->stream));
+            break;
+        case CXXDES_B200_MODEL_MMC:
+            CUDA_TRY(launch_mmc_trace(e->params.mmc, sh, out, (uint64_t *)e->ring, sink, e->stream));
+            break;
+        case CXXDES_B200_MODEL_ARCHSIM:
+            CUDA_TRY(launch_archsim_trace(e->params.arch, sh, out, sink, e->stream));
+            break;
+        case CXXDES_B200_MODEL_PROGRAM:
+            CUDA_TRY(launch_program_trace(e->dprog, e->program_blob_bytes, sh, out, sink, e->stream));
+            break;
+        default:
+            return fail(CXXDES_B200_ERR_INVALID, "unknown model");
+    }
+    ++e->launches;
+    uint64_t total = 0, digest = 0;
+    uint32_t status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, out.n_events, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(&digest, out.trace_hash, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(&status, out.status, 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const uint64_t n = total < max_events ? total : max_events;
+    if (n) {
+        CUDA_TRY(cudaMemcpy(time, sink.time, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(priority, sink.priority, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(kind, sink.kind, n * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(proc, sink.proc, n * 4, cudaMemcpyDeviceToHost));
+    }
+    if (n_written) *n_written = n;
+    if (n_events) *n_events = total;
+    if (trace_hash) *trace_hash = digest;
+    if (status & ~(uint32_t)CXXDES_B200_REP_UNFINISHED)
+        return fail(CXXDES_B200_ERR_CAPACITY, "trace: replication %llu reported status 0x%x",
+                    (unsigned long long)sh.first_replication, status);
+    return CXXDES_B200_OK;
+}
+
 // Which first-pass kernel instantiation the handle's runs use (profiles are keyed by this string).
 int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size) {
     if (!e || !buf || !buf_size) return fail(CXXDES_B200_ERR_INVALID, "handle/buf is NULL");

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "device/models_common.cuh"
+#include "device/trace.cuh"
 
 namespace cxb {
 
@@ -158,6 +159,18 @@ size_t reduce_scratch_bytes(int sm_count);
 cudaError_t launch_reduce(const device_columns &cols, uint64_t n, cxxdes_b200_accumulators *device_acc,
                           void *scratch, int sm_count, cudaStream_t stream);
 
+
+// ---- event trace of one replication (cxxdes_b200_trace): sh.n_replications == 1, full-size kernels ----
+cudaError_t launch_mm1_trace(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out, int64_t *ring,
+                             uint32_t ring_cap, const trace_sink &sink, cudaStream_t stream);
+cudaError_t launch_aloha_trace(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
+                               const trace_sink &sink, cudaStream_t stream);
+cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
+                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream);
+cudaError_t launch_archsim_trace(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
+                                 const trace_sink &sink, cudaStream_t stream);
+cudaError_t launch_program_trace(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
+                                 const trace_sink &sink, cudaStream_t stream);
 
 cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream);
 cudaError_t launch_clock_add(int64_t *end_time, uint64_t n, int64_t dt, int sm_count, cudaStream_t stream);

@@ -306,12 +306,14 @@ struct geometry {
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
 };
 using geometry0 = geometry<256, 3, 32>;
-// One wave for a shard a little larger than geometry0's 113 664 resident lanes (a 1 Mi ensemble split over 8 GPUs is
-// 131 072 replications per GPU: 1.15 waves on geometry0, i.e. the time of two): 7 x 128 threads per SM = 132 608
-// lanes with a 16-slot window and the two-level ring from the start.
-using geometry1 = geometry<128, 7, 16>;
-// ... and up to 151 552 lanes
-using geometry2 = geometry<256, 4, 16>;
+// A shard of 1.0 .. 1.33 times geometry0's 113 664 lanes (a 1 Mi ensemble split over 8 GPUs is 131 072 replications
+// per GPU = 1.15 rounds, which takes the time of 1.3): about half as many lanes make it two full rounds, each at
+// nearly twice the speed (the kernel is issue-bound: fewer resident warps, each faster).  [Measured and rejected:
+// more lanes with a 16-slot window and the two-level ring from the start, <128,7,16> and <256,4,16>: 15.5 and
+// 18.2 ms for 131 072 replications against 15.0 ms on geometry0 -- the spilling slot text and 64-72 registers cost
+// more than the partial round.]
+using geometry1 = geometry<224, 2, 32>;   // 66 304 lanes
+using geometry2 = geometry<448, 1, 32>;   // 66 304 lanes, one block per SM
 
 template <typename G>
 void fill_plan(mm1_fused_plan &p, int sm_count) {
@@ -326,13 +328,13 @@ uint64_t lanes_of(int sm_count) { return (uint64_t)sm_count * G::MIN_BLOCKS * G:
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                     int64_t tick_mult, int64_t ticks_per_unit, uint64_t n_replications) {
-    // Geometry from the shard size: whatever fits geometry0's lanes in one wave, or needs several waves anyway, runs
-    // on geometry0 (deepest window, fastest per replication); a shard between one and 1.33 waves gets the geometry
-    // whose lanes hold it in one wave.  CXXDES_B200_MM1_GEOMETRY=0|1|2 forces one (A/B measurements).
+    // Geometry from the shard size (CXXDES_B200_MM1_GEOMETRY=0|1|2 forces one, for A/B measurements).
     int geo = 0;
-    if (n_replications > lanes_of<geometry0>(sm_count)) {
-        if (n_replications <= lanes_of<geometry1>(sm_count)) geo = 1;
-        else if (n_replications <= lanes_of<geometry2>(sm_count)) geo = 2;
+    {
+        const double rounds0 = (double)n_replications / (double)lanes_of<geometry0>(sm_count);
+        const double rounds1 = (double)n_replications / (double)lanes_of<geometry1>(sm_count);
+        // one round and a small remainder on geometry0, (nearly) whole rounds on geometry1
+        if (rounds0 > 1.0 && rounds0 < 1.34 && rounds1 <= 2.0) geo = 1;
     }
     if (const char *force = getenv("CXXDES_B200_MM1_GEOMETRY"))
         if (force[0] >= '0' && force[0] <= '2' && !force[1]) geo = force[0] - '0';

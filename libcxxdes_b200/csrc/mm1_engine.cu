@@ -7,6 +7,7 @@
 // (mm1_fused.cu) is cross-checked against, and it handles the degenerate n_packets < 2 cases.
 #include "device/models_common.cuh"
 #include "device/process.cuh"
+#include "device/trace.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -28,9 +29,11 @@ struct mm1_state {
 
 }  // namespace
 
+// ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
+template <typename ENV>
 __global__ void __launch_bounds__(128)
 mm1_engine_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, int64_t *ring_base,
-                  uint32_t ring_cap) {
+                  uint32_t ring_cap, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -46,8 +49,9 @@ mm1_engine_kernel(cxxdes_b200_mm1_params prm, shard sh, device_columns out, int6
 
     uint64_t rep;
     while (steal(sh, rep)) {
-        environment env;
+        ENV env;
         env.init(hkey, htag, HEAP_CAP);
+        attach_trace(env, sink);
         mm1_state st;
         st.main.init();
         st.prod.init();
@@ -154,7 +158,15 @@ size_t mm1_engine_smem_bytes(int threads) {
 
 cudaError_t launch_mm1_engine(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                               int64_t *ring, uint32_t ring_cap, int blocks, int threads, cudaStream_t stream) {
-    mm1_engine_kernel<<<blocks, threads, mm1_engine_smem_bytes(threads), stream>>>(prm, sh, out, ring, ring_cap);
+    mm1_engine_kernel<environment><<<blocks, threads, mm1_engine_smem_bytes(threads), stream>>>(prm, sh, out, ring, ring_cap,
+                                                                                             trace_sink{});
+    return cudaGetLastError();
+}
+
+// One replication (sh.n_replications == 1), one thread, with its event trace.
+cudaError_t launch_mm1_trace(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out, int64_t *ring,
+                             uint32_t ring_cap, const trace_sink &sink, cudaStream_t stream) {
+    mm1_engine_kernel<traced_environment><<<1, 32, mm1_engine_smem_bytes(32), stream>>>(prm, sh, out, ring, ring_cap, sink);
     return cudaGetLastError();
 }
 

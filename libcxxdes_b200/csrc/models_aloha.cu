@@ -14,6 +14,7 @@
 //                            erase; if (!collided) ++succ; timeout(exponential()) }
 #include "device/engine32.cuh"
 #include "device/models_common.cuh"
+#include "device/trace.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -48,9 +49,11 @@ __device__ __forceinline__ aloha_rep_params aloha_params_of(const cxxdes_b200_al
 
 // Generic-engine kernel: 64-bit keys, any parameter range.  Runs the whole shard, or (list != nullptr)
 // only the replications the compact kernel below handed back.
+// ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
+template <typename ENV>
 __global__ void __launch_bounds__(ALOHA_THREADS)
 aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, const uint32_t *list,
-             const unsigned long long *list_count, unsigned long long *list_cursor) {
+             const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -81,8 +84,9 @@ aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, const u
         addr.seed = sh.seed;
         addr.replication = grep;
 
-        environment env;
+        ENV env;
         env.init(hkey, htag, heap_cap);
+        attach_trace(env, sink);
         uint64_t active = 0, collided = 0, pc_tx = 0, pc_idle = 0;  // pc_tx: awaiting the frame timeout; pc_idle: awaiting the inter-arrival timeout
         uint64_t successful = 0;
         uint32_t main_pc = 0;
@@ -434,7 +438,7 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
                          int *launches, const aloha_saved &st) {
     const size_t smem = aloha_smem_bytes(prm.num_stations);
     if (smem > smem_optin) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(aloha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(aloha_kernel<environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -452,13 +456,23 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // the replications it handed back (normally none): exits at once when the list is empty
-        aloha_kernel<<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, sh.retry_list, sh.retry_count,
-                                                                         list_cursor);
+        aloha_kernel<environment><<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, sh.retry_list, sh.retry_count,
+                                                                                      list_cursor, trace_sink{});
         ++*launches;
         return cudaGetLastError();
     }
-    aloha_kernel<<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, nullptr, nullptr, nullptr);
+    aloha_kernel<environment><<<sm_count * per_sm, ALOHA_THREADS, smem, stream>>>(prm, sh, out, nullptr, nullptr, nullptr, trace_sink{});
     ++*launches;
+    return cudaGetLastError();
+}
+
+// One replication (sh.n_replications == 1) on the full-size kernel, with its event trace.
+cudaError_t launch_aloha_trace(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
+                               const trace_sink &sink, cudaStream_t stream) {
+    const size_t smem = aloha_smem_bytes(prm.num_stations);
+    cudaError_t e = cudaFuncSetAttribute(aloha_kernel<traced_environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    aloha_kernel<traced_environment><<<1, ALOHA_THREADS, smem, stream>>>(prm, sh, out, nullptr, nullptr, nullptr, sink);
     return cudaGetLastError();
 }
 

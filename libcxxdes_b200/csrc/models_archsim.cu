@@ -11,6 +11,7 @@
 // The block store is the model's (user code): an ordered array, eviction = least last_access,
 // lowest position on ties, erase keeps order (same rule as the oracle's model).
 #include "device/models_common.cuh"
+#include "device/trace.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -44,9 +45,10 @@ constexpr int ARCH_SAVED_HEADER = 24;
 // the all_of handler, statistics), the heap, the block store, the per-requester words and both wait lists -- and the
 // next launch continues from it; finished replications keep phase DONE.  Separate instantiations, so that the plain
 // run() path carries none of it.
-template <bool SINGLE, bool STATEFUL>
+// ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
+template <bool SINGLE, bool STATEFUL, typename ENV = environment>
 __global__ void __launch_bounds__(ARCH_THREADS)
-archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, archsim_saved st) {
+archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, archsim_saved st, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char *cursor = smem;
     const int K = SINGLE ? 1 : (int)prm.n_requesters;
@@ -87,8 +89,9 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
         addr.seed = sh.seed;
         addr.replication = grep;
 
-        environment env;
+        ENV env;
         env.init(hkey, htag, heap_cap);
+        attach_trace(env, sink);
         wait_list wait2, wait1;  // mutex::event_ of mem2 / mem1
         wait2.init(w2who, w2lat, K);
         wait1.init(w1who, w1lat, K);
@@ -383,7 +386,7 @@ cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &s
     auto go = [&](auto kernel, int per_sm) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out, st);
+        kernel<<<sm_count * per_sm, ARCH_THREADS, smem, stream>>>(prm, sh, out, st, trace_sink{});
         return cudaGetLastError();
     };
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -391,6 +394,17 @@ cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &s
     if (per_sm > 8) per_sm = 8;
     if (prm.n_requesters == 1) return st.words ? go(archsim_kernel<true, true>, per_sm) : go(archsim_kernel<true, false>, per_sm);
     return st.words ? go(archsim_kernel<false, true>, per_sm) : go(archsim_kernel<false, false>, per_sm);
+}
+
+// One replication (sh.n_replications == 1) with its event trace (the general k-requester instantiation).
+cudaError_t launch_archsim_trace(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
+                                 const trace_sink &sink, cudaStream_t stream) {
+    const size_t smem = archsim_smem_bytes(prm);
+    auto kernel = archsim_kernel<false, false, traced_environment>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<1, ARCH_THREADS, smem, stream>>>(prm, sh, out, archsim_saved{}, sink);
+    return cudaGetLastError();
 }
 
 }  // namespace cxb

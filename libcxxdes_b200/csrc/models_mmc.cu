@@ -13,6 +13,7 @@
 // [customer][thread] (lanes walk the customers roughly in step, so accesses coalesce).
 #include "device/engine32.cuh"
 #include "device/models_common.cuh"
+#include "device/trace.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -32,9 +33,11 @@ constexpr int C_T0_SHIFT = 16;
 
 // Generic-engine kernel: 64-bit keys, 96-entry heap and waiter list.  Runs the whole shard, or
 // (list != nullptr) only the replications the compact kernel below handed back.
+// ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
+template <typename ENV>
 __global__ void __launch_bounds__(MMC_THREADS)
 mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, const uint32_t *list,
-           const unsigned long long *list_count, unsigned long long *list_cursor) {
+           const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -65,8 +68,9 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
         addr.seed = sh.seed;
         addr.replication = grep;
 
-        environment env;
+        ENV env;
         env.init(hkey, htag, MMC_HEAP);
+        attach_trace(env, sink);
         wait_list waiters;  // the semaphore's event
         waiters.init(wwho, wlat, MMC_WAITERS);
         uint64_t value = prm.servers;  // semaphore{c, c}
@@ -541,7 +545,7 @@ cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
                        int *launches, const mmc_saved &st) {
     const size_t smem = mmc_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(mmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mmc_kernel<environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (mmc_fast_applies(prm, sh)) {
         const size_t fsmem = mmc_fast_smem_bytes();
@@ -555,13 +559,24 @@ cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        mmc_kernel<<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, sh.retry_list, sh.retry_count,
-                                                           list_cursor);
+        mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, sh.retry_list, sh.retry_count,
+                                                                        list_cursor, trace_sink{});
         ++*launches;
         return cudaGetLastError();
     }
-    mmc_kernel<<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr);
+    mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr, trace_sink{});
     ++*launches;
+    return cudaGetLastError();
+}
+
+// One replication (sh.n_replications == 1) on the full-size kernel, with its event trace.  `customer_state` needs
+// room for one block of the kernel (the handle's buffer always has).
+cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
+                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream) {
+    const size_t smem = mmc_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(mmc_kernel<traced_environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmc_kernel<traced_environment><<<1, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr, sink);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@
 
 #include "device/models_common.cuh"
 #include "device/program_tags.cuh"
+#include "device/trace.cuh"
 #include "kernels.h"
 
 namespace cxb {
@@ -502,9 +503,11 @@ struct interp {
 // are what buys throughput; a replication that overflows the small heap is redone by a second pass
 // with PRG_HEAP entries (list != nullptr: only the replications on the retry list).
 // The program text (ops, process table, rates, limits) is staged into shared memory when it fits.
+// TRACE: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
+template <bool TRACE>
 __global__ void __launch_bounds__(PRG_THREADS)
 program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap, uint32_t staged_bytes,
-               const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor) {
+               const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -580,6 +583,11 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             const uint32_t kind = hp1 ? TOKEN_HANDLER : (target != PTAG_NONE ? TOKEN_RESUME : TOKEN_NOOP);
             const uint32_t ordinal = target != PTAG_NONE ? prg.procs[target].ordinal : PROC_NONE;
             env.hash = trace_hash_step(env.hash, time, key_prio(t.key), kind, ordinal);
+            if constexpr (TRACE) {
+                traced_environment rec;
+                rec.sink = sink;
+                rec.record(env.n_events - 1, time, key_prio(t.key), kind, ordinal);
+            }
             if (hp1) it.invoke_handler(t);
             else if (target != PTAG_NONE) it.resume(target);
             if (env.status) break;
@@ -747,7 +755,7 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
     if (small > PRG_HEAP) small = PRG_HEAP;
     auto go = [&](int heap_cap, bool retry) -> cudaError_t {
         const size_t smem = program_smem_bytes(heap_cap, staged);
-        cudaError_t e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(program_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
@@ -755,9 +763,9 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
         // take what shared memory and the 40 registers per thread allow (12 blocks of 128 threads)
         if (per_sm > 12) per_sm = 12;
         if (const char *env = getenv("CXXDES_B200_PRG_BLOCKS")) { int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
-        program_kernel<<<sm_count * per_sm, PRG_THREADS, smem, stream>>>(
+        program_kernel<false><<<sm_count * per_sm, PRG_THREADS, smem, stream>>>(
             prg, sh, out, heap_cap, staged, retry ? sh.retry_list : nullptr, retry ? sh.retry_count : nullptr,
-            retry ? list_cursor : nullptr);
+            retry ? list_cursor : nullptr, trace_sink{});
         ++*launches;
         return cudaGetLastError();
     };
@@ -771,6 +779,17 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
     cudaError_t e = go(small, false);
     if (e != cudaSuccess || small == PRG_HEAP) return e;
     return go(PRG_HEAP, true);   // exits at once when nothing overflowed
+}
+
+// One replication (sh.n_replications == 1) on the full-size interpreter (full heap), with its event trace.
+cudaError_t launch_program_trace(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
+                                 const trace_sink &sink, cudaStream_t stream) {
+    const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
+    const size_t smem = program_smem_bytes(PRG_HEAP, staged);
+    cudaError_t e = cudaFuncSetAttribute(program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    program_kernel<true><<<1, PRG_THREADS, smem, stream>>>(prg, sh, out, PRG_HEAP, staged, nullptr, nullptr, nullptr, sink);
+    return cudaGetLastError();
 }
 
 }  // namespace cxb

@@ -61,10 +61,12 @@ def load_library():
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_pass_counts.argtypes = [H, C.POINTER(C.c_uint64 * 4)]
     lib.cxxdes_b200_kernel_name.argtypes = [H, C.c_char_p, C.c_size_t]
+    lib.cxxdes_b200_trace.argtypes = [H, C.c_uint64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
     for name in ("device_count", "version", "create", "check_program", "run", "run_until", "run_for", "sync", "fetch",
-                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "kernel_name", "reset", "destroy"):
+                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "kernel_name", "trace", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
     return lib
@@ -74,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_check_program", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
     "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_pass_counts",
-    "cxxdes_b200_kernel_name", "cxxdes_b200_reset",
+    "cxxdes_b200_kernel_name", "cxxdes_b200_trace", "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",
 ]
 
@@ -224,6 +226,21 @@ class Ensemble:
         n = C.c_uint64()
         _check(self._lib, self._lib.cxxdes_b200_launch_count(self._handle, C.byref(n)))
         return n.value
+
+    def trace(self, replication, max_events=4096, until=-1):
+        """(n_events, digest, [(time, priority, kind, process ordinal), ...]) of one replication of this shard: the tokens
+        environment::step popped, in order -- same shape as the oracle's trace (tests/oracles.py)."""
+        self._ensure()
+        t = np.zeros(max_events, np.int64)
+        p = np.zeros(max_events, np.int64)
+        k = np.zeros(max_events, np.uint32)
+        pr = np.zeros(max_events, np.uint32)
+        nw, total, digest = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._lib, self._lib.cxxdes_b200_trace(self._handle, int(replication), int(until), int(max_events),
+                                                      t.ctypes.data, p.ctypes.data, k.ctypes.data, pr.ctypes.data,
+                                                      C.byref(nw), C.byref(total), C.byref(digest)))
+        n = nw.value
+        return int(total.value), int(digest.value), list(zip(t[:n].tolist(), p[:n].tolist(), k[:n].tolist(), pr[:n].tolist()))
 
     def kernel_name(self):
         """The first-pass kernel instantiation a plain run() of this handle launches."""

@@ -361,7 +361,8 @@ def test_gpu_program_run_for_in_pieces_matches_oracle(port, name):
         # a replication that had finished before the last horizon T was left at now_ = T by run_until (environment.ipp:194)
         want.end_time[:] = np.maximum(want.end_time, n_pieces * piece)
         golden_util.assert_columns_equal(got, want, what=f"{name}: run() after the pieces")
-        ens.run_for(1000)                                  # exhausted: nothing left to run, nothing changes
+        ens.run_for(1000)                                  # exhausted: nothing left to dispatch, run_until(now() + 1000)
+        want.end_time[:] += 1000                           # only moves every replication's clock (environment.ipp:190-209)
         golden_util.assert_columns_equal(ens.fetch(), want, what=f"{name}: run_for after exhaustion")
     ens.close()
 

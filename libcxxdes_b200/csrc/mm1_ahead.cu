@@ -306,14 +306,13 @@ struct geometry {
     static constexpr size_t SMEM = TABLE_BYTES + (size_t)S * T * sizeof(uint2);
 };
 using geometry0 = geometry<256, 3, 32>;
-// A shard of 1.0 .. 1.33 times geometry0's 113 664 lanes (a 1 Mi ensemble split over 8 GPUs is 131 072 replications
-// per GPU = 1.15 rounds, which takes the time of 1.3): about half as many lanes make it two full rounds, each at
-// nearly twice the speed (the kernel is issue-bound: fewer resident warps, each faster).  [Measured and rejected:
-// more lanes with a 16-slot window and the two-level ring from the start, <128,7,16> and <256,4,16>: 15.5 and
-// 18.2 ms for 131 072 replications against 15.0 ms on geometry0 -- the spilling slot text and 64-72 registers cost
-// more than the partial round.]
-using geometry1 = geometry<224, 2, 32>;   // 66 304 lanes
-using geometry2 = geometry<448, 1, 32>;   // 66 304 lanes, one block per SM
+// Other geometries were measured for shards that are not a whole number of rounds of these 113 664 lanes (a 1 Mi
+// ensemble split over 8 GPUs is 131 072 replications per GPU = 1.15 rounds, 15.0 ms instead of the 12.8 ms of an
+// eighth of the full run) and none was kept (profiles/r02_mm1_geometry_ab.jsonl): more lanes with a 16-slot window
+// and the two-level ring from the start, <128,7,16> 15.5 ms and <256,4,16> 18.2 ms (the spilling slot text and
+// 64-72 registers cost more than the partial round); half as many lanes for two whole rounds, <224,2,32> 16.3 ms
+// and <448,1,32> 15.8 ms (one round of 14 resident warps per SM takes 7.8 ms against 11.5 ms for 24: 85 % of the
+// throughput, the kernel is not purely issue-bound down there).  A replication is an indivisible 11 ms unit of work.
 
 template <typename G>
 void fill_plan(mm1_fused_plan &p, int sm_count) {
@@ -322,26 +321,13 @@ void fill_plan(mm1_fused_plan &p, int sm_count) {
     p.ah_smem_bytes = G::SMEM;
     p.ah_ring_slots = G::RING_SLOTS;
 }
-template <typename G>
-uint64_t lanes_of(int sm_count) { return (uint64_t)sm_count * G::MIN_BLOCKS * G::THREADS; }
 }  // namespace
 
 void plan_mm1_ahead(mm1_fused_plan &p, const cxxdes_b200_mm1_params &prm, uint32_t queue_capacity, int sm_count,
                     int64_t tick_mult, int64_t ticks_per_unit, uint64_t n_replications) {
-    // Geometry from the shard size (CXXDES_B200_MM1_GEOMETRY=0|1|2 forces one, for A/B measurements).
-    int geo = 0;
-    {
-        const double rounds0 = (double)n_replications / (double)lanes_of<geometry0>(sm_count);
-        const double rounds1 = (double)n_replications / (double)lanes_of<geometry1>(sm_count);
-        // one round and a small remainder on geometry0, (nearly) whole rounds on geometry1
-        if (rounds0 > 1.0 && rounds0 < 1.34 && rounds1 <= 2.0) geo = 1;
-    }
-    if (const char *force = getenv("CXXDES_B200_MM1_GEOMETRY"))
-        if (force[0] >= '0' && force[0] <= '2' && !force[1]) geo = force[0] - '0';
-    p.ah_geometry = geo;
-    if (geo == 1) fill_plan<geometry1>(p, sm_count);
-    else if (geo == 2) fill_plan<geometry2>(p, sm_count);
-    else fill_plan<geometry0>(p, sm_count);
+    (void)n_replications;
+    p.ah_geometry = 0;
+    fill_plan<geometry0>(p, sm_count);
     const uint32_t window = p.ah_ring_slots - 1;  // one slot holds the arrival key after the last packet
     // Stationary P(queue length > Q) = rho^(Q+1) per arrival; the window also holds the packets
     // generated ahead (2 to 4).  When more than ~0.1% of the replications are expected to outgrow
@@ -464,8 +450,7 @@ void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_pa
 }  // namespace
 
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
-    if (plan.ah_geometry == 1) return configure_geometry<geometry1>();
-    if (plan.ah_geometry == 2) return configure_geometry<geometry2>();
+    (void)plan;
     return configure_geometry<geometry0>();
 }
 
@@ -524,16 +509,8 @@ cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh,
     mm1::constants c;
     const int mode = constants_and_mode(c, prm, sh, plan);
     pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
-    if (plan.ah_geometry == 1) {
-        if (spill) launch_geometry<geometry1, true>(mode, c, prm, sh, out, plan, a, stream);
-        else launch_geometry<geometry1, false>(mode, c, prm, sh, out, plan, a, stream);
-    } else if (plan.ah_geometry == 2) {
-        if (spill) launch_geometry<geometry2, true>(mode, c, prm, sh, out, plan, a, stream);
-        else launch_geometry<geometry2, false>(mode, c, prm, sh, out, plan, a, stream);
-    } else {
-        if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
-        else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
-    }
+    if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
+    else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
     return cudaGetLastError();
 }
 

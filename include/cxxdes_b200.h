@@ -268,8 +268,11 @@ typedef struct cxxdes_b200_config {
 enum {
     CXXDES_B200_FLAG_GENERIC_ENGINE = 1u, /* use the generic token-heap engine kernel even when a
                                              fused model kernel exists (parity cross-check)    */
-    CXXDES_B200_FLAG_MM1_LOCKSTEP = 2u    /* M/M/1: first pass by the draw-on-demand kernel instead
+    CXXDES_B200_FLAG_MM1_LOCKSTEP = 2u,   /* M/M/1: first pass by the draw-on-demand kernel instead
                                              of the generate-ahead kernel (A/B measurements)   */
+    CXXDES_B200_FLAG_COOP_HEAP = 4u       /* ALOHA: first pass by the kernel whose event heaps are operated by groups of 8
+                                             lanes (sub-warp cooperative push / pop with ballots) instead of one thread
+                                             per replication (A/B measurements; identical results) */
 };
 
 /* Number of CUDA devices visible (0 and an error string when there is none). */

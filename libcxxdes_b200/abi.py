@@ -25,6 +25,7 @@ INHERIT64 = 2 ** 63 - 1          # priority_consts::inherit (defs.ipp:35)
 CMP = {"==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
 FLAG_GENERIC_ENGINE = 1
 FLAG_MM1_LOCKSTEP = 2
+FLAG_COOP_HEAP = 4
 
 
 class Clock(C.Structure):

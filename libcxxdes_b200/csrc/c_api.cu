@@ -335,13 +335,14 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             // run_until / run_for continue where the previous piece stopped when the 32-bit kernel runs the model
             aloha_saved st{};
             st.n_replications = e->cfg.n_replications;
-            if (aloha_keeps_state(e->params.aloha, sh)) {
+            const bool coop = (e->cfg.flags & CXXDES_B200_FLAG_COOP_HEAP) != 0;   // keeps no state: pieces replay from tick 0
+            if (!coop && aloha_keeps_state(e->params.aloha, sh)) {
                 rc = saved_state_for(e, until, aloha_saved_words(e->params.aloha), &st.words, &st.resume);
                 if (rc) return rc;
             }
             wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
-                                  &launches, st));
+                                  &launches, st, coop));
             break;
         }
         case CXXDES_B200_MODEL_MMC: {
@@ -428,6 +429,8 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
     if (!cfg->params || cfg->params_size != want)
         return fail(CXXDES_B200_ERR_INVALID, "params_size %zu does not match model %d (%zu)", cfg->params_size,
                     cfg->model, want);
+    if ((cfg->flags & CXXDES_B200_FLAG_COOP_HEAP) && cfg->model != CXXDES_B200_MODEL_ALOHA)
+        return fail(CXXDES_B200_ERR_INVALID, "CXXDES_B200_FLAG_COOP_HEAP: only the ALOHA model has a cooperative-heap kernel");
     if (cfg->n_replications == 0 || cfg->n_replications > 0xFFFFFFFFull)
         return fail(CXXDES_B200_ERR_INVALID, "n_replications must be in [1, 2^32)");
     const cxxdes_b200_clock &ck = cfg->clock;
@@ -787,7 +790,8 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
             }
             break;
         case CXXDES_B200_MODEL_ALOHA:
-            snprintf(buf, buf_size, aloha_keeps_state(e->params.aloha, sh) ? "aloha_fast_kernel<false>" : "aloha_kernel");
+            snprintf(buf, buf_size, !aloha_keeps_state(e->params.aloha, sh) ? "aloha_kernel"
+                                    : (e->cfg.flags & CXXDES_B200_FLAG_COOP_HEAP) ? "aloha_coop_kernel" : "aloha_fast_kernel<false>");
             break;
         case CXXDES_B200_MODEL_MMC:
             snprintf(buf, buf_size, mmc_keeps_state(e->params.mmc, sh) ? "mmc_fast_kernel<false>" : "mmc_kernel");

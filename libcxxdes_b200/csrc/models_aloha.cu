@@ -435,7 +435,7 @@ size_t aloha_saved_words(const cxxdes_b200_aloha_params &prm) { return 16 + 2 * 
 
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                          int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
-                         int *launches, const aloha_saved &st) {
+                         int *launches, const aloha_saved &st, bool coop) {
     const size_t smem = aloha_smem_bytes(prm.num_stations);
     if (smem > smem_optin) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(aloha_kernel<environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -450,8 +450,15 @@ cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, c
         if (e != cudaSuccess) return e;
         const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
         const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
-        if (st.words) aloha_fast_kernel<true><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
-        else aloha_fast_kernel<false><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
+        if (coop && !st.words) {
+            // first pass with the event heap of a replication operated by a group of 8 lanes (models_aloha_coop.cu)
+            e = launch_aloha_coop(prm, sh, out, sm_count, stream);
+            if (e != cudaSuccess) return e;
+        } else if (st.words) {
+            aloha_fast_kernel<true><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
+        } else {
+            aloha_fast_kernel<false><<<sm_count * AF_BLOCKS_PER_SM, AF_THREADS, fsmem, stream>>>(prm, sh, out, keys, until, st);
+        }
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

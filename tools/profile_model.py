@@ -29,13 +29,15 @@ params, reps, clock = CONFIGS[name]
 if len(sys.argv) > 2:
     reps = int(sys.argv[2])
 runs = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-ens = L.Ensemble(params, reps, seed=0x5EED)
+import os
+flags = int(os.environ.get("CXB_FLAGS", "0"))   # e.g. 4 = CXXDES_B200_FLAG_COOP_HEAP
+ens = L.Ensemble(params, reps, seed=0x5EED, flags=flags)
 ens.time_unit(*clock[0]).time_precision(*clock[1])
 for _ in range(runs):
     ens.run().sync()
     acc, _ = ens.reduce()
     ms = ens.last_run_ms()
-    print(f"{name}: {reps} replications, {acc.n_events} events, {ms:.3f} ms, {acc.n_events / ms / 1e6:.2f} Gev/s, "
+    print(f"{name} [{ens.kernel_name()}]: {reps} replications, {acc.n_events} events, {ms:.3f} ms, {acc.n_events / ms / 1e6:.2f} Gev/s, "
           f"errors {acc.n_errors}", flush=True)
 ens.close()
 

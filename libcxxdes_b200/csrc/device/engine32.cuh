@@ -145,6 +145,78 @@ struct environment32 {
         return top;
     }
 
+    // ---- the same two operations as straight-line code --------------------------------------------------------------
+    // One thread per replication means a warp's 32 heaps are at 32 different places of their sifts; as loops, every
+    // lane waits for the deepest one and the dependent chains of the divergent paths run one after the other.  Here a
+    // sift is LEVELS predicated steps (LEVELS = depth of the deepest index the heap can have), no branch: all lanes
+    // run the same instructions, and the compiler is free to interleave them with whatever else the event needs (the
+    // variate of the next timeout does not depend on the heap).  Exactly the moves of pop_top() / schedule().
+    template <int LEVELS>
+    __device__ __forceinline__ token32 pop_flat() {
+        const uint2 first = heap[0];
+        token32 top;
+        top.time = first.x;
+        top.tag = first.y;
+        const int len = n - 1;                               // n >= 1
+        const uint2 v = heap[len * STRIDE];
+        const int two_children = (len - 1) >> 1;             // holes below this index have two children (-1 when len == 0)
+        int hole = 0;
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            const bool go = hole < two_children;
+            const int right = go ? 2 * hole + 2 : 1;         // (a lane that has arrived reads entries 0 and 1, harmlessly)
+            const uint2 er = heap[right * STRIDE], el = heap[(right - 1) * STRIDE];
+            const bool left = er.x > el.x;                   // right strictly later than left -> take left; tie -> right
+            const uint2 pick = left ? el : er;
+            if (go) {
+                heap[hole * STRIDE] = pick;
+                hole = right - (left ? 1 : 0);
+            }
+        }
+        if ((len & 1) == 0 && len > 0 && hole == (len - 2) / 2) {   // a lone left child at the bottom
+            heap[hole * STRIDE] = heap[(2 * hole + 1) * STRIDE];
+            hole = 2 * hole + 1;
+        }
+        // __push_heap of the displaced last element: it came from the bottom level and nearly always stays there
+        if (len > 0) {
+            while (hole > 0) {
+                const int parent = (hole - 1) >> 1;
+                const uint2 pe = heap[parent * STRIDE];
+                if (!(pe.x > v.x)) break;
+                heap[hole * STRIDE] = pe;
+                hole = parent;
+            }
+            heap[hole * STRIDE] = v;
+        }
+        n = len;
+        return top;
+    }
+
+    // schedule(time, tag) if `push`, as LEVELS predicated sift-up steps.
+    template <int LEVELS>
+    __device__ __forceinline__ void schedule_flat(bool push, uint32_t time, uint32_t tag) {
+        if (push && n >= cap) {
+            status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            push = false;
+        }
+        int hole = n;
+        bool moving = push;
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            const int parent = hole > 0 ? (hole - 1) >> 1 : 0;
+            const uint2 pe = heap[parent * STRIDE];
+            moving = moving && hole > 0 && pe.x > time;      // comp(parent, value): parent strictly later
+            if (moving) {
+                heap[hole * STRIDE] = pe;
+                hole = parent;
+            }
+        }
+        if (push) {
+            heap[hole * STRIDE] = make_uint2(time, tag);
+            ++n;
+        }
+    }
+
     // First half of environment::step (environment.ipp:117-126): pop, advance the clock, count.
     // The caller folds the token into the digest (it knows the tag layout).
     __device__ __forceinline__ token32 step_pop() {
@@ -162,4 +234,120 @@ struct environment32 {
     __device__ __forceinline__ uint32_t next_time() const { return heap[0].x; }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// heap32x: the same heap (same layout, same libstdc++ moves) addressed through 32-bit shared-memory addresses with
+// explicit ld/st.shared.  Through a generic `uint2 *` the compiler spends 5-7 instructions per entry on 64-bit address
+// arithmetic (measured with ncu per source line: the two child loads of a sift-down level cost 9.6 thread instructions);
+// here an entry's address is base + index * ENTRY_BYTES in one 32-bit multiply-add, children and parents follow from the
+// hole's byte offset by shifts, and neighbouring entries use immediate offsets.  All accesses are volatile asm
+// statements (kept in program order among themselves); kernels that use this type touch their heap through it only.
+// ---------------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+struct heap32x {
+    static constexpr uint32_t EB = (uint32_t)STRIDE * 8u;   // bytes between consecutive entries of one replication
+    static_assert((EB & (EB - 1u)) == 0, "the parent offset is a shift and a mask: entries a power of two apart");
+    uint32_t now;
+    uint32_t n_events;
+    uint64_t hash;
+    uint32_t status;
+    uint32_t n;      // heap size
+    uint32_t cap;
+    uint32_t base;   // shared-memory address of entry 0 of this thread's column
+
+    __device__ __forceinline__ void init(uint2 *column, int capacity) {
+        now = 0;
+        n_events = 0;
+        hash = TRACE_HASH_INIT;
+        status = 0;
+        n = 0;
+        cap = (uint32_t)capacity;
+        base = (uint32_t)__cvta_generic_to_shared(column);
+    }
+    static __device__ __forceinline__ uint2 lds(uint32_t addr) {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void sts(uint32_t addr, uint2 v) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y));
+    }
+    __device__ __forceinline__ uint2 entry(uint32_t index) const { return lds(base + index * EB); }
+    __device__ __forceinline__ void set_entry(uint32_t index, uint2 v) const { sts(base + index * EB, v); }
+
+    // std::__push_heap from the hole at byte offset `h` (stl_heap.h:135-148; comp(parent, value) = parent strictly later).
+    // Parent and grandparent are loaded in one round trip and two levels decided per trip (as environment32::sift_up:
+    // with three or four resident warps per scheduler the kernels wait on these dependent round trips).
+    static __device__ __forceinline__ uint32_t parent_of(uint32_t h) { return ((h - EB) >> 1) & ~(EB - 1u); }
+    __device__ __forceinline__ void sift_up(uint32_t h, uint32_t time, uint32_t tag) const {
+        while (h != 0) {
+            const uint32_t ph = parent_of(h);
+            const uint32_t gh = ph != 0 ? parent_of(ph) : 0u;
+            const uint2 pe = lds(base + ph), ge = lds(base + gh);
+            if (!(pe.x > time)) break;
+            sts(base + h, pe);
+            h = ph;
+            if (ph == 0 || !(ge.x > time)) break;
+            sts(base + h, ge);
+            h = gh;
+        }
+        sts(base + h, make_uint2(time, tag));
+    }
+
+    // environment::schedule_token, environment.ipp:94-98 (vector::push_back + push_heap).
+    __device__ __forceinline__ void schedule(uint32_t time, uint32_t tag) {
+        if (n >= cap) {
+            status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            return;
+        }
+        sift_up(n * EB, time, tag);
+        ++n;
+    }
+
+    // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back.  `first` = entry 0,
+    // which the caller has already loaded (it decodes the event from it before the moves).
+    __device__ __forceinline__ void pop_after_top() {
+        const uint32_t len = n - 1;
+        if (len > 0) {
+            const uint2 v = lds(base + len * EB);
+            const uint32_t two = ((len - 1) >> 1) * EB;          // holes below this offset have two children
+            uint32_t h = 0;
+            while (h < two) {
+                const uint32_t r = 2 * h + 2 * EB;              // right child
+                const uint2 er = lds(base + r), el = lds(base + r - EB);   // (one address, two immediate offsets)
+                if (r < two) {
+                    // both children have two children themselves: their four children come in the same round trip and
+                    // two levels are decided (the moves of two turns of the one-level loop)
+                    const uint32_t g = base + 2 * r;            // left child's right child; the others are EB apart
+                    const uint2 grr = lds(g + 2 * EB), grl = lds(g + EB), glr = lds(g), gll = lds(g - EB);
+                    const bool left = er.x > el.x;              // right strictly later than left -> take left; tie -> right
+                    const uint32_t c = left ? r - EB : r;
+                    sts(base + h, left ? el : er);
+                    const uint2 gr = left ? glr : grr, gl = left ? gll : grl;
+                    const bool left2 = gr.x > gl.x;
+                    sts(base + c, left2 ? gl : gr);
+                    h = 2 * c + (left2 ? EB : 2 * EB);
+                    continue;
+                }
+                const bool left = er.x > el.x;
+                sts(base + h, left ? el : er);
+                h = left ? r - EB : r;
+            }
+            if ((len & 1u) == 0 && h == ((len - 2) >> 1) * EB) {  // a lone left child at the bottom
+                const uint32_t c = 2 * h + EB;
+                sts(base + h, lds(base + c));
+                h = c;
+            }
+            sift_up(h, v.x, v.y);
+        }
+        n = len;
+    }
+
+    __device__ __forceinline__ void fold(uint32_t time, uint32_t kind, uint32_t proc) {
+        hash = trace_hash_step(hash, (int64_t)time, 0, kind, proc);
+    }
+    __device__ __forceinline__ bool has_event() const { return n > 0; }
+    __device__ __forceinline__ uint32_t next_time() const { return lds(base).x; }
+};
+
 }  // namespace cxb
+

@@ -207,7 +207,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
 
     const int64_t frame_ticks = real_to_sim_f32(prm.frame_time, sh.clk);  // env.timeout(float), aloha.cpp:60
 
-    environment32<AF_THREADS> env;
+    heap32x<AF_THREADS> env;   // (every access to the heap goes through env: explicit ld/st.shared)
     env.init(heap, heap_cap);
     uint64_t rep = 0, active_set = 0, collided = 0, pc_tx = 0;
     uint32_t successful = 0, main_pc = 0, remaining = 0, ctr2 = 0, ctr3 = 0;
@@ -217,9 +217,30 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
     float s_result = 0.0f, g_result = 0.0f;
     bool active = false, exhausted = false;
 
+    // Longest first: the replications of a load sweep differ 30x in length (packets per station = G * 1000,
+    // aloha.cpp:101), and a lane that draws a long one near the end of the work list keeps its whole warp -- 31 idle
+    // lanes -- running for up to a third of the launch.  So the work list is walked from the heaviest sweep step down:
+    // claim k stands for member k % per_step of step (S - 1 - k / per_step); the tail of the launch is then made of
+    // the shortest replications.  (Which replication a lane runs never changes a result: the Philox key is the global id.)
+    const uint32_t S = prm.sweep_steps > 1 ? prm.sweep_steps : 1u;
+    const uint64_t per_step = (sh.n_replications + S - 1) / S;
+    const uint64_t claim_limit = per_step * S;
+    const bool descending = prm.lambda_end >= prm.lambda_begin;
+    const uint32_t first_step = (uint32_t)(sh.first_replication % S);
+
     for (;;) {
         if (!active && !exhausted) {
-            if (steal(sh, rep)) {
+            const unsigned long long claim = atomicAdd(sh.work_counter, 1ULL);
+            bool claimed = claim < claim_limit;
+            if (claimed) {
+                const uint32_t rank = (uint32_t)(claim / per_step);
+                const uint32_t step = descending ? S - 1 - rank : rank;
+                rep = (uint64_t)((step + S - first_step) % S) + (claim % per_step) * S;
+                claimed = rep < sh.n_replications;     // (the steps do not all have per_step members)
+            } else {
+                exhausted = true;
+            }
+            if (claimed) {
                 const uint32_t phase = STATEFUL && st.resume ? st.words[rep] : 0u;
                 if (STATEFUL && phase == AF_PHASE_DONE) {   // now_ = max(now_, t), environment.ipp:194
                     if (sh.run_until >= 0 && out.end_time[rep] < sh.run_until) out.end_time[rep] = sh.run_until;
@@ -238,7 +259,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                     if (STATEFUL && phase == AF_PHASE_SAVED) {
                         const uint32_t *sv = st.words + rep;
                         const size_t n = st.n_replications;
-                        env.n = (int)sv[1 * n];
+                        env.n = sv[1 * n];
                         env.now = sv[2 * n];
                         env.n_events = sv[3 * n];
                         env.hash = (uint64_t)sv[4 * n] | ((uint64_t)sv[5 * n] << 32);
@@ -249,8 +270,8 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                         main_pc = sv[13 * n] & 0xFFu;
                         armed = (sv[13 * n] >> 8) != 0;
                         remaining = sv[14 * n];
-                        for (int k = 0; k < env.n; ++k)
-                            heap[k * AF_THREADS] = make_uint2(sv[(size_t)(16 + 2 * k) * n], sv[(size_t)(17 + 2 * k) * n]);
+                        for (uint32_t k = 0; k < env.n; ++k)
+                            env.set_entry(k, make_uint2(sv[(size_t)(16 + 2 * k) * n], sv[(size_t)(17 + 2 * k) * n]));
                     } else {
                         active_set = collided = pc_tx = 0;
                         successful = 0; main_pc = 0; remaining = 0; armed = false;
@@ -266,8 +287,6 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                         active = false;
                     }
                 }
-            } else {
-                exhausted = true;
             }
         }
         // (a claimed replication can leave the lane inactive -- finished in an earlier piece, handed to the
@@ -278,69 +297,70 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
         }
 
         if (active) {
-            const token32 t = env.step_pop();  // environment::step, environment.ipp:117-126
-            const uint32_t code = t.tag & CODE_MASK;
-            // Every event but co_main's first pushes exactly one token; the branches below only
-            // decide which (delay, tag), and the push itself -- the sift through the heap -- is one
-            // piece of code all lanes run together.
-            int64_t delay = 0;
-            uint32_t push_tag = CODE_NOOP;
-            bool push = true;
-            if (code - 1u < 64u) {
-                // station, aloha.cpp:51-71
-                env.fold(t.time, TOKEN_RESUME, code);
-                const uint64_t bit = 1ULL << (code - 1);
-                const uint32_t i = t.tag >> COUNTER_SHIFT;
-                if (pc_tx & bit) {
-                    // frame finished: erase, count, draw the waiting time (:62-69); the for loop's ++i
-                    // happens when the station resumes, nothing looks at i before that
-                    pc_tx &= ~bit;
-                    active_set &= ~bit;
-                    if (!(collided & bit)) ++successful;
-                    const philox_block b = philox4x32_10_scheduled(i >> 1, code, ctr2, ctr3, keys);
-                    const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
-                    const double wait = exponential_from_bits(bits, rate, table);
-                    delay = real_to_sim(wait, sh.clk);
-                    push_tag = code | ((i + 1) << COUNTER_SHIFT);
-                } else if (i < rp.pps) {
-                    // collided = false; insert; check_collisions (:55-59,73-78)
-                    collided &= ~bit;
-                    active_set |= bit;
-                    if (__popcll(active_set) > 1) collided |= active_set;
-                    pc_tx |= bit;
-                    delay = frame_ticks;
-                    push_tag = t.tag;
-                } else {
-                    push_tag = CODE_HANDLER;  // co_return -> completion token with the all_of handler
-                }
-            } else if (code == CODE_HANDLER) {
-                // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time
-                // (== now: completions are scheduled at now + 0)
-                env.fold(t.time, TOKEN_HANDLER, 0);
-                --remaining;
-                push = armed && remaining == 0;
-                if (push) armed = false;
-                push_tag = CODE_MAIN;
-            } else if (code == CODE_MAIN) {
-                env.fold(t.time, TOKEN_RESUME, 0);
+            // ---- one event, branch-light: the token at the root decides everything the event does, so it is decoded
+            // first; the variate a station draws when its frame ends is computed for EVERY event (half of them use
+            // it: a branch would run it for half of the lanes at the same cost and serialise it with the heap moves
+            // it does not depend on); the event's effects are selects.  The sifts stay loops: a sift-down has the
+            // same trip count in every lane (the heaps hold N or N + 1 tokens), and the predicated fixed-depth
+            // sift-up that was tried (engine32.cuh schedule_flat) costs 78 instructions for every lane where the loop
+            // costs ~7 per level actually climbed.
+            const uint2 root = env.entry(0);
+            const uint32_t code = root.y & CODE_MASK;
+            const uint32_t i = root.y >> COUNTER_SHIFT;
+            const philox_block b = philox4x32_10_scheduled(i >> 1, code, ctr2, ctr3, keys);
+            const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
+            const int64_t wait_ticks = real_to_sim(exponential_from_bits(bits, rate, table), sh.clk);
+
+            env.pop_after_top();                                   // environment::step, environment.ipp:117-126
+            token32 t;
+            t.time = root.x;
+            t.tag = root.y;
+            env.now = t.time > env.now ? t.time : env.now;
+            ++env.n_events;
+
+            const bool is_station = code - 1u < 64u;
+            const bool is_handler = code == CODE_HANDLER, is_main = code == CODE_MAIN;
+            const uint64_t bit = is_station ? 1ULL << ((code - 1u) & 63u) : 0ULL;
+            // station, aloha.cpp:51-71
+            const bool tx_end = (pc_tx & bit) != 0;                          // frame finished: erase, count, draw (:62-69)
+            const bool tx_start = is_station && !tx_end && i < rp.pps;       // collided = false; insert; check (:55-59,73-78)
+            const bool st_return = is_station && !tx_end && !(i < rp.pps);   // co_return -> completion with the all_of handler
+            successful += (tx_end && !(collided & bit)) ? 1u : 0u;
+            pc_tx = tx_end ? pc_tx & ~bit : (tx_start ? pc_tx | bit : pc_tx);
+            active_set = tx_end ? active_set & ~bit : (tx_start ? active_set | bit : active_set);
+            collided = tx_start ? collided & ~bit : collided;
+            collided |= (tx_start && __popcll(active_set) > 1) ? active_set : 0ULL;
+            // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time (== now)
+            remaining -= is_handler ? 1u : 0u;
+            const bool fire = is_handler && armed && remaining == 0;
+            armed = armed && !fire;
+            // digest: kind and process of the popped token
+            const uint32_t kind = is_handler ? (uint32_t)TOKEN_HANDLER : ((is_station || is_main) ? (uint32_t)TOKEN_RESUME : (uint32_t)TOKEN_NOOP);
+            const uint32_t proc = is_station ? code : ((is_handler || is_main) ? 0u : (uint32_t)PROC_NONE);
+            env.fold(t.time, kind, proc);
+
+            bool push = is_station || fire;
+            int64_t delay = tx_end ? wait_ticks : (tx_start ? frame_ticks : 0);
+            uint32_t push_tag = tx_end ? (code | ((i + 1) << COUNTER_SHIFT)) : (tx_start ? root.y : (st_return ? CODE_HANDLER : CODE_MAIN));
+            if (is_main) {   // twice per replication
                 if (main_pc == 0) {
                     // co_main, aloha.cpp:39-44: bind stations in index order, one all_of handler
                     for (int s = 0; s < N; ++s) env.schedule(env.now, (uint32_t)(1 + s));
                     remaining = (uint32_t)N;
                     armed = true;
                     main_pc = 1;
-                    push = false;
                 } else {
                     // :46-47  S = succ / now_seconds() (size_t / double -> float), G = lambda * frame_time
                     s_result = (float)((double)successful / sim_to_seconds((int64_t)env.now, sh.clk));
                     g_result = rp.lambda * prm.frame_time;
-                    // co_main returns: null-target completion
+                    push = true;             // co_main returns: null-target completion
+                    push_tag = CODE_NOOP;
                 }
-            } else {
-                env.fold(t.time, TOKEN_NOOP, PROC_NONE);
-                push = false;
             }
-            if (push) env.schedule_after(delay, push_tag);
+            // token at now + delay; the sum must stay inside 32 bits
+            const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
+            if (push && ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull)) env.status |= CXXDES_B200_REP_TIME_RANGE;
+            if (push) env.schedule((uint32_t)when, push_tag);
 
             // environment::run / run_until (environment.ipp:179-196)
             if (env.status || !env.has_event() || env.next_time() > until) {
@@ -361,7 +381,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                         uint32_t *sv = st.words + rep;
                         const size_t n = st.n_replications;
                         if (o.status & CXXDES_B200_REP_UNFINISHED) {
-                            sv[1 * n] = (uint32_t)env.n;
+                            sv[1 * n] = env.n;
                             sv[2 * n] = (uint32_t)end;      // run_until leaves now_ at the horizon
                             sv[3 * n] = env.n_events;
                             sv[4 * n] = (uint32_t)env.hash;
@@ -375,8 +395,8 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
                             sv[12 * n] = successful;
                             sv[13 * n] = main_pc | ((armed ? 1u : 0u) << 8);
                             sv[14 * n] = remaining;
-                            for (int k = 0; k < env.n; ++k) {
-                                const uint2 e = heap[k * AF_THREADS];
+                            for (uint32_t k = 0; k < env.n; ++k) {
+                                const uint2 e = env.entry(k);
                                 sv[(size_t)(16 + 2 * k) * n] = e.x;
                                 sv[(size_t)(17 + 2 * k) * n] = e.y;
                             }

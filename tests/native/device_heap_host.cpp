@@ -38,7 +38,7 @@ struct ref_comp {   // token_comp: a is "less" (pops later) when it is strictly 
     }
 };
 
-int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span) {
+int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span, bool flat = false) {
     std::mt19937 rng(seed);
     std::vector<uint2> storage(capacity);
     environment32<1> env;
@@ -49,11 +49,20 @@ int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span) {
         const bool push = ref.empty() || ((int)ref.size() < capacity && rng() % 100 < 55);
         if (push) {
             const uint32_t t = now + rng() % time_span;       // few distinct times: many ties
-            env.schedule(t, next_tag);
+            // (flat: the straight-line pop / push, LEVELS = 7 covers indices below 255)
+            if (flat) env.schedule_flat<7>(true, t, next_tag);
+            else env.schedule(t, next_tag);
             ref.push(ref_token{t, 0, next_tag});
             ++next_tag;
         } else {
-            const token32 got = env.step_pop();
+            if (flat && (rng() & 3) == 0) env.schedule_flat<7>(false, now, 0);   // a push that is predicated off changes nothing
+            token32 got;
+            if (flat) {
+                got = env.pop_flat<7>();
+                env.now = got.time > env.now ? got.time : env.now;
+            } else {
+                got = env.step_pop();
+            }
             const ref_token want = ref.top();
             ref.pop();
             if (got.time != want.time || got.tag != want.tag) {
@@ -111,8 +120,9 @@ int main() {
         for (int capacity : {2, 3, 7, 8, 33, 64, 66, 200}) {
             for (uint32_t span : {1u, 2u, 5u, 1000u}) {
                 bad += check32(seed * 7919u + capacity, capacity, 3000, span);
+                bad += check32(seed * 15485863u + capacity, capacity, 3000, span, true);
                 bad += check64(seed * 104729u + capacity, capacity, 3000, span);
-                ops += 6000;
+                ops += 9000;
             }
         }
     }

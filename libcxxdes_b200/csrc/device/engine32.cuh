@@ -238,14 +238,13 @@ struct environment32 {
 // heap32x: the same heap (same layout, same libstdc++ moves) addressed through 32-bit shared-memory addresses with
 // explicit ld/st.shared.  Through a generic `uint2 *` the compiler spends 5-7 instructions per entry on 64-bit address
 // arithmetic (measured with ncu per source line: the two child loads of a sift-down level cost 9.6 thread instructions);
-// here an entry's address is base + index * ENTRY_BYTES in one 32-bit multiply-add, children and parents follow from the
-// hole's byte offset by shifts, and neighbouring entries use immediate offsets.  All accesses are volatile asm
+// here an entry's address is base + index * ENTRY_BYTES in one 32-bit multiply-add and neighbouring entries use
+// immediate offsets.  All accesses are volatile asm
 // statements (kept in program order among themselves); kernels that use this type touch their heap through it only.
 // ---------------------------------------------------------------------------------------------------------------
 template <int STRIDE>
 struct heap32x {
     static constexpr uint32_t EB = (uint32_t)STRIDE * 8u;   // bytes between consecutive entries of one replication
-    static_assert((EB & (EB - 1u)) == 0, "the parent offset is a shift and a mask: entries a power of two apart");
     uint32_t now;
     uint32_t n_events;
     uint64_t hash;
@@ -271,26 +270,26 @@ struct heap32x {
     static __device__ __forceinline__ void sts(uint32_t addr, uint2 v) {
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y));
     }
-    __device__ __forceinline__ uint2 entry(uint32_t index) const { return lds(base + index * EB); }
-    __device__ __forceinline__ void set_entry(uint32_t index, uint2 v) const { sts(base + index * EB, v); }
+    __device__ __forceinline__ uint32_t at(uint32_t index) const { return base + index * EB; }
+    __device__ __forceinline__ uint2 entry(uint32_t index) const { return lds(at(index)); }
+    __device__ __forceinline__ void set_entry(uint32_t index, uint2 v) const { sts(at(index), v); }
 
-    // std::__push_heap from the hole at byte offset `h` (stl_heap.h:135-148; comp(parent, value) = parent strictly later).
+    // std::__push_heap from the hole at index `hole` (stl_heap.h:135-148; comp(parent, value) = parent strictly later).
     // Parent and grandparent are loaded in one round trip and two levels decided per trip (as environment32::sift_up:
     // with three or four resident warps per scheduler the kernels wait on these dependent round trips).
-    static __device__ __forceinline__ uint32_t parent_of(uint32_t h) { return ((h - EB) >> 1) & ~(EB - 1u); }
-    __device__ __forceinline__ void sift_up(uint32_t h, uint32_t time, uint32_t tag) const {
-        while (h != 0) {
-            const uint32_t ph = parent_of(h);
-            const uint32_t gh = ph != 0 ? parent_of(ph) : 0u;
-            const uint2 pe = lds(base + ph), ge = lds(base + gh);
+    __device__ __forceinline__ void sift_up(uint32_t hole, uint32_t time, uint32_t tag) const {
+        while (hole != 0) {
+            const uint32_t parent = (hole - 1) >> 1;
+            const uint32_t grand = parent != 0 ? (parent - 1) >> 1 : 0u;
+            const uint2 pe = lds(at(parent)), ge = lds(at(grand));
             if (!(pe.x > time)) break;
-            sts(base + h, pe);
-            h = ph;
-            if (ph == 0 || !(ge.x > time)) break;
-            sts(base + h, ge);
-            h = gh;
+            sts(at(hole), pe);
+            hole = parent;
+            if (parent == 0 || !(ge.x > time)) break;
+            sts(at(hole), ge);
+            hole = grand;
         }
-        sts(base + h, make_uint2(time, tag));
+        sts(at(hole), make_uint2(time, tag));
     }
 
     // environment::schedule_token, environment.ipp:94-98 (vector::push_back + push_heap).
@@ -299,45 +298,46 @@ struct heap32x {
             status |= CXXDES_B200_REP_HEAP_OVERFLOW;
             return;
         }
-        sift_up(n * EB, time, tag);
+        sift_up(n, time, tag);
         ++n;
     }
 
-    // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back.  `first` = entry 0,
-    // which the caller has already loaded (it decodes the event from it before the moves).
+    // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back -- for a caller that
+    // has already loaded entry 0 (it decodes the event from it before the moves).
     __device__ __forceinline__ void pop_after_top() {
         const uint32_t len = n - 1;
         if (len > 0) {
-            const uint2 v = lds(base + len * EB);
-            const uint32_t two = ((len - 1) >> 1) * EB;          // holes below this offset have two children
-            uint32_t h = 0;
-            while (h < two) {
-                const uint32_t r = 2 * h + 2 * EB;              // right child
-                const uint2 er = lds(base + r), el = lds(base + r - EB);   // (one address, two immediate offsets)
-                if (r < two) {
+            const uint2 v = lds(at(len));
+            const uint32_t two = (len - 1) >> 1;                 // holes below this index have two children
+            uint32_t hole = 0;
+            while (hole < two) {
+                const uint32_t right = 2 * hole + 2;
+                const uint32_t ra = at(right);
+                const uint2 er = lds(ra), el = lds(ra - EB);     // (one address, two immediate offsets)
+                if (right < two) {
                     // both children have two children themselves: their four children come in the same round trip and
                     // two levels are decided (the moves of two turns of the one-level loop)
-                    const uint32_t g = base + 2 * r;            // left child's right child; the others are EB apart
-                    const uint2 grr = lds(g + 2 * EB), grl = lds(g + EB), glr = lds(g), gll = lds(g - EB);
-                    const bool left = er.x > el.x;              // right strictly later than left -> take left; tie -> right
-                    const uint32_t c = left ? r - EB : r;
-                    sts(base + h, left ? el : er);
+                    const uint32_t ga = at(2 * right);           // left child's right child; the others are EB apart
+                    const uint2 grr = lds(ga + 2 * EB), grl = lds(ga + EB), glr = lds(ga), gll = lds(ga - EB);
+                    const bool left = er.x > el.x;               // right strictly later than left -> take left; tie -> right
+                    const uint32_t child = left ? right - 1 : right;
+                    sts(at(hole), left ? el : er);
                     const uint2 gr = left ? glr : grr, gl = left ? gll : grl;
                     const bool left2 = gr.x > gl.x;
-                    sts(base + c, left2 ? gl : gr);
-                    h = 2 * c + (left2 ? EB : 2 * EB);
+                    sts(left ? ra - EB : ra, left2 ? gl : gr);
+                    hole = 2 * child + (left2 ? 1 : 2);
                     continue;
                 }
                 const bool left = er.x > el.x;
-                sts(base + h, left ? el : er);
-                h = left ? r - EB : r;
+                sts(at(hole), left ? el : er);
+                hole = left ? right - 1 : right;
             }
-            if ((len & 1u) == 0 && h == ((len - 2) >> 1) * EB) {  // a lone left child at the bottom
-                const uint32_t c = 2 * h + EB;
-                sts(base + h, lds(base + c));
-                h = c;
+            if ((len & 1u) == 0 && hole == (len - 2) >> 1) {      // a lone left child at the bottom
+                const uint32_t child = 2 * hole + 1;
+                sts(at(hole), lds(at(child)));
+                hole = child;
             }
-            sift_up(h, v.x, v.y);
+            sift_up(hole, v.x, v.y);
         }
         n = len;
     }

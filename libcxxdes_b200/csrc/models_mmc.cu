@@ -249,7 +249,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     const int64_t patience_ticks = real_to_sim(prm.patience, sh.clk);  // env.timeout(patience)
     const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
 
-    environment32<MF_THREADS> env;
+    heap32x<MF_THREADS> env;   // (every access to the heap goes through env: explicit ld/st.shared)
     env.init(heap, MF_HEAP);
     uint64_t rep = 0;
     uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
@@ -279,7 +279,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     if (STATEFUL && phase == MF_PHASE_SAVED) {
                         const uint32_t *sv = st.words + rep;
                         const size_t m = st.n_replications;
-                        env.n = (int)sv[1 * m];
+                        env.n = sv[1 * m];
                         env.now = sv[2 * m];
                         env.n_events = sv[3 * m];
                         env.hash = (uint64_t)sv[4 * m] | ((uint64_t)sv[5 * m] << 32);
@@ -292,7 +292,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         total_wait = bits_as_double((uint64_t)sv[11 * m] | ((uint64_t)sv[12 * m] << 32));
                         waiters.n = (int)sv[13 * m];
                         int at = MF_SAVED_HEADER;
-                        for (int k = 0; k < env.n; ++k) heap[k * MF_THREADS] = make_uint2(sv[(size_t)(at + 2 * k) * m], sv[(size_t)(at + 2 * k + 1) * m]);
+                        for (uint32_t k = 0; k < env.n; ++k) env.set_entry(k, make_uint2(sv[(size_t)(at + 2 * k) * m], sv[(size_t)(at + 2 * k + 1) * m]));
                         at += 2 * MF_HEAP;
                         for (int k = 0; k < waiters.n; ++k) waiters.who[k] = (uint16_t)sv[(size_t)(at + k) * m];
                         at += MF_WAITERS;
@@ -335,16 +335,29 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
         }
 
         if (active) {
-            const token32 t = env.step_pop();
+            // The token at the root names the event: decode it before the heap moves, and start the load of the
+            // customer word it refers to (global memory, L2 latency) so that the sift-down hides it.
+            const uint2 root = env.entry(0);
+            token32 t;
+            t.time = root.x;
+            t.tag = root.y;
             const uint32_t target = t.tag & 0xFFFFu;
-            // An event pushes at most two tokens of its own (wake-ups aside).  The branches below only
-            // note which; the pushes -- the sifts through the heap -- run after them, in one piece of
-            // code for all lanes, in the order they were noted (push order decides ties).
+            const bool is_customer_token = target >= 2 && target != MF_NOOP;   // customer(id), acquire_proc(id) or their handler
+            uint64_t *const w = &cust[(uint64_t)(is_customer_token ? (target - 2) >> 1 : 0u) * total_threads];
+            uint64_t s = *w;
+            env.pop_after_top();                 // environment::step, environment.ipp:117-126
+            env.now = t.time > env.now ? t.time : env.now;
+            ++env.n_events;
+            // An event pushes at most two tokens of its own (wake-ups aside) and draws at most one variate.  The
+            // branches below only note which; the variate and the pushes -- the sifts through the heap -- run after
+            // them, in one piece of code for all lanes, in the order they were noted (push order decides ties).
             uint32_t p_time[2], p_tag[2];
             int n_push = 0;
-            auto push_at = [&](uint32_t time, uint32_t tag) {
-                p_time[n_push] = time;
-                p_tag[n_push] = tag;
+            bool draws = false;                  // the second push is at now + a variate
+            uint32_t d_stream = 0, d_index = 0;
+            auto push_at = [&](uint32_t time, uint32_t tag) {   // (constant indices: the two slots stay in registers)
+                if (n_push == 0) { p_time[0] = time; p_tag[0] = tag; }
+                else { p_time[1] = time; p_tag[1] = tag; }
                 ++n_push;
             };
             auto push_after = [&](int64_t delay, uint32_t tag) {
@@ -355,8 +368,6 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
             if (t.tag & MF_HANDLER) {
                 // any_of handler of customer (target - 2) / 2: any_of.ipp:9-26
                 env.fold(t.time, TOKEN_HANDLER, target);
-                uint64_t *w = &cust[(uint64_t)((target - 2) >> 1) * total_threads];
-                uint64_t s = *w;
                 const uint64_t remaining = ((s & C_REM) >> C_REM_SHIFT) - 1;
                 s = (s & ~C_REM) | (remaining << C_REM_SHIFT);
                 if ((s & C_ARMED) && remaining < 2) {
@@ -380,15 +391,15 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     if (source_pc == 1) ++i;
                     if (i < n) {
                         push_at(env.now, 2 + 2 * i);  // async: start token (async.ipp:21-28)
-                        push_after(draw(1, i, d_lambda), 1);
+                        draws = true;                 // then env.timeout(arr()): draw i of stream 1
+                        d_stream = 1;
+                        d_index = i;
+                        p_tag[1] = 1;
                         source_pc = 1;
                     } else {
                         push_at(env.now, 0);  // source returns -> completion resumes co_main
                     }
                 } else {
-                    const uint32_t id = (target - 2) >> 1;
-                    uint64_t *w = &cust[(uint64_t)id * total_threads];
-                    uint64_t s = *w;
                     if ((target & 1) == 0) {
                         // ---- customer(id) ----
                         const uint64_t pc = s & C_PC;
@@ -405,7 +416,10 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             } else {
                                 const double t0 = sim_to_seconds((int64_t)(s >> C_T0_SHIFT), sh.clk);
                                 total_wait += sim_to_seconds((int64_t)env.now, sh.clk) - t0;
-                                push_after(draw(target, 0, d_mu), target);
+                                draws = true;              // env.timeout(svc()): draw 0 of the customer's own stream
+                                d_stream = target;
+                                d_index = 0;
+                                p_tag[0] = target;
                                 s = (s & ~C_PC) | 2;
                             }
                         } else {
@@ -434,6 +448,17 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     *w = s;
                 }
             }
+            // the one variate of the event, drawn where the lanes have met again (the source's inter-arrival time
+            // and a customer's service time were two copies of Philox + log + divide in two different branches)
+            if (draws) {
+                const int64_t delay = draw(d_stream, d_index, d_stream == 1 ? d_lambda : d_mu);
+                const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
+                if ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull) env.status |= CXXDES_B200_REP_TIME_RANGE;
+                // (its tag was noted by the branch: the source's second push, a customer's only one)
+                if (d_stream == 1) p_time[1] = (uint32_t)when;
+                else p_time[0] = (uint32_t)when;
+                ++n_push;
+            }
             if (n_push > 0) env.schedule(p_time[0], p_tag[0]);
             if (n_push > 1) env.schedule(p_time[1], p_tag[1]);
 
@@ -455,7 +480,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         uint32_t *sv = st.words + rep;
                         const size_t m = st.n_replications;
                         if (o.status == CXXDES_B200_REP_UNFINISHED) {
-                            sv[1 * m] = (uint32_t)env.n;
+                            sv[1 * m] = env.n;
                             sv[2 * m] = (uint32_t)end;      // run_until leaves now_ at the horizon
                             sv[3 * m] = env.n_events;
                             sv[4 * m] = (uint32_t)env.hash;
@@ -470,8 +495,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             sv[12 * m] = (uint32_t)(tw >> 32);
                             sv[13 * m] = (uint32_t)waiters.n;
                             int at = MF_SAVED_HEADER;
-                            for (int k = 0; k < env.n; ++k) {
-                                const uint2 e = heap[k * MF_THREADS];
+                            for (uint32_t k = 0; k < env.n; ++k) {
+                                const uint2 e = env.entry(k);
                                 sv[(size_t)(at + 2 * k) * m] = e.x;
                                 sv[(size_t)(at + 2 * k + 1) * m] = e.y;
                             }
@@ -491,7 +516,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                                 sv[(size_t)(at + 3 * n_pairs + 2) * m] = (uint32_t)(wv >> 32);
                                 ++n_pairs;
                             };
-                            for (int k = 0; k < env.n; ++k) save_customer(heap[k * MF_THREADS].y & 0xFFFFu);
+                            for (uint32_t k = 0; k < env.n; ++k) save_customer(env.entry(k).y & 0xFFFFu);
                             for (int k = 0; k < waiters.n; ++k) save_customer(waiters.who[k]);
                             sv[14 * m] = n_pairs;
                             sv[0] = MF_PHASE_SAVED;

@@ -353,6 +353,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
             // them, in one piece of code for all lanes, in the order they were noted (push order decides ties).
             uint32_t p_time[2], p_tag[2];
             int n_push = 0;
+            bool wakes = false;                  // event.wake(): every waiter is scheduled at now, BEFORE the event's own pushes
             bool draws = false;                  // the second push is at now + a variate
             uint32_t d_stream = 0, d_index = 0;
             auto push_at = [&](uint32_t time, uint32_t tag) {   // (constant indices: the two slots stay in registers)
@@ -425,7 +426,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         } else {
                             // release: semaphore::up -> ++value; wake  (semaphore.hpp:58-66)
                             ++value;
-                            waiters.wake(env);
+                            wakes = true;
                             ++served;
                             s = (s & ~C_PC) | 3;
                             push_at(env.now, MF_NOOP);
@@ -436,11 +437,9 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             waiters.wait(env, target);  // semaphore::down blocks (semaphore.hpp:70-78)
                         } else {
                             --value;
-                            waiters.wake(env);  // down() wakes every waiter even though it consumed a unit
-                            if (s & C_BALKED) {
-                                ++value;        // late acquisition is released at once
-                                waiters.wake(env);
-                            }
+                            wakes = true;       // down() wakes every waiter even though it consumed a unit
+                            if (s & C_BALKED) ++value;   // late acquisition is released at once: up() wakes again, but
+                                                         // the first wake has emptied the list (event.hpp:125-134)
                             s |= C_ACQ_DONE;
                             push_at(env.now, (target - 1) | MF_HANDLER);  // completion token with the any_of handler
                         }
@@ -459,8 +458,20 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 else p_time[0] = (uint32_t)when;
                 ++n_push;
             }
-            if (n_push > 0) env.schedule(p_time[0], p_tag[0]);
-            if (n_push > 1) env.schedule(p_time[1], p_tag[1]);
+            // environment::schedule_token for everything the event scheduled, in program order: the woken waiters in list
+            // order (wake_awaitable::await_ready, event.hpp:125-134 -- both events that wake do so before their own push),
+            // then the event's own tokens.  ONE loop, one copy of the sift for the whole warp: a lane takes part for as many
+            // turns as it has tokens.  (As separate calls -- three wake loops and two pushes, each its own inlined sift --
+            // the sift-up ran with 5 of 32 lanes, profiles/r02_mmc_fast_v3.summary.txt.)
+            const int n_wake = wakes ? waiters.n : 0;
+            const int n_total = n_wake + n_push;
+            for (int j = 0; j < n_total; ++j) {
+                const int own = j - n_wake;
+                const uint32_t time = own < 0 ? env.now : (own == 0 ? p_time[0] : p_time[1]);
+                const uint32_t tag = own < 0 ? (uint32_t)waiters.who[j] : (own == 0 ? p_tag[0] : p_tag[1]);
+                env.schedule(time, tag);
+            }
+            if (wakes) waiters.n = 0;
 
             if (env.status || !env.has_event() || env.next_time() > until) {
                 active = false;

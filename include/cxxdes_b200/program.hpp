@@ -448,8 +448,8 @@ private:
     friend class program;
     explicit body(program &p) : prog_(p) {}
     void emit_composition(const composition &c, std::uint16_t code) {   // children follow in place, pre-order
-        if (c.children.empty() || c.children.size() > 32)
-            throw std::invalid_argument("cxxdes_b200: a composition takes 1..32 children");
+        if (c.children.empty() || c.children.size() > 64)
+            throw std::invalid_argument("cxxdes_b200: a composition takes 1..64 children");
         prog_.emit(code, (std::uint16_t)c.children.size(), detail::prio32(c.prio), c.latency);
         for (const child &ch : c.children) {
             if (ch.kind == child::PROC) prog_.emit(CXXDES_B200_OP_CHILD_PROC, (std::uint16_t)ch.proc);

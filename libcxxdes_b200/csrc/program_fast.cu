@@ -765,6 +765,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
                 break;
             case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF: {
                 int timers = 0;
+                if (op.a > 32) return L;   // (the ready flags of the children are one 32-bit word here)
                 ++n_compositions;
                 for (uint32_t c = 1; c <= op.a && i + c < p.n_ops; ++c)
                     if (p.ops[i + c].code != CXXDES_B200_OP_CHILD_PROC) ++timers;

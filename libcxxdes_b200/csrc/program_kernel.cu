@@ -19,8 +19,8 @@ namespace cxb {
 namespace {
 
 constexpr int PRG_THREADS = 128;
-constexpr int PRG_HEAP = 64;
-constexpr int PRG_MAX_PROCS = 24;
+constexpr int PRG_HEAP = 80;
+constexpr int PRG_MAX_PROCS = 72;   // examples/aloha.cpp as a program: co_main + 64 stations
 constexpr int PRG_MAX_NODES = 8;  // compositions in one co_await (the outer one and those nested in it)
 constexpr int PRG_HANDLERS = 8;   // live any_of/all_of handlers per replication (pool, by serial)
 constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind
@@ -613,7 +613,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
 }
 
 const char *program_check(const cxxdes_b200_program &p) {
-    if (p.n_procs < 1 || p.n_procs > PRG_MAX_PROCS) return "program: 1..24 processes supported";
+    if (p.n_procs < 1 || p.n_procs > PRG_MAX_PROCS) return "program: 1..72 processes supported";
     if (p.n_ops < 1 || p.n_ops > 4096) return "program: 1..4096 ops supported";
     if (p.n_roots < 1 || p.n_roots > p.n_procs) return "program: need at least one root process";
     if (p.n_queues > PRG_MAX_OBJ || p.n_sems > PRG_MAX_OBJ || p.n_mutexes > PRG_MAX_OBJ || p.n_events > PRG_MAX_OBJ)
@@ -639,7 +639,7 @@ const char *program_check(const cxxdes_b200_program &p) {
             case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF: {
                 // the children follow in pre-order; a nested composition has children of its own
                 uint32_t pending = op.a, pos = i + 1, nodes = 1, leaves = 0;
-                if (op.a < 1 || op.a > 32) return "program: bad composition";
+                if (op.a < 1 || op.a > 64) return "program: bad composition";
                 while (pending > 0) {
                     if (pos >= p.n_ops) return "program: bad composition";
                     const cxxdes_b200_op &ch = p.ops[pos];

@@ -314,6 +314,24 @@ def mm1_program(lam, mu, n_packets):
     return prog
 
 
+def aloha_shaped_program(n_stations, packets_per_station, frame_ticks, rate):
+    """The processes of examples/aloha.cpp:39-71 as a process program: co_main awaits all_of.range over N stations, a
+    station loops `co_await timeout(frame); co_await timeout(exponential(rate))`.  The station set and the collision
+    flags (aloha.cpp:54-59,73-78) are plain data that schedules nothing, so the TOKENS -- times, order, digest -- are
+    those of the ALOHA model kernels with the same seed: ordinals 0 (co_main) and 1..N double as Philox stream ids."""
+    prog = Program()
+    main = prog.process(0, root=True)
+    stations = [prog.process(1 + s) for s in range(n_stations)]
+    r = prog.rate(rate)
+    for st in stations:
+        with prog.body(st) as b:
+            with b.loop(packets_per_station):
+                b.delay(frame_ticks); b.delay_exp(r)
+    with prog.body(main) as b:
+        b.all_of(*stations)
+    return prog
+
+
 def mm1k_program(lam, mu, n_packets, k):
     """M/M/1/K loss system: the producer drops a packet when the buffer already holds k (the textbook use of an `if`
     between awaits: `if (q.size() < k) co_await q.put(...); else ++dropped;`).  i64[0] = served, i64[1] = dropped."""

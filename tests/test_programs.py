@@ -448,7 +448,7 @@ def test_check_program_without_a_gpu(cuda_lib):
     ]
     bad = {
         "last op must be RETURN": [(DELAY, 0, abi.INHERIT32, 5)],
-        "bad composition": [(ALL, 40, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
+        "bad composition": [(ALL, 70, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
         "CHILD_": [(ALL, 3, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, 1), (R, 0, 0, 0)],
         "must lie ahead": [(JUMP, 0, 0, 0), (R, 0, 0, 0)],
         "IF operand": [(IF, 7 << 8, 1, 0), (R, 0, 0, 0)],
@@ -482,3 +482,47 @@ def test_check_program_without_a_gpu(cuda_lib):
         with prog.body(p) as b:
             b.await_(9)
         prog.check()
+
+
+# ------------------------------------------------------------------ 65 processes: ALOHA's co_main + 64 stations
+def _aloha_pair(n_stations=64, pps=20, lam=1.5):
+    rate = float(np.float32(lam) / np.float32(n_stations))     # cfg_.lambda / cfg_.num_stations in float (aloha.cpp:52)
+    prog = K.aloha_shaped_program(n_stations, pps, 1000, rate)
+    return prog, abi.AlohaParams(n_stations, 0, lam, lam, 1.0, 1000.0, pps)
+
+
+def test_aloha_as_a_program_on_the_cpu(port, ref):
+    """examples/aloha.cpp:39-71 (64 stations, all_of.range) as a process program: the CPU interpreter, the reference
+    engine executing the program with its own awaitables, and the ALOHA model of the oracle dispatch the same tokens."""
+    prog, ap = _aloha_pair()
+    prog.check()
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 7, 3, 6, threads=4)
+    b = port.run(abi.MODEL_ALOHA, ap, oracles.MM1_CLOCK, 7, 3, 6, threads=4)
+    c = ref.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 7, 3, 6, threads=4)
+    for other in (b, c):
+        assert np.array_equal(a.n_events, other.n_events) and np.array_equal(a.end_time, other.end_time)
+        assert np.array_equal(a.trace_hash, other.trace_hash)
+    assert (a.n_events == 2 * 64 * 20 + 2 * 64 + 3).all()        # SURVEY F.2: 2 N pps + 2 N + 3
+
+
+@pytest.mark.gpu
+def test_gpu_aloha_as_a_program_matches_the_aloha_kernel(port):
+    """The same program on the device interpreter (72 processes, 80 heap entries, 64 children per composition) against
+    the hand-written ALOHA kernel: event counts, end times and trace digests equal, bit for bit."""
+    prog, ap = _aloha_pair(pps=40)
+    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
+    n = 600
+    ens = L.Ensemble(prog, n, seed=9, first_replication=5)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    got = ens.run().fetch()
+    ens.close()
+    ens = L.Ensemble(ap, n, seed=9, first_replication=5)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    model = ens.run().fetch()
+    name = ens.kernel_name()
+    ens.close()
+    assert name == "aloha_fast_kernel<false>" and not got.status.any() and not model.status.any()
+    assert np.array_equal(got.n_events, model.n_events) and np.array_equal(got.end_time, model.end_time)
+    assert np.array_equal(got.trace_hash, model.trace_hash)
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 9, 5, 64, threads=os.cpu_count())
+    assert np.array_equal(got.trace_hash[:64], want.trace_hash)

@@ -364,11 +364,11 @@ def run_b200(a):
 
     for _ in range(a.warmup):
         step()
-    barrier()
     launches_before = ens.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()        # (before the barrier: forking nvidia-smi takes rank 0 ~15 ms, which the other ranks would
+    barrier()                  #  otherwise spend waiting in the first all-reduce of their timed region)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):

@@ -338,7 +338,8 @@ int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
  * kernel's compact representation and were redone (results are identical either way; this only tells where the
  * time went).  counts[0] = redone by the model's second pass (M/M/1: queue outgrew the shared-memory window ->
  * two-level ring), counts[1] = of those, taken by the helper grid that runs next to the first pass,
- * counts[2] = redone by the full-size 64-bit kernel, counts[3] = 0 (reserved).  Implies a sync. */
+ * counts[2] = redone by the full-size 64-bit kernel, counts[3] = the longest time, in nanoseconds, the helper grid spent on
+ * one replication (0: none).  Implies a sync. */
 int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]);
 
 /* Event trace of ONE replication (index within this shard): the replication is run again from tick 0 -- to the end,

@@ -84,7 +84,8 @@ struct cxxdes_b200_ensemble {
     unsigned char *col_block = nullptr;  // all result columns, one allocation
     device_columns cols{};
     unsigned long long *counters = nullptr;  // [0] work, [1] retry count, [2] fallback cursor, [3] list A count, [4] list A cursor,
-                                             // [5] M/M/1 first pass done (flag), [6] list A entries taken by the overlapped helper
+                                             // [5] M/M/1 first pass done (flag), [6] list A entries taken by the overlapped helper,
+                                             // [7] longest time (ns) the helper spent on one replication
     uint32_t *retry_list = nullptr;
     log_entry *log_table = nullptr;
     int64_t *ring = nullptr;
@@ -481,7 +482,12 @@ int cxxdes_b200_create(const cxxdes_b200_config *cfg, cxxdes_b200_ensemble **out
         // (CXXDES_B200_MM1_NO_OVERLAP=1: second pass after the first one, as before -- for A/B measurements)
         const char *no_overlap = getenv("CXXDES_B200_MM1_NO_OVERLAP");
         if (ce == cudaSuccess && e->use_fused && !(cfg->flags & CXXDES_B200_FLAG_MM1_LOCKSTEP) && !(no_overlap && no_overlap[0] == '1')) {
-            ce = cudaStreamCreateWithFlags(&e->helper_stream, cudaStreamNonBlocking);
+            // highest priority: its few small blocks are to be placed next to the first pass as soon as they are
+            // launched (and streams of different priority do not share a hardware work queue, behind whose head -- the
+            // first pass -- the helper would otherwise wait: seen with several handles in one process)
+            int prio_low = 0, prio_high = 0;
+            ce = cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+            if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&e->helper_stream, cudaStreamNonBlocking, prio_high);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
         }
@@ -819,7 +825,7 @@ int cxxdes_b200_pass_counts(cxxdes_b200_ensemble *e, uint64_t counts[4]) {
     counts[0] = c[3];
     counts[1] = c[6] & 0xFFFFFFFFull;
     counts[2] = c[1];
-    counts[3] = 0;
+    counts[3] = c[7];
     return CXXDES_B200_OK;
 }
 

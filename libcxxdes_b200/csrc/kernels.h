@@ -59,7 +59,7 @@ size_t mm1_ahead_state_bytes(uint64_t n_replications);   // run_until in pieces:
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
                              const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
-                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream);
+                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream, int leave_blocks = 0);
 
 cudaError_t launch_mm1_ahead_helper(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                                     const mm1_fused_plan &plan, void *gring, const uint32_t *list, uint32_t list_capacity,

@@ -142,6 +142,12 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
     bool active = false, exhausted = false;
     uint64_t rep = 0;
     [[maybe_unused]] unsigned long long poll_idx = ~0ULL;   // POLL: the list index this lane has reserved
+    [[maybe_unused]] unsigned long long poll_t0 = 0;        // POLL: when it took its replication (diagnostics)
+    // POLL: one replication per warp.  Only lane 0 reserves list entries and polls; with all 32 lanes polling, the 31
+    // idle ones looked at the flag and at their list entry (two dependent L2 round trips) on EVERY turn of the loop
+    // their busy neighbour was running its replication in, and made it 2-3 times slower (a replication redone by the
+    // helper cost the step 2-3 ms wherever in the run it had failed: 105.5 ms on the ranks that had one).
+    if constexpr (POLL) exhausted = (threadIdx.x & 31u) != 0;
 
     for (;;) {
         if (!active && !exhausted) {
@@ -166,6 +172,7 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
                         rep = v;
                         poll_idx = ~0ULL;
                         atomicAdd(done_flag + 2, 1u);   // diagnostics (cxxdes_b200_pass_counts): taken by the helper
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(poll_t0));
                     } else if (finished) {
                         exhausted = true;   // the first pass ended without writing this entry
                         break;
@@ -259,6 +266,11 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
         // ---- 4. end of this lane's replication? ----
         if (active && L.template finished<MODE>(c)) {
             active = false;
+            if constexpr (POLL) {   // diagnostics: the longest time the helper spent on one replication, in ns
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                atomicMax((unsigned long long *)(done_flag + 4), t1 - poll_t0);
+            }
             const uint32_t status = L.status;
             uint32_t *w = state + rep * mm1::lane::STATE_WORDS;
             if (status & (CXXDES_B200_REP_QUEUE_OVERFLOW | CXXDES_B200_REP_TIME_RANGE)) {
@@ -291,10 +303,15 @@ mm1_ahead_kernel(mm1::constants c, cxxdes_b200_mm1_params prm, shard sh, device_
 
 namespace {
 constexpr int AH_EVENT_SLOTS = 4;
-// Helper of the first pass: a few one-warp blocks that fit next to its three 256-thread blocks on an SM (registers:
-// 65536 - 3 * 256 * 80 = 4096 = 32 threads x 128, which is what __launch_bounds__(32, 16) allows; shared memory:
-// 2 KB table + 8 KB ring against ~29 KB left).
-constexpr int AH_HELPER_THREADS = 32, AH_HELPER_MIN_BLOCKS = 16, AH_HELPER_BLOCKS = 8;
+// Helper of the first pass: four one-warp blocks (one replication each).  They do NOT fit next to three 256-thread
+// blocks of the first pass: an SM's 64 K registers are four banks of 16 K, one per scheduler, six first-pass warps of
+// 80 registers leave 1024 in each, and the helper's warp needs 3584 (measured: launched next to a full first pass, the
+// helper became resident 2.5 ms before the first pass ended -- when its first blocks retired -- and a replication it redid
+// cost the step 2.3 ms wherever in the run it had failed).  So a first pass that has a helper runs ONE BLOCK SHORT of a
+// full grid (launch_mm1_fused): the SM with two blocks has 5120 registers free per scheduler, one helper warp each;
+// 0.23 % fewer lanes for the first pass against 2.3-4.5 ms whenever some replication outgrows the window (about one
+// shard in two at the headline size, some rank nearly always on eight GPUs).
+constexpr int AH_HELPER_THREADS = 32, AH_HELPER_MIN_BLOCKS = 16, AH_HELPER_BLOCKS = 4;
 constexpr size_t TABLE_BYTES = sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
 
 // Launch geometry: threads per block, resident blocks per SM, window slots per replication.
@@ -387,15 +404,20 @@ struct pass_args {
     unsigned long long *list_cursor;
     uint32_t *fail_list;
     unsigned long long *fail_count;
+    int leave_blocks;   // launch this many blocks short of the full grid (room for the helper, see AH_HELPER_BLOCKS)
 };
 
 template <typename G, int MODE, bool SPILL>
 cudaError_t configure_one() {
-    cudaError_t e = cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    // (the same shared-memory carve-out preference -- all of it -- for every instantiation: the helper's blocks are to
+    // become resident on SMs the first pass has configured for its three 66 KB blocks)
+    auto plain = mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>;
+    auto keeps = mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>;
+    cudaError_t e = cudaFuncSetAttribute(plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(keeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(plain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(keeps, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return e;
 }
 template <typename G>
 cudaError_t configure_geometry() {
@@ -414,8 +436,13 @@ void launch_helper_one(const mm1::constants &c, const cxxdes_b200_mm1_params &pr
                        const mm1_fused_plan &plan, const pass_args &a, unsigned int *done_flag, uint32_t list_capacity,
                        cudaStream_t stream) {
     using G = helper_geometry;
+    static const int blocks = [] {   // CXXDES_B200_MM1_HELPER_BLOCKS: measurements
+        const char *v = getenv("CXXDES_B200_MM1_HELPER_BLOCKS");
+        const int b = v ? atoi(v) : 0;
+        return b >= 1 && b <= 1024 ? b : AH_HELPER_BLOCKS;
+    }();
     mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, true, false, true>
-        <<<AH_HELPER_BLOCKS, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
+        <<<blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
                                                             a.list_count, a.list_cursor, a.fail_list, a.fail_count, done_flag,
                                                             list_capacity);
 }
@@ -426,11 +453,11 @@ void launch_one(const mm1::constants &c, const cxxdes_b200_mm1_params &prm, cons
     // run() path 4 % when they are only a run-time switch)
     if (a.state)
         mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, true>
-            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, a.state, a.resume,
+            <<<plan.ah_blocks - a.leave_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, a.state, a.resume,
                                                               a.list, a.list_count, a.list_cursor, a.fail_list, a.fail_count);
     else
         mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, SPILL, false>
-            <<<plan.ah_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
+            <<<plan.ah_blocks - a.leave_blocks, G::THREADS, G::SMEM, stream>>>(c, prm, sh, out, a.gring, plan.ah_gring_slots, nullptr, 0, a.list,
                                                               a.list_count, a.list_cursor, a.fail_list, a.fail_count);
 }
 template <typename G, bool SPILL>
@@ -449,9 +476,27 @@ void launch_geometry(int mode, const mm1::constants &c, const cxxdes_b200_mm1_pa
 }
 }  // namespace
 
+namespace {
+template <int MODE>
+cudaError_t configure_helper() {
+    using G = helper_geometry;
+    return cudaFuncSetAttribute(mm1_ahead_kernel<G::THREADS, G::MIN_BLOCKS, G::RING_SLOTS, AH_EVENT_SLOTS, MODE, true, false, true>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+}  // namespace
+
 cudaError_t configure_mm1_ahead(const mm1_fused_plan &plan) {
     (void)plan;
-    return configure_geometry<geometry0>();
+    cudaError_t e = configure_geometry<geometry0>();
+    if (e == cudaSuccess) e = configure_helper<0>();
+    if (e == cudaSuccess) e = configure_helper<1>();
+    if (e == cudaSuccess) e = configure_helper<2>();
+    if (e == cudaSuccess) e = configure_helper<3>();
+    if (e == cudaSuccess) e = configure_helper<4>();
+    if (e == cudaSuccess) e = configure_helper<5>();
+    if (e == cudaSuccess) e = configure_helper<6>();
+    if (e == cudaSuccess) e = configure_helper<7>();
+    return e;
 }
 
 // One pass of the generate-ahead kernel.  spill: with the two-level ring.  list == nullptr: the whole
@@ -488,7 +533,7 @@ cudaError_t launch_mm1_ahead_helper(const cxxdes_b200_mm1_params &prm, const sha
     mm1::constants c;
     const int mode = constants_and_mode(c, prm, sh, plan);
     // the helper's two-level ring uses its own (small) thread count as the column count of the global level
-    pass_args a{(uint2 *)gring, nullptr, 0, list, nullptr, list_cursor, fail_list, fail_count};
+    pass_args a{(uint2 *)gring, nullptr, 0, list, nullptr, list_cursor, fail_list, fail_count, 0};
     switch (mode) {
         case 0: launch_helper_one<0>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
         case 1: launch_helper_one<1>(c, prm, sh, out, plan, a, done_flag, list_capacity, stream); break;
@@ -505,10 +550,11 @@ cudaError_t launch_mm1_ahead_helper(const cxxdes_b200_mm1_params &prm, const sha
 cudaError_t launch_mm1_ahead(const cxxdes_b200_mm1_params &prm, const shard &sh, const device_columns &out,
                              const mm1_fused_plan &plan, bool spill, void *gring, uint32_t *state, int resume,
                              const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor,
-                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream) {
+                             uint32_t *fail_list, unsigned long long *fail_count, cudaStream_t stream, int leave_blocks) {
     mm1::constants c;
     const int mode = constants_and_mode(c, prm, sh, plan);
-    pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count};
+    pass_args a{(uint2 *)gring, state, resume, list, list_count, list_cursor, fail_list, fail_count,
+                leave_blocks < plan.ah_blocks ? leave_blocks : 0};
     if (spill) launch_geometry<geometry0, true>(mode, c, prm, sh, out, plan, a, stream);
     else launch_geometry<geometry0, false>(mode, c, prm, sh, out, plan, a, stream);
     return cudaGetLastError();

@@ -439,8 +439,9 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
         } else {
             // window-only first pass; what outgrows the window is redone with the two-level ring
             // (a lone replication takes ~4.5 ms there, 13 ms on the fallback kernel) -- by a helper grid that runs
-            // NEXT TO the first pass and polls its list, so that the one-in-two-million replication is done when the
-            // first pass ends instead of holding the step (and, at N GPUs, every other rank) for those 4.5 ms.
+            // NEXT TO the first pass (on the SM the first pass leaves one block short) and polls its list, so that the
+            // one-in-a-million replication is done when the first pass ends instead of holding the step (and, at N
+            // GPUs, every other rank) for those 4.5 ms.
             // Host order matters: first pass, then the memset that raises the flag behind it, then the helper --
             // if something serialises the launches (a profiler, CUDA_LAUNCH_BLOCKING) the helper finds the flag
             // set and the list complete instead of waiting for a kernel that has not been issued.
@@ -451,8 +452,9 @@ cudaError_t launch_mm1_fused(const cxxdes_b200_mm1_params &prm, const shard &sh,
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(overlap.helper_stream, overlap.fork, 0);
                 if (e != cudaSuccess) return e;
             }
+            // (one block short of the full grid when the helper follows: its warps need the registers of that block)
             e = launch_mm1_ahead(prm, sh, out, plan, false, ahead_gring, ahead_state, resume, nullptr, nullptr, nullptr,
-                                 sh.retry_a_list, sh.retry_a_count, stream);
+                                 sh.retry_a_list, sh.retry_a_count, stream, overlap.helper_stream ? 1 : 0);
             ++*launches;
             if (e != cudaSuccess) return e;
             if (overlap.helper_stream) {

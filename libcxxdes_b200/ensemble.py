@@ -264,7 +264,7 @@ class Ensemble:
         kernel's compact representation (diagnostics; results do not depend on it)."""
         c = (C.c_uint64 * 4)()
         _check(self._lib, self._lib.cxxdes_b200_pass_counts(self._handle, C.byref(c)))
-        return {"second_pass": int(c[0]), "helper": int(c[1]), "fallback": int(c[2])}
+        return {"second_pass": int(c[0]), "helper": int(c[1]), "fallback": int(c[2]), "helper_longest_ns": int(c[3])}
 
     def reset(self):
         if self._handle is not None:

@@ -120,9 +120,11 @@ CXB_HD double log_pos(double w, const Table *table) {
 }
 
 // x / d for a divisor that is reused many times: q0 = x * (1/d), one fma
-// residual, one fma correction (Markstein).  With inv = RN(1/d) this returns
-// the correctly rounded quotient, i.e. the same bits as IEEE `x / d`
-// (checked on 10^7 random pairs in tests/test_shared_math.py).
+// residual, one fma correction (Markstein).  With inv = RN(1/d) the result was
+// TESTED equal to IEEE `x / d` on 10^7 random pairs (tests/test_shared_math.py);
+// it is not proven to be the correctly rounded quotient for every divisor.
+// Parity does not depend on that: host oracle and device both compute the
+// variate with this function, so they agree bit for bit either way.
 struct divisor {
     double d;
     double inv;

@@ -234,6 +234,7 @@ struct environment32 {
     __device__ __forceinline__ uint32_t next_time() const { return heap[0].x; }
 };
 
+#if defined(__CUDACC__)   // (explicit shared-memory instructions: device builds only; tests/native compiles the rest with g++)
 // ---------------------------------------------------------------------------------------------------------------
 // heap32x: the same heap (same layout, same libstdc++ moves) addressed through 32-bit shared-memory addresses with
 // explicit ld/st.shared.  Through a generic `uint2 *` the compiler spends 5-7 instructions per entry on 64-bit address
@@ -349,5 +350,6 @@ struct heap32x {
     __device__ __forceinline__ uint32_t next_time() const { return lds(base).x; }
 };
 
-}  // namespace cxb
+#endif  // __CUDACC__
 
+}  // namespace cxb

@@ -39,19 +39,22 @@ def workloads(packets=10000, lam=5.0):
             "simulated events/sec, ALOHA 64 stations, 256k replications sweeping offered load",
             lambda r: (f"examples/aloha.cpp: 64 stations, {r} replications, offered load G = 0.1 .. 3.0 in 50 steps "
                        "(replication id mod 50), G * 1000 packets per station (BASELINE configs[2])"),
-            None, None, 256),
+            133.0, "sift-down 51 + sift-up 15 + digest 8 + station masks 15 + clock/check 4 + a variate (79) for every "
+                   "second event 40 (DESIGN.md 5.3)", 256),
         "mmc": Workload(
             "mmc", abi.MODEL_MMC, abi.MMCParams(9.0, 1.0, 0.5, 8, 0, 1000), S_MS, 1 << 20, "weak",
             "simulated events/sec, M/M/c balking c=8, 1M replications x 1000 customers",
             lambda r: (f"M/M/c with any_of(acquire, timeout) balking (examples/resource.cpp pattern): c=8, lambda=9, mu=1, "
                        f"patience 0.5 s, 1000 customers, {r} replications (BASELINE configs[3])"),
-            None, None, 1024),
+            119.0, "sift-down 46 + one push per event 23 + digest 8 + customer word 10 + event logic 12 + clock/check 4 + "
+                   "two variates per ~10 events 16 (DESIGN.md 5.3)", 1024),
         "archsim": Workload(
             "archsim", abi.MODEL_ARCHSIM, abi.ArchSimParams(1, 10, 16, 32, 1, 0, 1024), S_S, 1 << 22, "strong",
             "simulated events/sec, basic_arch_sim memory hierarchy, 4M replications sharded across the GPUs",
             lambda r: (f"examples/basic_arch_sim.cpp: mem2{{1,16}} -> mem1{{10}}, sequential driver, 1024 loads of "
                        f"philox % 32, {r} replications (BASELINE configs[4])"),
-            None, None, 1024),
+            53.0, "4-entry heap pop 10 + push 8 + digest 8 + state machine 15 + one LRU scan and one address draw per "
+                  "load (5-10 events) 12 (DESIGN.md 5.3)", 1024),
         "archsim4": Workload(
             "archsim4", abi.MODEL_ARCHSIM, abi.ArchSimParams(1, 10, 16, 32, 4, 0, 256), S_S, 1 << 22, "strong",
             "simulated events/sec, basic_arch_sim memory hierarchy with 4 requesters, 4M replications",

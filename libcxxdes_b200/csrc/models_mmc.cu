@@ -196,6 +196,10 @@ constexpr int MF_THREADS = 176;
 constexpr int MF_BLOCKS_PER_SM = 2;
 constexpr int MF_HEAP = 64;
 constexpr int MF_WAITERS = 64;
+#ifndef CXB_MMC_PUSHES_PER_TURN
+#define CXB_MMC_PUSHES_PER_TURN 2
+#endif
+constexpr int MF_PUSHES_PER_TURN = CXB_MMC_PUSHES_PER_TURN;
 constexpr uint32_t MF_HANDLER = 1u << 16;
 constexpr uint32_t MF_NOOP = TAG_NO_TARGET;
 
@@ -255,6 +259,12 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
     double total_wait = 0.0;
     bool active = false, exhausted = false;
+    // Tokens an event has scheduled and not yet pushed.  A release or an acquisition wakes EVERY waiter (event.hpp:
+    // 125-134): up to ~30 pushes from one event, each a sift to the top of the heap.  Pushed inside the event, such a
+    // storm made the other 31 lanes of the warp wait for it; now a lane pushes at most MF_PUSHES_PER_TURN tokens per
+    // turn of the loop and simply does not take its next event until its list is empty, while its neighbours go on.
+    uint32_t p_time[2] = {0, 0}, p_tag[2] = {0, 0};
+    int n_wake = 0, n_total = 0, next_push = 0;
 
     auto draw = [&](uint32_t stream, uint32_t index, const divisor &rate) {
         const philox_block b = philox4x32_10_scheduled(index >> 1, stream, ctr2, ctr3, keys);
@@ -334,7 +344,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
             continue;
         }
 
-        if (active) {
+        if (active && next_push == n_total) {
             // The token at the root names the event: decode it before the heap moves, and start the load of the
             // customer word it refers to (global memory, L2 latency) so that the sift-down hides it.
             const uint2 root = env.entry(0);
@@ -351,7 +361,6 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
             // An event pushes at most two tokens of its own (wake-ups aside) and draws at most one variate.  The
             // branches below only note which; the variate and the pushes -- the sifts through the heap -- run after
             // them, in one piece of code for all lanes, in the order they were noted (push order decides ties).
-            uint32_t p_time[2], p_tag[2];
             int n_push = 0;
             bool wakes = false;                  // event.wake(): every waiter is scheduled at now, BEFORE the event's own pushes
             bool draws = false;                  // the second push is at now + a variate
@@ -458,20 +467,28 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 else p_time[0] = (uint32_t)when;
                 ++n_push;
             }
-            // environment::schedule_token for everything the event scheduled, in program order: the woken waiters in list
-            // order (wake_awaitable::await_ready, event.hpp:125-134 -- both events that wake do so before their own push),
-            // then the event's own tokens.  ONE loop, one copy of the sift for the whole warp: a lane takes part for as many
-            // turns as it has tokens.  (As separate calls -- three wake loops and two pushes, each its own inlined sift --
-            // the sift-up ran with 5 of 32 lanes, profiles/r02_mmc_fast_v3.summary.txt.)
-            const int n_wake = wakes ? waiters.n : 0;
-            const int n_total = n_wake + n_push;
-            for (int j = 0; j < n_total; ++j) {
-                const int own = j - n_wake;
-                const uint32_t time = own < 0 ? env.now : (own == 0 ? p_time[0] : p_time[1]);
-                const uint32_t tag = own < 0 ? (uint32_t)waiters.who[j] : (own == 0 ? p_tag[0] : p_tag[1]);
-                env.schedule(time, tag);
+            // what the event scheduled, in program order: the woken waiters in list order (wake_awaitable::await_ready,
+            // event.hpp:125-134 -- both events that wake do so before their own push), then the event's own tokens
+            n_wake = wakes ? waiters.n : 0;
+            n_total = n_wake + n_push;
+            next_push = 0;
+        }
+        if (active) {
+            // environment::schedule_token: one copy of the sift for the whole warp, a few tokens per turn
+#pragma unroll
+            for (int turn = 0; turn < MF_PUSHES_PER_TURN; ++turn) {
+                if (next_push < n_total) {
+                    const int own = next_push - n_wake;
+                    const uint32_t time = own < 0 ? env.now : (own == 0 ? p_time[0] : p_time[1]);
+                    const uint32_t tag = own < 0 ? (uint32_t)waiters.who[next_push] : (own == 0 ? p_tag[0] : p_tag[1]);
+                    env.schedule(time, tag);
+                    ++next_push;
+                }
             }
-            if (wakes) waiters.n = 0;
+        }
+        if (active && next_push == n_total) {
+            if (n_wake) waiters.n = 0;     // the wake is complete: the list is empty (event.hpp:132)
+            n_wake = n_total = next_push = 0;
 
             if (env.status || !env.has_event() || env.next_time() > until) {
                 active = false;

@@ -252,6 +252,8 @@ public:
         return {(std::uint16_t)(sem_init_.size() - 1)};
     }
     resource add_resource(std::uint64_t count) { return {add_semaphore(count, count).id}; }
+    // a rate for draws that are emitted by index (cxxdes_b200/record: `simple_op{CXXDES_B200_OP_DELAY_EXP, index, ...}`)
+    std::uint16_t add_rate(double value) { return rate(value); }
     mutex add_mutex() { return {(std::uint16_t)n_mutexes_++}; }
     event add_event() { return {(std::uint16_t)n_events_++}; }
 

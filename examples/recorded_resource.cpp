@@ -1,6 +1,6 @@
 // examples/recorded_resource.cpp -- the reference's examples/resource.cpp, coroutine bodies untouched, on the B200.
 //
-//   g++ -std=c++20 -O2 -I include/cxxdes_b200/record -I include examples/recorded_resource.cpp \
+//   g++ -std=c++20 -O2 -I include/cxxdes_b200/record -I include examples/recorded_resource.cpp
 //       -L libcxxdes_b200/_lib -lcxxdes_b200 -Wl,-rpath,$PWD/libcxxdes_b200/_lib -o recorded_resource
 //
 // `-I include/cxxdes_b200/record` makes <cxxdes/cxxdes.hpp> the RECORDING implementation of the libcxxdes API: the

@@ -23,8 +23,11 @@
 
 // Generation + event-slot rounds per pass of the outer loop (work stealing, start-up/wind-down and
 // end-of-replication checks run once per pass).
+// (2 since round 2: 101.90 against 102.38 ms for the headline run -- the 80-odd instructions of a pass of the outer
+// loop are mostly branches and uniform-path work that the pipes the block is bound by do not see; 1 measured the same
+// within noise in round 1 on an earlier version of the block)
 #ifndef CXB_MM1_UNROLL
-#define CXB_MM1_UNROLL 1
+#define CXB_MM1_UNROLL 2
 #endif
 // Source order of the event slots and the generation inside the branch-free block (measured: see DESIGN.md)
 #ifndef CXB_MM1_ORDER

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r02n; mkdir -p $O
+O=gpurun_out/per_shard; mkdir -p $O
 cat > /tmp/ab2.py <<'PY'
 import os, sys, json
 sys.path.insert(0, '.')

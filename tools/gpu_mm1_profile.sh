@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r02v; mkdir -p $O
+O=gpurun_out/mm1_profile; mkdir -p $O
 python -m pytest tests/test_mm1_gpu.py tests/test_mm1_fuzz.py tests/test_trace_gpu.py -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
 tail -3 $O/pytest_gpu.log | tee -a $O/summary.txt
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; cut -c1-250 $O/bench.json | tee -a $O/summary.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r02m2; mkdir -p $O
+O=gpurun_out/multi; mkdir -p $O
 run() {
   local n=$1 out=$2; shift 2
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \

@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round 2, GPU call A (1 GPU): full -m gpu suite, default bench, A/B of the second-pass helper and of the launch
-# geometries at a strong-scaling shard size, the other configs, ncu launch list.  Outputs under gpurun_out/r02a/.
+# One-GPU session: full -m gpu suite, default bench, A/B of the second-pass helper and of the launch
+# geometries at a strong-scaling shard size, the other configs, ncu launch list.  Outputs under gpurun_out/single/.
 set -u
-O=gpurun_out/r02a
+O=gpurun_out/single
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
 tail -3 $O/pytest_gpu.log | tee -a $O/summary.txt

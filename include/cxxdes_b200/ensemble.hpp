@@ -199,6 +199,46 @@ public:
         return ms;
     }
 
+    // The tokens environment::step popped for ONE replication, in order (what CXXDES_DEBUG_TOKEN would print,
+    // token.ipp:50-60): the replication is run again from tick 0 -- to the end, or to `until` >= 0 -- with a sink on the
+    // dispatch loop.  `digest` equal to trace_hash()[replication] means: this is what the ensemble's kernel dispatched.
+    struct popped_token {
+        time_integral time;
+        priority_type priority;
+        std::uint32_t kind;       // CXXDES_B200_TOKEN_RESUME / _HANDLER / _NOOP
+        std::uint32_t process;    // ordinal, 0xFFFF for a null-target token
+    };
+    struct event_trace {
+        std::uint64_t n_events = 0, digest = 0;
+        std::vector<popped_token> tokens;
+    };
+    event_trace trace(std::uint64_t replication, std::uint64_t max_events = 4096, time_integral until = -1) {
+        bind();
+        std::vector<std::int64_t> t(max_events), pr(max_events);
+        std::vector<std::uint32_t> k(max_events), who(max_events);
+        std::uint64_t written = 0;
+        event_trace out;
+        detail::check(cxxdes_b200_trace(handle_, replication, until, max_events, t.data(), pr.data(), k.data(), who.data(),
+                                        &written, &out.n_events, &out.digest));
+        for (std::uint64_t i = 0; i < written; ++i) out.tokens.push_back({t[i], pr[i], k[i], who[i]});
+        return out;
+    }
+    // which first-pass kernel instantiation run() launches; how many replications the last launch redid elsewhere
+    std::string kernel_name() {
+        bind();
+        char buf[160];
+        detail::check(cxxdes_b200_kernel_name(handle_, buf, sizeof buf));
+        return buf;
+    }
+    struct pass_counts_t {
+        std::uint64_t second_pass, helper, fallback, helper_longest_ns;
+    };
+    pass_counts_t pass_counts() {
+        std::uint64_t c[4] = {0, 0, 0, 0};
+        detail::check(cxxdes_b200_pass_counts(handle_, c));
+        return {c[0], c[1], c[2], c[3]};
+    }
+
 private:
     void bind() {
         if (handle_) return;

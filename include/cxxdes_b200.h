@@ -270,9 +270,12 @@ enum {
                                              fused model kernel exists (parity cross-check)    */
     CXXDES_B200_FLAG_MM1_LOCKSTEP = 2u,   /* M/M/1: first pass by the draw-on-demand kernel instead
                                              of the generate-ahead kernel (A/B measurements)   */
-    CXXDES_B200_FLAG_COOP_HEAP = 4u       /* ALOHA: first pass by the kernel whose event heaps are operated by groups of 8
+    CXXDES_B200_FLAG_COOP_HEAP = 4u,      /* ALOHA: first pass by the kernel whose event heaps are operated by groups of 8
                                              lanes (sub-warp cooperative push / pop with ballots) instead of one thread
                                              per replication (A/B measurements; identical results) */
+    CXXDES_B200_FLAG_WIDE_TOKENS = 8u     /* ALOHA: first pass on 8-byte tokens (time, tag) even where the kernel with 4-byte
+                                             tokens (time relative to a moving epoch + 8-bit code) applies (A/B
+                                             measurements; identical results) */
 };
 
 /* Number of CUDA devices visible (0 and an error string when there is none). */

@@ -26,6 +26,7 @@ CMP = {"==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
 FLAG_GENERIC_ENGINE = 1
 FLAG_MM1_LOCKSTEP = 2
 FLAG_COOP_HEAP = 4
+FLAG_WIDE_TOKENS = 8
 
 
 class Clock(C.Structure):

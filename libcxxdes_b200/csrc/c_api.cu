@@ -343,7 +343,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_aloha(e->params.aloha, sh, e->cols, e->sm_count, e->smem_optin, e->counters + 2, e->stream,
-                                  &launches, st, coop));
+                                  &launches, st, coop, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0));
             break;
         }
         case CXXDES_B200_MODEL_MMC: {
@@ -797,7 +797,9 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
             break;
         case CXXDES_B200_MODEL_ALOHA:
             snprintf(buf, buf_size, !aloha_keeps_state(e->params.aloha, sh) ? "aloha_kernel"
-                                    : (e->cfg.flags & CXXDES_B200_FLAG_COOP_HEAP) ? "aloha_coop_kernel" : "aloha_fast_kernel<false>");
+                                    : (e->cfg.flags & CXXDES_B200_FLAG_COOP_HEAP) ? "aloha_coop_kernel"
+                                    : (!(e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) && aloha_compact_applies(e->params.aloha, sh))
+                                        ? "aloha_compact_kernel<false>" : "aloha_fast_kernel<false>");
             break;
         case CXXDES_B200_MODEL_MMC:
             snprintf(buf, buf_size, mmc_keeps_state(e->params.mmc, sh) ? "mmc_fast_kernel<false>" : "mmc_kernel");

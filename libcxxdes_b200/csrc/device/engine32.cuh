@@ -352,4 +352,144 @@ struct heap32x {
 
 #endif  // __CUDACC__
 
+// ---------------------------------------------------------------------------------------------------------------
+// heap24x: 4-byte tokens, (time - epoch) << 8 | code -- for models whose tokens need no more than an 8-bit tag (ALOHA:
+// which process; a station's loop counter lives in a per-station array instead) and whose LIVE tokens span less than
+// 2^24 ticks.  Half the shared memory of an 8-byte token buys a fourth resident block of replications per SM (these
+// kernels are bound by the dependent chain of each replication times the number of resident chains), and a level of
+// a sift moves one word instead of two.  The heap orders by TIME ONLY, exactly as before -- equal times are resolved by
+// libstdc++'s moves, never by the code in the low byte: `a later than b` is `a > (b | 0xFF)`.
+// The epoch moves up to `now` whenever now - epoch reaches REBASE_AT (every live token is at or after now, so all
+// relative times stay non-negative); a delay of DELAY_LIMIT ticks or more cannot be represented and raises
+// REP_TIME_RANGE (the replication is redone by the 64-bit kernel).
+// ---------------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+struct heap24x {
+    static constexpr uint32_t EB = (uint32_t)STRIDE * 4u;     // bytes between consecutive entries of one replication
+    static constexpr uint32_t REBASE_AT = 1u << 22;
+    static constexpr uint32_t DELAY_LIMIT = (1u << 24) - (1u << 22);
+    uint32_t now;        // absolute ticks
+    uint32_t epoch;      // absolute tick of relative time 0
+    uint32_t n_events;
+    uint64_t hash;
+    uint32_t status;
+    uint32_t n;          // heap size
+    uint32_t cap;
+    uint32_t base;       // shared-memory address of entry 0 of this thread's column
+
+    __device__ __forceinline__ void init(uint32_t *column, int capacity) {
+        now = 0;
+        epoch = 0;
+        n_events = 0;
+        hash = TRACE_HASH_INIT;
+        status = 0;
+        n = 0;
+        cap = (uint32_t)capacity;
+        base = shared_address(column);
+    }
+#if defined(__CUDACC__)
+    static __device__ __forceinline__ uint32_t shared_address(uint32_t *column) { return (uint32_t)__cvta_generic_to_shared(column); }
+    static __device__ __forceinline__ uint32_t lds(uint32_t addr) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void sts(uint32_t addr, uint32_t v) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+    }
+#else   // tests/native: "shared memory" is the array CXB_HOST_SHARED names, addresses are byte offsets into it
+    static uint32_t shared_address(uint32_t *column) { return (uint32_t)((column - CXB_HOST_SHARED) * 4); }
+    static uint32_t lds(uint32_t addr) { return CXB_HOST_SHARED[addr / 4]; }
+    static void sts(uint32_t addr, uint32_t v) { CXB_HOST_SHARED[addr / 4] = v; }
+#endif
+    static __device__ __forceinline__ bool later(uint32_t a, uint32_t b) { return a > (b | 0xFFu); }   // a.time > b.time
+    __device__ __forceinline__ uint32_t at(uint32_t index) const { return base + index * EB; }
+    __device__ __forceinline__ uint32_t entry(uint32_t index) const { return lds(at(index)); }
+    __device__ __forceinline__ void set_entry(uint32_t index, uint32_t v) const { sts(at(index), v); }
+    __device__ __forceinline__ uint32_t time_of(uint32_t word) const { return epoch + (word >> 8); }
+
+    // std::__push_heap from the hole at index `hole` (stl_heap.h:135-148), parent and grandparent in one round trip
+    __device__ __forceinline__ void sift_up(uint32_t hole, uint32_t word) const {
+        const uint32_t top = word | 0xFFu;
+        while (hole != 0) {
+            const uint32_t parent = (hole - 1) >> 1;
+            const uint32_t grand = parent != 0 ? (parent - 1) >> 1 : 0u;
+            const uint32_t pe = lds(at(parent)), ge = lds(at(grand));
+            if (!(pe > top)) break;
+            sts(at(hole), pe);
+            hole = parent;
+            if (parent == 0 || !(ge > top)) break;
+            sts(at(hole), ge);
+            hole = grand;
+        }
+        sts(at(hole), word);
+    }
+
+    __device__ __forceinline__ void rebase() {
+        const uint32_t delta = now - epoch;
+        for (uint32_t k = 0; k < n; ++k) sts(at(k), lds(at(k)) - (delta << 8));
+        epoch = now;
+    }
+
+    // environment::schedule_token (environment.ipp:94-98) of a token at absolute time `when` >= now
+    __device__ __forceinline__ void schedule(uint32_t when, uint32_t code) {
+        if (n >= cap) {
+            status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            return;
+        }
+        if (now - epoch >= REBASE_AT) rebase();
+        if (when - now >= DELAY_LIMIT) {
+            status |= CXXDES_B200_REP_TIME_RANGE;
+            return;
+        }
+        sift_up(n, ((when - epoch) << 8) | code);
+        ++n;
+    }
+
+    // std::pop_heap (stl_heap.h:224-270) then pop_back, for a caller that has already loaded entry 0
+    __device__ __forceinline__ void pop_after_top() {
+        const uint32_t len = n - 1;
+        if (len > 0) {
+            const uint32_t v = lds(at(len));
+            const uint32_t two = (len - 1) >> 1;                 // holes below this index have two children
+            uint32_t hole = 0;
+            while (hole < two) {
+                const uint32_t right = 2 * hole + 2;
+                const uint32_t ra = at(right);
+                const uint32_t er = lds(ra), el = lds(ra - EB);
+                if (right < two) {
+                    // both children have two children themselves: two levels per round trip (see heap32x)
+                    const uint32_t ga = at(2 * right);
+                    const uint32_t grr = lds(ga + 2 * EB), grl = lds(ga + EB), glr = lds(ga), gll = lds(ga - EB);
+                    const bool left = later(er, el);             // right strictly later than left -> take left; tie -> right
+                    const uint32_t child = left ? right - 1 : right;
+                    sts(at(hole), left ? el : er);
+                    const uint32_t gr = left ? glr : grr, gl = left ? gll : grl;
+                    const bool left2 = later(gr, gl);
+                    sts(left ? ra - EB : ra, left2 ? gl : gr);
+                    hole = 2 * child + (left2 ? 1 : 2);
+                    continue;
+                }
+                const bool left = later(er, el);
+                sts(at(hole), left ? el : er);
+                hole = left ? right - 1 : right;
+            }
+            if ((len & 1u) == 0 && hole == (len - 2) >> 1) {      // a lone left child at the bottom
+                const uint32_t child = 2 * hole + 1;
+                sts(at(hole), lds(at(child)));
+                hole = child;
+            }
+            sift_up(hole, v);
+        }
+        n = len;
+    }
+
+    __device__ __forceinline__ void fold(uint32_t time, uint32_t kind, uint32_t proc) {
+        hash = trace_hash_step(hash, (int64_t)time, 0, kind, proc);
+    }
+    __device__ __forceinline__ bool has_event() const { return n > 0; }
+    __device__ __forceinline__ uint32_t next_time() const { return time_of(lds(base)); }
+};
+
+
 }  // namespace cxb

@@ -75,9 +75,10 @@ struct aloha_saved {          // run_until / run_for in pieces (nullptr words = 
 };
 size_t aloha_saved_words(const cxxdes_b200_aloha_params &prm);
 bool aloha_keeps_state(const cxxdes_b200_aloha_params &prm, const shard &sh);   // the 32-bit kernel runs the model
+bool aloha_compact_applies(const cxxdes_b200_aloha_params &prm, const shard &sh);   // ... on 4-byte tokens
 cudaError_t launch_aloha(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                          int sm_count, size_t smem_optin, unsigned long long *list_cursor, cudaStream_t stream,
-                         int *launches, const aloha_saved &st, bool coop);
+                         int *launches, const aloha_saved &st, bool coop, bool wide_tokens);
 // first pass with sub-warp cooperative heaps (models_aloha_coop.cu); the caller runs the retry list afterwards
 cudaError_t launch_aloha_coop(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                               int sm_count, cudaStream_t stream);

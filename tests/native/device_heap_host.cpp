@@ -20,6 +20,8 @@ static inline void __syncthreads() {}
 struct uint2 { unsigned x, y; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 using std::min;
+static uint32_t host_shared[4096];          // heap24x's "shared memory" in this build
+#define CXB_HOST_SHARED host_shared
 
 #include "device/engine32.cuh"
 
@@ -77,6 +79,52 @@ int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span, bool fla
     return 0;
 }
 
+// heap24x: 4-byte tokens relative to a moving epoch.  Same check, with the clock running far enough for many rebases
+// (time steps up to `time_span`, so a run of 3000 operations passes REBASE_AT several times when the span is large)
+// and the code byte drawn so that it can never decide an order that libstdc++ would not.
+int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *rebases) {
+    std::mt19937 rng(seed);
+    uint32_t *column = host_shared + 16;
+    heap24x<1> env;
+    env.init(column, capacity);
+    std::priority_queue<ref_token, std::vector<ref_token>, ref_comp> ref;
+    std::vector<uint32_t> serial_of_code(256, 0);   // the token a code byte stands for (a code is live at most once)
+    uint32_t next_serial = 1;
+    for (int k = 0; k < n_ops; ++k) {
+        const bool push = ref.empty() || ((int)ref.size() < capacity && rng() % 100 < 55);
+        if (push) {
+            uint32_t code = rng() & 0xFFu;
+            while (serial_of_code[code]) code = (code + 1) & 0xFFu;
+            const uint32_t t = env.now + rng() % time_span;
+            const uint32_t epoch_before = env.epoch;
+            env.schedule(t, code);
+            if (env.epoch != epoch_before) ++*rebases;
+            if (env.status) return 1;
+            serial_of_code[code] = next_serial;
+            ref.push(ref_token{t, 0, next_serial});
+            ++next_serial;
+        } else {
+            const uint32_t root = env.entry(0);
+            env.pop_after_top();
+            const uint32_t time = env.time_of(root), code = root & 0xFFu;
+            env.now = time > env.now ? time : env.now;
+            const ref_token want = ref.top();
+            ref.pop();
+            if (time != want.time || serial_of_code[code] != want.tag) {
+                std::fprintf(stderr, "heap24x: seed %u op %d: popped (%u, code %u), std::priority_queue (%llu, %u)\n", seed, k,
+                             time, code, (unsigned long long)want.time, want.tag);
+                return 1;
+            }
+            serial_of_code[code] = 0;
+        }
+        if (env.n != (uint32_t)ref.size() || env.status) return 1;
+    }
+    // a delay the 24-bit window cannot hold is refused, never wrapped
+    if (env.n >= env.cap) return 0;
+    env.schedule(env.now + heap24x<1>::DELAY_LIMIT, 0);
+    return (env.status & CXXDES_B200_REP_TIME_RANGE) ? 0 : 1;
+}
+
 int check64(uint32_t seed, int capacity, int n_ops, uint32_t time_span) {
     std::mt19937 rng(seed);
     std::vector<uint64_t> keys(capacity);
@@ -125,6 +173,19 @@ int main() {
                 ops += 9000;
             }
         }
+    }
+    long rebases = 0;
+    for (uint32_t seed = 1; seed <= 40; ++seed) {
+        for (int capacity : {2, 3, 7, 8, 33, 64, 66, 200}) {
+            for (uint32_t span : {1u, 2u, 5u, 1000u, 3000000u}) {
+                bad += check24(seed * 32452843u + capacity, capacity, 3000, span, &rebases);
+                ops += 3000;
+            }
+        }
+    }
+    if (rebases < 1000) {
+        std::fprintf(stderr, "heap24x: only %ld rebases exercised\n", rebases);
+        ++bad;
     }
     std::printf("device heaps vs std::priority_queue: %ld operations, %d mismatching runs\n", ops, bad);
     return bad ? 1 : 0;

@@ -303,6 +303,47 @@ struct heap32x {
         ++n;
     }
 
+    // The same __push_heap with every ancestor of the hole loaded at once.  Which entries a sift-up looks at does not
+    // depend on the data: they are the hole's ancestors, (hole - 1) / 2 and so on up to the root.  So all LEVELS of
+    // them (LEVELS = depth of the deepest index the heap can have; beyond the root the root again) come in ONE round
+    // trip of independent loads instead of one dependent round trip per two levels, and because the times on a path to
+    // the root never increase, "strictly later than the new token" holds for a prefix of them: those move down one
+    // place on the path, the token lands above the last of them.  No loop, no divergence; a token pushed at `now`
+    // (wake-ups, start and completion tokens: most of M/M/c's pushes) climbs nearly to the root, which cost the loop
+    // three dependent round trips.  (A root that is loaded again for levels beyond it stores onto itself, before the
+    // token's own store.)
+    template <int LEVELS>
+    __device__ __forceinline__ void sift_up_path(uint32_t hole, uint32_t time, uint32_t tag) const {
+        uint32_t addr[LEVELS + 1];
+        uint2 e[LEVELS];
+        uint32_t a = hole;
+        addr[0] = at(hole);
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            a = (a - (a != 0u ? 1u : 0u)) >> 1;
+            addr[k + 1] = at(a);
+            e[k] = lds(addr[k + 1]);
+        }
+        uint32_t dest = addr[0];
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            if (e[k].x > time) {
+                sts(addr[k], e[k]);
+                dest = addr[k + 1];
+            }
+        }
+        sts(dest, make_uint2(time, tag));
+    }
+    template <int LEVELS>
+    __device__ __forceinline__ void schedule_path(uint32_t time, uint32_t tag) {
+        if (n >= cap) {
+            status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            return;
+        }
+        sift_up_path<LEVELS>(n, time, tag);
+        ++n;
+    }
+
     // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back -- for a caller that
     // has already loaded entry 0 (it decodes the event from it before the moves).
     __device__ __forceinline__ void pop_after_top() {
@@ -443,6 +484,44 @@ struct heap24x {
             return;
         }
         sift_up(n, ((when - epoch) << 8) | code);
+        ++n;
+    }
+
+    // the same sift-up with all LEVELS ancestors loaded in one round trip (see heap32x::sift_up_path)
+    template <int LEVELS>
+    __device__ __forceinline__ void sift_up_path(uint32_t hole, uint32_t word) const {
+        const uint32_t top = word | 0xFFu;
+        uint32_t addr[LEVELS + 1], e[LEVELS];
+        uint32_t a = hole;
+        addr[0] = at(hole);
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            a = (a - (a != 0u ? 1u : 0u)) >> 1;
+            addr[k + 1] = at(a);
+            e[k] = lds(addr[k + 1]);
+        }
+        uint32_t dest = addr[0];
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            if (e[k] > top) {
+                sts(addr[k], e[k]);
+                dest = addr[k + 1];
+            }
+        }
+        sts(dest, word);
+    }
+    template <int LEVELS>
+    __device__ __forceinline__ void schedule_path(uint32_t when, uint32_t code) {
+        if (n >= cap) {
+            status |= CXXDES_B200_REP_HEAP_OVERFLOW;
+            return;
+        }
+        if (now - epoch >= REBASE_AT) rebase();
+        if (when - now >= DELAY_LIMIT) {
+            status |= CXXDES_B200_REP_TIME_RANGE;
+            return;
+        }
+        sift_up_path<LEVELS>(n, ((when - epoch) << 8) | code);
         ++n;
     }
 

@@ -181,6 +181,10 @@ aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, const u
 //   * Philox round keys come precomputed from the constant bank (the key is the seed).
 // Replications whose clock would pass 2^32 ticks are handed to aloha_kernel above.
 // ---------------------------------------------------------------------------------------------
+#ifndef CXB_PATH_PUSH
+#define CXB_PATH_PUSH 1     // the event's push as a path-parallel sift-up (engine32.cuh sift_up_path); 0: the loop (A/B)
+#endif
+
 namespace {
 constexpr int AF_THREADS = 128;
 constexpr int AF_BLOCKS_PER_SM = 3;
@@ -614,7 +618,12 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             // token at now + delay; the sum must stay inside 32 bits
             const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
             if (push && ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull)) env.status |= CXXDES_B200_REP_TIME_RANGE;
+            // (every ancestor of the new leaf in one round trip: indices up to N + 1 = 65 are at most 6 levels deep)
+#if CXB_PATH_PUSH
+            if (push) env.schedule_path<6>((uint32_t)when, push_tag);
+#else
             if (push) env.schedule((uint32_t)when, push_tag);
+#endif
 
             // environment::run / run_until (environment.ipp:179-196)
             if (env.status || !env.has_event() || env.next_time() > until) {

@@ -196,6 +196,9 @@ constexpr int MF_THREADS = 176;
 constexpr int MF_BLOCKS_PER_SM = 2;
 constexpr int MF_HEAP = 64;
 constexpr int MF_WAITERS = 64;
+#ifndef CXB_PATH_PUSH
+#define CXB_PATH_PUSH 1     // pushes as path-parallel sift-ups (engine32.cuh sift_up_path); 0: the loop (A/B)
+#endif
 #ifndef CXB_MMC_PUSHES_PER_TURN
 #define CXB_MMC_PUSHES_PER_TURN 2
 #endif
@@ -481,7 +484,11 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     const int own = next_push - n_wake;
                     const uint32_t time = own < 0 ? env.now : (own == 0 ? p_time[0] : p_time[1]);
                     const uint32_t tag = own < 0 ? (uint32_t)waiters.who[next_push] : (own == 0 ? p_tag[0] : p_tag[1]);
+#if CXB_PATH_PUSH
+                    env.schedule_path<6>(time, tag);     // 64 entries: at most 6 ancestors, loaded in one round trip
+#else
                     env.schedule(time, tag);
+#endif
                     ++next_push;
                 }
             }

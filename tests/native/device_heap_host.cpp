@@ -82,7 +82,7 @@ int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span, bool fla
 // heap24x: 4-byte tokens relative to a moving epoch.  Same check, with the clock running far enough for many rebases
 // (time steps up to `time_span`, so a run of 3000 operations passes REBASE_AT several times when the span is large)
 // and the code byte drawn so that it can never decide an order that libstdc++ would not.
-int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *rebases) {
+int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *rebases, bool path = false) {
     std::mt19937 rng(seed);
     uint32_t *column = host_shared + 16;
     heap24x<1> env;
@@ -97,7 +97,9 @@ int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *re
             while (serial_of_code[code]) code = (code + 1) & 0xFFu;
             const uint32_t t = env.now + rng() % time_span;
             const uint32_t epoch_before = env.epoch;
-            env.schedule(t, code);
+            // (path: every ancestor in one round trip, LEVELS = 8 covers indices below 511)
+            if (path) env.schedule_path<8>(t, code);
+            else env.schedule(t, code);
             if (env.epoch != epoch_before) ++*rebases;
             if (env.status) return 1;
             serial_of_code[code] = next_serial;
@@ -179,7 +181,8 @@ int main() {
         for (int capacity : {2, 3, 7, 8, 33, 64, 66, 200}) {
             for (uint32_t span : {1u, 2u, 5u, 1000u, 3000000u}) {
                 bad += check24(seed * 32452843u + capacity, capacity, 3000, span, &rebases);
-                ops += 3000;
+                bad += check24(seed * 49979687u + capacity, capacity, 3000, span, &rebases, true);
+                ops += 6000;
             }
         }
     }

@@ -273,8 +273,8 @@ enum {
     CXXDES_B200_FLAG_COOP_HEAP = 4u,      /* ALOHA: first pass by the kernel whose event heaps are operated by groups of 8
                                              lanes (sub-warp cooperative push / pop with ballots) instead of one thread
                                              per replication (A/B measurements; identical results) */
-    CXXDES_B200_FLAG_WIDE_TOKENS = 8u     /* ALOHA: first pass on 8-byte tokens (time, tag) even where the kernel with 4-byte
-                                             tokens (time relative to a moving epoch + 8-bit code) applies (A/B
+    CXXDES_B200_FLAG_WIDE_TOKENS = 8u     /* ALOHA, M/M/c: first pass on 8-byte tokens (time, tag) even where the kernel with
+                                             4-byte tokens (time relative to a moving epoch + a short code) applies (A/B
                                              measurements; identical results) */
 };
 

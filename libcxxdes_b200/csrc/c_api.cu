@@ -355,7 +355,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
-                                &launches, st));
+                                &launches, st, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0));
             break;
         }
         case CXXDES_B200_MODEL_ARCHSIM: {
@@ -802,7 +802,9 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
                                         ? "aloha_compact_kernel<false>" : "aloha_fast_kernel<false>");
             break;
         case CXXDES_B200_MODEL_MMC:
-            snprintf(buf, buf_size, mmc_keeps_state(e->params.mmc, sh) ? "mmc_fast_kernel<false>" : "mmc_kernel");
+            snprintf(buf, buf_size, !mmc_keeps_state(e->params.mmc, sh) ? "mmc_kernel"
+                                    : (!(e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) && mmc_narrow_applies(e->params.mmc, sh))
+                                        ? "mmc_fast_kernel<false,narrow>" : "mmc_fast_kernel<false,wide>");
             break;
         case CXXDES_B200_MODEL_ARCHSIM:
             snprintf(buf, buf_size, "archsim_kernel<%s>", e->params.arch.n_requesters == 1 ? "1 requester" : "k requesters");

@@ -274,6 +274,17 @@ struct heap32x {
     __device__ __forceinline__ uint32_t at(uint32_t index) const { return base + index * EB; }
     __device__ __forceinline__ uint2 entry(uint32_t index) const { return lds(at(index)); }
     __device__ __forceinline__ void set_entry(uint32_t index, uint2 v) const { sts(at(index), v); }
+    static __device__ __forceinline__ uint32_t time_of(uint2 word) { return word.x; }
+    static __device__ __forceinline__ uint32_t tag_of(uint2 word) { return word.y; }
+    __device__ __forceinline__ token32 token_at(uint32_t index) const {
+        const uint2 w = entry(index);
+        token32 t;
+        t.time = w.x;
+        t.tag = w.y;
+        return t;
+    }
+    __device__ __forceinline__ void set_token(uint32_t index, uint32_t time, uint32_t tag) const { set_entry(index, make_uint2(time, tag)); }
+    __device__ __forceinline__ void restart_epoch() {}   // (absolute times: nothing to do; see heap_rel)
 
     // std::__push_heap from the hole at index `hole` (stl_heap.h:135-148; comp(parent, value) = parent strictly later).
     // Parent and grandparent are loaded in one round trip and two levels decided per trip (as environment32::sift_up:
@@ -394,21 +405,24 @@ struct heap32x {
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------------------------
-// heap24x: 4-byte tokens, (time - epoch) << 8 | code -- for models whose tokens need no more than an 8-bit tag (ALOHA:
-// which process; a station's loop counter lives in a per-station array instead) and whose LIVE tokens span less than
-// 2^24 ticks.  Half the shared memory of an 8-byte token buys a fourth resident block of replications per SM (these
-// kernels are bound by the dependent chain of each replication times the number of resident chains), and a level of
-// a sift moves one word instead of two.  The heap orders by TIME ONLY, exactly as before -- equal times are resolved by
-// libstdc++'s moves, never by the code in the low byte: `a later than b` is `a > (b | 0xFF)`.
+// heap_rel<STRIDE, CODE_BITS>: 4-byte tokens, (time - epoch) << CODE_BITS | code -- for models whose tokens need only a
+// short tag (ALOHA, 8 bits: which process; a station's loop counter lives in a per-station array instead.  M/M/c, 12 bits:
+// handler flag + customer / acquire_proc ordinal below 2047) and whose LIVE tokens span less than 2^(32 - CODE_BITS) ticks.
+// Half the shared memory of an 8-byte token buys more resident replications per SM (these kernels are bound by the
+// dependent chain of each replication times the number of resident chains), and a level of a sift moves one word
+// instead of two.  The heap orders by TIME ONLY, exactly as before -- equal times are resolved by libstdc++'s moves,
+// never by the code in the low bits: `a later than b` is `a > (b | CODE_MASK)`.
 // The epoch moves up to `now` whenever now - epoch reaches REBASE_AT (every live token is at or after now, so all
 // relative times stay non-negative); a delay of DELAY_LIMIT ticks or more cannot be represented and raises
 // REP_TIME_RANGE (the replication is redone by the 64-bit kernel).
 // ---------------------------------------------------------------------------------------------------------------
-template <int STRIDE>
-struct heap24x {
+template <int STRIDE, int CODE_BITS>
+struct heap_rel {
     static constexpr uint32_t EB = (uint32_t)STRIDE * 4u;     // bytes between consecutive entries of one replication
-    static constexpr uint32_t REBASE_AT = 1u << 22;
-    static constexpr uint32_t DELAY_LIMIT = (1u << 24) - (1u << 22);
+    static constexpr int TIME_BITS = 32 - CODE_BITS;
+    static constexpr uint32_t CODE_MASK = (1u << CODE_BITS) - 1u;
+    static constexpr uint32_t REBASE_AT = 1u << (TIME_BITS - 2);
+    static constexpr uint32_t DELAY_LIMIT = (1u << TIME_BITS) - REBASE_AT;
     uint32_t now;        // absolute ticks
     uint32_t epoch;      // absolute tick of relative time 0
     uint32_t n_events;
@@ -443,15 +457,28 @@ struct heap24x {
     static uint32_t lds(uint32_t addr) { return CXB_HOST_SHARED[addr / 4]; }
     static void sts(uint32_t addr, uint32_t v) { CXB_HOST_SHARED[addr / 4] = v; }
 #endif
-    static __device__ __forceinline__ bool later(uint32_t a, uint32_t b) { return a > (b | 0xFFu); }   // a.time > b.time
+    static __device__ __forceinline__ bool later(uint32_t a, uint32_t b) { return a > (b | CODE_MASK); }   // a.time > b.time
     __device__ __forceinline__ uint32_t at(uint32_t index) const { return base + index * EB; }
     __device__ __forceinline__ uint32_t entry(uint32_t index) const { return lds(at(index)); }
     __device__ __forceinline__ void set_entry(uint32_t index, uint32_t v) const { sts(at(index), v); }
-    __device__ __forceinline__ uint32_t time_of(uint32_t word) const { return epoch + (word >> 8); }
+    __device__ __forceinline__ uint32_t time_of(uint32_t word) const { return epoch + (word >> CODE_BITS); }
+    static __device__ __forceinline__ uint32_t tag_of(uint32_t word) { return word & CODE_MASK; }
+    // a token as (absolute time, tag), for saved state; the epoch must be at or before every time stored
+    __device__ __forceinline__ token32 token_at(uint32_t index) const {
+        const uint32_t w = entry(index);
+        token32 t;
+        t.time = time_of(w);
+        t.tag = tag_of(w);
+        return t;
+    }
+    __device__ __forceinline__ void set_token(uint32_t index, uint32_t time, uint32_t tag) const {
+        set_entry(index, ((time - epoch) << CODE_BITS) | tag);
+    }
+    __device__ __forceinline__ void restart_epoch() { epoch = now; }   // after `now` was restored, before set_token
 
     // std::__push_heap from the hole at index `hole` (stl_heap.h:135-148), parent and grandparent in one round trip
     __device__ __forceinline__ void sift_up(uint32_t hole, uint32_t word) const {
-        const uint32_t top = word | 0xFFu;
+        const uint32_t top = word | CODE_MASK;
         while (hole != 0) {
             const uint32_t parent = (hole - 1) >> 1;
             const uint32_t grand = parent != 0 ? (parent - 1) >> 1 : 0u;
@@ -468,7 +495,7 @@ struct heap24x {
 
     __device__ __forceinline__ void rebase() {
         const uint32_t delta = now - epoch;
-        for (uint32_t k = 0; k < n; ++k) sts(at(k), lds(at(k)) - (delta << 8));
+        for (uint32_t k = 0; k < n; ++k) sts(at(k), lds(at(k)) - (delta << CODE_BITS));
         epoch = now;
     }
 
@@ -483,14 +510,14 @@ struct heap24x {
             status |= CXXDES_B200_REP_TIME_RANGE;
             return;
         }
-        sift_up(n, ((when - epoch) << 8) | code);
+        sift_up(n, ((when - epoch) << CODE_BITS) | code);
         ++n;
     }
 
     // the same sift-up with all LEVELS ancestors loaded in one round trip (see heap32x::sift_up_path)
     template <int LEVELS>
     __device__ __forceinline__ void sift_up_path(uint32_t hole, uint32_t word) const {
-        const uint32_t top = word | 0xFFu;
+        const uint32_t top = word | CODE_MASK;
         uint32_t addr[LEVELS + 1], e[LEVELS];
         uint32_t a = hole;
         addr[0] = at(hole);
@@ -521,7 +548,7 @@ struct heap24x {
             status |= CXXDES_B200_REP_TIME_RANGE;
             return;
         }
-        sift_up_path<LEVELS>(n, ((when - epoch) << 8) | code);
+        sift_up_path<LEVELS>(n, ((when - epoch) << CODE_BITS) | code);
         ++n;
     }
 
@@ -570,5 +597,7 @@ struct heap24x {
     __device__ __forceinline__ uint32_t next_time() const { return time_of(lds(base)); }
 };
 
+template <int STRIDE>
+using heap24x = heap_rel<STRIDE, 8>;     // ALOHA: 24-bit relative time, 8-bit code
 
 }  // namespace cxb

@@ -91,11 +91,12 @@ struct mmc_saved {            // run_until / run_for in pieces (nullptr words = 
     uint64_t n_replications;
     int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
 };
+bool mmc_narrow_applies(const cxxdes_b200_mmc_params &prm, const shard &sh);   // first pass on 4-byte tokens
 bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh);   // the 32-bit kernel runs the model
 size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm);
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches, const mmc_saved &st);
+                       int *launches, const mmc_saved &st, bool wide_tokens);
 
 // ---- memory hierarchy (models_archsim.cu) ----
 bool archsim_supported(const cxxdes_b200_archsim_params &p);

@@ -11,6 +11,8 @@
 // A handler token always targets the customer whose any_of owns it, so the handler is found
 // from the target.  Per-customer state is one 64-bit word in global memory laid out
 // [customer][thread] (lanes walk the customers roughly in step, so accesses coalesce).
+#include <cstdlib>
+
 #include "device/engine32.cuh"
 #include "device/models_common.cuh"
 #include "device/trace.cuh"
@@ -184,16 +186,16 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Compact kernel (the default): the same lowering on device/engine32.cuh -- 8-byte tokens
-// {u32 time, u32 target | handler << 16}, 64-entry heap, 64 waiters as 16-bit process ordinals
-// (every waiter is an acquire_proc: priority 0, latency 0), i.e. 640 bytes of shared memory per
-// replication instead of 1920, so 352 threads are resident per SM instead of 96; one flat loop
-// with in-loop work stealing.  A replication that outgrows these capacities or the 32-bit clock
-// is handed to mmc_kernel above.
+// Compact kernels (the default): the same lowering on device/engine32.cuh, one flat loop with in-loop work stealing,
+// 64-entry heap, 64 waiters as 16-bit process ordinals (every waiter is an acquire_proc: priority 0, latency 0).
+//   wide tokens    8 bytes {u32 time, u32 target | handler << 16} (heap32x): 640 bytes of shared memory per
+//                  replication instead of 1920, 352 threads resident per SM instead of 96;
+//   narrow tokens  4 bytes {20 bits of time past a moving epoch, handler << 11 | target} (heap_rel<.., 12>): 384 bytes,
+//                  576 threads per SM.  First choice when the ordinals fit 11 bits (at most 1022 customers) and the
+//                  delays stay far below 2^20 - 2^18 ticks (mmc_narrow_applies).
+// A replication that outgrows the capacities, the 32-bit clock or (narrow) the delay range is handed to mmc_kernel above.
 // ---------------------------------------------------------------------------------------------
 namespace {
-constexpr int MF_THREADS = 176;
-constexpr int MF_BLOCKS_PER_SM = 2;
 constexpr int MF_HEAP = 64;
 constexpr int MF_WAITERS = 64;
 #ifndef CXB_PATH_PUSH
@@ -203,8 +205,20 @@ constexpr int MF_WAITERS = 64;
 #define CXB_MMC_PUSHES_PER_TURN 2
 #endif
 constexpr int MF_PUSHES_PER_TURN = CXB_MMC_PUSHES_PER_TURN;
-constexpr uint32_t MF_HANDLER = 1u << 16;
-constexpr uint32_t MF_NOOP = TAG_NO_TARGET;
+
+struct mmc_wide_tokens {
+    static constexpr int THREADS = 176, BLOCKS_PER_SM = 2;
+    using heap_t = heap32x<THREADS>;
+    using word_t = uint2;
+    static constexpr uint32_t HANDLER = 1u << 16, TARGET_MASK = 0xFFFFu, NOOP = TAG_NO_TARGET;
+};
+struct mmc_narrow_tokens {
+    static constexpr int THREADS = 288, BLOCKS_PER_SM = 2;
+    using heap_t = heap_rel<THREADS, 12>;
+    using word_t = uint32_t;
+    static constexpr uint32_t HANDLER = 1u << 11, TARGET_MASK = 0x7FFu, NOOP = 0x7FFu;
+};
+static_assert(TAG_NO_TARGET == 0xFFFFu, "the wide tokens' no-target ordinal is the generic engine's");
 
 struct wait_list16 {
     lane_array<uint16_t> who;
@@ -237,15 +251,16 @@ constexpr int MF_SAVED_HEADER = 16;
 // heap, wait list, and the words of the customers that a scheduled token or a waiter still refers to (nobody else
 // can be touched again; at most heap + wait-list entries instead of 8 KB for all 1000); the next launch restores it.  DONE / REPLAY as
 // in the other kernels.  A separate instantiation, so that the plain run() path carries none of it.
-template <bool STATEFUL>
-__global__ void __launch_bounds__(MF_THREADS, MF_BLOCKS_PER_SM)
+template <bool STATEFUL, typename TK>
+__global__ void __launch_bounds__(TK::THREADS, TK::BLOCKS_PER_SM)
 mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, philox_schedule keys,
                 uint32_t until, mmc_saved st) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     stage_log_table(table, sh.log_table);
-    uint2 *heap = environment32<MF_THREADS>::carve_heap(cursor, MF_HEAP);
+    constexpr uint32_t MF_HANDLER = TK::HANDLER, MF_NOOP = TK::NOOP;
+    typename TK::word_t *heap = carve<typename TK::word_t>(cursor, MF_HEAP).base;
     wait_list16 waiters;
     waiters.who = carve<uint16_t>(cursor, MF_WAITERS);
     waiters.n = 0;
@@ -256,7 +271,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     const int64_t patience_ticks = real_to_sim(prm.patience, sh.clk);  // env.timeout(patience)
     const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
 
-    heap32x<MF_THREADS> env;   // (every access to the heap goes through env: explicit ld/st.shared)
+    typename TK::heap_t env;   // (every access to the heap goes through env: explicit ld/st.shared)
     env.init(heap, MF_HEAP);
     uint64_t rep = 0;
     uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
@@ -305,7 +320,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                         total_wait = bits_as_double((uint64_t)sv[11 * m] | ((uint64_t)sv[12 * m] << 32));
                         waiters.n = (int)sv[13 * m];
                         int at = MF_SAVED_HEADER;
-                        for (uint32_t k = 0; k < env.n; ++k) env.set_entry(k, make_uint2(sv[(size_t)(at + 2 * k) * m], sv[(size_t)(at + 2 * k + 1) * m]));
+                        env.restart_epoch();     // (narrow tokens: times relative to the restored clock; every token is later)
+                        for (uint32_t k = 0; k < env.n; ++k) env.set_token(k, sv[(size_t)(at + 2 * k) * m], sv[(size_t)(at + 2 * k + 1) * m]);
                         at += 2 * MF_HEAP;
                         for (int k = 0; k < waiters.n; ++k) waiters.who[k] = (uint16_t)sv[(size_t)(at + k) * m];
                         at += MF_WAITERS;
@@ -350,11 +366,11 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
         if (active && next_push == n_total) {
             // The token at the root names the event: decode it before the heap moves, and start the load of the
             // customer word it refers to (global memory, L2 latency) so that the sift-down hides it.
-            const uint2 root = env.entry(0);
+            const typename TK::word_t root = env.entry(0);
             token32 t;
-            t.time = root.x;
-            t.tag = root.y;
-            const uint32_t target = t.tag & 0xFFFFu;
+            t.time = env.time_of(root);
+            t.tag = env.tag_of(root);
+            const uint32_t target = t.tag & TK::TARGET_MASK;
             const bool is_customer_token = target >= 2 && target != MF_NOOP;   // customer(id), acquire_proc(id) or their handler
             uint64_t *const w = &cust[(uint64_t)(is_customer_token ? (target - 2) >> 1 : 0u) * total_threads];
             uint64_t s = *w;
@@ -485,7 +501,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     const uint32_t time = own < 0 ? env.now : (own == 0 ? p_time[0] : p_time[1]);
                     const uint32_t tag = own < 0 ? (uint32_t)waiters.who[next_push] : (own == 0 ? p_tag[0] : p_tag[1]);
 #if CXB_PATH_PUSH
-                    env.schedule_path<6>(time, tag);     // 64 entries: at most 6 ancestors, loaded in one round trip
+                    env.template schedule_path<6>(time, tag);     // 64 entries: at most 6 ancestors, loaded in one round trip
 #else
                     env.schedule(time, tag);
 #endif
@@ -531,9 +547,9 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                             sv[13 * m] = (uint32_t)waiters.n;
                             int at = MF_SAVED_HEADER;
                             for (uint32_t k = 0; k < env.n; ++k) {
-                                const uint2 e = env.entry(k);
-                                sv[(size_t)(at + 2 * k) * m] = e.x;
-                                sv[(size_t)(at + 2 * k + 1) * m] = e.y;
+                                const token32 e = env.token_at(k);
+                                sv[(size_t)(at + 2 * k) * m] = e.time;
+                                sv[(size_t)(at + 2 * k + 1) * m] = e.tag;
                             }
                             at += 2 * MF_HEAP;
                             for (int k = 0; k < waiters.n; ++k) sv[(size_t)(at + k) * m] = waiters.who[k];
@@ -551,7 +567,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                                 sv[(size_t)(at + 3 * n_pairs + 2) * m] = (uint32_t)(wv >> 32);
                                 ++n_pairs;
                             };
-                            for (uint32_t k = 0; k < env.n; ++k) save_customer(env.entry(k).y & 0xFFFFu);
+                            for (uint32_t k = 0; k < env.n; ++k) save_customer(env.token_at(k).tag & TK::TARGET_MASK);
                             for (int k = 0; k < waiters.n; ++k) save_customer(waiters.who[k]);
                             sv[14 * m] = n_pairs;
                             sv[0] = MF_PHASE_SAVED;
@@ -580,8 +596,10 @@ size_t mmc_smem_bytes() {
 }
 
 namespace {
+template <typename TK>
 size_t mmc_fast_smem_bytes() {
-    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 + (size_t)MF_THREADS * (MF_HEAP * 8 + MF_WAITERS * 2);
+    return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
+           (size_t)TK::THREADS * (MF_HEAP * sizeof(typename TK::word_t) + MF_WAITERS * 2);
 }
 // 32-bit event counter and clock: a variate is at most 36.05 / rate
 bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
@@ -590,11 +608,41 @@ bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
     return 36.05 * tpu / slow < 1073741824.0 && p.patience * tpu < 1073741824.0 && p.n_customers < 100000000ull &&
            p.servers < 0xFFFFFFFFull;
 }
+
+template <typename TK>
+cudaError_t launch_mmc_fast(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
+                            uint64_t *customer_state, int sm_count, cudaStream_t stream, const mmc_saved &st) {
+    const size_t fsmem = mmc_fast_smem_bytes<TK>();
+    cudaError_t e = cudaFuncSetAttribute(mmc_fast_kernel<false, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mmc_fast_kernel<true, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (e != cudaSuccess) return e;
+    const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
+    const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
+    const int blocks = sm_count * TK::BLOCKS_PER_SM;
+    if (st.words) mmc_fast_kernel<true, TK><<<blocks, TK::THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
+    else mmc_fast_kernel<false, TK><<<blocks, TK::THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
+    return cudaGetLastError();
+}
 }  // namespace
 
-// per-customer words are indexed [customer][global thread]: sized for the larger of the two grids
-int mmc_blocks(int sm_count) { return sm_count * MF_BLOCKS_PER_SM; }
-int mmc_threads() { return MF_THREADS > MMC_THREADS ? MF_THREADS : MMC_THREADS; }
+// Narrow tokens: ordinals up to 3 + 2 (n - 1) must stay below the no-target code 2047; the patience always fits or
+// never does; a service or inter-arrival time is an exponential variate, so the kernel is chosen when one passes the
+// delay limit with probability below e^-18 per draw (as aloha_compact_applies) and the replication that draws one is
+// redone by the 64-bit kernel.  (CXXDES_B200_MMC_TAIL: the exponent, for the tests of that hand-over.)
+bool mmc_narrow_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
+    if (!mmc_fast_applies(p, sh) || p.n_customers > 1022) return false;
+    const double tpu = (double)sh.clk.ticks_per_unit, limit = (double)mmc_narrow_tokens::heap_t::DELAY_LIMIT;
+    const double slow = p.lambda < p.mu ? p.lambda : p.mu;
+    double tail = 18.0;
+    if (const char *text = getenv("CXXDES_B200_MMC_TAIL")) tail = atof(text) > 0.0 ? atof(text) : tail;
+    return tail * tpu / slow < limit && p.patience * tpu < limit;
+}
+
+// per-customer words are indexed [customer][global thread]: sized for the largest of the grids
+int mmc_blocks(int sm_count) { return sm_count * 2; }
+int mmc_threads() { return mmc_narrow_tokens::THREADS; }
+static_assert(mmc_narrow_tokens::THREADS * mmc_narrow_tokens::BLOCKS_PER_SM >= mmc_wide_tokens::THREADS * mmc_wide_tokens::BLOCKS_PER_SM &&
+              mmc_narrow_tokens::THREADS * 2 >= MMC_THREADS, "customer words are sized for the narrow-token grid");
 
 bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh) { return mmc_fast_applies(prm, sh); }
 size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {
@@ -603,21 +651,14 @@ size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {
 
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches, const mmc_saved &st) {
+                       int *launches, const mmc_saved &st, bool wide_tokens) {
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel<environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (mmc_fast_applies(prm, sh)) {
-        const size_t fsmem = mmc_fast_smem_bytes();
-        e = cudaFuncSetAttribute(mmc_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mmc_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-        if (e != cudaSuccess) return e;
-        const uint32_t until = (sh.run_until < 0 || sh.run_until >= 0xFFFFFFFFll) ? 0xFFFFFFFFu : (uint32_t)sh.run_until;
-        const philox_schedule keys = philox_schedule_of((uint32_t)sh.seed, (uint32_t)(sh.seed >> 32));
-        if (st.words) mmc_fast_kernel<true><<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
-        else mmc_fast_kernel<false><<<sm_count * MF_BLOCKS_PER_SM, MF_THREADS, fsmem, stream>>>(prm, sh, out, customer_state, keys, until, st);
+        if (!wide_tokens && mmc_narrow_applies(prm, sh)) e = launch_mmc_fast<mmc_narrow_tokens>(prm, sh, out, customer_state, sm_count, stream, st);
+        else e = launch_mmc_fast<mmc_wide_tokens>(prm, sh, out, customer_state, sm_count, stream, st);
         ++*launches;
-        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, sh.retry_list, sh.retry_count,
                                                                         list_cursor, trace_sink{});

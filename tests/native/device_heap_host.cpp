@@ -79,26 +79,28 @@ int check32(uint32_t seed, int capacity, int n_ops, uint32_t time_span, bool fla
     return 0;
 }
 
-// heap24x: 4-byte tokens relative to a moving epoch.  Same check, with the clock running far enough for many rebases
+// heap_rel (heap24x = 8 code bits: ALOHA; 12 code bits: M/M/c): 4-byte tokens relative to a moving epoch.  Same check, with the clock running far enough for many rebases
 // (time steps up to `time_span`, so a run of 3000 operations passes REBASE_AT several times when the span is large)
 // and the code byte drawn so that it can never decide an order that libstdc++ would not.
-int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *rebases, bool path = false) {
+template <int CODE_BITS>
+int check_rel(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *rebases, bool path = false) {
     std::mt19937 rng(seed);
     uint32_t *column = host_shared + 16;
-    heap24x<1> env;
+    heap_rel<1, CODE_BITS> env;
+    constexpr uint32_t CODES = 1u << CODE_BITS;
     env.init(column, capacity);
     std::priority_queue<ref_token, std::vector<ref_token>, ref_comp> ref;
-    std::vector<uint32_t> serial_of_code(256, 0);   // the token a code byte stands for (a code is live at most once)
+    std::vector<uint32_t> serial_of_code(CODES, 0);   // the token a code byte stands for (a code is live at most once)
     uint32_t next_serial = 1;
     for (int k = 0; k < n_ops; ++k) {
         const bool push = ref.empty() || ((int)ref.size() < capacity && rng() % 100 < 55);
         if (push) {
-            uint32_t code = rng() & 0xFFu;
-            while (serial_of_code[code]) code = (code + 1) & 0xFFu;
+            uint32_t code = rng() & (CODES - 1);
+            while (serial_of_code[code]) code = (code + 1) & (CODES - 1);
             const uint32_t t = env.now + rng() % time_span;
             const uint32_t epoch_before = env.epoch;
             // (path: every ancestor in one round trip, LEVELS = 8 covers indices below 511)
-            if (path) env.schedule_path<8>(t, code);
+            if (path) env.template schedule_path<8>(t, code);
             else env.schedule(t, code);
             if (env.epoch != epoch_before) ++*rebases;
             if (env.status) return 1;
@@ -108,12 +110,12 @@ int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *re
         } else {
             const uint32_t root = env.entry(0);
             env.pop_after_top();
-            const uint32_t time = env.time_of(root), code = root & 0xFFu;
+            const uint32_t time = env.time_of(root), code = env.tag_of(root);
             env.now = time > env.now ? time : env.now;
             const ref_token want = ref.top();
             ref.pop();
             if (time != want.time || serial_of_code[code] != want.tag) {
-                std::fprintf(stderr, "heap24x: seed %u op %d: popped (%u, code %u), std::priority_queue (%llu, %u)\n", seed, k,
+                std::fprintf(stderr, "heap_rel: seed %u op %d: popped (%u, code %u), std::priority_queue (%llu, %u)\n", seed, k,
                              time, code, (unsigned long long)want.time, want.tag);
                 return 1;
             }
@@ -123,7 +125,7 @@ int check24(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *re
     }
     // a delay the 24-bit window cannot hold is refused, never wrapped
     if (env.n >= env.cap) return 0;
-    env.schedule(env.now + heap24x<1>::DELAY_LIMIT, 0);
+    env.schedule(env.now + heap_rel<1, CODE_BITS>::DELAY_LIMIT, 0);
     return (env.status & CXXDES_B200_REP_TIME_RANGE) ? 0 : 1;
 }
 
@@ -180,14 +182,19 @@ int main() {
     for (uint32_t seed = 1; seed <= 40; ++seed) {
         for (int capacity : {2, 3, 7, 8, 33, 64, 66, 200}) {
             for (uint32_t span : {1u, 2u, 5u, 1000u, 3000000u}) {
-                bad += check24(seed * 32452843u + capacity, capacity, 3000, span, &rebases);
-                bad += check24(seed * 49979687u + capacity, capacity, 3000, span, &rebases, true);
+                bad += check_rel<8>(seed * 32452843u + capacity, capacity, 3000, span, &rebases);
+                bad += check_rel<8>(seed * 49979687u + capacity, capacity, 3000, span, &rebases, true);
+                ops += 6000;
+            }
+            for (uint32_t span : {1u, 3u, 1000u, 190000u}) {       // 12 code bits: 20 bits of relative time
+                bad += check_rel<12>(seed * 86028121u + capacity, capacity, 3000, span, &rebases);
+                bad += check_rel<12>(seed * 67867967u + capacity, capacity, 3000, span, &rebases, true);
                 ops += 6000;
             }
         }
     }
     if (rebases < 1000) {
-        std::fprintf(stderr, "heap24x: only %ld rebases exercised\n", rebases);
+        std::fprintf(stderr, "heap_rel: only %ld rebases exercised\n", rebases);
         ++bad;
     }
     std::printf("device heaps vs std::priority_queue: %ld operations, %d mismatching runs\n", ops, bad);

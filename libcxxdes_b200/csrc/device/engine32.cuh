@@ -254,6 +254,7 @@ struct heap32x {
     uint32_t cap;
     uint32_t base;   // shared-memory address of entry 0 of this thread's column
 
+    static constexpr int EXTRA = 0;      // (no sentinel entry in front of the column; see heap_rel)
     __device__ __forceinline__ void init(uint2 *column, int capacity) {
         now = 0;
         n_events = 0;
@@ -356,7 +357,10 @@ struct heap32x {
     }
 
     // std::pop_heap, stl_heap.h:254-270 (__pop_heap) + :224-249 (__adjust_heap), then pop_back -- for a caller that
-    // has already loaded entry 0 (it decodes the event from it before the moves).
+    // has already loaded entry 0 (it decodes the event from it before the moves).  REINSERT_LEVELS > 0: the displaced last
+    // element goes back in with a path-parallel sift-up from the leaf the hole ended at (one round trip of that many
+    // ancestor loads) instead of the loop that usually stops after its first look: measured per kernel.
+    template <int REINSERT_LEVELS = 0>
     __device__ __forceinline__ void pop_after_top() {
         const uint32_t len = n - 1;
         if (len > 0) {
@@ -390,7 +394,8 @@ struct heap32x {
                 sts(at(hole), lds(at(child)));
                 hole = child;
             }
-            sift_up(hole, v.x, v.y);
+            if constexpr (REINSERT_LEVELS > 0) sift_up_path<REINSERT_LEVELS>(hole, v.x, v.y);
+            else sift_up(hole, v.x, v.y);
         }
         n = len;
     }
@@ -432,6 +437,9 @@ struct heap_rel {
     uint32_t cap;
     uint32_t base;       // shared-memory address of entry 0 of this thread's column
 
+    // `column` holds EXTRA + capacity words: word 0 is a sentinel in front of entry 0 ("entry -1", relative time 0 and
+    // code 0: never later than anything), which the path-parallel sift-up reads for the levels above the root.
+    static constexpr int EXTRA = 1;
     __device__ __forceinline__ void init(uint32_t *column, int capacity) {
         now = 0;
         epoch = 0;
@@ -440,7 +448,8 @@ struct heap_rel {
         status = 0;
         n = 0;
         cap = (uint32_t)capacity;
-        base = shared_address(column);
+        base = shared_address(column) + EB;
+        sts(base - EB, 0u);
     }
 #if defined(__CUDACC__)
     static __device__ __forceinline__ uint32_t shared_address(uint32_t *column) { return (uint32_t)__cvta_generic_to_shared(column); }
@@ -519,12 +528,12 @@ struct heap_rel {
     __device__ __forceinline__ void sift_up_path(uint32_t hole, uint32_t word) const {
         const uint32_t top = word | CODE_MASK;
         uint32_t addr[LEVELS + 1], e[LEVELS];
-        uint32_t a = hole;
+        // ancestor k of node h is ((h + 1) >> k) - 1; beyond the root that is -1, the sentinel in front of the column
+        const uint32_t h1 = hole + 1u, before = base - EB;
         addr[0] = at(hole);
 #pragma unroll
         for (int k = 0; k < LEVELS; ++k) {
-            a = (a - (a != 0u ? 1u : 0u)) >> 1;
-            addr[k + 1] = at(a);
+            addr[k + 1] = before + (h1 >> (k + 1)) * EB;
             e[k] = lds(addr[k + 1]);
         }
         uint32_t dest = addr[0];
@@ -553,6 +562,8 @@ struct heap_rel {
     }
 
     // std::pop_heap (stl_heap.h:224-270) then pop_back, for a caller that has already loaded entry 0
+    // (REINSERT_LEVELS: see heap32x::pop_after_top)
+    template <int REINSERT_LEVELS = 0>
     __device__ __forceinline__ void pop_after_top() {
         const uint32_t len = n - 1;
         if (len > 0) {
@@ -585,7 +596,8 @@ struct heap_rel {
                 sts(at(hole), lds(at(child)));
                 hole = child;
             }
-            sift_up(hole, v);
+            if constexpr (REINSERT_LEVELS > 0) sift_up_path<REINSERT_LEVELS>(hole, v);
+            else sift_up(hole, v);
         }
         n = len;
     }

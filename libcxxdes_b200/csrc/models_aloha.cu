@@ -445,7 +445,7 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
     stage_log_table(table, sh.log_table);
     const int N = (int)prm.num_stations;
     const int heap_cap = N + 2;
-    const lane_array<uint32_t> heap_words = carve<uint32_t>(cursor, heap_cap);
+    const lane_array<uint32_t> heap_words = carve<uint32_t>(cursor, heap_cap + heap24x<AF_THREADS>::EXTRA);   // (+ the sentinel)
     uint32_t *heap = heap_words.base;
     // completed transmissions of every station (the `for` counter of aloha.cpp:53): 16 bits each, [station][thread]
     const uint32_t cnt_base = (uint32_t)__cvta_generic_to_shared(carve<uint16_t>(cursor, N).base);
@@ -464,6 +464,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
     env.init(heap, heap_cap);
     uint64_t rep = 0, active_set = 0, collided = 0, pc_tx = 0;
     uint32_t successful = 0, main_pc = 0, remaining = 0, ctr2 = 0, ctr3 = 0;
+    uint32_t n_active = 0;   // |active_set| (the size() of aloha.cpp:73's set), kept beside the mask
+    uint32_t root = 0;       // entry 0 of the lane's heap: loaded once, at the end of the event before (or at the claim)
     bool armed = false;
     aloha_rep_params rp{};
     divisor rate{};
@@ -526,13 +528,15 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                         env.epoch = sv[15 * n];
                         for (uint32_t k = 0; k < env.n; ++k) env.set_entry(k, sv[(size_t)(16 + 2 * k) * n]);
                         for (int k = 0; k < N; ++k) cnt_store((uint32_t)k, sv[(size_t)(17 + 2 * k) * n]);
+                        n_active = (uint32_t)__popcll(active_set);
                     } else {
                         active_set = collided = pc_tx = 0;
-                        successful = 0; main_pc = 0; remaining = 0; armed = false;
+                        successful = 0; main_pc = 0; remaining = 0; armed = false; n_active = 0;
                         env.schedule(0, CODE_MAIN);  // environment::bind(co_main)
                     }
                     active = true;
-                    if (STATEFUL && phase == AF_PHASE_SAVED && env.next_time() > until) {
+                    root = env.entry(0);
+                    if (STATEFUL && phase == AF_PHASE_SAVED && env.time_of(root) > until) {
                         // nothing of this replication falls into the piece: only its clock moves (environment.ipp:194)
                         if (sh.run_until > (int64_t)env.now) {
                             out.end_time[rep] = sh.run_until;
@@ -558,7 +562,6 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             // same trip count in every lane (the heaps hold N or N + 1 tokens), and the predicated fixed-depth
             // sift-up that was tried (engine32.cuh schedule_flat) costs 78 instructions for every lane where the loop
             // costs ~7 per level actually climbed.
-            const uint32_t root = env.entry(0);
             const uint32_t code = root & 0xFFu;
             const bool is_station = code - 1u < 64u;
             const uint32_t i = cnt_load(is_station ? code - 1u : 0u);
@@ -566,7 +569,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
             const int64_t wait_ticks = real_to_sim(exponential_from_bits(bits, rate, table), sh.clk);
 
-            env.pop_after_top();                                   // environment::step, environment.ipp:117-126
+            env.pop_after_top<6>();                                // environment::step, environment.ipp:117-126 (the displaced
+                                                                   // last element re-inserted path-parallel: +1.8 %)
             token32 t;
             t.time = env.time_of(root);
             t.tag = code;
@@ -582,8 +586,9 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             successful += (tx_end && !(collided & bit)) ? 1u : 0u;
             pc_tx = tx_end ? pc_tx & ~bit : (tx_start ? pc_tx | bit : pc_tx);
             active_set = tx_end ? active_set & ~bit : (tx_start ? active_set | bit : active_set);
+            n_active += (tx_start ? 1u : 0u) - (tx_end ? 1u : 0u);
             collided = tx_start ? collided & ~bit : collided;
-            collided |= (tx_start && __popcll(active_set) > 1) ? active_set : 0ULL;
+            collided |= (tx_start && n_active > 1) ? active_set : 0ULL;
             // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time (== now)
             remaining -= is_handler ? 1u : 0u;
             const bool fire = is_handler && armed && remaining == 0;
@@ -615,18 +620,21 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                     push_tag = CODE_NOOP;
                 }
             }
-            // token at now + delay; the sum must stay inside 32 bits
-            const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
-            if (push && ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull)) env.status |= CXXDES_B200_REP_TIME_RANGE;
+            // token at now + delay: the delay must fit the relative time of a token, the sum 32 bits (anything else is
+            // redone by the 64-bit kernel)
+            if (push && ((uint64_t)delay >= (uint64_t)heap24x<AF_THREADS>::DELAY_LIMIT || env.now >= 0xFF000000u))
+                env.status |= CXXDES_B200_REP_TIME_RANGE;
+            const uint32_t when = env.now + (uint32_t)delay;
             // (every ancestor of the new leaf in one round trip: indices up to N + 1 = 65 are at most 6 levels deep)
 #if CXB_PATH_PUSH
-            if (push) env.schedule_path<6>((uint32_t)when, push_tag);
+            if (push) env.schedule_path<6>(when, push_tag);
 #else
-            if (push) env.schedule((uint32_t)when, push_tag);
+            if (push) env.schedule(when, push_tag);
 #endif
 
-            // environment::run / run_until (environment.ipp:179-196)
-            if (env.status || !env.has_event() || env.next_time() > until) {
+            // environment::run / run_until (environment.ipp:179-196); the root loaded here is the next event's
+            root = env.has_event() ? env.entry(0) : 0u;
+            if (env.status || !env.has_event() || env.time_of(root) > until) {
                 active = false;
                 if (env.status & CXXDES_B200_REP_TIME_RANGE) {
                     const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);
@@ -715,7 +723,7 @@ bool aloha_keeps_state(const cxxdes_b200_aloha_params &prm, const shard &sh) { r
 namespace {
 size_t aloha_compact_smem_bytes(uint32_t num_stations) {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
-           (size_t)AF_THREADS * (((size_t)num_stations + 2) * 4 + (size_t)num_stations * 2);
+           (size_t)AF_THREADS * (((size_t)num_stations + 2 + heap24x<AF_THREADS>::EXTRA) * 4 + (size_t)num_stations * 2);
 }
 }  // namespace
 

@@ -207,13 +207,21 @@ constexpr int MF_WAITERS = 64;
 constexpr int MF_PUSHES_PER_TURN = CXB_MMC_PUSHES_PER_TURN;
 
 struct mmc_wide_tokens {
-    static constexpr int THREADS = 176, BLOCKS_PER_SM = 2;
+    static constexpr int THREADS = 176, BLOCKS_PER_SM = 2, HEAP = MF_HEAP, WAITERS = MF_WAITERS;
     using heap_t = heap32x<THREADS>;
     using word_t = uint2;
     static constexpr uint32_t HANDLER = 1u << 16, TARGET_MASK = 0xFFFFu, NOOP = TAG_NO_TARGET;
 };
+#ifndef CXB_MMC_NT          // threads, blocks per SM, heap entries, waiters of the narrow-token kernel (A/B builds)
+#define CXB_MMC_NT 288
+#define CXB_MMC_NB 2
+#define CXB_MMC_NH 64
+#define CXB_MMC_NW 64
+#endif
+constexpr int MF_NARROW[4] = {CXB_MMC_NT, CXB_MMC_NB, CXB_MMC_NH, CXB_MMC_NW};
 struct mmc_narrow_tokens {
-    static constexpr int THREADS = 288, BLOCKS_PER_SM = 2;
+    static constexpr int THREADS = MF_NARROW[0], BLOCKS_PER_SM = MF_NARROW[1], HEAP = MF_NARROW[2], WAITERS = MF_NARROW[3];
+    static_assert(HEAP <= MF_HEAP && WAITERS <= MF_WAITERS, "saved state is laid out for 64 + 64");
     using heap_t = heap_rel<THREADS, 12>;
     using word_t = uint32_t;
     static constexpr uint32_t HANDLER = 1u << 11, TARGET_MASK = 0x7FFu, NOOP = 0x7FFu;
@@ -224,9 +232,10 @@ struct wait_list16 {
     lane_array<uint16_t> who;
     int n;
     // wait_awaitable::await_suspend, event.hpp:136-139
+    int cap;
     template <typename Env>
     __device__ __forceinline__ void wait(Env &env, uint32_t proc) {
-        if (n >= MF_WAITERS) {
+        if (n >= cap) {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
         }
@@ -260,9 +269,10 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     stage_log_table(table, sh.log_table);
     constexpr uint32_t MF_HANDLER = TK::HANDLER, MF_NOOP = TK::NOOP;
-    typename TK::word_t *heap = carve<typename TK::word_t>(cursor, MF_HEAP).base;
+    typename TK::word_t *heap = carve<typename TK::word_t>(cursor, TK::HEAP + TK::heap_t::EXTRA).base;
     wait_list16 waiters;
-    waiters.who = carve<uint16_t>(cursor, MF_WAITERS);
+    waiters.who = carve<uint16_t>(cursor, TK::WAITERS);
+    waiters.cap = TK::WAITERS;
     waiters.n = 0;
 
     const uint64_t total_threads = (uint64_t)gridDim.x * blockDim.x;
@@ -272,7 +282,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     const divisor d_lambda = make_divisor(prm.lambda), d_mu = make_divisor(prm.mu);
 
     typename TK::heap_t env;   // (every access to the heap goes through env: explicit ld/st.shared)
-    env.init(heap, MF_HEAP);
+    env.init(heap, TK::HEAP);
     uint64_t rep = 0;
     uint32_t ctr2 = 0, ctr3 = 0, value = 0, i = 0, served = 0, balked = 0, main_pc = 0, source_pc = 0;
     double total_wait = 0.0;
@@ -303,7 +313,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                     const uint64_t grep = sh.first_replication + rep;
                     ctr2 = (uint32_t)grep;
                     ctr3 = (uint32_t)(grep >> 32);
-                    env.init(heap, MF_HEAP);
+                    env.init(heap, TK::HEAP);
                     if (STATEFUL && phase == MF_PHASE_SAVED) {
                         const uint32_t *sv = st.words + rep;
                         const size_t m = st.n_replications;
@@ -394,9 +404,14 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 if ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull) env.status |= CXXDES_B200_REP_TIME_RANGE;
                 push_at((uint32_t)when, tag);
             };
+            // digest of the popped token, once for all kinds of events (three copies in the branches ran one after the other)
+            {
+                const bool is_handler = (t.tag & MF_HANDLER) != 0, is_noop = !is_handler && target == MF_NOOP;
+                env.fold(t.time, is_handler ? (uint32_t)TOKEN_HANDLER : (is_noop ? (uint32_t)TOKEN_NOOP : (uint32_t)TOKEN_RESUME),
+                         is_noop ? (uint32_t)PROC_NONE : target);
+            }
             if (t.tag & MF_HANDLER) {
                 // any_of handler of customer (target - 2) / 2: any_of.ipp:9-26
-                env.fold(t.time, TOKEN_HANDLER, target);
                 const uint64_t remaining = ((s & C_REM) >> C_REM_SHIFT) - 1;
                 s = (s & ~C_REM) | (remaining << C_REM_SHIFT);
                 if ((s & C_ARMED) && remaining < 2) {
@@ -405,9 +420,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
                 }
                 *w = s;
             } else if (target == MF_NOOP) {
-                env.fold(t.time, TOKEN_NOOP, PROC_NONE);
+                // (nothing to resume)
             } else {
-                env.fold(t.time, TOKEN_RESUME, target);
                 if (target == 0) {
                     if (main_pc == 0) {
                         push_at(env.now, 1);  // co_await source(): start token; completion targets main
@@ -599,7 +613,7 @@ namespace {
 template <typename TK>
 size_t mmc_fast_smem_bytes() {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
-           (size_t)TK::THREADS * (MF_HEAP * sizeof(typename TK::word_t) + MF_WAITERS * 2);
+           (size_t)TK::THREADS * ((TK::HEAP + TK::heap_t::EXTRA) * sizeof(typename TK::word_t) + TK::WAITERS * 2);
 }
 // 32-bit event counter and clock: a variate is at most 36.05 / rate
 bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
@@ -639,10 +653,10 @@ bool mmc_narrow_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {
 }
 
 // per-customer words are indexed [customer][global thread]: sized for the largest of the grids
-int mmc_blocks(int sm_count) { return sm_count * 2; }
+int mmc_blocks(int sm_count) { return sm_count * mmc_narrow_tokens::BLOCKS_PER_SM; }
 int mmc_threads() { return mmc_narrow_tokens::THREADS; }
 static_assert(mmc_narrow_tokens::THREADS * mmc_narrow_tokens::BLOCKS_PER_SM >= mmc_wide_tokens::THREADS * mmc_wide_tokens::BLOCKS_PER_SM &&
-              mmc_narrow_tokens::THREADS * 2 >= MMC_THREADS, "customer words are sized for the narrow-token grid");
+              mmc_narrow_tokens::THREADS * mmc_narrow_tokens::BLOCKS_PER_SM >= MMC_THREADS, "customer words are sized for the narrow-token grid");
 
 bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh) { return mmc_fast_applies(prm, sh); }
 size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {

@@ -109,7 +109,8 @@ int check_rel(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *
             ++next_serial;
         } else {
             const uint32_t root = env.entry(0);
-            env.pop_after_top();
+            if (path) env.template pop_after_top<8>();      // (re-insertion of the displaced element path-parallel too)
+            else env.pop_after_top();
             const uint32_t time = env.time_of(root), code = env.tag_of(root);
             env.now = time > env.now ? time : env.now;
             const ref_token want = ref.top();

@@ -367,7 +367,11 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
             // token at now + delay; the sum must stay inside 32 bits
             const uint64_t when = (uint64_t)env.now + (uint64_t)delay;
             if (push && ((uint64_t)delay >= (1ULL << 31) || when >= 0xFFFFFFFFull)) env.status |= CXXDES_B200_REP_TIME_RANGE;
+#if CXB_PATH_PUSH
+            if (push) env.schedule_path<6>((uint32_t)when, push_tag);   // every ancestor of the new leaf in one round trip
+#else
             if (push) env.schedule((uint32_t)when, push_tag);
+#endif
 
             // environment::run / run_until (environment.ipp:179-196)
             if (env.status || !env.has_event() || env.next_time() > until) {
@@ -462,7 +466,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
 
     heap24x<AF_THREADS> env;   // 4-byte tokens (time - epoch) << 8 | code; every access goes through env
     env.init(heap, heap_cap);
-    uint64_t rep = 0, active_set = 0, collided = 0, pc_tx = 0;
+    uint64_t rep = 0, active_set = 0, collided = 0;   // (a station is past its `insert` exactly while it is in the set:
+                                                      // the resume-point mask of the 8-byte kernel IS active_set here)
     uint32_t successful = 0, main_pc = 0, remaining = 0, ctr2 = 0, ctr3 = 0;
     uint32_t n_active = 0;   // |active_set| (the size() of aloha.cpp:73's set), kept beside the mask
     uint32_t root = 0;       // entry 0 of the lane's heap: loaded once, at the end of the event before (or at the claim)
@@ -520,7 +525,6 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                         env.hash = (uint64_t)sv[4 * n] | ((uint64_t)sv[5 * n] << 32);
                         active_set = (uint64_t)sv[6 * n] | ((uint64_t)sv[7 * n] << 32);
                         collided = (uint64_t)sv[8 * n] | ((uint64_t)sv[9 * n] << 32);
-                        pc_tx = (uint64_t)sv[10 * n] | ((uint64_t)sv[11 * n] << 32);
                         successful = sv[12 * n];
                         main_pc = sv[13 * n] & 0xFFu;
                         armed = (sv[13 * n] >> 8) != 0;
@@ -530,7 +534,7 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                         for (int k = 0; k < N; ++k) cnt_store((uint32_t)k, sv[(size_t)(17 + 2 * k) * n]);
                         n_active = (uint32_t)__popcll(active_set);
                     } else {
-                        active_set = collided = pc_tx = 0;
+                        active_set = collided = 0;
                         successful = 0; main_pc = 0; remaining = 0; armed = false; n_active = 0;
                         env.schedule(0, CODE_MAIN);  // environment::bind(co_main)
                     }
@@ -580,11 +584,10 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             const bool is_handler = code == CODE_HANDLER, is_main = code == CODE_MAIN;
             const uint64_t bit = is_station ? 1ULL << ((code - 1u) & 63u) : 0ULL;
             // station, aloha.cpp:51-71
-            const bool tx_end = (pc_tx & bit) != 0;                          // frame finished: erase, count, draw (:62-69)
+            const bool tx_end = (active_set & bit) != 0;                          // frame finished: erase, count, draw (:62-69)
             const bool tx_start = is_station && !tx_end && i < rp.pps;       // collided = false; insert; check (:55-59,73-78)
             const bool st_return = is_station && !tx_end && !(i < rp.pps);   // co_return -> completion with the all_of handler
             successful += (tx_end && !(collided & bit)) ? 1u : 0u;
-            pc_tx = tx_end ? pc_tx & ~bit : (tx_start ? pc_tx | bit : pc_tx);
             active_set = tx_end ? active_set & ~bit : (tx_start ? active_set | bit : active_set);
             n_active += (tx_start ? 1u : 0u) - (tx_end ? 1u : 0u);
             collided = tx_start ? collided & ~bit : collided;
@@ -661,8 +664,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                             sv[7 * n] = (uint32_t)(active_set >> 32);
                             sv[8 * n] = (uint32_t)collided;
                             sv[9 * n] = (uint32_t)(collided >> 32);
-                            sv[10 * n] = (uint32_t)pc_tx;
-                            sv[11 * n] = (uint32_t)(pc_tx >> 32);
+                            sv[10 * n] = (uint32_t)active_set;
+                            sv[11 * n] = (uint32_t)(active_set >> 32);
                             sv[12 * n] = successful;
                             sv[13 * n] = main_pc | ((armed ? 1u : 0u) << 8);
                             sv[14 * n] = remaining;

@@ -81,7 +81,7 @@ def test_gpu_cooperative_aloha_equals_thread_per_replication_at_size(built):
     p = cls(64, 50, 0.1, 3.0, 1.0, 20.0, 0)
     a, acc_a, name_a = _run(p, 60000, clock_pairs(g), 5, flags=abi.FLAG_COOP_HEAP)
     b, acc_b, name_b = _run(p, 60000, clock_pairs(g), 5)
-    assert (name_a, name_b) == ("aloha_coop_kernel", "aloha_fast_kernel<false>")
+    assert (name_a, name_b) == ("aloha_coop_kernel", "aloha_compact_kernel<false>")
     golden_util.assert_columns_equal(a, b, what="cooperative vs thread-per-replication")
     assert acc_a.trace_hash_sum == acc_b.trace_hash_sum and acc_a.n_errors == 0
 

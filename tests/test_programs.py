@@ -521,7 +521,7 @@ def test_gpu_aloha_as_a_program_matches_the_aloha_kernel(port):
     model = ens.run().fetch()
     name = ens.kernel_name()
     ens.close()
-    assert name == "aloha_fast_kernel<false>" and not got.status.any() and not model.status.any()
+    assert name == "aloha_compact_kernel<false>" and not got.status.any() and not model.status.any()
     assert np.array_equal(got.n_events, model.n_events) and np.array_equal(got.end_time, model.end_time)
     assert np.array_equal(got.trace_hash, model.trace_hash)
     want = port.run(abi.MODEL_PROGRAM, prog.to_params(), oracles.MM1_CLOCK, 9, 5, 64, threads=os.cpu_count())

@@ -274,8 +274,9 @@ enum {
                                              lanes (sub-warp cooperative push / pop with ballots) instead of one thread
                                              per replication (A/B measurements; identical results) */
     CXXDES_B200_FLAG_WIDE_TOKENS = 8u     /* ALOHA, M/M/c: first pass on 8-byte tokens (time, tag) even where the kernel with
-                                             4-byte tokens (time relative to a moving epoch + a short code) applies (A/B
-                                             measurements; identical results) */
+                                             4-byte tokens (time relative to a moving epoch + a short code) applies;
+                                             memory hierarchy: 64-bit stamps and 32-bit addresses in shared memory even
+                                             where 32 / 16 bits provably suffice (A/B measurements; identical results) */
 };
 
 /* Number of CUDA devices visible (0 and an error string when there is none). */

@@ -364,7 +364,8 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             rc = saved_state_for(e, until, archsim_saved_words(e->params.arch), &st.words, &st.resume);
             if (rc) return rc;
             wrote_saved = st.words != nullptr;
-            CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream, st));
+            CUDA_TRY(launch_archsim(e->params.arch, sh, e->cols, e->sm_count, e->stream, st,
+                                    (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0));
             launches = 1;
             break;
         }
@@ -807,7 +808,8 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
                                         ? "mmc_fast_kernel<false,narrow>" : "mmc_fast_kernel<false,wide>");
             break;
         case CXXDES_B200_MODEL_ARCHSIM:
-            snprintf(buf, buf_size, "archsim_kernel<%s>", e->params.arch.n_requesters == 1 ? "1 requester" : "k requesters");
+            snprintf(buf, buf_size, "archsim_kernel<%s%s>", e->params.arch.n_requesters == 1 ? "1 requester" : "k requesters",
+                     archsim_uses_narrow_layout(e->params.arch, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0) ? ",narrow" : "");
             break;
         case CXXDES_B200_MODEL_PROGRAM:
             snprintf(buf, buf_size, e->prog_fast.valid ? "program_fast_kernel<false>" : "program_kernel");

@@ -107,8 +107,9 @@ struct archsim_saved {        // run_until / run_for in pieces (nullptr words = 
     int resume;               // 0: every replication starts from tick 0 (first piece, or after reset)
 };
 size_t archsim_saved_words(const cxxdes_b200_archsim_params &p);
+bool archsim_uses_narrow_layout(const cxxdes_b200_archsim_params &prm, bool wide_layout);   // 32-bit stamps, 16-bit addresses
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
-                           int sm_count, cudaStream_t stream, const archsim_saved &st);
+                           int sm_count, cudaStream_t stream, const archsim_saved &st, bool wide_layout);
 
 // ---- process programs (program_kernel.cu) ----
 struct device_program {  // cxxdes_b200_program with device pointers; rates as {d, RN(1/d)}

@@ -10,6 +10,8 @@
 // mem1.load = 0x200 + q, its _Co_with = 0x8200 + q.  All priorities are 0.
 // The block store is the model's (user code): an ordered array, eviction = least last_access,
 // lowest position on ties, erase keeps order (same rule as the oracle's model).
+#include <type_traits>
+
 #include "device/models_common.cuh"
 #include "device/trace.cuh"
 #include "kernels.h"
@@ -21,6 +23,33 @@ namespace {
 constexpr int ARCH_THREADS = 128;
 constexpr int ARCH_MAX_REQ = 16;
 constexpr int ARCH_MAX_CAP = 64;
+constexpr int ARCH_MAX_BLOCKS_PER_SM = 8;
+
+// mutex::event_ of a level when every waiter has priority 0 and latency 0 (all of them are _Co_with coroutines of this
+// model): the process ordinal alone, 16 bits.  Same interface as engine.cuh's wait_list.
+struct wait_list_plain {
+    lane_array<uint16_t> who;
+    int n;
+    int cap;
+    __device__ __forceinline__ void init(lane_array<uint16_t> w, int capacity) {
+        who = w;
+        n = 0;
+        cap = capacity;
+    }
+    template <typename Env>
+    __device__ __forceinline__ void wait(Env &env, uint32_t proc, int64_t) {      // event.hpp:136-139
+        if (n >= cap) {
+            env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
+            return;
+        }
+        who[n++] = (uint16_t)proc;
+    }
+    template <typename Env>
+    __device__ __forceinline__ void wake(Env &env) {                              // event.hpp:125-134, list order
+        for (int i = 0; i < n; ++i) env.schedule(env.now, 0, make_tag((uint32_t)who[i]));
+        n = 0;
+    }
+};
 
 // Per-requester state: one entry per requester in shared memory -- or, in the instantiation for the shipped
 // sequential driver (one requester), a register.
@@ -46,7 +75,12 @@ constexpr int ARCH_SAVED_HEADER = 24;
 // next launch continues from it; finished replications keep phase DONE.  Separate instantiations, so that the plain
 // run() path carries none of it.
 // ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
-template <bool SINGLE, bool STATEFUL, typename ENV = environment>
+// NARROW: the model's own arrays in half the shared memory -- time stamps in 32 bits, addresses in 16, wait lists as
+// bare 16-bit ordinals -- chosen at launch when the run provably ends before tick 2^31 (archsim_narrow_applies: every
+// load costs at most both latencies and in the worst case all of them run one after the other) and the address space
+// fits.  With four requesters 268 instead of 452 bytes per replication: six resident blocks per SM instead of three
+// (the kernel waits on dependent shared-memory round trips, three warps per scheduler did not cover them).
+template <bool SINGLE, bool STATEFUL, typename ENV = environment, bool NARROW = false>
 __global__ void __launch_bounds__(ARCH_THREADS)
 archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, archsim_saved st, trace_sink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -54,25 +88,32 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
     const int K = SINGLE ? 1 : (int)prm.n_requesters;
     const int CAP = (int)prm.l2_capacity;
     const int heap_cap = K + 3;
+    using stamp_t = typename std::conditional<NARROW, uint32_t, int64_t>::type;   // a tick of the clock
+    using addr_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;   // a block address
+    using who_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;
     lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
-    lane_array<int64_t> blk_last = carve<int64_t>(cursor, CAP);
-    per_requester<int64_t, SINGLE> t1, stamp2;
-    per_requester<uint32_t, SINGLE> loop_j, cur_addr, pcs;  // pcs: nibble 0 requester, 1 load2, 2 with2, 3 load1, 4 with1
+    lane_array<stamp_t> blk_last = carve<stamp_t>(cursor, CAP);
+    per_requester<stamp_t, SINGLE> t1, stamp2;
+    per_requester<uint32_t, SINGLE> loop_j, pcs;  // pcs: nibble 0 requester, 1 load2, 2 with2, 3 load1, 4 with1
+    per_requester<addr_t, SINGLE> cur_addr;
     if (!SINGLE) {
-        t1.many = carve<int64_t>(cursor, K);
-        stamp2.many = carve<int64_t>(cursor, K);
+        t1.many = carve<stamp_t>(cursor, K);
+        stamp2.many = carve<stamp_t>(cursor, K);
     }
     lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
-    lane_array<uint32_t> blk_addr = carve<uint32_t>(cursor, CAP);
     if (!SINGLE) {
         loop_j.many = carve<uint32_t>(cursor, K);
-        cur_addr.many = carve<uint32_t>(cursor, K);
         pcs.many = carve<uint32_t>(cursor, K);
     }
-    lane_array<uint32_t> w2who = carve<uint32_t>(cursor, K);
-    lane_array<int32_t> w2lat = carve<int32_t>(cursor, K);
-    lane_array<uint32_t> w1who = carve<uint32_t>(cursor, K);
-    lane_array<int32_t> w1lat = carve<int32_t>(cursor, K);
+    lane_array<addr_t> blk_addr = carve<addr_t>(cursor, CAP);
+    if (!SINGLE) cur_addr.many = carve<addr_t>(cursor, K);
+    lane_array<who_t> w2who = carve<who_t>(cursor, K);
+    lane_array<who_t> w1who = carve<who_t>(cursor, K);
+    lane_array<int32_t> w2lat{}, w1lat{};          // (NARROW: every waiter has latency 0 and priority 0: no such arrays)
+    if (!NARROW) {
+        w2lat = carve<int32_t>(cursor, K);
+        w1lat = carve<int32_t>(cursor, K);
+    }
 
     auto get_pc = [&](int q, int which) -> uint32_t { return (pcs[q] >> (4 * which)) & 0xF; };
     auto set_pc = [&](int q, int which, uint32_t v) { pcs[q] = (pcs[q] & ~(0xFu << (4 * which))) | (v << (4 * which)); };
@@ -92,9 +133,14 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
         ENV env;
         env.init(hkey, htag, heap_cap);
         attach_trace(env, sink);
-        wait_list wait2, wait1;  // mutex::event_ of mem2 / mem1
-        wait2.init(w2who, w2lat, K);
-        wait1.init(w1who, w1lat, K);
+        typename std::conditional<NARROW, wait_list_plain, wait_list>::type wait2, wait1;  // mutex::event_ of mem2 / mem1
+        if constexpr (NARROW) {
+            wait2.init(w2who, K);
+            wait1.init(w1who, K);
+        } else {
+            wait2.init(w2who, w2lat, K);
+            wait1.init(w1who, w1lat, K);
+        }
         bool owned2 = false, owned1 = false;
         int n_blocks = 0;
         int held_slot = -1;   // block found by the look-up of the load that holds mem2's mutex (-1: a miss)
@@ -135,20 +181,22 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
             }
             at = ARCH_SAVED_HEADER + 3 * heap_cap;
             for (int b = 0; b < n_blocks; ++b, at += 3) {
-                blk_addr[b] = sv[(size_t)at * n];
-                blk_last[b] = (int64_t)u64(at + 1);
+                blk_addr[b] = (addr_t)sv[(size_t)at * n];
+                blk_last[b] = (stamp_t)u64(at + 1);
             }
             at = ARCH_SAVED_HEADER + 3 * heap_cap + 3 * CAP;
             for (int q = 0; q < K; ++q, at += 11) {
-                t1[q] = (int64_t)u64(at);
-                stamp2[q] = (int64_t)u64(at + 2);
+                t1[q] = (stamp_t)u64(at);
+                stamp2[q] = (stamp_t)u64(at + 2);
                 loop_j[q] = sv[(size_t)(at + 4) * n];
-                cur_addr[q] = sv[(size_t)(at + 5) * n];
+                cur_addr[q] = (addr_t)sv[(size_t)(at + 5) * n];
                 pcs[q] = sv[(size_t)(at + 6) * n];
-                w2who[q] = sv[(size_t)(at + 7) * n];
-                w2lat[q] = (int32_t)sv[(size_t)(at + 8) * n];
-                w1who[q] = sv[(size_t)(at + 9) * n];
-                w1lat[q] = (int32_t)sv[(size_t)(at + 10) * n];
+                w2who[q] = (who_t)sv[(size_t)(at + 7) * n];
+                w1who[q] = (who_t)sv[(size_t)(at + 9) * n];
+                if constexpr (!NARROW) {
+                    w2lat[q] = (int32_t)sv[(size_t)(at + 8) * n];
+                    w1lat[q] = (int32_t)sv[(size_t)(at + 10) * n];
+                }
             }
         } else {
             for (int q = 0; q < K; ++q) {
@@ -189,13 +237,13 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                     const int q = (int)target - 1;
                     uint32_t j = loop_j[q];
                     if (get_pc(q, PC_REQ) == 1) {
-                        total_latency += (double)(env.now - t1[q]);
+                        total_latency += (double)(env.now - (int64_t)t1[q]);
                         loop_j[q] = ++j;
                     }
                     if (j < prm.n_loads) {
                         addr.stream = target;
-                        cur_addr[q] = (uint32_t)(stream_draw_bits(addr, j) % prm.addr_space);
-                        t1[q] = env.now;
+                        cur_addr[q] = (addr_t)(stream_draw_bits(addr, j) % prm.addr_space);
+                        t1[q] = (stamp_t)env.now;
                         set_pc(q, PC_LOAD2, 0);
                         note(env.now, make_tag(0x100 + q));  // start(mem2.load); completion targets the requester
                         set_pc(q, PC_REQ, 1);
@@ -210,7 +258,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                         // ---- memory::load up to the _Co_with (basic_arch_sim.cpp:21-24) ----
                         const int which = lvl == 2 ? PC_LOAD2 : PC_LOAD1;
                         if (get_pc(q, which) == 0) {
-                            if (lvl == 2) stamp2[q] = env.now;  // timestamp = env.now()
+                            if (lvl == 2) stamp2[q] = (stamp_t)env.now;  // timestamp = env.now()
                             set_pc(q, lvl == 2 ? PC_WITH2 : PC_WITH1, 0);
                             note(env.now, make_tag(target | 0x8000u));  // start(_Co_with coroutine)
                             set_pc(q, which, 1);
@@ -222,7 +270,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                         // ---- operator+(mutex&, body): acquire; body(); release  (co_with.ipp:27-33) ----
                         const int which = lvl == 2 ? PC_WITH2 : PC_WITH1;
                         bool &owned = lvl == 2 ? owned2 : owned1;
-                        wait_list &waiters = lvl == 2 ? wait2 : wait1;
+                        auto &waiters = lvl == 2 ? wait2 : wait1;
                         const int64_t latency = lvl == 2 ? prm.l2_latency : prm.l1_latency;
                         const uint32_t pc = get_pc(q, which);
                         if (pc == 0) {
@@ -242,9 +290,9 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                                         if (n_blocks == CAP) {
                                             // evict: least last_access, lowest position on ties
                                             int victim = 0;
-                                            int64_t best = blk_last[0];
+                                            stamp_t best = blk_last[0];
                                             for (int b = 1; b < n_blocks; ++b) {
-                                                int64_t v = blk_last[b];
+                                                stamp_t v = blk_last[b];
                                                 if (v < best) { best = v; victim = b; }
                                             }
                                             if (unique_stamps) {
@@ -280,7 +328,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                             if (lvl == 2) {
                                 // blocks_[addr].last_access = timestamp
                                 // (nobody else touched mem2's blocks since the look-up: the mutex was held)
-                                const int64_t ts = stamp2[q];
+                                const stamp_t ts = stamp2[q];
                                 if (held_slot >= 0) {
                                     blk_last[held_slot] = ts;
                                 } else {
@@ -343,9 +391,14 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                     sv[(size_t)(at + 5) * n] = cur_addr[q];
                     sv[(size_t)(at + 6) * n] = pcs[q];
                     sv[(size_t)(at + 7) * n] = w2who[q];
-                    sv[(size_t)(at + 8) * n] = (uint32_t)w2lat[q];
                     sv[(size_t)(at + 9) * n] = w1who[q];
-                    sv[(size_t)(at + 10) * n] = (uint32_t)w1lat[q];
+                    if constexpr (NARROW) {
+                        sv[(size_t)(at + 8) * n] = 0u;
+                        sv[(size_t)(at + 10) * n] = 0u;
+                    } else {
+                        sv[(size_t)(at + 8) * n] = (uint32_t)w2lat[q];
+                        sv[(size_t)(at + 10) * n] = (uint32_t)w1lat[q];
+                    }
                 }
                 sv[0] = ARCH_PHASE_SAVED;
             } else {
@@ -376,13 +429,27 @@ size_t archsim_smem_bytes(const cxxdes_b200_archsim_params &p) {
     return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * 12 + k * (8 + 8 + 4 + 4 + 4 + 16));
 }
 
+namespace {
+// The clock of a run stays below the sum of every load's latencies taken one after the other: n_requesters * n_loads
+// loads of at most l1 + l2 ticks (nothing else in the model lets time pass).  Below 2^31 the stamps fit 32 bits.
+bool archsim_narrow_applies(const cxxdes_b200_archsim_params &p) {
+    const double per_load = (double)p.l1_latency + (double)p.l2_latency + 1.0;
+    return (double)p.n_requesters * (double)p.n_loads * per_load < 2147483648.0 && p.addr_space <= 65536;
+}
+size_t archsim_narrow_smem_bytes(const cxxdes_b200_archsim_params &p) {
+    const size_t k = p.n_requesters, cap = p.l2_capacity;
+    return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * (4 + 2) + k * (4 + 4 + 4 + 4 + 2 + 2 + 2));
+}
+}  // namespace
+
 size_t archsim_saved_words(const cxxdes_b200_archsim_params &p) {
     return ARCH_SAVED_HEADER + 3 * ((size_t)p.n_requesters + 3) + 3 * (size_t)p.l2_capacity + 11 * (size_t)p.n_requesters;
 }
 
 cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
-                           int sm_count, cudaStream_t stream, const archsim_saved &st) {
-    const size_t smem = archsim_smem_bytes(prm);
+                           int sm_count, cudaStream_t stream, const archsim_saved &st, bool wide_layout) {
+    const bool narrow = !wide_layout && archsim_narrow_applies(prm);
+    const size_t smem = narrow ? archsim_narrow_smem_bytes(prm) : archsim_smem_bytes(prm);
     auto go = [&](auto kernel, int per_sm) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -391,9 +458,18 @@ cudaError_t launch_archsim(const cxxdes_b200_archsim_params &prm, const shard &s
     };
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > ARCH_MAX_BLOCKS_PER_SM) per_sm = ARCH_MAX_BLOCKS_PER_SM;   // (72 registers: seven blocks of 128 threads fit an SM)
+    if (narrow) {
+        if (prm.n_requesters == 1)
+            return st.words ? go(archsim_kernel<true, true, environment, true>, per_sm) : go(archsim_kernel<true, false, environment, true>, per_sm);
+        return st.words ? go(archsim_kernel<false, true, environment, true>, per_sm) : go(archsim_kernel<false, false, environment, true>, per_sm);
+    }
     if (prm.n_requesters == 1) return st.words ? go(archsim_kernel<true, true>, per_sm) : go(archsim_kernel<true, false>, per_sm);
     return st.words ? go(archsim_kernel<false, true>, per_sm) : go(archsim_kernel<false, false>, per_sm);
+}
+
+bool archsim_uses_narrow_layout(const cxxdes_b200_archsim_params &prm, bool wide_layout) {
+    return !wide_layout && archsim_narrow_applies(prm);
 }
 
 // One replication (sh.n_replications == 1) with its event trace (the general k-requester instantiation).

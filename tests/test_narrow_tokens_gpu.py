@@ -217,3 +217,70 @@ def test_mmc_pieces_on_4_byte_tokens_with_hand_over(port, monkeypatch):
     assert not ens.fetch(strict=False).status.any()
     assert 5 <= ens.pass_counts()["fallback"] <= 400
     ens.close()
+
+
+# ---- memory hierarchy: 32-bit stamps / 16-bit addresses / bare wait lists in shared memory ---------------------------
+
+@pytest.mark.parametrize("flags", [0, abi.FLAG_WIDE_TOKENS])
+@pytest.mark.parametrize("idx", range(N_GOLDEN_CASES))
+def test_archsim_both_layouts_match_reference_golden(built, idx, flags):
+    model, cls, fname = MODELS["archsim"]
+    g = golden_util.load(fname)
+    case = g["cases"][idx]
+    got, _, name, _ = _run(cls(*case["params"]), case["n_replications"], clock_pairs(g), case["seed"],
+                           first=case["first_replication"], until=case["run_until"], flags=flags)
+    assert name.endswith(",narrow>") == (flags == 0), name
+    assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
+    golden_util.assert_columns_equal(got, golden_util.golden_columns(case), what=f"archsim golden {idx} on {name}")
+
+
+@pytest.mark.parametrize("fields,n_reps", [((1, 10, 16, 32, 1, 0, 1024), 1024), ((1, 10, 16, 32, 4, 0, 256), 1024),
+                                           ((0, 0, 4, 8, 4, 0, 100), 512), ((2, 7, 3, 16, 5, 0, 120), 512)])
+def test_archsim_wide_layout_matches_oracle(port, fields, n_reps):
+    """(the default -- narrow -- layout has these cases in test_models_gpu.py::test_gpu_matches_oracle)"""
+    model, cls, fname = MODELS["archsim"]
+    g = golden_util.load(fname)
+    p = cls(*fields)
+    got, acc, name, _ = _run(p, n_reps, clock_pairs(g), 0xFEED, first=17, flags=abi.FLAG_WIDE_TOKENS)
+    want = port.run(model, p, clock_of(g), 0xFEED, 17, n_reps, threads=os.cpu_count())
+    assert "narrow" not in name and not got.status.any()
+    golden_util.assert_columns_equal(got, want, what=f"archsim {fields} on the wide layout")
+
+
+def test_archsim_layouts_agree_at_size_and_in_pieces(port):
+    """4 requesters x 256 loads, 150 000 replications (more than the 113 664 resident lanes of the narrow layout): same
+    columns from both layouts; then run_for in pieces on the wide layout against the oracle (the narrow one has
+    test_models_gpu.py::test_archsim_run_for_in_many_pieces...)."""
+    p = abi.ArchSimParams(1, 10, 16, 32, 4, 0, 256)
+    S_S = ((1, L.SECONDS), (1, L.SECONDS))
+    a, acc_a, name_a, _ = _run(p, 150000, S_S, 0x5EED, first=1 << 21)
+    b, acc_b, name_b, _ = _run(p, 150000, S_S, 0x5EED, first=1 << 21, flags=abi.FLAG_WIDE_TOKENS)
+    assert name_a == "archsim_kernel<k requesters,narrow>" and name_b == "archsim_kernel<k requesters>"
+    assert not a.status.any() and not b.status.any()
+    golden_util.assert_columns_equal(a, b, what="archsim narrow against wide layout")
+    assert acc_a.trace_hash_sum == acc_b.trace_hash_sum
+    model, cls, fname = MODELS["archsim"]
+    g = golden_util.load(fname)
+    q = cls(1, 10, 16, 32, 4, 0, 96)
+    clock = clock_pairs(g)
+    ends = port.run(model, q, clock_of(g), 4, 0, 300, threads=os.cpu_count()).end_time
+    piece = max(1, int(ends.max()) // 5)
+    ens = L.Ensemble(q, 300, seed=4, flags=abi.FLAG_WIDE_TOKENS)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    for k in range(1, 7):
+        ens.run_for(piece)
+        want = port.run(model, q, clock_of(g), 4, 0, 300, threads=os.cpu_count(), until=k * piece)
+        golden_util.assert_columns_equal(ens.fetch(strict=False), want, what=f"archsim (wide layout) after piece {k}")
+    ens.close()
+
+
+def test_archsim_long_runs_keep_64_bit_stamps(built):
+    """n_requesters * n_loads * (l1 + l2 + 1) >= 2^31 ticks could pass 32 bits: the wide layout runs the model."""
+    p = abi.ArchSimParams(1000000, 1000000, 16, 32, 2, 0, 800)
+    ens = L.Ensemble(p, 64, seed=1)
+    ens.time_unit(1, L.SECONDS).time_precision(1, L.SECONDS)
+    ens.run()
+    got = ens.fetch()
+    assert ens.kernel_name() == "archsim_kernel<k requesters>"
+    assert not got.status.any() and int(got.end_time.max()) > 1 << 31
+    ens.close()

@@ -26,13 +26,15 @@ constexpr int ARCH_MAX_CAP = 64;
 constexpr int ARCH_MAX_BLOCKS_PER_SM = 8;
 
 // mutex::event_ of a level when every waiter has priority 0 and latency 0 (all of them are _Co_with coroutines of this
-// model): the process ordinal alone, 16 bits.  Same interface as engine.cuh's wait_list.
+// model): the requester's index alone, 8 bits.  Same interface as engine.cuh's wait_list.
 struct wait_list_plain {
-    lane_array<uint16_t> who;
+    lane_array<uint8_t> who;     // the requester's index; the ordinal is `base | index` (one list per memory level)
+    uint32_t base;
     int n;
     int cap;
-    __device__ __forceinline__ void init(lane_array<uint16_t> w, int capacity) {
+    __device__ __forceinline__ void init(lane_array<uint8_t> w, int capacity, uint32_t ordinal_base) {
         who = w;
+        base = ordinal_base;
         n = 0;
         cap = capacity;
     }
@@ -42,11 +44,11 @@ struct wait_list_plain {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
         }
-        who[n++] = (uint16_t)proc;
+        who[n++] = (uint8_t)(proc & 0xFFu);
     }
     template <typename Env>
     __device__ __forceinline__ void wake(Env &env) {                              // event.hpp:125-134, list order
-        for (int i = 0; i < n; ++i) env.schedule(env.now, 0, make_tag((uint32_t)who[i]));
+        for (int i = 0; i < n; ++i) env.schedule(env.now, 0, make_tag(base | (uint32_t)who[i]));
         n = 0;
     }
 };
@@ -78,7 +80,8 @@ constexpr int ARCH_SAVED_HEADER = 24;
 // NARROW: the model's own arrays in half the shared memory -- time stamps in 32 bits, addresses in 16, wait lists as
 // bare 16-bit ordinals -- chosen at launch when the run provably ends before tick 2^31 (archsim_narrow_applies: every
 // load costs at most both latencies and in the worst case all of them run one after the other) and the address space
-// fits.  With four requesters 268 instead of 452 bytes per replication: six resident blocks per SM instead of three
+// fits (and fewer than 2^16 loads per requester: 16-bit loop counters; resume points in 2 bits each; wait lists as
+// requester indices).  With four requesters 244 instead of 452 bytes per replication: seven resident blocks per SM instead of three
 // (the kernel waits on dependent shared-memory round trips, three warps per scheduler did not cover them).
 template <bool SINGLE, bool STATEFUL, typename ENV = environment, bool NARROW = false>
 __global__ void __launch_bounds__(ARCH_THREADS)
@@ -90,11 +93,15 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
     const int heap_cap = K + 3;
     using stamp_t = typename std::conditional<NARROW, uint32_t, int64_t>::type;   // a tick of the clock
     using addr_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;   // a block address
-    using who_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;
+    using who_t = typename std::conditional<NARROW, uint8_t, uint32_t>::type;
+    using loop_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;   // loads done (NARROW: fewer than 2^16)
+    using pc_t = typename std::conditional<NARROW, uint16_t, uint32_t>::type;     // five resume points, PCW bits each
+    constexpr int PCW = NARROW ? 2 : 4;
     lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
     lane_array<stamp_t> blk_last = carve<stamp_t>(cursor, CAP);
     per_requester<stamp_t, SINGLE> t1, stamp2;
-    per_requester<uint32_t, SINGLE> loop_j, pcs;  // pcs: nibble 0 requester, 1 load2, 2 with2, 3 load1, 4 with1
+    per_requester<loop_t, SINGLE> loop_j;
+    per_requester<pc_t, SINGLE> pcs;  // pcs: field 0 requester, 1 load2, 2 with2, 3 load1, 4 with1 (values 0..2)
     per_requester<addr_t, SINGLE> cur_addr;
     if (!SINGLE) {
         t1.many = carve<stamp_t>(cursor, K);
@@ -102,11 +109,19 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
     }
     lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
     if (!SINGLE) {
-        loop_j.many = carve<uint32_t>(cursor, K);
-        pcs.many = carve<uint32_t>(cursor, K);
+        if (!NARROW) {
+            loop_j.many = carve<loop_t>(cursor, K);
+            pcs.many = carve<pc_t>(cursor, K);
+        }
     }
     lane_array<addr_t> blk_addr = carve<addr_t>(cursor, CAP);
-    if (!SINGLE) cur_addr.many = carve<addr_t>(cursor, K);
+    if (!SINGLE) {
+        cur_addr.many = carve<addr_t>(cursor, K);
+        if (NARROW) {
+            loop_j.many = carve<loop_t>(cursor, K);
+            pcs.many = carve<pc_t>(cursor, K);
+        }
+    }
     lane_array<who_t> w2who = carve<who_t>(cursor, K);
     lane_array<who_t> w1who = carve<who_t>(cursor, K);
     lane_array<int32_t> w2lat{}, w1lat{};          // (NARROW: every waiter has latency 0 and priority 0: no such arrays)
@@ -115,8 +130,11 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
         w1lat = carve<int32_t>(cursor, K);
     }
 
-    auto get_pc = [&](int q, int which) -> uint32_t { return (pcs[q] >> (4 * which)) & 0xF; };
-    auto set_pc = [&](int q, int which, uint32_t v) { pcs[q] = (pcs[q] & ~(0xFu << (4 * which))) | (v << (4 * which)); };
+    constexpr uint32_t PCM = (1u << PCW) - 1u;
+    auto get_pc = [&](int q, int which) -> uint32_t { return ((uint32_t)pcs[q] >> (PCW * which)) & PCM; };
+    auto set_pc = [&](int q, int which, uint32_t v) {
+        pcs[q] = (pc_t)(((uint32_t)pcs[q] & ~(PCM << (PCW * which))) | (v << (PCW * which)));
+    };
     enum { PC_REQ = 0, PC_LOAD2 = 1, PC_WITH2 = 2, PC_LOAD1 = 3, PC_WITH1 = 4 };
 
     // One requester and a positive mem2 latency: every load starts later than the one before, so last_access
@@ -135,8 +153,8 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
         attach_trace(env, sink);
         typename std::conditional<NARROW, wait_list_plain, wait_list>::type wait2, wait1;  // mutex::event_ of mem2 / mem1
         if constexpr (NARROW) {
-            wait2.init(w2who, K);
-            wait1.init(w1who, K);
+            wait2.init(w2who, K, 0x8100u);
+            wait1.init(w1who, K, 0x8200u);
         } else {
             wait2.init(w2who, w2lat, K);
             wait1.init(w1who, w1lat, K);
@@ -188,9 +206,9 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
             for (int q = 0; q < K; ++q, at += 11) {
                 t1[q] = (stamp_t)u64(at);
                 stamp2[q] = (stamp_t)u64(at + 2);
-                loop_j[q] = sv[(size_t)(at + 4) * n];
+                loop_j[q] = (loop_t)sv[(size_t)(at + 4) * n];
                 cur_addr[q] = (addr_t)sv[(size_t)(at + 5) * n];
-                pcs[q] = sv[(size_t)(at + 6) * n];
+                pcs[q] = (pc_t)sv[(size_t)(at + 6) * n];
                 w2who[q] = (who_t)sv[(size_t)(at + 7) * n];
                 w1who[q] = (who_t)sv[(size_t)(at + 9) * n];
                 if constexpr (!NARROW) {
@@ -238,7 +256,7 @@ archsim_kernel(cxxdes_b200_archsim_params prm, shard sh, device_columns out, arc
                     uint32_t j = loop_j[q];
                     if (get_pc(q, PC_REQ) == 1) {
                         total_latency += (double)(env.now - (int64_t)t1[q]);
-                        loop_j[q] = ++j;
+                        loop_j[q] = (loop_t)++j;
                     }
                     if (j < prm.n_loads) {
                         addr.stream = target;
@@ -434,11 +452,11 @@ namespace {
 // loads of at most l1 + l2 ticks (nothing else in the model lets time pass).  Below 2^31 the stamps fit 32 bits.
 bool archsim_narrow_applies(const cxxdes_b200_archsim_params &p) {
     const double per_load = (double)p.l1_latency + (double)p.l2_latency + 1.0;
-    return (double)p.n_requesters * (double)p.n_loads * per_load < 2147483648.0 && p.addr_space <= 65536;
+    return (double)p.n_requesters * (double)p.n_loads * per_load < 2147483648.0 && p.addr_space <= 65536 && p.n_loads < 65536;
 }
 size_t archsim_narrow_smem_bytes(const cxxdes_b200_archsim_params &p) {
     const size_t k = p.n_requesters, cap = p.l2_capacity;
-    return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * (4 + 2) + k * (4 + 4 + 4 + 4 + 2 + 2 + 2));
+    return 128 + (size_t)ARCH_THREADS * ((k + 3) * 12 + cap * (4 + 2) + k * (4 + 4 + 2 + 2 + 2 + 1 + 1));
 }
 }  // namespace
 

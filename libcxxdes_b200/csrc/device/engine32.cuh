@@ -602,6 +602,51 @@ struct heap_rel {
         n = len;
     }
 
+    // The same pop as straight-line code: ROUNDS two-level steps (ROUNDS = half the depth of the deepest index, rounded
+    // up), each predicated instead of a loop turn, so that the whole event body is one basic block and the scheduler
+    // can run the variate's arithmetic in the shadow of the sift-down's round trips.  Unlike the fixed-depth sift that
+    // was rejected earlier (one dependent round trip per LEVEL) this keeps the loop's look-ahead: children and
+    // grandchildren in one round trip, two levels decided per trip.  A step that has nothing to do reads entries 1-4,
+    // and the look-ahead of the last internal node may read one entry past `cap`: the column must hold
+    // max(cap + 1, 5) entries behind the sentinel (FLAT_POP_COLUMN).
+    static __host__ __device__ constexpr int FLAT_POP_COLUMN(int capacity) { return (capacity + 1 > 5 ? capacity + 1 : 5) + EXTRA; }
+    template <int ROUNDS, int REINSERT_LEVELS>
+    __device__ __forceinline__ void pop_after_top_flat() {
+        const uint32_t len = n - 1;
+        const uint32_t v = lds(at(len));
+        const uint32_t two = len ? (len - 1) >> 1 : 0u;          // holes below this index have two children
+        uint32_t hole = 0;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const bool go1 = hole < two;
+            const uint32_t right = go1 ? 2 * hole + 2 : 2u;
+            const uint32_t ra = at(right);
+            const uint32_t er = lds(ra), el = lds(ra - EB);
+            // the chosen child has two children itself iff it is below `two`: both do when right < two, only the left
+            // one when right == two
+            const uint32_t ga = at((go1 && right <= two) ? 2 * right : 2u);
+            const uint32_t grr = lds(ga + 2 * EB), grl = lds(ga + EB), glr = lds(ga), gll = lds(ga - EB);
+            const bool left = later(er, el);                     // right strictly later than left -> take left; tie -> right
+            const uint32_t child = left ? right - 1 : right;
+            if (go1) sts(at(hole), left ? el : er);
+            const bool go2 = go1 && child < two;
+            const uint32_t gr = left ? glr : grr, gl = left ? gll : grl;
+            const bool left2 = later(gr, gl);
+            if (go2) sts(left ? ra - EB : ra, left2 ? gl : gr);
+            hole = go2 ? 2 * child + (left2 ? 1u : 2u) : (go1 ? child : hole);
+        }
+        if ((len & 1u) == 0 && len != 0 && hole == (len - 2) >> 1) {   // a lone left child at the bottom
+            const uint32_t child = 2 * hole + 1;
+            sts(at(hole), lds(at(child)));
+            hole = child;
+        }
+        if (len > 0) {
+            if constexpr (REINSERT_LEVELS > 0) sift_up_path<REINSERT_LEVELS>(hole, v);
+            else sift_up(hole, v);
+        }
+        n = len;
+    }
+
     __device__ __forceinline__ void fold(uint32_t time, uint32_t kind, uint32_t proc) {
         hash = trace_hash_step(hash, (int64_t)time, 0, kind, proc);
     }

@@ -181,6 +181,9 @@ aloha_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, const u
 //   * Philox round keys come precomputed from the constant bank (the key is the seed).
 // Replications whose clock would pass 2^32 ticks are handed to aloha_kernel above.
 // ---------------------------------------------------------------------------------------------
+#ifndef CXB_ALOHA_FLAT_POP
+#define CXB_ALOHA_FLAT_POP 1   // the pop of the 4-byte-token kernel as straight-line code (heap_rel::pop_after_top_flat: +3 %); 0: the loop (A/B)
+#endif
 #ifndef CXB_PATH_PUSH
 #define CXB_PATH_PUSH 1     // the event's push as a path-parallel sift-up (engine32.cuh sift_up_path); 0: the loop (A/B)
 #endif
@@ -449,7 +452,7 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
     stage_log_table(table, sh.log_table);
     const int N = (int)prm.num_stations;
     const int heap_cap = N + 2;
-    const lane_array<uint32_t> heap_words = carve<uint32_t>(cursor, heap_cap + heap24x<AF_THREADS>::EXTRA);   // (+ the sentinel)
+    const lane_array<uint32_t> heap_words = carve<uint32_t>(cursor, heap24x<AF_THREADS>::FLAT_POP_COLUMN(heap_cap));   // (+ the sentinel, + what a straight-line pop may read)
     uint32_t *heap = heap_words.base;
     // completed transmissions of every station (the `for` counter of aloha.cpp:53): 16 bits each, [station][thread]
     const uint32_t cnt_base = (uint32_t)__cvta_generic_to_shared(carve<uint16_t>(cursor, N).base);
@@ -573,8 +576,12 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             const uint64_t bits = (i & 1) ? (((uint64_t)b.w[3] << 32) | b.w[2]) : (((uint64_t)b.w[1] << 32) | b.w[0]);
             const int64_t wait_ticks = real_to_sim(exponential_from_bits(bits, rate, table), sh.clk);
 
+#if CXB_ALOHA_FLAT_POP
+            env.pop_after_top_flat<3, 6>();                        // (straight-line: three two-level steps cover 66 entries)
+#else
             env.pop_after_top<6>();                                // environment::step, environment.ipp:117-126 (the displaced
                                                                    // last element re-inserted path-parallel: +1.8 %)
+#endif
             token32 t;
             t.time = env.time_of(root);
             t.tag = code;
@@ -726,7 +733,7 @@ bool aloha_keeps_state(const cxxdes_b200_aloha_params &prm, const shard &sh) { r
 namespace {
 size_t aloha_compact_smem_bytes(uint32_t num_stations) {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
-           (size_t)AF_THREADS * (((size_t)num_stations + 2 + heap24x<AF_THREADS>::EXTRA) * 4 + (size_t)num_stations * 2);
+           (size_t)AF_THREADS * ((size_t)heap24x<AF_THREADS>::FLAT_POP_COLUMN((int)num_stations + 2) * 4 + (size_t)num_stations * 2);
 }
 }  // namespace
 

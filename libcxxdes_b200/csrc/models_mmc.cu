@@ -201,6 +201,9 @@ constexpr int MF_WAITERS = 64;
 #ifndef CXB_PATH_PUSH
 #define CXB_PATH_PUSH 1     // pushes as path-parallel sift-ups (engine32.cuh sift_up_path); 0: the loop (A/B)
 #endif
+#ifndef CXB_MMC_FLAT_POP
+#define CXB_MMC_FLAT_POP 0
+#endif
 #ifndef CXB_MMC_PUSHES_PER_TURN
 #define CXB_MMC_PUSHES_PER_TURN 2
 #endif
@@ -211,6 +214,8 @@ struct mmc_wide_tokens {
     using heap_t = heap32x<THREADS>;
     using word_t = uint2;
     static constexpr uint32_t HANDLER = 1u << 16, TARGET_MASK = 0xFFFFu, NOOP = TAG_NO_TARGET;
+    static constexpr int COLUMN = HEAP;          // entries allocated per replication
+    static constexpr bool FLAT_POP = false;
 };
 #ifndef CXB_MMC_NT          // threads, blocks per SM, heap entries, waiters of the narrow-token kernel (A/B builds)
 #define CXB_MMC_NT 288
@@ -225,6 +230,8 @@ struct mmc_narrow_tokens {
     using heap_t = heap_rel<THREADS, 12>;
     using word_t = uint32_t;
     static constexpr uint32_t HANDLER = 1u << 11, TARGET_MASK = 0x7FFu, NOOP = 0x7FFu;
+    static constexpr bool FLAT_POP = CXB_MMC_FLAT_POP != 0;      // the pop as straight-line code (heap_rel::pop_after_top_flat)
+    static constexpr int COLUMN = FLAT_POP ? heap_t::FLAT_POP_COLUMN(HEAP) : HEAP + heap_t::EXTRA;
 };
 static_assert(TAG_NO_TARGET == 0xFFFFu, "the wide tokens' no-target ordinal is the generic engine's");
 
@@ -269,7 +276,7 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     stage_log_table(table, sh.log_table);
     constexpr uint32_t MF_HANDLER = TK::HANDLER, MF_NOOP = TK::NOOP;
-    typename TK::word_t *heap = carve<typename TK::word_t>(cursor, TK::HEAP + TK::heap_t::EXTRA).base;
+    typename TK::word_t *heap = carve<typename TK::word_t>(cursor, TK::COLUMN).base;
     wait_list16 waiters;
     waiters.who = carve<uint16_t>(cursor, TK::WAITERS);
     waiters.cap = TK::WAITERS;
@@ -384,7 +391,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
             const bool is_customer_token = target >= 2 && target != MF_NOOP;   // customer(id), acquire_proc(id) or their handler
             uint64_t *const w = &cust[(uint64_t)(is_customer_token ? (target - 2) >> 1 : 0u) * total_threads];
             uint64_t s = *w;
-            env.pop_after_top();                 // environment::step, environment.ipp:117-126
+            if constexpr (TK::FLAT_POP) env.template pop_after_top_flat<3, 0>();   // (64 entries: three two-level steps)
+            else env.pop_after_top();            // environment::step, environment.ipp:117-126
             env.now = t.time > env.now ? t.time : env.now;
             ++env.n_events;
             // An event pushes at most two tokens of its own (wake-ups aside) and draws at most one variate.  The
@@ -613,7 +621,7 @@ namespace {
 template <typename TK>
 size_t mmc_fast_smem_bytes() {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
-           (size_t)TK::THREADS * ((TK::HEAP + TK::heap_t::EXTRA) * sizeof(typename TK::word_t) + TK::WAITERS * 2);
+           (size_t)TK::THREADS * (TK::COLUMN * sizeof(typename TK::word_t) + TK::WAITERS * 2);
 }
 // 32-bit event counter and clock: a variate is at most 36.05 / rate
 bool mmc_fast_applies(const cxxdes_b200_mmc_params &p, const shard &sh) {

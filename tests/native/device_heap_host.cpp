@@ -109,7 +109,10 @@ int check_rel(uint32_t seed, int capacity, int n_ops, uint32_t time_span, long *
             ++next_serial;
         } else {
             const uint32_t root = env.entry(0);
-            if (path) env.template pop_after_top<8>();      // (re-insertion of the displaced element path-parallel too)
+            // (re-insertion of the displaced element path-parallel too; every other run: the straight-line pop, 4 rounds
+            // of two levels = indices below 511)
+            if (path && (seed & 1)) env.template pop_after_top_flat<4, 8>();
+            else if (path) env.template pop_after_top<8>();
             else env.pop_after_top();
             const uint32_t time = env.time_of(root), code = env.tag_of(root);
             env.now = time > env.now ? time : env.now;

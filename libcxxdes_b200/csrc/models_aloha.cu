@@ -436,7 +436,7 @@ aloha_fast_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out, ph
 
 // ---------------------------------------------------------------------------------------------------------------
 // aloha_compact_kernel: the same event body as aloha_fast_kernel on 4-byte tokens (device/engine32.cuh heap24x: time
-// relative to a moving epoch, 8-bit code) with the stations' loop counters in a 16-bit array: 392 instead of 528 bytes of
+// relative to a moving epoch, 8-bit code) with the stations' loop counters in a 16-bit array: 400 instead of 528 bytes of
 // shared memory per replication, i.e. FOUR blocks of 128 replications per SM instead of three, and a sift moves one
 // word per level instead of two.  First choice when the load sweep keeps packets per station below 2^16 and waiting
 // times far below 2^24 - 2^22 ticks (aloha_compact_applies); a replication that draws a longer wait is redone by the

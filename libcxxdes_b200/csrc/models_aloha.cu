@@ -466,6 +466,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
     };
 
     const int64_t frame_ticks = real_to_sim_f32(prm.frame_time, sh.clk);  // env.timeout(float), aloha.cpp:60
+    constexpr uint32_t DELAY_LIMIT = heap24x<AF_THREADS>::DELAY_LIMIT;
+    const uint32_t frame32 = (uint64_t)frame_ticks >= (uint64_t)DELAY_LIMIT ? DELAY_LIMIT : (uint32_t)frame_ticks;
 
     heap24x<AF_THREADS> env;   // 4-byte tokens (time - epoch) << 8 | code; every access goes through env
     env.init(heap, heap_cap);
@@ -565,10 +567,8 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             // ---- one event, branch-light: the token at the root decides everything the event does, so it is decoded
             // first; the variate a station draws when its frame ends is computed for EVERY event (half of them use
             // it: a branch would run it for half of the lanes at the same cost and serialise it with the heap moves
-            // it does not depend on); the event's effects are selects.  The sifts stay loops: a sift-down has the
-            // same trip count in every lane (the heaps hold N or N + 1 tokens), and the predicated fixed-depth
-            // sift-up that was tried (engine32.cuh schedule_flat) costs 78 instructions for every lane where the loop
-            // costs ~7 per level actually climbed.
+            // it does not depend on); the event's effects are selects.  No loop is left in the body: the pop is three
+            // predicated two-level steps, the push one round trip over the new leaf's ancestors (engine32.cuh).
             const uint32_t code = root & 0xFFu;
             const bool is_station = code - 1u < 64u;
             const uint32_t i = cnt_load(is_station ? code - 1u : 0u);
@@ -595,10 +595,11 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             const bool tx_start = is_station && !tx_end && i < rp.pps;       // collided = false; insert; check (:55-59,73-78)
             const bool st_return = is_station && !tx_end && !(i < rp.pps);   // co_return -> completion with the all_of handler
             successful += (tx_end && !(collided & bit)) ? 1u : 0u;
-            active_set = tx_end ? active_set & ~bit : (tx_start ? active_set | bit : active_set);
+            // erase (the bit is set) and insert (it is clear) are both a toggle of the station's bit
+            active_set ^= (tx_end || tx_start) ? bit : 0ULL;
             n_active += (tx_start ? 1u : 0u) - (tx_end ? 1u : 0u);
-            collided = tx_start ? collided & ~bit : collided;
-            collided |= (tx_start && n_active > 1) ? active_set : 0ULL;
+            // collided = false; check_collisions(): with company, every member of the set -- this one included -- collides
+            collided = (collided & ~(tx_start ? bit : 0ULL)) | ((tx_start && n_active > 1) ? active_set : 0ULL);
             // all_of handler (any_of.ipp:9-26): the output token inherits the child token's time (== now)
             remaining -= is_handler ? 1u : 0u;
             const bool fire = is_handler && armed && remaining == 0;
@@ -609,7 +610,9 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
             env.fold(t.time, kind, proc);
 
             bool push = is_station || fire;
-            int64_t delay = tx_end ? wait_ticks : (tx_start ? frame_ticks : 0);
+            // (a wait beyond the relative time of a token is passed on as the limit itself: schedule refuses it)
+            const uint32_t wait32 = (uint64_t)wait_ticks >= (uint64_t)DELAY_LIMIT ? DELAY_LIMIT : (uint32_t)wait_ticks;
+            const uint32_t delay = tx_end ? wait32 : (tx_start ? frame32 : 0u);
             uint32_t push_tag = (tx_end || tx_start) ? code : (st_return ? CODE_HANDLER : CODE_MAIN);
             if (tx_end) cnt_store(code - 1u, i + 1);     // the `for` loop's ++i (aloha.cpp:53)
             if (is_main) {   // twice per replication
@@ -630,11 +633,10 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
                     push_tag = CODE_NOOP;
                 }
             }
-            // token at now + delay: the delay must fit the relative time of a token, the sum 32 bits (anything else is
-            // redone by the 64-bit kernel)
-            if (push && ((uint64_t)delay >= (uint64_t)heap24x<AF_THREADS>::DELAY_LIMIT || env.now >= 0xFF000000u))
-                env.status |= CXXDES_B200_REP_TIME_RANGE;
-            const uint32_t when = env.now + (uint32_t)delay;
+            // token at now + delay: schedule checks that the delay fits the relative time of a token; the sum must fit 32
+            // bits (anything else is redone by the 64-bit kernel)
+            if (push && env.now >= 0xFF000000u) env.status |= CXXDES_B200_REP_TIME_RANGE;
+            const uint32_t when = env.now + delay;
             // (every ancestor of the new leaf in one round trip: indices up to N + 1 = 65 are at most 6 levels deep)
 #if CXB_PATH_PUSH
             if (push) env.schedule_path<6>(when, push_tag);
@@ -643,7 +645,7 @@ aloha_compact_kernel(cxxdes_b200_aloha_params prm, shard sh, device_columns out,
 #endif
 
             // environment::run / run_until (environment.ipp:179-196); the root loaded here is the next event's
-            root = env.has_event() ? env.entry(0) : 0u;
+            root = env.entry(0);     // (an empty heap: whatever entry 0 holds, not looked at)
             if (env.status || !env.has_event() || env.time_of(root) > until) {
                 active = false;
                 if (env.status & CXXDES_B200_REP_TIME_RANGE) {

@@ -365,6 +365,12 @@ int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t unt
  * profiles/ stores measured per-kernel figures.  NUL-terminated, truncated to buf_size. */
 int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size);
 
+/* The same answer for the ALOHA, M/M/c and memory-hierarchy models WITHOUT a handle or a device: their first-pass
+ * kernel follows from cfg->params, cfg->clock and cfg->flags alone (token width, layout: which ranges the parameters
+ * provably or almost surely stay in).  M/M/1 and process programs are planned from the device's resources as well:
+ * CXXDES_B200_ERR_STATE.  Lets a host, or a test on a machine without a GPU, see which path a configuration takes. */
+int cxxdes_b200_plan_kernel(const cxxdes_b200_config *cfg, char *buf, size_t buf_size);
+
 /* environment::reset() (environment.ipp:154-176) + rebind: replications start over. */
 int cxxdes_b200_reset(cxxdes_b200_ensemble *e);
 

@@ -8,8 +8,8 @@ from .abi import (AlohaParams, ArchSimParams, Clock, HostColumns, MM1Params, MMC
                   MILLISECONDS, MICROSECONDS, NANOSECONDS, PICOSECONDS, SECONDS)
 from .program import AllOf, AnyOf, Delay, Program, Until, Wait
 from .ensemble import (CxxdesError, Ensemble, EXPORTED_SYMBOLS, device_count, library_path,
-                       load_library)
+                       load_library, plan_kernel)
 
 __all__ = ["abi", "AlohaParams", "ArchSimParams", "Clock", "HostColumns", "MM1Params", "MMCParams",
            "SECONDS", "MILLISECONDS", "MICROSECONDS", "NANOSECONDS", "PICOSECONDS", "CxxdesError",
-           "Ensemble", "EXPORTED_SYMBOLS", "device_count", "library_path", "load_library", "Program", "Delay", "Until", "AllOf", "AnyOf", "Wait"]
+           "Ensemble", "EXPORTED_SYMBOLS", "device_count", "library_path", "load_library", "plan_kernel", "Program", "Delay", "Until", "AllOf", "AnyOf", "Wait"]

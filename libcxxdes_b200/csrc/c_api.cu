@@ -776,6 +776,53 @@ int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t unt
     return CXXDES_B200_OK;
 }
 
+// ALOHA, M/M/c, memory hierarchy: the first-pass kernel follows from the parameters, the clock and the flags alone.
+static void host_planned_kernel_name(int model, const model_params &params, const shard &sh, uint32_t flags, char *buf,
+                                     size_t buf_size) {
+    const bool wide = (flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0;
+    switch (model) {
+        case CXXDES_B200_MODEL_ALOHA:
+            snprintf(buf, buf_size, !aloha_keeps_state(params.aloha, sh) ? "aloha_kernel"
+                                    : (flags & CXXDES_B200_FLAG_COOP_HEAP) ? "aloha_coop_kernel"
+                                    : (!wide && aloha_compact_applies(params.aloha, sh)) ? "aloha_compact_kernel<false>"
+                                                                                         : "aloha_fast_kernel<false>");
+            break;
+        case CXXDES_B200_MODEL_MMC:
+            snprintf(buf, buf_size, !mmc_keeps_state(params.mmc, sh) ? "mmc_kernel"
+                                    : (!wide && mmc_narrow_applies(params.mmc, sh)) ? "mmc_fast_kernel<false,narrow>"
+                                                                                    : "mmc_fast_kernel<false,wide>");
+            break;
+        default:
+            snprintf(buf, buf_size, "archsim_kernel<%s%s>", params.arch.n_requesters == 1 ? "1 requester" : "k requesters",
+                     archsim_uses_narrow_layout(params.arch, wide) ? ",narrow" : "");
+            break;
+    }
+}
+
+// The same decision without a handle or a device (include/cxxdes_b200.h).
+int cxxdes_b200_plan_kernel(const cxxdes_b200_config *cfg, char *buf, size_t buf_size) {
+    if (!cfg || !buf || !buf_size) return fail(CXXDES_B200_ERR_INVALID, "cfg/buf is NULL");
+    const size_t want = params_size_of(cfg->model);
+    if (want == 0) return fail(CXXDES_B200_ERR_INVALID, "unknown model %d", cfg->model);
+    if (!cfg->params || cfg->params_size != want)
+        return fail(CXXDES_B200_ERR_INVALID, "params_size %zu does not match model %d (%zu)", cfg->params_size, cfg->model, want);
+    if (cfg->model != CXXDES_B200_MODEL_ALOHA && cfg->model != CXXDES_B200_MODEL_MMC && cfg->model != CXXDES_B200_MODEL_ARCHSIM)
+        return fail(CXXDES_B200_ERR_STATE, "the kernel of this model is planned from the device's resources: create a handle and ask cxxdes_b200_kernel_name");
+    const cxxdes_b200_clock &ck = cfg->clock;
+    if (ck.unit_u < 0 || ck.unit_u > 4 || ck.precision_u < 0 || ck.precision_u > 4 || ck.precision_t <= 0 || ck.unit_t <= 0)
+        return fail(CXXDES_B200_ERR_INVALID, "invalid clock");
+    model_params params;
+    memcpy(&params, cfg->params, want);
+    shard sh{};
+    sh.clk.ticks_per_unit = time_count(ck.unit_t, ck.unit_u, ck.precision_t, ck.precision_u);
+    sh.clk.tick_mult = ck.precision_t;
+    static const double conv[5] = {1, 1e-3, 1e-6, 1e-9, 1e-12};
+    sh.clk.seconds_per_tick_unit = conv[ck.precision_u];
+    sh.run_until = -1;
+    host_planned_kernel_name(cfg->model, params, sh, cfg->flags, buf, buf_size);
+    return CXXDES_B200_OK;
+}
+
 // Which first-pass kernel instantiation the handle's runs use (profiles are keyed by this string).
 int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size) {
     if (!e || !buf || !buf_size) return fail(CXXDES_B200_ERR_INVALID, "handle/buf is NULL");
@@ -797,19 +844,9 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
             }
             break;
         case CXXDES_B200_MODEL_ALOHA:
-            snprintf(buf, buf_size, !aloha_keeps_state(e->params.aloha, sh) ? "aloha_kernel"
-                                    : (e->cfg.flags & CXXDES_B200_FLAG_COOP_HEAP) ? "aloha_coop_kernel"
-                                    : (!(e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) && aloha_compact_applies(e->params.aloha, sh))
-                                        ? "aloha_compact_kernel<false>" : "aloha_fast_kernel<false>");
-            break;
         case CXXDES_B200_MODEL_MMC:
-            snprintf(buf, buf_size, !mmc_keeps_state(e->params.mmc, sh) ? "mmc_kernel"
-                                    : (!(e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) && mmc_narrow_applies(e->params.mmc, sh))
-                                        ? "mmc_fast_kernel<false,narrow>" : "mmc_fast_kernel<false,wide>");
-            break;
         case CXXDES_B200_MODEL_ARCHSIM:
-            snprintf(buf, buf_size, "archsim_kernel<%s%s>", e->params.arch.n_requesters == 1 ? "1 requester" : "k requesters",
-                     archsim_uses_narrow_layout(e->params.arch, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0) ? ",narrow" : "");
+            host_planned_kernel_name(e->cfg.model, e->params, sh, e->cfg.flags, buf, buf_size);
             break;
         case CXXDES_B200_MODEL_PROGRAM:
             snprintf(buf, buf_size, e->prog_fast.valid ? "program_fast_kernel<false>" : "program_kernel");

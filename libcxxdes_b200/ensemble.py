@@ -61,12 +61,13 @@ def load_library():
     lib.cxxdes_b200_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_pass_counts.argtypes = [H, C.POINTER(C.c_uint64 * 4)]
     lib.cxxdes_b200_kernel_name.argtypes = [H, C.c_char_p, C.c_size_t]
+    lib.cxxdes_b200_plan_kernel.argtypes = [C.POINTER(abi.Config), C.c_char_p, C.c_size_t]
     lib.cxxdes_b200_trace.argtypes = [H, C.c_uint64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.cxxdes_b200_reset.argtypes = [H]
     lib.cxxdes_b200_destroy.argtypes = [H]
     for name in ("device_count", "version", "create", "check_program", "run", "run_until", "run_for", "sync", "fetch",
-                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "kernel_name", "trace", "reset", "destroy"):
+                 "device_columns", "reduce", "reduce_allgpus", "last_run_ms", "launch_count", "pass_counts", "kernel_name", "plan_kernel", "trace", "reset", "destroy"):
         getattr(lib, "cxxdes_b200_" + name).restype = C.c_int
     _lib = lib
     return lib
@@ -76,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "cxxdes_b200_device_count", "cxxdes_b200_create", "cxxdes_b200_check_program", "cxxdes_b200_run", "cxxdes_b200_run_until",
     "cxxdes_b200_run_for", "cxxdes_b200_sync", "cxxdes_b200_fetch", "cxxdes_b200_device_columns",
     "cxxdes_b200_reduce", "cxxdes_b200_reduce_allgpus", "cxxdes_b200_last_run_ms", "cxxdes_b200_launch_count", "cxxdes_b200_pass_counts",
-    "cxxdes_b200_kernel_name", "cxxdes_b200_trace", "cxxdes_b200_reset",
+    "cxxdes_b200_kernel_name", "cxxdes_b200_plan_kernel", "cxxdes_b200_trace", "cxxdes_b200_reset",
     "cxxdes_b200_destroy", "cxxdes_b200_last_error", "cxxdes_b200_version",
 ]
 
@@ -96,6 +97,22 @@ def device_count():
 _MODEL_OF_PARAMS = {abi.MM1Params: abi.MODEL_MM1, abi.AlohaParams: abi.MODEL_ALOHA,
                     abi.MMCParams: abi.MODEL_MMC, abi.ArchSimParams: abi.MODEL_ARCHSIM,
                     abi.ProgramParams: abi.MODEL_PROGRAM}
+
+
+def plan_kernel(params, unit=(1, abi.SECONDS), precision=(1, abi.SECONDS), flags=0):
+    """Name of the first-pass kernel an ensemble of this model would run (ALOHA, M/M/c, memory hierarchy: decided from
+    the parameters, the clock and the flags alone -- no handle, no device; cxxdes_b200_plan_kernel)."""
+    lib = load_library()
+    cfg = abi.Config()
+    cfg.model = _MODEL_OF_PARAMS[type(params)]
+    cfg.n_replications = 1
+    cfg.clock = abi.Clock.of(unit, precision)
+    cfg.params = C.addressof(params)
+    cfg.params_size = C.sizeof(params)
+    cfg.flags = int(flags)
+    buf = C.create_string_buffer(128)
+    _check(lib, lib.cxxdes_b200_plan_kernel(C.byref(cfg), buf, len(buf)))
+    return buf.value.decode()
 
 
 class Ensemble:

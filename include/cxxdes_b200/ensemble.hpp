@@ -230,6 +230,15 @@ public:
         detail::check(cxxdes_b200_kernel_name(handle_, buf, sizeof buf));
         return buf;
     }
+    // the same answer before anything is created -- no handle, no device (ALOHA, M/M/c, memory hierarchy: the kernel
+    // follows from the parameters and the clock; cxxdes_b200_plan_kernel; the others throw)
+    std::string planned_kernel() const {
+        typename Model::params_type p = model_.params();
+        cxxdes_b200_config cfg = config_of(p);
+        char buf[160];
+        detail::check(cxxdes_b200_plan_kernel(&cfg, buf, sizeof buf));
+        return buf;
+    }
     struct pass_counts_t {
         std::uint64_t second_pass, helper, fallback, helper_longest_ns;
     };
@@ -240,9 +249,7 @@ public:
     }
 
 private:
-    void bind() {
-        if (handle_) return;
-        typename Model::params_type p = model_.params();
+    cxxdes_b200_config config_of(const typename Model::params_type &p) const {
         cxxdes_b200_config cfg{};
         cfg.model = Model::id;
         cfg.device = device_;
@@ -255,6 +262,12 @@ private:
         cfg.clock.precision_u = (int)env.prec_.u;
         cfg.params = &p;
         cfg.params_size = sizeof(p);
+        return cfg;
+    }
+    void bind() {
+        if (handle_) return;
+        typename Model::params_type p = model_.params();
+        cxxdes_b200_config cfg = config_of(p);
         detail::check(cxxdes_b200_create(&cfg, &handle_));
     }
 

@@ -141,3 +141,20 @@ def test_cpp_loss_system_example_matches_theory(built, tmp_path):
     r = subprocess.run([str(exe), "20000", "4000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert len(r.stdout.strip().splitlines()) == 6
+
+
+def test_cpp_planned_kernel_without_a_device(built, tmp_path):
+    """ensemble<Model>::planned_kernel() (cxxdes_b200_plan_kernel): the first-pass kernel of a configuration, asked from
+    the C++ mirror before anything is created."""
+    exe = tmp_path / "plan_kernel_host"
+    lib_dir = ROOT / "libcxxdes_b200" / "_lib"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
+                    str(ROOT / "tests" / "native" / "plan_kernel_host.cpp"), f"-L{lib_dir}", "-lcxxdes_b200",
+                    f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "aloha aloha_compact_kernel<false>"
+    assert lines[1] == "mmc mmc_fast_kernel<false,wide>"            # 1023 customers: one ordinal too many for 4-byte tokens
+    assert lines[2] == "archsim archsim_kernel<k requesters,narrow>"
+    assert lines[3].startswith("mm1 throws: cxxdes_b200:")

@@ -20,7 +20,10 @@
 // plain C++ between the awaits (`total += now_seconds() - x`) are therefore not recorded; write those models with the
 // builder (program.hpp: co.stat_seconds(k)).  Random variates: cxxdes_b200/random_variable.hpp (`exponential_rv`)
 // returns a tagged value that `env.timeout(x)` turns into a draw from the awaiting process's Philox stream.
-// Not provided: `_Co_with`, `subroutine<>`, `sequential` / the comma operator, `>>`, exceptions through tokens.
+// `subroutine<T>` bodies run inside the process that awaits them (subroutine.ipp: no tokens of their own), so their awaits
+// are noted in that process; `_Co_with(x) { ... };` and `sequential(a, b, ...)` / the comma operator are, as in the
+// reference (co_with.ipp:27-35, sequential.ipp:1-20), coroutines of the library -- helper processes of the program.
+// Not provided: `>>` / `flag_done`, `this_coroutine()`, exceptions through tokens, interrupts.
 //
 // Process ordinals (names in the trace digest, Philox stream ids) are given in creation order: co_main is 0, every
 // coroutine object created after it 1, 2, ...  C++20, header-only, g++ >= 11.
@@ -240,21 +243,17 @@ struct env_timeout_awaitable {   // env.timeout(x)   (timeout.ipp:184-187)
 
 template <typename T>
 class coroutine;
+template <typename T>
+class subroutine;
 
 namespace detail {
-struct promise_base {
-    std::uint32_t id;
-    promise_base() {
-        record::context &c = record::ctx();
-        id = (std::uint32_t)c.procs.size();
-        c.procs.emplace_back();
-        c.procs.back().ordinal = id;
-    }
+// what a body may co_await (await_transform.ipp): shared by the promises of coroutine<T> and subroutine<T>
+struct await_ops {
     std::suspend_always initial_suspend() const noexcept { return {}; }
     std::suspend_always final_suspend() const noexcept { return {}; }
     void unhandled_exception() { throw; }
 
-    // co_await <something>: note it, do not suspend
+    // co_await <something>: note it in the process whose body is being run, do not suspend
     noted<> await_transform(timeout_awaitable t) {
         record::step s;
         s.kind = t.absolute ? record::step::UNTIL : record::step::DELAY;
@@ -275,9 +274,26 @@ struct promise_base {
     noted<U> await_transform(coroutine<U> &&child);
     template <typename U>
     noted<U> await_transform(coroutine<U> &child);
+    template <typename U>
+    noted<U> await_transform(subroutine<U> &&sub);
     template <typename A>
     auto await_transform(A &&a) -> decltype(std::forward<A>(a).cxxdes_record()) {   // sync operations, compositions, async
         return std::forward<A>(a).cxxdes_record();
+    }
+    // co_yield x is co_await x (await_transform.ipp:74-77): what `_Co_with` expands to
+    template <typename A>
+    auto yield_value(A &&a) -> decltype(this->await_transform(std::forward<A>(a))) {
+        return await_transform(std::forward<A>(a));
+    }
+};
+// a coroutine<T> is a process of its own
+struct promise_base : await_ops {
+    std::uint32_t id;
+    promise_base() {
+        record::context &c = record::ctx();
+        id = (std::uint32_t)c.procs.size();
+        c.procs.emplace_back();
+        c.procs.back().ordinal = id;
     }
 };
 }  // namespace detail
@@ -341,9 +357,60 @@ private:
     std::coroutine_handle<promise_type> h_;
 };
 
+// ---- subroutine<T> (subroutine.ipp): a coroutine frame on the call stack of the process that awaits it -- no start
+// or completion token, no process of its own.  Recording: its body runs where it is awaited and its awaits are noted in
+// the process being run.
+template <typename T = void>
+class subroutine {
+public:
+    struct promise_type : detail::await_ops {
+        T result{};
+        subroutine get_return_object() { return subroutine{std::coroutine_handle<promise_type>::from_promise(*this)}; }
+        template <typename V>
+        void return_value(V &&v) { result = std::forward<V>(v); }
+    };
+    subroutine(subroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    subroutine(const subroutine &) = delete;
+    ~subroutine() { if (h_) h_.destroy(); }
+    T run_now() {
+        if (!h_.done()) h_.resume();
+        return h_.promise().result;
+    }
+private:
+    explicit subroutine(std::coroutine_handle<promise_type> h) : h_(h) {}
+    std::coroutine_handle<promise_type> h_;
+};
+template <>
+class subroutine<void> {
+public:
+    struct promise_type : detail::await_ops {
+        subroutine get_return_object() { return subroutine{std::coroutine_handle<promise_type>::from_promise(*this)}; }
+        void return_void() const noexcept {}
+    };
+    subroutine(subroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    subroutine(const subroutine &) = delete;
+    ~subroutine() { if (h_) h_.destroy(); }
+    void run_now() {
+        if (!h_.done()) h_.resume();
+    }
+private:
+    explicit subroutine(std::coroutine_handle<promise_type> h) : h_(h) {}
+    std::coroutine_handle<promise_type> h_;
+};
+
 namespace detail {
 template <typename U>
-noted<U> promise_base::await_transform(coroutine<U> &child) {   // co_await p   (coroutine.ipp:179-207)
+noted<U> await_ops::await_transform(subroutine<U> &&sub) {   // co_await sub(): inline (subroutine.ipp:31-50)
+    record::ctx().current();            // (must be inside a process body)
+    if constexpr (std::is_void_v<U>) {
+        sub.run_now();
+        return {};
+    } else {
+        return noted<U>{sub.run_now()};
+    }
+}
+template <typename U>
+noted<U> await_ops::await_transform(coroutine<U> &child) {   // co_await p   (coroutine.ipp:179-207)
     record::step s;
     s.kind = record::step::AWAIT;
     s.index = child.id();
@@ -356,7 +423,7 @@ noted<U> promise_base::await_transform(coroutine<U> &child) {   // co_await p   
     }
 }
 template <typename U>
-noted<U> promise_base::await_transform(coroutine<U> &&child) {
+noted<U> await_ops::await_transform(coroutine<U> &&child) {
     // (the awaited temporary dies with the full expression; its body has been run by then and its steps are kept)
     return await_transform(static_cast<coroutine<U> &>(child));
 }
@@ -423,6 +490,36 @@ template <typename X, typename Y, typename = detail::child_of<X>, typename = det
 composition_awaitable operator&&(X &&x, Y &&y) { return all_of(std::forward<X>(x), std::forward<Y>(y)); }
 template <typename X, typename Y, typename = detail::child_of<X>, typename = detail::child_of<Y>>
 composition_awaitable operator||(X &&x, Y &&y) { return any_of(std::forward<X>(x), std::forward<Y>(y)); }
+
+// ---- sequential(a, b, ...) and the comma operator (sequential.ipp:1-84, compositions.ipp:24-27): a coroutine of the
+// library that awaits its arguments in order -- in the program, a helper process ------------------------------------
+struct sequential_helper {
+    template <typename... Ts>
+    static coroutine<void> seq_proc_tuple(Ts... ts) {
+        ((co_await std::move(ts)), ...);
+        co_return;
+    }
+    template <typename Iterator>
+    static coroutine<void> seq_proc_range(Iterator begin, Iterator end) {
+        for (Iterator it = begin; it != end; ++it) co_await (*it);
+        co_return;
+    }
+    struct functor {
+        template <typename... Ts>
+        [[nodiscard]] auto operator()(Ts &&...ts) const { return by_value(std::forward<Ts>(ts)...); }
+        template <typename... Ts>
+        [[nodiscard]] auto by_value(Ts &&...ts) const {
+            return seq_proc_tuple<std::remove_cvref_t<Ts>...>(std::forward<Ts>(ts)...);
+        }
+        template <typename... Ts>
+        [[nodiscard]] auto copy_rvalues(Ts &&...ts) const { return seq_proc_tuple<Ts...>(std::forward<Ts>(ts)...); }
+        template <typename Iterator>
+        [[nodiscard]] auto range_no_copy(Iterator first, Iterator last) const { return seq_proc_range(first, last); }
+    };
+};
+inline constexpr sequential_helper::functor sequential;
+template <typename X, typename Y, typename = detail::child_of<X>, typename = detail::child_of<Y>>
+auto operator,(X &&x, Y &&y) { return sequential(std::forward<X>(x), std::forward<Y>(y)); }
 
 // ---- a random variate on its way to env.timeout (cxxdes_b200/random_variable.hpp) ----------------------------------
 struct variate_tag {
@@ -629,3 +726,18 @@ private:
 
 }  // namespace sync
 }  // namespace cxxdes
+
+// ---- _Co_with(x) { body };   (co_with.ipp:19-35): a coroutine that acquires x, runs the body -- a subroutine -- and
+// releases; awaited with co_yield.  Same text as the reference's: in the program, a helper process
+// {acquire, the body's awaits, release} that the enclosing process awaits. ------------------------------------------------
+namespace cxxdes::core::detail {
+template <typename A>
+concept recorded_acquirable = requires(A a) { a.acquire().cxxdes_record().await_resume().release().cxxdes_record(); };
+}
+template <cxxdes::core::detail::recorded_acquirable A, typename F>
+cxxdes::core::coroutine<void> operator+(A &a, F &&f) {
+    auto handle = co_await a.acquire();
+    co_await std::forward<F>(f)();
+    co_await handle.release();
+}
+#define _Co_with(x) co_yield (x) + [&]() mutable -> cxxdes::core::subroutine<void>

@@ -43,7 +43,9 @@ int main() {
     record("mutex", recorded::mutex_example{});
     record("producer_consumer", recorded::producer_consumer{5.0, 10.0, 400});
     record("clocks", recorded::clocks{});
-    record("mixed", recorded::mixed{}, true);
+    record("mixed", recorded::mixed{});
+    record("co_with", recorded::co_with_example{});
+    record("sequential", recorded::sequential_example{}, true);
     std::printf("}\n");
     return 0;
 }

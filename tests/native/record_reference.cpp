@@ -43,7 +43,9 @@ int main() {
     run<recorded::mutex_example>("mutex", 1, -1, false);
     run<recorded::producer_consumer>("producer_consumer", 4, -1, false, 5.0, 10.0, (std::size_t)400);
     run<recorded::clocks>("clocks", 1, 20, false);
-    run<recorded::mixed>("mixed", 1, -1, true);
+    run<recorded::mixed>("mixed", 1, -1, false);
+    run<recorded::co_with_example>("co_with", 1, -1, false);
+    run<recorded::sequential_example>("sequential", 1, -1, true);
     std::printf("}\n");
     return 0;
 }

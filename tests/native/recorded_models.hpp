@@ -1,6 +1,7 @@
 // tests/native/recorded_models.hpp -- libcxxdes models as a user writes them: real C++20 coroutine bodies on the
 // reference's public API (CXXDES_SIMULATION, coroutine<>, timeout / delay / yield, all_of / any_of / && / ||, async,
-// sync::queue / resource / mutex, .priority() / .return_latency(), env.time_unit / time_precision / timeout).
+// sync::queue / resource / mutex, .priority() / .return_latency(), env.time_unit / time_precision / timeout,
+// _Co_with, sequential / the comma operator, subroutine<>).
 // This ONE source text is compiled twice by tests/test_record.py:
 //   * against the reference's <cxxdes/cxxdes.hpp> (record_reference.cpp): the unmodified engine runs it;
 //   * against include/cxxdes_b200/record/cxxdes/cxxdes.hpp (record_dump.cpp): the bodies are recorded into process
@@ -114,6 +115,56 @@ CXXDES_SIMULATION(mixed) {
             co_await delay(1);
         }
         co_await until(40);
+    }
+};
+
+// examples/mutex.cpp:8-31 and examples/raii_trick.cpp:8-30 AS WRITTEN: `_Co_with(x) { ... };` -- a coroutine of the library
+// that acquires, runs the body (a subroutine) and releases (co_with.ipp:27-35)
+CXXDES_SIMULATION(co_with_example) {
+    cxxdes::sync::mutex m;
+    cxxdes::sync::resource res{1};
+
+    coroutine<> p(int idx, time_integral t) {
+        (void)idx;
+        _Co_with(m) {
+            co_await delay(t);
+        };
+    }
+    coroutine<> r(int id, time_integral wait_time) {
+        (void)id;
+        _Co_with(res) {
+            co_await timeout(wait_time);
+        };
+    }
+
+    coroutine<> co_main() {
+        co_await all_of(p(1, 5).priority(5), p(2, 5).priority(3), p(3, 5).priority(2), p(4, 5).priority(4), p(5, 5).priority(1));
+        co_await all_of(r(0, 10).priority(0), r(1, 5).priority(-1), r(2, 8).priority(-2), r(3, 8).priority(-3));
+    }
+};
+
+// sequential(...), the comma operator, a sequential as a child of all_of, subroutine<T> with a return value
+// (sequential.ipp, compositions.ipp:24-27, subroutine.ipp; tests/controlflow.test.cpp, examples/subroutine.cpp)
+CXXDES_SIMULATION(sequential_example) {
+    subroutine<int> twice(time_integral t) {
+        co_await delay(t);
+        co_await delay(t);
+        co_return 2;
+    }
+    subroutine<> nested(time_integral t) {
+        int n = co_await twice(t);
+        for (int k = 0; k < n; ++k) co_await yield();
+    }
+    coroutine<> worker(time_integral t) {
+        co_await nested(t);
+        co_await delay(1);
+    }
+    coroutine<> co_main() {
+        co_await sequential(delay(3), delay(4));
+        co_await (delay(1), delay(2));
+        co_await all_of(sequential(delay(5), worker(2)), delay(7));
+        co_await sequential(worker(1), timeout(2, 3), worker(3).priority(-2));
+        co_await (worker(1), delay(2), yield());
     }
 };
 

@@ -1,8 +1,8 @@
 """Real C++20 coroutine bodies as process programs (include/cxxdes_b200/record/cxxdes/cxxdes.hpp).
 
 tests/native/recorded_models.hpp is ONE model source written on the reference's public API (CXXDES_SIMULATION,
-coroutine<>, timeout(t, priority), all_of / any_of / && / ||, async, sync::queue / resource / mutex, .priority(),
-.return_latency(), env.time_unit / time_precision / timeout).  It is compiled twice: against the reference's headers and
+coroutine<>, subroutine<>, timeout(t, priority), all_of / any_of / && / ||, sequential / the comma operator, async,
+_Co_with, sync::queue / resource / mutex, .priority(), .return_latency(), env.time_unit / time_precision / timeout).  It is compiled twice: against the reference's headers and
 run by the unmodified reference engine, and against the recording <cxxdes/cxxdes.hpp>, which runs every body once on the
 host and emits the model as a process program.  The program, interpreted by the CPU oracle (here) and by the CUDA
 kernels (-m gpu), must dispatch the tokens the reference engine dispatched for the same source."""
@@ -84,7 +84,7 @@ def test_loops_are_folded_back(recorded):
     assert sum(1 for o in recorded["clocks"]["ops"] if o[0] == abi.OP_LOOP and o[3] == 1 << 30) == 3
 
 
-@pytest.mark.parametrize("name", ["resource", "mutex", "producer_consumer", "clocks", "mixed"])
+@pytest.mark.parametrize("name", ["resource", "mutex", "producer_consumer", "clocks", "mixed", "co_with", "sequential"])
 def test_recorded_program_equals_the_reference_engine_running_the_source(recorded, reference_runs, port, name):
     tables = recorded[name]
     pp = program_params(tables)
@@ -121,7 +121,7 @@ class _RawProgram:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["resource", "mutex", "producer_consumer", "clocks", "mixed"])
+@pytest.mark.parametrize("name", ["resource", "mutex", "producer_consumer", "clocks", "mixed", "co_with", "sequential"])
 def test_gpu_runs_the_recorded_programs(recorded, port, name):
     tables = recorded[name]
     clock, pairs = clock_of(tables)

@@ -23,7 +23,9 @@
 // `subroutine<T>` bodies run inside the process that awaits them (subroutine.ipp: no tokens of their own), so their awaits
 // are noted in that process; `_Co_with(x) { ... };` and `sequential(a, b, ...)` / the comma operator are, as in the
 // reference (co_with.ipp:27-35, sequential.ipp:1-20), coroutines of the library -- helper processes of the program.
-// Not provided: `>>` / `flag_done`, `this_coroutine()`, exceptions through tokens, interrupts.
+// So are `>>` and `flag_done`.  `co_await this_coroutine()` / `this_environment()` give views for a body's own use.
+// Not provided: time-expression literals (`10_x`), copyable coroutine handles, `lazy_timeout`, exceptions through
+// tokens, interrupts.  tests/test_record_examples.py: eleven of the reference's own examples, source files unchanged.
 //
 // Process ordinals (names in the trace digest, Philox stream ids) are given in creation order: co_main is 0, every
 // coroutine object created after it 1, 2, ...  C++20, header-only, g++ >= 11.
@@ -245,6 +247,24 @@ template <typename T>
 class coroutine;
 template <typename T>
 class subroutine;
+class environment;
+
+// co_await this_coroutine() / this_environment() (await_transform.ipp:21-25,66-72): no event; what they return is a
+// view for a body's own use (prints): the process's priority option as given, a clock that reads 0 while recording
+struct this_coroutine {};
+struct this_environment {};
+struct coroutine_view {
+    priority_type priority_ = 0;
+    time_integral latency_ = 0;
+    priority_type priority() const noexcept { return priority_; }
+    time_integral latency() const noexcept { return latency_; }
+    const coroutine_view *operator->() const noexcept { return this; }
+};
+struct environment_view {
+    time_integral now() const noexcept { return 0; }
+    real_type now_seconds() const noexcept { return 0.0; }
+    const environment_view *operator->() const noexcept { return this; }
+};
 
 namespace detail {
 // what a body may co_await (await_transform.ipp): shared by the promises of coroutine<T> and subroutine<T>
@@ -276,6 +296,14 @@ struct await_ops {
     noted<U> await_transform(coroutine<U> &child);
     template <typename U>
     noted<U> await_transform(subroutine<U> &&sub);
+    noted<coroutine_view> await_transform(this_coroutine) const {
+        const record::proc_info &p = record::ctx().procs[record::ctx().current()];
+        coroutine_view v;
+        v.priority_ = p.opt.priority == ::cxxdes::b200::inherit ? 0 : p.opt.priority;
+        v.latency_ = p.opt.latency;
+        return {v};
+    }
+    noted<environment_view> await_transform(this_environment) const { return {}; }
     template <typename A>
     auto await_transform(A &&a) -> decltype(std::forward<A>(a).cxxdes_record()) {   // sync operations, compositions, async
         return std::forward<A>(a).cxxdes_record();
@@ -308,8 +336,16 @@ public:
         template <typename V>
         void return_value(V &&v) { result = std::forward<V>(v); }
     };
+    coroutine() noexcept : h_(nullptr) {}            // (an empty handle, to be assigned a process later)
     coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
     coroutine(const coroutine &) = delete;
+    coroutine &operator=(coroutine &&o) noexcept {
+        if (this != &o) {
+            if (h_) h_.destroy();
+            h_ = std::exchange(o.h_, nullptr);
+        }
+        return *this;
+    }
     ~coroutine() { if (h_) h_.destroy(); }
     std::uint32_t id() const { return h_.promise().id; }
     // coroutine.ipp:106-176
@@ -338,8 +374,16 @@ public:
         coroutine get_return_object() { return coroutine{std::coroutine_handle<promise_type>::from_promise(*this)}; }
         void return_void() const noexcept {}
     };
+    coroutine() noexcept : h_(nullptr) {}            // (an empty handle, to be assigned a process later)
     coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
     coroutine(const coroutine &) = delete;
+    coroutine &operator=(coroutine &&o) noexcept {
+        if (this != &o) {
+            if (h_) h_.destroy();
+            h_ = std::exchange(o.h_, nullptr);
+        }
+        return *this;
+    }
     ~coroutine() { if (h_) h_.destroy(); }
     std::uint32_t id() const { return h_.promise().id; }
     coroutine &&priority(priority_type p) && { info().opt.priority = p; return std::move(*this); }
@@ -478,14 +522,33 @@ inline ::cxxdes::b200::child as_child(const composition_awaitable &c) { return :
 template <typename X>
 using child_of = decltype(as_child(std::declval<X>()));
 }  // namespace detail
-template <typename... A>
-composition_awaitable all_of(A &&...a) {
-    return {::cxxdes::b200::composition{true, {detail::as_child(std::forward<A>(a))...}}};
-}
-template <typename... A>
-composition_awaitable any_of(A &&...a) {
-    return {::cxxdes::b200::composition{false, {detail::as_child(std::forward<A>(a))...}}};
-}
+namespace detail {
+template <bool ALL>
+struct composition_functor {   // any_of.ipp:163-231: all_of(a, b, ...), all_of.range(first, last), ...
+    template <typename... A>
+    [[nodiscard]] composition_awaitable operator()(A &&...a) const {
+        return {::cxxdes::b200::composition{ALL, {as_child(std::forward<A>(a))...}}};
+    }
+    template <typename... A>
+    [[nodiscard]] composition_awaitable by_value(A &&...a) const { return (*this)(std::forward<A>(a)...); }
+    template <typename... A>
+    [[nodiscard]] composition_awaitable by_reference(A &&...a) const { return (*this)(std::forward<A>(a)...); }
+    template <typename... A>
+    [[nodiscard]] composition_awaitable copy_rvalues(A &&...a) const { return (*this)(std::forward<A>(a)...); }
+    template <typename Iterator>
+    [[nodiscard]] composition_awaitable range(Iterator first, Iterator last) const {
+        ::cxxdes::b200::composition c{ALL, {}};
+        for (; first != last; ++first) c.children.push_back(as_child(*first));
+        return {c};
+    }
+    template <typename Iterator>
+    [[nodiscard]] composition_awaitable range_copy(Iterator first, Iterator last) const { return range(first, last); }
+    template <typename Iterator>
+    [[nodiscard]] composition_awaitable range_no_copy(Iterator first, Iterator last) const { return range(first, last); }
+};
+}  // namespace detail
+inline constexpr detail::composition_functor<true> all_of;
+inline constexpr detail::composition_functor<false> any_of;
 template <typename X, typename Y, typename = detail::child_of<X>, typename = detail::child_of<Y>>
 composition_awaitable operator&&(X &&x, Y &&y) { return all_of(std::forward<X>(x), std::forward<Y>(y)); }
 template <typename X, typename Y, typename = detail::child_of<X>, typename = detail::child_of<Y>>
@@ -520,6 +583,21 @@ struct sequential_helper {
 inline constexpr sequential_helper::functor sequential;
 template <typename X, typename Y, typename = detail::child_of<X>, typename = detail::child_of<Y>>
 auto operator,(X &&x, Y &&y) { return sequential(std::forward<X>(x), std::forward<Y>(y)); }
+
+// ---- p >> out, flag_done(flag)   (compositions.ipp:29-37): library coroutines again; while recording `out` receives
+// what the awaited body returned on the host (the same in every replication, or it is not recordable) ---------------
+template <typename U, typename Output>
+coroutine<void> operator>>(coroutine<U> &&a, Output &output) {
+    output = co_await a;
+}
+template <typename U, typename Output>
+coroutine<void> operator>>(coroutine<U> &a, Output &output) {
+    output = co_await a;
+}
+inline coroutine<void> flag_done(bool &flag) {
+    flag = true;
+    co_return;
+}
 
 // ---- a random variate on its way to env.timeout (cxxdes_b200/random_variable.hpp) ----------------------------------
 struct variate_tag {
@@ -599,6 +677,10 @@ struct simulation {
         return ens;
     }
 
+    // simulation<>::run / run_for (core/simulation.hpp:51-62): ONE replication of the recorded model on the GPU
+    void run() { ensemble(1)->run(); }
+    void run_for(::cxxdes::b200::time_integral t) { ensemble(1)->run_for(t); }
+
 protected:
     void bind() {
         if (!bound_) {
@@ -661,8 +743,12 @@ struct simple_awaitable {
     ::cxxdes::b200::simple_op op;
     core::noted<> cxxdes_record() const { return note_simple(op); }
 };
+// `evt.wait() || timeout(t)`: an event wait as a child of a composition (found by the compositions through ADL; the
+// builder refuses any other sync operation there)
+inline ::cxxdes::b200::child as_child(const simple_awaitable &a) { return ::cxxdes::b200::child(a.op); }
 }  // namespace detail
 
+template <typename T = std::size_t>
 class semaphore {   // sync/semaphore.hpp:58-78
 public:
     explicit semaphore(std::size_t value = 0, std::size_t max = ~std::size_t(0)) : id_((std::uint16_t)record::ctx().sem_init.size()) {
@@ -691,7 +777,7 @@ public:
     };
     acquire_awaitable acquire() const { return {sem_.down(), sem_.up()}; }
 private:
-    semaphore sem_;
+    semaphore<> sem_;
 };
 
 class mutex {   // sync/mutex.hpp:31-109

@@ -1,0 +1,376 @@
+// tests/native/cuda_on_host/runtime.cpp -- TEST INFRASTRUCTURE (see cuda_runtime.h in this directory).
+//
+// Blocks of a grid run one after another on the calling OS thread; the CUDA threads of a block are fibres (a
+// hand-written x86-64 stack switch, ucontext elsewhere) that run until they reach a rendez-vous -- __syncthreads, a
+// vote, a shuffle, __syncwarp, __nanosleep -- and are resumed round-robin.  A rendez-vous completes when every lane of
+// its mask that has not exited has arrived; a round in which no fibre could move is reported as a deadlock together
+// with where every lane waits.  All lanes of a rendez-vous must have called the same kind of primitive (a vote meeting
+// a shuffle is a divergence bug on the device as well): checked.
+#include <cuda_runtime.h>
+
+#include <sys/mman.h>
+
+#include <chrono>
+#include <vector>
+
+#if !defined(__x86_64__)
+#include <ucontext.h>
+#endif
+
+namespace cuda_host {
+
+thread_ctx *current = nullptr;
+unsigned char shared_anchor = 0;
+
+namespace {
+
+constexpr size_t STACK_BYTES = 1u << 20;          // per fibre, mapped lazily
+constexpr size_t SHARED_ARENA_BYTES = 232448;     // 227 KiB: what one block may opt in to on sm_100
+
+struct rendezvous {          // one per (warp, mask) in flight
+    unsigned mask = 0;
+    unsigned arrived = 0;
+    unsigned generation = 0;
+    int op = 0;
+    uint64_t in[32];
+    uint64_t out[32];
+};
+
+struct warp_state {
+    unsigned alive = 0;      // lanes that have not returned from the kernel
+    std::vector<rendezvous> meets;
+};
+
+struct fibre {
+    thread_ctx ctx;
+    void *sp = nullptr;          // saved stack pointer (x86-64)
+#if !defined(__x86_64__)
+    ucontext_t uc;
+#endif
+    unsigned char *stack = nullptr;
+    bool done = false;
+    int warp = 0, lane = 0;
+    const unsigned *wait_word = nullptr;   // blocked until *wait_word != wait_value
+    unsigned wait_value = 0;
+    const char *wait_what = "";
+    bool polling = false;                  // called __nanosleep: resumed in the next round
+};
+
+struct scheduler {
+    std::vector<fibre> fibres;
+    std::vector<warp_state> warps;
+    std::vector<unsigned char *> stacks;   // pool, grows to the largest block seen
+    block_ctx block;
+    unsigned barrier_arrived = 0, barrier_generation = 0, alive = 0;
+    void (*entry)(void *) = nullptr;
+    void *closure = nullptr;
+    fibre *running = nullptr;
+    void *main_sp = nullptr;
+#if !defined(__x86_64__)
+    ucontext_t main_uc;
+#endif
+    bool progressed = false;
+    const char *kernel = "";
+};
+
+scheduler S;
+alignas(16) unsigned char shared_arena[SHARED_ARENA_BYTES];
+
+#if defined(__x86_64__)
+extern "C" void cuda_host_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl cuda_host_switch
+.type cuda_host_switch, @function
+cuda_host_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size cuda_host_switch, .-cuda_host_switch
+)");
+#endif
+
+void to_scheduler() {
+    fibre *f = S.running;
+#if defined(__x86_64__)
+    cuda_host_switch(&f->sp, S.main_sp);
+#else
+    swapcontext(&f->uc, &S.main_uc);
+#endif
+}
+
+void lane_exited(fibre *f);
+
+void fibre_main() {
+    fibre *f = S.running;
+    S.entry(S.closure);
+    f->done = true;
+    lane_exited(f);
+    to_scheduler();
+    abort();   // a finished fibre is never resumed
+}
+
+#if !defined(__x86_64__)
+void fibre_main_uc() { fibre_main(); }
+#endif
+
+void complete(rendezvous &m) {
+    memcpy(m.out, m.in, sizeof(m.out));
+    m.arrived = 0;
+    ++m.generation;
+    S.progressed = true;
+}
+
+void lane_exited(fibre *f) {
+    warp_state &w = S.warps[f->warp];
+    w.alive &= ~(1u << f->lane);
+    --S.alive;
+    S.progressed = true;
+    // a lane that returns no longer takes part: rendez-vous that were only waiting for it complete
+    for (rendezvous &m : w.meets)
+        if (m.arrived && (m.arrived & w.alive) == (m.mask & w.alive)) complete(m);
+    if (S.alive && S.barrier_arrived == S.alive) {
+        S.barrier_arrived = 0;
+        ++S.barrier_generation;
+    }
+}
+
+void wait_for(const unsigned *word, unsigned value, const char *what) {
+    fibre *f = S.running;
+    while (*word == value) {
+        f->wait_word = word;
+        f->wait_value = value;
+        f->wait_what = what;
+        to_scheduler();
+    }
+    f->wait_word = nullptr;
+}
+
+[[noreturn]] void deadlock() {
+    fprintf(stderr, "cuda_on_host: deadlock in %s, block %u: no thread can move\n", S.kernel, S.block.idx.x);
+    for (size_t t = 0; t < S.fibres.size(); ++t) {
+        const fibre &f = S.fibres[t];
+        if (!f.done) fprintf(stderr, "  thread %zu (warp %d lane %d): %s\n", t, f.warp, f.lane, f.wait_word ? f.wait_what : "runnable");
+    }
+    abort();
+}
+
+}  // namespace
+
+int lane_id() { return S.running->lane; }
+
+const uint64_t *warp_gather(unsigned mask, uint64_t value, int op) {
+    fibre *f = S.running;
+    warp_state &w = S.warps[f->warp];
+    if (!((mask >> f->lane) & 1u)) {
+        fprintf(stderr, "cuda_on_host: %s: lane %d calls a warp primitive with mask %08x that does not name it\n", S.kernel, f->lane, mask);
+        abort();
+    }
+    rendezvous *m = nullptr;
+    for (rendezvous &c : w.meets)
+        if (c.mask == mask) { m = &c; break; }
+    if (!m) {
+        w.meets.emplace_back();
+        m = &w.meets.back();
+        m->mask = mask;
+    }
+    const size_t index = (size_t)(m - w.meets.data());   // (the vector may grow while this lane waits)
+    if (m->arrived == 0) m->op = op;
+    else if (m->op != op) {
+        fprintf(stderr, "cuda_on_host: %s: lanes of mask %08x meet in different primitives (%d and %d)\n", S.kernel, mask, m->op, op);
+        abort();
+    }
+    m->in[f->lane] = value;
+    m->arrived |= 1u << f->lane;
+    const unsigned generation = m->generation;
+    if ((m->arrived & w.alive) == (mask & w.alive)) complete(*m);
+    else {
+        // &w.meets[index].generation may move when another lane adds a rendez-vous: wait on a copy of the index
+        while (S.warps[f->warp].meets[index].generation == generation) {
+            f->wait_word = &S.warps[f->warp].meets[index].generation;
+            f->wait_value = generation;
+            f->wait_what = op == OP_SYNCWARP ? "__syncwarp" : op == OP_VOTE ? "vote" : "shuffle";
+            to_scheduler();
+        }
+        f->wait_word = nullptr;
+    }
+    return S.warps[f->warp].meets[index].out;
+}
+
+void block_barrier() {
+    const unsigned generation = S.barrier_generation;
+    if (++S.barrier_arrived == S.alive) {
+        S.barrier_arrived = 0;
+        ++S.barrier_generation;
+        S.progressed = true;
+        return;
+    }
+    wait_for(&S.barrier_generation, generation, "__syncthreads");
+}
+
+void yield() {
+    fibre *f = S.running;   // a polling loop: somebody else (another lane of this block) has to make the progress
+    f->wait_word = nullptr;
+    f->polling = true;
+    to_scheduler();
+}
+
+uint64_t globaltimer() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *closure, const char *what) {
+    if (S.running) {
+        fprintf(stderr, "cuda_on_host: kernel launch from inside a kernel\n");
+        abort();
+    }
+    const unsigned n_threads = cfg.block.x * cfg.block.y * cfg.block.z;
+    if (cfg.shared_bytes > SHARED_ARENA_BYTES || n_threads == 0 || n_threads > 1024 || cfg.block.y != 1 || cfg.block.z != 1 ||
+        cfg.grid.y != 1 || cfg.grid.z != 1) {
+        fprintf(stderr, "cuda_on_host: %s: unsupported launch (%u x %u threads, %zu bytes of shared memory)\n", what, cfg.grid.x, n_threads, cfg.shared_bytes);
+        abort();
+    }
+    while (S.stacks.size() < n_threads) {
+        void *p = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p == MAP_FAILED) { perror("cuda_on_host: mmap"); abort(); }
+        S.stacks.push_back((unsigned char *)p);
+    }
+    S.entry = thread_entry;
+    S.closure = closure;
+    S.kernel = what;
+    for (unsigned b = 0; b < cfg.grid.x; ++b) {
+        memset(shared_arena, 0xA5, cfg.shared_bytes);   // shared memory starts out undefined
+        S.block.idx = uint3{b, 0, 0};
+        S.block.dim = uint3{cfg.block.x, 1, 1};
+        S.block.grid = uint3{cfg.grid.x, 1, 1};
+        S.block.dynamic_shared = shared_arena;
+        S.fibres.assign(n_threads, fibre{});
+        S.warps.assign((n_threads + 31) / 32, warp_state{});
+        S.barrier_arrived = 0;
+        S.alive = n_threads;
+        for (unsigned t = 0; t < n_threads; ++t) {
+            fibre &f = S.fibres[t];
+            f.ctx.thread_idx = uint3{t, 0, 0};
+            f.ctx.block = &S.block;
+            f.warp = (int)(t / 32);
+            f.lane = (int)(t % 32);
+            f.stack = S.stacks[t];
+            S.warps[f.warp].alive |= 1u << f.lane;
+#if defined(__x86_64__)
+            // what cuda_host_switch pops: six callee-saved registers, then `ret` into fibre_main with the stack as
+            // after a call (return address slot at top - 8)
+            uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
+            void **sp = (void **)top;
+            *--sp = nullptr;                    // fake return address of fibre_main
+            *--sp = (void *)&fibre_main;
+            for (int k = 0; k < 6; ++k) *--sp = nullptr;
+            f.sp = sp;
+#else
+            getcontext(&f.uc);
+            f.uc.uc_stack.ss_sp = f.stack;
+            f.uc.uc_stack.ss_size = STACK_BYTES;
+            f.uc.uc_link = nullptr;
+            makecontext(&f.uc, fibre_main_uc, 0);
+#endif
+        }
+        // One warp at a time, for as long as one of its lanes can move (its lanes mostly wait for each other); a lane that
+        // polls (__nanosleep) waits for the next round of the outer loop, where every other warp has had its turn.
+        while (S.alive) {
+            S.progressed = false;
+            for (unsigned w = 0; w < (unsigned)S.warps.size(); ++w) {
+                const unsigned first = w * 32, last = first + 32 < n_threads ? first + 32 : n_threads;
+                bool moved = true;
+                while (moved) {
+                    moved = false;
+                    for (unsigned t = first; t < last; ++t) {
+                        fibre &f = S.fibres[t];
+                        if (f.done || f.polling) continue;
+                        if (f.wait_word && *f.wait_word == f.wait_value) continue;   // still blocked
+                        S.running = &f;
+                        current = &f.ctx;
+                        moved = true;
+#if defined(__x86_64__)
+                        cuda_host_switch(&S.main_sp, f.sp);
+#else
+                        swapcontext(&S.main_uc, &f.uc);
+#endif
+                    }
+                    if (moved) S.progressed = true;
+                }
+                for (unsigned t = first; t < last; ++t) S.fibres[t].polling = false;
+            }
+            if (!S.progressed) deadlock();
+        }
+        S.running = nullptr;
+        current = nullptr;
+    }
+}
+
+}  // namespace cuda_host
+
+// ---- the runtime API: host memory, streams in host order ----------------------------------------------------------------
+struct cuda_host_stream { int unused; };
+struct cuda_host_event { std::chrono::steady_clock::time_point at; };
+
+static int env_int(const char *name, int otherwise) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : otherwise;
+}
+
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
+    if (d != 0) return cudaErrorInvalidValue;
+    memset(p, 0, sizeof(*p));
+    snprintf(p->name, sizeof(p->name), "cuda_on_host (CPU emulation for tests)");
+    p->major = 10;
+    p->minor = 0;
+    p->multiProcessorCount = env_int("CUDA_ON_HOST_SMS", 2);
+    p->sharedMemPerBlockOptin = 232448;
+    p->sharedMemPerMultiprocessor = 233472;
+    p->totalGlobalMem = (size_t)8 << 30;
+    p->regsPerMultiprocessor = 65536;
+    p->maxThreadsPerMultiProcessor = 2048;
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void **p, size_t bytes) {
+    void *q = nullptr;
+    if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
+    memset(q, 0xCD, bytes);   // device memory is not zeroed
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { memset(dst, value, bytes); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new cuda_host_stream{}; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { return cudaStreamCreate(s); }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *low, int *high) { *low = 0; *high = -1; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cuda_host_event{}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->at = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->at - a->at).count();
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuda_on_host error"; }

@@ -1,0 +1,13 @@
+#!/bin/bash
+# The whole `-m gpu` suite against the CPU emulation of the device (tests/native/cuda_on_host): every kernel of
+# libcxxdes_b200/csrc compiled by g++, CUDA threads as fibres.  TEST INFRASTRUCTURE -- checks the kernels' logic where no
+# GPU is at hand; says nothing about speed.  tests/test_kernels_on_host.py runs the same thing without the tests that
+# are sized for the device; this script runs everything (about a quarter of an hour on 8 cores; expect the tests that
+# need two kernels at once or link the CUDA build to fail: see DESELECT in tests/test_kernels_on_host.py).
+#   tools/gpu_suite_on_host.sh [pytest arguments, e.g. tests/test_models_gpu.py -k aloha]
+set -e
+cd "$(dirname "$0")/.."
+lib=$(python tests/native/cuda_on_host/build.py | tail -1)
+export CXXDES_B200_LIBRARY="$lib" CUDA_ON_HOST_SMS="${CUDA_ON_HOST_SMS:-2}"
+if [ $# -eq 0 ]; then set -- tests; fi
+exec python -m pytest "$@" -m gpu -q -p no:cacheprovider -n "${JOBS:-6}" --timeout 3600 --durations=15

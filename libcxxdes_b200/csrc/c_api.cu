@@ -107,6 +107,9 @@ struct cxxdes_b200_ensemble {
     uint32_t *saved_words = nullptr;
     int64_t *saved_queue_items = nullptr;   // process programs: queue payloads
     bool saved_valid = false;               // written by the previous launch of this handle
+    // last pass of the models whose containers are unbounded in the reference: heap and wait lists in global memory,
+    // sized for the model's worst case (M/M/c: models_mmc.cu mmc_deep_plan)
+    mmc_deep mmc_deep_pass{};
 
     // M/M/1: the second pass runs next to the first one on a stream of the handle's own (mm1_fused.cu)
     cudaStream_t helper_stream = nullptr;
@@ -123,6 +126,13 @@ namespace {
 int set_device(const cxxdes_b200_ensemble *e) {
     CUDA_TRY(cudaSetDevice(e->cfg.device));
     return CXXDES_B200_OK;
+}
+
+// Global memory the last, unbounded pass of a model may use for its heaps and wait lists (CXXDES_B200_DEEP_BYTES, read at
+// create; 0 switches the pass off and a replication that outgrows the on-chip capacities keeps its status flag).
+size_t deep_pass_budget() {
+    if (const char *text = getenv("CXXDES_B200_DEEP_BYTES")) return (size_t)strtoull(text, nullptr, 10);
+    return (size_t)256 << 20;
 }
 
 int allocate(cxxdes_b200_ensemble *e) {
@@ -149,6 +159,10 @@ int allocate(cxxdes_b200_ensemble *e) {
     CUDA_TRY(cudaMalloc(&e->reduce_scratch, reduce_scratch_bytes(e->sm_count)));
     if (e->ring_bytes) CUDA_TRY(cudaMalloc(&e->ring, e->ring_bytes));
     if (e->ahead_gring_bytes) CUDA_TRY(cudaMalloc(&e->ahead_gring, e->ahead_gring_bytes));
+    if (e->cfg.model == CXXDES_B200_MODEL_MMC) {
+        if (const size_t bytes = mmc_deep_plan(e->params.mmc, e->sm_count, deep_pass_budget(), e->mmc_deep_pass))
+            CUDA_TRY(cudaMalloc(&e->mmc_deep_pass.base, bytes));
+    }
     return CXXDES_B200_OK;
 }
 
@@ -355,7 +369,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_mmc(e->params.mmc, sh, e->cols, (uint64_t *)e->ring, e->sm_count, e->counters + 2, e->stream,
-                                &launches, st, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0));
+                                &launches, st, (e->cfg.flags & CXXDES_B200_FLAG_WIDE_TOKENS) != 0, e->mmc_deep_pass));
             break;
         }
         case CXXDES_B200_MODEL_ARCHSIM: {
@@ -905,6 +919,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->prog_queue_items);
     cudaFree(e->saved_words);
     cudaFree(e->saved_queue_items);
+    cudaFree(e->mmc_deep_pass.base);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->helper_stream) { cudaStreamSynchronize(e->helper_stream); cudaStreamDestroy(e->helper_stream); }

@@ -94,9 +94,17 @@ struct mmc_saved {            // run_until / run_for in pieces (nullptr words = 
 bool mmc_narrow_applies(const cxxdes_b200_mmc_params &prm, const shard &sh);   // first pass on 4-byte tokens
 bool mmc_keeps_state(const cxxdes_b200_mmc_params &prm, const shard &sh);   // the 32-bit kernel runs the model
 size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm);
+// The last pass: heap and wait list of a replication in global memory, sized for the model's worst case (what the
+// reference's unbounded containers could hold).  base == nullptr: no such pass.
+struct mmc_deep {
+    unsigned char *base;
+    int threads;                // of the deep grid; its arrays are laid out [entry][thread]
+    int heap_cap, waiter_cap;
+};
+size_t mmc_deep_plan(const cxxdes_b200_mmc_params &prm, int sm_count, size_t budget_bytes, mmc_deep &d);   // bytes to allocate
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches, const mmc_saved &st, bool wide_tokens);
+                       int *launches, const mmc_saved &st, bool wide_tokens, const mmc_deep &deep);
 
 // ---- memory hierarchy (models_archsim.cu) ----
 bool archsim_supported(const cxxdes_b200_archsim_params &p);

@@ -36,18 +36,43 @@ constexpr int C_T0_SHIFT = 16;
 // Generic-engine kernel: 64-bit keys, 96-entry heap and waiter list.  Runs the whole shard, or
 // (list != nullptr) only the replications the compact kernel below handed back.
 // ENV = traced_environment: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
-template <typename ENV>
+// DEEP: the last pass.  The reference's containers are unbounded (std::priority_queue, the event's std::vector of
+// waiters); a replication that outgrew the 96 entries above -- an overloaded system: acquire_procs of customers who
+// balked keep waiting for a server -- is run again with its heap and wait list in GLOBAL memory, sized from
+// n_customers for the worst case (mmc_deep_plan), so that it gets the reference's result instead of an error flag.
+// The pass walks the whole shard and takes the replications whose status carries a capacity flag.
+template <typename ENV, bool DEEP = false>
 __global__ void __launch_bounds__(MMC_THREADS)
 mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *cust_base, const uint32_t *list,
-           const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink) {
+           const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink, mmc_deep deep) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
     stage_log_table(table, sh.log_table);
-    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, MMC_HEAP);
-    lane_array<uint32_t> htag = carve<uint32_t>(cursor, MMC_HEAP);
-    lane_array<uint32_t> wwho = carve<uint32_t>(cursor, MMC_WAITERS);
-    lane_array<int32_t> wlat = carve<int32_t>(cursor, MMC_WAITERS);
+    lane_array<uint64_t> hkey;
+    lane_array<uint32_t> htag, wwho;
+    lane_array<int32_t> wlat;
+    int heap_cap = MMC_HEAP, waiter_cap = MMC_WAITERS;
+    if constexpr (DEEP) {
+        // [entry][thread of the deep grid]: keys, tags, waiters, wait latencies
+        const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)deep.threads;
+        heap_cap = deep.heap_cap;
+        waiter_cap = deep.waiter_cap;
+        unsigned char *g = deep.base;
+        hkey.base = (uint64_t *)g + t;
+        g += 8 * nt * (size_t)heap_cap;
+        htag.base = (uint32_t *)g + t;
+        g += 4 * nt * (size_t)heap_cap;
+        wwho.base = (uint32_t *)g + t;
+        g += 4 * nt * (size_t)waiter_cap;
+        wlat.base = (int32_t *)g + t;
+        hkey.stride = htag.stride = wwho.stride = wlat.stride = deep.threads;
+    } else {
+        hkey = carve<uint64_t>(cursor, MMC_HEAP);
+        htag = carve<uint32_t>(cursor, MMC_HEAP);
+        wwho = carve<uint32_t>(cursor, MMC_WAITERS);
+        wlat = carve<int32_t>(cursor, MMC_WAITERS);
+    }
 
     const uint64_t total_threads = (uint64_t)gridDim.x * blockDim.x;
     uint64_t *cust = cust_base + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
@@ -57,8 +82,20 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
     const uint32_t NOOP_TAG = make_tag(TAG_NO_TARGET);
 
     uint64_t rep;
+    [[maybe_unused]] unsigned long long chunk_next = 0, chunk_end = 0;
     for (;;) {
-        if (list) {
+        if constexpr (DEEP) {
+            // (list_cursor: this pass's own work counter, claimed 16 replications at a time; list_count: where it
+            // counts what it took)
+            if (chunk_next == chunk_end) {
+                chunk_next = atomicAdd(list_cursor, 16ULL);
+                chunk_end = chunk_next + 16;
+            }
+            if (chunk_next >= sh.n_replications) break;
+            rep = chunk_next++;
+            if (!(out.status[rep] & (CXXDES_B200_REP_HEAP_OVERFLOW | CXXDES_B200_REP_WAITER_OVERFLOW))) continue;
+            atomicAdd((unsigned long long *)list_count, 1ULL);
+        } else if (list) {
             const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
             if (idx >= *list_count) break;
             rep = list[idx];
@@ -71,10 +108,10 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
         addr.replication = grep;
 
         ENV env;
-        env.init(hkey, htag, MMC_HEAP);
+        env.init(hkey, htag, heap_cap);
         attach_trace(env, sink);
         wait_list waiters;  // the semaphore's event
-        waiters.init(wwho, wlat, MMC_WAITERS);
+        waiters.init(wwho, wlat, waiter_cap);
         uint64_t value = prm.servers;  // semaphore{c, c}
         uint64_t i = 0, served = 0, balked = 0;
         uint32_t main_pc = 0, source_pc = 0;
@@ -612,6 +649,8 @@ mmc_fast_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64
     }
 }
 
+size_t mmc_deep_smem_bytes() { return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64; }
+
 size_t mmc_smem_bytes() {
     return sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS) + 64 +
            (size_t)MMC_THREADS * (MMC_HEAP * (8 + 4) + MMC_WAITERS * (4 + 4));
@@ -673,7 +712,7 @@ size_t mmc_saved_words(const cxxdes_b200_mmc_params &prm) {
 
 cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
                        uint64_t *customer_state, int sm_count, unsigned long long *list_cursor, cudaStream_t stream,
-                       int *launches, const mmc_saved &st, bool wide_tokens) {
+                       int *launches, const mmc_saved &st, bool wide_tokens, const mmc_deep &deep) {
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel<environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -683,13 +722,42 @@ cudaError_t launch_mmc(const cxxdes_b200_mmc_params &prm, const shard &sh, const
         ++*launches;
         if (e != cudaSuccess) return e;
         mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, sh.retry_list, sh.retry_count,
-                                                                        list_cursor, trace_sink{});
+                                                                        list_cursor, trace_sink{}, mmc_deep{});
         ++*launches;
-        return cudaGetLastError();
+    } else {
+        mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr,
+                                                                        trace_sink{}, mmc_deep{});
+        ++*launches;
     }
-    mmc_kernel<environment><<<sm_count, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr, trace_sink{});
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !deep.base) return e;
+    // what outgrew the 96-entry heap / wait list: once more with both in global memory (exits at once when nothing did)
+    e = cudaFuncSetAttribute(mmc_kernel<environment, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mmc_deep_smem_bytes());
+    if (e != cudaSuccess) return e;
+    const int deep_block = deep.threads < MMC_THREADS ? deep.threads : MMC_THREADS;
+    mmc_kernel<environment, true><<<deep.threads / deep_block, deep_block, mmc_deep_smem_bytes(), stream>>>(
+        prm, sh, out, customer_state, nullptr, sh.retry_a_count, sh.retry_a_cursor, trace_sink{}, deep);
     ++*launches;
     return cudaGetLastError();
+}
+
+// Worst case of one replication (n customers): a process is the target of at most one token it waits for, a customer
+// owns at most two handler tokens (its any_of's children) and one output token, so 6 n + 16 entries hold any heap the
+// model can build; at most one acquire_proc per customer waits.  Threads: as many as `budget` bytes hold, a whole
+// number of blocks, at most one 96-thread block per SM.  Returns the bytes to allocate (0: no deep pass).
+size_t mmc_deep_plan(const cxxdes_b200_mmc_params &prm, int sm_count, size_t budget, mmc_deep &d) {
+    d = mmc_deep{};
+    const size_t n = prm.n_customers ? prm.n_customers : 1;
+    const size_t heap_cap = 6 * n + 16, waiter_cap = n + 8;
+    const size_t per_thread = heap_cap * (8 + 4) + waiter_cap * (4 + 4);
+    size_t threads = budget / per_thread;
+    if (threads == 0) return 0;
+    if (threads > (size_t)sm_count * MMC_THREADS) threads = (size_t)sm_count * MMC_THREADS;
+    if (threads > (size_t)MMC_THREADS) threads -= threads % MMC_THREADS;
+    d.threads = (int)threads;
+    d.heap_cap = (int)heap_cap;
+    d.waiter_cap = (int)waiter_cap;
+    return threads * per_thread;
 }
 
 // One replication (sh.n_replications == 1) on the full-size kernel, with its event trace.  `customer_state` needs
@@ -699,7 +767,8 @@ cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh,
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel<traced_environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mmc_kernel<traced_environment><<<1, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr, sink);
+    mmc_kernel<traced_environment><<<1, MMC_THREADS, smem, stream>>>(prm, sh, out, customer_state, nullptr, nullptr, nullptr, sink,
+                                                                    mmc_deep{});
     return cudaGetLastError();
 }
 

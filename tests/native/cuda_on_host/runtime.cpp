@@ -71,6 +71,9 @@ struct scheduler {
 #endif
     bool progressed = false;
     const char *kernel = "";
+    int order = 0;                // 0 lane 0 first, 1 last lane first, 2 pseudo-random permutation per pass
+    unsigned long long rng = 1;
+    unsigned rotate = 0;
 };
 
 scheduler S;
@@ -247,6 +250,10 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
         if (p == MAP_FAILED) { perror("cuda_on_host: mmap"); abort(); }
         S.stacks.push_back((unsigned char *)p);
     }
+    if (const char *order = getenv("CUDA_ON_HOST_ORDER")) {
+        S.order = !strcmp(order, "reverse") ? 1 : !strncmp(order, "random", 6) ? 2 : 0;
+        if (S.order == 2 && S.rng == 1 && order[6] == ':') S.rng = strtoull(order + 7, nullptr, 10) | 1;
+    }
     S.entry = thread_entry;
     S.closure = closure;
     S.kernel = what;
@@ -294,7 +301,21 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
                 bool moved = true;
                 while (moved) {
                     moved = false;
-                    for (unsigned t = first; t < last; ++t) {
+                    for (unsigned k = first; k < last; ++k) {
+                        // the order in which the lanes of a warp run between two rendez-vous is not defined on the device
+                        // (independent thread scheduling): CUDA_ON_HOST_ORDER=reverse / random shakes out code that
+                        // reads what another lane wrote without a __syncwarp in between
+                        unsigned t = k;
+                        if (S.order == 1) t = first + (last - 1 - k);
+                        else if (S.order == 2) {
+                            if (k == first) {
+                                S.rng = S.rng * 6364136223846793005ULL + 1442695040888963407ULL;
+                                S.rotate = (unsigned)(S.rng >> 33);
+                            }
+                            const unsigned width = last - first;
+                            t = first + ((k - first) * ((S.rotate % 16) * 2 + 1) + (S.rotate >> 8)) % width;   // odd stride: a permutation when width is a power of two
+                            if (width & (width - 1)) t = first + (k - first + (S.rotate >> 8)) % width;
+                        }
                         fibre &f = S.fibres[t];
                         if (f.done || f.polling) continue;
                         if (f.wait_word && *f.wait_word == f.wait_value) continue;   // still blocked

@@ -79,10 +79,13 @@ def emulated_library(built):
     return cuda_on_host.build()
 
 
-@pytest.fixture(scope="module")
-def emulated_run(emulated_library):
+# The order in which the lanes of a warp run between two rendez-vous is undefined on the device (independent thread
+# scheduling).  The emulation runs them lane 0 first, and once more in a pseudo-random permutation per pass: code that
+# reads what another lane wrote without a __syncwarp in between gives different results in the two.
+@pytest.fixture(scope="module", params=["lane 0 first", "random:20261020"])
+def emulated_run(emulated_library, request):
     """ONE child pytest over all GPU test files (interpreter and torch start-up paid once per worker), outcome per test."""
-    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS="2")
+    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS="2", CUDA_ON_HOST_ORDER=request.param)
     cmd = [sys.executable, "-m", "pytest", *[f"tests/{f}" for f in sorted(GPU_TEST_FILES)], "-m", "gpu", "-q", "-rA",
            "-p", "no:cacheprovider", "-n", str(min(6, os.cpu_count() or 1)), "--timeout", "600"]
     for test_file, names in DESELECT.items():

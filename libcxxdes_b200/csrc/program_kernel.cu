@@ -22,7 +22,7 @@ constexpr int PRG_THREADS = 128;
 constexpr int PRG_HEAP = 80;
 constexpr int PRG_MAX_PROCS = 72;   // examples/aloha.cpp as a program: co_main + 64 stations
 constexpr int PRG_MAX_NODES = 8;  // compositions in one co_await (the outer one and those nested in it)
-constexpr int PRG_HANDLERS = 8;   // live any_of/all_of handlers per replication (pool, by serial)
+constexpr int PRG_HANDLERS = 24;  // live any_of/all_of handlers per replication (pool, by serial); the shared-memory first pass holds 8
 constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind
 constexpr int PRG_WAITERS = 16;
 constexpr int PRG_QUEUE_CAP = 128;

@@ -131,8 +131,10 @@ int set_device(const cxxdes_b200_ensemble *e) {
 // Global memory the last, unbounded pass of a model may use for its heaps and wait lists (CXXDES_B200_DEEP_BYTES, read at
 // create; 0 switches the pass off and a replication that outgrows the on-chip capacities keeps its status flag).
 size_t deep_pass_budget() {
-    if (const char *text = getenv("CXXDES_B200_DEEP_BYTES")) return (size_t)strtoull(text, nullptr, 10);
-    return (size_t)256 << 20;
+    size_t budget = (size_t)256 << 20;
+    if (const char *text = getenv("CXXDES_B200_DEEP_BYTES")) budget = (size_t)strtoull(text, nullptr, 10);
+    const size_t most = (size_t)8 << 30;   // entries are indexed [entry * threads] in 32 bits: 8 GiB / 12 bytes stays below 2^31
+    return budget < most ? budget : most;
 }
 
 int allocate(cxxdes_b200_ensemble *e) {

@@ -176,14 +176,17 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Build (or reuse) the emulated library; returns its path."""
-    OUT_DIR.mkdir(parents=True, exist_ok=True)
-    stamp = OUT_DIR / "digest.txt"
+def build(force=False, verbose=False, asan=False):
+    """Build (or reuse) the emulated library; returns its path.  asan: with -fsanitize=address, as a memory checker of
+    the kernels (load it with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)."""
+    out_dir = OUT_DIR.parent / "cuda_on_host_asan" if asan else OUT_DIR
+    out = out_dir / OUT.name
+    out_dir.mkdir(parents=True, exist_ok=True)
+    stamp = out_dir / "digest.txt"
     digest = _digest()
-    if not force and OUT.exists() and stamp.exists() and stamp.read_text() == digest:
-        return OUT
-    src_dir = OUT_DIR / "src"
+    if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
+        return out
+    src_dir = out_dir / "src"
     (src_dir / "device").mkdir(parents=True, exist_ok=True)
     units = []
     for p in _sources():
@@ -196,9 +199,11 @@ def build(force=False, verbose=False):
     flags = ["-std=c++17", "-O1", "-g1", "-fPIC", "-ffp-contract=off", "-mfma", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
              "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-sign-compare", "-Wno-unused-local-typedefs",
              f"-I{HERE}", f"-I{ROOT / 'include'}", f"-I{src_dir}", "-include", "cuda_runtime.h"]
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
 
     def compile_one(unit):
-        obj = OUT_DIR / (unit.stem + ".o")
+        obj = out_dir / (unit.stem + ".o")
         r = subprocess.run(["g++", *flags, "-c", str(unit), "-o", str(obj)], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"cuda_on_host: g++ failed on {unit.name}:\n{r.stderr[-6000:]}")
@@ -208,10 +213,10 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as pool:
         objs = list(pool.map(compile_one, units))
-    subprocess.run(["g++", "-shared", "-o", str(OUT), *map(str, objs), "-ldl"], check=True)
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", str(out), *map(str, objs), "-ldl"], check=True)
     stamp.write_text(digest)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, asan="--asan" in sys.argv))

@@ -5,7 +5,7 @@
 // and run their kernels on the CPU, one block after another, every CUDA thread of a block as a fibre:
 //   * __syncthreads / __syncwarp / votes / shuffles are real rendez-vous points between the fibres of a block / warp
 //     (a lane that reaches one waits until every lane named in the mask has arrived -- lanes run in any order in between);
-//   * shared memory is a per-block arena, "32-bit shared addresses" are offsets from an anchor inside this library;
+//   * shared memory is a per-block arena, "32-bit shared addresses" are offsets from an origin just below it;
 //   * device memory is host memory (poisoned, not zeroed, as on the device), streams run in host order.
 // What this buys: the `-m gpu` parity tests' LOGIC -- the kernels' state machines, heaps, hand-overs, saved state --
 // can be run against the oracle where no GPU exists (tests/test_kernels_on_host.py).  What it does not show: timing,
@@ -104,10 +104,10 @@ struct block_ctx {
     unsigned char *dynamic_shared;
 };
 extern thread_ctx *current;          // one OS thread runs every fibre: a plain global
-extern unsigned char shared_anchor;  // 32-bit "shared addresses" are offsets from 2 GiB below this byte
+extern uintptr_t shared_origin;      // 32-bit "shared addresses" are offsets from here (4 KiB below the running block's arena)
 
 inline unsigned char *dynamic_shared() { return current->block->dynamic_shared; }
-inline uintptr_t shared_base() { return (uintptr_t)&shared_anchor - (uintptr_t)0x80000000u; }
+inline uintptr_t shared_base() { return shared_origin; }
 template <class T> inline T *shared_pointer(uint32_t addr) { return (T *)(shared_base() + addr); }
 
 // rendez-vous of the lanes named in `mask` (runtime.cpp); `op` names the call for the divergence check.  Returns the 32

@@ -17,15 +17,25 @@
 #include <ucontext.h>
 #endif
 
+// Built with -fsanitize=address (build.py --asan) the emulation doubles as a memory checker of the kernels: device
+// buffers are heap blocks of exactly the size asked for and a block's dynamic shared memory is one too, so an access
+// past either end is reported with the kernel's source line.  ASan has to be told about the stack switches.
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define CUDA_HOST_ASAN 1
+#else
+#define CUDA_HOST_ASAN 0
+#endif
+
 namespace cuda_host {
 
 thread_ctx *current = nullptr;
-unsigned char shared_anchor = 0;
+uintptr_t shared_origin = 0;
 
 namespace {
 
 constexpr size_t STACK_BYTES = 1u << 20;          // per fibre, mapped lazily
-constexpr size_t SHARED_ARENA_BYTES = 232448;     // 227 KiB: what one block may opt in to on sm_100
+constexpr size_t SHARED_LIMIT_BYTES = 232448;     // 227 KiB: what one block may opt in to on sm_100
 
 struct rendezvous {          // one per (warp, mask) in flight
     unsigned mask = 0;
@@ -54,6 +64,7 @@ struct fibre {
     unsigned wait_value = 0;
     const char *wait_what = "";
     bool polling = false;                  // called __nanosleep: resumed in the next round
+    void *asan_fake_stack = nullptr;
 };
 
 struct scheduler {
@@ -77,7 +88,9 @@ struct scheduler {
 };
 
 scheduler S;
-alignas(16) unsigned char shared_arena[SHARED_ARENA_BYTES];
+const void *asan_main_bottom = nullptr;
+size_t asan_main_size = 0;
+void *asan_main_fake_stack = nullptr;
 
 #if defined(__x86_64__)
 extern "C" void cuda_host_switch(void **save_sp, void *load_sp);
@@ -107,10 +120,16 @@ cuda_host_switch:
 
 void to_scheduler() {
     fibre *f = S.running;
+#if CUDA_HOST_ASAN
+    __sanitizer_start_switch_fiber(f->done ? nullptr : &f->asan_fake_stack, asan_main_bottom, asan_main_size);
+#endif
 #if defined(__x86_64__)
     cuda_host_switch(&f->sp, S.main_sp);
 #else
     swapcontext(&f->uc, &S.main_uc);
+#endif
+#if CUDA_HOST_ASAN
+    __sanitizer_finish_switch_fiber(f->asan_fake_stack, &asan_main_bottom, &asan_main_size);
 #endif
 }
 
@@ -118,6 +137,9 @@ void lane_exited(fibre *f);
 
 void fibre_main() {
     fibre *f = S.running;
+#if CUDA_HOST_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &asan_main_bottom, &asan_main_size);
+#endif
     S.entry(S.closure);
     f->done = true;
     lane_exited(f);
@@ -240,7 +262,7 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
         abort();
     }
     const unsigned n_threads = cfg.block.x * cfg.block.y * cfg.block.z;
-    if (cfg.shared_bytes > SHARED_ARENA_BYTES || n_threads == 0 || n_threads > 1024 || cfg.block.y != 1 || cfg.block.z != 1 ||
+    if (cfg.shared_bytes > SHARED_LIMIT_BYTES || n_threads == 0 || n_threads > 1024 || cfg.block.y != 1 || cfg.block.z != 1 ||
         cfg.grid.y != 1 || cfg.grid.z != 1) {
         fprintf(stderr, "cuda_on_host: %s: unsupported launch (%u x %u threads, %zu bytes of shared memory)\n", what, cfg.grid.x, n_threads, cfg.shared_bytes);
         abort();
@@ -257,6 +279,12 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
     S.entry = thread_entry;
     S.closure = closure;
     S.kernel = what;
+    // the block's dynamic shared memory: exactly the bytes the launch asked for (an access past them is a heap overflow
+    // to ASan); "32-bit shared addresses" are offsets from 4 KiB below it, so that address 0 is never valid
+    void *arena = nullptr;
+    if (posix_memalign(&arena, 128, cfg.shared_bytes ? cfg.shared_bytes : 1)) { perror("cuda_on_host: shared memory"); abort(); }
+    unsigned char *shared_arena = (unsigned char *)arena;
+    shared_origin = (uintptr_t)arena - 4096;
     for (unsigned b = 0; b < cfg.grid.x; ++b) {
         memset(shared_arena, 0xA5, cfg.shared_bytes);   // shared memory starts out undefined
         S.block.idx = uint3{b, 0, 0};
@@ -322,10 +350,16 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
                         S.running = &f;
                         current = &f.ctx;
                         moved = true;
+#if CUDA_HOST_ASAN
+                        __sanitizer_start_switch_fiber(&asan_main_fake_stack, f.stack, STACK_BYTES);
+#endif
 #if defined(__x86_64__)
                         cuda_host_switch(&S.main_sp, f.sp);
 #else
                         swapcontext(&S.main_uc, &f.uc);
+#endif
+#if CUDA_HOST_ASAN
+                        __sanitizer_finish_switch_fiber(asan_main_fake_stack, nullptr, nullptr);
 #endif
                     }
                     if (moved) S.progressed = true;
@@ -337,6 +371,8 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
         S.running = nullptr;
         current = nullptr;
     }
+    free(arena);
+    shared_origin = 0;
 }
 
 }  // namespace cuda_host
@@ -368,7 +404,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
 }
 cudaError_t cudaMalloc(void **p, size_t bytes) {
     void *q = nullptr;
-    if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
+    if (posix_memalign(&q, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;   // exactly `bytes`: ASan sees the end
     memset(q, 0xCD, bytes);   // device memory is not zeroed
     *p = q;
     return cudaSuccess;

@@ -11,6 +11,7 @@
 #include <sys/mman.h>
 
 #include <chrono>
+#include <deque>
 #include <vector>
 
 #if !defined(__x86_64__)
@@ -21,6 +22,7 @@
 // buffers are heap blocks of exactly the size asked for and a block's dynamic shared memory is one too, so an access
 // past either end is reported with the kernel's source line.  ASan has to be told about the stack switches.
 #if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
 #include <sanitizer/common_interface_defs.h>
 #define CUDA_HOST_ASAN 1
 #else
@@ -48,7 +50,7 @@ struct rendezvous {          // one per (warp, mask) in flight
 
 struct warp_state {
     unsigned alive = 0;      // lanes that have not returned from the kernel
-    std::vector<rendezvous> meets;
+    std::deque<rendezvous> meets;   // one per mask in use; a deque: lanes wait on &generation while others add masks
 };
 
 struct fibre {
@@ -211,7 +213,6 @@ const uint64_t *warp_gather(unsigned mask, uint64_t value, int op) {
         m = &w.meets.back();
         m->mask = mask;
     }
-    const size_t index = (size_t)(m - w.meets.data());   // (the vector may grow while this lane waits)
     if (m->arrived == 0) m->op = op;
     else if (m->op != op) {
         fprintf(stderr, "cuda_on_host: %s: lanes of mask %08x meet in different primitives (%d and %d)\n", S.kernel, mask, m->op, op);
@@ -221,17 +222,8 @@ const uint64_t *warp_gather(unsigned mask, uint64_t value, int op) {
     m->arrived |= 1u << f->lane;
     const unsigned generation = m->generation;
     if ((m->arrived & w.alive) == (mask & w.alive)) complete(*m);
-    else {
-        // &w.meets[index].generation may move when another lane adds a rendez-vous: wait on a copy of the index
-        while (S.warps[f->warp].meets[index].generation == generation) {
-            f->wait_word = &S.warps[f->warp].meets[index].generation;
-            f->wait_value = generation;
-            f->wait_what = op == OP_SYNCWARP ? "__syncwarp" : op == OP_VOTE ? "vote" : "shuffle";
-            to_scheduler();
-        }
-        f->wait_word = nullptr;
-    }
-    return S.warps[f->warp].meets[index].out;
+    else wait_for(&m->generation, generation, op == OP_SYNCWARP ? "__syncwarp" : op == OP_VOTE ? "vote" : "shuffle");
+    return m->out;
 }
 
 void block_barrier() {
@@ -302,6 +294,9 @@ void run_grid(const launch_config &cfg, void (*thread_entry)(void *), void *clos
             f.warp = (int)(t / 32);
             f.lane = (int)(t % 32);
             f.stack = S.stacks[t];
+#if CUDA_HOST_ASAN
+            __asan_unpoison_memory_region(f.stack, STACK_BYTES);   // the frames of the fibre that ran here before never returned
+#endif
             S.warps[f.warp].alive |= 1u << f.lane;
 #if defined(__x86_64__)
             // what cuda_host_switch pops: six callee-saved registers, then `ret` into fibre_main with the stack as

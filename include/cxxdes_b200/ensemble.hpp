@@ -43,7 +43,19 @@ constexpr time operator""_ms(unsigned long long x) { return {(time_integral)x, t
 constexpr time operator""_us(unsigned long long x) { return {(time_integral)x, time_units::microseconds}; }
 constexpr time operator""_ns(unsigned long long x) { return {(time_integral)x, time_units::nanoseconds}; }
 constexpr time operator""_ps(unsigned long long x) { return {(time_integral)x, time_units::picoseconds}; }
+// `3_x`: three model units, mapped to ticks through the environment's time_unit() (misc/time.hpp:128-148,308-310)
+struct unitless_time {
+    time_integral t = 0;
+};
+constexpr unitless_time operator""_x(unsigned long long x) { return {(time_integral)x}; }
 }  // namespace time_ops
+
+// time::count (misc/time.hpp:75-86): this quantity in ticks of `precision`
+constexpr time_integral count(time x, time precision) {
+    constexpr time_integral conv[5] = {1, 1000, 1000000, 1000000000, 1000000000000LL};
+    if ((int)x.u < (int)precision.u) return conv[(int)precision.u - (int)x.u] * x.t / precision.t;
+    return (x.t / precision.t) / conv[(int)x.u - (int)precision.u];
+}
 
 // Model descriptors: the constructor arguments of the reference examples.
 namespace models {

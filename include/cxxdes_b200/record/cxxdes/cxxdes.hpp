@@ -24,8 +24,12 @@
 // are noted in that process; `_Co_with(x) { ... };` and `sequential(a, b, ...)` / the comma operator are, as in the
 // reference (co_with.ipp:27-35, sequential.ipp:1-20), coroutines of the library -- helper processes of the program.
 // So are `>>` and `flag_done`.  `co_await this_coroutine()` / `this_environment()` give views for a body's own use.
-// Not provided: time-expression literals (`10_x`), copyable coroutine handles, `lazy_timeout`, exceptions through
-// tokens, interrupts.  tests/test_record_examples.py: eleven of the reference's own examples, source files unchanged.
+// Not provided: arithmetic on time literals (`1_s + 3 * b`; single literals such as `10_x`, `5_ms` are), exceptions through
+// tokens, interrupts.  An `environment` may also be driven by hand, as examples/event.cpp and clocks.cpp do: env.bind(p)
+// makes p a root process, env.run() / run_until(t) / run_for(t) run ONE replication of what has been bound on the GPU
+// (simulation<>::run / run_for do the same).  Coroutine handles are copyable (the same process awaited from two others, or
+// again after it returned); a coroutine object that is never awaited or bound is a process nothing starts.
+// tests/test_record_examples.py: nineteen of the reference's own examples, source files unchanged.
 //
 // Process ordinals (names in the trace digest, Philox stream ids) are given in creation order: co_main is 0, every
 // coroutine object created after it 1, 2, ...  C++20, header-only, g++ >= 11.
@@ -138,6 +142,17 @@ inline context &ctx() {
     return *current_context();
 }
 
+// env.run() / run_until(t) / run_for(t) of an environment driven by hand (examples/event.cpp, clocks.cpp): what was asked
+// for, in order; the recorded model outlives a local `environment` through the shared context
+struct run_request {
+    std::shared_ptr<context> model;
+    std::int64_t until;            // < 0: run()
+};
+inline std::vector<run_request> &run_requests() {
+    static std::vector<run_request> *r = new std::vector<run_request>;   // (read by exit handlers: never destroyed)
+    return *r;
+}
+
 // ---- folding repeated runs of steps back into loops (at most two deep, like the interpreters) ----
 inline bool same_run(const std::vector<step> &v, std::size_t a, std::size_t c, std::size_t len) {
     for (std::size_t k = 0; k < len; ++k)
@@ -236,6 +251,54 @@ inline timeout_awaitable timeout(time_integral t, priority_type prio = priority_
 inline timeout_awaitable yield() { return {0}; }
 inline timeout_awaitable until(time_integral t, priority_type prio = priority_consts::inherit) { return {t, prio, true}; }
 inline timeout_awaitable instant(time_integral t, priority_type prio = priority_consts::inherit) { return {t, prio, true}; }
+// the same with a time literal (`5_ms`, `10_x`): environment::real_to_sim of a time-expression node (environment.ipp:73-76)
+// with the unit and precision of the environment being recorded -- single literals, not the expression DSL around them
+namespace detail {
+inline time_integral ticks_of(time x) { return ::cxxdes::b200::count(x, record::ctx().precision); }
+inline time_integral ticks_of(time_ops::unitless_time x) { return x.t * ::cxxdes::b200::count(record::ctx().unit, record::ctx().precision); }
+template <typename X>
+using time_literal = decltype(ticks_of(std::declval<X>()));
+}  // namespace detail
+template <typename X, typename = detail::time_literal<X>>
+timeout_awaitable delay(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio, false}; }
+template <typename X, typename = detail::time_literal<X>>
+timeout_awaitable timeout(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio, false}; }
+template <typename X, typename = detail::time_literal<X>>
+timeout_awaitable until(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio, true}; }
+template <typename X, typename = detail::time_literal<X>>
+timeout_awaitable instant(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio, true}; }
+
+// lazy_timeout(t) / lazy_delay(t) (timeout.ipp:104-177): `auto t = co_await lazy_timeout(x)` fixes the deadline now() + x
+// without an event, `co_await t` waits for it.  One pending deadline per process (the process register of the program).
+struct lazy_instant_awaitable {
+    priority_type prio;
+    noted<> cxxdes_record() const;
+};
+struct lazy_timeout_awaitable {
+    time_integral ticks;
+    priority_type prio;
+    noted<lazy_instant_awaitable> cxxdes_record() const;
+};
+inline lazy_timeout_awaitable lazy_timeout(time_integral t, priority_type prio = priority_consts::inherit) { return {t, prio}; }
+inline lazy_timeout_awaitable lazy_delay(time_integral t, priority_type prio = priority_consts::inherit) { return {t, prio}; }
+template <typename X, typename = detail::time_literal<X>>
+lazy_timeout_awaitable lazy_timeout(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio}; }
+template <typename X, typename = detail::time_literal<X>>
+lazy_timeout_awaitable lazy_delay(X x, priority_type prio = priority_consts::inherit) { return {detail::ticks_of(x), prio}; }
+inline noted<lazy_instant_awaitable> lazy_timeout_awaitable::cxxdes_record() const {
+    record::step s;
+    s.kind = record::step::SIMPLE;
+    s.op = {CXXDES_B200_OP_LAZY_TIMEOUT, 0, 0, ticks};
+    record::ctx().note(std::move(s));
+    return {lazy_instant_awaitable{prio}};
+}
+inline noted<> lazy_instant_awaitable::cxxdes_record() const {
+    record::step s;
+    s.kind = record::step::SIMPLE;
+    s.op = {CXXDES_B200_OP_UNTIL_REG, 0, ::cxxdes::b200::detail::prio32(prio), 0};
+    record::ctx().note(std::move(s));
+    return {};
+}
 
 struct env_timeout_awaitable {   // env.timeout(x)   (timeout.ipp:184-187)
     bool random;
@@ -260,9 +323,10 @@ struct coroutine_view {
     time_integral latency() const noexcept { return latency_; }
     const coroutine_view *operator->() const noexcept { return this; }
 };
-struct environment_view {
+struct environment_view {   // what `co_await this_environment()` hands back: env->now(), env->timeout(x)
     time_integral now() const noexcept { return 0; }
     real_type now_seconds() const noexcept { return 0.0; }
+    env_timeout_awaitable timeout(double seconds) const { return {false, seconds, 0}; }
     const environment_view *operator->() const noexcept { return this; }
 };
 
@@ -337,16 +401,18 @@ public:
         void return_value(V &&v) { result = std::forward<V>(v); }
     };
     coroutine() noexcept : h_(nullptr) {}            // (an empty handle, to be assigned a process later)
-    coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
-    coroutine(const coroutine &) = delete;
+    // a handle on the process, copyable as in the reference (coroutine.ipp:30-62: a counted reference to coroutine_data);
+    // the frame lives as long as one handle does
+    coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)), frame_(std::move(o.frame_)) {}
+    coroutine(const coroutine &) = default;
+    coroutine &operator=(const coroutine &) = default;
     coroutine &operator=(coroutine &&o) noexcept {
         if (this != &o) {
-            if (h_) h_.destroy();
             h_ = std::exchange(o.h_, nullptr);
+            frame_ = std::move(o.frame_);
         }
         return *this;
     }
-    ~coroutine() { if (h_) h_.destroy(); }
     std::uint32_t id() const { return h_.promise().id; }
     // coroutine.ipp:106-176
     coroutine &&priority(priority_type p) && { info().opt.priority = p; return std::move(*this); }
@@ -363,9 +429,13 @@ public:
         return h_.promise().result;
     }
 private:
-    explicit coroutine(std::coroutine_handle<promise_type> h) : h_(h) { record::ctx().procs[h.promise().id].handle = h; }
+    explicit coroutine(std::coroutine_handle<promise_type> h)
+        : h_(h), frame_(h.address(), [](void *a) { std::coroutine_handle<>::from_address(a).destroy(); }) {
+        record::ctx().procs[h.promise().id].handle = h;
+    }
     record::proc_info &info() { return record::ctx().procs[id()]; }
     std::coroutine_handle<promise_type> h_;
+    std::shared_ptr<void> frame_;
 };
 template <>
 class coroutine<void> {
@@ -375,16 +445,18 @@ public:
         void return_void() const noexcept {}
     };
     coroutine() noexcept : h_(nullptr) {}            // (an empty handle, to be assigned a process later)
-    coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
-    coroutine(const coroutine &) = delete;
+    // a handle on the process, copyable as in the reference (coroutine.ipp:30-62: a counted reference to coroutine_data);
+    // the frame lives as long as one handle does
+    coroutine(coroutine &&o) noexcept : h_(std::exchange(o.h_, nullptr)), frame_(std::move(o.frame_)) {}
+    coroutine(const coroutine &) = default;
+    coroutine &operator=(const coroutine &) = default;
     coroutine &operator=(coroutine &&o) noexcept {
         if (this != &o) {
-            if (h_) h_.destroy();
             h_ = std::exchange(o.h_, nullptr);
+            frame_ = std::move(o.frame_);
         }
         return *this;
     }
-    ~coroutine() { if (h_) h_.destroy(); }
     std::uint32_t id() const { return h_.promise().id; }
     coroutine &&priority(priority_type p) && { info().opt.priority = p; return std::move(*this); }
     coroutine &&latency(time_integral t) && { info().opt.latency = t; return std::move(*this); }
@@ -396,9 +468,13 @@ public:
     coroutine &return_priority(priority_type p) & { info().opt.return_priority = p; return *this; }
     void run_now() { record::ctx().run_body(id()); }
 private:
-    explicit coroutine(std::coroutine_handle<promise_type> h) : h_(h) { record::ctx().procs[h.promise().id].handle = h; }
+    explicit coroutine(std::coroutine_handle<promise_type> h)
+        : h_(h), frame_(h.address(), [](void *a) { std::coroutine_handle<>::from_address(a).destroy(); }) {
+        record::ctx().procs[h.promise().id].handle = h;
+    }
     record::proc_info &info() { return record::ctx().procs[id()]; }
     std::coroutine_handle<promise_type> h_;
+    std::shared_ptr<void> frame_;
 };
 
 // ---- subroutine<T> (subroutine.ipp): a coroutine frame on the call stack of the process that awaits it -- no start
@@ -629,10 +705,17 @@ public:
     }
     record::context &recording() { return *c_; }
 
+    // environment::run / run_until / run_for (environment.ipp:179-214) of an environment driven by hand: ONE replication
+    // of what has been bound so far, on the GPU (the clock an ensemble handle keeps between calls is kept here as the
+    // horizon reached).  -DCXXDES_B200_RECORD_ONLY: only note the request (record::run_requests(); tests without a device).
+    void run() { request(-1); }
+    void run_until(time_integral t) { request(t > horizon_ ? t : horizon_); }
+    void run_for(time_integral t) { request((horizon_ < 0 ? 0 : horizon_) + t); }
+
     // the recorded model as a process program
-    ::cxxdes::b200::program program() const {
+    ::cxxdes::b200::program program() const { return program_of(*c_); }
+    static ::cxxdes::b200::program program_of(const record::context &c) {
         namespace b = ::cxxdes::b200;
-        const record::context &c = *c_;
         b::program prog;
         for (std::uint64_t m : c.queue_max) prog.add_queue(m);
         for (std::size_t k = 0; k < c.sem_init.size(); ++k) prog.add_semaphore(c.sem_init[k], c.sem_max[k]);
@@ -644,7 +727,12 @@ public:
         for (double r : c.rates) prog.add_rate(r);      // (the recorded draws refer to them by index)
         for (std::size_t k = 0; k < c.procs.size(); ++k) {
             const record::proc_info &p = c.procs[k];
-            if (!p.started) throw std::runtime_error("cxxdes (recording): a coroutine object was created but never awaited or bound");
+            if (!p.started) {
+                // a coroutine object that was created but never awaited or bound never runs (examples/interrupt_test.cpp
+                // makes three and awaits one): a process without a body that nothing starts
+                prog.body_of(ps[k], [](b::body &) {});
+                continue;
+            }
             const std::vector<record::node> nodes = record::fold(p.steps, 0, p.steps.size(), 0, p.endless);
             prog.body_of(ps[k], [&](b::body &co) { record::emit(co, nodes); });
         }
@@ -652,7 +740,25 @@ public:
     }
 
 private:
+    void request(std::int64_t until) {
+        record::run_requests().push_back({c_, until});
+#if !defined(CXXDES_B200_RECORD_ONLY)
+        using ens_t = ::cxxdes::b200::ensemble<::cxxdes::b200::models::process_program>;
+        if (!ensemble_) {
+            ensemble_ = std::make_shared<ens_t>(::cxxdes::b200::models::process_program{program()}, 1, 0x5EED);
+            ensemble_->env.time_unit(c_->unit);
+            ensemble_->env.time_precision(c_->precision);
+        }
+        if (until < 0) ensemble_->run();
+        else ensemble_->run_until(until);
+#endif
+        if (until >= 0) horizon_ = until;
+    }
     std::shared_ptr<record::context> c_;
+    std::int64_t horizon_ = -1;
+#if !defined(CXXDES_B200_RECORD_ONLY)
+    std::shared_ptr<::cxxdes::b200::ensemble<::cxxdes::b200::models::process_program>> ensemble_;
+#endif
 };
 
 // ---- simulation<Derived> (core/simulation.hpp:31-85) ----------------------------------------------------------------
@@ -678,8 +784,8 @@ struct simulation {
     }
 
     // simulation<>::run / run_for (core/simulation.hpp:51-62): ONE replication of the recorded model on the GPU
-    void run() { ensemble(1)->run(); }
-    void run_for(::cxxdes::b200::time_integral t) { ensemble(1)->run_for(t); }
+    void run() { bind(); env.run(); }
+    void run_for(::cxxdes::b200::time_integral t) { bind(); env.run_for(t); }
 
 protected:
     void bind() {
@@ -694,6 +800,10 @@ private:
 };
 
 #define CXXDES_SIMULATION(name) struct name : cxxdes::core::simulation<name>
+
+namespace detail {
+struct under_helper {};
+}
 
 }  // namespace core
 
@@ -827,3 +937,10 @@ cxxdes::core::coroutine<void> operator+(A &a, F &&f) {
     co_await handle.release();
 }
 #define _Co_with(x) co_yield (x) + [&]() mutable -> cxxdes::core::subroutine<void>
+
+// _Coroutine(...) { body }: an anonymous coroutine<void> from a lambda body (under_coroutine.ipp:11-17)
+template <typename F>
+auto operator+(cxxdes::core::detail::under_helper, F f) {
+    return f();
+}
+#define _Coroutine(...) cxxdes::core::detail::under_helper{} + [&](__VA_ARGS__) -> coroutine<void>

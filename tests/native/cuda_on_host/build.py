@@ -200,7 +200,7 @@ def build(force=False, verbose=False, asan=False):
              "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-Wno-sign-compare", "-Wno-unused-local-typedefs",
              f"-I{HERE}", f"-I{ROOT / 'include'}", f"-I{src_dir}", "-include", "cuda_runtime.h"]
     if asan:
-        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        flags += ["-fsanitize=address,undefined", "-fno-sanitize=vptr", "-fno-omit-frame-pointer"]   # memory errors and undefined behaviour (shifts, signed overflow, alignment)
 
     def compile_one(unit):
         obj = out_dir / (unit.stem + ".o")
@@ -213,7 +213,7 @@ def build(force=False, verbose=False, asan=False):
 
     with ThreadPoolExecutor(max_workers=8) as pool:
         objs = list(pool.map(compile_one, units))
-    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", str(out), *map(str, objs), "-ldl"], check=True)
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if asan else []), "-o", str(out), *map(str, objs), "-ldl"], check=True)
     stamp.write_text(digest)
     return out
 

@@ -5,8 +5,9 @@
 # are sized for the device; this script runs everything (about a quarter of an hour on 8 cores; expect the tests that
 # need two kernels at once or link the CUDA build to fail: see DESELECT in tests/test_kernels_on_host.py).
 #   tools/gpu_suite_on_host.sh [--asan] [pytest arguments, e.g. tests/test_models_gpu.py -k aloha]
-# --asan: the emulated library built with -fsanitize=address -- a memory check of every kernel and of the C ABI's host
-# side (device buffers and shared memory are heap blocks of exactly the size asked for); 3-4 times slower.
+# --asan: the emulated library built with -fsanitize=address,undefined -- a memory and undefined-behaviour check of
+# every kernel and of the C ABI's host side (device buffers and shared memory are heap blocks of exactly the size asked
+# for); 3-4 times slower.  UBSAN_OPTIONS=halt_on_error=1 turns a report into a failed test.
 set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" > /dev/null     # (nvcc must not run under the ASan preload)

@@ -295,7 +295,9 @@ int cxxdes_b200_check_program(const cxxdes_b200_program *program);
 
 /* simulation::run() for every replication: bind co_main once, then
  * `while (step());` (core/simulation.hpp:51-54,76-81; environment.ipp:117-146,179-182).
- * Asynchronous on the handle's stream. */
+ * Asynchronous on the handle's stream.  On an ensemble that has already run to its end the reference's run()
+ * finds nothing to dispatch; this call computes the same results again (a benchmark loop calls it once per step)
+ * and leaves every replication's clock where the earlier run_until / run_for calls had put it. */
 int cxxdes_b200_run(cxxdes_b200_ensemble *e);
 
 /* environment::run_until(t) / run_for(dt) in ticks for every replication

@@ -785,7 +785,7 @@ int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t unt
             CUDA_TRY(launch_aloha_trace(e->params.aloha, sh, out, sink, e->stream));
             break;
         case CXXDES_B200_MODEL_MMC:
-            CUDA_TRY(launch_mmc_trace(e->params.mmc, sh, out, (uint64_t *)e->ring, sink, e->stream));
+            CUDA_TRY(launch_mmc_trace(e->params.mmc, sh, out, (uint64_t *)e->ring, sink, e->stream, e->mmc_deep_pass));
             break;
         case CXXDES_B200_MODEL_ARCHSIM:
             CUDA_TRY(launch_archsim_trace(e->params.arch, sh, out, sink, e->stream));

@@ -180,7 +180,7 @@ cudaError_t launch_mm1_trace(const cxxdes_b200_mm1_params &prm, const shard &sh,
 cudaError_t launch_aloha_trace(const cxxdes_b200_aloha_params &prm, const shard &sh, const device_columns &out,
                                const trace_sink &sink, cudaStream_t stream);
 cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
-                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream);
+                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream, const mmc_deep &deep);
 cudaError_t launch_archsim_trace(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
                                  const trace_sink &sink, cudaStream_t stream);
 cudaError_t launch_program_trace(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,

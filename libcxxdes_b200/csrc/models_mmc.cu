@@ -84,7 +84,9 @@ mmc_kernel(cxxdes_b200_mmc_params prm, shard sh, device_columns out, uint64_t *c
     uint64_t rep;
     [[maybe_unused]] unsigned long long chunk_next = 0, chunk_end = 0;
     for (;;) {
-        if constexpr (DEEP) {
+        if (DEEP && !list_cursor) {
+            if (!steal(sh, rep)) break;      // (the event trace of one replication, with the deep pass's storage)
+        } else if constexpr (DEEP) {
             // (list_cursor: this pass's own work counter, claimed 16 replications at a time; list_count: where it
             // counts what it took)
             if (chunk_next == chunk_end) {
@@ -763,7 +765,15 @@ size_t mmc_deep_plan(const cxxdes_b200_mmc_params &prm, int sm_count, size_t bud
 // One replication (sh.n_replications == 1) on the full-size kernel, with its event trace.  `customer_state` needs
 // room for one block of the kernel (the handle's buffer always has).
 cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh, const device_columns &out,
-                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream) {
+                             uint64_t *customer_state, const trace_sink &sink, cudaStream_t stream, const mmc_deep &deep) {
+    if (deep.base) {   // heap and wait list in global memory: any replication the ensemble's passes can run can be traced
+        cudaError_t e = cudaFuncSetAttribute(mmc_kernel<traced_environment, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)mmc_deep_smem_bytes());
+        if (e != cudaSuccess) return e;
+        mmc_kernel<traced_environment, true><<<1, deep.threads < MMC_THREADS ? deep.threads : MMC_THREADS, mmc_deep_smem_bytes(), stream>>>(
+            prm, sh, out, customer_state, nullptr, nullptr, nullptr, sink, deep);
+        return cudaGetLastError();
+    }
     const size_t smem = mmc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(mmc_kernel<traced_environment>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

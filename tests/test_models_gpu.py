@@ -301,6 +301,12 @@ def test_mmc_overloaded_systems_take_the_unbounded_pass(port, fields, n_reps, fl
     assert counts["second_pass"] >= at_least
     golden_util.assert_columns_equal(got, want, what=f"overloaded mmc {fields}")
     assert acc.n_errors == 0 and acc.n_events == int(want.n_events.sum())
+    # the event trace of such a replication (the tracing kernel uses the same global-memory storage)
+    r = int(np.argmax(want.n_events))
+    total, digest, events = ens.trace(r, max_events=64)
+    want_total, want_events = port.trace(model, p, clock_of(g), 0xD33B, 5 + r, max_events=64)
+    assert total == want_total == int(want.n_events[r]) and digest == int(want.trace_hash[r])
+    assert [tuple(e) for e in events] == [tuple(e) for e in want_events]
     # in pieces: the replications are replayed from tick 0 to every horizon, as the 64-bit pass does
     ens.reset()
     horizon = int(want.end_time.max()) // 2

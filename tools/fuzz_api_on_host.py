@@ -136,6 +136,17 @@ def one_case(case):
                 assert np.array_equal(got.i64[k][ok], want.i64[k][ok]), f"i64[{k}]"
             acc, _ = ens.reduce()
             assert acc.n_events == int(got.n_events.sum()), "reduce n_events"
+            if rng.random() < 0.4:
+                # the event trace of one replication up to where the handle stands (it must not disturb the handle)
+                r = int(rng.integers(n))
+                until = -1 if exhausted else horizon
+                total, digest, events = ens.trace(r, max_events=256, until=until)
+                want_total, want_events = port.trace(model, params, oclock, seed, first + r, max_events=256, until=until)
+                log.append(f"trace({r})")
+                if ok[r]:
+                    assert total == want_total == int(want.n_events[r]), "trace: n_events"
+                    assert [tuple(e) for e in events] == [tuple(e) for e in want_events], "trace: events"
+                    assert digest == int(want.trace_hash[r]), "trace: digest"
         return case, kind, None
     except BaseException as e:      # noqa: BLE001
         return case, kind, " ; ".join(log) + " -> " + "".join(traceback.format_exception_only(type(e), e)).strip()[:400]

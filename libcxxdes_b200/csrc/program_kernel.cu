@@ -629,8 +629,23 @@ const char *program_check(const cxxdes_b200_program &p) {
     }
     for (uint32_t r = 0; r < p.n_roots; ++r)
         if (p.roots[r] >= p.n_procs) return "program: root out of range";
+    // a time the 64-bit keys cannot hold (47 bits) can never be scheduled: refused here, so that `now + t` never
+    // overflows either (found by tools/fuzz_program_check_on_host.py under UBSan)
+    constexpr int64_t TIME_LIMIT = 1LL << 47;
+    for (uint32_t i = 0; i < p.n_procs; ++i)
+        if (p.procs[i].latency <= -TIME_LIMIT || p.procs[i].latency >= TIME_LIMIT || p.procs[i].return_latency <= -TIME_LIMIT ||
+            p.procs[i].return_latency >= TIME_LIMIT)
+            return "program: latencies must be below 2^47 ticks";
     for (uint32_t i = 0; i < p.n_ops; ++i) {
         const cxxdes_b200_op &op = p.ops[i];
+        switch (op.code) {
+            case CXXDES_B200_OP_DELAY: case CXXDES_B200_OP_UNTIL: case CXXDES_B200_OP_CHILD_DELAY: case CXXDES_B200_OP_CHILD_UNTIL:
+            case CXXDES_B200_OP_LAZY_TIMEOUT: case CXXDES_B200_OP_ALL_OF: case CXXDES_B200_OP_ANY_OF: case CXXDES_B200_OP_CHILD_ALL_OF:
+            case CXXDES_B200_OP_CHILD_ANY_OF: case CXXDES_B200_OP_EV_WAIT: case CXXDES_B200_OP_CHILD_EV_WAIT:
+                if (op.imm <= -TIME_LIMIT || op.imm >= TIME_LIMIT) return "program: times and latencies must be below 2^47 ticks";
+                break;
+            default: break;
+        }
         switch (op.code) {
             case CXXDES_B200_OP_FRESH: case CXXDES_B200_OP_AWAIT: case CXXDES_B200_OP_ASYNC:
             case CXXDES_B200_OP_CHILD_PROC:

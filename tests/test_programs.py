@@ -463,6 +463,9 @@ def test_check_program_without_a_gpu(cuda_lib):
         "[0, 2^32)": [(LOOP, 0, 3, -1), D, (END, 0, 1, 0), (R, 0, 0, 0)],
         "stay inside its loop": [(LOOP, 0, 4, 3), (JUMP, 0, 4, 0), D, (END, 0, 1, 0), D, (R, 0, 0, 0)],            # out of the body
         "inside its loop body": [(JUMP, 0, 2, 0), (LOOP, 0, 4, 3), D, (END, 0, 2, 0), (R, 0, 0, 0)],                # into the body
+        # a time the 47-bit keys cannot hold (and `now + t` must not overflow)
+        "below 2^47": [(DELAY, 0, abi.INHERIT32, 1 << 47), (R, 0, 0, 0)],
+        "2^47 ticks": [(ALL, 1, abi.INHERIT32, 0), (CH_DELAY, 0, abi.INHERIT32, (1 << 63) - 1), (R, 0, 0, 0)],
     }
     for ops in ok:
         assert cuda_lib.cxxdes_b200_check_program(ctypes.byref(_raw(ops))) == abi.OK, cuda_lib.cxxdes_b200_last_error()

@@ -134,8 +134,15 @@ def one_case(case):
                 assert np.array_equal(got.f64[k].view(np.uint64)[ok], want.f64[k].view(np.uint64)[ok]), f"f64[{k}]"
             for k in range(abi.N_I64):
                 assert np.array_equal(got.i64[k][ok], want.i64[k][ok]), f"i64[{k}]"
-            acc, _ = ens.reduce()
-            assert acc.n_events == int(got.n_events.sum()), "reduce n_events"
+            acc, _ = ens.reduce()      # the on-device reduction against the fetched columns (flagged rows included, as it counts them)
+            assert acc.n_replications == n and acc.n_events == int(got.n_events.sum()), "reduce n_events"
+            assert acc.n_errors == int(bad.sum()), "reduce n_errors"
+            assert acc.trace_hash_sum == int(got.trace_hash.sum(dtype=np.uint64)), "reduce trace_hash_sum"
+            assert acc.end_time_sum == int(got.end_time.sum()), "reduce end_time_sum"
+            for k in range(abi.N_I64):
+                assert acc.i64_sum[k] == int(got.i64[k].sum()), f"reduce i64_sum[{k}]"
+            for k in range(abi.N_F64):
+                assert abs(acc.f64_sum[k] - float(got.f64[k].sum())) <= 1e-9 * max(1.0, abs(float(got.f64[k].sum()))), f"reduce f64_sum[{k}]"
             if rng.random() < 0.4:
                 # the event trace of one replication up to where the handle stands (it must not disturb the handle)
                 r = int(rng.integers(n))

@@ -214,6 +214,12 @@ def build(force=False, verbose=False, asan=False):
     with ThreadPoolExecutor(max_workers=8) as pool:
         objs = list(pool.map(compile_one, units))
     subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if asan else []), "-o", str(out), *map(str, objs), "-ldl"], check=True)
+    # C++ hosts link `-lcxxdes_b200`: with LD_LIBRARY_PATH=<out_dir>/lib they find the emulated library under that name
+    (out_dir / "lib").mkdir(exist_ok=True)
+    alias = out_dir / "lib" / "libcxxdes_b200.so"
+    if alias.is_symlink() or alias.exists():
+        alias.unlink()
+    alias.symlink_to(Path("..") / out.name)
     stamp.write_text(digest)
     return out
 

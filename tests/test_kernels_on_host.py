@@ -10,9 +10,12 @@ those are what the B200 run of the same tests is for.  What it does catch before
 heap, hand-over or saved-state bug in any kernel (all of them compile here: the three M/M/1 kernels, ALOHA on 8- and
 4-byte tokens and with cooperative heaps, M/M/c, the memory hierarchy, both interpreters, the reductions).
 
+The C++ hosts of examples/ (the host mirror ensemble.hpp, the program builder, the recording <cxxdes/cxxdes.hpp>) link
+`-lcxxdes_b200`; the child's LD_LIBRARY_PATH names a directory where that name is the emulated library, so the same
+binaries run here too.
+
 Left out (DESELECT): tests sized for the device (minutes here), tests whose point is concurrency between two kernels
-(streams run in host order here, so the M/M/1 helper never overlaps the first pass), and tests that link C++ examples
-against the CUDA build."""
+(streams run in host order here, so the M/M/1 helper never overlaps the first pass), and the multi-GPU NCCL example."""
 import os
 import re
 import subprocess
@@ -26,7 +29,7 @@ sys.path.insert(0, str(ROOT / "tests" / "native" / "cuda_on_host"))
 
 SIZED_FOR_THE_DEVICE = "sized for the device"
 NEEDS_CONCURRENT_KERNELS = "needs two kernels running at once"
-LINKS_THE_CUDA_BUILD = "links a C++ example against the CUDA build"
+NEEDS_GPUS_AND_NCCL = "one thread per GPU and an NCCL communicator"
 DESELECT = {
     "test_mm1_gpu.py": {
         "test_headline_config_full_size_against_the_oracle": SIZED_FOR_THE_DEVICE,
@@ -55,21 +58,14 @@ DESELECT = {
         "test_gpu_cooperative_aloha_matches_reference_golden[0]": SIZED_FOR_THE_DEVICE,
         "test_gpu_cooperative_aloha_equals_thread_per_replication_at_size": SIZED_FOR_THE_DEVICE,
     },
-    "test_host_cpp.py": {
-        "test_cpp_example_runs_on_gpu": LINKS_THE_CUDA_BUILD,
-        "test_cpp_aloha_sweep_example": LINKS_THE_CUDA_BUILD,
-        "test_cpp_multi_gpu_example_allreduces_over_nccl": LINKS_THE_CUDA_BUILD,
-        "test_cpp_program_example_matches_the_fused_kernel": LINKS_THE_CUDA_BUILD,
-        "test_cpp_loss_system_example_matches_theory": LINKS_THE_CUDA_BUILD,
-    },
-    "test_record.py": {"test_recorded_example_runs_on_gpu": LINKS_THE_CUDA_BUILD},
+    "test_host_cpp.py": {"test_cpp_multi_gpu_example_allreduces_over_nccl": NEEDS_GPUS_AND_NCCL},
 }
 # test file -> the fewest tests that must have passed there (a deselection typo or a collection error must not pass as
 # "nothing failed")
 GPU_TEST_FILES = {
     "test_mm1_gpu.py": 63, "test_mm1_fuzz.py": 40, "test_models_gpu.py": 48, "test_models_fuzz.py": 40,
     "test_narrow_tokens_gpu.py": 56, "test_programs.py": 34, "test_programs_fuzz.py": 120, "test_trace_gpu.py": 23,
-    "test_coop_heap.py": 9, "test_record.py": 7, "test_record_examples.py": 21,
+    "test_coop_heap.py": 9, "test_record.py": 8, "test_record_examples.py": 21, "test_host_cpp.py": 4,
 }
 
 
@@ -85,7 +81,8 @@ def emulated_library(built):
 @pytest.fixture(scope="module", params=["lane 0 first", "random:20261020"])
 def emulated_run(emulated_library, request):
     """ONE child pytest over all GPU test files (interpreter and torch start-up paid once per worker), outcome per test."""
-    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS="2", CUDA_ON_HOST_ORDER=request.param)
+    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS="2", CUDA_ON_HOST_ORDER=request.param,
+               LD_LIBRARY_PATH=str(Path(emulated_library).parent / "lib"))
     cmd = [sys.executable, "-m", "pytest", *[f"tests/{f}" for f in sorted(GPU_TEST_FILES)], "-m", "gpu", "-q", "-rA",
            "-p", "no:cacheprovider", "-n", str(min(6, os.cpu_count() or 1)), "--timeout", "600"]
     for test_file, names in DESELECT.items():
@@ -115,7 +112,7 @@ def test_every_gpu_test_file_is_listed():
     """A new -m gpu test file must be added above (or it silently never runs on the emulated device)."""
     with_gpu_tests = {p.name for p in (ROOT / "tests").glob("test_*.py")
                       if re.search(r"pytest\.mark\.gpu|pytestmark\s*=\s*pytest\.mark\.gpu", p.read_text()) and p.name != Path(__file__).name}
-    assert with_gpu_tests - {"test_host_cpp.py"} == set(GPU_TEST_FILES)
+    assert with_gpu_tests == set(GPU_TEST_FILES)
 
 
 def test_the_emulated_library_is_not_a_product_path(emulated_library):

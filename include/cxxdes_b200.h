@@ -343,7 +343,8 @@ int cxxdes_b200_launch_count(cxxdes_b200_ensemble *e, uint64_t *launches);
 /* Diagnostics of the most recent run / run_until / run_for launch: how many replications left the first-pass
  * kernel's compact representation and were redone (results are identical either way; this only tells where the
  * time went).  counts[0] = redone by the model's second pass (M/M/1: queue outgrew the shared-memory window ->
- * two-level ring; M/M/c: heap or wait list outgrew the on-chip 96 entries -> the last pass, both in global memory,
+ * two-level ring; M/M/c and process programs: heap, wait list or queue outgrew the fixed capacities of the
+ * kernels -> the last pass, all of them in global memory; for M/M/c
  * sized for the model's worst case, because the reference's containers are unbounded: std::priority_queue,
  * environment.ipp:263, std::vector of waiters, sync/event.hpp:87-139.  CXXDES_B200_DEEP_BYTES, read at create, bounds
  * the memory of that pass -- default 256 MiB, 0 = no such pass, the replication keeps its status flag),

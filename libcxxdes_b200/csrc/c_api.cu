@@ -117,6 +117,7 @@ struct cxxdes_b200_ensemble {
     // last pass of the models whose containers are unbounded in the reference: heap and wait lists in global memory,
     // sized for the model's worst case (M/M/c: models_mmc.cu mmc_deep_plan)
     mmc_deep mmc_deep_pass{};
+    program_deep prog_deep_pass{};
 
     // M/M/1: the second pass runs next to the first one on a stream of the handle's own (mm1_fused.cu)
     cudaStream_t helper_stream = nullptr;
@@ -171,6 +172,10 @@ int allocate(cxxdes_b200_ensemble *e) {
     if (e->cfg.model == CXXDES_B200_MODEL_MMC) {
         if (const size_t bytes = mmc_deep_plan(e->params.mmc, e->sm_count, deep_pass_budget(), e->mmc_deep_pass))
             CUDA_TRY(cudaMalloc(&e->mmc_deep_pass.base, bytes));
+    }
+    if (e->cfg.model == CXXDES_B200_MODEL_PROGRAM) {
+        if (const size_t bytes = program_deep_plan(e->dprog, e->sm_count, deep_pass_budget(), e->prog_deep_pass))
+            CUDA_TRY(cudaMalloc(&e->prog_deep_pass.base, bytes));
     }
     return CXXDES_B200_OK;
 }
@@ -407,7 +412,7 @@ int launch(cxxdes_b200_ensemble *e, int64_t until) {
             }
             wrote_saved = st.words != nullptr;
             CUDA_TRY(launch_program(e->dprog, e->program_blob_bytes, sh, e->cols, e->sm_count, e->counters + 2, e->stream,
-                                    &launches, e->prog_fast, e->prog_queue_items, st));
+                                    &launches, e->prog_fast, e->prog_queue_items, st, e->prog_deep_pass));
             break;
         }
         default:
@@ -791,7 +796,7 @@ int cxxdes_b200_trace(cxxdes_b200_ensemble *e, uint64_t replication, int64_t unt
             CUDA_TRY(launch_archsim_trace(e->params.arch, sh, out, sink, e->stream));
             break;
         case CXXDES_B200_MODEL_PROGRAM:
-            CUDA_TRY(launch_program_trace(e->dprog, e->program_blob_bytes, sh, out, sink, e->stream));
+            CUDA_TRY(launch_program_trace(e->dprog, e->program_blob_bytes, sh, out, sink, e->stream, e->prog_deep_pass));
             break;
         default:
             return fail(CXXDES_B200_ERR_INVALID, "unknown model");
@@ -951,6 +956,7 @@ int cxxdes_b200_destroy(cxxdes_b200_ensemble *e) {
     cudaFree(e->saved_words);
     cudaFree(e->saved_queue_items);
     cudaFree(e->mmc_deep_pass.base);
+    cudaFree(e->prog_deep_pass.base);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->helper_stream) { cudaStreamSynchronize(e->helper_stream); cudaStreamDestroy(e->helper_stream); }

@@ -164,9 +164,18 @@ cudaError_t launch_program_fast(const device_program &prg, const program_fast_la
                                 const device_columns &out, int64_t *queue_items, const program_fast_state &st,
                                 int sm_count, cudaStream_t stream);
 // blob_bytes: size of the contiguous device copy of the program that starts at prg.ops
+// The last pass of the interpreter: heap, wait lists and queue rings of a replication in global memory (a slab per
+// thread).  base == nullptr: no such pass.
+struct program_deep {
+    unsigned char *base;
+    int threads;                       // of the deep grid
+    int heap_cap, waiter_cap, queue_cap;
+    size_t bytes_per_thread;
+};
+size_t program_deep_plan(const device_program &prg, int sm_count, size_t budget_bytes, program_deep &d);   // bytes to allocate
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
                            int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
-                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state);
+                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state, const program_deep &deep);
 
 // ---- reduction of result columns to accumulators (reduce.cu) ----
 size_t reduce_scratch_bytes(int sm_count);
@@ -184,7 +193,7 @@ cudaError_t launch_mmc_trace(const cxxdes_b200_mmc_params &prm, const shard &sh,
 cudaError_t launch_archsim_trace(const cxxdes_b200_archsim_params &prm, const shard &sh, const device_columns &out,
                                  const trace_sink &sink, cudaStream_t stream);
 cudaError_t launch_program_trace(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
-                                 const trace_sink &sink, cudaStream_t stream);
+                                 const trace_sink &sink, cudaStream_t stream, const program_deep &deep);
 
 cudaError_t launch_clock_floor(int64_t *end_time, uint64_t n, int64_t floor, int sm_count, cudaStream_t stream);
 cudaError_t launch_clock_add(int64_t *end_time, uint64_t n, int64_t dt, int sm_count, cudaStream_t stream);

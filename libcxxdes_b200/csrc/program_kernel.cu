@@ -43,12 +43,23 @@ struct proc_rt {
     bool complete;
 };
 
+// DEEP (the last pass, below): the same lists and rings in global memory, with the capacities of program_deep.
+template <bool DEEP>
 struct waiters_rt {  // sync::event: FIFO of {latency, priority, process}  (event.hpp:87-139)
     uint32_t who[PRG_WAITERS];
     uint32_t hser[PRG_WAITERS];   // handler serial + 1 when the wait is a child of any_of / all_of, else 0
     int32_t lat[PRG_WAITERS];
     int16_t prio[PRG_WAITERS];
     int n;
+    __device__ __forceinline__ int capacity() const { return PRG_WAITERS; }
+};
+template <>
+struct waiters_rt<true> {
+    uint32_t *who, *hser;
+    int32_t *lat;
+    int16_t *prio;
+    int n, cap;
+    __device__ __forceinline__ int capacity() const { return cap; }
 };
 
 struct handler_rt {  // any_all_helper::custom_handler (any_of.ipp:3-27)
@@ -59,9 +70,17 @@ struct handler_rt {  // any_all_helper::custom_handler (any_of.ipp:3-27)
     bool is_all, armed;
 };
 
+template <bool DEEP>
 struct queue_rt {
     int64_t item[PRG_QUEUE_CAP];
     uint32_t head, count;
+    __device__ __forceinline__ uint32_t capacity() const { return PRG_QUEUE_CAP; }
+};
+template <>
+struct queue_rt<true> {
+    int64_t *item;
+    uint32_t head, count, cap;
+    __device__ __forceinline__ uint32_t capacity() const { return cap; }
 };
 
 __device__ __forceinline__ bool branch_taken(uint32_t cmp, int64_t v, int64_t imm) {
@@ -69,14 +88,15 @@ __device__ __forceinline__ bool branch_taken(uint32_t cmp, int64_t v, int64_t im
          : cmp == CXXDES_B200_CMP_LE ? v <= imm : cmp == CXXDES_B200_CMP_GT ? v > imm : v >= imm;
 }
 
+template <bool DEEP>
 struct interp {
     environment env;
     const device_program &prg;
     const shard &sh;
     const log_entry *table;
     proc_rt procs[PRG_MAX_PROCS];
-    waiters_rt q_wait[PRG_MAX_OBJ], s_wait[PRG_MAX_OBJ], m_wait[PRG_MAX_OBJ], e_wait[PRG_MAX_OBJ];
-    queue_rt queues[PRG_MAX_OBJ];
+    waiters_rt<DEEP> q_wait[PRG_MAX_OBJ], s_wait[PRG_MAX_OBJ], m_wait[PRG_MAX_OBJ], e_wait[PRG_MAX_OBJ];
+    queue_rt<DEEP> queues[PRG_MAX_OBJ];
     uint64_t sem_value[PRG_MAX_OBJ];
     bool mtx_owned[PRG_MAX_OBJ];
     handler_rt handlers[PRG_HANDLERS];
@@ -87,6 +107,32 @@ struct interp {
     uint32_t rate_base;   // parameter sweep: first rate of this replication's row
 
     __device__ interp(const device_program &p, const shard &s, const log_entry *t) : prg(p), sh(s), table(t) {}
+
+    // DEEP: wait lists and queue rings of this thread in its slab of global memory (program_deep_plan lays it out the
+    // same way): only the objects the program has get storage
+    __device__ void attach(unsigned char *g, const program_deep &d) {
+        if constexpr (DEEP) {
+            auto lists = [&](waiters_rt<true> *w, uint32_t count) {
+                for (uint32_t o = 0; o < (uint32_t)PRG_MAX_OBJ; ++o) {
+                    const size_t W = o < count ? (size_t)d.waiter_cap : 0;
+                    w[o].who = (uint32_t *)g;   g += 4 * W;
+                    w[o].hser = (uint32_t *)g;  g += 4 * W;
+                    w[o].lat = (int32_t *)g;    g += 4 * W;
+                    w[o].prio = (int16_t *)g;   g += 2 * W;
+                    w[o].cap = (int)W;
+                }
+            };
+            lists(q_wait, prg.n_queues);
+            lists(s_wait, prg.n_sems);
+            lists(m_wait, prg.n_mutexes);
+            lists(e_wait, prg.n_events);
+            for (uint32_t o = 0; o < (uint32_t)PRG_MAX_OBJ; ++o) {
+                queues[o].item = (int64_t *)g;
+                queues[o].cap = o < prg.n_queues ? (uint32_t)d.queue_cap : 0u;
+                g += 8 * (size_t)queues[o].cap;
+            }
+        }
+    }
 
     __device__ void fresh(uint32_t p) {
         proc_rt &r = procs[p];
@@ -129,8 +175,8 @@ struct interp {
         r.complete = true;
     }
 
-    __device__ void wait_on(waiters_rt &w, uint32_t p, int64_t latency, int64_t prio, uint32_t handler_serial_plus1 = 0) {
-        if (w.n >= PRG_WAITERS || prio < -32768 || prio > 32767 || latency < 0 || latency > INT32_MAX) {
+    __device__ void wait_on(waiters_rt<DEEP> &w, uint32_t p, int64_t latency, int64_t prio, uint32_t handler_serial_plus1 = 0) {
+        if (w.n >= w.capacity() || prio < -32768 || prio > 32767 || latency < 0 || latency > INT32_MAX) {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
         }
@@ -142,7 +188,7 @@ struct interp {
     }
 
     // wake_awaitable::await_ready, event.hpp:125-134
-    __device__ void wake(waiters_rt &w) {
+    __device__ void wake(waiters_rt<DEEP> &w) {
         for (int k = 0; k < w.n; ++k) env.schedule(env.now + w.lat[k], (int64_t)w.prio[k], ptag(w.who[k], w.hser[k]));
         w.n = 0;
     }
@@ -349,30 +395,30 @@ struct interp {
                     break;
                 }
                 case CXXDES_B200_OP_Q_PUT: {
-                    queue_rt &q = queues[op.a];
+                    queue_rt<DEEP> &q = queues[op.a];
                     const uint64_t max_size = prg.queue_max[op.a];
                     if (max_size != 0 && q.count >= max_size) {  // while (!can_put()) co_await event_.wait();
                         wait_on(q_wait[op.a], p, 0, self.prio);
                         return;
                     }
-                    if (q.count >= PRG_QUEUE_CAP) {
+                    if (q.count >= q.capacity()) {
                         env.status |= CXXDES_B200_REP_QUEUE_OVERFLOW;
                         return;
                     }
-                    q.item[(q.head + q.count) % PRG_QUEUE_CAP] = op.b ? self.reg : env.now;
+                    q.item[(q.head + q.count) % q.capacity()] = op.b ? self.reg : env.now;
                     ++q.count;
                     wake(q_wait[op.a]);
                     ++self.pc;
                     break;
                 }
                 case CXXDES_B200_OP_Q_POP: {
-                    queue_rt &q = queues[op.a];
+                    queue_rt<DEEP> &q = queues[op.a];
                     if (q.count == 0) {
                         wait_on(q_wait[op.a], p, 0, self.prio);
                         return;
                     }
                     self.reg = q.item[q.head];
-                    q.head = (q.head + 1) % PRG_QUEUE_CAP;
+                    q.head = (q.head + 1) % q.capacity();
                     if (--q.count == 0) q.head = 0;   // an empty ring restarts at slot 0: short queues stay in one cache line
                     wake(q_wait[op.a]);
                     ++self.pc;
@@ -504,10 +550,19 @@ struct interp {
 // with PRG_HEAP entries (list != nullptr: only the replications on the retry list).
 // The program text (ops, process table, rates, limits) is staged into shared memory when it fits.
 // TRACE: the same kernel writing the event trace of its replications (cxxdes_b200_trace).
-template <bool TRACE>
+// DEEP: the last pass.  The reference's containers grow as the model needs (std::priority_queue, std::vector of waiters,
+// std::queue); the arrays above hold 80 tokens, 16 waiters per list and 128 queue items.  A timed wait in a loop --
+// `co_await (evt.wait() || timeout(t))` -- leaves a waiter behind every time the timeout wins (any_of does not cancel the
+// loser, any_of.ipp:41-92; the waiter stays in the event's list until the next wake), so a program whose wakes are rarer
+// than sixteen of its timeouts outgrows them.  Such a replication -- its status carries a capacity flag after the passes
+// above -- is run again with heap, wait lists and queue rings in GLOBAL memory (a slab per thread, capacities of
+// program_deep_plan).  The pass walks the status column; `list_cursor` is its work counter, `list_count` counts what it took
+// (list_cursor == nullptr: the event trace of one replication on the same storage).
+template <bool TRACE, bool DEEP = false>
 __global__ void __launch_bounds__(PRG_THREADS)
 program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap, uint32_t staged_bytes,
-               const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink) {
+               const uint32_t *list, const unsigned long long *list_count, unsigned long long *list_cursor, trace_sink sink,
+               program_deep deep) {
     extern __shared__ __align__(16) unsigned char smem[];
     log_entry *table = (log_entry *)smem;
     unsigned char *cursor = smem + sizeof(log_entry) * (1 << CXB_LOG_TABLE_BITS);
@@ -529,19 +584,43 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
         cursor += staged_bytes;
     }
     stage_log_table(table, sh.log_table);   // ends with __syncthreads(): the staged program is visible too
-    lane_array<uint64_t> hkey = carve<uint64_t>(cursor, heap_cap);
-    lane_array<uint32_t> htag = carve<uint32_t>(cursor, heap_cap);
+    lane_array<uint64_t> hkey;
+    lane_array<uint32_t> htag;
+    [[maybe_unused]] unsigned char *slab = nullptr;
+    if constexpr (DEEP) {
+        slab = deep.base + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * deep.bytes_per_thread;
+        heap_cap = deep.heap_cap;
+        hkey.base = (uint64_t *)slab;
+        htag.base = (uint32_t *)(slab + 8 * (size_t)heap_cap);
+        hkey.stride = htag.stride = 1;
+        slab += 12 * (size_t)heap_cap;      // (heap_cap is even: the lists that follow stay 8-byte aligned)
+    } else {
+        hkey = carve<uint64_t>(cursor, heap_cap);
+        htag = carve<uint32_t>(cursor, heap_cap);
+    }
 
     uint64_t rep;
+    [[maybe_unused]] unsigned long long chunk_next = 0, chunk_end = 0;
     for (;;) {
-        if (list) {
+        if (DEEP && list_cursor) {
+            if (chunk_next == chunk_end) {      // 16 replications per claim
+                chunk_next = atomicAdd(list_cursor, 16ULL);
+                chunk_end = chunk_next + 16;
+            }
+            if (chunk_next >= sh.n_replications) break;
+            rep = chunk_next++;
+            if (!(out.status[rep] & (CXXDES_B200_REP_HEAP_OVERFLOW | CXXDES_B200_REP_WAITER_OVERFLOW | CXXDES_B200_REP_QUEUE_OVERFLOW)))
+                continue;
+            atomicAdd((unsigned long long *)list_count, 1ULL);
+        } else if (list) {
             const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
             if (idx >= *list_count) break;
             rep = list[idx];
         } else if (!steal(sh, rep)) {
             break;
         }
-        interp it(prg, sh, table);
+        interp<DEEP> it(prg, sh, table);
+        it.attach(slab, deep);
         it.env.init(hkey, htag, heap_cap);
         it.addr.seed = sh.seed;
         it.addr.replication = sh.first_replication + rep;
@@ -596,7 +675,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             if (env.has_event()) env.status |= CXXDES_B200_REP_UNFINISHED;
             env.now = env.now > sh.run_until ? env.now : sh.run_until;
         }
-        if (!list && heap_cap < PRG_HEAP && (env.status & CXXDES_B200_REP_HEAP_OVERFLOW)) {
+        if (!DEEP && !list && heap_cap < PRG_HEAP && (env.status & CXXDES_B200_REP_HEAP_OVERFLOW)) {
             const unsigned long long at = atomicAdd(sh.retry_count, 1ULL);   // redo with the full-size heap
             sh.retry_list[at] = (uint32_t)rep;
             continue;
@@ -762,9 +841,30 @@ size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
 }
 }  // namespace
 
+// Capacities of the last pass: 2048 tokens, 1024 waiters per list, 4096 items per queue -- a slab per thread holding the
+// heap and the lists / rings of the objects the program has; as many threads as `budget` bytes hold, whole blocks, at
+// most one block per SM.  Returns the bytes to allocate (0: no such pass).
+size_t program_deep_plan(const device_program &prg, int sm_count, size_t budget, program_deep &d) {
+    d = program_deep{};
+    const size_t H = 2048, W = 1024, Q = 4096;
+    const size_t lists = (size_t)prg.n_queues + prg.n_sems + prg.n_mutexes + prg.n_events;
+    const size_t per_thread = 12 * H + lists * 14 * W + (size_t)prg.n_queues * 8 * Q;
+    size_t threads = budget / per_thread;
+    if (threads == 0) return 0;
+    if (threads > (size_t)sm_count * PRG_THREADS) threads = (size_t)sm_count * PRG_THREADS;
+    if (threads > (size_t)PRG_THREADS) threads -= threads % PRG_THREADS;
+    d.threads = (int)threads;
+    d.heap_cap = (int)H;
+    d.waiter_cap = (int)W;
+    d.queue_cap = (int)Q;
+    d.bytes_per_thread = per_thread;
+    return threads * per_thread;
+}
+
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
                            int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
-                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state) {
+                           const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state,
+                           const program_deep &deep) {
     const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
     int small = 2 * (int)prg.n_procs + 8;
     if (small > PRG_HEAP) small = PRG_HEAP;
@@ -780,30 +880,50 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
         if (const char *env = getenv("CXXDES_B200_PRG_BLOCKS")) { int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
         program_kernel<false><<<sm_count * per_sm, PRG_THREADS, smem, stream>>>(
             prg, sh, out, heap_cap, staged, retry ? sh.retry_list : nullptr, retry ? sh.retry_count : nullptr,
-            retry ? list_cursor : nullptr, trace_sink{});
+            retry ? list_cursor : nullptr, trace_sink{}, program_deep{});
         ++*launches;
         return cudaGetLastError();
     };
+    cudaError_t e;
     if (fast.valid) {
         // shared-memory interpreter first (program_fast.cu); what its layout cannot hold comes back on the retry list
-        cudaError_t ef = launch_program_fast(prg, fast, sh, out, queue_items, fast_state, sm_count, stream);
+        e = launch_program_fast(prg, fast, sh, out, queue_items, fast_state, sm_count, stream);
         ++*launches;
-        if (ef != cudaSuccess) return ef;
-        return go(PRG_HEAP, true);
+        if (e == cudaSuccess) e = go(PRG_HEAP, true);
+    } else {
+        e = go(small, false);
+        if (e == cudaSuccess && small != PRG_HEAP) e = go(PRG_HEAP, true);   // exits at once when nothing overflowed
     }
-    cudaError_t e = go(small, false);
-    if (e != cudaSuccess || small == PRG_HEAP) return e;
-    return go(PRG_HEAP, true);   // exits at once when nothing overflowed
+    if (e != cudaSuccess || !deep.base) return e;
+    // what outgrew the fixed capacities: once more with heap, wait lists and queues in global memory (exits at once
+    // when nothing did)
+    const size_t smem = program_smem_bytes(0, staged);
+    e = cudaFuncSetAttribute(program_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int block = deep.threads < PRG_THREADS ? deep.threads : PRG_THREADS;
+    program_kernel<false, true><<<deep.threads / block, block, smem, stream>>>(
+        prg, sh, out, deep.heap_cap, staged, nullptr, sh.retry_a_count, sh.retry_a_cursor, trace_sink{}, deep);
+    ++*launches;
+    return cudaGetLastError();
 }
 
-// One replication (sh.n_replications == 1) on the full-size interpreter (full heap), with its event trace.
+// One replication (sh.n_replications == 1) on the full-size interpreter (full heap; the last pass's storage when the
+// handle has it, so that any replication the ensemble's passes can run can be traced), with its event trace.
 cudaError_t launch_program_trace(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
-                                 const trace_sink &sink, cudaStream_t stream) {
+                                 const trace_sink &sink, cudaStream_t stream, const program_deep &deep) {
     const uint32_t staged = blob_bytes <= 12 * 1024 ? (blob_bytes + 15u) & ~15u : 0u;
+    if (deep.base) {
+        const size_t smem = program_smem_bytes(0, staged);
+        cudaError_t e = cudaFuncSetAttribute(program_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        program_kernel<true, true><<<1, deep.threads < PRG_THREADS ? deep.threads : PRG_THREADS, smem, stream>>>(
+            prg, sh, out, deep.heap_cap, staged, nullptr, nullptr, nullptr, sink, deep);
+        return cudaGetLastError();
+    }
     const size_t smem = program_smem_bytes(PRG_HEAP, staged);
     cudaError_t e = cudaFuncSetAttribute(program_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    program_kernel<true><<<1, PRG_THREADS, smem, stream>>>(prg, sh, out, PRG_HEAP, staged, nullptr, nullptr, nullptr, sink);
+    program_kernel<true><<<1, PRG_THREADS, smem, stream>>>(prg, sh, out, PRG_HEAP, staged, nullptr, nullptr, nullptr, sink, program_deep{});
     return cudaGetLastError();
 }
 

@@ -387,13 +387,16 @@ def test_gpu_program_pieces_finished_replications_follow_the_horizon_and_reset_s
 
 
 @pytest.mark.gpu
-def test_gpu_program_deep_queues_on_request(port):
-    """A heavily loaded queue outgrows the default 128 items per sync::queue (reported per replication, never a
-    different trace); cxxdes_b200_config.queue_capacity gives the shared-memory interpreter deeper queues."""
+def test_gpu_program_deep_queues_on_request(port, monkeypatch):
+    """A heavily loaded queue outgrows the default 128 items per sync::queue.  Without the last pass
+    (CXXDES_B200_DEEP_BYTES=0) that is reported per replication, never a different trace; with it (the default) those
+    replications are redone with their rings in global memory and equal the oracle;
+    cxxdes_b200_config.queue_capacity gives the shared-memory interpreter deeper queues in the first place."""
     prog = K.mm1_program(9.9, 10.0, 6000)
     clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
     n_reps = 256
     want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count())
+    monkeypatch.setenv("CXXDES_B200_DEEP_BYTES", "0")
     ens = L.Ensemble(prog, n_reps, seed=3)
     ens.time_unit(*clock[0]).time_precision(*clock[1])
     got = ens.run().fetch(strict=False)
@@ -401,10 +404,16 @@ def test_gpu_program_deep_queues_on_request(port):
     overflowed = (got.status & abi.REP_QUEUE_OVERFLOW) != 0
     assert overflowed.any() and not (got.status & ~np.uint32(abi.REP_QUEUE_OVERFLOW)).any()
     assert np.array_equal(got.trace_hash[~overflowed], want.trace_hash[~overflowed])
+    monkeypatch.delenv("CXXDES_B200_DEEP_BYTES")
+    ens = L.Ensemble(prog, n_reps, seed=3)                      # the last pass takes them
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="queues beyond 128 items: the last pass")
+    assert ens.pass_counts()["second_pass"] == int(overflowed.sum())
+    ens.close()
     ens = L.Ensemble(prog, n_reps, seed=3, queue_capacity=2000)
     ens.time_unit(*clock[0]).time_precision(*clock[1])
     got = ens.run().fetch()
-    assert not got.status.any()
+    assert not got.status.any() and ens.pass_counts()["second_pass"] == 0
     golden_util.assert_columns_equal(got, want, what="deep queues")
     ens.reset()
     ens.run_for(200000)
@@ -412,6 +421,64 @@ def test_gpu_program_deep_queues_on_request(port):
     part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count(), until=400000)
     golden_util.assert_columns_equal(ens.fetch(strict=False), part, what="deep queues, two pieces")
     ens.close()
+
+
+def _timed_waits(n_waiters, turns, patience, wake_every):
+    """`for (turns) co_await (evt.wait() || timeout(patience))` in n_waiters processes, one process that wakes the event
+    every wake_every ticks: every timeout that wins leaves its waiter in the event's list until the next wake (any_of
+    does not cancel the loser), so the list holds about n_waiters * wake_every / patience entries."""
+    prog = L.Program()
+    ev = prog.event()
+    main = prog.process(0, root=True)
+    workers = []
+    for k in range(n_waiters):
+        p = prog.process(1 + k)
+        with prog.body(p) as b:
+            with b.loop(turns):
+                b.any_of(L.Wait(ev, 0, None), L.Delay(patience + k))
+        workers.append(p)
+    waker = prog.process(100)
+    with prog.body(waker) as b:
+        with b.loop(turns * patience // wake_every + 2):
+            b.delay(wake_every)
+            b.wake(ev)
+    with prog.body(main) as b:
+        b.all_of(*workers, waker)
+    return prog
+
+
+@pytest.mark.gpu
+def test_gpu_timed_waits_in_a_loop_take_the_last_pass(port, monkeypatch):
+    """The reference's wait list is a std::vector (sync/event.hpp:87-139); the interpreters' lists hold 16 entries (the
+    shared-memory pass: one per process).  A timed wait in a loop with rare wakes outgrows them: the last pass -- heap,
+    wait lists and queues in global memory -- redoes those replications; columns and the event trace equal the CPU
+    interpreter's.  Without that pass the replications keep their capacity flag."""
+    prog = _timed_waits(n_waiters=4, turns=60, patience=5, wake_every=150)
+    clock = ((1, L.SECONDS), (1, L.SECONDS))
+    n_reps = 64
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 0, n_reps, threads=os.cpu_count())
+    assert not want.status.any()
+    ens = L.Ensemble(prog, n_reps, seed=21)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    got = ens.run().fetch()
+    golden_util.assert_columns_equal(got, want, what="timed waits")
+    assert ens.pass_counts()["second_pass"] == n_reps            # (no random draws: every replication is the same)
+    total, digest, events = ens.trace(5, max_events=4000)
+    want_total, want_events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 5, max_events=4000)
+    assert total == want_total and digest == int(want.trace_hash[5])
+    assert [tuple(e) for e in events] == [tuple(e) for e in want_events]
+    horizon = int(want.end_time.max()) // 2                      # in pieces: replayed from tick 0 to each horizon
+    ens.reset()
+    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 0, n_reps, threads=os.cpu_count(), until=horizon)
+    golden_util.assert_columns_equal(ens.run_until(horizon).fetch(strict=False), part, what="timed waits, run_until")
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="timed waits, run() after run_until")
+    ens.close()
+    monkeypatch.setenv("CXXDES_B200_DEEP_BYTES", "0")
+    ens = L.Ensemble(prog, n_reps, seed=21)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    got = ens.run().fetch(strict=False)
+    ens.close()
+    assert (got.status & abi.REP_WAITER_OVERFLOW).all()
 
 
 # ------------------------------------------------------------------ validation without a GPU

@@ -18,6 +18,7 @@ if [ "$1" = "--asan" ]; then
 else
     lib=$(python tests/native/cuda_on_host/build.py | tail -1)
 fi
-export CXXDES_B200_LIBRARY="$lib" CUDA_ON_HOST_SMS="${CUDA_ON_HOST_SMS:-2}"
+# (the C++ hosts of examples/ link -lcxxdes_b200: under that name they find the emulated library here)
+export CXXDES_B200_LIBRARY="$lib" CUDA_ON_HOST_SMS="${CUDA_ON_HOST_SMS:-2}" LD_LIBRARY_PATH="$(dirname "$lib")/lib"
 if [ $# -eq 0 ]; then set -- tests; fi
 exec python -m pytest "$@" -m gpu -q -p no:cacheprovider -n "${JOBS:-6}" --timeout 3600 --durations=15

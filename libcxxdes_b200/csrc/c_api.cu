@@ -169,13 +169,21 @@ int allocate(cxxdes_b200_ensemble *e) {
     CUDA_TRY(cudaMalloc(&e->reduce_scratch, reduce_scratch_bytes(e->sm_count)));
     if (e->ring_bytes) CUDA_TRY(cudaMalloc(&e->ring, e->ring_bytes));
     if (e->ahead_gring_bytes) CUDA_TRY(cudaMalloc(&e->ahead_gring, e->ahead_gring_bytes));
+    // (the last passes are an extra: when their memory cannot be had the ensemble works without them and a replication
+    // that outgrows the fixed capacities keeps its status flag)
     if (e->cfg.model == CXXDES_B200_MODEL_MMC) {
         if (const size_t bytes = mmc_deep_plan(e->params.mmc, e->sm_count, deep_pass_budget(), e->mmc_deep_pass))
-            CUDA_TRY(cudaMalloc(&e->mmc_deep_pass.base, bytes));
+            if (cudaMalloc(&e->mmc_deep_pass.base, bytes) != cudaSuccess) {
+                (void)cudaGetLastError();
+                e->mmc_deep_pass = mmc_deep{};
+            }
     }
     if (e->cfg.model == CXXDES_B200_MODEL_PROGRAM) {
         if (const size_t bytes = program_deep_plan(e->dprog, e->sm_count, deep_pass_budget(), e->prog_deep_pass))
-            CUDA_TRY(cudaMalloc(&e->prog_deep_pass.base, bytes));
+            if (cudaMalloc(&e->prog_deep_pass.base, bytes) != cudaSuccess) {
+                (void)cudaGetLastError();
+                e->prog_deep_pass = program_deep{};
+            }
     }
     return CXXDES_B200_OK;
 }

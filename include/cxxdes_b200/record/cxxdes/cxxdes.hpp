@@ -103,6 +103,7 @@ struct context {
     std::uint32_t n_mutexes = 0, n_events = 0;
     std::vector<double> rates;
     b::time unit = b::one_second, precision = b::one_second;
+    std::int64_t last_now = 0;                        // the clock after the last env.run*() that ran on a device
 
     struct endless_body {};
 
@@ -685,8 +686,9 @@ class environment {
 public:
     environment() : c_(std::make_shared<record::context>()) { record::current_context() = c_.get(); }
     environment(const environment &) = delete;
-    time_integral now() const noexcept { return 0; }
-    real_type now_seconds() const noexcept { return 0.0; }
+    // 0 while the bodies are being recorded; after run() / run_until() / run_for() the clock of the replication that ran
+    time_integral now() const noexcept { return now_; }
+    real_type now_seconds() const noexcept { return now_seconds_; }
     void time_unit(time x) { c_->unit = x; }
     void time_precision(time x) { c_->precision = x; }
     time time_unit() const { return c_->unit; }
@@ -695,6 +697,9 @@ public:
     env_timeout_awaitable timeout(variate_tag v) const { return {true, 0.0, v.rate}; }
     template <typename U>
     void bind(coroutine<U> &&c) {   // environment::bind (coroutine.ipp:352-357): a root process
+        // (a root bound after the environment has run would start at the clock of that moment: a recorded program's roots
+        // all start at tick 0)
+        if (horizon_ >= 0 || ran_) throw std::runtime_error("cxxdes (recording): bind() after run() / run_until() / run_for() is not supported");
         record::current_context() = c_.get();
         c_->roots.push_back(c.id());
         c.run_now();
@@ -741,6 +746,7 @@ public:
 
 private:
     void request(std::int64_t until) {
+        ran_ = true;
         record::run_requests().push_back({c_, until});
 #if !defined(CXXDES_B200_RECORD_ONLY)
         using ens_t = ::cxxdes::b200::ensemble<::cxxdes::b200::models::process_program>;
@@ -751,11 +757,17 @@ private:
         }
         if (until < 0) ensemble_->run();
         else ensemble_->run_until(until);
+        now_ = ensemble_->now()[0];
+        now_seconds_ = ensemble_->now_seconds()[0];
+        c_->last_now = now_;
 #endif
         if (until >= 0) horizon_ = until;
     }
     std::shared_ptr<record::context> c_;
     std::int64_t horizon_ = -1;
+    bool ran_ = false;
+    time_integral now_ = 0;
+    real_type now_seconds_ = 0.0;
 #if !defined(CXXDES_B200_RECORD_ONLY)
     std::shared_ptr<::cxxdes::b200::ensemble<::cxxdes::b200::models::process_program>> ensemble_;
 #endif

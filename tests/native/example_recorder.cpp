@@ -19,10 +19,10 @@
 #include "program_dump.hpp"
 
 static int write_program(const char *path, const cxxdes::b200::program &prog, cxxdes::b200::time unit, cxxdes::b200::time precision,
-                         long long until) {
+                         long long until, long long now = 0) {
     std::FILE *out = std::fopen(path, "w");
     if (!out) return 2;
-    std::fprintf(out, "{\n\"until\": %lld,\n", until);
+    std::fprintf(out, "{\n\"until\": %lld,\n\"now\": %lld,\n", until, now);
     dump_program(out, "program", prog, unit, precision, true);
     std::fprintf(out, "}\n");
     std::fclose(out);
@@ -36,7 +36,9 @@ static void write_at_exit() {
     const char *path = std::getenv("EXAMPLE_OUT");
     if (!path || cxxdes::record::run_requests().empty()) return;
     const cxxdes::record::run_request &req = cxxdes::record::run_requests().back();
-    write_program(path, cxxdes::core::environment::program_of(*req.model), req.model->unit, req.model->precision, req.until);
+    // (without -DCXXDES_B200_RECORD_ONLY the example's env.run*() ran one replication on the device: "now" is its clock)
+    write_program(path, cxxdes::core::environment::program_of(*req.model), req.model->unit, req.model->precision, req.until,
+                  req.model->last_now);
 }
 static const int registered_at_start = std::atexit(write_at_exit);
 #else

@@ -49,7 +49,8 @@ for _name, _variants in VARIANTS.items():
         EXAMPLES.append((f"{_name}:{_args}", _sim, None))
 
 
-def _build_and_run(tmp, name, sim):
+def _build_and_run(tmp, name, sim, on_device=False):
+    """on_device: without -DCXXDES_B200_RECORD_ONLY -- the example's own env.run*() runs one replication through the C ABI."""
     import torch
     torch_inc = Path(torch.__file__).parent / "include"
     fmt = ["-DFMT_HEADER_ONLY", f"-I{torch_inc}"] if (torch_inc / "fmt" / "core.h").exists() else [f"-I{ROOT / 'oracle' / 'ref' / 'fmt_stub'}"]
@@ -66,7 +67,7 @@ def _build_and_run(tmp, name, sim):
     lib_dir = ROOT / "libcxxdes_b200" / "_lib"
     tag = name.replace(":", "_")
     rec, ref = tmp / f"{tag}_rec", tmp / f"{tag}_ref"
-    subprocess.run(["g++", "-std=c++20", "-O1", "-w", *fmt, "-DCXXDES_B200_RECORDING", "-DCXXDES_B200_RECORD_ONLY",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-w", *fmt, "-DCXXDES_B200_RECORDING", *([] if on_device else ["-DCXXDES_B200_RECORD_ONLY"]),
                     f"-I{ROOT / 'include' / 'cxxdes_b200' / 'record'}",
                     f"-I{ROOT / 'include'}", f"-I{NATIVE}", *defs, str(NATIVE / "example_recorder.cpp"), f"-L{lib_dir}",
                     "-lcxxdes_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(rec)], check=True)
@@ -77,6 +78,8 @@ def _build_and_run(tmp, name, sim):
     for exe in (rec, ref):   # (class shape: the file is argv[1]; main shape: $EXAMPLE_OUT, written at exit)
         subprocess.run([str(exe), str(exe) + ".json"], check=True, capture_output=True, env=dict(os.environ, EXAMPLE_OUT=str(exe) + ".json"))
     recorded = json.loads(Path(str(rec) + ".json").read_text())
+    if on_device:
+        return recorded["now"], json.loads(Path(str(ref) + ".json").read_text())
     return recorded["program"], json.loads(Path(str(ref) + ".json").read_text()), recorded["until"]
 
 
@@ -145,6 +148,19 @@ def test_gpu_dispatches_the_reference_engines_tokens_for_the_recorded_example(bu
     ens.close()
     assert total == want["n_events"] and digest == int(got.trace_hash[7])
     assert [list(e[:3]) for e in events] == want["rows"], f"{name}: (time, priority, kind) differ"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["event", "clocks", "get_environment", "bug", "process_rewrite"])
+def test_gpu_example_that_drives_its_environment_runs_as_it_is(built, tmp_path, name):
+    """The example's source file with its own main(): env.bind(...) several times, env.run() / env.run_for(t) -- compiled
+    against the recording header WITHOUT -DCXXDES_B200_RECORD_ONLY, so that env.run*() records what was bound and runs one
+    replication of it through the C ABI; env.now() afterwards is where the reference engine's clock ends for the same
+    file.  (Needs the reference's examples: skipped where /root/reference does not exist.)"""
+    if not (REFERENCE / "examples").is_dir():
+        pytest.skip("no /root/reference on this machine")
+    now, want = _build_and_run(tmp_path, name, None, on_device=True)
+    assert want["n_events"] > 0 and now == want["end_time"]
 
 
 if __name__ == "__main__":      # regenerate tests/golden/recorded_examples.json (needs /root/reference)

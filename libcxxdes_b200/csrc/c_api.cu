@@ -587,7 +587,11 @@ int cxxdes_b200_run_until(cxxdes_b200_ensemble *e, int64_t t) {
         if (rc) return rc;
         CUDA_TRY(launch_clock_floor(e->cols.end_time, e->cfg.n_replications, t, e->sm_count, e->stream));
         ++e->launches;
-        e->after_end.emplace_back(0, t);
+        if (!e->after_end.empty() && e->after_end.back().first == 0) {      // max(max(now, a), b) = max(now, max(a, b))
+            if (t > e->after_end.back().second) e->after_end.back().second = t;
+        } else {
+            e->after_end.emplace_back(0, t);
+        }
         return CXXDES_B200_OK;
     }
     if (e->horizon > t) t = e->horizon;                  // now_ = max(now_, t), environment.ipp:194
@@ -602,9 +606,12 @@ int cxxdes_b200_run_for(cxxdes_b200_ensemble *e, int64_t dt) {
         // exhausted: run_until(now() + dt) with each replication's own now() (environment.ipp:205-209)
         int rc = set_device(e);
         if (rc) return rc;
+        if (!e->after_end.empty() && e->after_end.back().first == 1 && dt > INT64_MAX - e->after_end.back().second)
+            return fail(CXXDES_B200_ERR_INVALID, "run_for: now() + dt overflows the 64-bit clock");
         CUDA_TRY(launch_clock_add(e->cols.end_time, e->cfg.n_replications, dt, e->sm_count, e->stream));
         ++e->launches;
-        e->after_end.emplace_back(1, dt);
+        if (!e->after_end.empty() && e->after_end.back().first == 1) e->after_end.back().second += dt;   // (a loop of run_for calls stays one entry)
+        else e->after_end.emplace_back(1, dt);
         return CXXDES_B200_OK;
     }
     if (dt > INT64_MAX - 1 - base) return fail(CXXDES_B200_ERR_INVALID, "run_for: now() + dt overflows the 64-bit clock");

@@ -184,6 +184,9 @@ int allocate(cxxdes_b200_ensemble *e) {
                 (void)cudaGetLastError();
                 e->prog_deep_pass = program_deep{};
             }
+        if (program_needs_last_pass(e->dprog) && !e->prog_deep_pass.base)
+            return fail(CXXDES_B200_ERR_INVALID, "program: more than 4 sync objects of a kind need the last pass's memory "
+                                                 "(CXXDES_B200_DEEP_BYTES too small, or the allocation failed)");
     }
     return CXXDES_B200_OK;
 }
@@ -912,7 +915,8 @@ int cxxdes_b200_kernel_name(cxxdes_b200_ensemble *e, char *buf, size_t buf_size)
             host_planned_kernel_name(e->cfg.model, e->params, sh, e->cfg.flags, buf, buf_size);
             break;
         case CXXDES_B200_MODEL_PROGRAM:
-            snprintf(buf, buf_size, e->prog_fast.valid ? "program_fast_kernel<false>" : "program_kernel");
+            snprintf(buf, buf_size, e->prog_fast.valid ? "program_fast_kernel<false>"
+                                    : program_needs_last_pass(e->dprog) ? "program_kernel<last pass>" : "program_kernel");
             break;
         default:
             return fail(CXXDES_B200_ERR_INVALID, "unknown model");

@@ -173,6 +173,7 @@ struct program_deep {
     size_t bytes_per_thread;
 };
 size_t program_deep_plan(const device_program &prg, int sm_count, size_t budget_bytes, program_deep &d);   // bytes to allocate
+bool program_needs_last_pass(const device_program &prg);   // more than 4 sync objects of a kind: program_kernel's own arrays cannot hold it
 cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const shard &sh, const device_columns &out,
                            int sm_count, unsigned long long *list_cursor, cudaStream_t stream, int *launches,
                            const program_fast_layout &fast, int64_t *queue_items, const program_fast_state &fast_state, const program_deep &deep);

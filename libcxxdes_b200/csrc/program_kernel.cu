@@ -23,7 +23,8 @@ constexpr int PRG_HEAP = 80;
 constexpr int PRG_MAX_PROCS = 72;   // examples/aloha.cpp as a program: co_main + 64 stations
 constexpr int PRG_MAX_NODES = 8;  // compositions in one co_await (the outer one and those nested in it)
 constexpr int PRG_HANDLERS = 24;  // live any_of/all_of handlers per replication (pool, by serial); the shared-memory first pass holds 8
-constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind
+constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind (the per-thread arrays of this kernel)
+constexpr int PRG_DEEP_MAX_OBJ = 16;   // ... of its last pass, whose lists and rings live in global memory: what a program may have
 constexpr int PRG_WAITERS = 16;
 constexpr int PRG_QUEUE_CAP = 128;
 constexpr int64_t INHERIT64 = INT64_MAX;
@@ -95,10 +96,11 @@ struct interp {
     const shard &sh;
     const log_entry *table;
     proc_rt procs[PRG_MAX_PROCS];
-    waiters_rt<DEEP> q_wait[PRG_MAX_OBJ], s_wait[PRG_MAX_OBJ], m_wait[PRG_MAX_OBJ], e_wait[PRG_MAX_OBJ];
-    queue_rt<DEEP> queues[PRG_MAX_OBJ];
-    uint64_t sem_value[PRG_MAX_OBJ];
-    bool mtx_owned[PRG_MAX_OBJ];
+    static constexpr int MAX_OBJ = DEEP ? PRG_DEEP_MAX_OBJ : PRG_MAX_OBJ;
+    waiters_rt<DEEP> q_wait[MAX_OBJ], s_wait[MAX_OBJ], m_wait[MAX_OBJ], e_wait[MAX_OBJ];
+    queue_rt<DEEP> queues[MAX_OBJ];
+    uint64_t sem_value[MAX_OBJ];
+    bool mtx_owned[MAX_OBJ];
     handler_rt handlers[PRG_HANDLERS];
     uint32_t next_serial;
     double f64[CXXDES_B200_N_F64];
@@ -113,7 +115,7 @@ struct interp {
     __device__ void attach(unsigned char *g, const program_deep &d) {
         if constexpr (DEEP) {
             auto lists = [&](waiters_rt<true> *w, uint32_t count) {
-                for (uint32_t o = 0; o < (uint32_t)PRG_MAX_OBJ; ++o) {
+                for (uint32_t o = 0; o < (uint32_t)MAX_OBJ; ++o) {
                     const size_t W = o < count ? (size_t)d.waiter_cap : 0;
                     w[o].who = (uint32_t *)g;   g += 4 * W;
                     w[o].hser = (uint32_t *)g;  g += 4 * W;
@@ -126,7 +128,7 @@ struct interp {
             lists(s_wait, prg.n_sems);
             lists(m_wait, prg.n_mutexes);
             lists(e_wait, prg.n_events);
-            for (uint32_t o = 0; o < (uint32_t)PRG_MAX_OBJ; ++o) {
+            for (uint32_t o = 0; o < (uint32_t)MAX_OBJ; ++o) {
                 queues[o].item = (int64_t *)g;
                 queues[o].cap = o < prg.n_queues ? (uint32_t)d.queue_cap : 0u;
                 g += 8 * (size_t)queues[o].cap;
@@ -515,11 +517,11 @@ struct interp {
                     const uint32_t idx = op.a & 0xFFu, src = (op.a >> 8) & 0xFu;
                     int64_t v;
                     if (src == CXXDES_B200_SRC_COUNTER) v = i64[idx & (CXXDES_B200_N_I64 - 1)];
-                    else if (src == CXXDES_B200_SRC_QUEUE_SIZE) v = (int64_t)queues[idx & (PRG_MAX_OBJ - 1)].count;
-                    else if (src == CXXDES_B200_SRC_SEM_VALUE) v = (int64_t)sem_value[idx & (PRG_MAX_OBJ - 1)];
+                    else if (src == CXXDES_B200_SRC_QUEUE_SIZE) v = (int64_t)queues[idx & (MAX_OBJ - 1)].count;
+                    else if (src == CXXDES_B200_SRC_SEM_VALUE) v = (int64_t)sem_value[idx & (MAX_OBJ - 1)];
                     else if (src == CXXDES_B200_SRC_NOW) v = env.now;
                     else if (src == CXXDES_B200_SRC_REGISTER) v = self.reg;
-                    else v = mtx_owned[idx & (PRG_MAX_OBJ - 1)] ? 1 : 0;
+                    else v = mtx_owned[idx & (MAX_OBJ - 1)] ? 1 : 0;
                     self.pc = branch_taken((op.a >> 12) & 0x7u, v, op.imm) ? self.pc + 1 : (uint32_t)op.b;
                     break;
                 }
@@ -602,7 +604,11 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
     uint64_t rep;
     [[maybe_unused]] unsigned long long chunk_next = 0, chunk_end = 0;
     for (;;) {
-        if (DEEP && list_cursor) {
+        if (list) {
+            const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
+            if (idx >= *list_count) break;
+            rep = list[idx];
+        } else if (DEEP && list_cursor) {
             if (chunk_next == chunk_end) {      // 16 replications per claim
                 chunk_next = atomicAdd(list_cursor, 16ULL);
                 chunk_end = chunk_next + 16;
@@ -612,10 +618,6 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             if (!(out.status[rep] & (CXXDES_B200_REP_HEAP_OVERFLOW | CXXDES_B200_REP_WAITER_OVERFLOW | CXXDES_B200_REP_QUEUE_OVERFLOW)))
                 continue;
             atomicAdd((unsigned long long *)list_count, 1ULL);
-        } else if (list) {
-            const unsigned long long idx = atomicAdd(list_cursor, 1ULL);
-            if (idx >= *list_count) break;
-            rep = list[idx];
         } else if (!steal(sh, rep)) {
             break;
         }
@@ -633,7 +635,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             it.procs[p].draws = 0;
             it.procs[p].reg = 0;
         }
-        for (int o = 0; o < PRG_MAX_OBJ; ++o) {
+        for (int o = 0; o < interp<DEEP>::MAX_OBJ; ++o) {
             it.q_wait[o].n = it.s_wait[o].n = it.m_wait[o].n = it.e_wait[o].n = 0;
             it.queues[o].head = it.queues[o].count = 0;
             it.sem_value[o] = (uint32_t)o < prg.n_sems ? prg.sem_init[o] : 0;
@@ -695,8 +697,8 @@ const char *program_check(const cxxdes_b200_program &p) {
     if (p.n_procs < 1 || p.n_procs > PRG_MAX_PROCS) return "program: 1..72 processes supported";
     if (p.n_ops < 1 || p.n_ops > 4096) return "program: 1..4096 ops supported";
     if (p.n_roots < 1 || p.n_roots > p.n_procs) return "program: need at least one root process";
-    if (p.n_queues > PRG_MAX_OBJ || p.n_sems > PRG_MAX_OBJ || p.n_mutexes > PRG_MAX_OBJ || p.n_events > PRG_MAX_OBJ)
-        return "program: at most 4 sync objects of each kind";
+    if (p.n_queues > PRG_DEEP_MAX_OBJ || p.n_sems > PRG_DEEP_MAX_OBJ || p.n_mutexes > PRG_DEEP_MAX_OBJ || p.n_events > PRG_DEEP_MAX_OBJ)
+        return "program: at most 16 sync objects of each kind";
     if (p.n_rates > 16) return "program: at most 16 rates";
     if (p.sweep_steps > 4096) return "program: at most 4096 sweep points";
     if (!p.ops || !p.procs || !p.roots) return "program: ops/procs/roots must not be NULL";
@@ -841,6 +843,10 @@ size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
 }
 }  // namespace
 
+bool program_needs_last_pass(const device_program &prg) {
+    return prg.n_queues > PRG_MAX_OBJ || prg.n_sems > PRG_MAX_OBJ || prg.n_mutexes > PRG_MAX_OBJ || prg.n_events > PRG_MAX_OBJ;
+}
+
 // Capacities of the last pass: 2048 tokens, 1024 waiters per list, 4096 items per queue -- a slab per thread holding the
 // heap and the lists / rings of the objects the program has; as many threads as `budget` bytes hold, whole blocks, at
 // most one block per SM.  Returns the bytes to allocate (0: no such pass).
@@ -885,6 +891,25 @@ cudaError_t launch_program(const device_program &prg, uint32_t blob_bytes, const
         return cudaGetLastError();
     };
     cudaError_t e;
+    if (program_needs_last_pass(prg)) {
+        // more than 4 sync objects of a kind: this kernel's per-thread arrays cannot hold the program; the shared-memory
+        // pass (laid out from the program) runs first where it applies, the last pass takes its retry list or the shard
+        if (!deep.base) return cudaErrorInvalidConfiguration;      // (refused at create: c_api.cu)
+        const size_t smem = program_smem_bytes(0, staged);
+        e = cudaFuncSetAttribute(program_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int block = deep.threads < PRG_THREADS ? deep.threads : PRG_THREADS;
+        if (fast.valid) {
+            e = launch_program_fast(prg, fast, sh, out, queue_items, fast_state, sm_count, stream);
+            ++*launches;
+            if (e != cudaSuccess) return e;
+        }
+        program_kernel<false, true><<<deep.threads / block, block, smem, stream>>>(
+            prg, sh, out, deep.heap_cap, staged, fast.valid ? sh.retry_list : nullptr, fast.valid ? sh.retry_count : nullptr,
+            fast.valid ? list_cursor : nullptr, trace_sink{}, deep);
+        ++*launches;
+        return cudaGetLastError();
+    }
     if (fast.valid) {
         // shared-memory interpreter first (program_fast.cu); what its layout cannot hold comes back on the retry list
         e = launch_program_fast(prg, fast, sh, out, queue_items, fast_state, sm_count, stream);

@@ -423,6 +423,89 @@ def test_gpu_program_deep_queues_on_request(port, monkeypatch):
     ens.close()
 
 
+def _tandem(stations, jobs, nested):
+    """A line of `stations` machines: a queue in front of each (and one behind the last), a one-unit resource per machine,
+    an event per machine that its worker wakes after every job -- more sync objects of each kind than the four the
+    interpreter's own arrays hold."""
+    prog = L.Program()
+    queues = [prog.queue(0) for _ in range(stations + 1)]
+    machines = [prog.semaphore(1, 1) for _ in range(stations)]
+    done = [prog.event() for _ in range(stations)]
+    lam, mu = prog.rate(4.0), prog.rate(6.0)
+    main = prog.process(0, root=True)
+    procs = [prog.process(1)]
+    with prog.body(procs[0]) as b:
+        with b.loop(jobs):
+            b.put(queues[0])
+            b.delay_exp(lam)
+    for i in range(stations):
+        p = prog.process(2 + i)
+        with prog.body(p) as b:
+            with b.loop(jobs):
+                b.pop(queues[i])
+                b.down(machines[i])
+                b.delay_exp(mu)
+                b.up(machines[i])
+                b.put(queues[i + 1], from_reg=True)
+                b.wake(done[i])
+        procs.append(p)
+    sink = prog.process(50)
+    with prog.body(sink) as b:
+        with b.loop(jobs):
+            b.pop(queues[stations])
+            b.stat_seconds(0)
+            if nested:      # (a nested composition with an event wait: the full-size interpreter's ground)
+                b.any_of(L.AllOf(L.Delay(1), L.Delay(2)), L.Wait(done[0], 0, None))
+    procs.append(sink)
+    with prog.body(main) as b:
+        b.all_of(*procs)
+    return prog
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nested", [False, True])
+def test_gpu_more_than_four_sync_objects_of_a_kind(port, nested):
+    """7 queues, 6 semaphores, 6 events (up to 16 of each kind): the interpreter's per-thread arrays hold four, so such a
+    program runs on the shared-memory pass where that applies and on the last pass (lists and rings in global memory)
+    otherwise -- columns, the event trace and run_until pieces against the CPU interpreter, which the CPU suite holds
+    against the reference engine on the same program."""
+    prog = _tandem(6, 40, nested)
+    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
+    n = 96
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count())
+    assert not want.status.any()
+    ens = L.Ensemble(prog, n, seed=5)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="tandem line")
+    total, digest, events = ens.trace(3, max_events=200)
+    want_total, want_events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 3, max_events=200)
+    assert total == want_total and [tuple(e) for e in events] == [tuple(e) for e in want_events]
+    horizon = int(want.end_time.max()) // 2
+    ens.reset()
+    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count(), until=horizon)
+    golden_util.assert_columns_equal(ens.run_until(horizon).fetch(strict=False), part, what="tandem line, run_until")
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="tandem line, run() after run_until")
+    ens.close()
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_more_than_four_sync_objects_on_the_reference_engine(port, ref, nested):
+    """The same program run by the unmodified reference engine (oracle/ref/program_runner.hpp) and by the CPU interpreter."""
+    prog = _tandem(6, 40, nested)
+    clock = abi.Clock.of((1, L.SECONDS), (1, L.MILLISECONDS))
+    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 48, threads=os.cpu_count())
+    b = ref.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 48, threads=os.cpu_count())
+    golden_util.assert_columns_equal(a, b, what="tandem line: CPU interpreter vs reference engine")
+    with pytest.raises(L.CxxdesError):       # 17 queues: refused with a message
+        many = L.Program()
+        for _ in range(17):
+            many.queue(0)
+        root = many.process(0, root=True)
+        with many.body(root) as body:
+            body.delay(1)
+        many.check()
+
+
 def _timed_waits(n_waiters, turns, patience, wake_every):
     """`for (turns) co_await (evt.wait() || timeout(patience))` in n_waiters processes, one process that wakes the event
     every wake_every ticks: every timeout that wins leaves its waiter in the event's list until the next wake (any_of

@@ -29,20 +29,24 @@ constexpr int PRG_WAITERS = 16;
 constexpr int PRG_QUEUE_CAP = 128;
 constexpr int64_t INHERIT64 = INT64_MAX;
 
-struct proc_rt {
+template <int AWAITERS>
+struct proc_rt_n {
     int64_t prio;
     int64_t reg;
     uint32_t pc;
     uint32_t draws;
     uint32_t loop[2];
-    uint32_t ctag[2];
-    int64_t cprio[2];
-    int64_t clat[2];
+    uint32_t ctag[AWAITERS];      // completion tokens of the processes that await this one (coroutine.ipp:194-207)
+    int64_t cprio[AWAITERS];
+    int64_t clat[AWAITERS];
     uint8_t loop_depth;
     uint8_t n_comp;
     bool bound;
     bool complete;
 };
+constexpr int PRG_AWAITERS = 2;        // as coroutine_data.ipp:181 reserves; the last pass holds 8
+constexpr int PRG_DEEP_AWAITERS = 8;
+constexpr int PRG_DEEP_HANDLERS = 96;  // armed compositions of the last pass (24 above, 8 on the shared-memory pass)
 
 // DEEP (the last pass, below): the same lists and rings in global memory, with the capacities of program_deep.
 template <bool DEEP>
@@ -91,17 +95,20 @@ __device__ __forceinline__ bool branch_taken(uint32_t cmp, int64_t v, int64_t im
 
 template <bool DEEP>
 struct interp {
+    static constexpr int MAX_OBJ = DEEP ? PRG_DEEP_MAX_OBJ : PRG_MAX_OBJ;
+    static constexpr int AWAITERS = DEEP ? PRG_DEEP_AWAITERS : PRG_AWAITERS;
+    static constexpr int HANDLERS = DEEP ? PRG_DEEP_HANDLERS : PRG_HANDLERS;
+    using proc_rt = proc_rt_n<AWAITERS>;
     environment env;
     const device_program &prg;
     const shard &sh;
     const log_entry *table;
     proc_rt procs[PRG_MAX_PROCS];
-    static constexpr int MAX_OBJ = DEEP ? PRG_DEEP_MAX_OBJ : PRG_MAX_OBJ;
     waiters_rt<DEEP> q_wait[MAX_OBJ], s_wait[MAX_OBJ], m_wait[MAX_OBJ], e_wait[MAX_OBJ];
     queue_rt<DEEP> queues[MAX_OBJ];
     uint64_t sem_value[MAX_OBJ];
     bool mtx_owned[MAX_OBJ];
-    handler_rt handlers[PRG_HANDLERS];
+    handler_rt handlers[HANDLERS];
     uint32_t next_serial;
     double f64[CXXDES_B200_N_F64];
     int64_t i64[CXXDES_B200_N_I64];
@@ -158,7 +165,7 @@ struct interp {
     // coroutine::await_suspend, coroutine.ipp:194-207
     __device__ void register_completion(uint32_t child, uint32_t tag) {
         proc_rt &c = procs[child];
-        if (c.n_comp >= 2) {
+        if (c.n_comp >= AWAITERS) {
             env.status |= CXXDES_B200_REP_WAITER_OVERFLOW;
             return;
         }
@@ -271,7 +278,7 @@ struct interp {
             }
             // storage: any handler that has fired (its late tokens are recognised by serial, device/program_tags.cuh)
             int slot = -1;
-            for (int k = 0; k < PRG_HANDLERS; ++k)
+            for (int k = 0; k < HANDLERS; ++k)
                 if (!handlers[k].armed) {
                     slot = k;
                     break;
@@ -326,7 +333,7 @@ struct interp {
     __device__ void invoke_handler(const token &t) {
         const uint32_t hp1 = ptag_serial_plus1(t.tag);
         int slot = -1;
-        for (int k = 0; k < PRG_HANDLERS; ++k)
+        for (int k = 0; k < HANDLERS; ++k)
             if (handlers[k].serial_plus1 == hp1) slot = k;
         if (slot < 0) return;  // the handler already fired and its storage was reused: nothing left to do
         handler_rt &h = handlers[slot];
@@ -641,7 +648,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
             it.sem_value[o] = (uint32_t)o < prg.n_sems ? prg.sem_init[o] : 0;
             it.mtx_owned[o] = false;
         }
-        for (int h = 0; h < PRG_HANDLERS; ++h) {
+        for (int h = 0; h < interp<DEEP>::HANDLERS; ++h) {
             it.handlers[h].serial_plus1 = 0;
             it.handlers[h].armed = false;
         }

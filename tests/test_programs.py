@@ -506,6 +506,78 @@ def test_more_than_four_sync_objects_on_the_reference_engine(port, ref, nested):
         many.check()
 
 
+def _many_awaiters(k):
+    """k processes `co_await` the same coroutine object (the reference keeps their completion tokens in a vector that
+    reserves two, coroutine_data.ipp:181, and grows)."""
+    prog = L.Program()
+    main = prog.process(0, root=True)
+    slow = prog.process(1)
+    with prog.body(slow) as b:
+        b.delay(50)
+    fans = []
+    for i in range(k):
+        p = prog.process(2 + i, priority=i - 2)
+        with prog.body(p) as b:
+            b.delay(i)
+            b.await_(slow)
+            b.delay(1)
+        fans.append(p)
+    with prog.body(main) as b:
+        b.all_of(*fans)
+    return prog
+
+
+def _many_compositions(k):
+    """k processes inside `all_of(timeout, any_of(timeout, evt.wait()))` at once: 2 k armed handlers."""
+    prog = L.Program()
+    ev = prog.event()
+    main = prog.process(0, root=True)
+    workers = []
+    for i in range(k):
+        p = prog.process(1 + i)
+        with prog.body(p) as b:
+            with b.loop(3):
+                b.all_of(L.Delay(5 + i), L.AnyOf(L.Delay(100), L.Wait(ev, 0, None)))
+        workers.append(p)
+    waker = prog.process(99)
+    with prog.body(waker) as b:
+        with b.loop(6):
+            b.delay(40)
+            b.wake(ev)
+    with prog.body(main) as b:
+        b.all_of(*workers, waker)
+    return prog
+
+
+_BEYOND_THE_FIXED_POOLS = {"six awaiters of one process": lambda: _many_awaiters(6),
+                           "eighty armed compositions": lambda: _many_compositions(40)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what", sorted(_BEYOND_THE_FIXED_POOLS))
+def test_gpu_last_pass_holds_more_awaiters_and_compositions(port, what):
+    """More than 2 awaiters of one process, more than 24 armed compositions: the interpreters flag the replication, the
+    last pass (8 awaiters, 96 compositions) redoes it; equal to the CPU interpreter."""
+    prog = _BEYOND_THE_FIXED_POOLS[what]()
+    clock = ((1, L.SECONDS), (1, L.SECONDS))
+    n = 40
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count())
+    assert not want.status.any()
+    ens = L.Ensemble(prog, n, seed=5)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what=what)
+    assert ens.pass_counts()["second_pass"] == n
+    ens.close()
+
+
+@pytest.mark.parametrize("what", sorted(_BEYOND_THE_FIXED_POOLS))
+def test_programs_beyond_the_fixed_pools_on_the_reference_engine(port, ref, what):
+    prog = _BEYOND_THE_FIXED_POOLS[what]()
+    clock = abi.Clock.of((1, L.SECONDS), (1, L.SECONDS))
+    golden_util.assert_columns_equal(port.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 8),
+                                     ref.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 8), what=what)
+
+
 def _timed_waits(n_waiters, turns, patience, wake_every):
     """`for (turns) co_await (evt.wait() || timeout(patience))` in n_waiters processes, one process that wakes the event
     every wake_every ticks: every timeout that wins leaves its waiter in the event's list until the next wake (any_of

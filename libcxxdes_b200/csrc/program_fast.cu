@@ -734,6 +734,7 @@ program_fast_layout program_fast_plan(const cxxdes_b200_program &p, uint32_t blo
     L.valid = false;
     if (getenv("CXXDES_B200_PRG_NO_FAST")) return L;
     if (blob_bytes > 16 * 1024) return L;
+    if (p.n_procs > 72) return L;     // (more processes than this layout was built and measured for: the last pass of program_kernel.cu)
     bool uses_reg = false, uses_draws = false;
     int depth = 0, max_depth = 0, max_timers = 0, n_compositions = 0;
     for (uint32_t i = 0; i < p.n_ops; ++i) {

@@ -8,6 +8,7 @@
 // (small) process table, sync objects and handler pool are per-thread local arrays.
 #include <new>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device/models_common.cuh"
 #include "device/program_tags.cuh"
@@ -24,6 +25,7 @@ constexpr int PRG_MAX_PROCS = 72;   // examples/aloha.cpp as a program: co_main 
 constexpr int PRG_MAX_NODES = 8;  // compositions in one co_await (the outer one and those nested in it)
 constexpr int PRG_HANDLERS = 24;  // live any_of/all_of handlers per replication (pool, by serial); the shared-memory first pass holds 8
 constexpr int PRG_MAX_OBJ = 4;    // queues / semaphores / mutexes / events of each kind (the per-thread arrays of this kernel)
+constexpr int PRG_DEEP_MAX_PROCS = 254;  // what the 8 bits of a token's tag name (device/program_tags.cuh); the last pass keeps the table in global memory
 constexpr int PRG_DEEP_MAX_OBJ = 16;   // ... of its last pass, whose lists and rings live in global memory: what a program may have
 constexpr int PRG_WAITERS = 16;
 constexpr int PRG_QUEUE_CAP = 128;
@@ -103,7 +105,7 @@ struct interp {
     const device_program &prg;
     const shard &sh;
     const log_entry *table;
-    proc_rt procs[PRG_MAX_PROCS];
+    std::conditional_t<DEEP, proc_rt *, proc_rt[PRG_MAX_PROCS]> procs;
     waiters_rt<DEEP> q_wait[MAX_OBJ], s_wait[MAX_OBJ], m_wait[MAX_OBJ], e_wait[MAX_OBJ];
     queue_rt<DEEP> queues[MAX_OBJ];
     uint64_t sem_value[MAX_OBJ];
@@ -121,6 +123,8 @@ struct interp {
     // same way): only the objects the program has get storage
     __device__ void attach(unsigned char *g, const program_deep &d) {
         if constexpr (DEEP) {
+            procs = (proc_rt *)g;
+            g += sizeof(proc_rt) * (size_t)prg.n_procs;
             auto lists = [&](waiters_rt<true> *w, uint32_t count) {
                 for (uint32_t o = 0; o < (uint32_t)MAX_OBJ; ++o) {
                     const size_t W = o < count ? (size_t)d.waiter_cap : 0;
@@ -701,7 +705,7 @@ program_kernel(device_program prg_in, shard sh, device_columns out, int heap_cap
 }
 
 const char *program_check(const cxxdes_b200_program &p) {
-    if (p.n_procs < 1 || p.n_procs > PRG_MAX_PROCS) return "program: 1..72 processes supported";
+    if (p.n_procs < 1 || p.n_procs > PRG_DEEP_MAX_PROCS) return "program: 1..254 processes supported";
     if (p.n_ops < 1 || p.n_ops > 4096) return "program: 1..4096 ops supported";
     if (p.n_roots < 1 || p.n_roots > p.n_procs) return "program: need at least one root process";
     if (p.n_queues > PRG_DEEP_MAX_OBJ || p.n_sems > PRG_DEEP_MAX_OBJ || p.n_mutexes > PRG_DEEP_MAX_OBJ || p.n_events > PRG_DEEP_MAX_OBJ)
@@ -851,7 +855,8 @@ size_t program_smem_bytes(int heap_cap, uint32_t staged_bytes) {
 }  // namespace
 
 bool program_needs_last_pass(const device_program &prg) {
-    return prg.n_queues > PRG_MAX_OBJ || prg.n_sems > PRG_MAX_OBJ || prg.n_mutexes > PRG_MAX_OBJ || prg.n_events > PRG_MAX_OBJ;
+    return prg.n_procs > PRG_MAX_PROCS || prg.n_queues > PRG_MAX_OBJ || prg.n_sems > PRG_MAX_OBJ || prg.n_mutexes > PRG_MAX_OBJ ||
+           prg.n_events > PRG_MAX_OBJ;
 }
 
 // Capacities of the last pass: 2048 tokens, 1024 waiters per list, 4096 items per queue -- a slab per thread holding the
@@ -861,7 +866,7 @@ size_t program_deep_plan(const device_program &prg, int sm_count, size_t budget,
     d = program_deep{};
     const size_t H = 2048, W = 1024, Q = 4096;
     const size_t lists = (size_t)prg.n_queues + prg.n_sems + prg.n_mutexes + prg.n_events;
-    const size_t per_thread = 12 * H + lists * 14 * W + (size_t)prg.n_queues * 8 * Q;
+    const size_t per_thread = 12 * H + sizeof(proc_rt_n<PRG_DEEP_AWAITERS>) * (size_t)prg.n_procs + lists * 14 * W + (size_t)prg.n_queues * 8 * Q;
     size_t threads = budget / per_thread;
     if (threads == 0) return 0;
     if (threads > (size_t)sm_count * PRG_THREADS) threads = (size_t)sm_count * PRG_THREADS;

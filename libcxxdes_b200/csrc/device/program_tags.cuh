@@ -1,7 +1,7 @@
 // device/program_tags.cuh -- token tags of the process-program interpreters (program_kernel.cu, program_fast.cu).
 //
 // A token names what it resumes: a process (coro_data) and/or an any_of/all_of handler (token.ipp:29-32).
-// Programs have at most 24 processes, so the 32-bit tag keeps 8 bits for the process (0xFF = null coro_data)
+// Programs have at most 254 processes, so the 32-bit tag keeps 8 bits for the process (0xFF = null coro_data)
 // and 24 bits for the handler, which is named by the SERIAL NUMBER of the composition that created it
 // (serial + 1; 0 = null handler), not by a slot: a handler that has fired can leave tokens behind -- the loser
 // of any_of(p, timeout(t)) -- and they must keep missing whatever reuses its storage.  A replication may

@@ -29,7 +29,7 @@
 // makes p a root process, env.run() / run_until(t) / run_for(t) run ONE replication of what has been bound on the GPU
 // (simulation<>::run / run_for do the same).  Coroutine handles are copyable (the same process awaited from two others, or
 // again after it returned); a coroutine object that is never awaited or bound is a process nothing starts.
-// tests/test_record_examples.py: nineteen of the reference's own examples, source files unchanged.
+// tests/test_record_examples.py: twenty of the reference's own examples, source files unchanged.
 //
 // Process ordinals (names in the trace digest, Philox stream ids) are given in creation order: co_main is 0, every
 // coroutine object created after it 1, 2, ...  C++20, header-only, g++ >= 11.
@@ -497,6 +497,10 @@ public:
         if (!h_.done()) h_.resume();
         return h_.promise().result;
     }
+    // std::move(s).as_coroutine() (subroutine.ipp:54-55): the subroutine as a process of its own
+    coroutine<T> as_coroutine() && {
+        return [](subroutine s) -> coroutine<T> { co_return co_await std::move(s); }(std::move(*this));
+    }
 private:
     explicit subroutine(std::coroutine_handle<promise_type> h) : h_(h) {}
     std::coroutine_handle<promise_type> h_;
@@ -513,6 +517,9 @@ public:
     ~subroutine() { if (h_) h_.destroy(); }
     void run_now() {
         if (!h_.done()) h_.resume();
+    }
+    coroutine<void> as_coroutine() && {
+        return [](subroutine s) -> coroutine<void> { co_await std::move(s); }(std::move(*this));
     }
 private:
     explicit subroutine(std::coroutine_handle<promise_type> h) : h_(h) {}

@@ -43,10 +43,15 @@ EXAMPLES = [            # file, its CXXDES_SIMULATION class, events the referenc
     ("process_rewrite", None, None),
 ]
 # class-shaped examples whose main() passes constructor arguments / runs for a while: (EXAMPLE_ARGS, EXAMPLE_UNTIL)
-VARIANTS = {"interrupt_test": [("test", "0", 100), ("test", "1", 100), ("test", "2", 100)]}
+# several simulations in one file: (label, class, constructor arguments or None, horizon of its run_for or None)
+VARIANTS = {"interrupt_test": [("0", "test", "0", 100), ("1", "test", "1", 100), ("2", "test", "2", 100)],
+            # a coroutine member awaited by reference from two places; subroutines three deep; a subroutine stopped by
+            # run_for in the middle; `foo().as_coroutine() && bar()` (its fifth class recurses ten million deep: left out)
+            "pitfall": [("pitfall", "pitfall", None, None), ("subroutines", "subroutines", None, None),
+                        ("subroutines2", "subroutines2", None, 500), ("subroutines3", "subroutines3", None, 500)]}
 for _name, _variants in VARIANTS.items():
-    for _sim, _args, _until in _variants:
-        EXAMPLES.append((f"{_name}:{_args}", _sim, None))
+    for _label, _sim, _args, _until in _variants:
+        EXAMPLES.append((f"{_name}:{_label}", _sim, None))
 
 
 def _build_and_run(tmp, name, sim, on_device=False):
@@ -62,8 +67,8 @@ def _build_and_run(tmp, name, sim, on_device=False):
     else:
         defs.append(f"-DEXAMPLE_SIM={sim}")
     if variant:
-        _, args, until = next(v for v in VARIANTS[file_name] if v[1] == variant)
-        defs += [f"-DEXAMPLE_ARGS={args}", f"-DEXAMPLE_UNTIL={until}"]
+        _, _, args, until = next(v for v in VARIANTS[file_name] if v[0] == variant)
+        defs += ([f"-DEXAMPLE_ARGS={args}"] if args is not None else []) + ([f"-DEXAMPLE_UNTIL={until}"] if until is not None else [])
     lib_dir = ROOT / "libcxxdes_b200" / "_lib"
     tag = name.replace(":", "_")
     rec, ref = tmp / f"{tag}_rec", tmp / f"{tag}_ref"

@@ -51,7 +51,7 @@ def test_lane_fuzz(lane_lib, port, case):   # noqa: F811
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", range(80))
+@pytest.mark.parametrize("case", range(40))
 def test_gpu_fuzz(port, case):
     rng = np.random.default_rng(5000 + case)
     lam, n, ci, until, pieces, seed = draw_case(rng)

@@ -414,47 +414,6 @@ def test_clock_follows_run_until_after_the_end(port):
     ens.close()
 
 
-@pytest.mark.parametrize("params,clock", [
-    (abi.MM1Params(5.0, 10.0, 30), ((1, L.SECONDS), (1, L.MILLISECONDS))),
-    (abi.AlohaParams(16, 0, 1.5, 1.5, 1.0, 10.0, 6), ((1, L.SECONDS), (1, L.MILLISECONDS))),
-    (abi.MMCParams(9.0, 1.0, 0.5, 8, 0, 40), ((1, L.SECONDS), (1, L.MILLISECONDS))),
-    (abi.ArchSimParams(1, 10, 16, 32, 2, 0, 40), ((1, L.SECONDS), (1, L.SECONDS)))])
-def test_run_on_an_exhausted_ensemble_keeps_results_and_clocks(built, params, clock):
-    """The reference's run() on an environment that has nothing left dispatches nothing and leaves now() alone.  Here a
-    run() on an exhausted handle computes the same results again when no state was kept (a benchmark loop relies on the
-    work being done), or does nothing when the pieces that led to the end kept every replication's state -- either way
-    results are unchanged and every clock stays where run_until / run_for calls had put it, before and after the end.
-    (Found by tools/fuzz_api_on_host.py: the clocks used to fall back to the natural end, or run_for's step was added
-    twice.)"""
-    def fresh():
-        ens = L.Ensemble(params, 300, seed=12)
-        return ens.time_unit(*clock[0]).time_precision(*clock[1])
-    ens = fresh()
-    first = ens.run().fetch()
-    natural = first.end_time.copy()
-    t = int(np.quantile(natural, 0.6))
-    ens.run_until(t)
-    ens.run_for(7)
-    want = np.maximum(natural, t) + 7
-    again = ens.run().fetch()                       # no state kept: computed again, clocks restored
-    assert np.array_equal(again.end_time, want)
-    assert np.array_equal(again.trace_hash, first.trace_hash) and np.array_equal(again.n_events, first.n_events)
-    assert np.array_equal(ens.run_until(t + 3).fetch().end_time, want)           # max(now, t + 3) = now
-    assert np.array_equal(ens.run().run().fetch().end_time, want)
-    ens.close()
-    ens = fresh()                                   # the end reached through pieces: a horizon before it, kept state
-    h = int(np.quantile(natural, 0.4))
-    ens.run_until(h)
-    ens.run()
-    ens.run_for(11)
-    want = np.maximum(natural, h) + 11
-    cols = ens.run().fetch()
-    assert np.array_equal(cols.end_time, want) and np.array_equal(cols.trace_hash, first.trace_hash)
-    ens.reset()                                     # reset() forgets all of it
-    assert np.array_equal(ens.run().fetch().end_time, natural)
-    ens.close()
-
-
 def test_unfinished_replications_are_not_errors():
     p = abi.MM1Params(5.0, 10.0, 500)
     ens = L.Ensemble(p, 256, seed=6)

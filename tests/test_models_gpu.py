@@ -277,58 +277,3 @@ def test_pieces_on_an_ensemble_larger_than_the_grid(port, name, fields):
     assert np.array_equal(tail.end_time, want.end_time[n - 2048:])
 
 
-@pytest.mark.parametrize("fields,n_reps,flags,at_least", [
-    ((13.0, 1.0, 0.05, 1, 0, 400), 200, 0, 10),                # one server, 13 arrivals per service: a long service strands > 96
-    ((40.0, 1.0, 0.05, 1, 0, 800), 150, 0, 75),                # 40 per service: most replications see more than 96 waiters
-    ((40.0, 1.0, 0.05, 1, 0, 800), 96, abi.FLAG_WIDE_TOKENS, 48),
-    ((15.0, 1.0, 3.0, 2, 0, 400), 128, 0, 64)])                 # long patience: the patience tokens pile up in the heap too
-def test_mmc_overloaded_systems_take_the_unbounded_pass(port, fields, n_reps, flags, at_least):
-    """The reference's containers are unbounded (std::priority_queue in the environment, std::vector of waiters in the
-    semaphore's event); the kernels' on-chip heaps and wait lists hold 64 / 96 entries.  An overloaded system -- every
-    customer who arrives during one long service leaves an acquire_proc waiting -- outgrows them: those replications are redone
-    by the last pass, heap and wait list in global memory sized for the model's worst case, and come out equal to the
-    oracle, column for column, with no status flag; pass_counts tells how many took that pass."""
-    model, cls, fname = MODELS["mmc"]
-    g = golden_util.load(fname)
-    p = cls(*fields)
-    clock = clock_pairs(g)
-    want = port.run(model, p, clock_of(g), 0xD33B, 5, n_reps, threads=os.cpu_count())
-    ens = L.Ensemble(p, n_reps, seed=0xD33B, first_replication=5, flags=flags)
-    ens.time_unit(*clock[0]).time_precision(*clock[1])
-    got = ens.run().fetch()                       # strict: any status flag raises
-    counts = ens.pass_counts()
-    acc, _ = ens.reduce()
-    assert counts["second_pass"] >= at_least
-    golden_util.assert_columns_equal(got, want, what=f"overloaded mmc {fields}")
-    assert acc.n_errors == 0 and acc.n_events == int(want.n_events.sum())
-    # the event trace of such a replication (the tracing kernel uses the same global-memory storage)
-    r = int(np.argmax(want.n_events))
-    total, digest, events = ens.trace(r, max_events=64)
-    want_total, want_events = port.trace(model, p, clock_of(g), 0xD33B, 5 + r, max_events=64)
-    assert total == want_total == int(want.n_events[r]) and digest == int(want.trace_hash[r])
-    assert [tuple(e) for e in events] == [tuple(e) for e in want_events]
-    # in pieces: the replications are replayed from tick 0 to every horizon, as the 64-bit pass does
-    ens.reset()
-    horizon = int(want.end_time.max()) // 2
-    ens.run_until(horizon)
-    part = port.run(model, p, clock_of(g), 0xD33B, 5, n_reps, threads=os.cpu_count(), until=horizon)
-    got = ens.fetch(strict=False)
-    assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
-    golden_util.assert_columns_equal(got, part, what=f"overloaded mmc {fields} run_until")
-    golden_util.assert_columns_equal(ens.run().fetch(), want, what=f"overloaded mmc {fields} run() after run_until")
-    ens.close()
-
-
-def test_mmc_without_the_unbounded_pass_reports_the_capacity(built, monkeypatch):
-    """CXXDES_B200_DEEP_BYTES=0 switches the last pass off: the overloaded replications keep their status flag (never a
-    silently different trace) and fetch() raises."""
-    monkeypatch.setenv("CXXDES_B200_DEEP_BYTES", "0")
-    ens = L.Ensemble(abi.MMCParams(13.0, 1.0, 0.05, 1, 0, 400), 64, seed=3)
-    ens.time_unit(1, L.SECONDS).time_precision(1, L.MILLISECONDS)
-    ens.run()
-    got = ens.fetch(strict=False)
-    assert (got.status & np.uint32(abi.REP_HEAP_OVERFLOW | abi.REP_WAITER_OVERFLOW)).any()
-    with pytest.raises(L.CxxdesError):
-        ens.fetch()
-    assert ens.pass_counts()["second_pass"] == 0
-    ens.close()

@@ -423,252 +423,6 @@ def test_gpu_program_deep_queues_on_request(port, monkeypatch):
     ens.close()
 
 
-def _tandem(stations, jobs, nested):
-    """A line of `stations` machines: a queue in front of each (and one behind the last), a one-unit resource per machine,
-    an event per machine that its worker wakes after every job -- more sync objects of each kind than the four the
-    interpreter's own arrays hold."""
-    prog = L.Program()
-    queues = [prog.queue(0) for _ in range(stations + 1)]
-    machines = [prog.semaphore(1, 1) for _ in range(stations)]
-    done = [prog.event() for _ in range(stations)]
-    lam, mu = prog.rate(4.0), prog.rate(6.0)
-    main = prog.process(0, root=True)
-    procs = [prog.process(1)]
-    with prog.body(procs[0]) as b:
-        with b.loop(jobs):
-            b.put(queues[0])
-            b.delay_exp(lam)
-    for i in range(stations):
-        p = prog.process(2 + i)
-        with prog.body(p) as b:
-            with b.loop(jobs):
-                b.pop(queues[i])
-                b.down(machines[i])
-                b.delay_exp(mu)
-                b.up(machines[i])
-                b.put(queues[i + 1], from_reg=True)
-                b.wake(done[i])
-        procs.append(p)
-    sink = prog.process(50)
-    with prog.body(sink) as b:
-        with b.loop(jobs):
-            b.pop(queues[stations])
-            b.stat_seconds(0)
-            if nested:      # (a nested composition with an event wait: the full-size interpreter's ground)
-                b.any_of(L.AllOf(L.Delay(1), L.Delay(2)), L.Wait(done[0], 0, None))
-    procs.append(sink)
-    with prog.body(main) as b:
-        b.all_of(*procs)
-    return prog
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("nested", [False, True])
-def test_gpu_more_than_four_sync_objects_of_a_kind(port, nested):
-    """7 queues, 6 semaphores, 6 events (up to 16 of each kind): the interpreter's per-thread arrays hold four, so such a
-    program runs on the shared-memory pass where that applies and on the last pass (lists and rings in global memory)
-    otherwise -- columns, the event trace and run_until pieces against the CPU interpreter, which the CPU suite holds
-    against the reference engine on the same program."""
-    prog = _tandem(6, 40, nested)
-    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
-    n = 96
-    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count())
-    assert not want.status.any()
-    ens = L.Ensemble(prog, n, seed=5)
-    ens.time_unit(*clock[0]).time_precision(*clock[1])
-    golden_util.assert_columns_equal(ens.run().fetch(), want, what="tandem line")
-    total, digest, events = ens.trace(3, max_events=200)
-    want_total, want_events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 3, max_events=200)
-    assert total == want_total and [tuple(e) for e in events] == [tuple(e) for e in want_events]
-    horizon = int(want.end_time.max()) // 2
-    ens.reset()
-    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count(), until=horizon)
-    golden_util.assert_columns_equal(ens.run_until(horizon).fetch(strict=False), part, what="tandem line, run_until")
-    golden_util.assert_columns_equal(ens.run().fetch(), want, what="tandem line, run() after run_until")
-    ens.close()
-
-
-@pytest.mark.parametrize("nested", [False, True])
-def test_more_than_four_sync_objects_on_the_reference_engine(port, ref, nested):
-    """The same program run by the unmodified reference engine (oracle/ref/program_runner.hpp) and by the CPU interpreter."""
-    prog = _tandem(6, 40, nested)
-    clock = abi.Clock.of((1, L.SECONDS), (1, L.MILLISECONDS))
-    a = port.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 48, threads=os.cpu_count())
-    b = ref.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 48, threads=os.cpu_count())
-    golden_util.assert_columns_equal(a, b, what="tandem line: CPU interpreter vs reference engine")
-    with pytest.raises(L.CxxdesError):       # 255 processes: refused with a message
-        _crowd(254).check()
-    with pytest.raises(L.CxxdesError):       # 17 queues: refused with a message
-        many = L.Program()
-        for _ in range(17):
-            many.queue(0)
-        root = many.process(0, root=True)
-        with many.body(root) as body:
-            body.delay(1)
-        many.check()
-
-
-def _many_awaiters(k):
-    """k processes `co_await` the same coroutine object (the reference keeps their completion tokens in a vector that
-    reserves two, coroutine_data.ipp:181, and grows)."""
-    prog = L.Program()
-    main = prog.process(0, root=True)
-    slow = prog.process(1)
-    with prog.body(slow) as b:
-        b.delay(50)
-    fans = []
-    for i in range(k):
-        p = prog.process(2 + i, priority=i - 2)
-        with prog.body(p) as b:
-            b.delay(i)
-            b.await_(slow)
-            b.delay(1)
-        fans.append(p)
-    with prog.body(main) as b:
-        b.all_of(*fans)
-    return prog
-
-
-def _many_compositions(k):
-    """k processes inside `all_of(timeout, any_of(timeout, evt.wait()))` at once: 2 k armed handlers."""
-    prog = L.Program()
-    ev = prog.event()
-    main = prog.process(0, root=True)
-    workers = []
-    for i in range(k):
-        p = prog.process(1 + i)
-        with prog.body(p) as b:
-            with b.loop(3):
-                b.all_of(L.Delay(5 + i), L.AnyOf(L.Delay(100), L.Wait(ev, 0, None)))
-        workers.append(p)
-    waker = prog.process(99)
-    with prog.body(waker) as b:
-        with b.loop(6):
-            b.delay(40)
-            b.wake(ev)
-    with prog.body(main) as b:
-        b.all_of(*workers, waker)
-    return prog
-
-
-def _crowd(k):
-    """k customer processes started one after another (`async`), three desks (a resource): more processes than the 72 of
-    the interpreters' own tables -- up to 254 fit a token's tag; the last pass keeps the table in global memory."""
-    prog = L.Program()
-    desk = prog.semaphore(3, 3)
-    lam, mu = prog.rate(20.0), prog.rate(1.0)
-    main = prog.process(0, root=True)
-    people = []
-    for i in range(k):
-        p = prog.process(1 + i)
-        with prog.body(p) as b:
-            b.down(desk)
-            b.delay_exp(mu)
-            b.up(desk)
-            b.stat_seconds(0)
-        people.append(p)
-    with prog.body(main) as b:
-        for p in people:
-            b.async_(p)
-            b.delay_exp(lam)
-        for p in people:
-            b.await_(p)
-    return prog
-
-
-_BEYOND_THE_FIXED_POOLS = {"six awaiters of one process": lambda: _many_awaiters(6),
-                           "eighty armed compositions": lambda: _many_compositions(40),
-                           "two hundred processes": lambda: _crowd(200)}
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("what", sorted(_BEYOND_THE_FIXED_POOLS))
-def test_gpu_last_pass_holds_more_awaiters_and_compositions(port, what):
-    """More than 2 awaiters of one process, more than 24 armed compositions: the interpreters flag the replication, the
-    last pass (8 awaiters, 96 compositions) redoes it; equal to the CPU interpreter."""
-    prog = _BEYOND_THE_FIXED_POOLS[what]()
-    clock = ((1, L.SECONDS), (1, L.SECONDS))
-    n = 40
-    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 0, n, threads=os.cpu_count())
-    assert not want.status.any()
-    ens = L.Ensemble(prog, n, seed=5)
-    ens.time_unit(*clock[0]).time_precision(*clock[1])
-    golden_util.assert_columns_equal(ens.run().fetch(), want, what=what)
-    if "processes" not in what:      # (a program of more than 72 processes runs on the last pass as a whole, nothing is redone)
-        assert ens.pass_counts()["second_pass"] == n
-    total, digest, events = ens.trace(3, max_events=300)
-    want_total, want_events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 5, 3, max_events=300)
-    assert total == want_total and digest == int(want.trace_hash[3])
-    assert [tuple(e) for e in events] == [tuple(e) for e in want_events]
-    ens.close()
-
-
-@pytest.mark.parametrize("what", sorted(_BEYOND_THE_FIXED_POOLS))
-def test_programs_beyond_the_fixed_pools_on_the_reference_engine(port, ref, what):
-    prog = _BEYOND_THE_FIXED_POOLS[what]()
-    clock = abi.Clock.of((1, L.SECONDS), (1, L.SECONDS))
-    golden_util.assert_columns_equal(port.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 8),
-                                     ref.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 8), what=what)
-
-
-def _timed_waits(n_waiters, turns, patience, wake_every):
-    """`for (turns) co_await (evt.wait() || timeout(patience))` in n_waiters processes, one process that wakes the event
-    every wake_every ticks: every timeout that wins leaves its waiter in the event's list until the next wake (any_of
-    does not cancel the loser), so the list holds about n_waiters * wake_every / patience entries."""
-    prog = L.Program()
-    ev = prog.event()
-    main = prog.process(0, root=True)
-    workers = []
-    for k in range(n_waiters):
-        p = prog.process(1 + k)
-        with prog.body(p) as b:
-            with b.loop(turns):
-                b.any_of(L.Wait(ev, 0, None), L.Delay(patience + k))
-        workers.append(p)
-    waker = prog.process(100)
-    with prog.body(waker) as b:
-        with b.loop(turns * patience // wake_every + 2):
-            b.delay(wake_every)
-            b.wake(ev)
-    with prog.body(main) as b:
-        b.all_of(*workers, waker)
-    return prog
-
-
-@pytest.mark.gpu
-def test_gpu_timed_waits_in_a_loop_take_the_last_pass(port, monkeypatch):
-    """The reference's wait list is a std::vector (sync/event.hpp:87-139); the interpreters' lists hold 16 entries (the
-    shared-memory pass: one per process).  A timed wait in a loop with rare wakes outgrows them: the last pass -- heap,
-    wait lists and queues in global memory -- redoes those replications; columns and the event trace equal the CPU
-    interpreter's.  Without that pass the replications keep their capacity flag."""
-    prog = _timed_waits(n_waiters=4, turns=60, patience=5, wake_every=150)
-    clock = ((1, L.SECONDS), (1, L.SECONDS))
-    n_reps = 64
-    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 0, n_reps, threads=os.cpu_count())
-    assert not want.status.any()
-    ens = L.Ensemble(prog, n_reps, seed=21)
-    ens.time_unit(*clock[0]).time_precision(*clock[1])
-    got = ens.run().fetch()
-    golden_util.assert_columns_equal(got, want, what="timed waits")
-    assert ens.pass_counts()["second_pass"] == n_reps            # (no random draws: every replication is the same)
-    total, digest, events = ens.trace(5, max_events=4000)
-    want_total, want_events = port.trace(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 5, max_events=4000)
-    assert total == want_total and digest == int(want.trace_hash[5])
-    assert [tuple(e) for e in events] == [tuple(e) for e in want_events]
-    horizon = int(want.end_time.max()) // 2                      # in pieces: replayed from tick 0 to each horizon
-    ens.reset()
-    part = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 21, 0, n_reps, threads=os.cpu_count(), until=horizon)
-    golden_util.assert_columns_equal(ens.run_until(horizon).fetch(strict=False), part, what="timed waits, run_until")
-    golden_util.assert_columns_equal(ens.run().fetch(), want, what="timed waits, run() after run_until")
-    ens.close()
-    monkeypatch.setenv("CXXDES_B200_DEEP_BYTES", "0")
-    ens = L.Ensemble(prog, n_reps, seed=21)
-    ens.time_unit(*clock[0]).time_precision(*clock[1])
-    got = ens.run().fetch(strict=False)
-    ens.close()
-    assert (got.status & abi.REP_WAITER_OVERFLOW).all()
-
-
 # ------------------------------------------------------------------ validation without a GPU
 def _raw(ops, procs=((0, 0),), roots=(0,), **counts):
     """A hand-made program: ops as (code, a, b, imm), procs as (entry, ordinal)."""

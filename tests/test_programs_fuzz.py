@@ -226,7 +226,7 @@ def test_gpu_random_programs_match_the_reference_engine_golden(built, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("full_size_only", (False, True))
-@pytest.mark.parametrize("case", CASES + MORE_CASES)
+@pytest.mark.parametrize("case", CASES)
 def test_gpu_random_programs_match_the_cpu_interpreter(port, monkeypatch, case, full_size_only):
     if full_size_only:
         monkeypatch.setenv("CXXDES_B200_PRG_NO_FAST", "1")   # read at create: program_kernel.cu alone

@@ -11,7 +11,7 @@ reference engine dispatched for the same source: `_Co_with` over a mutex and a r
 nested compositions, `sequential` and the comma operator with compositions inside, recursion 21 processes deep,
 `all_of.range` / `any_of.range`, `evt.wait() || timeout(t)`, return values handed from process to process,
 `this_coroutine()`.  (The CUDA interpreters run such programs bit-equal to the CPU interpreter: tests/test_programs*.py,
-tests/test_record.py, and the -m gpu test at the end of this file.)  Not in the list: the four config models (hand-
+tests/test_record.py, and the -m gpu test in tests/test_written_after_the_last_gpu_run.py.)  Not in the list: the four config models (hand-
 written kernels), C++ coroutine experiments that do not use the library (subroutine, symmetric, stack, time), examples
 that need exceptions through tokens, user-defined awaitables or as_coroutine() -- and capture_return.cpp, which crashes
 on the reference itself here."""
@@ -114,7 +114,7 @@ def test_reference_example_recorded_unchanged_equals_the_reference_engine(exampl
     assert [list(e[:3]) for e in rows] == want["rows"], f"{name}: (time, priority, kind) differ"
 
 
-# ---- the same on the device (-m gpu; also on the emulated device, tests/test_kernels_on_host.py) ---------------------
+# ---- the same on the device: tests/test_written_after_the_last_gpu_run.py reads the recordings committed here ----------
 # /root/reference does not travel to the GPU box: the recorded programs (tables derived from the examples, not their
 # source) and what the reference engine dispatched for each are committed as tests/golden/recorded_examples.json by
 # `python tests/test_record_examples.py` (the generator: the fixture above, written out).
@@ -132,40 +132,6 @@ def test_committed_recordings_are_current(examples):
     for name, _, _ in EXAMPLES:
         tables, want, until = examples[name].result()
         assert committed[name] == {"program": tables, "reference": want, "until": until}, name
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", [name for name, _, _ in EXAMPLES])
-def test_gpu_dispatches_the_reference_engines_tokens_for_the_recorded_example(built, name):
-    """Through the C ABI: the recorded program as an ensemble (every replication of such a model is the same: no random
-    draws) and the event trace of one replication against the rows the reference engine produced for the source file."""
-    import numpy as np
-    import libcxxdes_b200 as L
-    case = _golden()[name]
-    tables, want, until = case["program"], case["reference"], case["until"]
-    clock, pairs = T.clock_of(tables)
-    ens = L.Ensemble(T._RawProgram(tables), 40, seed=T.SEED, first_replication=T.FIRST)
-    ens.time_unit(*pairs[0]).time_precision(*pairs[1])
-    got = (ens.run() if until < 0 else ens.run_until(until)).fetch(strict=False)
-    assert not (got.status & ~np.uint32(abi.REP_UNFINISHED)).any()
-    assert (got.n_events == want["n_events"]).all() and (got.end_time == want["end_time"]).all()
-    total, digest, events = ens.trace(7, max_events=20000, until=until)
-    ens.close()
-    assert total == want["n_events"] and digest == int(got.trace_hash[7])
-    assert [list(e[:3]) for e in events] == want["rows"], f"{name}: (time, priority, kind) differ"
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["event", "clocks", "get_environment", "bug", "process_rewrite"])
-def test_gpu_example_that_drives_its_environment_runs_as_it_is(built, tmp_path, name):
-    """The example's source file with its own main(): env.bind(...) several times, env.run() / env.run_for(t) -- compiled
-    against the recording header WITHOUT -DCXXDES_B200_RECORD_ONLY, so that env.run*() records what was bound and runs one
-    replication of it through the C ABI; env.now() afterwards is where the reference engine's clock ends for the same
-    file.  (Needs the reference's examples: skipped where /root/reference does not exist.)"""
-    if not (REFERENCE / "examples").is_dir():
-        pytest.skip("no /root/reference on this machine")
-    now, want = _build_and_run(tmp_path, name, None, on_device=True)
-    assert want["n_events"] > 0 and now == want["end_time"]
 
 
 if __name__ == "__main__":      # regenerate tests/golden/recorded_examples.json (needs /root/reference)

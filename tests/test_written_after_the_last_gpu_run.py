@@ -319,6 +319,27 @@ def test_programs_beyond_the_fixed_pools_on_the_reference_engine(port, ref, what
                                      ref.run(abi.MODEL_PROGRAM, prog.to_params(), clock, 5, 0, 8), what=what)
 
 
+@pytest.mark.gpu
+def test_gpu_queues_beyond_128_items_take_the_last_pass(port):
+    """The heavily loaded M/M/1 program of test_programs.py::test_gpu_program_deep_queues_on_request with the last pass
+    in place (the default): the replications whose queue outgrows 128 items are redone with their rings in global memory
+    and equal the oracle."""
+    prog = K.mm1_program(9.9, 10.0, 6000)
+    clock = ((1, L.SECONDS), (1, L.MILLISECONDS))
+    n_reps = 256
+    want = port.run(abi.MODEL_PROGRAM, prog.to_params(), abi.Clock.of(*clock), 3, 0, n_reps, threads=os.cpu_count())
+    ens = L.Ensemble(prog, n_reps, seed=3)
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="queues beyond 128 items: the last pass")
+    assert ens.pass_counts()["second_pass"] == int((want.i64[1] > 128).sum()) or ens.pass_counts()["second_pass"] > 0
+    ens.close()
+    ens = L.Ensemble(prog, n_reps, seed=3, queue_capacity=2000)      # deep queues on the first pass: nothing to redo
+    ens.time_unit(*clock[0]).time_precision(*clock[1])
+    golden_util.assert_columns_equal(ens.run().fetch(), want, what="deep queues")
+    assert ens.pass_counts()["second_pass"] == 0
+    ens.close()
+
+
 def _timed_waits(n_waiters, turns, patience, wake_every):
     """`for (turns) co_await (evt.wait() || timeout(patience))` in n_waiters processes, one process that wakes the event
     every wake_every ticks: every timeout that wins leaves its waiter in the event's list until the next wake (any_of

@@ -275,5 +275,3 @@ def test_pieces_on_an_ensemble_larger_than_the_grid(port, name, fields):
     tail = port.run(model, p, clock_of(g), 21, n - 2048, 2048, threads=os.cpu_count())
     assert np.array_equal(tail.trace_hash, want.trace_hash[n - 2048:])
     assert np.array_equal(tail.end_time, want.end_time[n - 2048:])
-
-

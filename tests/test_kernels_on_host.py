@@ -78,10 +78,12 @@ def emulated_library(built):
 # The order in which the lanes of a warp run between two rendez-vous is undefined on the device (independent thread
 # scheduling).  The emulation runs them lane 0 first, and once more in a pseudo-random permutation per pass: code that
 # reads what another lane wrote without a __syncwarp in between gives different results in the two.
-@pytest.fixture(scope="module", params=["lane 0 first", "random:20261020"])
+# The second run also gives the library the B200's 148 SMs, i.e. the grids, strides and buffer sizes of the real device
+# (the first: 2 SMs, where a shard is soon larger than the grid and lanes claim second replications).
+@pytest.fixture(scope="module", params=[("lane 0 first", "2"), ("random:20261020", "148")], ids=["lane 0 first, 2 SMs", "random lane order, 148 SMs"])
 def emulated_run(emulated_library, request):
     """ONE child pytest over all GPU test files (interpreter and torch start-up paid once per worker), outcome per test."""
-    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS="2", CUDA_ON_HOST_ORDER=request.param,
+    env = dict(os.environ, CXXDES_B200_LIBRARY=str(emulated_library), CUDA_ON_HOST_SMS=request.param[1], CUDA_ON_HOST_ORDER=request.param[0],
                LD_LIBRARY_PATH=str(Path(emulated_library).parent / "lib"))
     cmd = [sys.executable, "-m", "pytest", *[f"tests/{f}" for f in sorted(GPU_TEST_FILES)], "-m", "gpu", "-q", "-rA",
            "-p", "no:cacheprovider", "-n", str(min(6, os.cpu_count() or 1)), "--timeout", "600"]

@@ -65,7 +65,7 @@ DESELECT = {
 GPU_TEST_FILES = {
     "test_mm1_gpu.py": 59, "test_mm1_fuzz.py": 40, "test_models_gpu.py": 43, "test_models_fuzz.py": 40,
     "test_narrow_tokens_gpu.py": 56, "test_programs.py": 34, "test_programs_fuzz.py": 120, "test_trace_gpu.py": 23,
-    "test_coop_heap.py": 9, "test_record.py": 8, "test_host_cpp.py": 4, "test_written_after_the_last_gpu_run.py": 286,
+    "test_coop_heap.py": 9, "test_record.py": 8, "test_host_cpp.py": 4, "test_written_after_the_last_gpu_run.py": 281,   # (+ 5 that need the reference's examples, skipped where /root/reference is absent)
 }
 
 
